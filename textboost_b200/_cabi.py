@@ -1,0 +1,89 @@
+"""ctypes binding of libtextboost_b200.so (declared in include/textboost_b200.h).
+
+The library is the product: there is NO fallback.  Loading fails loudly when the shared object is
+missing (run ``python -c 'import __graft_entry__ as g; g.build()'``), and every compute entry point
+returns TB_E_ARCH on a device that is not sm_100, which `call()` turns into a RuntimeError.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t,
+                    c_void_p)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libtextboost_b200.so")
+
+TB_ACT_NONE, TB_ACT_SILU, TB_ACT_QUICK_GELU, TB_ACT_GELU = 0, 1, 2, 3
+TB_OUT_F16, TB_OUT_F32, TB_OUT_F32_ACC = 0, 1, 2
+
+
+class Epilogue(Structure):
+    _fields_ = [
+        ("bias", c_void_p),
+        ("rowvec", c_void_p),
+        ("rows_per_group", c_int32),
+        ("residual", c_void_p),
+        ("ldr", c_int64),
+        ("alpha", c_float),
+        ("act", c_int32),
+        ("out_kind", c_int32),
+    ]
+
+
+_lib = None
+
+# name -> argtypes (restype is always int unless listed in _RESTYPES)
+_SIGNATURES = {
+    "tb_version": [],
+    "tb_last_error": [],
+    "tb_check_device": [],
+    "tb_gemm_f16": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
+                    POINTER(Epilogue), c_void_p],
+    "tb_conv3x3_f16": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                       POINTER(Epilogue), c_void_p],
+}
+_RESTYPES = {"tb_last_error": c_char_p}
+
+
+def exported_symbols():
+    """Names the header declares (used by the CPU-side ABI test)."""
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the CUDA extension is the product and has no fallback. "
+                "Build it with `python -m textboost_b200.build`.")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in _SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, c_int)
+        _lib = l
+    return _lib
+
+
+def last_error() -> str:
+    return lib().tb_last_error().decode(errors="replace")
+
+
+def call(name: str, *args):
+    rc = getattr(lib(), name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {last_error()}")
+
+
+def stream_ptr():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return c_void_p(0)
+    return c_void_p(t.data_ptr())

@@ -1,0 +1,405 @@
+// tcgen05 / TMEM / TMA GEMM with fused epilogue, and conv3x3 as an implicit GEMM on the same
+// mainloop (A operand gathered by a 4-D TMA box over the NHWC tensor, borders zero-filled by TMA).
+//
+//   C[M,N] = epilogue( A[M,K] * B[N,K]^T )      A, B fp16 K-major, accumulate fp32 in TMEM.
+//
+// CTA = 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane issues
+// tcgen05.mma), warps 2..5 = epilogue (tcgen05.ld -> registers -> fused bias/act/residual -> HBM).
+// One 128 x BN output tile per CTA; STAGES-deep smem ring guarded by full/empty mbarriers;
+// up to two CTAs co-reside on an SM so one tile's epilogue overlaps the other's mainloop.
+#include "host_util.h"
+#include "sm100.cuh"
+
+namespace tb {
+
+struct GemmParams {
+  int M, N, K;        // logical sizes (K = 9*Cin for conv)
+  int num_kb;         // number of 64-wide k blocks
+  int n_tiles;        // ceil(N / BN)
+  // conv geometry (CONV only)
+  int H, W, kb_per_tap;
+  // epilogue
+  void* C;
+  long long ldc;
+  const __half* bias;
+  const __half* rowvec;
+  int rows_per_group;
+  const __half* residual;
+  long long ldr;
+  float alpha;
+  int act;
+  int out_kind;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case TB_ACT_SILU: return x / (1.f + __expf(-x));
+    case TB_ACT_QUICK_GELU: return x / (1.f + __expf(-1.702f * x));
+    case TB_ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+    default: return x;
+  }
+}
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
+
+template <int BN>
+constexpr int tmem_cols() {
+  return BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+}
+
+template <int BN, int STAGES, bool CONV>
+__global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                      const __grid_constant__ CUtensorMap tmB,
+                                                      const GemmParams p) {
+  constexpr int B_STAGE_BYTES = BN * BK * 2;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr int TMEM_COLS = tmem_cols<BN>();
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // manual 1 KiB alignment (SWIZZLE_128B atoms)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x % p.n_tiles;
+  const int m_tile = blockIdx.x / p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(tmem_full_bar), 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int cw = 0, ch = 0, cb = 0;
+      if (CONV) {
+        const int p0 = m_tile * BM;
+        cw = p0 % p.W;
+        ch = (p0 / p.W) % p.H;
+        cb = p0 / (p.W * p.H);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        const uint32_t fb = smem_u32(&full_bar[stage]);
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        const uint32_t sb = sa + A_STAGE_BYTES;
+        mbar_expect_tx(fb, STAGE_BYTES);
+        if (CONV) {
+          const int tap = kb / p.kb_per_tap;
+          const int c0 = (kb - tap * p.kb_per_tap) * BK;
+          const int ky = tap / 3, kx = tap - ky * 3;
+          tma_load_4d(sa, &tmA, fb, c0, cw + kx - 1, ch + ky - 1, cb);
+        } else {
+          tma_load_2d(sa, &tmA, fb, kb * BK, m_tile * BM);
+        }
+        tma_load_2d(sb, &tmB, fb, kb * BK, n_tile * BN);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t ad = umma_desc_sw128(sa + k * 32, 16, 1024);
+          const uint64_t bd = umma_desc_sw128(sb + k * 32, 16, 1024);
+          umma_f16_ss(tmem_base, ad, bd, idesc, (kb | k) != 0);
+        }
+        umma_commit(smem_u32(&empty_bar[stage]));  // frees the smem slot when these MMAs retire
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(smem_u32(tmem_full_bar));
+    }
+  } else {
+    // ------------------------------------------------ epilogue (warps 2..5)
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    const long long m = (long long)m_tile * BM + row;
+    mbar_wait(smem_u32(tmem_full_bar), 0);
+    tc_fence_after();
+    const bool row_ok = m < p.M;
+    const __half* rv = nullptr;
+    if (p.rowvec && row_ok) rv = p.rowvec + (m / p.rows_per_group) * (long long)p.N;
+    const __half* res = nullptr;
+    if (p.residual && row_ok) res = p.residual + m * p.ldr;
+
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c, r);
+      tmem_ld_wait();
+      if (row_ok) {
+        const int n0 = n_tile * BN + c;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const int n = n0 + j;
+          if (n < p.N) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j + i]) * p.alpha;
+            if (p.bias) {
+              const uint4 q = *reinterpret_cast<const uint4*>(p.bias + n);
+              const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(h[i]);
+                v[2 * i] += f.x;
+                v[2 * i + 1] += f.y;
+              }
+            }
+            if (rv) {
+              const uint4 q = *reinterpret_cast<const uint4*>(rv + n);
+              const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(h[i]);
+                v[2 * i] += f.x;
+                v[2 * i + 1] += f.y;
+              }
+            }
+            if (p.act != TB_ACT_NONE) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], p.act);
+            }
+            if (res) {
+              const uint4 q = *reinterpret_cast<const uint4*>(res + n);
+              const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(h[i]);
+                v[2 * i] += f.x;
+                v[2 * i + 1] += f.y;
+              }
+            }
+            if (p.out_kind == TB_OUT_F16) {
+              uint4 o;
+              o.x = pack_half2(v[0], v[1]);
+              o.y = pack_half2(v[2], v[3]);
+              o.z = pack_half2(v[4], v[5]);
+              o.w = pack_half2(v[6], v[7]);
+              *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C) + m * p.ldc + n) = o;
+            } else {
+              float* cp = reinterpret_cast<float*>(p.C) + m * p.ldc + n;
+              float4 o0 = make_float4(v[0], v[1], v[2], v[3]);
+              float4 o1 = make_float4(v[4], v[5], v[6], v[7]);
+              if (p.out_kind == TB_OUT_F32_ACC) {
+                const float4 a0 = *reinterpret_cast<const float4*>(cp);
+                const float4 a1 = *reinterpret_cast<const float4*>(cp + 4);
+                o0.x += a0.x; o0.y += a0.y; o0.z += a0.z; o0.w += a0.w;
+                o1.x += a1.x; o1.y += a1.y; o1.z += a1.z; o1.w += a1.w;
+              }
+              *reinterpret_cast<float4*>(cp) = o0;
+              *reinterpret_cast<float4*>(cp + 4) = o1;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------ host side
+
+template <int BN, int STAGES>
+constexpr int gemm_smem_bytes() {
+  return STAGES * (A_STAGE_BYTES + BN * BK * 2) + (2 * STAGES + 2) * 8 + 1024;
+}
+
+template <int BN, int STAGES, bool CONV>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, int m_tiles,
+                       cudaStream_t st) {
+  constexpr int smem = gemm_smem_bytes<BN, STAGES>();
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, CONV>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(gemm<%d,%d>): %s", BN, STAGES, cudaGetErrorString(e));
+      return TB_E_CUDA;
+    }
+    configured = true;
+  }
+  p.n_tiles = (p.N + BN - 1) / BN;
+  dim3 grid(p.n_tiles * m_tiles);
+  gemm_tc_kernel<BN, STAGES, CONV><<<grid, 192, smem, st>>>(tmA, tmB, p);
+  return check_launch("gemm_tc_kernel");
+}
+
+// Choose the N tile: 256 when N is a multiple of 256 or large, 160 for the 320/640/960/1920 family,
+// else 128 / 64 / 32 by size.
+static int pick_bn(int N) {
+  if (N % 256 == 0) return 256;
+  if (N % 160 == 0) return 160;
+  if (N % 128 == 0) return 128;
+  if (N >= 1024) return 256;
+  if (N > 96) return 128;
+  if (N > 32) return 64;
+  return 32;
+}
+
+template <bool CONV>
+static int dispatch_gemm(const CUtensorMap& tmA, const void* Bw, long long ldb, GemmParams& p,
+                         int m_tiles, cudaStream_t st) {
+  const int bn = pick_bn(p.N);
+  CUtensorMap tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
+    uint64_t strides[1] = {(uint64_t)ldb * 2};
+    uint32_t box[2] = {(uint32_t)BK, (uint32_t)bn};
+    int rc = make_tmap_f16(&tmB, Bw, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  switch (bn) {
+    case 256: return launch_gemm<256, 4, CONV>(tmA, tmB, p, m_tiles, st);
+    case 160: return launch_gemm<160, 3, CONV>(tmA, tmB, p, m_tiles, st);
+    case 128: return launch_gemm<128, 3, CONV>(tmA, tmB, p, m_tiles, st);
+    case 64: return launch_gemm<64, 4, CONV>(tmA, tmB, p, m_tiles, st);
+    default: return launch_gemm<32, 4, CONV>(tmA, tmB, p, m_tiles, st);
+  }
+}
+
+static int fill_epilogue(GemmParams& p, void* C, long long ldc, const tb_epilogue* ep) {
+  p.C = C;
+  p.ldc = ldc;
+  p.bias = nullptr;
+  p.rowvec = nullptr;
+  p.rows_per_group = 1;
+  p.residual = nullptr;
+  p.ldr = 0;
+  p.alpha = 1.f;
+  p.act = TB_ACT_NONE;
+  p.out_kind = TB_OUT_F16;
+  if (ep) {
+    p.bias = reinterpret_cast<const __half*>(ep->bias);
+    p.rowvec = reinterpret_cast<const __half*>(ep->rowvec);
+    p.rows_per_group = ep->rows_per_group > 0 ? ep->rows_per_group : 1;
+    p.residual = reinterpret_cast<const __half*>(ep->residual);
+    p.ldr = ep->ldr;
+    p.alpha = ep->alpha;
+    p.act = ep->act;
+    p.out_kind = ep->out_kind;
+    TB_REQUIRE(p.act >= 0 && p.act <= 3, TB_E_ARG, "epilogue: unknown activation %d", p.act);
+    TB_REQUIRE(p.out_kind >= 0 && p.out_kind <= 2, TB_E_ARG, "epilogue: unknown out_kind %d",
+               p.out_kind);
+    TB_REQUIRE(!p.residual || (p.ldr % 8 == 0), TB_E_ALIGN, "epilogue: ldr %% 8 != 0");
+    TB_REQUIRE(((uintptr_t)p.bias | (uintptr_t)p.rowvec | (uintptr_t)p.residual) % 16 == 0,
+               TB_E_ALIGN, "epilogue: bias/rowvec/residual must be 16-byte aligned");
+  }
+  const int esz = p.out_kind == TB_OUT_F16 ? 2 : 4;
+  TB_REQUIRE(((uintptr_t)C % 16 == 0) && ((ldc * esz) % 16 == 0), TB_E_ALIGN,
+             "output pointer / ldc not 16-byte aligned");
+  return TB_OK;
+}
+
+}  // namespace tb
+
+using namespace tb;
+
+extern "C" int tb_gemm_f16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
+                           int64_t ldc, int M, int N, int K, const tb_epilogue* ep, void* stream) {
+  int rc = tb_check_device();
+  if (rc) return rc;
+  TB_REQUIRE(A && B && C, TB_E_ARG, "tb_gemm_f16: null pointer");
+  TB_REQUIRE(M > 0 && N > 0 && K > 0, TB_E_SHAPE, "tb_gemm_f16: M,N,K must be positive (%d,%d,%d)",
+             M, N, K);
+  TB_REQUIRE(N % 8 == 0 && K % 8 == 0, TB_E_SHAPE, "tb_gemm_f16: N and K must be multiples of 8");
+  TB_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && lda >= K && ldb >= K, TB_E_ALIGN,
+             "tb_gemm_f16: lda/ldb must be >= K and multiples of 8");
+  TB_REQUIRE(((uintptr_t)A | (uintptr_t)B) % 16 == 0, TB_E_ALIGN, "tb_gemm_f16: A/B alignment");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.num_kb = (K + BK - 1) / BK;
+  rc = fill_epilogue(p, C, ldc, ep);
+  if (rc) return rc;
+  CUtensorMap tmA;
+  uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+  uint64_t strides[1] = {(uint64_t)lda * 2};
+  uint32_t box[2] = {(uint32_t)BK, (uint32_t)BM};
+  rc = make_tmap_f16(&tmA, A, 2, dims, strides, box);
+  if (rc) return rc;
+  return dispatch_gemm<false>(tmA, B, ldb, p, (M + BM - 1) / BM, (cudaStream_t)stream);
+}
+
+extern "C" int tb_conv3x3_f16(const void* x, const void* w, void* y, int B, int H, int W, int Cin,
+                              int Cout, const tb_epilogue* ep, void* stream) {
+  int rc = tb_check_device();
+  if (rc) return rc;
+  TB_REQUIRE(x && w && y, TB_E_ARG, "tb_conv3x3_f16: null pointer");
+  TB_REQUIRE(B > 0 && H > 0 && W > 0, TB_E_SHAPE, "tb_conv3x3_f16: bad B/H/W");
+  TB_REQUIRE(Cin % 64 == 0 && Cout % 8 == 0, TB_E_SHAPE,
+             "tb_conv3x3_f16: Cin %% 64 and Cout %% 8 required (Cin=%d Cout=%d)", Cin, Cout);
+  // 128-pixel tile = box_b images x box_h rows x box_w columns, contiguous in (b,h,w) order.
+  int bw = W < 128 ? W : 128;
+  TB_REQUIRE(128 % bw == 0 && W % bw == 0, TB_E_SHAPE, "tb_conv3x3_f16: W=%d does not tile 128", W);
+  int bh = 128 / bw;
+  if (bh > H) bh = H;
+  TB_REQUIRE(bw == W || bh == 1, TB_E_SHAPE, "tb_conv3x3_f16: tiling");
+  TB_REQUIRE(H % bh == 0 && 128 % (bw * bh) == 0, TB_E_SHAPE,
+             "tb_conv3x3_f16: H=%d does not tile 128 pixels", H);
+  int bb = 128 / (bw * bh);
+  TB_REQUIRE(bb == 1 || bh == H, TB_E_SHAPE, "tb_conv3x3_f16: tiling (batch)");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = B * H * W;
+  p.N = Cout;
+  p.K = 9 * Cin;
+  p.kb_per_tap = Cin / BK;
+  p.num_kb = 9 * p.kb_per_tap;
+  p.H = H;
+  p.W = W;
+  rc = fill_epilogue(p, y, Cout, ep);
+  if (rc) return rc;
+  CUtensorMap tmA;
+  uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+  uint32_t box[4] = {(uint32_t)BK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb};
+  rc = make_tmap_f16(&tmA, x, 4, dims, strides, box);
+  if (rc) return rc;
+  return dispatch_gemm<true>(tmA, w, (long long)9 * Cin, p, (p.M + BM - 1) / BM,
+                             (cudaStream_t)stream);
+}

@@ -1,0 +1,40 @@
+// Host-side helpers shared by the C-ABI entry points: thread-local error text,
+// the driver entry point for cuTensorMapEncodeTiled, launch checking.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/textboost_b200.h"
+
+namespace tb {
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+// Tiled fp16 tensor map with 128-byte swizzle and zero OOB fill.
+// dims/strides innermost first; strides in BYTES for dims 1..rank-1 (dim 0 is contiguous).
+int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                  const uint64_t* strides_bytes, const uint32_t* box);
+
+inline int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+}  // namespace tb
+
+#define TB_REQUIRE(cond, code, ...)  \
+  do {                               \
+    if (!(cond)) {                   \
+      tb::set_error(__VA_ARGS__);    \
+      return (code);                 \
+    }                                \
+  } while (0)
