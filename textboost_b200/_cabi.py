@@ -42,6 +42,11 @@ _SIGNATURES = {
                     POINTER(Epilogue), c_void_p],
     "tb_conv3x3_f16": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                        POINTER(Epilogue), c_void_p],
+    "tb_attn_fwd_f16": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
+                        c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p],
+    "tb_attn_bwd_f16": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
+                        c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                        c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p],
 }
 _RESTYPES = {"tb_last_error": c_char_p}
 

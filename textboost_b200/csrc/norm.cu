@@ -1,0 +1,427 @@
+// HBM-bound normalisation kernels, channels-last:
+//   GroupNorm(+SiLU) forward / input-gradient  (diffusers ResnetBlock2D norm1/norm2, Transformer2D norm,
+//                                               conv_norm_out; 61 call sites per UNet forward)
+//   LayerNorm forward / input-gradient         (BasicTransformerBlock norm1-3; CLIP layer_norm1/2, final)
+// 16-byte vector accesses, fp32 statistics.  The UNet and the text encoder are frozen apart from
+// LoRA / embedding rows, so no affine-parameter gradients exist on this path.
+#include "host_util.h"
+#include "sm100.cuh"
+
+namespace tb {
+
+__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 o;
+  o.x = pack_half2(f[0], f[1]);
+  o.y = pack_half2(f[2], f[3]);
+  o.z = pack_half2(f[4], f[5]);
+  o.w = pack_half2(f[6], f[7]);
+  return o;
+}
+__device__ __forceinline__ float silu_f(float z) { return z / (1.f + __expf(-z)); }
+__device__ __forceinline__ float silu_grad(float z) {
+  const float s = 1.f / (1.f + __expf(-z));
+  return s * (1.f + z * (1.f - s));
+}
+
+// ---------------------------------------------------------------------------------- GroupNorm
+// Thread mapping shared by all four kernels: block = nvec * k threads (nvec = C/8 16-byte vectors per
+// pixel), thread owns vector column v = tid % nvec and pixels pl, pl+k, ... of the CTA's pixel chunk.
+struct GnGeom {
+  int HW, C, G, cpg, nvec, k, ppc;  // ppc = pixels per CTA
+};
+
+// MODE 0: forward statistics  (sum x, sum x^2)
+// MODE 1: backward statistics (sum dz*gamma, sum dz*gamma*xhat)
+template <int MODE>
+__global__ void gn_stats_kernel(const __half* __restrict__ x, const __half* __restrict__ dy,
+                                const __half* __restrict__ gamma, const __half* __restrict__ beta,
+                                const float* __restrict__ fstats, float* __restrict__ out, GnGeom g,
+                                float eps, int silu) {
+  extern __shared__ float sg[];  // [G][2]
+  const int b = blockIdx.y;
+  const int v = threadIdx.x % g.nvec, pl = threadIdx.x / g.nvec;
+  for (int i = threadIdx.x; i < 2 * g.G; i += blockDim.x) sg[i] = 0.f;
+  __syncthreads();
+  const int p0 = blockIdx.x * g.ppc;
+  const int p1 = min(p0 + g.ppc, g.HW);
+  float s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+  float a[8], bb[8], gm[8], mean[8], rstd[8];
+  if (MODE == 1) {
+    const float n = (float)g.HW * g.cpg;
+    float gf[8], bf[8];
+    unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), gf);
+    unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), bf);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int grp = (v * 8 + i) / g.cpg;
+      const float su = fstats[(b * g.G + grp) * 2], sq = fstats[(b * g.G + grp) * 2 + 1];
+      mean[i] = su / n;
+      rstd[i] = rsqrtf(fmaxf(sq / n - mean[i] * mean[i], 0.f) + eps);
+      gm[i] = gf[i];
+      a[i] = rstd[i] * gf[i];
+      bb[i] = bf[i] - mean[i] * a[i];
+    }
+  }
+  const size_t base = (size_t)b * g.HW * g.C + (size_t)v * 8;
+  for (int p = p0 + pl; p < p1; p += g.k) {
+    float xf[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + base + (size_t)p * g.C), xf);
+    if (MODE == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s1[i] += xf[i];
+        s2[i] += xf[i] * xf[i];
+      }
+    } else {
+      float df[8];
+      unpack8(*reinterpret_cast<const uint4*>(dy + base + (size_t)p * g.C), df);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float dz = df[i];
+        if (silu) dz *= silu_grad(xf[i] * a[i] + bb[i]);
+        const float dxh = dz * gm[i];
+        s1[i] += dxh;
+        s2[i] += dxh * (xf[i] - mean[i]) * rstd[i];
+      }
+    }
+  }
+  // fold the 8 channels into their groups (runs of equal group id), then one shared atomic per run
+  int cur = (v * 8) / g.cpg;
+  float r1 = 0.f, r2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int grp = (v * 8 + i) / g.cpg;
+    if (grp != cur) {
+      atomicAdd(&sg[cur * 2], r1);
+      atomicAdd(&sg[cur * 2 + 1], r2);
+      cur = grp;
+      r1 = r2 = 0.f;
+    }
+    r1 += s1[i];
+    r2 += s2[i];
+  }
+  atomicAdd(&sg[cur * 2], r1);
+  atomicAdd(&sg[cur * 2 + 1], r2);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * g.G; i += blockDim.x) atomicAdd(&out[(size_t)b * g.G * 2 + i], sg[i]);
+}
+
+// MODE 0: y = act(xhat*gamma + beta);  MODE 1: dx = rstd*(dz*gamma - S1/n - xhat*S2/n)
+template <int MODE>
+__global__ void gn_apply_kernel(const __half* __restrict__ x, const __half* __restrict__ dy,
+                                const __half* __restrict__ gamma, const __half* __restrict__ beta,
+                                const float* __restrict__ fstats, const float* __restrict__ bstats,
+                                __half* __restrict__ out, GnGeom g, float eps, int silu) {
+  const int b = blockIdx.y;
+  const int v = threadIdx.x % g.nvec, pl = threadIdx.x / g.nvec;
+  const int p0 = blockIdx.x * g.ppc;
+  const int p1 = min(p0 + g.ppc, g.HW);
+  const float n = (float)g.HW * g.cpg;
+  float a[8], bb[8], gm[8], mean[8], rstd[8], m1[8], m2[8];
+  {
+    float gf[8], bf[8];
+    unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), gf);
+    unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), bf);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int grp = (v * 8 + i) / g.cpg;
+      const float su = fstats[(b * g.G + grp) * 2], sq = fstats[(b * g.G + grp) * 2 + 1];
+      mean[i] = su / n;
+      rstd[i] = rsqrtf(fmaxf(sq / n - mean[i] * mean[i], 0.f) + eps);
+      gm[i] = gf[i];
+      a[i] = rstd[i] * gf[i];
+      bb[i] = bf[i] - mean[i] * a[i];
+      if (MODE == 1) {
+        m1[i] = bstats[(b * g.G + grp) * 2] / n;
+        m2[i] = bstats[(b * g.G + grp) * 2 + 1] / n;
+      }
+    }
+  }
+  const size_t base = (size_t)b * g.HW * g.C + (size_t)v * 8;
+  for (int p = p0 + pl; p < p1; p += g.k) {
+    float xf[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + base + (size_t)p * g.C), xf);
+    if (MODE == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float z = xf[i] * a[i] + bb[i];
+        o[i] = silu ? silu_f(z) : z;
+      }
+    } else {
+      float df[8];
+      unpack8(*reinterpret_cast<const uint4*>(dy + base + (size_t)p * g.C), df);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float dz = df[i];
+        if (silu) dz *= silu_grad(xf[i] * a[i] + bb[i]);
+        const float xh = (xf[i] - mean[i]) * rstd[i];
+        o[i] = rstd[i] * (dz * gm[i] - m1[i] - xh * m2[i]);
+      }
+    }
+    *reinterpret_cast<uint4*>(out + base + (size_t)p * g.C) = pack8(o);
+  }
+}
+
+static int gn_geom(GnGeom& g, int HW, int C, int G) {
+  TB_REQUIRE(C % 8 == 0 && G > 0 && C % G == 0, TB_E_SHAPE, "groupnorm: C=%d G=%d unsupported", C, G);
+  g.HW = HW;
+  g.C = C;
+  g.G = G;
+  g.cpg = C / G;
+  g.nvec = C / 8;
+  TB_REQUIRE(g.nvec <= 1024, TB_E_SHAPE, "groupnorm: C=%d too wide", C);
+  g.k = g.nvec >= 256 ? 1 : 256 / g.nvec;
+  int per_thread = 16;
+  g.ppc = g.k * per_thread;
+  return TB_OK;
+}
+
+// ---------------------------------------------------------------------------------- LayerNorm
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float* f);
+template <>
+__device__ __forceinline__ void load8<__half>(const __half* p, float* f) {
+  unpack8(*reinterpret_cast<const uint4*>(p), f);
+}
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float* f) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float* f);
+template <>
+__device__ __forceinline__ void store8<__half>(__half* p, const float* f) {
+  *reinterpret_cast<uint4*>(p) = pack8(f);
+}
+template <>
+__device__ __forceinline__ void store8<float>(float* p, const float* f) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr int LN_MAXV = 5;  // C <= 1280: at most 5 vectors of 8 per lane
+
+// one warp per row; the row stays in registers (two-pass mean / variance)
+template <typename XT, typename WT>
+__global__ void ln_fwd_kernel(const XT* __restrict__ x, long long ldx, const WT* __restrict__ gamma,
+                              const WT* __restrict__ beta, __half* __restrict__ y, long long ldy,
+                              float* __restrict__ stats, int M, int C, float eps) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const int nvec = C / 8;
+  float v[LN_MAXV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_MAXV; ++j) {
+    const int vi = lane + j * 32;
+    if (vi < nvec) {
+      load8<XT>(x + row * ldx + vi * 8, v[j]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += v[j][i];
+    }
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_MAXV; ++j) {
+    const int vi = lane + j * 32;
+    if (vi < nvec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = v[j][i] - mean;
+        q += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+  for (int j = 0; j < LN_MAXV; ++j) {
+    const int vi = lane + j * 32;
+    if (vi < nvec) {
+      float gf[8], bf[8], o[8];
+      load8<WT>(gamma + vi * 8, gf);
+      load8<WT>(beta + vi * 8, bf);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = (v[j][i] - mean) * rstd * gf[i] + bf[i];
+      store8<__half>(y + row * ldy + vi * 8, o);
+    }
+  }
+  if (lane == 0 && stats) {
+    stats[row * 2] = mean;
+    stats[row * 2 + 1] = rstd;
+  }
+}
+
+// dx = rstd * (dy*gamma - mean(dy*gamma) - xhat * mean(dy*gamma*xhat))  (+ add)
+template <typename XT, typename WT, typename DT>
+__global__ void ln_bwd_kernel(const __half* __restrict__ dy, long long lddy, const XT* __restrict__ x,
+                              long long ldx, const WT* __restrict__ gamma,
+                              const float* __restrict__ stats, const DT* __restrict__ add,
+                              DT* __restrict__ dx, int M, int C) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const int nvec = C / 8;
+  const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
+  float g[LN_MAXV][8], xh[LN_MAXV][8];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_MAXV; ++j) {
+    const int vi = lane + j * 32;
+    if (vi < nvec) {
+      float df[8], gf[8], xf[8];
+      load8<__half>(dy + row * lddy + vi * 8, df);
+      load8<WT>(gamma + vi * 8, gf);
+      load8<XT>(x + row * ldx + vi * 8, xf);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        g[j][i] = df[i] * gf[i];
+        xh[j][i] = (xf[i] - mean) * rstd;
+        s1 += g[j][i];
+        s2 += g[j][i] * xh[j][i];
+      }
+    }
+  }
+  s1 = warp_sum(s1) / C;
+  s2 = warp_sum(s2) / C;
+#pragma unroll
+  for (int j = 0; j < LN_MAXV; ++j) {
+    const int vi = lane + j * 32;
+    if (vi < nvec) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = rstd * (g[j][i] - s1 - xh[j][i] * s2);
+      if (add) {
+        float af[8];
+        load8<DT>(add + row * (long long)C + vi * 8, af);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += af[i];
+      }
+      store8<DT>(dx + row * (long long)C + vi * 8, o);
+    }
+  }
+}
+
+}  // namespace tb
+
+using namespace tb;
+
+extern "C" int tb_groupnorm_fwd_f16(const void* x, const void* gamma, const void* beta, void* y,
+                                    float* stats, int B, int HW, int C, int G, float eps, int silu,
+                                    void* stream) {
+  int rc = tb_check_device();
+  if (rc) return rc;
+  TB_REQUIRE(x && gamma && beta && y && stats, TB_E_ARG, "tb_groupnorm_fwd_f16: null pointer");
+  GnGeom g;
+  if ((rc = gn_geom(g, HW, C, G))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(stats, 0, (size_t)B * G * 2 * sizeof(float), st);
+  TB_REQUIRE(e == cudaSuccess, TB_E_CUDA, "groupnorm memset: %s", cudaGetErrorString(e));
+  dim3 grid((HW + g.ppc - 1) / g.ppc, B);
+  const int threads = g.nvec * g.k;
+  gn_stats_kernel<0><<<grid, threads, 2 * G * sizeof(float), st>>>(
+      (const __half*)x, nullptr, nullptr, nullptr, nullptr, stats, g, eps, silu);
+  if ((rc = check_launch("gn_stats_kernel<0>"))) return rc;
+  gn_apply_kernel<0><<<grid, threads, 0, st>>>((const __half*)x, nullptr, (const __half*)gamma,
+                                              (const __half*)beta, stats, nullptr, (__half*)y, g, eps,
+                                              silu);
+  return check_launch("gn_apply_kernel<0>");
+}
+
+extern "C" int tb_groupnorm_bwd_f16(const void* dy, const void* x, const void* gamma, const void* beta,
+                                    const float* stats, float* dstats, void* dx, int B, int HW, int C,
+                                    int G, float eps, int silu, void* stream) {
+  int rc = tb_check_device();
+  if (rc) return rc;
+  TB_REQUIRE(dy && x && gamma && beta && stats && dstats && dx, TB_E_ARG,
+             "tb_groupnorm_bwd_f16: null pointer");
+  GnGeom g;
+  if ((rc = gn_geom(g, HW, C, G))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(dstats, 0, (size_t)B * G * 2 * sizeof(float), st);
+  TB_REQUIRE(e == cudaSuccess, TB_E_CUDA, "groupnorm memset: %s", cudaGetErrorString(e));
+  dim3 grid((HW + g.ppc - 1) / g.ppc, B);
+  const int threads = g.nvec * g.k;
+  gn_stats_kernel<1><<<grid, threads, 2 * G * sizeof(float), st>>>(
+      (const __half*)x, (const __half*)dy, (const __half*)gamma, (const __half*)beta, stats, dstats, g,
+      eps, silu);
+  if ((rc = check_launch("gn_stats_kernel<1>"))) return rc;
+  gn_apply_kernel<1><<<grid, threads, 0, st>>>((const __half*)x, (const __half*)dy,
+                                              (const __half*)gamma, (const __half*)beta, stats, dstats,
+                                              (__half*)dx, g, eps, silu);
+  return check_launch("gn_apply_kernel<1>");
+}
+
+extern "C" int tb_layernorm_fwd(const void* x, int x_f32, int64_t ldx, const void* gamma,
+                                const void* beta, int w_f32, void* y, int64_t ldy, float* stats, int M,
+                                int C, float eps, void* stream) {
+  int rc = tb_check_device();
+  if (rc) return rc;
+  TB_REQUIRE(x && gamma && beta && y, TB_E_ARG, "tb_layernorm_fwd: null pointer");
+  TB_REQUIRE(C % 8 == 0 && C <= LN_MAXV * 256, TB_E_SHAPE, "tb_layernorm_fwd: C=%d unsupported", C);
+  TB_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0, TB_E_ALIGN, "tb_layernorm_fwd: ldx/ldy alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int wpb = 8;
+  const unsigned grid = (unsigned)((M + wpb - 1) / wpb);
+  if (x_f32 && w_f32)
+    ln_fwd_kernel<float, float><<<grid, wpb * 32, 0, st>>>((const float*)x, ldx, (const float*)gamma,
+                                                           (const float*)beta, (__half*)y, ldy, stats,
+                                                           M, C, eps);
+  else if (!x_f32 && !w_f32)
+    ln_fwd_kernel<__half, __half><<<grid, wpb * 32, 0, st>>>((const __half*)x, ldx,
+                                                             (const __half*)gamma, (const __half*)beta,
+                                                             (__half*)y, ldy, stats, M, C, eps);
+  else if (x_f32 && !w_f32)
+    ln_fwd_kernel<float, __half><<<grid, wpb * 32, 0, st>>>((const float*)x, ldx, (const __half*)gamma,
+                                                            (const __half*)beta, (__half*)y, ldy, stats,
+                                                            M, C, eps);
+  else
+    ln_fwd_kernel<__half, float><<<grid, wpb * 32, 0, st>>>((const __half*)x, ldx, (const float*)gamma,
+                                                            (const float*)beta, (__half*)y, ldy, stats,
+                                                            M, C, eps);
+  return check_launch("ln_fwd_kernel");
+}
+
+extern "C" int tb_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int x_f32, int64_t ldx,
+                                const void* gamma, int w_f32, const float* stats, const void* add,
+                                void* dx, int dx_f32, int M, int C, void* stream) {
+  int rc = tb_check_device();
+  if (rc) return rc;
+  TB_REQUIRE(dy && x && gamma && stats && dx, TB_E_ARG, "tb_layernorm_bwd: null pointer");
+  TB_REQUIRE(C % 8 == 0 && C <= LN_MAXV * 256, TB_E_SHAPE, "tb_layernorm_bwd: C=%d unsupported", C);
+  TB_REQUIRE(x_f32 == w_f32 && x_f32 == dx_f32, TB_E_ARG,
+             "tb_layernorm_bwd: supported type sets are all-fp16 (UNet) or x/gamma/dx fp32 (CLIP)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int wpb = 8;
+  const unsigned grid = (unsigned)((M + wpb - 1) / wpb);
+  if (x_f32)
+    ln_bwd_kernel<float, float, float><<<grid, wpb * 32, 0, st>>>(
+        (const __half*)dy, lddy, (const float*)x, ldx, (const float*)gamma, stats, (const float*)add,
+        (float*)dx, M, C);
+  else
+    ln_bwd_kernel<__half, __half, __half><<<grid, wpb * 32, 0, st>>>(
+        (const __half*)dy, lddy, (const __half*)x, ldx, (const __half*)gamma, stats,
+        (const __half*)add, (__half*)dx, M, C);
+  return check_launch("ln_bwd_kernel");
+}

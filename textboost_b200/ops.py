@@ -61,3 +61,40 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, *, bias=None, rowvec=None, residua
     C.call("tb_conv3x3_f16", C.ptr(x), C.ptr(w), C.ptr(out), B, H, W, Cin, Cout, ctypes.byref(ep),
            C.stream_ptr())
     return out
+
+
+def attn_fwd(q, k, v, heads, scale=None, out=None):
+    """q [B,Nq,*] k,v [B,Nk,*] fp16 views whose last dim holds heads*d columns (row stride free).
+    Returns (o [B,Nq,heads*d], lse [B,heads,Nq])."""
+    B, Nq, Ch = q.shape
+    Nk = k.shape[1]
+    d = Ch // heads
+    scale = d ** -0.5 if scale is None else scale
+    assert q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1
+    assert q.stride(0) == Nq * q.stride(1) and k.stride(0) == Nk * k.stride(1) and v.stride(0) == Nk * v.stride(1)
+    if out is None:
+        out = torch.empty((B, Nq, Ch), device=q.device, dtype=F16)
+    lse = torch.empty((B, heads, Nq), device=q.device, dtype=F32)
+    C.call("tb_attn_fwd_f16", C.ptr(q), q.stride(1), C.ptr(k), k.stride(1), C.ptr(v), v.stride(1),
+           C.ptr(out), out.stride(1), C.ptr(lse), B, heads, Nq, Nk, d, scale, C.stream_ptr())
+    return out, lse
+
+
+def attn_bwd(q, k, v, o, do, lse, heads, scale=None, need_dq=True, dk=None, dv=None):
+    """Returns (dq_acc fp32 [B,Nq,C] or None, dk, dv fp16 [B,Nk,C])."""
+    B, Nq, Ch = q.shape
+    Nk = k.shape[1]
+    d = Ch // heads
+    scale = d ** -0.5 if scale is None else scale
+    delta = torch.empty((B, heads, Nq), device=q.device, dtype=F32)
+    dq = torch.empty((B, Nq, Ch), device=q.device, dtype=F32) if need_dq else None
+    if dk is None:
+        dk = torch.empty((B, Nk, Ch), device=q.device, dtype=F16)
+    if dv is None:
+        dv = torch.empty((B, Nk, Ch), device=q.device, dtype=F16)
+    assert do.stride(2) == 1 and o.stride(2) == 1
+    C.call("tb_attn_bwd_f16", C.ptr(q), q.stride(1), C.ptr(k), k.stride(1), C.ptr(v), v.stride(1),
+           C.ptr(o), o.stride(1), C.ptr(do), do.stride(1), C.ptr(lse), C.ptr(delta), C.ptr(dq),
+           dq.stride(1) if dq is not None else 0, C.ptr(dk), dk.stride(1),
+           C.ptr(dv), dv.stride(1), B, heads, Nq, Nk, d, scale, C.stream_ptr())
+    return dq, dk, dv
