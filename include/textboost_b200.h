@@ -51,8 +51,9 @@ typedef struct tb_epilogue {
   const void* bias;     /* fp16 [N] or NULL */
   const void* rowvec;   /* fp16 [ceil(M/rows_per_group), N] or NULL (ResnetBlock2D time-embedding add) */
   int32_t rows_per_group;
-  const void* residual; /* fp16 [M, ldr] or NULL */
+  const void* residual; /* [M, ldr] fp16 (fp32 when residual_f32 != 0) or NULL */
   int64_t ldr;
+  int32_t residual_f32; /* CLIP residual stream is fp32 (accelerate autocast keeps LN / adds in fp32) */
   float alpha;
   int32_t act;
   int32_t out_kind;
@@ -95,6 +96,108 @@ int tb_attn_bwd_f16(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
                     const void* o, int64_t ldo, const void* dO, int64_t lddo, const float* lse,
                     float* delta, float* dQacc, int64_t lddq, void* dK, int64_t lddk, void* dV,
                     int64_t lddv, int B, int heads, int Nq, int Nk, int d, float scale, void* stream);
+
+/* ---- normalisation (HBM-bound, channels-last fp16, fp32 statistics) ---------------------------
+ * GroupNorm(+SiLU): diffusers ResnetBlock2D.norm1/norm2 + nonlinearity, Transformer2DModel.norm,
+ * conv_norm_out + conv_act (inside unet(...), train_textboost.py:1063 / backward :1108).
+ * x,y,dy,dx [B, HW, C] fp16; gamma/beta fp16 [C]; stats [B,G,2] fp32 = (sum x, sum x^2) written by the
+ * forward and consumed by the backward; dstats [B,G,2] fp32 workspace. */
+int tb_groupnorm_fwd_f16(const void* x, const void* gamma, const void* beta, void* y, float* stats, int B,
+                         int HW, int C, int G, float eps, int silu, void* stream);
+/* dx = GN_backward(dy) + add  (add fp16 [B,HW,C] or NULL: the residual branch's gradient). */
+int tb_groupnorm_bwd_f16(const void* dy, const void* x, const void* gamma, const void* beta,
+                         const float* stats, float* dstats, const void* add, void* dx, int B, int HW,
+                         int C, int G, float eps, int silu, void* stream);
+/* LayerNorm over the last dim of [M, C].  Type sets: UNet (x, gamma/beta, y all fp16) and CLIP (x and
+ * gamma/beta fp32 — the residual stream stays fp32 under accelerate's autocast — y fp16 for the next
+ * GEMM or fp32 for the final LayerNorm).  stats [M,2] = (mean, rstd).  ld* in elements. */
+int tb_layernorm_fwd(const void* x, int x_f32, int64_t ldx, const void* gamma, const void* beta, int w_f32,
+                     void* y, int y_f32, int64_t ldy, float* stats, int M, int C, float eps, void* stream);
+/* dx = LN_backward(dy) + add (add may be NULL or alias dx); dx/add/x/gamma share a type (fp16 | fp32). */
+int tb_layernorm_bwd(const void* dy, int dy_f32, int64_t lddy, const void* x, int x_f32, int64_t ldx,
+                     const void* gamma, const float* stats, const void* add, void* dx, int M, int C,
+                     void* stream);
+
+/* ---- elementwise / data movement (HBM-bound) -------------------------------------------------- */
+/* diffusers GEGLU: out[M,F] = h[:, :F] * gelu(h[:, F:]);  backward gives dh [M,2F]. */
+int tb_geglu_fwd_f16(const void* h, void* out, int64_t M, int F, void* stream);
+int tb_geglu_bwd_f16(const void* dg, const void* h, void* dh, int64_t M, int F, void* stream);
+/* Upsample2D: nearest x2 on NHWC, and its adjoint (2x2 sum). */
+int tb_upsample2x_fwd_f16(const void* x, void* y, int B, int H, int W, int C, void* stream);
+int tb_upsample2x_bwd_f16(const void* dy, void* dx, int B, int H, int W, int C, void* stream);
+/* dst[r, :cols] (=|+=) src[r, :cols] with row strides: skip-connection concat / split / residual adds. */
+int tb_copy2d_f16(void* dst, int64_t ldd, const void* src, int64_t lds, int64_t rows, int cols,
+                  int accumulate, void* stream);
+int tb_cast_f32_f16(void* dst, int64_t ldd, const void* src, int64_t lds, int64_t rows, int cols,
+                    float scale, void* stream);
+/* Downsample2D (conv3x3 stride 2 pad 1): forward = im2col + tb_gemm_f16; backward = zero-stuff +
+ * tb_conv3x3_f16 with the flipped weight. */
+int tb_im2col3x3s2_f16(const void* x, void* col, int B, int H, int W, int C, void* stream);
+int tb_zero_stuff2x_f16(const void* dy, void* out, int B, int Ho, int Wo, int C, void* stream);
+/* diffusers get_timestep_embedding(flip_sin_to_cos=True, freq_shift=0) -> fp16 [B, dim] = [cos | sin]. */
+int tb_timestep_embedding_f16(const int64_t* t, void* out, int B, int dim, void* stream);
+int tb_silu_f16(const void* x, void* y, int64_t n, void* stream);
+/* DDPMScheduler.add_noise (+ target: epsilon or get_velocity), train_textboost.py:1052, :1070-1075.
+ * x0/eps fp32 [B, per_image]; acp = alphas_cumprod fp32 [T]; noisy fp16; target fp32 (may be NULL). */
+int tb_add_noise(const float* x0, const float* eps, const int64_t* t, const float* acp, void* noisy_f16,
+                 float* target, int B, int per_image, int v_prediction, void* stream);
+/* F.mse_loss(pred.float(), target.float()).mean() fused with its gradient (train_textboost.py:1085-1090):
+ * *loss_acc += weight*mse;  dpred = weight * 2 (pred-target)/n * (*loss_scale). */
+int tb_mse_fwd_bwd(const void* pred_f16, const float* target, int64_t n, float weight,
+                   const float* loss_scale, float* loss_acc, void* dpred_f16, void* stream);
+/* conv_in (4 -> C0) reads the NCHW fp16 sample and writes NHWC; conv_out (C0 -> 4) does the reverse.
+ * Weights in the diffusers layout [Cout, Cin, 3, 3]. */
+int tb_conv_in_f16(const void* x_nchw, const void* w, const void* bias, void* y_nhwc, int B, int H, int W,
+                   int Cin, int Cout, void* stream);
+int tb_conv_out_f16(const void* h_nhwc, const void* w, const void* bias, void* y_nchw, int B, int H, int W,
+                    int Cin, int Cout, void* stream);
+int tb_conv_out_bwd_f16(const void* dy_nchw, const void* w, void* dh_nhwc, int B, int H, int W, int Cin,
+                        int Cout, void* stream);
+
+/* ---- CLIP text encoder pieces that are not GEMM / LayerNorm ------------------------------------
+ * (transformers CLIPTextTransformer called from textboost/text_encoder.py:62-69; peft LoRA Linear
+ * configured at train_textboost.py:702-709.) */
+/* x[m,:] = tok(ids[m]) + pos[m % L]; tok(id) = id < n_base ? base[id] * (*decay) : added[id - n_base]. */
+int tb_clip_embed(const int64_t* ids, const float* base, const float* added, const float* decay,
+                  const float* pos, float* x, int M, int L, int D, int n_base, void* stream);
+/* grad_rows[id - n_base, :] += g[m, :] for id >= n_base only (train_textboost.py:1109-1117). */
+int tb_clip_embed_grad(const int64_t* ids, const float* g, float* grad_rows, int M, int D, int n_base,
+                       void* stream);
+/* LoRA fused into the QKV GEMM as a K-extension: y_ext[:, D:D+R] = y_ext[:, :D] @ A^T (A fp32 [R, D]). */
+int tb_lora_down(void* y_ext, int64_t ld, const float* A, int M, int D, int R, int RPAD, void* stream);
+/* write scaling*B (fp32 [T][D][r]) into the extension block of Wext [T*D, D+RPAD] and WextT. */
+int tb_lora_pack(const float* B, void* Wext, void* WextT, int T, int D, int r, int RPAD, float scaling,
+                 void* stream);
+/* dB [T][D][r] += scaling * dY^T xa ;  dA [T*r][D] += dxa^T y   (accumulating, fp32). */
+int tb_lora_grad(const void* dY, const void* y_ext, const void* dA_ext, int64_t ld, float* dB, float* dA,
+                 int M, int T, int D, int r, float scaling, void* stream);
+/* dA_ext[:, :D] += dA_ext[:, D:D+R] @ A. */
+int tb_lora_dx(void* dA_ext, int64_t ld, const float* A, int M, int D, int R, void* stream);
+/* causal attention over L <= 128 tokens, head_dim 64; qkv [B*L, 3D] fused; dqkv laid out like qkv. */
+int tb_clip_attn_fwd(const void* qkv, void* out, int B, int L, int D, int heads, void* stream);
+int tb_clip_attn_bwd(const void* qkv, const void* dO, void* dqkv, int B, int L, int D, int heads,
+                     void* stream);
+int tb_act_fwd_f16(const void* u, void* out, int64_t n, int kind, void* stream);
+int tb_act_bwd_f16(const void* u, const void* g, void* out, int64_t n, int kind, void* stream);
+/* TextBoostModel.forward override (textboost/text_encoder.py:71-86): rows whose ids[b,1]==eos_id become
+ * null_emb [L,D]; with use_fixed, position 0 of every row becomes null_emb[0].  backward=1 zeroes the
+ * gradient at the overwritten slots instead. */
+int tb_null_override(const int64_t* ids, const float* null_emb, float* h, int B, int L, int D, int eos_id,
+                     int use_fixed, int backward, void* stream);
+/* knowledge-preservation loss (train_textboost.py:1096-1106): kind 0 = 1-cos, 1 = mse, mean over the M
+ * rows; *loss_acc += weight*kp; dh_acc += d(weight*kp)/dh * (*loss_scale)  (dh_acc may be NULL). */
+int tb_kpl_fwd_bwd(const float* h, const float* h0, int M, int D, int kind, float weight,
+                   const float* loss_scale, float* loss_acc, float* dh_acc, void* stream);
+
+/* ---- optimiser tail (train_textboost.py:1109-1149; torch.optim.AdamW; accelerate GradScaler) ----
+ * Flat fp32 buffers [LoRA (n_lora) | added embedding rows (n_rows*D)].  state: fp32[16] on the device:
+ * [0] loss scale [1] growth tracker [2] found_inf [3] sum g^2 [4] step [5] frozen-row decay
+ * [6] clip coef [7] grad norm [8] skipped steps.  grads are consumed AND zeroed. */
+int tb_optim_mix_mask(float* grad_lora_b, int64_t n, int D, int r, int parity, void* stream);
+int tb_adamw_fused_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n_lora,
+                        int n_rows, int D, float lr_lora, float lr_emb, float beta1, float beta2, float eps,
+                        float weight_decay, float max_grad_norm, float inv_world, float mean_norm,
+                        float* state, float* row_norm_mean, void* stream);
 
 #ifdef __cplusplus
 }

@@ -25,6 +25,7 @@ class Epilogue(Structure):
         ("rows_per_group", c_int32),
         ("residual", c_void_p),
         ("ldr", c_int64),
+        ("residual_f32", c_int32),
         ("alpha", c_float),
         ("act", c_int32),
         ("out_kind", c_int32),
@@ -47,6 +48,44 @@ _SIGNATURES = {
     "tb_attn_bwd_f16": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                         c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                         c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p],
+    "tb_groupnorm_fwd_f16": [c_void_p] * 5 + [c_int] * 4 + [c_float, c_int, c_void_p],
+    "tb_groupnorm_bwd_f16": [c_void_p] * 8 + [c_int] * 4 + [c_float, c_int, c_void_p],
+    "tb_layernorm_fwd": [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int64,
+                         c_void_p, c_int, c_int, c_float, c_void_p],
+    "tb_layernorm_bwd": [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p,
+                         c_void_p, c_int, c_int, c_void_p],
+    "tb_geglu_fwd_f16": [c_void_p, c_void_p, c_int64, c_int, c_void_p],
+    "tb_geglu_bwd_f16": [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p],
+    "tb_upsample2x_fwd_f16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "tb_upsample2x_bwd_f16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "tb_copy2d_f16": [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p],
+    "tb_cast_f32_f16": [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_float, c_void_p],
+    "tb_im2col3x3s2_f16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "tb_zero_stuff2x_f16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "tb_timestep_embedding_f16": [c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "tb_silu_f16": [c_void_p, c_void_p, c_int64, c_void_p],
+    "tb_add_noise": [c_void_p] * 6 + [c_int, c_int, c_int, c_void_p],
+    "tb_mse_fwd_bwd": [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p],
+    "tb_conv_in_f16": [c_void_p] * 4 + [c_int] * 5 + [c_void_p],
+    "tb_conv_out_f16": [c_void_p] * 4 + [c_int] * 5 + [c_void_p],
+    "tb_conv_out_bwd_f16": [c_void_p] * 3 + [c_int] * 5 + [c_void_p],
+    "tb_clip_embed": [c_void_p] * 6 + [c_int] * 4 + [c_void_p],
+    "tb_clip_embed_grad": [c_void_p] * 3 + [c_int] * 3 + [c_void_p],
+    "tb_lora_down": [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "tb_lora_pack": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p],
+    "tb_lora_grad": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                     c_float, c_void_p],
+    "tb_lora_dx": [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p],
+    "tb_clip_attn_fwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "tb_clip_attn_bwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "tb_act_fwd_f16": [c_void_p, c_void_p, c_int64, c_int, c_void_p],
+    "tb_act_bwd_f16": [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p],
+    "tb_null_override": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "tb_kpl_fwd_bwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                       c_void_p],
+    "tb_optim_mix_mask": [c_void_p, c_int64, c_int, c_int, c_int, c_void_p],
+    "tb_adamw_fused_step": [c_void_p] * 4 + [c_int64, c_int, c_int] + [c_float] * 10 + [c_void_p, c_void_p,
+                                                                                      c_void_p],
 }
 _RESTYPES = {"tb_last_error": c_char_p}
 

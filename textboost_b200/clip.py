@@ -1,0 +1,254 @@
+"""CLIP text encoder (ViT-L/14 text tower, or OpenCLIP-H) with rank-r LoRA fused into the QKV GEMM,
+forward and hand-derived backward on the B200 kernels.
+
+Replaces, for the TextBoost path, ``transformers.CLIPTextModel`` + peft LoRA ``Linear`` +
+``textboost.text_encoder.TextBoostModel`` (/root/reference/textboost/text_encoder.py:17-87, called from
+train_textboost.py:1054-1059 and :1099-1100; LoRA configured at :702-709).
+
+Precision policy mirrors accelerate fp16 autocast: master weights fp32, residual
+stream / LayerNorm / softmax statistics fp32, GEMM operands fp16 (static fp16 copies of the frozen base
+weights), fp32 accumulation.
+
+LoRA is not a separate pair of tiny GEMMs: with xa = LN(x) A^T (r columns per target) appended to the
+GEMM's K dimension and scaling*B appended to the weight, one tcgen05 GEMM computes
+  [q|k|v] = [LN(x) | xa] [W | sB]^T + b
+and the same trick with the transposed operand gives dLN(x) and dxa in one dgrad GEMM.
+
+Trainable state lives in ONE flat fp32 buffer  [A (layers x 3r x D) | B (layers x 3 x D x r) | added rows]
+with a same-shaped gradient buffer: that buffer is what the single NCCL all-reduce and the fused AdamW see.
+"""
+from __future__ import annotations
+
+import ctypes
+import dataclasses
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import _cabi as C
+from . import ops
+
+F16 = torch.float16
+F32 = torch.float32
+EOS_ID = 49407  # hard-coded in textboost/text_encoder.py:71
+RPAD = 16       # K-extension columns reserved for the LoRA down-projections (3 targets x r <= 16)
+
+
+@dataclasses.dataclass
+class ClipConfig:
+    vocab_size: int = 49408
+    hidden_size: int = 768
+    intermediate_size: int = 3072
+    num_hidden_layers: int = 12
+    num_attention_heads: int = 12
+    max_position_embeddings: int = 77
+    hidden_act: str = "quick_gelu"
+    layer_norm_eps: float = 1e-5
+
+    @staticmethod
+    def clip_l():
+        return ClipConfig()
+
+    @staticmethod
+    def openclip_h():
+        return ClipConfig(hidden_size=1024, intermediate_size=4096, num_hidden_layers=23,
+                          num_attention_heads=16, hidden_act="gelu")
+
+
+LORA_TARGETS = ("q_proj", "k_proj", "v_proj")
+
+
+class TrainableState:
+    """Flat fp32 parameter / gradient buffers shared by the encoder, the all-reduce and the optimiser."""
+
+    def __init__(self, n_layers: int, D: int, r: int, n_rows: int, device):
+        self.n_layers, self.D, self.r, self.n_rows = n_layers, D, r, n_rows
+        self.T = len(LORA_TARGETS) if r > 0 else 0
+        self.n_a = n_layers * self.T * r * D
+        self.n_b = n_layers * self.T * D * r
+        self.n_lora = self.n_a + self.n_b
+        self.n_total = self.n_lora + n_rows * D
+        self.params = torch.zeros(self.n_total, device=device, dtype=F32)
+        self.grads = torch.zeros(self.n_total, device=device, dtype=F32)
+
+    def A(self, l, buf=None):  # [T*r, D]
+        buf = self.params if buf is None else buf
+        sz = self.T * self.r * self.D
+        return buf[l * sz:(l + 1) * sz].view(self.T * self.r, self.D)
+
+    def B(self, l, buf=None):  # [T, D, r]
+        buf = self.params if buf is None else buf
+        sz = self.T * self.D * self.r
+        return buf[self.n_a + l * sz:self.n_a + (l + 1) * sz].view(self.T, self.D, self.r)
+
+    def rows(self, buf=None):  # [n_rows, D]
+        buf = self.params if buf is None else buf
+        return buf[self.n_lora:].view(self.n_rows, self.D)
+
+    def b_segment(self, buf=None):
+        buf = self.params if buf is None else buf
+        return buf[self.n_a:self.n_lora]
+
+
+class ClipEngine:
+    """sd: HF ``text_model.*`` keys (fp32).  LoRA keys in peft naming are honoured if present."""
+
+    def __init__(self, cfg: ClipConfig, sd: Dict[str, torch.Tensor], device, lora_r: int = 0,
+                 lora_alpha: Optional[int] = None, n_base: Optional[int] = None, seed: int = 0):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        D, nl = cfg.hidden_size, cfg.num_hidden_layers
+        self.D, self.nl, self.heads = D, nl, cfg.num_attention_heads
+        assert D // self.heads == 64, "CLIP text towers use head_dim 64"
+        self.r = lora_r
+        self.scaling = (lora_alpha if lora_alpha is not None else lora_r) / lora_r if lora_r else 0.0
+        self.act = C.TB_ACT_QUICK_GELU if cfg.hidden_act == "quick_gelu" else C.TB_ACT_GELU
+        self.Kext = D + (RPAD if lora_r else 0)
+        assert 3 * lora_r <= RPAD
+
+        def g32(k):
+            return sd[k].detach().to(device=self.device, dtype=F32).contiguous()
+
+        def g16(k):
+            return sd[k].detach().to(device=self.device, dtype=F16).contiguous()
+
+        def base_key(prefix, kind):  # peft renames W to base_layer.W after injection
+            k = f"{prefix}.base_layer.{kind}"
+            return k if k in sd else f"{prefix}.{kind}"
+
+        emb = g32("text_model.embeddings.token_embedding.weight")
+        self.n_base = emb.shape[0] if n_base is None else n_base
+        self.tok_base = emb[:self.n_base].contiguous()
+        n_rows = emb.shape[0] - self.n_base
+        self.pos = g32("text_model.embeddings.position_embedding.weight")
+        self.state = TrainableState(nl, D, lora_r, n_rows, self.device)
+        if n_rows:
+            self.state.rows().copy_(emb[self.n_base:])
+        self.layers = []
+        gen = torch.Generator().manual_seed(seed)
+        for l in range(nl):
+            p = f"text_model.encoder.layers.{l}."
+            L = {}
+            L["ln1"] = (g32(p + "layer_norm1.weight"), g32(p + "layer_norm1.bias"))
+            L["ln2"] = (g32(p + "layer_norm2.weight"), g32(p + "layer_norm2.bias"))
+            ws, bs = [], []
+            for t in LORA_TARGETS:
+                ws.append(g16(base_key(p + "self_attn." + t, "weight")))
+                bs.append(g16(base_key(p + "self_attn." + t, "bias")))
+            wqkv = torch.cat(ws, 0)  # [3D, D]
+            wext = torch.zeros((3 * D, self.Kext), device=self.device, dtype=F16)
+            wext[:, :D] = wqkv
+            wext_t = torch.zeros((self.Kext, 3 * D), device=self.device, dtype=F16)
+            wext_t[:D] = wqkv.t()
+            L["wqkv"], L["wqkv_t"], L["bqkv"] = wext, wext_t, torch.cat(bs, 0)
+            for name, key in (("o", "self_attn.out_proj"), ("f1", "mlp.fc1"), ("f2", "mlp.fc2")):
+                w = g16(p + key + ".weight")
+                L["w" + name], L["w" + name + "_t"] = w, w.t().contiguous()
+                L["b" + name] = g16(p + key + ".bias")
+            self.layers.append(L)
+            if lora_r:
+                for ti, t in enumerate(LORA_TARGETS):
+                    ka = f"{p}self_attn.{t}.lora_A.default.weight"
+                    kb = f"{p}self_attn.{t}.lora_B.default.weight"
+                    if ka in sd:
+                        self.state.A(l)[ti * lora_r:(ti + 1) * lora_r].copy_(sd[ka].to(self.device, F32))
+                        self.state.B(l)[ti].copy_(sd[kb].to(self.device, F32))
+                    else:  # peft init_lora_weights="gaussian": A ~ N(0, 1/r), B = 0
+                        a = torch.randn((lora_r, D), generator=gen) / lora_r
+                        self.state.A(l)[ti * lora_r:(ti + 1) * lora_r].copy_(a.to(self.device))
+        self.lnf = (g32("text_model.final_layer_norm.weight"), g32("text_model.final_layer_norm.bias"))
+        self.null_embedding = torch.zeros((cfg.max_position_embeddings, D), device=self.device, dtype=F32)
+        self.use_fixed_special = False
+        self.decay = torch.ones(1, device=self.device, dtype=F32)  # lazy weight decay of frozen rows (D8)
+        self._ctx = None
+
+    # textboost/text_encoder.py:28-32
+    def set_null_embedding(self, t: torch.Tensor):
+        assert t.shape == self.null_embedding.shape, (t.shape, self.null_embedding.shape)
+        self.null_embedding = t.detach().to(self.device, F32).contiguous()
+        self.use_fixed_special = True
+
+    def pack_lora(self):
+        """refresh the B-dependent extension blocks of the fused QKV weights (after every optimiser step)."""
+        if not self.r:
+            return
+        st = self.state
+        for l, L in enumerate(self.layers):
+            C.call("tb_lora_pack", C.ptr(st.B(l)), C.ptr(L["wqkv"]), C.ptr(L["wqkv_t"]), st.T, self.D,
+                   self.r, RPAD, self.scaling, C.stream_ptr())
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, input_ids: torch.Tensor, save_for_backward: bool = False) -> torch.Tensor:
+        """input_ids int64 [B, L] on the device -> last_hidden_state fp32 [B, L, D] (after the override)."""
+        assert input_ids.dtype == torch.int64 and input_ids.is_cuda
+        ids = input_ids.contiguous()
+        B, Lq = ids.shape
+        D, M = self.D, B * Lq
+        st = self.state
+        s = C.stream_ptr()
+        x = torch.empty((M, D), device=self.device, dtype=F32)
+        C.call("tb_clip_embed", C.ptr(ids), C.ptr(self.tok_base), C.ptr(st.rows() if st.n_rows else None),
+               C.ptr(self.decay), C.ptr(self.pos), C.ptr(x), M, Lq, D, self.n_base, s)
+        saved = []
+        for l, L in enumerate(self.layers):
+            y_ext = torch.empty((M, self.Kext), device=self.device, dtype=F16)
+            _, st1 = ops.layernorm(x, *L["ln1"], eps=self.cfg.layer_norm_eps, out=y_ext[:, :D])
+            if self.r:
+                C.call("tb_lora_down", C.ptr(y_ext), self.Kext, C.ptr(st.A(l)), M, D, st.T * self.r, RPAD, s)
+            qkv = ops.gemm(y_ext, L["wqkv"], bias=L["bqkv"])
+            o = torch.empty((M, D), device=self.device, dtype=F16)
+            C.call("tb_clip_attn_fwd", C.ptr(qkv), C.ptr(o), B, Lq, D, self.heads, s)
+            x2 = ops.gemm(o, L["wo"], bias=L["bo"], residual=x, out_kind=C.TB_OUT_F32)
+            y2, st2 = ops.layernorm(x2, *L["ln2"], eps=self.cfg.layer_norm_eps)
+            u = ops.gemm(y2, L["wf1"], bias=L["bf1"])
+            a = torch.empty_like(u)
+            C.call("tb_act_fwd_f16", C.ptr(u), C.ptr(a), u.numel(), self.act, s)
+            x3 = ops.gemm(a, L["wf2"], bias=L["bf2"], residual=x2, out_kind=C.TB_OUT_F32)
+            if save_for_backward:
+                saved.append((x, st1, y_ext, qkv, x2, st2, u))
+            x = x3
+        out, stf = ops.layernorm(x, *self.lnf, eps=self.cfg.layer_norm_eps, out_dtype=F32)
+        C.call("tb_null_override", C.ptr(ids), C.ptr(self.null_embedding), C.ptr(out), B, Lq, D, EOS_ID,
+               int(self.use_fixed_special), 0, s)
+        if save_for_backward:
+            self._ctx = (ids, saved, x, stf)
+        return out.view(B, Lq, D)
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, d_out: torch.Tensor):
+        """d_out fp32 [B, L, D] (consumed / overwritten).  Accumulates into state.grads."""
+        assert self._ctx is not None, "forward(save_for_backward=True) must precede backward"
+        ids, saved, xf, stf = self._ctx
+        self._ctx = None
+        B, Lq = ids.shape
+        D, M = self.D, B * Lq
+        st = self.state
+        s = C.stream_ptr()
+        d_out = d_out.contiguous().view(M, D)
+        C.call("tb_null_override", C.ptr(ids), None, C.ptr(d_out), B, Lq, D, EOS_ID,
+               int(self.use_fixed_special), 1, s)
+        g = ops.layernorm_bwd(d_out, xf, self.lnf[0], stf)
+        for l in reversed(range(self.nl)):
+            L = self.layers[l]
+            x, st1, y_ext, qkv, x2, st2, u = saved[l]
+            g16 = ops.cast_f32_f16(g)
+            da = ops.gemm(g16, L["wf2_t"])
+            du = torch.empty_like(da)
+            C.call("tb_act_bwd_f16", C.ptr(u), C.ptr(da), C.ptr(du), u.numel(), self.act, s)
+            dy2 = ops.gemm(du, L["wf1_t"])
+            g = ops.layernorm_bwd(dy2, x2, L["ln2"][0], st2, add=g, out=g)
+            g16 = ops.cast_f32_f16(g)
+            do = ops.gemm(g16, L["wo_t"])
+            dqkv = torch.empty_like(qkv)
+            C.call("tb_clip_attn_bwd", C.ptr(qkv), C.ptr(do), C.ptr(dqkv), B, Lq, D, self.heads, s)
+            dy_ext = ops.gemm(dqkv, L["wqkv_t"])
+            if self.r:
+                C.call("tb_lora_grad", C.ptr(dqkv), C.ptr(y_ext), C.ptr(dy_ext), self.Kext,
+                       C.ptr(st.B(l, st.grads)), C.ptr(st.A(l, st.grads)), M, st.T, D, self.r,
+                       self.scaling, s)
+                C.call("tb_lora_dx", C.ptr(dy_ext), self.Kext, C.ptr(st.A(l)), M, D, st.T * self.r, s)
+            g = ops.layernorm_bwd(dy_ext[:, :D], x, L["ln1"][0], st1, add=g, out=g)
+            saved[l] = None
+        if st.n_rows:
+            C.call("tb_clip_embed_grad", C.ptr(ids), C.ptr(g), C.ptr(st.rows(st.grads)), M, D, self.n_base, s)
+        return g.view(B, Lq, D)

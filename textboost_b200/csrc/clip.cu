@@ -1,0 +1,456 @@
+// Text-encoder-specific kernels (everything that is not a GEMM / LayerNorm):
+//   token+position embedding gather, LoRA down-projection / weight packing / gradients, causal
+//   attention over 77 tokens (forward and backward), activation forward/backward, the TextBoostModel
+//   null-embedding override (textboost/text_encoder.py:71-86), sparse embedding-row gradients and the
+//   knowledge-preservation loss (train_textboost.py:1096-1106).
+// Sizes are tiny (616 tokens x 768): plain SIMT kernels, fp32 accumulation.
+#include "host_util.h"
+#include "sm100.cuh"
+
+namespace tb {
+
+__device__ __forceinline__ float warp_sum_c(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// x[m,:] = tok(ids[m]) + pos[m % L];  tok(id) = id < n_base ? base[id]*decay : added[id-n_base]
+__global__ void clip_embed_kernel(const long long* __restrict__ ids, const float* __restrict__ base,
+                                  const float* __restrict__ added, const float* __restrict__ decay,
+                                  const float* __restrict__ pos, float* __restrict__ x, int M, int L, int D,
+                                  int n_base) {
+  const int m = blockIdx.x;
+  const long long id = ids[m];
+  const float dc = decay ? *decay : 1.f;
+  const float* src = id < n_base ? base + id * (long long)D : added + (id - n_base) * (long long)D;
+  const float sc = id < n_base ? dc : 1.f;
+  const float* pp = pos + (long long)(m % L) * D;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) x[(long long)m * D + c] = src[c] * sc + pp[c];
+}
+
+// dE[id-n_base, :] += g[m, :] for id >= n_base (added rows only: train_textboost.py:1109-1117)
+__global__ void clip_embed_grad_kernel(const long long* __restrict__ ids, const float* __restrict__ g,
+                                       float* __restrict__ grad_rows, int M, int D, int n_base) {
+  const int m = blockIdx.x;
+  const long long id = ids[m];
+  if (id < n_base) return;
+  float* dst = grad_rows + (id - n_base) * (long long)D;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) atomicAdd(dst + c, g[(long long)m * D + c]);
+}
+
+// xa[m, j] = sum_c y[m,c] * A[j,c]  -> written as fp16 into the K-extension columns of the GEMM A operand
+// (columns D .. D+R-1 of a row of stride ld; columns D+R .. D+RPAD-1 are zeroed).
+__global__ void lora_down_kernel(__half* __restrict__ y_ext, long long ld, const float* __restrict__ A,
+                                 int M, int D, int R, int RPAD) {
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const int lane = threadIdx.x & 31;
+  __half* row = y_ext + (long long)m * ld;
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    const float v = __half2float(row[c]);
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < R) acc[j] += v * A[(long long)j * D + c];
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = warp_sum_c(acc[j]);
+  if (lane < RPAD) {
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j == lane && j < R) v = acc[j];
+    row[D + lane] = __float2half(v);
+  }
+}
+
+// Pack the LoRA up-projections into the extension columns of the fused QKV weight and its transpose:
+//   Wext[t*D + n, D + t*r + j]   = scaling * B_t[n, j]        (forward operand, [T*D, D+RPAD])
+//   WextT[D + t*r + j, t*D + n]  = scaling * B_t[n, j]        (dgrad operand,  [D+RPAD, T*D])
+// everything else inside the extension block is zero.  B is [T][D][r] fp32.
+__global__ void lora_pack_kernel(const float* __restrict__ Bm, __half* __restrict__ Wext,
+                                 __half* __restrict__ WextT, int T, int D, int r, int RPAD, float scaling) {
+  const int K = D + RPAD;
+  const long long total = (long long)T * D * RPAD;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i % RPAD);
+    const long long row = i / RPAD;  // t*D + n
+    const int t = (int)(row / D), n = (int)(row % D);
+    float v = 0.f;
+    if (e >= t * r && e < (t + 1) * r) v = scaling * Bm[((long long)t * D + n) * r + (e - t * r)];
+    const __half hv = __float2half(v);
+    Wext[row * K + D + e] = hv;
+    WextT[(long long)(D + e) * (T * D) + row] = hv;
+  }
+}
+
+// LoRA gradients for one layer (accumulating, fp32):
+//   dB_t[n, j] += sum_m dY[m, t*D+n] * xa[m, t*r+j]
+//   dA[tj, c]  += sum_m dxa[m, tj] * y[m, c]
+// dY [M, T*D] fp16, xa = y_ext[:, D:D+R], y = y_ext[:, :D], dxa = dA_ext[:, D:D+R] (all fp16).
+// grid.x covers T*D (dB rows) then D (dA columns); one warp per output row, lanes over m.
+__global__ void lora_grad_kernel(const __half* __restrict__ dY, const __half* __restrict__ y_ext,
+                                 const __half* __restrict__ dA_ext, long long ld, float* __restrict__ dB,
+                                 float* __restrict__ dA, int M, int T, int D, int r, float scaling) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int R = T * r;
+  if (w < T * D) {
+    const int t = w / D;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int m = lane; m < M; m += 32) {
+      const float g = __half2float(dY[(long long)m * (T * D) + w]);
+      for (int j = 0; j < r; ++j) acc[j] += g * __half2float(y_ext[(long long)m * ld + D + t * r + j]);
+    }
+    for (int j = 0; j < r; ++j) {
+      const float s = warp_sum_c(acc[j]);
+      if (lane == 0) dB[(long long)w * r + j] += scaling * s;
+    }
+  } else if (w < T * D + D) {
+    const int c = w - T * D;
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int m = lane; m < M; m += 32) {
+      const float yv = __half2float(y_ext[(long long)m * ld + c]);
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j < R) acc[j] += yv * __half2float(dA_ext[(long long)m * ld + D + j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < R) {
+        const float s = warp_sum_c(acc[j]);
+        if (lane == 0) dA[(long long)j * D + c] += s;
+      }
+    }
+  }
+}
+
+// dy[m, c] += sum_j dxa[m, j] * A[j, c]   (in place on the first D columns of dA_ext)
+__global__ void lora_dx_kernel(__half* __restrict__ dA_ext, long long ld, const float* __restrict__ A,
+                               int M, int D, int R) {
+  const int m = blockIdx.x;
+  __shared__ float sx[16];
+  if (threadIdx.x < 16) sx[threadIdx.x] = threadIdx.x < R ? __half2float(dA_ext[(long long)m * ld + D + threadIdx.x]) : 0.f;
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float v = __half2float(dA_ext[(long long)m * ld + c]);
+    for (int j = 0; j < R; ++j) v += sx[j] * A[(long long)j * D + c];
+    dA_ext[(long long)m * ld + c] = __float2half(v);
+  }
+}
+
+// ------------------------------------------------------------------ causal attention, L <= 128, d = 64
+// qkv [B*L, 3*D] fp16 (q | k | v, head h at columns h*64); one CTA per (b, h).
+template <bool BWD>
+__global__ void clip_attn_kernel(const __half* __restrict__ qkv, const __half* __restrict__ dO,
+                                 __half* __restrict__ out, int L, int D, int heads, float scale) {
+  constexpr int HD = 64;
+  extern __shared__ float smf[];
+  float* sP = smf;                       // [L][L+1]
+  float* sdS = sP + L * (L + 1);         // [L][L+1] (BWD only)
+  __half* sQ = reinterpret_cast<__half*>(BWD ? sdS + L * (L + 1) : sP + L * (L + 1));
+  __half* sK = sQ + L * HD;
+  __half* sV = sK + L * HD;
+  __half* sdO = sV + L * HD;  // BWD only
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const long long rs = 3LL * D;
+  const __half* base = qkv + (long long)b * L * rs + h * HD;
+  for (int i = threadIdx.x; i < L * HD / 8; i += blockDim.x) {
+    const int l = i / (HD / 8), v = i % (HD / 8);
+    reinterpret_cast<uint4*>(sQ)[i] = *reinterpret_cast<const uint4*>(base + l * rs + v * 8);
+    reinterpret_cast<uint4*>(sK)[i] = *reinterpret_cast<const uint4*>(base + l * rs + D + v * 8);
+    reinterpret_cast<uint4*>(sV)[i] = *reinterpret_cast<const uint4*>(base + l * rs + 2 * D + v * 8);
+    if (BWD)
+      reinterpret_cast<uint4*>(sdO)[i] =
+          *reinterpret_cast<const uint4*>(dO + ((long long)b * L + l) * D + h * HD + v * 8);
+  }
+  __syncthreads();
+  // S = scale * Q K^T with the causal mask (j <= i)
+  for (int idx = threadIdx.x; idx < L * L; idx += blockDim.x) {
+    const int i = idx / L, j = idx % L;
+    float acc = -INFINITY;
+    if (j <= i) {
+      acc = 0.f;
+      const __half2* qp = reinterpret_cast<const __half2*>(sQ + i * HD);
+      const __half2* kp = reinterpret_cast<const __half2*>(sK + j * HD);
+#pragma unroll 8
+      for (int c = 0; c < HD / 2; ++c) {
+        const float2 a = __half22float2(qp[c]), bb = __half22float2(kp[c]);
+        acc += a.x * bb.x + a.y * bb.y;
+      }
+      acc *= scale;
+    }
+    sP[i * (L + 1) + j] = acc;
+  }
+  __syncthreads();
+  // row softmax (fp32), one warp per row
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int i = warp; i < L; i += nw) {
+    float mx = -INFINITY;
+    for (int j = lane; j <= i; j += 32) mx = fmaxf(mx, sP[i * (L + 1) + j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < L; j += 32) {
+      const float e = j <= i ? __expf(sP[i * (L + 1) + j] - mx) : 0.f;
+      sP[i * (L + 1) + j] = e;
+      sum += e;
+    }
+    sum = warp_sum_c(sum);
+    const float inv = 1.f / sum;
+    // the reference casts the probabilities to the matmul dtype (fp16 under autocast) before P V
+    for (int j = lane; j < L; j += 32) sP[i * (L + 1) + j] = __half2float(__float2half(sP[i * (L + 1) + j] * inv));
+  }
+  __syncthreads();
+  if (!BWD) {
+    for (int idx = threadIdx.x; idx < L * HD; idx += blockDim.x) {
+      const int i = idx / HD, c = idx % HD;
+      float acc = 0.f;
+      for (int j = 0; j <= i; ++j) acc += sP[i * (L + 1) + j] * __half2float(sV[j * HD + c]);
+      out[((long long)b * L + i) * D + h * HD + c] = __float2half(acc);
+    }
+    return;
+  }
+  // backward: dP = dO V^T ; dS = P o (dP - rowsum(P o dP)) ; dQ = scale dS K ; dK = scale dS^T Q ; dV = P^T dO
+  for (int idx = threadIdx.x; idx < L * L; idx += blockDim.x) {
+    const int i = idx / L, j = idx % L;
+    float acc = 0.f;
+    if (j <= i) {
+      const __half2* gp = reinterpret_cast<const __half2*>(sdO + i * HD);
+      const __half2* vp = reinterpret_cast<const __half2*>(sV + j * HD);
+#pragma unroll 8
+      for (int c = 0; c < HD / 2; ++c) {
+        const float2 a = __half22float2(gp[c]), bb = __half22float2(vp[c]);
+        acc += a.x * bb.x + a.y * bb.y;
+      }
+    }
+    sdS[i * (L + 1) + j] = acc;
+  }
+  __syncthreads();
+  for (int i = warp; i < L; i += nw) {
+    float dsum = 0.f;
+    for (int j = lane; j <= i; j += 32) dsum += sP[i * (L + 1) + j] * sdS[i * (L + 1) + j];
+    dsum = warp_sum_c(dsum);
+    for (int j = lane; j < L; j += 32)
+      sdS[i * (L + 1) + j] = j <= i ? sP[i * (L + 1) + j] * (sdS[i * (L + 1) + j] - dsum) * scale : 0.f;
+  }
+  __syncthreads();
+  __half* obase = out + (long long)b * L * rs + h * HD;  // d(qkv) laid out like qkv
+  for (int idx = threadIdx.x; idx < L * HD; idx += blockDim.x) {
+    const int i = idx / HD, c = idx % HD;
+    float dq = 0.f, dk = 0.f, dv = 0.f;
+    for (int j = 0; j <= i; ++j) dq += sdS[i * (L + 1) + j] * __half2float(sK[j * HD + c]);
+    for (int j = i; j < L; ++j) {
+      dk += sdS[j * (L + 1) + i] * __half2float(sQ[j * HD + c]);
+      dv += sP[j * (L + 1) + i] * __half2float(sdO[j * HD + c]);
+    }
+    obase[i * rs + c] = __float2half(dq);
+    obase[i * rs + D + c] = __float2half(dk);
+    obase[i * rs + 2 * D + c] = __float2half(dv);
+  }
+}
+
+// ------------------------------------------------------------------ activations (fc1 -> act -> fc2)
+__device__ __forceinline__ float act_fwd(float u, int kind) {
+  if (kind == TB_ACT_QUICK_GELU) return u / (1.f + __expf(-1.702f * u));
+  return 0.5f * u * (1.f + erff(u * 0.70710678118654752f));
+}
+__device__ __forceinline__ float act_bwd(float u, int kind) {
+  if (kind == TB_ACT_QUICK_GELU) {
+    const float s = 1.f / (1.f + __expf(-1.702f * u));
+    return s * (1.f + 1.702f * u * (1.f - s));
+  }
+  const float cdf = 0.5f * (1.f + erff(u * 0.70710678118654752f));
+  return cdf + u * 0.3989422804014327f * __expf(-0.5f * u * u);
+}
+// BWD=false: out = act(u);  BWD=true: out = g * act'(u)
+template <bool BWD>
+__global__ void act_kernel(const __half* __restrict__ u, const __half* __restrict__ g,
+                           __half* __restrict__ out, long long n, int kind) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float x = __half2float(u[i]);
+    out[i] = __float2half(BWD ? __half2float(g[i]) * act_bwd(x, kind) : act_fwd(x, kind));
+  }
+}
+
+// ------------------------------------------------------------------ TextBoostModel override
+// forward : rows with ids[b,1]==eos -> null[l,:]; if fixed: position 0 -> null[0,:]   (text_encoder.py:71-86)
+// backward: the overwritten slots receive no gradient -> zero them.
+template <bool BWD>
+__global__ void null_override_kernel(const long long* __restrict__ ids, const float* __restrict__ null_emb,
+                                     float* __restrict__ h, int L, int D, int eos_id, int use_fixed) {
+  const int m = blockIdx.x;
+  const int b = m / L, l = m % L;
+  const bool whole = ids[(long long)b * L + 1] == eos_id;
+  const bool hit = whole || (use_fixed && l == 0);
+  if (!hit) return;
+  for (int c = threadIdx.x; c < D; c += blockDim.x)
+    h[(long long)m * D + c] = BWD ? 0.f : null_emb[(long long)l * D + c];
+}
+
+// fp32 [M,D] -> fp16 copy (encoder_hidden_states.to(unet.dtype), train_textboost.py:1066)
+// ------------------------------------------------------------------ knowledge-preservation loss
+// cos : loss += w * mean_m (1 - cos(h_m, h0_m));  dh = -w/M * ls * (h0/(|h||h0|) - cos h/|h|^2)
+// mse : loss += w * mean((h-h0)^2);               dh = w * 2 (h-h0)/(M*D) * ls
+// dh is ACCUMULATED into dh_acc (the same buffer also receives d ehs from the UNet for other rows).
+__global__ void kpl_kernel(const float* __restrict__ h, const float* __restrict__ h0, int M, int D, int kind,
+                           float weight, const float* __restrict__ loss_scale, float* __restrict__ loss_acc,
+                           float* __restrict__ dh) {
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const int lane = threadIdx.x & 31;
+  const float ls = loss_scale ? *loss_scale : 1.f;
+  const float* a = h + (long long)m * D;
+  const float* b = h0 + (long long)m * D;
+  float* g = dh ? dh + (long long)m * D : nullptr;
+  if (kind == 0) {
+    float ab = 0.f, aa = 0.f, bb = 0.f;
+    for (int c = lane; c < D; c += 32) {
+      ab += a[c] * b[c];
+      aa += a[c] * a[c];
+      bb += b[c] * b[c];
+    }
+    ab = warp_sum_c(ab);
+    aa = warp_sum_c(aa);
+    bb = warp_sum_c(bb);
+    // F.cosine_similarity clamps each norm at eps = 1e-8
+    const float na = fmaxf(sqrtf(aa), 1e-8f), nb = fmaxf(sqrtf(bb), 1e-8f);
+    const float cs = ab / (na * nb);
+    if (lane == 0) atomicAdd(loss_acc, weight * (1.f - cs) / M);
+    if (g) {
+      const float k = -weight / M * ls;
+      for (int c = lane; c < D; c += 32) g[c] += k * (b[c] / (na * nb) - cs * a[c] / (na * na));
+    }
+  } else {
+    float s = 0.f;
+    const float k = weight * 2.f / ((float)M * D) * ls;
+    for (int c = lane; c < D; c += 32) {
+      const float d = a[c] - b[c];
+      s += d * d;
+      if (g) g[c] += k * d;
+    }
+    s = warp_sum_c(s);
+    if (lane == 0) atomicAdd(loss_acc, weight * s / ((float)M * D));
+  }
+}
+
+}  // namespace tb
+
+using namespace tb;
+
+#define TB_ENTER()            \
+  int rc = tb_check_device(); \
+  if (rc) return rc;          \
+  cudaStream_t st = (cudaStream_t)stream
+
+extern "C" int tb_clip_embed(const int64_t* ids, const float* base, const float* added, const float* decay,
+                             const float* pos, float* x, int M, int L, int D, int n_base, void* stream) {
+  TB_ENTER();
+  TB_REQUIRE(ids && base && pos && x, TB_E_ARG, "tb_clip_embed: null pointer");
+  clip_embed_kernel<<<M, 256, 0, st>>>((const long long*)ids, base, added, decay, pos, x, M, L, D, n_base);
+  return check_launch("clip_embed_kernel");
+}
+extern "C" int tb_clip_embed_grad(const int64_t* ids, const float* g, float* grad_rows, int M, int D,
+                                  int n_base, void* stream) {
+  TB_ENTER();
+  TB_REQUIRE(ids && g && grad_rows, TB_E_ARG, "tb_clip_embed_grad: null pointer");
+  clip_embed_grad_kernel<<<M, 256, 0, st>>>((const long long*)ids, g, grad_rows, M, D, n_base);
+  return check_launch("clip_embed_grad_kernel");
+}
+extern "C" int tb_lora_down(void* y_ext, int64_t ld, const float* A, int M, int D, int R, int RPAD,
+                            void* stream) {
+  TB_ENTER();
+  TB_REQUIRE(y_ext && A && R <= 16 && RPAD <= 16 && R <= RPAD, TB_E_ARG, "tb_lora_down: bad args (R=%d)", R);
+  lora_down_kernel<<<(M + 7) / 8, 256, 0, st>>>((__half*)y_ext, ld, A, M, D, R, RPAD);
+  return check_launch("lora_down_kernel");
+}
+extern "C" int tb_lora_pack(const float* Bm, void* Wext, void* WextT, int T, int D, int r, int RPAD,
+                            float scaling, void* stream) {
+  TB_ENTER();
+  TB_REQUIRE(Bm && Wext && WextT && T * r <= RPAD, TB_E_ARG, "tb_lora_pack: bad args");
+  const long long total = (long long)T * D * RPAD;
+  lora_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Bm, (__half*)Wext, (__half*)WextT, T, D,
+                                                                   r, RPAD, scaling);
+  return check_launch("lora_pack_kernel");
+}
+extern "C" int tb_lora_grad(const void* dY, const void* y_ext, const void* dA_ext, int64_t ld, float* dB,
+                            float* dA, int M, int T, int D, int r, float scaling, void* stream) {
+  TB_ENTER();
+  TB_REQUIRE(dY && y_ext && dA_ext && dB && dA && r <= 8 && T * r <= 16, TB_E_ARG, "tb_lora_grad: bad args");
+  const int warps = T * D + D;
+  lora_grad_kernel<<<(warps + 7) / 8, 256, 0, st>>>((const __half*)dY, (const __half*)y_ext,
+                                                   (const __half*)dA_ext, ld, dB, dA, M, T, D, r, scaling);
+  return check_launch("lora_grad_kernel");
+}
+extern "C" int tb_lora_dx(void* dA_ext, int64_t ld, const float* A, int M, int D, int R, void* stream) {
+  TB_ENTER();
+  TB_REQUIRE(dA_ext && A && R <= 16, TB_E_ARG, "tb_lora_dx: bad args");
+  lora_dx_kernel<<<M, 256, 0, st>>>((__half*)dA_ext, ld, A, M, D, R);
+  return check_launch("lora_dx_kernel");
+}
+extern "C" int tb_clip_attn_fwd(const void* qkv, void* out, int B, int L, int D, int heads, void* stream) {
+  TB_ENTER();
+  TB_REQUIRE(qkv && out && D == heads * 64 && L <= 128, TB_E_SHAPE,
+             "tb_clip_attn_fwd: head_dim must be 64 and L <= 128 (D=%d heads=%d L=%d)", D, heads, L);
+  const int smem = L * (L + 1) * 4 + 3 * L * 64 * 2;
+  static bool cfg = false;
+  if (!cfg) {
+    cudaFuncSetAttribute(clip_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 129 * 4 + 3 * 128 * 64 * 2);
+    cfg = true;
+  }
+  clip_attn_kernel<false><<<B * heads, 256, smem, st>>>((const __half*)qkv, nullptr, (__half*)out, L, D,
+                                                        heads, 0.125f);
+  return check_launch("clip_attn_kernel<fwd>");
+}
+extern "C" int tb_clip_attn_bwd(const void* qkv, const void* dO, void* dqkv, int B, int L, int D, int heads,
+                                void* stream) {
+  TB_ENTER();
+  TB_REQUIRE(qkv && dO && dqkv && D == heads * 64 && L <= 128, TB_E_SHAPE, "tb_clip_attn_bwd: bad shape");
+  const int smem = 2 * L * (L + 1) * 4 + 4 * L * 64 * 2;
+  static bool cfg = false;
+  if (!cfg) {
+    cudaFuncSetAttribute(clip_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 129 * 4 + 4 * 128 * 64 * 2);
+    cfg = true;
+  }
+  clip_attn_kernel<true><<<B * heads, 256, smem, st>>>((const __half*)qkv, (const __half*)dO, (__half*)dqkv,
+                                                       L, D, heads, 0.125f);
+  return check_launch("clip_attn_kernel<bwd>");
+}
+extern "C" int tb_act_fwd_f16(const void* u, void* out, int64_t n, int kind, void* stream) {
+  TB_ENTER();
+  TB_REQUIRE(u && out && (kind == TB_ACT_QUICK_GELU || kind == TB_ACT_GELU), TB_E_ARG, "tb_act_fwd_f16: bad args");
+  act_kernel<false><<<(unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, st>>>(
+      (const __half*)u, nullptr, (__half*)out, n, kind);
+  return check_launch("act_kernel<fwd>");
+}
+extern "C" int tb_act_bwd_f16(const void* u, const void* g, void* out, int64_t n, int kind, void* stream) {
+  TB_ENTER();
+  TB_REQUIRE(u && g && out && (kind == TB_ACT_QUICK_GELU || kind == TB_ACT_GELU), TB_E_ARG, "tb_act_bwd_f16: bad args");
+  act_kernel<true><<<(unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, st>>>(
+      (const __half*)u, (const __half*)g, (__half*)out, n, kind);
+  return check_launch("act_kernel<bwd>");
+}
+extern "C" int tb_null_override(const int64_t* ids, const float* null_emb, float* h, int B, int L, int D,
+                                int eos_id, int use_fixed, int backward, void* stream) {
+  TB_ENTER();
+  TB_REQUIRE(ids && h && (backward || null_emb), TB_E_ARG, "tb_null_override: null pointer");
+  if (backward)
+    null_override_kernel<true><<<B * L, 256, 0, st>>>((const long long*)ids, null_emb, h, L, D, eos_id, use_fixed);
+  else
+    null_override_kernel<false><<<B * L, 256, 0, st>>>((const long long*)ids, null_emb, h, L, D, eos_id, use_fixed);
+  return check_launch("null_override_kernel");
+}
+extern "C" int tb_kpl_fwd_bwd(const float* h, const float* h0, int M, int D, int kind, float weight,
+                              const float* loss_scale, float* loss_acc, float* dh_acc, void* stream) {
+  TB_ENTER();
+  TB_REQUIRE(h && h0 && loss_acc && (kind == 0 || kind == 1), TB_E_ARG, "tb_kpl_fwd_bwd: bad args");
+  kpl_kernel<<<(M + 7) / 8, 256, 0, st>>>(h, h0, M, D, kind, weight, loss_scale, loss_acc, dh_acc);
+  return check_launch("kpl_kernel");
+}

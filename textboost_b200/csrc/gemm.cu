@@ -24,8 +24,9 @@ struct GemmParams {
   const __half* bias;
   const __half* rowvec;
   int rows_per_group;
-  const __half* residual;
+  const void* residual;
   long long ldr;
+  int res_f32;
   float alpha;
   int act;
   int out_kind;
@@ -159,7 +160,11 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     const __half* rv = nullptr;
     if (p.rowvec && row_ok) rv = p.rowvec + (m / p.rows_per_group) * (long long)p.N;
     const __half* res = nullptr;
-    if (p.residual && row_ok) res = p.residual + m * p.ldr;
+    const float* res32 = nullptr;
+    if (p.residual && row_ok) {
+      if (p.res_f32) res32 = reinterpret_cast<const float*>(p.residual) + m * p.ldr;
+      else res = reinterpret_cast<const __half*>(p.residual) + m * p.ldr;
+    }
 
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
@@ -208,6 +213,12 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                 v[2 * i] += f.x;
                 v[2 * i + 1] += f.y;
               }
+            }
+            if (res32) {
+              const float4 a0 = *reinterpret_cast<const float4*>(res32 + n);
+              const float4 a1 = *reinterpret_cast<const float4*>(res32 + n + 4);
+              v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
+              v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
             }
             if (p.out_kind == TB_OUT_F16) {
               uint4 o;
@@ -308,6 +319,7 @@ static int fill_epilogue(GemmParams& p, void* C, long long ldc, const tb_epilogu
   p.rows_per_group = 1;
   p.residual = nullptr;
   p.ldr = 0;
+  p.res_f32 = 0;
   p.alpha = 1.f;
   p.act = TB_ACT_NONE;
   p.out_kind = TB_OUT_F16;
@@ -315,8 +327,9 @@ static int fill_epilogue(GemmParams& p, void* C, long long ldc, const tb_epilogu
     p.bias = reinterpret_cast<const __half*>(ep->bias);
     p.rowvec = reinterpret_cast<const __half*>(ep->rowvec);
     p.rows_per_group = ep->rows_per_group > 0 ? ep->rows_per_group : 1;
-    p.residual = reinterpret_cast<const __half*>(ep->residual);
+    p.residual = ep->residual;
     p.ldr = ep->ldr;
+    p.res_f32 = ep->residual_f32;
     p.alpha = ep->alpha;
     p.act = ep->act;
     p.out_kind = ep->out_kind;

@@ -122,7 +122,8 @@ template <int MODE>
 __global__ void gn_apply_kernel(const __half* __restrict__ x, const __half* __restrict__ dy,
                                 const __half* __restrict__ gamma, const __half* __restrict__ beta,
                                 const float* __restrict__ fstats, const float* __restrict__ bstats,
-                                __half* __restrict__ out, GnGeom g, float eps, int silu) {
+                                const __half* __restrict__ add, __half* __restrict__ out, GnGeom g,
+                                float eps, int silu) {
   const int b = blockIdx.y;
   const int v = threadIdx.x % g.nvec, pl = threadIdx.x / g.nvec;
   const int p0 = blockIdx.x * g.ppc;
@@ -167,6 +168,12 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, const __half* __re
         if (silu) dz *= silu_grad(xf[i] * a[i] + bb[i]);
         const float xh = (xf[i] - mean[i]) * rstd[i];
         o[i] = rstd[i] * (dz * gm[i] - m1[i] - xh * m2[i]);
+      }
+      if (add) {
+        float af[8];
+        unpack8(*reinterpret_cast<const uint4*>(add + base + (size_t)p * g.C), af);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += af[i];
       }
     }
     *reinterpret_cast<uint4*>(out + base + (size_t)p * g.C) = pack8(o);
@@ -222,9 +229,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 constexpr int LN_MAXV = 5;  // C <= 1280: at most 5 vectors of 8 per lane
 
 // one warp per row; the row stays in registers (two-pass mean / variance)
-template <typename XT, typename WT>
+template <typename XT, typename WT, typename YT>
 __global__ void ln_fwd_kernel(const XT* __restrict__ x, long long ldx, const WT* __restrict__ gamma,
-                              const WT* __restrict__ beta, __half* __restrict__ y, long long ldy,
+                              const WT* __restrict__ beta, YT* __restrict__ y, long long ldy,
                               float* __restrict__ stats, int M, int C, float eps) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -264,7 +271,7 @@ __global__ void ln_fwd_kernel(const XT* __restrict__ x, long long ldx, const WT*
       load8<WT>(beta + vi * 8, bf);
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = (v[j][i] - mean) * rstd * gf[i] + bf[i];
-      store8<__half>(y + row * ldy + vi * 8, o);
+      store8<YT>(y + row * ldy + vi * 8, o);
     }
   }
   if (lane == 0 && stats) {
@@ -274,8 +281,8 @@ __global__ void ln_fwd_kernel(const XT* __restrict__ x, long long ldx, const WT*
 }
 
 // dx = rstd * (dy*gamma - mean(dy*gamma) - xhat * mean(dy*gamma*xhat))  (+ add)
-template <typename XT, typename WT, typename DT>
-__global__ void ln_bwd_kernel(const __half* __restrict__ dy, long long lddy, const XT* __restrict__ x,
+template <typename DYT, typename XT, typename WT, typename DT>
+__global__ void ln_bwd_kernel(const DYT* __restrict__ dy, long long lddy, const XT* __restrict__ x,
                               long long ldx, const WT* __restrict__ gamma,
                               const float* __restrict__ stats, const DT* __restrict__ add,
                               DT* __restrict__ dx, int M, int C) {
@@ -291,7 +298,7 @@ __global__ void ln_bwd_kernel(const __half* __restrict__ dy, long long lddy, con
     const int vi = lane + j * 32;
     if (vi < nvec) {
       float df[8], gf[8], xf[8];
-      load8<__half>(dy + row * lddy + vi * 8, df);
+      load8<DYT>(dy + row * lddy + vi * 8, df);
       load8<WT>(gamma + vi * 8, gf);
       load8<XT>(x + row * ldx + vi * 8, xf);
 #pragma unroll
@@ -344,14 +351,14 @@ extern "C" int tb_groupnorm_fwd_f16(const void* x, const void* gamma, const void
       (const __half*)x, nullptr, nullptr, nullptr, nullptr, stats, g, eps, silu);
   if ((rc = check_launch("gn_stats_kernel<0>"))) return rc;
   gn_apply_kernel<0><<<grid, threads, 0, st>>>((const __half*)x, nullptr, (const __half*)gamma,
-                                              (const __half*)beta, stats, nullptr, (__half*)y, g, eps,
-                                              silu);
+                                              (const __half*)beta, stats, nullptr, nullptr, (__half*)y, g,
+                                              eps, silu);
   return check_launch("gn_apply_kernel<0>");
 }
 
 extern "C" int tb_groupnorm_bwd_f16(const void* dy, const void* x, const void* gamma, const void* beta,
-                                    const float* stats, float* dstats, void* dx, int B, int HW, int C,
-                                    int G, float eps, int silu, void* stream) {
+                                    const float* stats, float* dstats, const void* add, void* dx, int B,
+                                    int HW, int C, int G, float eps, int silu, void* stream) {
   int rc = tb_check_device();
   if (rc) return rc;
   TB_REQUIRE(dy && x && gamma && beta && stats && dstats && dx, TB_E_ARG,
@@ -369,13 +376,13 @@ extern "C" int tb_groupnorm_bwd_f16(const void* dy, const void* x, const void* g
   if ((rc = check_launch("gn_stats_kernel<1>"))) return rc;
   gn_apply_kernel<1><<<grid, threads, 0, st>>>((const __half*)x, (const __half*)dy,
                                               (const __half*)gamma, (const __half*)beta, stats, dstats,
-                                              (__half*)dx, g, eps, silu);
+                                              (const __half*)add, (__half*)dx, g, eps, silu);
   return check_launch("gn_apply_kernel<1>");
 }
 
 extern "C" int tb_layernorm_fwd(const void* x, int x_f32, int64_t ldx, const void* gamma,
-                                const void* beta, int w_f32, void* y, int64_t ldy, float* stats, int M,
-                                int C, float eps, void* stream) {
+                                const void* beta, int w_f32, void* y, int y_f32, int64_t ldy,
+                                float* stats, int M, int C, float eps, void* stream) {
   int rc = tb_check_device();
   if (rc) return rc;
   TB_REQUIRE(x && gamma && beta && y, TB_E_ARG, "tb_layernorm_fwd: null pointer");
@@ -384,44 +391,45 @@ extern "C" int tb_layernorm_fwd(const void* x, int x_f32, int64_t ldx, const voi
   cudaStream_t st = (cudaStream_t)stream;
   const int wpb = 8;
   const unsigned grid = (unsigned)((M + wpb - 1) / wpb);
-  if (x_f32 && w_f32)
-    ln_fwd_kernel<float, float><<<grid, wpb * 32, 0, st>>>((const float*)x, ldx, (const float*)gamma,
-                                                           (const float*)beta, (__half*)y, ldy, stats,
-                                                           M, C, eps);
-  else if (!x_f32 && !w_f32)
-    ln_fwd_kernel<__half, __half><<<grid, wpb * 32, 0, st>>>((const __half*)x, ldx,
-                                                             (const __half*)gamma, (const __half*)beta,
-                                                             (__half*)y, ldy, stats, M, C, eps);
-  else if (x_f32 && !w_f32)
-    ln_fwd_kernel<float, __half><<<grid, wpb * 32, 0, st>>>((const float*)x, ldx, (const __half*)gamma,
-                                                            (const __half*)beta, (__half*)y, ldy, stats,
-                                                            M, C, eps);
-  else
-    ln_fwd_kernel<__half, float><<<grid, wpb * 32, 0, st>>>((const __half*)x, ldx, (const float*)gamma,
-                                                            (const float*)beta, (__half*)y, ldy, stats,
-                                                            M, C, eps);
+  if (!x_f32 && !w_f32 && !y_f32)
+    ln_fwd_kernel<__half, __half, __half><<<grid, wpb * 32, 0, st>>>(
+        (const __half*)x, ldx, (const __half*)gamma, (const __half*)beta, (__half*)y, ldy, stats, M, C, eps);
+  else if (x_f32 && w_f32 && !y_f32)
+    ln_fwd_kernel<float, float, __half><<<grid, wpb * 32, 0, st>>>(
+        (const float*)x, ldx, (const float*)gamma, (const float*)beta, (__half*)y, ldy, stats, M, C, eps);
+  else if (x_f32 && w_f32 && y_f32)
+    ln_fwd_kernel<float, float, float><<<grid, wpb * 32, 0, st>>>(
+        (const float*)x, ldx, (const float*)gamma, (const float*)beta, (float*)y, ldy, stats, M, C, eps);
+  else {
+    set_error("tb_layernorm_fwd: unsupported type set x_f32=%d w_f32=%d y_f32=%d", x_f32, w_f32, y_f32);
+    return TB_E_ARG;
+  }
   return check_launch("ln_fwd_kernel");
 }
 
-extern "C" int tb_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int x_f32, int64_t ldx,
-                                const void* gamma, int w_f32, const float* stats, const void* add,
-                                void* dx, int dx_f32, int M, int C, void* stream) {
+extern "C" int tb_layernorm_bwd(const void* dy, int dy_f32, int64_t lddy, const void* x, int x_f32,
+                                int64_t ldx, const void* gamma, const float* stats, const void* add,
+                                void* dx, int M, int C, void* stream) {
   int rc = tb_check_device();
   if (rc) return rc;
   TB_REQUIRE(dy && x && gamma && stats && dx, TB_E_ARG, "tb_layernorm_bwd: null pointer");
   TB_REQUIRE(C % 8 == 0 && C <= LN_MAXV * 256, TB_E_SHAPE, "tb_layernorm_bwd: C=%d unsupported", C);
-  TB_REQUIRE(x_f32 == w_f32 && x_f32 == dx_f32, TB_E_ARG,
-             "tb_layernorm_bwd: supported type sets are all-fp16 (UNet) or x/gamma/dx fp32 (CLIP)");
+  TB_REQUIRE(x_f32 || !dy_f32, TB_E_ARG, "tb_layernorm_bwd: fp32 dy requires the fp32 (CLIP) type set");
   cudaStream_t st = (cudaStream_t)stream;
   const int wpb = 8;
   const unsigned grid = (unsigned)((M + wpb - 1) / wpb);
-  if (x_f32)
-    ln_bwd_kernel<float, float, float><<<grid, wpb * 32, 0, st>>>(
+  // UNet: everything fp16.  CLIP: x / gamma / add / dx fp32, dy fp16 (from a GEMM) or fp32 (final LN).
+  if (!x_f32)
+    ln_bwd_kernel<__half, __half, __half, __half><<<grid, wpb * 32, 0, st>>>(
+        (const __half*)dy, lddy, (const __half*)x, ldx, (const __half*)gamma, stats, (const __half*)add,
+        (__half*)dx, M, C);
+  else if (!dy_f32)
+    ln_bwd_kernel<__half, float, float, float><<<grid, wpb * 32, 0, st>>>(
         (const __half*)dy, lddy, (const float*)x, ldx, (const float*)gamma, stats, (const float*)add,
         (float*)dx, M, C);
   else
-    ln_bwd_kernel<__half, __half, __half><<<grid, wpb * 32, 0, st>>>(
-        (const __half*)dy, lddy, (const __half*)x, ldx, (const __half*)gamma, stats,
-        (const __half*)add, (__half*)dx, M, C);
+    ln_bwd_kernel<float, float, float, float><<<grid, wpb * 32, 0, st>>>(
+        (const float*)dy, lddy, (const float*)x, ldx, (const float*)gamma, stats, (const float*)add,
+        (float*)dx, M, C);
   return check_launch("ln_bwd_kernel");
 }
