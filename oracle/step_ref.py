@@ -1,0 +1,107 @@
+"""oracle (test infrastructure): one TextBoost training step in plain PyTorch + autograd.
+
+Follows /root/reference/train_textboost.py line by line:
+  :1041-1052  noise / timesteps / add_noise           (inputs here, so both samplers are testable)
+  :1054-1067  encode_prompt -> unet(...).sample
+  :1070-1075  target (epsilon | v_prediction)
+  :1085-1090  loss = mse(pred.float(), target.float()).mean()
+  :1096-1106  knowledge-preservation loss (cos | mse) on the prior prompts, weight kpl_weight
+  :1108       backward
+  :1109-1117  zero the embedding-gradient rows below min(added_token_ids)
+  :1119-1126  --mixing mask on lora_B grads
+  :1128-1133  clip_grad_norm_(text_model.encoder.parameters(), max_grad_norm)   (LoRA only)
+  :1134-1136  AdamW step (embedding lr = emb_learning_rate, LoRA lr = learning_rate), zero_grad
+  :1138-1149  renormalise the added rows to norm <= mean_norm
+The fp16 autocast / GradScaler of accelerate is NOT modelled: the oracle is the exact-arithmetic
+(fp32, or fp64 when the caller casts the modules) statement of the same function.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import ddpm_ref
+
+
+def lora_named_parameters(te):
+    return [(n, p) for n, p in te.named_parameters() if "lora_" in n]
+
+
+def forward_loss(unet, te, te0, latents, noise, timesteps, input_ids, prior_ids=None, kpl_weight=0.1,
+                 kpl_type="cos", prediction_type="epsilon"):
+    """Returns (loss, model_pred, encoder_hidden_states)."""
+    noisy = ddpm_ref.add_noise(latents, noise, timesteps)
+    ehs = te(input_ids)
+    pred = unet(noisy, timesteps, ehs)
+    if prediction_type == "epsilon":
+        target = noise
+    elif prediction_type == "v_prediction":
+        target = ddpm_ref.get_velocity(latents, noise, timesteps)
+    else:
+        raise ValueError(prediction_type)
+    loss = F.mse_loss(pred.float(), target.float(), reduction="none").mean()
+    if kpl_weight > 0.0 and prior_ids is not None:
+        h = te(prior_ids).float()
+        with torch.no_grad():
+            h0 = te0(prior_ids).float()
+        if kpl_type == "cos":
+            kp = (1 - F.cosine_similarity(h, h0, dim=-1)).mean()
+        else:
+            kp = F.mse_loss(h, h0, reduction="mean")
+        loss = loss + kpl_weight * kp
+    return loss, pred, ehs
+
+
+def reference_step(unet, te, te0, latents, noise, timesteps, input_ids, prior_ids=None, *,
+                   n_base: int, kpl_weight=0.1, kpl_type="cos", prediction_type="epsilon",
+                   optimizer: Optional[torch.optim.Optimizer] = None, max_grad_norm=1.0, mixing=None,
+                   mean_norm: Optional[float] = None) -> Dict[str, torch.Tensor]:
+    """Runs forward + backward (+ the optimiser tail when `optimizer` is given).
+
+    n_base = min(added_token_ids): rows below it never train.  Returns loss, pred, d(ehs) and the
+    gradients that reach the trainable parameters (after the row mask, before clipping).
+    """
+    emb = te.get_input_embeddings().weight
+    for _, p in lora_named_parameters(te):
+        p.grad = None
+    emb.grad = None
+    loss, pred, ehs = forward_loss(unet, te, te0, latents, noise, timesteps, input_ids, prior_ids,
+                                   kpl_weight, kpl_type, prediction_type)
+    ehs.retain_grad()
+    loss.backward()
+    if emb.grad is not None:
+        emb.grad[:n_base] = 0  # :1109-1117
+    if mixing is not None:  # :1119-1126
+        for n, p in lora_named_parameters(te):
+            if "lora_B" in n:
+                if mixing == "object":
+                    p.grad[1::2, :] = 0.0
+                else:
+                    p.grad[0::2, :] = 0.0
+    out = {"loss": loss.detach(), "pred": pred.detach(), "d_ehs": ehs.grad.detach().clone(),
+           "grad_rows": emb.grad[n_base:].detach().clone() if emb.grad is not None else None,
+           "grad_lora": {n: p.grad.detach().clone() for n, p in lora_named_parameters(te)}}
+    if optimizer is not None:
+        if max_grad_norm:
+            out["grad_norm"] = torch.nn.utils.clip_grad_norm_(
+                [p for _, p in lora_named_parameters(te)], max_grad_norm)
+        optimizer.step()
+        optimizer.zero_grad(set_to_none=True)
+        if mean_norm is not None:  # :1138-1149
+            with torch.no_grad():
+                rows = emb[n_base:]
+                v = rows.norm(dim=-1, keepdim=True)
+                out["added_embedding_norm"] = v.mean()
+                emb[n_base:] = torch.minimum(torch.full_like(v, mean_norm), v) / v * rows
+    return out
+
+
+def make_optimizer(te, learning_rate=5e-5, emb_learning_rate=1e-3, betas=(0.9, 0.999), weight_decay=1e-2,
+                   eps=1e-8):
+    """train_textboost.py:829-854."""
+    return torch.optim.AdamW(
+        [{"params": [te.get_input_embeddings().weight], "lr": emb_learning_rate},
+         {"params": [p for _, p in lora_named_parameters(te)]}],
+        lr=learning_rate, betas=betas, weight_decay=weight_decay, eps=eps)

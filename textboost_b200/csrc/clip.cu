@@ -152,9 +152,10 @@ __global__ void clip_attn_kernel(const __half* __restrict__ qkv, const __half* _
                                  __half* __restrict__ out, int L, int D, int heads, float scale) {
   constexpr int HD = 64;
   extern __shared__ float smf[];
-  float* sP = smf;                       // [L][L+1]
-  float* sdS = sP + L * (L + 1);         // [L][L+1] (BWD only)
-  __half* sQ = reinterpret_cast<__half*>(BWD ? sdS + L * (L + 1) : sP + L * (L + 1));
+  const int PS = (L * (L + 1) + 3) & ~3;  // keep the fp16 tiles 16-byte aligned
+  float* sP = smf;                        // [L][L+1]
+  float* sdS = sP + PS;                   // [L][L+1] (BWD only)
+  __half* sQ = reinterpret_cast<__half*>(BWD ? sdS + PS : sP + PS);
   __half* sK = sQ + L * HD;
   __half* sV = sK + L * HD;
   __half* sdO = sV + L * HD;  // BWD only
@@ -399,7 +400,7 @@ extern "C" int tb_clip_attn_fwd(const void* qkv, void* out, int B, int L, int D,
   TB_ENTER();
   TB_REQUIRE(qkv && out && D == heads * 64 && L <= 128, TB_E_SHAPE,
              "tb_clip_attn_fwd: head_dim must be 64 and L <= 128 (D=%d heads=%d L=%d)", D, heads, L);
-  const int smem = L * (L + 1) * 4 + 3 * L * 64 * 2;
+  const int smem = ((L * (L + 1) + 3) & ~3) * 4 + 3 * L * 64 * 2;
   static bool cfg = false;
   if (!cfg) {
     cudaFuncSetAttribute(clip_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 129 * 4 + 3 * 128 * 64 * 2);
@@ -413,7 +414,7 @@ extern "C" int tb_clip_attn_bwd(const void* qkv, const void* dO, void* dqkv, int
                                 void* stream) {
   TB_ENTER();
   TB_REQUIRE(qkv && dO && dqkv && D == heads * 64 && L <= 128, TB_E_SHAPE, "tb_clip_attn_bwd: bad shape");
-  const int smem = 2 * L * (L + 1) * 4 + 4 * L * 64 * 2;
+  const int smem = 2 * ((L * (L + 1) + 3) & ~3) * 4 + 4 * L * 64 * 2;
   static bool cfg = false;
   if (!cfg) {
     cudaFuncSetAttribute(clip_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 129 * 4 + 4 * 128 * 64 * 2);

@@ -1,0 +1,212 @@
+"""Synthetic workload of BASELINE.json: random-init weights at the exact SD-1.5 / SD-2.1 shapes,
+synthetic latents and literal prompt ids.  No checkpoints, datasets or tokenizer files exist offline
+(SURVEY.md §8d), so this is what bench.py, smoke() and the GPU tests run on.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Tuple
+
+import torch
+
+from .clip import ClipConfig, ClipEngine
+from .trainer import TextBoostTrainer
+from .unet import UNetConfig, UNetEngine
+
+BOS, EOS = 49406, 49407
+
+
+# ---------------------------------------------------------------------------------- shapes
+def unet_shapes(cfg: UNetConfig) -> Dict[str, Tuple[int, ...]]:
+    """diffusers UNet2DConditionModel state-dict keys -> shapes."""
+    ch = cfg.block_out_channels
+    T = ch[0] * 4
+    ctx = cfg.cross_attention_dim
+    s: Dict[str, Tuple[int, ...]] = {}
+
+    def conv(p, co, ci, k):
+        s[p + ".weight"] = (co, ci, k, k)
+        s[p + ".bias"] = (co,)
+
+    def lin(p, co, ci, bias=True):
+        s[p + ".weight"] = (co, ci)
+        if bias:
+            s[p + ".bias"] = (co,)
+
+    def norm(p, c):
+        s[p + ".weight"] = (c,)
+        s[p + ".bias"] = (c,)
+
+    def resnet(p, ci, co):
+        norm(p + "norm1", ci)
+        conv(p + "conv1", co, ci, 3)
+        lin(p + "time_emb_proj", co, T)
+        norm(p + "norm2", co)
+        conv(p + "conv2", co, co, 3)
+        if ci != co:
+            conv(p + "conv_shortcut", co, ci, 1)
+
+    def transformer(p, c):
+        norm(p + "norm", c)
+        if cfg.use_linear_projection:
+            lin(p + "proj_in", c, c)
+            lin(p + "proj_out", c, c)
+        else:
+            conv(p + "proj_in", c, c, 1)
+            conv(p + "proj_out", c, c, 1)
+        t = p + "transformer_blocks.0."
+        for n in ("norm1", "norm2", "norm3"):
+            norm(t + n, c)
+        for a, kd in (("attn1", c), ("attn2", ctx)):
+            lin(t + a + ".to_q", c, c, False)
+            lin(t + a + ".to_k", c, kd, False)
+            lin(t + a + ".to_v", c, kd, False)
+            lin(t + a + ".to_out.0", c, c)
+        lin(t + "ff.net.0.proj", 8 * c, c)
+        lin(t + "ff.net.2", c, 4 * c)
+
+    conv("conv_in", ch[0], cfg.in_channels, 3)
+    lin("time_embedding.linear_1", T, ch[0])
+    lin("time_embedding.linear_2", T, T)
+    out = ch[0]
+    for i, c in enumerate(ch):
+        cin, out = out, c
+        for j in range(cfg.layers_per_block):
+            resnet(f"down_blocks.{i}.resnets.{j}.", cin if j == 0 else out, out)
+            if cfg.down_has_attn[i]:
+                transformer(f"down_blocks.{i}.attentions.{j}.", out)
+        if i != len(ch) - 1:
+            conv(f"down_blocks.{i}.downsamplers.0.conv", out, out, 3)
+    resnet("mid_block.resnets.0.", ch[-1], ch[-1])
+    transformer("mid_block.attentions.0.", ch[-1])
+    resnet("mid_block.resnets.1.", ch[-1], ch[-1])
+    rev = list(reversed(ch))
+    rev_attn = list(reversed(cfg.down_has_attn))
+    out = rev[0]
+    n = cfg.layers_per_block + 1
+    for i, c in enumerate(rev):
+        prev, out = out, c
+        cin = rev[min(i + 1, len(ch) - 1)]
+        for j in range(n):
+            skip = cin if j == n - 1 else out
+            rin = prev if j == 0 else out
+            resnet(f"up_blocks.{i}.resnets.{j}.", rin + skip, out)
+            if rev_attn[i]:
+                transformer(f"up_blocks.{i}.attentions.{j}.", out)
+        if i != len(ch) - 1:
+            conv(f"up_blocks.{i}.upsamplers.0.conv", out, out, 3)
+    norm("conv_norm_out", ch[0])
+    conv("conv_out", cfg.out_channels, ch[0], 3)
+    return s
+
+
+def clip_shapes(cfg: ClipConfig, vocab: int) -> Dict[str, Tuple[int, ...]]:
+    D, F = cfg.hidden_size, cfg.intermediate_size
+    s = {"text_model.embeddings.token_embedding.weight": (vocab, D),
+         "text_model.embeddings.position_embedding.weight": (cfg.max_position_embeddings, D)}
+    for l in range(cfg.num_hidden_layers):
+        p = f"text_model.encoder.layers.{l}."
+        for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            s[p + f"self_attn.{n}.weight"] = (D, D)
+            s[p + f"self_attn.{n}.bias"] = (D,)
+        for n in ("layer_norm1", "layer_norm2"):
+            s[p + n + ".weight"] = (D,)
+            s[p + n + ".bias"] = (D,)
+        s[p + "mlp.fc1.weight"] = (F, D)
+        s[p + "mlp.fc1.bias"] = (F,)
+        s[p + "mlp.fc2.weight"] = (D, F)
+        s[p + "mlp.fc2.bias"] = (D,)
+    s["text_model.final_layer_norm.weight"] = (D,)
+    s["text_model.final_layer_norm.bias"] = (D,)
+    return s
+
+
+# ---------------------------------------------------------------------------------- random init
+def random_unet_sd(cfg: UNetConfig, device, seed=0, dtype=torch.float16):
+    """N(0, 1/fan_in) conv/linear weights (residual-branch outputs damped), norm affine 1 + N(0,.1):
+    activations stay O(1) through the ~60 layers (a plain N(0, .02) init collapses the GroupNorm inputs)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    sd = {}
+    for k, shp in unet_shapes(cfg).items():
+        if len(shp) == 1:
+            if "norm" in k and k.endswith("weight"):
+                t = 1.0 + 0.1 * torch.randn(shp, generator=g, device=device)
+            else:
+                t = 0.05 * torch.randn(shp, generator=g, device=device)
+        else:
+            fan_in = math.prod(shp[1:])
+            gain = 0.5 if any(x in k for x in ("conv2.", "to_out.0", "ff.net.2", "proj_out")) else 1.0
+            t = torch.randn(shp, generator=g, device=device) * (gain / math.sqrt(fan_in))
+        sd[k] = t.to(dtype)
+    return sd
+
+
+def random_clip_sd(cfg: ClipConfig, vocab: int, device, seed=0):
+    g = torch.Generator(device=device).manual_seed(seed)
+    sd = {}
+    for k, shp in clip_shapes(cfg, vocab).items():
+        if "layer_norm" in k and k.endswith("weight"):
+            t = 1.0 + 0.1 * torch.randn(shp, generator=g, device=device)
+        elif k.endswith("bias"):
+            t = 0.02 * torch.randn(shp, generator=g, device=device)
+        else:
+            std = 0.02 / math.sqrt(2.0) if ("fc2" in k or "out_proj" in k) else 0.02
+            t = torch.randn(shp, generator=g, device=device) * std
+        sd[k] = t
+    return sd
+
+
+# ---------------------------------------------------------------------------------- inputs
+def instance_ids(B: int, placeholder_id: int, L: int = 77) -> torch.Tensor:
+    """'a <dog> dog' -> [BOS, 320, <placeholder>, 1929, EOS x 73] (CLIP BPE ids; structure is what matters)."""
+    row = torch.full((L,), EOS, dtype=torch.int64)
+    row[0], row[1], row[2], row[3] = BOS, 320, placeholder_id, 1929
+    return row.unsqueeze(0).repeat(B, 1)
+
+
+def prior_ids(B: int, seed: int, L: int = 77, null_prob: float = 0.1) -> torch.Tensor:
+    """[BOS, r_1..r_k, EOS...], r ~ U{1000..40000}, k ~ U{3..20}; ~10 % empty prompts (text_encoder.py:71)."""
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.full((B, L), EOS, dtype=torch.int64)
+    ids[:, 0] = BOS
+    for b in range(B):
+        if torch.rand((), generator=g).item() < null_prob:
+            continue
+        k = int(torch.randint(3, 21, (), generator=g))
+        ids[b, 1:1 + k] = torch.randint(1000, 40001, (k,), generator=g)
+    return ids
+
+
+def batch(B: int, H: int, seed: int, placeholder_id: int, device, rank: int = 0):
+    g = torch.Generator().manual_seed(seed + rank)
+    lat = torch.randn(B, 4, H, H, generator=g)
+    noise = torch.randn(B, 4, H, H, generator=g)
+    t = torch.randint(0, 1000, (B,), generator=g)
+    return {"latents": lat.to(device), "noise": noise.to(device), "timesteps": t.to(device),
+            "input_ids": instance_ids(B, placeholder_id).to(device),
+            "prior_ids": prior_ids(B, seed + 1000 + rank).to(device)}
+
+
+# ---------------------------------------------------------------------------------- whole trainer
+def build_trainer(model: str = "sd15", device="cuda", seed: int = 42, n_added: int = 1, lora_r: int = 4,
+                  kpl_weight: float = 0.1, lora_b_std: float = 0.0, **trainer_kw) -> TextBoostTrainer:
+    """Random-init SD-1.5 ('sd15') or SD-2.1 ('sd21') TextBoost trainer.  n_added rows are appended to the
+    vocabulary and initialised from an existing row (utils.add_token, textboost/utils.py:117-166)."""
+    ucfg = UNetConfig.sd15() if model == "sd15" else UNetConfig.sd21()
+    ccfg = ClipConfig.clip_l() if model == "sd15" else ClipConfig.openclip_h()
+    unet = UNetEngine(ucfg, random_unet_sd(ucfg, device, seed))
+    csd = random_clip_sd(ccfg, ccfg.vocab_size, device, seed + 1)
+    null = torch.randn((ccfg.max_position_embeddings, ccfg.hidden_size),
+                       generator=torch.Generator().manual_seed(seed + 2))
+    te0 = ClipEngine(ccfg, csd, device, lora_r=0) if kpl_weight > 0 else None
+    if te0 is not None:
+        te0.set_null_embedding(null)
+    emb = csd["text_model.embeddings.token_embedding.weight"]
+    csd = dict(csd)
+    csd["text_model.embeddings.token_embedding.weight"] = torch.cat([emb, emb[1929:1929 + n_added]], 0)
+    te = ClipEngine(ccfg, csd, device, lora_r=lora_r, n_base=ccfg.vocab_size, seed=seed + 3)
+    te.set_null_embedding(null)
+    if lora_b_std > 0:  # step-0 dL/dA is exactly 0 with B = 0 (SURVEY.md trap 13): tests use B != 0
+        g = torch.Generator(device=device).manual_seed(seed + 4)
+        te.state.b_segment().copy_(lora_b_std * torch.randn(te.state.n_b, generator=g, device=device))
+    return TextBoostTrainer(unet, te, te0, kpl_weight=kpl_weight, **trainer_kw)

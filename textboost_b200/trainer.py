@@ -1,0 +1,158 @@
+"""One TextBoost training step, fused end to end on the B200 kernels.
+
+Restates the body of the reference loop (/root/reference/train_textboost.py:1041-1149) as a fixed kernel
+sequence with no autograd graph and no host synchronisation:
+
+  add_noise -> text encoder (instance + prior prompts in one pass, LoRA fused) -> UNet forward ->
+  MSE (+grad) -> UNet dgrad to encoder_hidden_states -> frozen text encoder on the prior prompts ->
+  knowledge-preservation loss (+grad) -> text-encoder backward (LoRA A/B + added embedding rows) ->
+  ONE all-reduce of the flat gradient buffer -> fused unscale / clip / AdamW / renorm / GradScaler.
+
+Differences from the reference that do not change results: the DDP all-reduce covers
+only LoRA + added rows (the reference reduces the whole embedding matrix and then zeroes the frozen rows,
+D5); the weight decay of the frozen embedding rows is a lazily applied scalar (D8); instance and prior
+prompts share one encoder pass (the ops are row-independent).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _cabi as C
+from . import ops
+from .clip import ClipEngine
+from .unet import UNetEngine
+
+F16 = torch.float16
+F32 = torch.float32
+
+
+def alphas_cumprod(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, device="cpu"):
+    """SD scheduler config (scaled_linear): DDPMScheduler as used at train_textboost.py:644."""
+    betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=F32) ** 2
+    return torch.cumprod(1.0 - betas, dim=0).to(device)
+
+
+def timestep_probs(acp: torch.Tensor) -> torch.Tensor:
+    """train_textboost.py:991-997 (reachable here; the reference's flag keeps it dead code, D3)."""
+    logsnr = (acp / (1 - acp)).log()
+    w = -logsnr + logsnr.max()
+    return w / w.sum()
+
+
+class TextBoostTrainer:
+    def __init__(self, unet: UNetEngine, text_encoder: ClipEngine,
+                 original_text_encoder: Optional[ClipEngine] = None, *, learning_rate=5e-5,
+                 emb_learning_rate=1e-3, adam_beta1=0.9, adam_beta2=0.999, adam_weight_decay=1e-2,
+                 adam_epsilon=1e-8, max_grad_norm=1.0, kpl_weight=0.1, kpl_type="cos",
+                 prediction_type="epsilon", mixing=None, mean_norm: Optional[float] = None,
+                 mixed_precision="fp16", process_group=None):
+        self.unet, self.te, self.te0 = unet, text_encoder, original_text_encoder
+        self.dev = text_encoder.device
+        self.lr, self.emb_lr = learning_rate, emb_learning_rate
+        self.b1, self.b2, self.wd, self.eps = adam_beta1, adam_beta2, adam_weight_decay, adam_epsilon
+        self.max_grad_norm = max_grad_norm if max_grad_norm is not None else 0.0
+        self.kpl_weight, self.kpl_kind = kpl_weight, {"cos": 0, "mse": 1}[kpl_type]
+        self.v_pred = {"epsilon": False, "v_prediction": True}[prediction_type]
+        self.mixing = mixing
+        assert kpl_weight <= 0 or original_text_encoder is not None
+        st = text_encoder.state
+        self.exp_avg = torch.zeros_like(st.params)
+        self.exp_avg_sq = torch.zeros_like(st.params)
+        # [0] loss scale [1] growth tracker [2] found_inf [3] sum g^2 [4] step [5] frozen-row decay ...
+        self.opt_state = torch.zeros(16, device=self.dev, dtype=F32)
+        self.opt_state[0] = 65536.0 if mixed_precision == "fp16" else 1.0
+        self.opt_state[5] = 1.0
+        text_encoder.decay = self.opt_state[5:6]
+        if mean_norm is None:
+            # train_textboost.py:1017: mean row norm of the resized embedding matrix
+            n = text_encoder.tok_base.norm(dim=-1).sum() + st.rows().norm(dim=-1).sum()
+            mean_norm = float(n / (text_encoder.tok_base.shape[0] + st.n_rows))
+        self.mean_norm = mean_norm
+        self.acp = alphas_cumprod(device=self.dev)
+        self.loss = torch.zeros(1, device=self.dev, dtype=F32)
+        self.added_norm = torch.zeros(1, device=self.dev, dtype=F32)
+        self.pg = process_group
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(process_group)
+        self._graph = None
+
+    # ------------------------------------------------------------------ pieces (also used by tests)
+    def forward_backward(self, latents, noise, timesteps, input_ids, prior_ids=None):
+        """Everything up to (not including) the all-reduce: fills te.state.grads, self.loss."""
+        te, unet = self.te, self.unet
+        B = latents.shape[0]
+        use_kpl = self.kpl_weight > 0 and prior_ids is not None
+        te.pack_lora()
+        noisy, target = ops.add_noise(latents, noise, timesteps, self.acp, self.v_pred)
+        ids = torch.cat([input_ids, prior_ids], 0) if use_kpl else input_ids
+        h = te.forward(ids, save_for_backward=True)  # fp32 [B(+Bp), L, D]
+        Bt, L, D = h.shape
+        ehs = ops.cast_f32_f16(h[:B].view(B * L, D)).view(B, L, D)
+        pred = unet.forward(noisy, timesteps, ehs)
+        self.loss.zero_()
+        scale = self.opt_state[0:1]
+        dpred = ops.mse_fwd_bwd(pred, target, self.loss, 1.0, scale)
+        d_h = torch.zeros((Bt, L, D), device=self.dev, dtype=F32)
+        unet.backward(dpred, d_h[:B])
+        if use_kpl:
+            h0 = self.te0.forward(prior_ids)
+            Mp = (Bt - B) * L
+            C.call("tb_kpl_fwd_bwd", C.ptr(h[B:]), C.ptr(h0), Mp, D, self.kpl_kind, float(self.kpl_weight),
+                   C.ptr(scale), C.ptr(self.loss), C.ptr(d_h[B:]), C.stream_ptr())
+        te.backward(d_h)
+        self._pred = pred
+        return self.loss
+
+    def all_reduce(self):
+        if self.world > 1:
+            torch.distributed.all_reduce(self.te.state.grads, group=self.pg)
+
+    def optimizer_step(self):
+        st = self.te.state
+        if self.mixing is not None and st.n_b:
+            parity = 1 if self.mixing == "object" else 0  # train_textboost.py:1119-1126
+            C.call("tb_optim_mix_mask", C.ptr(st.b_segment(st.grads)), st.n_b, st.D, st.r, parity,
+                   C.stream_ptr())
+        C.call("tb_adamw_fused_step", C.ptr(st.params), C.ptr(st.grads), C.ptr(self.exp_avg),
+               C.ptr(self.exp_avg_sq), st.n_lora, st.n_rows, st.D, self.lr, self.emb_lr, self.b1, self.b2,
+               self.eps, self.wd, self.max_grad_norm, 1.0 / self.world, self.mean_norm,
+               C.ptr(self.opt_state), C.ptr(self.added_norm), C.stream_ptr())
+
+    # ------------------------------------------------------------------ the step
+    def step(self, latents, noise, timesteps, input_ids, prior_ids=None):
+        """latents/noise fp32 [B,4,H,W]; timesteps int64 [B]; ids int64 [B,L].  Returns the device-side
+        loss scalar (fp32[1]); nothing is synchronised."""
+        self.forward_backward(latents, noise, timesteps, input_ids, prior_ids)
+        self.all_reduce()
+        self.optimizer_step()
+        return self.loss
+
+    # ------------------------------------------------------------------ CUDA graph of the whole step
+    def capture(self, latents, noise, timesteps, input_ids, prior_ids=None, warmup=2):
+        """Capture step() into one CUDA graph over static input buffers; returns replay(inputs...)."""
+        static = [t.clone() if t is not None else None
+                  for t in (latents, noise, timesteps, input_ids, prior_ids)]
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self.step(*static)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.step(*static)
+        self._graph = g
+
+        def replay(latents, noise, timesteps, input_ids, prior_ids=None):
+            for dst, src in zip(static, (latents, noise, timesteps, input_ids, prior_ids)):
+                if dst is not None and src is not None and dst.data_ptr() != src.data_ptr():
+                    dst.copy_(src, non_blocking=True)
+            g.replay()
+            return self.loss
+
+        self.static_inputs = static
+        return replay
