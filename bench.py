@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py — training-images/sec of the TextBoost step (BASELINE.json metric) on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]              # this repo's CUDA path
+  python bench.py --impl reference [--gpus N] [--steps K] ...      # the reference path on the host CPU
+
+A "step" is one full TextBoost training step (train_textboost.py:1041-1149) on a synthetic batch of 8
+images per GPU at SD-1.5 shapes: add_noise -> CLIP-L text encoder with rank-4 LoRA (instance + prior
+prompts) -> frozen UNet forward at 64x64 latents -> MSE -> UNet activation-backward to the text
+conditioning -> knowledge-preservation loss vs the frozen encoder -> text-encoder backward -> (all-reduce of
+the flat LoRA+row gradient buffer) -> fused unscale/clip/AdamW/renorm.  Weights are random-init at the exact
+SD-1.5 shapes and inputs are synthetic (no checkpoints or datasets exist offline).
+
+One JSON line on stdout (rank 0).  `value`: inputs resident in HBM, whole step replayed as one CUDA graph,
+timed with CUDA events, max over ranks.  `e2e`: the same step through TextBoostTrainer.step_from_host with
+pinned HOST buffers (H2D of the batch and D2H of the loss inside the timed region, one sync per step).
+`roofline`: the dominant kernel family (tcgen05 implicit-GEMM conv3x3), algorithmic FLOPs / CUDA-event time
+of its launches inside an instrumented step, against MEASURED_PEAKS.json.  `cpu_baseline`: the oracle
+restatement of the reference step (plain PyTorch fp32, autograd) timed on this box's host cores on a
+bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "training-images/sec SD1.5 512^2 bs=8/GPU (full TextBoost step)"
+UNIT = "images/s"
+# SURVEY.md §8(d) / BASELINE.md §2: algorithmic TFLOP per image per step
+TFLOP_PER_IMG = {True: 1.7574, False: 1.7175}  # keyed by KPL on/off
+PER_GPU_BATCH = 8
+LATENT = 64
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
+                "source": "MEASURED_PEAKS.json (measured)"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons, power = [], [], set(), []
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # samples under load = upper half by power draw (the sampler brackets the timed region loosely)
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "power_w_max": max(power), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ CPU baseline (oracle)
+def cpu_reference_step_time(n_images: int, steps: int, warmup: int, use_kpl: bool, budget_s: float):
+    """Time the oracle restatement of the reference step (oracle/step_ref.py: diffusers-0.29 UNet +
+    transformers CLIP + peft LoRA + torch AdamW semantics, fp32, autograd) on the host cores.
+    Returns (images_per_s, ms_per_step, steps_done, threads)."""
+    import torch
+    from oracle import clip_ref, step_ref, unet_ref
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    V = 49408
+    with torch.no_grad():
+        unet = unet_ref.init_unet_(unet_ref.UNet2DConditionModelRef(unet_ref.UNetConfig.sd15()), 0)
+        unet.requires_grad_(False)
+        ccfg = clip_ref.ClipTextConfig.clip_l()
+        te0 = clip_ref.init_clip_(clip_ref.TextBoostModelRef(ccfg), 1)
+        null = torch.randn(77, ccfg.hidden_size, generator=torch.Generator().manual_seed(2))
+        te0.set_null_embedding(null)
+        import copy
+        te = copy.deepcopy(te0)
+        te0.requires_grad_(False)
+        te.resize_token_embeddings(V + 1)
+        te.get_input_embeddings().weight[V:] = te.get_input_embeddings().weight[1929:1930]
+    te.requires_grad_(False)
+    te.add_adapter(r=4)
+    te.get_input_embeddings().weight.requires_grad_(True)
+    opt = step_ref.make_optimizer(te)
+    mean_norm = te.get_input_embeddings().weight.detach().norm(dim=-1).mean().item()
+    from textboost_b200 import synthetic
+    bt = synthetic.batch(n_images, LATENT, 42, V, "cpu")
+
+    def one():
+        step_ref.reference_step(unet, te, te0, bt["latents"], bt["noise"], bt["timesteps"], bt["input_ids"],
+                                bt["prior_ids"] if use_kpl else None, n_base=V, optimizer=opt,
+                                kpl_weight=0.1 if use_kpl else 0.0, mean_norm=mean_norm)
+
+    t_start = time.perf_counter()
+    for _ in range(warmup):
+        one()
+        if time.perf_counter() - t_start > budget_s / 3:
+            break
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        one()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    ms = 1e3 * sum(times) / len(times)
+    return n_images / (ms / 1e3), ms, len(times), threads
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own (CPU) implementation of the path = the oracle port (the
+    reference is pure Python over diffusers/peft/accelerate wheels that are not installable here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    use_kpl = not args.no_kpl
+    n_img = args.ref_images
+    v, ms, done, threads = cpu_reference_step_time(n_img, args.steps, min(args.warmup, 1), use_kpl,
+                                                   budget_s=args.ref_budget_s)
+    sample = (f"{done} timed step(s) of the oracle port (oracle/step_ref.py, fp32 autograd) at bs={n_img} of the same "
+              f"SD-1.5 workload, {threads} torch threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+        "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus, use_kpl, note=f"CPU sample: bs={n_img} per step"),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(n_gpus, use_kpl, note=None):
+    cfg = {
+        "workload": ("SD-1.5 full TextBoost step 512^2 (latents 64x64) bs=8 per GPU fp16, synthetic latents + "
+                     "'a <dog> dog' prompts" + (" + knowledge-preservation (cos, w=0.1) on 8 prior prompts" if use_kpl else "")),
+        "baseline_config": "configs[1]" + (" + configs[2] (KPL on: the reference default kpl_weight=0.1)" if use_kpl else ""),
+        "per_gpu_batch": PER_GPU_BATCH, "global_batch": PER_GPU_BATCH * n_gpus, "latent": LATENT, "tokens": 77,
+        "lora_rank": 4, "added_rows": 1, "parallelism": f"dp{n_gpus}",
+        "l2_policy": "working set per step (3.4 GB weights + ~19 GB activations) >> 126 MB L2; no flush needed",
+    }
+    if note:
+        cfg["note"] = note
+    return cfg
+
+
+# ------------------------------------------------------------------------------------ kernel-family timing
+def kernel_family_timing(trainer, bt):
+    """One eager step with CUDA events around every tensor-core entry point (on the launching stream).
+    Returns {family: {"ms", "tflop", "launches"}}."""
+    import torch
+    from textboost_b200 import ops
+    rec = []
+
+    def wrap(name, fn, flops_of):
+        def inner(*a, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **kw)
+            e1.record()
+            rec.append((name, flops_of(*a, **kw), e0, e1))
+            return out
+        return inner
+
+    def f_conv(x, w, **kw):
+        B, H, W, Cin = x.shape
+        return 2.0 * B * H * W * w.shape[0] * 9 * Cin
+
+    def f_gemm(a, w, **kw):
+        return 2.0 * a.shape[0] * a.shape[1] * w.shape[0]
+
+    def f_attn_fwd(q, k, v, heads, **kw):
+        return 4.0 * q.shape[0] * q.shape[1] * k.shape[1] * q.shape[2]
+
+    def f_attn_bwd(q, k, v, o, do, lse, heads, scale=None, need_dq=True, **kw):
+        return (8.0 if need_dq else 6.0) * q.shape[0] * q.shape[1] * k.shape[1] * q.shape[2]
+
+    saved = {n: getattr(ops, n) for n in ("conv3x3", "gemm", "attn_fwd", "attn_bwd")}
+    ops.conv3x3 = wrap("conv3x3_igemm", saved["conv3x3"], f_conv)
+    ops.gemm = wrap("gemm", saved["gemm"], f_gemm)
+    ops.attn_fwd = wrap("attn_fwd", saved["attn_fwd"], f_attn_fwd)
+    ops.attn_bwd = wrap("attn_bwd", saved["attn_bwd"], f_attn_bwd)
+    try:
+        trainer.step(bt["latents"], bt["noise"], bt["timesteps"], bt["input_ids"], bt["prior_ids"])
+        torch.cuda.synchronize()
+    finally:
+        for n, f in saved.items():
+            setattr(ops, n, f)
+    fam = {}
+    for name, fl, e0, e1 in rec:
+        d = fam.setdefault(name, {"ms": 0.0, "tflop": 0.0, "launches": 0})
+        d["ms"] += e0.elapsed_time(e1)
+        d["tflop"] += fl / 1e12
+        d["launches"] += 1
+    return fam
+
+
+# ------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from textboost_b200 import _cabi, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun: python -m torch.distributed.run --nnodes=1 "
+                             f"--nproc-per-node {args.gpus} --master-addr 127.0.0.1 bench.py --gpus {args.gpus}")
+        raise SystemExit(f"WORLD_SIZE={world} does not match --gpus {args.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the CUDA library is the product and has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _cabi.call("tb_check_device")
+    use_kpl = not args.no_kpl
+    B = PER_GPU_BATCH
+    tr = synthetic.build_trainer("sd15", dev, seed=42, n_added=1, kpl_weight=0.1 if use_kpl else 0.0)
+    V = 49408
+    bt = synthetic.batch(B, LATENT, 42, V, dev, rank=rank)  # seed + rank: each rank its own shard
+    dev_args = (bt["latents"], bt["noise"], bt["timesteps"], bt["input_ids"], bt["prior_ids"] if use_kpl else None)
+    host_args = tuple(t.cpu().pin_memory() if t is not None else None for t in dev_args)
+    h2d = sum(t.numel() * t.element_size() for t in host_args if t is not None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # eager warm-up (also configures kernel attributes) then capture the step as one CUDA graph
+    n0 = _cabi.launch_count
+    tr.step(*dev_args)
+    torch.cuda.synchronize()
+    launches_per_step = _cabi.launch_count - n0 + (1 if world > 1 else 0)
+    graph_ok = True
+    try:
+        replay = tr.capture(*dev_args, warmup=1)
+    except Exception as e:  # keep measuring (eagerly) if capture is not possible, and say so
+        graph_ok = False
+        sys.stderr.write(f"[bench] CUDA-graph capture failed ({e}); timing the eager step\n")
+        tr._graph = None
+
+        def replay(*a):
+            return tr.step(*a)
+
+    for _ in range(args.warmup):
+        replay(*dev_args)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # ---- timed region 1: inputs resident in HBM
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        replay(*dev_args)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    # ---- timed region 2: end to end from pinned host buffers, loss read back every step
+    for _ in range(2):
+        tr.step_from_host(*host_args)
+    barrier()
+    e0.record()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        loss_val = tr.step_from_host(*host_args)
+    e1.record()
+    barrier()
+    ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+    state = tr.opt_state.tolist()
+
+    fam = None
+    cpu_base = None
+    if rank == 0:
+        tr._graph = None
+        fam = kernel_family_timing(tr, bt if use_kpl else {**bt, "prior_ids": None})
+    if world > 1:
+        dist.barrier()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        del tr
+        torch.cuda.empty_cache()
+        v, cms, done, threads = cpu_reference_step_time(args.ref_images, 1, 0, use_kpl, budget_s=120)
+        cpu_base = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                    "sample": f"{done} step of the oracle port (fp32 autograd, torch CPU) at bs={args.ref_images} "
+                              f"of the same SD-1.5 workload ({cms / 1e3:.1f} s); {threads} torch threads"}
+    if rank == 0:
+        peaks = read_peaks()
+        images = B * world
+        value = images / (ms / 1e3)
+        dom = max(fam, key=lambda k: fam[k]["ms"])
+        d = fam[dom]
+        achieved = d["tflop"] / (d["ms"] / 1e3)
+        step_tf = value * TFLOP_PER_IMG[use_kpl]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": workload_config(world, use_kpl),
+            "cuda_graph": graph_ok,
+            "e2e": {"value": images / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e,
+                    "api": "TextBoostTrainer.step_from_host (pinned host batch -> loss float)"},
+            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches_per_step": launches_per_step,
+            "clocks": clocks,
+            "roofline": {
+                "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["tf_sustained"],
+                "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"], "traffic": None,
+                "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                "launches_per_step": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
+                "flop_per_launch_avg": d["tflop"] * 1e12 / d["launches"],
+                "how": "CUDA events around every launch of the family in one instrumented eager step",
+                "families": {k: {"ms": round(v["ms"], 3), "tflops": round(v["tflop"] / (v["ms"] / 1e3), 1),
+                                 "launches": v["launches"]} for k, v in sorted(fam.items())},
+                "step": {"achieved": step_tf, "frac": step_tf / peaks["tf_sustained"],
+                         "tflop_per_image": TFLOP_PER_IMG[use_kpl]},
+            },
+            "cpu_baseline": cpu_base,
+            "loss": loss_val, "loss_scale": state[0], "skipped_steps": state[8],
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-kpl", action="store_true", help="configs[1] without the knowledge-preservation loss")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-images", type=int, default=1, help="images per CPU-baseline step (bounded sample)")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    sys.exit(run_reference_arm(args) if args.impl == "reference" else run_ours(args))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,159 @@
+"""oracle (test infrastructure): build the oracle twin of a synthetic TextBoost trainer and compare one step.
+
+Used only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs: it is
+the checker (or the timed CPU baseline), never something the product path routes through.
+
+``twin_of(trainer)`` rebuilds, from the state dicts a ``synthetic.build_trainer(..., keep_sd=True)`` kept,
+the plain-PyTorch modules of oracle/{unet,clip}_ref.py with identical weights, LoRA factors, added
+embedding rows and null embedding; ``compare_step`` runs oracle/step_ref.reference_step
+(train_textboost.py:1041-1149) and the product's step on the same batch and returns the error of every
+quantity the north star names: noise prediction, loss, LoRA A/B gradients, added-row gradients, and the
+parameters after the optimiser tail.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+
+from . import clip_ref, step_ref, unet_ref
+
+LORA_TARGETS = ("q_proj", "k_proj", "v_proj")
+
+
+def _unet_cfg(c) -> unet_ref.UNetConfig:
+    return unet_ref.UNetConfig(
+        in_channels=c.in_channels, out_channels=c.out_channels, block_out_channels=tuple(c.block_out_channels),
+        layers_per_block=c.layers_per_block, cross_attention_dim=c.cross_attention_dim,
+        attention_head_dim=tuple(c.attention_head_dim), down_has_attn=tuple(c.down_has_attn),
+        norm_num_groups=c.norm_num_groups, norm_eps=c.norm_eps, use_linear_projection=c.use_linear_projection,
+        sample_size=c.sample_size)
+
+
+def _clip_cfg(c, vocab=None) -> clip_ref.ClipTextConfig:
+    return clip_ref.ClipTextConfig(
+        vocab_size=vocab or c.vocab_size, hidden_size=c.hidden_size, intermediate_size=c.intermediate_size,
+        num_hidden_layers=c.num_hidden_layers, num_attention_heads=c.num_attention_heads,
+        hidden_act=c.hidden_act)
+
+
+def rel_max(a: torch.Tensor, b: torch.Tensor) -> float:
+    """max |a-b| / max |b|: the scale-free error used for fp16-vs-fp32 comparisons."""
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+def twin_of(trainer, device="cpu", dtype=torch.float32):
+    """(unet, te, te0, optimizer) oracle modules with the trainer's current weights."""
+    syn = trainer.synthetic
+    assert "unet_sd" in syn, "build the trainer with keep_sd=True"
+    ucfg, ccfg = syn["unet_cfg"], syn["clip_cfg"]
+    V, n_added, r = ccfg.vocab_size, syn["n_added"], syn["lora_r"]
+    unet = unet_ref.UNet2DConditionModelRef(_unet_cfg(ucfg))
+    unet.load_state_dict({k: v.detach().to("cpu", torch.float32) for k, v in syn["unet_sd"].items()})
+    unet = unet.to(device, dtype).requires_grad_(False)
+    csd = {k: v.detach().to("cpu", torch.float32) for k, v in syn["clip_sd"].items()}
+    te_eng = trainer.te
+    null = te_eng.null_embedding.detach().to("cpu", torch.float32)
+    te0 = None
+    if trainer.te0 is not None:
+        te0 = clip_ref.TextBoostModelRef(_clip_cfg(ccfg))
+        te0.load_state_dict(csd, strict=False)
+        te0.set_null_embedding(null.clone())
+        te0 = te0.to(device, dtype).requires_grad_(False)
+    te = clip_ref.TextBoostModelRef(_clip_cfg(ccfg))
+    te.load_state_dict(csd, strict=False)
+    te.resize_token_embeddings(V + n_added)
+    st = te_eng.state
+    with torch.no_grad():
+        te.get_input_embeddings().weight[V:] = st.rows().detach().cpu()
+    te.set_null_embedding(null.clone())
+    te.requires_grad_(False)
+    if r:
+        te.add_adapter(r=r)
+        with torch.no_grad():
+            for l, lyr in enumerate(te.text_model.encoder.layers):
+                for ti, t in enumerate(LORA_TARGETS):
+                    m = getattr(lyr.self_attn, t)
+                    m.lora_A["default"].weight.copy_(st.A(l)[ti * r:(ti + 1) * r].cpu())
+                    m.lora_B["default"].weight.copy_(st.B(l)[ti].cpu())
+    te = te.to(device, dtype)
+    te.get_input_embeddings().weight.requires_grad_(True)
+    opt = step_ref.make_optimizer(te, learning_rate=trainer.lr, emb_learning_rate=trainer.emb_lr,
+                                  betas=(trainer.b1, trainer.b2), weight_decay=trainer.wd, eps=trainer.eps)
+    return unet, te, te0, opt
+
+
+def lora_grads_flat(trainer, ref_grads: Dict[str, torch.Tensor], buf: torch.Tensor):
+    """(ours, ref) concatenated LoRA gradient vectors in the same (layer, target, A|B) order, plus the worst
+    per-tensor max-relative error."""
+    st = trainer.te.state
+    r = st.r
+    ours, refs, worst = [], [], 0.0
+    for l in range(st.n_layers):
+        for ti, t in enumerate(LORA_TARGETS):
+            n = f"text_model.encoder.layers.{l}.self_attn.{t}."
+            ra = ref_grads[n + "lora_A.default.weight"]
+            rb = ref_grads[n + "lora_B.default.weight"]
+            oa, ob = st.A(l, buf)[ti * r:(ti + 1) * r], st.B(l, buf)[ti]
+            worst = max(worst, rel_max(oa, ra), rel_max(ob, rb))
+            ours += [oa.detach().float().cpu().flatten(), ob.detach().float().cpu().flatten()]
+            refs += [ra.detach().float().cpu().flatten(), rb.detach().float().cpu().flatten()]
+    return torch.cat(ours), torch.cat(refs), worst
+
+
+def compare_step(trainer, batch: Dict[str, torch.Tensor], device="cpu", dtype=torch.float32,
+                 with_optimizer=True) -> Dict[str, float]:
+    """Run one step on the product (trainer, CUDA) and on the oracle twin; return error metrics."""
+    unet, te, te0, opt = twin_of(trainer, device, dtype)
+    V = trainer.synthetic["clip_cfg"].vocab_size
+    kind = {0: "cos", 1: "mse"}[trainer.kpl_kind]
+    use_kpl = trainer.kpl_weight > 0 and te0 is not None
+    b = {k: v.to(device) for k, v in batch.items()}
+    ref = step_ref.reference_step(
+        unet, te, te0, b["latents"].to(dtype), b["noise"].to(dtype), b["timesteps"], b["input_ids"],
+        b["prior_ids"] if use_kpl else None, n_base=V, kpl_weight=trainer.kpl_weight, kpl_type=kind,
+        prediction_type="v_prediction" if trainer.v_pred else "epsilon",
+        optimizer=opt if with_optimizer else None, max_grad_norm=trainer.max_grad_norm,
+        mixing=trainer.mixing, mean_norm=trainer.mean_norm)
+    scale = trainer.opt_state[0].item()
+    loss = trainer.forward_backward(batch["latents"], batch["noise"], batch["timesteps"], batch["input_ids"],
+                                    batch["prior_ids"] if use_kpl else None)
+    st = trainer.te.state
+    g = st.grads.detach().clone() / scale
+    if trainer.mixing is not None:  # the product applies the mask inside optimizer_step
+        parity = 1 if trainer.mixing == "object" else 0
+        gb = st.b_segment(g).view(-1, st.D, st.r)
+        gb[:, parity::2, :] = 0
+    out = {"loss": loss.item(), "loss_ref": ref["loss"].item(),
+           "pred_rel": rel_max(trainer._pred, ref["pred"])}
+    go, gr, worst = lora_grads_flat(trainer, ref["grad_lora"], g)
+    out["lora_grad_rel_l2"] = ((go - gr).norm() / gr.norm()).item()
+    out["lora_grad_cos"] = torch.nn.functional.cosine_similarity(go, gr, dim=0).item()
+    out["lora_grad_worst_tensor_rel"] = worst
+    out["lora_grad_ours"], out["lora_grad_ref"] = go, gr
+    if ref["grad_rows"] is not None and st.n_rows:
+        out["row_grad_rel"] = rel_max(st.rows(g), ref["grad_rows"])
+        out["row_grad_ours"], out["row_grad_ref"] = st.rows(g).detach().cpu(), ref["grad_rows"].detach().cpu()
+    if with_optimizer:
+        trainer.all_reduce()
+        trainer.optimizer_step()
+        torch.cuda.synchronize()
+        out["grad_norm"], out["grad_norm_ref"] = trainer.opt_state[7].item(), ref["grad_norm"].item()
+        out["added_norm"], out["added_norm_ref"] = trainer.added_norm.item(), ref["added_embedding_norm"].item()
+        emb = te.get_input_embeddings().weight.detach()
+        out["rows_after_rel"] = rel_max(st.rows(), emb[V:])
+        p_ours, p_ref = [], []
+        r = st.r
+        for l, lyr in enumerate(te.text_model.encoder.layers):
+            for ti, t in enumerate(LORA_TARGETS):
+                m = getattr(lyr.self_attn, t)
+                p_ours += [st.A(l)[ti * r:(ti + 1) * r].detach().cpu().flatten(), st.B(l)[ti].detach().cpu().flatten()]
+                p_ref += [m.lora_A["default"].weight.detach().cpu().flatten(),
+                          m.lora_B["default"].weight.detach().cpu().flatten()]
+        po, pr = torch.cat(p_ours), torch.cat(p_ref)
+        out["lora_param_max_abs_diff"] = (po - pr).abs().max().item()
+        out["frozen_decay"] = trainer.opt_state[5].item()
+        base0 = trainer.synthetic["clip_sd"]["text_model.embeddings.token_embedding.weight"][5].float().cpu()
+        out["frozen_decay_ref"] = (emb[5].cpu() / base0).mean().item()
+    return out

@@ -1,0 +1,300 @@
+"""GPU parity tests, kernel level: every C-ABI entry point on the hot path against a plain PyTorch fp32
+statement of the same op (floating-point kernels; tolerance stated per test).  All calls go through
+libtextboost_b200.so via textboost_b200.ops (ctypes)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+dev = "cuda"
+F16 = torch.float16
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu(built_lib):
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    from textboost_b200 import _cabi
+    _cabi.call("tb_check_device")  # fails loudly if the library cannot run here
+
+
+def relerr(a, b):
+    return ((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-9)).item()
+
+
+# fp16 inputs, fp32 accumulation, fp16 output: one rounding of the result => 2^-11 ~ 4.9e-4 of the max
+TOL_GEMM = 2e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 32, 64), (128, 256, 128), (256, 160, 320), (616, 768, 784),
+                                   (8, 1280, 320), (32768, 320, 320), (2048, 10240, 1280), (1000, 136, 72),
+                                   (616, 2304, 768), (77, 1280, 768)])
+def test_gemm(M, N, K):
+    from textboost_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(M + N + K)
+    a = torch.randn(M, K, device=dev, dtype=F16, generator=g)
+    w = torch.randn(N, K, device=dev, dtype=F16, generator=g) / K ** 0.5
+    out = ops.gemm(a, w)
+    assert relerr(out, a.float() @ w.float().t()) < TOL_GEMM
+
+
+def test_gemm_epilogues_and_strides():
+    from textboost_b200 import _cabi as C, ops
+    torch.manual_seed(0)
+    M, N, K = 1024, 320, 640
+    big = torch.randn(M, K + 64, device=dev, dtype=F16)
+    a = big[:, 32:32 + K]  # strided A view (row stride > K), 64-byte aligned start
+    w = torch.randn(N, K, device=dev, dtype=F16) / K ** 0.5
+    bias = torch.randn(N, device=dev, dtype=F16)
+    rowvec = torch.randn(M // 256, N, device=dev, dtype=F16)
+    res = torch.randn(M, N, device=dev, dtype=F16)
+    ref = F.silu(0.5 * (a.float() @ w.float().t()) + bias.float() + rowvec.float().repeat_interleave(256, 0)) + res.float()
+    out = ops.gemm(a, w, bias=bias, rowvec=rowvec, rows_per_group=256, residual=res, alpha=0.5, act=C.TB_ACT_SILU)
+    assert relerr(out, ref) < TOL_GEMM
+    acc = torch.ones(M, N, device=dev, dtype=torch.float32)
+    ops.gemm(a, w, out=acc, out_kind=C.TB_OUT_F32_ACC)
+    assert relerr(acc, 1.0 + a.float() @ w.float().t()) < 1e-5
+    res32 = torch.randn(M, N, device=dev, dtype=torch.float32)
+    o32 = ops.gemm(a, w, bias=bias, residual=res32, out_kind=C.TB_OUT_F32)
+    assert relerr(o32, a.float() @ w.float().t() + bias.float() + res32) < 1e-5
+    for act, f in [(C.TB_ACT_QUICK_GELU, lambda x: x * torch.sigmoid(1.702 * x)), (C.TB_ACT_GELU, F.gelu)]:
+        out = ops.gemm(a, w, bias=bias, act=act)
+        assert relerr(out, f(a.float() @ w.float().t() + bias.float())) < TOL_GEMM
+
+
+def test_gemm_rejects_bad_arguments():
+    from textboost_b200 import ops
+    a = torch.randn(16, 20, device=dev, dtype=F16)  # K % 8 != 0
+    w = torch.randn(8, 20, device=dev, dtype=F16)
+    with pytest.raises(RuntimeError, match="tb_gemm_f16"):
+        ops.gemm(a, w)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 8, 8, 64, 64), (2, 8, 8, 128, 160), (2, 16, 16, 64, 128),
+                                            (1, 32, 32, 64, 320), (1, 64, 64, 64, 32), (3, 8, 8, 64, 64),
+                                            (2, 64, 64, 320, 320), (8, 8, 8, 2560, 1280), (2, 64, 64, 960, 320)])
+def test_conv3x3(B, H, W, Cin, Cout):
+    from textboost_b200 import ops
+    from textboost_b200.unet import _conv_dgrad_weight, _conv_fwd_weight
+    g = torch.Generator(device=dev).manual_seed(B * H + Cin)
+    x = torch.randn(B, H, W, Cin, device=dev, dtype=F16, generator=g)
+    wt = torch.randn(Cout, Cin, 3, 3, device=dev, dtype=F16, generator=g) / (9 * Cin) ** 0.5
+    bias = torch.randn(Cout, device=dev, dtype=F16, generator=g)
+    xr = x.permute(0, 3, 1, 2).float().requires_grad_(True)
+    ref = F.conv2d(xr, wt.float(), bias.float(), padding=1)
+    out = ops.conv3x3(x, _conv_fwd_weight(wt), bias=bias)
+    assert relerr(out, ref.permute(0, 2, 3, 1)) < TOL_GEMM
+    if Cout % 64 == 0:  # input gradient = the same kernel on the flipped / transposed weight
+        dy = torch.randn(B, H, W, Cout, device=dev, dtype=F16, generator=g)
+        ref.backward(dy.permute(0, 3, 1, 2).float())
+        dx = ops.conv3x3(dy, _conv_dgrad_weight(wt))
+        assert relerr(dx, xr.grad.permute(0, 2, 3, 1)) < TOL_GEMM
+
+
+def test_strided_conv_and_upsample_paths():
+    """Downsample2D (im2col + GEMM / zero-stuff + conv dgrad) and Upsample2D (nearest x2 and its adjoint)."""
+    from textboost_b200 import ops
+    from textboost_b200.unet import _Conv3
+    torch.manual_seed(1)
+    B, H, Cc = 2, 16, 64
+    x = torch.randn(B, H, H, Cc, device=dev, dtype=F16)
+    wt = torch.randn(Cc, Cc, 3, 3, device=dev, dtype=F16) / (9 * Cc) ** 0.5
+    bias = torch.randn(Cc, device=dev, dtype=F16)
+    conv = _Conv3(wt, bias)
+    xr = x.permute(0, 3, 1, 2).float().requires_grad_(True)
+    ref = F.conv2d(xr, wt.float(), bias.float(), stride=2, padding=1)
+    out = ops.gemm(ops.im2col3x3s2(x), conv.wk, bias=bias).view(B, H // 2, H // 2, Cc)
+    assert relerr(out, ref.permute(0, 2, 3, 1)) < TOL_GEMM
+    dy = torch.randn(B, H // 2, H // 2, Cc, device=dev, dtype=F16)
+    ref.backward(dy.permute(0, 3, 1, 2).float())
+    dx = conv.dgrad(ops.zero_stuff2x(dy))
+    assert relerr(dx, xr.grad.permute(0, 2, 3, 1)) < TOL_GEMM
+    up = ops.upsample2x(x)
+    assert torch.equal(up, x.repeat_interleave(2, 1).repeat_interleave(2, 2))
+    dup = torch.randn(B, 2 * H, 2 * H, Cc, device=dev, dtype=F16)
+    ref_d = dup.float().view(B, H, 2, H, 2, Cc).sum((2, 4))
+    assert relerr(ops.upsample2x_bwd(dup), ref_d) < 1e-3
+
+
+# attention: P is rounded to fp16 before P V (as torch SDPA's flash kernels do); outputs fp16
+TOL_ATTN = 3e-3
+
+
+@pytest.mark.parametrize("B,H,Nq,Nk,d", [(1, 1, 128, 128, 64), (1, 2, 128, 128, 40), (2, 2, 256, 256, 40),
+                                         (1, 2, 256, 77, 40), (1, 2, 64, 64, 160), (2, 2, 256, 256, 160),
+                                         (1, 2, 256, 77, 160), (1, 2, 300, 200, 80), (2, 8, 1024, 1024, 80),
+                                         (1, 8, 4096, 4096, 40), (2, 8, 4096, 77, 40), (1, 5, 2304, 2304, 64)])
+def test_attention_fwd_bwd(B, H, Nq, Nk, d):
+    from textboost_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(Nq + Nk + d)
+    Cc = H * d
+    if Nq == Nk:
+        qkv = torch.randn(B, Nq, 3 * Cc, device=dev, dtype=F16, generator=g)
+        q, k, v = qkv[..., :Cc], qkv[..., Cc:2 * Cc], qkv[..., 2 * Cc:]
+    else:
+        q = torch.randn(B, Nq, Cc, device=dev, dtype=F16, generator=g)
+        kv = torch.randn(B, Nk, 2 * Cc, device=dev, dtype=F16, generator=g)
+        k, v = kv[..., :Cc], kv[..., Cc:]
+    do = torch.randn(B, Nq, Cc, device=dev, dtype=F16, generator=g)
+
+    def heads(t):
+        return t.reshape(B, -1, H, d).transpose(1, 2).float().detach().requires_grad_(True)
+
+    qr, kr, vr = heads(q), heads(k), heads(v)
+    s = (qr @ kr.transpose(-1, -2)) * d ** -0.5
+    oref = torch.softmax(s, -1) @ vr
+    oref.backward(do.reshape(B, Nq, H, d).transpose(1, 2).float())
+    o, lse = ops.attn_fwd(q, k, v, H)
+    assert relerr(o, oref.transpose(1, 2).reshape(B, Nq, Cc)) < TOL_ATTN
+    lse_ref = torch.logsumexp(s.detach(), -1) * math.log2(math.e)
+    assert (lse - lse_ref).abs().max().item() < 2e-2
+    dq, dk, dv = ops.attn_bwd(q, k, v, o, do, lse, H)
+    assert relerr(dq, qr.grad.transpose(1, 2).reshape(B, Nq, Cc)) < TOL_ATTN
+    assert relerr(dk, kr.grad.transpose(1, 2).reshape(B, Nk, Cc)) < TOL_ATTN
+    assert relerr(dv, vr.grad.transpose(1, 2).reshape(B, Nk, Cc)) < TOL_ATTN
+    dq2, dk2, dv2 = ops.attn_bwd(q, k, v, o, do, lse, H, need_dq=False)  # first cross-attention: dK/dV only
+    assert dq2 is None and torch.equal(dk2, dk) and torch.equal(dv2, dv)
+
+
+@pytest.mark.parametrize("B,HW,Cc,silu", [(2, 64, 64, True), (2, 4096, 320, True), (3, 1024, 640, False),
+                                          (2, 256, 1920, True), (2, 64, 2560, True)])
+def test_groupnorm_fwd_bwd(B, HW, Cc, silu):
+    from textboost_b200 import ops
+    torch.manual_seed(HW + Cc)
+    x = (torch.randn(B, HW, Cc, device=dev) * 1.5 + 0.3).to(F16)
+    gamma = (1 + 0.1 * torch.randn(Cc, device=dev)).to(F16)
+    beta = (0.1 * torch.randn(Cc, device=dev)).to(F16)
+    dy = torch.randn(B, HW, Cc, device=dev, dtype=F16)
+    add = torch.randn(B, HW, Cc, device=dev, dtype=F16)
+    xr = x.float().transpose(1, 2).requires_grad_(True)
+    yr = F.group_norm(xr, 32, gamma.float(), beta.float(), 1e-5)
+    if silu:
+        yr = F.silu(yr)
+    yr.backward(dy.float().transpose(1, 2))
+    y, st = ops.groupnorm(x, gamma, beta, 32, 1e-5, silu)
+    assert relerr(y, yr.transpose(1, 2)) < 2e-3
+    dx = ops.groupnorm_bwd(dy, x, gamma, beta, st, 32, 1e-5, silu, add=add)
+    assert relerr(dx, xr.grad.transpose(1, 2) + add.float()) < 3e-3
+
+
+@pytest.mark.parametrize("M,Cc,f32", [(512, 320, False), (77, 1280, False), (616, 768, True), (154, 1024, True)])
+def test_layernorm_fwd_bwd(M, Cc, f32):
+    from textboost_b200 import ops
+    torch.manual_seed(M + Cc)
+    dt = torch.float32 if f32 else F16
+    x = (torch.randn(M, Cc, device=dev) * 2 + 0.5).to(dt)
+    gamma = (1 + 0.1 * torch.randn(Cc, device=dev)).to(dt)
+    beta = (0.1 * torch.randn(Cc, device=dev)).to(dt)
+    dy = torch.randn(M, Cc, device=dev, dtype=F16)
+    add = torch.randn(M, Cc, device=dev, dtype=dt)
+    xr = x.float().requires_grad_(True)
+    yr = F.layer_norm(xr, (Cc,), gamma.float(), beta.float(), 1e-5)
+    yr.backward(dy.float())
+    y, st = ops.layernorm(x, gamma, beta)
+    assert relerr(y, yr) < 2e-3
+    dx = ops.layernorm_bwd(dy, x, gamma, st, add=add)
+    assert relerr(dx, xr.grad + add.float()) < (1e-5 if f32 else 3e-3)
+
+
+def test_elementwise_ops():
+    from textboost_b200 import ops
+    torch.manual_seed(3)
+    h = torch.randn(300, 2 * 640, device=dev, dtype=F16)
+    hr = h.float().requires_grad_(True)
+    a, gate = hr.chunk(2, -1)
+    gr = a * F.gelu(gate)
+    dg = torch.randn(300, 640, device=dev, dtype=F16)
+    gr.backward(dg.float())
+    assert relerr(ops.geglu(h), gr) < 2e-3
+    assert relerr(ops.geglu_bwd(dg, h), hr.grad) < 3e-3
+    t = torch.tensor([0, 1, 500, 999], device=dev)
+    te = ops.timestep_embedding(t, 320)
+    fr = torch.exp(-math.log(10000.0) * torch.arange(160, device=dev).float() / 160)
+    ref = torch.cat([torch.cos(t[:, None].float() * fr), torch.sin(t[:, None].float() * fr)], -1)
+    assert (te.float() - ref).abs().max() < 2e-3
+    # DDPM add_noise / velocity target (train_textboost.py:1052, 1070-1075)
+    from textboost_b200.trainer import alphas_cumprod
+    acp = alphas_cumprod(device=dev)
+    x0, eps = torch.randn(4, 4, 16, 16, device=dev), torch.randn(4, 4, 16, 16, device=dev)
+    sa, sb = acp[t].sqrt().view(-1, 1, 1, 1), (1 - acp[t]).sqrt().view(-1, 1, 1, 1)
+    noisy, target = ops.add_noise(x0, eps, t, acp, v_prediction=True)
+    assert relerr(noisy, sa * x0 + sb * eps) < 1e-3
+    torch.testing.assert_close(target, sa * eps - sb * x0, rtol=1e-5, atol=1e-6)
+    noisy, target = ops.add_noise(x0, eps, t, acp, v_prediction=False)
+    assert torch.equal(target, eps)
+    # MSE forward + gradient with a loss scale
+    pred = torch.randn(4, 4, 16, 16, device=dev, dtype=F16)
+    loss = torch.zeros(1, device=dev)
+    scale = torch.full((1,), 128.0, device=dev)
+    dpred = ops.mse_fwd_bwd(pred, target, loss, 1.0, scale)
+    torch.testing.assert_close(loss[0], F.mse_loss(pred.float(), target), rtol=1e-5, atol=1e-6)
+    assert relerr(dpred, 128.0 * 2 * (pred.float() - target) / pred.numel()) < 1e-3
+
+
+def test_conv_in_out():
+    from textboost_b200 import ops
+    torch.manual_seed(4)
+    x = torch.randn(2, 4, 16, 16, device=dev, dtype=F16)
+    w = torch.randn(64, 4, 3, 3, device=dev, dtype=F16) / 6
+    b = torch.randn(64, device=dev, dtype=F16)
+    y = ops.conv_in(x, w, b)
+    assert relerr(y, F.conv2d(x.float(), w.float(), b.float(), padding=1).permute(0, 2, 3, 1)) < TOL_GEMM
+    h = torch.randn(2, 16, 16, 64, device=dev, dtype=F16)
+    wo = torch.randn(4, 64, 3, 3, device=dev, dtype=F16) / 24
+    bo = torch.randn(4, device=dev, dtype=F16)
+    hr = h.float().permute(0, 3, 1, 2).requires_grad_(True)
+    ref = F.conv2d(hr, wo.float(), bo.float(), padding=1)
+    assert relerr(ops.conv_out(h, wo, bo), ref) < TOL_GEMM
+    dy = torch.randn(2, 4, 16, 16, device=dev, dtype=F16)
+    ref.backward(dy.float())
+    assert relerr(ops.conv_out_bwd(dy, wo), hr.grad.permute(0, 2, 3, 1)) < TOL_GEMM
+
+
+def test_fused_adamw_matches_torch():
+    """tb_adamw_fused_step == GradScaler.unscale_ + clip_grad_norm_(LoRA only) + torch.optim.AdamW + renorm
+    (train_textboost.py:1128-1149), over several steps, including an inf step that must be skipped."""
+    from textboost_b200 import _cabi as C
+    torch.manual_seed(5)
+    n_lora, n_rows, D = 4096, 3, 64
+    n = n_lora + n_rows * D
+    p = torch.randn(n, device=dev) * 0.05
+    lora_ref = torch.nn.Parameter(p[:n_lora].clone())
+    rows_ref = torch.nn.Parameter(p[n_lora:].clone().view(n_rows, D))
+    opt = torch.optim.AdamW([{"params": [rows_ref], "lr": 1e-3}, {"params": [lora_ref]}], lr=1e-4,
+                            betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)
+    m, v = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    state = torch.zeros(16, device=dev)
+    state[0], state[5] = 1024.0, 1.0
+    mean_norm = 0.3
+    norm_out = torch.zeros(1, device=dev)
+    world = 2
+    for step in range(6):
+        g = torch.randn(n, device=dev) * (3.0 if step == 1 else 0.01)
+        scale = state[0].item()
+        grads = g * scale * world  # as if summed over `world` ranks holding the same gradient
+        if step == 3:
+            grads[7] = float("inf")
+        before = p.clone()
+        C.call("tb_adamw_fused_step", C.ptr(p), C.ptr(grads), C.ptr(m), C.ptr(v), n_lora, n_rows, D, 1e-4, 1e-3,
+               0.9, 0.999, 1e-8, 1e-2, 1.0, 1.0 / world, mean_norm, C.ptr(state), C.ptr(norm_out), C.stream_ptr())
+        torch.cuda.synchronize()
+        assert torch.count_nonzero(grads) == 0  # zero_grad fused
+        if step == 3:
+            assert torch.equal(p[:n_lora], before[:n_lora]) and state[0].item() == scale / 2 and state[8].item() == 1
+            continue
+        lora_ref.grad, rows_ref.grad = g[:n_lora].clone(), g[n_lora:].clone().view(n_rows, D)
+        gn = torch.nn.utils.clip_grad_norm_([lora_ref], 1.0)
+        opt.step()
+        with torch.no_grad():
+            nv = rows_ref.norm(dim=-1, keepdim=True)
+            rows_ref.copy_(torch.minimum(torch.full_like(nv, mean_norm), nv) / nv * rows_ref)
+        assert abs(state[7].item() - gn.item()) < 1e-4 * gn.item()
+        torch.testing.assert_close(p[:n_lora], lora_ref.detach(), rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(p[n_lora:].view(n_rows, D), rows_ref.detach(), rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(norm_out[0], nv.mean(), rtol=1e-5, atol=1e-7)
+    assert state[4].item() == 5 and abs(state[5].item() - (1 - 1e-3 * 1e-2) ** 5) < 1e-6

@@ -115,10 +115,18 @@ def last_error() -> str:
     return lib().tb_last_error().decode(errors="replace")
 
 
+# kernels (and memset nodes) one call of each entry point enqueues; entry points not listed launch one
+_KERNELS_PER_CALL = {"tb_groupnorm_fwd_f16": 3, "tb_groupnorm_bwd_f16": 3, "tb_attn_bwd_f16": 2,
+                     "tb_adamw_fused_step": 3, "tb_version": 0, "tb_check_device": 0}
+launch_count = 0  # GPU launches enqueued through this binding since import (bench.py reports the delta)
+
+
 def call(name: str, *args):
+    global launch_count
     rc = getattr(lib(), name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {last_error()}")
+    launch_count += _KERNELS_PER_CALL.get(name, 1)
 
 
 def stream_ptr():

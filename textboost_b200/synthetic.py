@@ -188,13 +188,29 @@ def batch(B: int, H: int, seed: int, placeholder_id: int, device, rank: int = 0)
 
 
 # ---------------------------------------------------------------------------------- whole trainer
+def model_configs(model: str):
+    """'sd15' (config 2/3/4), 'sd21' (config 5: SD-2.x widths + OpenCLIP-H) or 'tiny' (same topology,
+    small widths: smoke() and the oracle-speed parity tests)."""
+    if model == "sd15":
+        return UNetConfig.sd15(), ClipConfig.clip_l()
+    if model == "sd21":
+        return UNetConfig.sd21(), ClipConfig.openclip_h()
+    if model == "tiny":
+        return (UNetConfig(block_out_channels=(64, 128, 128, 128), attention_head_dim=(2, 2, 2, 2),
+                           cross_attention_dim=128, sample_size=16),
+                ClipConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2))
+    raise ValueError(model)
+
+
 def build_trainer(model: str = "sd15", device="cuda", seed: int = 42, n_added: int = 1, lora_r: int = 4,
-                  kpl_weight: float = 0.1, lora_b_std: float = 0.0, **trainer_kw) -> TextBoostTrainer:
-    """Random-init SD-1.5 ('sd15') or SD-2.1 ('sd21') TextBoost trainer.  n_added rows are appended to the
-    vocabulary and initialised from an existing row (utils.add_token, textboost/utils.py:117-166)."""
-    ucfg = UNetConfig.sd15() if model == "sd15" else UNetConfig.sd21()
-    ccfg = ClipConfig.clip_l() if model == "sd15" else ClipConfig.openclip_h()
-    unet = UNetEngine(ucfg, random_unet_sd(ucfg, device, seed))
+                  kpl_weight: float = 0.1, lora_b_std: float = 0.0, keep_sd: bool = False,
+                  **trainer_kw) -> TextBoostTrainer:
+    """Random-init TextBoost trainer.  n_added rows are appended to the vocabulary and initialised from an
+    existing row (utils.add_token, textboost/utils.py:117-166).  keep_sd=True stashes the generated
+    state dicts on ``trainer.synthetic`` so a checker can rebuild the same model elsewhere."""
+    ucfg, ccfg = model_configs(model)
+    usd = random_unet_sd(ucfg, device, seed)
+    unet = UNetEngine(ucfg, usd)
     csd = random_clip_sd(ccfg, ccfg.vocab_size, device, seed + 1)
     null = torch.randn((ccfg.max_position_embeddings, ccfg.hidden_size),
                        generator=torch.Generator().manual_seed(seed + 2))
@@ -202,11 +218,16 @@ def build_trainer(model: str = "sd15", device="cuda", seed: int = 42, n_added: i
     if te0 is not None:
         te0.set_null_embedding(null)
     emb = csd["text_model.embeddings.token_embedding.weight"]
-    csd = dict(csd)
-    csd["text_model.embeddings.token_embedding.weight"] = torch.cat([emb, emb[1929:1929 + n_added]], 0)
-    te = ClipEngine(ccfg, csd, device, lora_r=lora_r, n_base=ccfg.vocab_size, seed=seed + 3)
+    csd_t = dict(csd)
+    csd_t["text_model.embeddings.token_embedding.weight"] = torch.cat([emb, emb[1929:1929 + n_added]], 0)
+    te = ClipEngine(ccfg, csd_t, device, lora_r=lora_r, n_base=ccfg.vocab_size, seed=seed + 3)
     te.set_null_embedding(null)
     if lora_b_std > 0:  # step-0 dL/dA is exactly 0 with B = 0 (SURVEY.md trap 13): tests use B != 0
         g = torch.Generator(device=device).manual_seed(seed + 4)
         te.state.b_segment().copy_(lora_b_std * torch.randn(te.state.n_b, generator=g, device=device))
-    return TextBoostTrainer(unet, te, te0, kpl_weight=kpl_weight, **trainer_kw)
+    tr = TextBoostTrainer(unet, te, te0, kpl_weight=kpl_weight, **trainer_kw)
+    tr.synthetic = {"model": model, "unet_cfg": ucfg, "clip_cfg": ccfg, "n_added": n_added, "lora_r": lora_r,
+                    "null": null}
+    if keep_sd:
+        tr.synthetic.update(unet_sd=usd, clip_sd=csd)
+    return tr

@@ -22,6 +22,7 @@ import torch
 from . import _cabi as C
 from . import ops
 from .clip import ClipEngine
+from .dp import GradSync
 from .unet import UNetEngine
 
 F16 = torch.float16
@@ -73,10 +74,8 @@ class TextBoostTrainer:
         self.acp = alphas_cumprod(device=self.dev)
         self.loss = torch.zeros(1, device=self.dev, dtype=F32)
         self.added_norm = torch.zeros(1, device=self.dev, dtype=F32)
-        self.pg = process_group
-        self.world = 1
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            self.world = torch.distributed.get_world_size(process_group)
+        self.sync = GradSync(process_group)
+        self.world = self.sync.world
         self._graph = None
 
     # ------------------------------------------------------------------ pieces (also used by tests)
@@ -107,8 +106,7 @@ class TextBoostTrainer:
         return self.loss
 
     def all_reduce(self):
-        if self.world > 1:
-            torch.distributed.all_reduce(self.te.state.grads, group=self.pg)
+        self.sync.all_reduce_(self.te.state.grads)
 
     def optimizer_step(self):
         st = self.te.state
@@ -155,4 +153,25 @@ class TextBoostTrainer:
             return self.loss
 
         self.static_inputs = static
+        self._replay = replay
         return replay
+
+    # ------------------------------------------------------------------ host-facing step
+    def step_from_host(self, latents, noise, timesteps, input_ids, prior_ids=None) -> float:
+        """One training step from HOST tensors (pinned memory makes the copies asynchronous): copies the
+        batch to the device, runs the step (graph replay once capture() has been called) and reads the loss
+        back, like the reference loop's ``loss.detach().item()`` (train_textboost.py:1230)."""
+        host = (latents, noise, timesteps, input_ids, prior_ids)
+        if self._graph is not None:
+            for dst, src in zip(self.static_inputs, host):
+                if dst is not None and src is not None:
+                    dst.copy_(src, non_blocking=True)
+            self._graph.replay()
+        else:
+            dev = [t.to(self.dev, non_blocking=True) if t is not None else None for t in host]
+            self.step(*dev)
+        if getattr(self, "_loss_host", None) is None:
+            self._loss_host = torch.empty(1, dtype=F32, pin_memory=True)
+        self._loss_host.copy_(self.loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self._loss_host[0])
