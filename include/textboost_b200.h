@@ -81,21 +81,27 @@ int tb_conv3x3_f16(const void* x, const void* w, void* y, int B, int H, int W, i
                    const tb_epilogue* ep, void* stream);
 
 /* ---- UNet attention (flash, tcgen05/TMEM) ------------------------------------------------------
- * softmax(Q K^T * scale) V per (batch, head); no mask, no dropout: diffusers AttnProcessor2_0 ->
- * F.scaled_dot_product_attention inside unet(...) at train_textboost.py:1063 (forward) and its
- * autograd backward at :1108.  q/k/v/o are token-major fp16 [B, N, ld*] with head h occupying columns
+ * softmax(Q K^T * scale) V per (batch, head); no dropout; causal=0: no mask (diffusers AttnProcessor2_0
+ * -> F.scaled_dot_product_attention inside unet(...) at train_textboost.py:1063, backward at :1108);
+ * causal=1 (Nq == Nk): key j visible to query i iff j <= i (transformers CLIPAttention under
+ * CLIPTextTransformer's causal mask, called from textboost/text_encoder.py:62-69).  q/k/v/o are token-major fp16 [B, N, ld*] with head h occupying columns
  * [h*d, (h+1)*d) of each row, so they can point into the fused QKV projection output.
  * lse [B, heads, Nq] fp32 (log2 domain) is written by the forward and read by the backward. */
 int tb_attn_fwd_f16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                     void* o, int64_t ldo, float* lse, int B, int heads, int Nq, int Nk, int d,
-                    float scale, void* stream);
+                    float scale, int causal, void* stream);
 /* delta: workspace [B, heads, Nq] fp32.  dQacc: fp32 [B*Nq, lddq] accumulator, zeroed here and filled
  * with red.add (NULL = dQ not needed: the first cross-attention of the UNet).
  * dK/dV fp16 [B, Nk, ldd*] head-major columns like k/v. */
 int tb_attn_bwd_f16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                     const void* o, int64_t ldo, const void* dO, int64_t lddo, const float* lse,
                     float* delta, float* dQacc, int64_t lddq, void* dK, int64_t lddk, void* dV,
-                    int64_t lddv, int B, int heads, int Nq, int Nk, int d, float scale, void* stream);
+                    int64_t lddv, int B, int heads, int Nq, int Nk, int d, float scale, int causal,
+                    void* stream);
+
+/* debug only: buf = device int64[16*8*10] receiving clock64 timestamps of CTA (0,0,0) of the following
+ * tb_attn_fwd_f16 launches ([iteration][event][warp]); NULL switches it off.  Not used by the product path. */
+int tb_attn_debug_trace(void* buf);
 
 /* ---- normalisation (HBM-bound, channels-last fp16, fp32 statistics) ---------------------------
  * GroupNorm(+SiLU): diffusers ResnetBlock2D.norm1/norm2 + nonlinearity, Transformer2DModel.norm,

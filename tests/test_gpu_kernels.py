@@ -161,6 +161,30 @@ def test_attention_fwd_bwd(B, H, Nq, Nk, d):
     assert dq2 is None and torch.equal(dk2, dk) and torch.equal(dv2, dv)
 
 
+@pytest.mark.parametrize("B,H,N,d", [(2, 12, 77, 64), (3, 2, 128, 64), (1, 2, 300, 40), (16, 16, 77, 64)])
+def test_attention_causal(B, H, N, d):
+    """causal=1: the CLIP text-encoder attention (77 tokens, head_dim 64) on the same flash kernels."""
+    from textboost_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(N + d)
+    Cc = H * d
+    qkv = torch.randn(B, N, 3 * Cc, device=dev, dtype=F16, generator=g)
+    q, k, v = qkv[..., :Cc], qkv[..., Cc:2 * Cc], qkv[..., 2 * Cc:]
+    do = torch.randn(B, N, Cc, device=dev, dtype=F16, generator=g)
+
+    def heads(t):
+        return t.reshape(B, -1, H, d).transpose(1, 2).float().detach().requires_grad_(True)
+
+    qr, kr, vr = heads(q), heads(k), heads(v)
+    oref = F.scaled_dot_product_attention(qr, kr, vr, is_causal=True)
+    oref.backward(do.reshape(B, N, H, d).transpose(1, 2).float())
+    o, lse = ops.attn_fwd(q, k, v, H, causal=True)
+    assert relerr(o, oref.transpose(1, 2).reshape(B, N, Cc)) < TOL_ATTN
+    dq, dk, dv = ops.attn_bwd(q, k, v, o, do, lse, H, causal=True)
+    assert relerr(dq, qr.grad.transpose(1, 2).reshape(B, N, Cc)) < TOL_ATTN
+    assert relerr(dk, kr.grad.transpose(1, 2).reshape(B, N, Cc)) < TOL_ATTN
+    assert relerr(dv, vr.grad.transpose(1, 2).reshape(B, N, Cc)) < TOL_ATTN
+
+
 @pytest.mark.parametrize("B,HW,Cc,silu", [(2, 64, 64, True), (2, 4096, 320, True), (3, 1024, 640, False),
                                           (2, 256, 1920, True), (2, 64, 2560, True)])
 def test_groupnorm_fwd_bwd(B, HW, Cc, silu):

@@ -44,10 +44,11 @@ _SIGNATURES = {
     "tb_conv3x3_f16": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                        POINTER(Epilogue), c_void_p],
     "tb_attn_fwd_f16": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
-                        c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p],
+                        c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
     "tb_attn_bwd_f16": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                         c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
-                        c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p],
+                        c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
+    "tb_attn_debug_trace": [c_void_p],
     "tb_groupnorm_fwd_f16": [c_void_p] * 5 + [c_int] * 4 + [c_float, c_int, c_void_p],
     "tb_groupnorm_bwd_f16": [c_void_p] * 8 + [c_int] * 4 + [c_float, c_int, c_void_p],
     "tb_layernorm_fwd": [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int64,
@@ -117,7 +118,8 @@ def last_error() -> str:
 
 # kernels (and memset nodes) one call of each entry point enqueues; entry points not listed launch one
 _KERNELS_PER_CALL = {"tb_groupnorm_fwd_f16": 3, "tb_groupnorm_bwd_f16": 3, "tb_attn_bwd_f16": 2,
-                     "tb_adamw_fused_step": 3, "tb_version": 0, "tb_check_device": 0}
+                     "tb_adamw_fused_step": 3, "tb_version": 0, "tb_check_device": 0,
+                     "tb_attn_debug_trace": 0}
 launch_count = 0  # GPU launches enqueued through this binding since import (bench.py reports the delta)
 
 

@@ -160,7 +160,7 @@ class ClipEngine:
         self.null_embedding = torch.zeros((cfg.max_position_embeddings, D), device=self.device, dtype=F32)
         self.use_fixed_special = False
         self.decay = torch.ones(1, device=self.device, dtype=F32)  # lazy weight decay of frozen rows (D8)
-        self._ctx = None
+        self._ctx = []  # saved forward contexts, most recent last (one per forward awaiting its backward)
 
     # textboost/text_encoder.py:28-32
     def set_null_embedding(self, t: torch.Tensor):
@@ -211,15 +211,21 @@ class ClipEngine:
         C.call("tb_null_override", C.ptr(ids), C.ptr(self.null_embedding), C.ptr(out), B, Lq, D, EOS_ID,
                int(self.use_fixed_special), 0, s)
         if save_for_backward:
-            self._ctx = (ids, saved, x, stf)
+            self._ctx.append((ids, saved, x, stf))
         return out.view(B, Lq, D)
 
+    def pop_ctx(self):
+        """Detach the context of the most recent forward(save_for_backward=True) (autograd wrappers keep it
+        on their own ctx so several forwards can be outstanding, as in train_textboost.py:1054-1100)."""
+        return self._ctx.pop()
+
     # ------------------------------------------------------------------ backward
-    def backward(self, d_out: torch.Tensor):
+    def backward(self, d_out: torch.Tensor, ctx=None):
         """d_out fp32 [B, L, D] (consumed / overwritten).  Accumulates into state.grads."""
-        assert self._ctx is not None, "forward(save_for_backward=True) must precede backward"
-        ids, saved, xf, stf = self._ctx
-        self._ctx = None
+        if ctx is None:
+            assert self._ctx, "forward(save_for_backward=True) must precede backward"
+            ctx = self._ctx.pop()
+        ids, saved, xf, stf = ctx
         B, Lq = ids.shape
         D, M = self.D, B * Lq
         st = self.state

@@ -1,13 +1,26 @@
 // Flash attention forward / backward on tcgen05 + TMEM for the UNet self- and cross-attention
-// (diffusers AttnProcessor2_0 -> F.scaled_dot_product_attention, no mask, no dropout).
+// (diffusers AttnProcessor2_0 -> F.scaled_dot_product_attention, no mask, no dropout) and, with
+// causal=1, for the CLIP text encoder (transformers CLIPAttention, 77 tokens, head_dim 64).
 //
 // Layout: q/k/v/o are token-major fp16 [B, N, ld] with head h at columns [h*d, (h+1)*d); TMA reads a
 // head's [128 x 64] box straight out of the fused projection output (4-D map: d, heads, N, B) and
-// zero-fills the d..64 padding and the rows past N.  head_dim d in {40, 64, 80, 160} (any d % 8 == 0
-// up to 192).  S / dP / dQ and the O / dK / dV accumulators live in TMEM.
+// zero-fills the d..64 padding and the rows past N.  head_dim d % 8 == 0, d <= 192.
 //
-// CTA = 192 threads: warps 0..3 = softmax / correction / epilogue (thread == tile row),
-// warp 4 = TMA producer, warp 5 = MMA issuer.
+// The softmax is the bound, not the tensor core: a 128x128 score tile costs 16384 exponentials = 1024
+// MUFU cycles per SM against 384 tensor cycles (d = 40).  So the kernels are organised around the
+// per-element instruction count of the softmax threads:
+//   * scores are read from TMEM in two passes (row max, then exp) so no 128-register row is held;
+//   * exp2 runs as ex2.approx.f16x2 on the packed pair (the result IS the fp16 P the MMA consumes);
+//   * forward: P goes back to TMEM (aliasing the first 64 score columns) and the PV product is a
+//     TMEM-A MMA, so no shared-memory round trip; the row sum is a second tiny MMA against a tile of
+//     ones (fp32 accumulation of exactly the P that multiplies V); the running max is only refreshed
+//     when it grows by more than 2^8, so O is rarely rescaled;
+//   * two CTAs co-reside per SM, one's MMAs overlapping the other's softmax.
+//
+// CTA = 320 threads: warps 0..7 = softmax / correction / epilogue (two threads per tile row: warp w owns
+// TMEM lane quarter w & 3 and the 64-column half w >> 2), warp 8 = TMA producer, warp 9 = MMA issuer.
+// Sixteen softmax warps per SM (two CTAs) are what it takes to keep the MUFU pipe busy: with one thread
+// per row the per-thread TMEM-load / exp latency chain leaves it ~40 % utilised (ncu, profiles/).
 #include "host_util.h"
 #include "sm100.cuh"
 
@@ -17,6 +30,8 @@ constexpr int ABOX = 16384;  // one [128 rows x 64 fp16] swizzled box
 
 struct AttnParams {
   int Nq, Nk, heads, d, dn;  // dn = d rounded up to 16 (MMA N / K extent)
+  int causal;                // key j visible to query i iff j <= i
+  int tmem_cols;             // power of two >= the columns the kernel uses
   float scale_log2;          // softmax scale * log2(e)
   float scale;               // softmax scale
   __half* O;                 // fwd: output; bwd: unused
@@ -30,6 +45,7 @@ struct AttnParams {
   __half* dV;
   long long lddv;
   int n_inner;               // fwd: kv tiles; bwd: q tiles
+  long long* trace;          // debug: clock64 timestamps of CTA (0,0,0), [iter][event][warp]; normally null
 };
 
 __device__ __forceinline__ uint32_t sw128_off(int row, int chunk16) {
@@ -38,19 +54,70 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int chunk16) {
   return (uint32_t)((chunk16 >> 3) * ABOX + row * 128 + (((chunk16 & 7) ^ (row & 7)) << 4));
 }
 
-__device__ __forceinline__ void named_bar_sync(int id, int n) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+// debug timeline (tb_attn_debug_trace): event e of iteration j seen by warp w of CTA (0,0,0)
+#define TB_TRACE(j, e)                                                                              \
+  if (p.trace && lane == 0 && (j) < 16 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)    \
+  p.trace[((j) * 8 + (e)) * 10 + warp] = clock64()
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+// exp2 of two fp32 exponents, returned as the packed fp16 pair {lo, hi}.
+// Two MUFU.EX2 (fp32) + one F2FP.  (ex2.approx.f16x2 also lowers to two MUFU ops, MUFU.EX2.F16, but those
+// issue at roughly half the fp32 rate on sm_100: measured 0.59 ms vs the fp32 form on the 64x64 layer.)
+__device__ __forceinline__ uint32_t exp2_pack(float lo, float hi) {
+#ifdef TB_ATTN_EX2_F16X2
+  uint32_t p, e;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(hi), "f"(lo));
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(e) : "r"(p));
+  return e;
+#else
+  float a, b;
+  uint32_t e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(lo));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(b) : "f"(hi));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(e) : "f"(b), "f"(a));
+  return e;
+#endif
+}
+__device__ __forceinline__ uint32_t hmul2_u32(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ void tmem_alloc_rt(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_rt(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+      "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+      "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
 }
 
 // ------------------------------------------------------------------------------------ forward
+// TMEM: S at [0,128) (fp32 scores; P, packed fp16, overwrites [0,64) once the scores are consumed),
+//       O at [128, 128+dn), row sum L at [128+dn, 128+dn+16).
 template <int NB, int STAGES>
-__global__ void __launch_bounds__(192) attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ,
-                                                       const __grid_constant__ CUtensorMap tmK,
-                                                       const __grid_constant__ CUtensorMap tmV,
-                                                       const AttnParams p) {
+__global__ void __launch_bounds__(320, NB == 1 ? 2 : 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   constexpr int TILE = NB * ABOX;
-  constexpr int TMEM_COLS = NB == 3 ? 512 : 256;
-  constexpr uint32_t S_COL = 0, O_COL = 128;
+  constexpr uint32_t S_COL = 0, P_COL = 0, O_COL = 128;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -58,8 +125,9 @@ __global__ void __launch_bounds__(192) attn_fwd_kernel(const __grid_constant__ C
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + TILE;
   uint8_t* sV = sK + STAGES * TILE;
-  uint8_t* sP = sV + STAGES * TILE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * ABOX);
+  uint8_t* sOnes = sV + STAGES * TILE;
+  float* sMax = reinterpret_cast<float*>(sOnes + ABOX);  // [2][128] partial row maxima of the two halves
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sMax + 256);
   uint64_t* bar_q = bars;
   uint64_t* bar_s = bars + 1;
   uint64_t* bar_p = bars + 2;
@@ -70,11 +138,14 @@ __global__ void __launch_bounds__(192) attn_fwd_kernel(const __grid_constant__ C
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const uint32_t L_COL = O_COL + p.dn;
+  // causal: kv tiles entirely above the diagonal contribute nothing
+  const int n_kv = p.causal ? min(p.n_inner, (min(q0 + 128, p.Nq) + 127) / 128) : p.n_inner;
 
-  if (threadIdx.x == 160) {
+  if (threadIdx.x == 288) {
     mbar_init(smem_u32(bar_q), 1);
     mbar_init(smem_u32(bar_s), 1);
-    mbar_init(smem_u32(bar_p), 128);
+    mbar_init(smem_u32(bar_p), 256);
     mbar_init(smem_u32(bar_o), 1);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&kv_full[s]), 1);
@@ -82,23 +153,32 @@ __global__ void __launch_bounds__(192) attn_fwd_kernel(const __grid_constant__ C
     }
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+  {  // tile of ones (B operand of the row-sum MMA); every element equal, so the swizzle is irrelevant
+    const uint4 ones = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+    for (int i = threadIdx.x; i < ABOX / 16; i += 320) reinterpret_cast<uint4*>(sOnes)[i] = ones;
+    fence_async_smem();
+  }
+  if (warp == 0) tmem_alloc_rt(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
-    if (lane == 0) {
+  if (warp == 8) {
+    // ---------------------------------------------------------------- TMA producer (warp-uniform)
+    if (elect_one()) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmK);
       tma_prefetch_desc(&tmV);
       mbar_expect_tx(smem_u32(bar_q), TILE);
       for (int x = 0; x < NB; ++x) tma_load_4d(smem_u32(sQ + x * ABOX), &tmQ, smem_u32(bar_q), x * 64, h, q0, b);
-      for (int j = 0; j < p.n_inner; ++j) {
-        const int s = j % STAGES;
-        const uint32_t ph = (j / STAGES) & 1;
-        mbar_wait(smem_u32(&kv_empty[s]), ph ^ 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_kv; ++j) {
+      const int s = j % STAGES;
+      const uint32_t ph = (j / STAGES) & 1;
+      mbar_wait(smem_u32(&kv_empty[s]), ph ^ 1);
+      if (elect_one()) {
         const uint32_t fb = smem_u32(&kv_full[s]);
         mbar_expect_tx(fb, 2 * TILE);
         for (int x = 0; x < NB; ++x) {
@@ -106,136 +186,157 @@ __global__ void __launch_bounds__(192) attn_fwd_kernel(const __grid_constant__ C
           tma_load_4d(smem_u32(sV + s * TILE + x * ABOX), &tmV, fb, x * 64, h, j * 128, b);
         }
       }
+      __syncwarp();
     }
-  } else if (warp == 5) {
-    if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_f16(128, 128, 0, 0);
-      const uint32_t idesc_o = umma_idesc_f16(128, p.dn, 0, 1);  // B = V is MN-major
-      const int nks = p.dn / 16;
-      mbar_wait(smem_u32(bar_q), 0);
-      for (int j = 0; j < p.n_inner; ++j) {
-        const int s = j % STAGES;
-        const uint32_t ph = (j / STAGES) & 1;
-        mbar_wait(smem_u32(&kv_full[s]), ph);
-        tc_fence_after();
-        const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK + s * TILE), aV = smem_u32(sV + s * TILE);
+  } else if (warp == 9) {
+    // ---------------------------------------------------------------- MMA issuer (warp-uniform)
+    const uint32_t idesc_s = umma_idesc_f16(128, 128, 0, 0);
+    const uint32_t idesc_o = umma_idesc_f16(128, p.dn, 0, 1);  // B = V is MN-major
+    const uint32_t idesc_l = umma_idesc_f16(128, 16, 0, 1);
+    const int nks = p.dn / 16;
+    const uint32_t hi = umma_desc_hi_sw128(1024);
+    const uint32_t q_lo = umma_desc_lo(smem_u32(sQ), 16);
+    const uint32_t ones_lo = umma_desc_lo(smem_u32(sOnes), ABOX);
+    mbar_wait(smem_u32(bar_q), 0);
+    for (int j = 0; j < n_kv; ++j) {
+      const int s = j % STAGES;
+      const uint32_t ph = (j / STAGES) & 1;
+      const uint32_t k_lo = umma_desc_lo(smem_u32(sK + s * TILE), 16);
+      const uint32_t v_lo = umma_desc_lo(smem_u32(sV + s * TILE), ABOX);
+      mbar_wait(smem_u32(&kv_full[s]), ph);
+      tc_fence_after();
+      if (elect_one()) {
         for (int ks = 0; ks < nks; ++ks) {
-          const uint32_t off = (ks >> 2) * ABOX + (ks & 3) * 32;
-          umma_f16_ss(tmem + S_COL, umma_desc_sw128(aQ + off, 16, 1024),
-                      umma_desc_sw128(aK + off, 16, 1024), idesc_s, ks > 0);
+          const uint32_t off = ((ks >> 2) * ABOX + (ks & 3) * 32) >> 4;
+          umma_f16_ss(tmem + S_COL, umma_desc_pack(q_lo + off, hi), umma_desc_pack(k_lo + off, hi), idesc_s, ks > 0);
         }
-        umma_commit(smem_u32(bar_s));
-        mbar_wait(smem_u32(bar_p), j & 1);
-        tc_fence_after();
-        const uint32_t aP = smem_u32(sP);
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint32_t offp = (ks >> 2) * ABOX + (ks & 3) * 32;
-          umma_f16_ss(tmem + O_COL, umma_desc_sw128(aP + offp, 16, 1024),
-                      umma_desc_sw128(aV + ks * 2048, ABOX, 1024), idesc_o, (j > 0) || (ks > 0));
+        umma_commit(smem_u32(bar_s));  // also: every earlier MMA (PV of tile j-1) has retired
+      }
+      __syncwarp();
+      TB_TRACE(j, 0);
+      mbar_wait(smem_u32(bar_p), j & 1);
+      tc_fence_after();
+      TB_TRACE(j, 1);
+      // keys past Nk have P == 0: skip their k-steps
+      const int kvalid = min(128, p.Nk - j * 128);
+      const int nkk = (kvalid + 15) >> 4;
+      if (elect_one()) {
+        for (int ks = 0; ks < nkk; ++ks) {
+          umma_f16_ts(tmem + O_COL, tmem + P_COL + ks * 8, umma_desc_pack(v_lo + ks * 128, hi), idesc_o,
+                      (j > 0) || (ks > 0));
+          umma_f16_ts(tmem + L_COL, tmem + P_COL + ks * 8, umma_desc_pack(ones_lo + ks * 128, hi), idesc_l,
+                      (j > 0) || (ks > 0));
         }
         umma_commit(smem_u32(&kv_empty[s]));
-        umma_commit(smem_u32(bar_o));
+        if (j == n_kv - 1) umma_commit(smem_u32(bar_o));
       }
+      __syncwarp();
+      TB_TRACE(j, 2);
     }
   } else {
-    // ---------------------------------------------------------------- softmax warps (row = thread)
-    const int row = warp * 32 + lane;
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-    float m = -INFINITY, l = 0.f;
-    for (int j = 0; j < p.n_inner; ++j) {
-      const int kv_valid = p.Nk - j * 128;  // columns >= kv_valid are padding
+    // ---------------------------------------------------------------- softmax warps (2 threads per row)
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    const int cbase = half * 64;  // first score column of this thread
+    float m_run = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      // columns >= limit are masked (padding keys, and keys above the causal diagonal)
+      int limit = p.Nk - j * 128;
+      if (p.causal) limit = min(limit, q0 + row + 1 - j * 128);
+      const bool masked = __any_sync(0xffffffffu, limit < cbase + 64);
+      TB_TRACE(j, 3);
       mbar_wait(smem_u32(bar_s), j & 1);
       tc_fence_after();
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(lane_addr + S_COL + c * 32, r);
-        tmem_ld_wait();
+      TB_TRACE(j, 4);
+      uint32_t r[64];
+      tmem_ld32(lane_addr + S_COL + cbase, r);
+      tmem_ld32(lane_addr + S_COL + cbase + 32, r + 32);
+      tmem_ld_wait();
+      TB_TRACE(j, 5);
+      if (masked) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float v = (c * 32 + i < kv_valid) ? __uint_as_float(r[i]) : -INFINITY;
-          mx = fmaxf(mx, v);
-        }
+        for (int i = 0; i < 64; ++i)
+          if (cbase + i >= limit) r[i] = 0xff800000u;  // -inf
       }
-      const float m_new = fmaxf(m, mx * p.scale_log2);
-      const float alpha = exp2f(m - m_new);
-      if (j > 0) {
-        mbar_wait(smem_u32(bar_o), (j - 1) & 1);  // PV_{j-1} retired: O readable, sP reusable
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, alpha != 1.f)) {
-          for (int c = 0; c < p.dn; c += 16) {
-            uint32_t r[16];
-            tmem_ld16(lane_addr + O_COL + c, r);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 64; i += 2) mx = fmax3(mx, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+      sMax[half * 128 + row] = mx;
+      // all 256 threads have their scores in registers past this barrier: P may now overwrite S
+      named_bar_sync(1, 256);
+      TB_TRACE(j, 6);
+      mx = fmaxf(mx, sMax[(half ^ 1) * 128 + row]);
+      const float m_tile = mx * p.scale_log2;
+      if (j == 0) {
+        m_run = m_tile;
+      } else {
+        // lazy rescale: keep the old reference max unless the row max grew by more than 2^8
+        const bool need = m_tile > m_run + 8.f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = need ? exp2f(m_run - m_tile) : 1.f;
+          // O and the row sum L are contiguous: the two halves split the 16-column chunks
+          for (int c = half * 16; c < p.dn + 16; c += 32) {
+            uint32_t t[16];
+            tmem_ld16(lane_addr + O_COL + c, t);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            tmem_st16(lane_addr + O_COL + c, r);
+            for (int i = 0; i < 16; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+            tmem_st16(lane_addr + O_COL + c, t);
           }
-          tmem_st_wait();
         }
+        if (need) m_run = m_tile;
       }
-      float rs = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(lane_addr + S_COL + c * 32, r);
-        tmem_ld_wait();
+      // P = exp2(S*c - m) as packed fp16, written over the consumed score columns [0, 64)
+      const float neg_m = -m_run;
+      uint32_t pk[32];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float pv[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int col = c * 32 + g * 8 + i;
-            const float e = exp2f(__uint_as_float(r[g * 8 + i]) * p.scale_log2 - m_new);
-            pv[i] = col < kv_valid ? e : 0.f;
-            rs += pv[i];
-          }
-          uint4 o;
-          o.x = pack_half2(pv[0], pv[1]);
-          o.y = pack_half2(pv[2], pv[3]);
-          o.z = pack_half2(pv[4], pv[5]);
-          o.w = pack_half2(pv[6], pv[7]);
-          *reinterpret_cast<uint4*>(sP + sw128_off(row, c * 4 + g)) = o;
-        }
-      }
-      l = l * alpha + rs;
-      m = m_new;
-      fence_async_smem();
+      for (int i = 0; i < 32; ++i)
+        pk[i] = exp2_pack(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, neg_m),
+                          fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, neg_m));
+      tmem_st32(lane_addr + P_COL + half * 32, pk);
+      tmem_st_wait();
       tc_fence_before();
       mbar_arrive(smem_u32(bar_p));
+      TB_TRACE(j, 7);
     }
-    mbar_wait(smem_u32(bar_o), (p.n_inner - 1) & 1);
+    mbar_wait(smem_u32(bar_o), 0);
     tc_fence_after();
+    float l;
+    {
+      uint32_t t[8];
+      tmem_ld8(lane_addr + L_COL, t);
+      tmem_ld_wait();
+      l = __uint_as_float(t[0]);
+    }
     const float inv_l = 1.f / l;
     const int q = q0 + row;
     const bool ok = q < p.Nq;
     __half* op = p.O + ((long long)b * p.Nq + q) * p.ldo + h * p.d;
-    for (int c = 0; c < p.dn; c += 16) {
-      uint32_t r[16];
-      tmem_ld16(lane_addr + O_COL + c, r);
+    for (int c = half * 16; c < p.dn; c += 32) {
+      uint32_t t[16];
+      tmem_ld16(lane_addr + O_COL + c, t);
       tmem_ld_wait();
       if (ok) {
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           if (c + g * 8 < p.d) {
             uint4 o;
-            o.x = pack_half2(__uint_as_float(r[g * 8 + 0]) * inv_l, __uint_as_float(r[g * 8 + 1]) * inv_l);
-            o.y = pack_half2(__uint_as_float(r[g * 8 + 2]) * inv_l, __uint_as_float(r[g * 8 + 3]) * inv_l);
-            o.z = pack_half2(__uint_as_float(r[g * 8 + 4]) * inv_l, __uint_as_float(r[g * 8 + 5]) * inv_l);
-            o.w = pack_half2(__uint_as_float(r[g * 8 + 6]) * inv_l, __uint_as_float(r[g * 8 + 7]) * inv_l);
+            o.x = pack_half2(__uint_as_float(t[g * 8 + 0]) * inv_l, __uint_as_float(t[g * 8 + 1]) * inv_l);
+            o.y = pack_half2(__uint_as_float(t[g * 8 + 2]) * inv_l, __uint_as_float(t[g * 8 + 3]) * inv_l);
+            o.z = pack_half2(__uint_as_float(t[g * 8 + 4]) * inv_l, __uint_as_float(t[g * 8 + 5]) * inv_l);
+            o.w = pack_half2(__uint_as_float(t[g * 8 + 6]) * inv_l, __uint_as_float(t[g * 8 + 7]) * inv_l);
             *reinterpret_cast<uint4*>(op + c + g * 8) = o;
           }
         }
       }
     }
-    if (ok && p.lse) p.lse[((long long)b * p.heads + h) * p.Nq + q] = m + log2f(l);
+    if (ok && half == 0 && p.lse) p.lse[((long long)b * p.heads + h) * p.Nq + q] = m_run + log2f(l);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem);
+  if (warp == 0) tmem_dealloc_rt(tmem, (uint32_t)p.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------ backward
@@ -271,15 +372,14 @@ __global__ void attn_delta_kernel(const __half* __restrict__ O, const __half* __
 //   S^T = K Q^T ; P^T = exp2(S^T*c - L) ; dP^T = V dO^T ; dS^T = P^T o (dP^T - delta)
 //   dV += P^T dO ; dK += dS^T Q ; dQ_i = dS K  (red.add into the fp32 dQ accumulator)
 // TMEM: X = [0,128) is S^T, then dP^T, then dQ_i in turn; dV at 128, dK at 128+dn.
+// Shared memory: dS^T overwrites P^T in place (P^T stays in registers for the dS product), which keeps
+// the head_dim <= 64 kernel at 98 KB so two CTAs co-reside per SM.
 template <int NB, int STAGES>
-__global__ void __launch_bounds__(192) attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ,
-                                                       const __grid_constant__ CUtensorMap tmK,
-                                                       const __grid_constant__ CUtensorMap tmV,
-                                                       const __grid_constant__ CUtensorMap tmdO,
-                                                       const AttnParams p) {
+__global__ void __launch_bounds__(320, NB == 1 ? 2 : 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                const AttnParams p) {
   constexpr int TILE = NB * ABOX;
-  constexpr bool INPLACE = NB == 3;  // dS^T overwrites P^T in place (shared memory budget)
-  constexpr int TMEM_COLS = NB == 1 ? 256 : 512;
   constexpr uint32_t X_COL = 0, DV_COL = 128;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -289,9 +389,9 @@ __global__ void __launch_bounds__(192) attn_bwd_kernel(const __grid_constant__ C
   uint8_t* sV = sK + TILE;
   uint8_t* sQ = sV + TILE;
   uint8_t* sdO = sQ + STAGES * TILE;
-  uint8_t* sPT = sdO + STAGES * TILE;
-  uint8_t* sDS = INPLACE ? sPT : sPT + 2 * ABOX;
-  float* sL = reinterpret_cast<float*>(sDS + 2 * ABOX);  // [128] L_i, [128] delta_i
+  uint8_t* sPT = sdO + STAGES * TILE;  // P^T, then dS^T in place
+  uint8_t* sDS = sPT;
+  float* sL = reinterpret_cast<float*>(sPT + 2 * ABOX);  // [128] L_i, [128] delta_i
   float* sD = sL + 128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 128);
   uint64_t* bar_kv = bars;
@@ -309,30 +409,33 @@ __global__ void __launch_bounds__(192) attn_bwd_kernel(const __grid_constant__ C
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kv0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const uint32_t DK_COL = DV_COL + p.dn;
+  // causal: q tiles entirely before this kv tile see none of its keys
+  const int i_begin = p.causal ? kv0 / 128 : 0;
 
-  if (threadIdx.x == 160) {
+  if (threadIdx.x == 288) {
     mbar_init(smem_u32(bar_kv), 1);
     mbar_init(smem_u32(bar_s), 1);
-    mbar_init(smem_u32(bar_pt), 128);
+    mbar_init(smem_u32(bar_pt), 256);
     mbar_init(smem_u32(bar_dp), 1);
     mbar_init(smem_u32(bar_dv), 1);
-    mbar_init(smem_u32(bar_ds), 128);
+    mbar_init(smem_u32(bar_ds), 256);
     mbar_init(smem_u32(bar_dq), 1);
-    mbar_init(smem_u32(bar_dqfree), 128);
+    mbar_init(smem_u32(bar_dqfree), 256);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&q_full[s]), 1);
       mbar_init(smem_u32(&q_empty[s]), 1);
     }
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+  if (warp == 0) tmem_alloc_rt(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
-    if (lane == 0) {
+  if (warp == 8) {
+    // ---------------------------------------------------------------- TMA producer (warp-uniform)
+    if (elect_one()) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmK);
       tma_prefetch_desc(&tmV);
@@ -342,10 +445,14 @@ __global__ void __launch_bounds__(192) attn_bwd_kernel(const __grid_constant__ C
         tma_load_4d(smem_u32(sK + x * ABOX), &tmK, smem_u32(bar_kv), x * 64, h, kv0, b);
         tma_load_4d(smem_u32(sV + x * ABOX), &tmV, smem_u32(bar_kv), x * 64, h, kv0, b);
       }
-      for (int i = 0; i < p.n_inner; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(smem_u32(&q_empty[s]), ph ^ 1);
+    }
+    __syncwarp();
+    for (int i = i_begin; i < p.n_inner; ++i) {
+      const int it = i - i_begin;
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(smem_u32(&q_empty[s]), ph ^ 1);
+      if (elect_one()) {
         const uint32_t fb = smem_u32(&q_full[s]);
         mbar_expect_tx(fb, 2 * TILE);
         for (int x = 0; x < NB; ++x) {
@@ -353,152 +460,179 @@ __global__ void __launch_bounds__(192) attn_bwd_kernel(const __grid_constant__ C
           tma_load_4d(smem_u32(sdO + s * TILE + x * ABOX), &tmdO, fb, x * 64, h, i * 128, b);
         }
       }
+      __syncwarp();
     }
-  } else if (warp == 5) {
-    if (lane == 0) {
-      const uint32_t idesc_kk = umma_idesc_f16(128, 128, 0, 0);     // S^T, dP^T : both K-major
-      const uint32_t idesc_acc = umma_idesc_f16(128, p.dn, 0, 1);   // dV, dK : B MN-major
-      const int nks = p.dn / 16;
-      // dQ = dS K: A = dS^T buffer read MN-major, B = K MN-major; N split at 128 when dn > 128
-      const int dq_n0 = p.dn > 128 ? 128 : p.dn;
-      const int dq_n1 = p.dn - dq_n0;
-      const uint32_t idesc_dq0 = umma_idesc_f16(128, dq_n0, 1, 1);
-      const uint32_t idesc_dq1 = umma_idesc_f16(128, dq_n1 > 0 ? dq_n1 : 16, 1, 1);
-      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aPT = smem_u32(sPT), aDS = smem_u32(sDS);
-      uint32_t ph_dqfree = 0;
-      mbar_wait(smem_u32(bar_kv), 0);
-      for (int i = 0; i < p.n_inner; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        const uint32_t aQ = smem_u32(sQ + s * TILE), adO = smem_u32(sdO + s * TILE);
-        mbar_wait(smem_u32(&q_full[s]), ph);
-        if (i > 0) {
-          mbar_wait(smem_u32(bar_dqfree), ph_dqfree);
-          ph_dqfree ^= 1;
-        }
-        tc_fence_after();
+  } else if (warp == 9) {
+    // ---------------------------------------------------------------- MMA issuer (warp-uniform)
+    const uint32_t idesc_kk = umma_idesc_f16(128, 128, 0, 0);     // S^T, dP^T : both K-major
+    const uint32_t idesc_acc = umma_idesc_f16(128, p.dn, 0, 1);   // dV, dK : B MN-major
+    const int nks = p.dn / 16;
+    // dQ = dS K: A = dS^T buffer read MN-major, B = K MN-major; N split at 128 when dn > 128
+    const int dq_n0 = p.dn > 128 ? 128 : p.dn;
+    const int dq_n1 = p.dn - dq_n0;
+    const uint32_t idesc_dq0 = umma_idesc_f16(128, dq_n0, 1, 1);
+    const uint32_t idesc_dq1 = umma_idesc_f16(128, dq_n1 > 0 ? dq_n1 : 16, 1, 1);
+    const uint32_t hi = umma_desc_hi_sw128(1024);
+    // K-major views (LBO unused) and MN-major views (LBO = distance between 64-column boxes)
+    const uint32_t k_lo = umma_desc_lo(smem_u32(sK), 16), v_lo = umma_desc_lo(smem_u32(sV), 16);
+    const uint32_t pt_lo = umma_desc_lo(smem_u32(sPT), 16);
+    const uint32_t k_mn = umma_desc_lo(smem_u32(sK), ABOX), ds_mn = umma_desc_lo(smem_u32(sDS), ABOX);
+    uint32_t ph_dqfree = 0;
+    mbar_wait(smem_u32(bar_kv), 0);
+    for (int i = i_begin; i < p.n_inner; ++i) {
+      const int it = i - i_begin;
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      const uint32_t q_lo = umma_desc_lo(smem_u32(sQ + s * TILE), 16), do_lo = umma_desc_lo(smem_u32(sdO + s * TILE), 16);
+      const uint32_t q_mn = umma_desc_lo(smem_u32(sQ + s * TILE), ABOX), do_mn = umma_desc_lo(smem_u32(sdO + s * TILE), ABOX);
+      mbar_wait(smem_u32(&q_full[s]), ph);
+      if (it > 0) {
+        mbar_wait(smem_u32(bar_dqfree), ph_dqfree);
+        ph_dqfree ^= 1;
+      }
+      tc_fence_after();
+      if (elect_one()) {
         for (int ks = 0; ks < nks; ++ks) {  // S^T = K Q^T
-          const uint32_t off = (ks >> 2) * ABOX + (ks & 3) * 32;
-          umma_f16_ss(tmem + X_COL, umma_desc_sw128(aK + off, 16, 1024),
-                      umma_desc_sw128(aQ + off, 16, 1024), idesc_kk, ks > 0);
+          const uint32_t off = ((ks >> 2) * ABOX + (ks & 3) * 32) >> 4;
+          umma_f16_ss(tmem + X_COL, umma_desc_pack(k_lo + off, hi), umma_desc_pack(q_lo + off, hi), idesc_kk, ks > 0);
         }
         umma_commit(smem_u32(bar_s));
-        mbar_wait(smem_u32(bar_pt), i & 1);  // P^T in smem, S^T drained from TMEM
-        tc_fence_after();
+      }
+      __syncwarp();
+      mbar_wait(smem_u32(bar_pt), it & 1);  // P^T in smem, S^T drained from TMEM
+      tc_fence_after();
+      if (elect_one()) {
         for (int ks = 0; ks < nks; ++ks) {  // dP^T = V dO^T
-          const uint32_t off = (ks >> 2) * ABOX + (ks & 3) * 32;
-          umma_f16_ss(tmem + X_COL, umma_desc_sw128(aV + off, 16, 1024),
-                      umma_desc_sw128(adO + off, 16, 1024), idesc_kk, ks > 0);
+          const uint32_t off = ((ks >> 2) * ABOX + (ks & 3) * 32) >> 4;
+          umma_f16_ss(tmem + X_COL, umma_desc_pack(v_lo + off, hi), umma_desc_pack(do_lo + off, hi), idesc_kk, ks > 0);
         }
         umma_commit(smem_u32(bar_dp));
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {  // dV += P^T dO
-          const uint32_t offp = (ks >> 2) * ABOX + (ks & 3) * 32;
-          umma_f16_ss(tmem + DV_COL, umma_desc_sw128(aPT + offp, 16, 1024),
-                      umma_desc_sw128(adO + ks * 2048, ABOX, 1024), idesc_acc, (i > 0) || (ks > 0));
+          const uint32_t offp = ((ks >> 2) * ABOX + (ks & 3) * 32) >> 4;
+          umma_f16_ss(tmem + DV_COL, umma_desc_pack(pt_lo + offp, hi), umma_desc_pack(do_mn + ks * 128, hi),
+                      idesc_acc, (it > 0) || (ks > 0));
         }
-        if (INPLACE) umma_commit(smem_u32(bar_dv));
-        mbar_wait(smem_u32(bar_ds), i & 1);  // dS^T in smem, dP^T drained
-        tc_fence_after();
+        umma_commit(smem_u32(bar_dv));  // P^T buffer may now be overwritten by dS^T
+      }
+      __syncwarp();
+      mbar_wait(smem_u32(bar_ds), it & 1);  // dS^T in smem, dP^T drained
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {  // dK += dS^T Q
-          const uint32_t offp = (ks >> 2) * ABOX + (ks & 3) * 32;
-          umma_f16_ss(tmem + DK_COL, umma_desc_sw128(aDS + offp, 16, 1024),
-                      umma_desc_sw128(aQ + ks * 2048, ABOX, 1024), idesc_acc, (i > 0) || (ks > 0));
+          const uint32_t offp = ((ks >> 2) * ABOX + (ks & 3) * 32) >> 4;
+          umma_f16_ss(tmem + DK_COL, umma_desc_pack(pt_lo + offp, hi), umma_desc_pack(q_mn + ks * 128, hi),
+                      idesc_acc, (it > 0) || (ks > 0));
         }
         if (p.dQacc) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {  // dQ_i = dS K   (A: [kv][q] read MN-major)
-            umma_f16_ss(tmem + X_COL, umma_desc_sw128(aDS + ks * 2048, ABOX, 1024),
-                        umma_desc_sw128(aK + ks * 2048, ABOX, 1024), idesc_dq0, ks > 0);
+            umma_f16_ss(tmem + X_COL, umma_desc_pack(ds_mn + ks * 128, hi), umma_desc_pack(k_mn + ks * 128, hi),
+                        idesc_dq0, ks > 0);
           }
         }
         umma_commit(smem_u32(bar_dq));
-        if (p.dQacc && dq_n1 > 0) {
-          // columns 128..dn of dQ reuse X once the first 128 have been drained
-          mbar_wait(smem_u32(bar_dqfree), ph_dqfree);
-          ph_dqfree ^= 1;
-          tc_fence_after();
+      }
+      __syncwarp();
+      if (p.dQacc && dq_n1 > 0) {
+        // columns 128..dn of dQ reuse X once the first 128 have been drained
+        mbar_wait(smem_u32(bar_dqfree), ph_dqfree);
+        ph_dqfree ^= 1;
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
-            umma_f16_ss(tmem + X_COL, umma_desc_sw128(aDS + ks * 2048, ABOX, 1024),
-                        umma_desc_sw128(aK + 2 * ABOX + ks * 2048, ABOX, 1024), idesc_dq1, ks > 0);
+            umma_f16_ss(tmem + X_COL, umma_desc_pack(ds_mn + ks * 128, hi),
+                        umma_desc_pack(k_mn + ((2 * ABOX) >> 4) + ks * 128, hi), idesc_dq1, ks > 0);
           }
           umma_commit(smem_u32(bar_dq));
         }
-        umma_commit(smem_u32(&q_empty[s]));
+        __syncwarp();
       }
+      if (elect_one()) umma_commit(smem_u32(&q_empty[s]));
+      __syncwarp();
     }
   } else {
     // ---------------------------------------------------------------- softmax / dS / epilogue
-    const int row = warp * 32 + lane;  // kv row inside the tile (and q row for the dQ drain)
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    // two threads per kv row: warp w owns lane quarter w & 3 and the q-column half w >> 2
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + lane;  // kv row inside the tile (and q row for the dQ drain)
+    const int cb = half * 64;             // first q column of this thread
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
     const bool kv_ok = kv0 + row < p.Nk;
     const long long bh = (long long)b * p.heads + h;
     uint32_t ph_dq = 0;
-    for (int i = 0; i < p.n_inner; ++i) {
+    for (int i = i_begin; i < p.n_inner; ++i) {
+      const int it = i - i_begin;
       const int q0 = i * 128;
       {
         const int q = q0 + row;
-        sL[row] = q < p.Nq ? p.lse[bh * p.Nq + q] : INFINITY;
-        sD[row] = q < p.Nq ? p.delta[bh * p.Nq + q] : 0.f;
+        // +inf makes exp2(. - L) == 0 for padding queries
+        if (half == 0) sL[row] = q < p.Nq ? p.lse[bh * p.Nq + q] : INFINITY;
+        else sD[row] = q < p.Nq ? p.delta[bh * p.Nq + q] : 0.f;
       }
-      named_bar_sync(1, 128);
-      mbar_wait(smem_u32(bar_s), i & 1);
+      named_bar_sync(1, 256);
+      // causal: query column c sees this key row iff q0 + c >= kv0 + row
+      const int cmin = p.causal ? (kv0 + row - q0) : 0;
+      const bool masked = __any_sync(0xffffffffu, cmin > cb);
+      mbar_wait(smem_u32(bar_s), it & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      uint32_t pt[32];  // this thread's 64 entries of P^T as packed fp16, kept for the dS product
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
-        tmem_ld32(lane_addr + X_COL + c * 32, r);
+        tmem_ld32(lane_addr + X_COL + cb + c * 32, r);
         tmem_ld_wait();
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          float pv[8];
+          const float4 l0 = *reinterpret_cast<const float4*>(sL + cb + c * 32 + g * 8);
+          const float4 l1 = *reinterpret_cast<const float4*>(sL + cb + c * 32 + g * 8 + 4);
+          uint32_t* o = pt + c * 16 + g * 4;
+          o[0] = exp2_pack(fmaf(__uint_as_float(r[g * 8 + 0]), p.scale_log2, -l0.x),
+                           fmaf(__uint_as_float(r[g * 8 + 1]), p.scale_log2, -l0.y));
+          o[1] = exp2_pack(fmaf(__uint_as_float(r[g * 8 + 2]), p.scale_log2, -l0.z),
+                           fmaf(__uint_as_float(r[g * 8 + 3]), p.scale_log2, -l0.w));
+          o[2] = exp2_pack(fmaf(__uint_as_float(r[g * 8 + 4]), p.scale_log2, -l1.x),
+                           fmaf(__uint_as_float(r[g * 8 + 5]), p.scale_log2, -l1.y));
+          o[3] = exp2_pack(fmaf(__uint_as_float(r[g * 8 + 6]), p.scale_log2, -l1.z),
+                           fmaf(__uint_as_float(r[g * 8 + 7]), p.scale_log2, -l1.w));
+          if (masked) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int col = c * 32 + g * 8 + k;
-            const float e = exp2f(__uint_as_float(r[g * 8 + k]) * p.scale_log2 - sL[col]);
-            pv[k] = kv_ok ? e : 0.f;
+            for (int k = 0; k < 4; ++k) {
+              const int col = cb + c * 32 + g * 8 + 2 * k;
+              if (col < cmin) o[k] &= 0xffff0000u;
+              if (col + 1 < cmin) o[k] &= 0x0000ffffu;
+            }
           }
-          uint4 o;
-          o.x = pack_half2(pv[0], pv[1]);
-          o.y = pack_half2(pv[2], pv[3]);
-          o.z = pack_half2(pv[4], pv[5]);
-          o.w = pack_half2(pv[6], pv[7]);
-          *reinterpret_cast<uint4*>(sPT + sw128_off(row, c * 4 + g)) = o;
+          if (!kv_ok) o[0] = o[1] = o[2] = o[3] = 0u;
+          *reinterpret_cast<uint4*>(sPT + sw128_off(row, half * 8 + c * 4 + g)) =
+              make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
       fence_async_smem();
       tc_fence_before();
       mbar_arrive(smem_u32(bar_pt));
 
-      mbar_wait(smem_u32(bar_dp), i & 1);
-      if (INPLACE) mbar_wait(smem_u32(bar_dv), i & 1);  // dV MMA has finished reading P^T
+      mbar_wait(smem_u32(bar_dp), it & 1);
+      mbar_wait(smem_u32(bar_dv), it & 1);  // the dV MMA has finished reading P^T: dS^T overwrites it
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
-        tmem_ld32(lane_addr + X_COL + c * 32, r);
+        tmem_ld32(lane_addr + X_COL + cb + c * 32, r);
         tmem_ld_wait();
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const uint32_t off = sw128_off(row, c * 4 + g);
-          const uint4 pq = *reinterpret_cast<const uint4*>(sPT + off);
-          const __half2* ph2 = reinterpret_cast<const __half2*>(&pq);
-          float ds[8];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 pf = __half22float2(ph2[k]);
-            const int col = c * 32 + g * 8 + 2 * k;
-            ds[2 * k] = pf.x * (__uint_as_float(r[g * 8 + 2 * k]) - sD[col]);
-            ds[2 * k + 1] = pf.y * (__uint_as_float(r[g * 8 + 2 * k + 1]) - sD[col + 1]);
-          }
+          const float4 d0 = *reinterpret_cast<const float4*>(sD + cb + c * 32 + g * 8);
+          const float4 d1 = *reinterpret_cast<const float4*>(sD + cb + c * 32 + g * 8 + 4);
+          const uint32_t* pp = pt + c * 16 + g * 4;
           uint4 o;
-          o.x = pack_half2(ds[0], ds[1]);
-          o.y = pack_half2(ds[2], ds[3]);
-          o.z = pack_half2(ds[4], ds[5]);
-          o.w = pack_half2(ds[6], ds[7]);
-          *reinterpret_cast<uint4*>(sDS + off) = o;
+          o.x = hmul2_u32(pp[0], pack_half2(__uint_as_float(r[g * 8 + 0]) - d0.x, __uint_as_float(r[g * 8 + 1]) - d0.y));
+          o.y = hmul2_u32(pp[1], pack_half2(__uint_as_float(r[g * 8 + 2]) - d0.z, __uint_as_float(r[g * 8 + 3]) - d0.w));
+          o.z = hmul2_u32(pp[2], pack_half2(__uint_as_float(r[g * 8 + 4]) - d1.x, __uint_as_float(r[g * 8 + 5]) - d1.y));
+          o.w = hmul2_u32(pp[3], pack_half2(__uint_as_float(r[g * 8 + 6]) - d1.z, __uint_as_float(r[g * 8 + 7]) - d1.w));
+          *reinterpret_cast<uint4*>(sDS + sw128_off(row, half * 8 + c * 4 + g)) = o;
         }
       }
       fence_async_smem();
@@ -516,7 +650,7 @@ __global__ void __launch_bounds__(192) attn_bwd_kernel(const __grid_constant__ C
           const int cbase = ch * 128;
           float* dq = p.dQacc + ((long long)b * p.Nq + q) * p.lddq + h * p.d + cbase;
           const int ncols = (p.dn - cbase) > 128 ? 128 : (p.dn - cbase);
-          for (int c = 0; c < ncols; c += 16) {
+          for (int c = half * 16; c < ncols; c += 32) {  // the two halves alternate 16-column chunks
             uint32_t r[16];
             tmem_ld16(lane_addr + X_COL + c, r);
             tmem_ld_wait();
@@ -541,7 +675,7 @@ __global__ void __launch_bounds__(192) attn_bwd_kernel(const __grid_constant__ C
     }
     // ------------------------------------------------------------ dV / dK epilogue
     // (bar_dq of the last iteration covered every MMA issued by the CTA)
-    for (int c = 0; c < p.dn; c += 16) {
+    for (int c = half * 16; c < p.dn; c += 32) {
       uint32_t rv[16], rk[16];
       tmem_ld16(lane_addr + DV_COL + c, rv);
       tmem_ld16(lane_addr + DK_COL + c, rk);
@@ -571,13 +705,20 @@ __global__ void __launch_bounds__(192) attn_bwd_kernel(const __grid_constant__ C
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem);
+  if (warp == 0) tmem_dealloc_rt(tmem, (uint32_t)p.tmem_cols);
 }
 
 }  // namespace tb
 
 // ------------------------------------------------------------------------------------ host side
 using namespace tb;
+
+static long long* g_attn_trace = nullptr;
+// debug hook (not part of the reference-facing surface): timestamps of CTA (0,0,0) of the next forward launches
+extern "C" int tb_attn_debug_trace(void* buf) {
+  g_attn_trace = (long long*)buf;
+  return TB_OK;
+}
 
 static int make_head_map(CUtensorMap* m, const void* base, long long ld, int B, int heads, int N,
                          int d) {
@@ -588,19 +729,21 @@ static int make_head_map(CUtensorMap* m, const void* base, long long ld, int B, 
 }
 
 static int check_attn_args(const char* fn, int B, int heads, int Nq, int Nk, int d, long long ldq,
-                           long long ldk, long long ldv) {
+                           long long ldk, long long ldv, int causal) {
   TB_REQUIRE(B > 0 && heads > 0 && Nq > 0 && Nk > 0, TB_E_SHAPE, "%s: bad sizes", fn);
   TB_REQUIRE(d % 8 == 0 && d >= 8 && d <= 192, TB_E_SHAPE, "%s: head_dim %d unsupported (d %% 8 == 0, d <= 192)", fn, d);
   TB_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0, TB_E_ALIGN, "%s: row strides must be multiples of 8", fn);
   TB_REQUIRE(ldq >= (long long)heads * d && ldk >= (long long)heads * d && ldv >= (long long)heads * d,
              TB_E_SHAPE, "%s: row stride smaller than heads*d", fn);
+  TB_REQUIRE(causal == 0 || causal == 1, TB_E_ARG, "%s: causal must be 0 or 1", fn);
+  TB_REQUIRE(!causal || Nq == Nk, TB_E_SHAPE, "%s: causal attention needs Nq == Nk", fn);
   return TB_OK;
 }
 
 template <int NB, int STAGES>
 static int launch_attn_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                            const AttnParams& p, int B, cudaStream_t st) {
-  constexpr int smem = NB * ABOX * (1 + 2 * STAGES) + 2 * ABOX + 256 + 1024;
+  constexpr int smem = NB * ABOX * (1 + 2 * STAGES) + ABOX + 1024 + 256 + 1024;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<NB, STAGES>,
@@ -612,14 +755,14 @@ static int launch_attn_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const C
     configured = true;
   }
   dim3 grid((p.Nq + 127) / 128, p.heads, B);
-  attn_fwd_kernel<NB, STAGES><<<grid, 192, smem, st>>>(tq, tk, tv, p);
+  attn_fwd_kernel<NB, STAGES><<<grid, 320, smem, st>>>(tq, tk, tv, p);
   return check_launch("attn_fwd_kernel");
 }
 
 template <int NB, int STAGES>
 static int launch_attn_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                            const CUtensorMap& tdo, const AttnParams& p, int B, cudaStream_t st) {
-  constexpr int smem = NB * ABOX * (2 + 2 * STAGES) + (NB == 3 ? 2 : 4) * ABOX + 1024 + 256 + 1024;
+  constexpr int smem = NB * ABOX * (2 + 2 * STAGES) + 2 * ABOX + 1024 + 256 + 1024;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<NB, STAGES>,
@@ -631,17 +774,17 @@ static int launch_attn_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const C
     configured = true;
   }
   dim3 grid((p.Nk + 127) / 128, p.heads, B);
-  attn_bwd_kernel<NB, STAGES><<<grid, 192, smem, st>>>(tq, tk, tv, tdo, p);
+  attn_bwd_kernel<NB, STAGES><<<grid, 320, smem, st>>>(tq, tk, tv, tdo, p);
   return check_launch("attn_bwd_kernel");
 }
 
 extern "C" int tb_attn_fwd_f16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                                int64_t ldv, void* o, int64_t ldo, float* lse, int B, int heads, int Nq,
-                               int Nk, int d, float scale, void* stream) {
+                               int Nk, int d, float scale, int causal, void* stream) {
   int rc = tb_check_device();
   if (rc) return rc;
   TB_REQUIRE(q && k && v && o, TB_E_ARG, "tb_attn_fwd_f16: null pointer");
-  rc = check_attn_args("tb_attn_fwd_f16", B, heads, Nq, Nk, d, ldq, ldk, ldv);
+  rc = check_attn_args("tb_attn_fwd_f16", B, heads, Nq, Nk, d, ldq, ldk, ldv, causal);
   if (rc) return rc;
   TB_REQUIRE(ldo % 8 == 0, TB_E_ALIGN, "tb_attn_fwd_f16: ldo %% 8");
   CUtensorMap tq, tk, tv;
@@ -651,14 +794,17 @@ extern "C" int tb_attn_fwd_f16(const void* q, int64_t ldq, const void* k, int64_
   AttnParams p;
   memset(&p, 0, sizeof(p));
   p.Nq = Nq; p.Nk = Nk; p.heads = heads; p.d = d; p.dn = (d + 15) / 16 * 16;
+  p.causal = causal;
+  p.tmem_cols = (128 + p.dn + 16 <= 256) ? 256 : 512;
   p.scale = scale;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.O = (__half*)o; p.ldo = ldo; p.lse = lse;
+  p.trace = g_attn_trace;
   p.n_inner = (Nk + 127) / 128;
   const int nb = (d + 63) / 64;
   cudaStream_t st = (cudaStream_t)stream;
   if (nb == 1) return launch_attn_fwd<1, 2>(tq, tk, tv, p, B, st);
-  if (nb == 2) return launch_attn_fwd<2, 2>(tq, tk, tv, p, B, st);
+  if (nb == 2) return launch_attn_fwd<2, 1>(tq, tk, tv, p, B, st);
   return launch_attn_fwd<3, 1>(tq, tk, tv, p, B, st);
 }
 
@@ -666,11 +812,11 @@ extern "C" int tb_attn_bwd_f16(const void* q, int64_t ldq, const void* k, int64_
                                int64_t ldv, const void* o, int64_t ldo, const void* dO, int64_t lddo,
                                const float* lse, float* delta, float* dQacc, int64_t lddq, void* dK,
                                int64_t lddk, void* dV, int64_t lddv, int B, int heads, int Nq, int Nk,
-                               int d, float scale, void* stream) {
+                               int d, float scale, int causal, void* stream) {
   int rc = tb_check_device();
   if (rc) return rc;
   TB_REQUIRE(q && k && v && o && dO && lse && delta && dK && dV, TB_E_ARG, "tb_attn_bwd_f16: null pointer");
-  rc = check_attn_args("tb_attn_bwd_f16", B, heads, Nq, Nk, d, ldq, ldk, ldv);
+  rc = check_attn_args("tb_attn_bwd_f16", B, heads, Nq, Nk, d, ldq, ldk, ldv, causal);
   if (rc) return rc;
   TB_REQUIRE(ldo % 8 == 0 && lddo % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0 && lddq % 4 == 0,
              TB_E_ALIGN, "tb_attn_bwd_f16: stride alignment");
@@ -694,6 +840,8 @@ extern "C" int tb_attn_bwd_f16(const void* q, int64_t ldq, const void* k, int64_
   AttnParams p;
   memset(&p, 0, sizeof(p));
   p.Nq = Nq; p.Nk = Nk; p.heads = heads; p.d = d; p.dn = (d + 15) / 16 * 16;
+  p.causal = causal;
+  p.tmem_cols = (128 + 2 * p.dn <= 256) ? 256 : 512;
   p.scale = scale;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = const_cast<float*>(lse);
@@ -703,7 +851,7 @@ extern "C" int tb_attn_bwd_f16(const void* q, int64_t ldq, const void* k, int64_
   p.dV = (__half*)dV; p.lddv = lddv;
   p.n_inner = (Nq + 127) / 128;
   const int nb = (d + 63) / 64;
-  if (nb == 1) return launch_attn_bwd<1, 2>(tq, tk, tv, tdo, p, B, st);
+  if (nb == 1) return launch_attn_bwd<1, 1>(tq, tk, tv, tdo, p, B, st);
   if (nb == 2) return launch_attn_bwd<2, 1>(tq, tk, tv, tdo, p, B, st);
   return launch_attn_bwd<3, 1>(tq, tk, tv, tdo, p, B, st);
 }

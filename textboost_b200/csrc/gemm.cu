@@ -5,8 +5,12 @@
 //
 // CTA = 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane issues
 // tcgen05.mma), warps 2..5 = epilogue (tcgen05.ld -> registers -> fused bias/act/residual -> HBM).
-// One 128 x BN output tile per CTA; STAGES-deep smem ring guarded by full/empty mbarriers;
-// up to two CTAs co-reside on an SM so one tile's epilogue overlaps the other's mainloop.
+// PERSISTENT: one CTA per SM walks the 128 x BN output tiles (n fastest, so concurrently running CTAs
+// share the A tile through L2).  Three pipelines run across tile boundaries: the STAGES-deep smem ring
+// (TMA <-> MMA, full/empty mbarriers), a two-deep TMEM accumulator ring (MMA <-> epilogue,
+// tmem_full/tmem_empty) so the epilogue of tile i overlaps the mainloop of tile i+1, and the tile walk.
+#include <stdlib.h>
+
 #include "host_util.h"
 #include "sm100.cuh"
 
@@ -16,6 +20,7 @@ struct GemmParams {
   int M, N, K;        // logical sizes (K = 9*Cin for conv)
   int num_kb;         // number of 64-wide k blocks
   int n_tiles;        // ceil(N / BN)
+  int m_tiles;        // ceil(M / 128)
   // conv geometry (CONV only)
   int H, W, kb_per_tap;
   // epilogue
@@ -30,6 +35,7 @@ struct GemmParams {
   float alpha;
   int act;
   int out_kind;
+  int tma_store;      // fp16 output through shared memory + TMA tile stores (full 128-byte lines)
 };
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -44,6 +50,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
+constexpr int C_BOX_BYTES = BM * 64 * 2;    // 16 KiB
 
 template <int BN>
 constexpr int tmem_cols() {
@@ -51,38 +58,45 @@ constexpr int tmem_cols() {
 }
 
 template <int BN, int STAGES, bool CONV>
-__global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                      const __grid_constant__ CUtensorMap tmB,
-                                                      const GemmParams p) {
+__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                         const __grid_constant__ CUtensorMap tmB,
+                                                         const __grid_constant__ CUtensorMap tmC,
+                                                         const GemmParams p) {
   constexpr int B_STAGE_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  constexpr int TMEM_COLS = tmem_cols<BN>();
+  constexpr int ACC_STRIDE = tmem_cols<BN>();       // columns per accumulator stage
+  constexpr int TMEM_COLS = 2 * ACC_STRIDE;         // two accumulator stages
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // manual 1 KiB alignment (SWIZZLE_128B atoms)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* sC = smem + STAGES * STAGE_BYTES;  // two [128 x 64] fp16 staging boxes for the TMA tile stores
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sC + 2 * C_BOX_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
-  uint64_t* tmem_full_bar = bars + 2 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;       // [2]
+  uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.x % p.n_tiles;
-  const int m_tile = blockIdx.x / p.n_tiles;
+  const int num_tiles = p.m_tiles * p.n_tiles;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_store) tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
-    mbar_init(smem_u32(tmem_full_bar), 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tmem_full_bar[a]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[a]), 128);
+    }
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
@@ -92,8 +106,12 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------ TMA producer (warp-uniform; one elected lane issues)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
       int cw = 0, ch = 0, cb = 0;
       if (CONV) {
         const int p0 = m_tile * BM;
@@ -101,23 +119,24 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         ch = (p0 / p.W) % p.H;
         cb = p0 / (p.W * p.H);
       }
-      int stage = 0;
-      uint32_t phase = 0;
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-        const uint32_t fb = smem_u32(&full_bar[stage]);
-        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-        const uint32_t sb = sa + A_STAGE_BYTES;
-        mbar_expect_tx(fb, STAGE_BYTES);
-        if (CONV) {
-          const int tap = kb / p.kb_per_tap;
-          const int c0 = (kb - tap * p.kb_per_tap) * BK;
-          const int ky = tap / 3, kx = tap - ky * 3;
-          tma_load_4d(sa, &tmA, fb, c0, cw + kx - 1, ch + ky - 1, cb);
-        } else {
-          tma_load_2d(sa, &tmA, fb, kb * BK, m_tile * BM);
+        if (elect_one()) {
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+          mbar_expect_tx(fb, STAGE_BYTES);
+          if (CONV) {
+            const int tap = kb / p.kb_per_tap;
+            const int c0 = (kb - tap * p.kb_per_tap) * BK;
+            const int ky = tap / 3, kx = tap - ky * 3;
+            tma_load_4d(sa, &tmA, fb, c0, cw + kx - 1, ch + ky - 1, cb);
+          } else {
+            tma_load_2d(sa, &tmA, fb, kb * BK, m_tile * BM);
+          }
+          tma_load_2d(sb, &tmB, fb, kb * BK, n_tile * BN);
         }
-        tma_load_2d(sb, &tmB, fb, kb * BK, n_tile * BN);
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -125,61 +144,83 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
+    // ------------------------------------------------ MMA issuer (warp-uniform; one elected lane issues)
+    constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0, 0);
+    const uint32_t dhi = umma_desc_hi_sw128(1024);
+    int stage = 0;
+    uint32_t phase = 0;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int acc = lt & 1;
+      mbar_wait(smem_u32(&tmem_empty_bar[acc]), ((lt >> 1) & 1) ^ 1);  // epilogue drained this stage
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-        const uint32_t sb = sa + A_STAGE_BYTES;
+        const uint32_t alo = umma_desc_lo(sa, 16), blo = umma_desc_lo(sa + A_STAGE_BYTES, 16);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t ad = umma_desc_sw128(sa + k * 32, 16, 1024);
-          const uint64_t bd = umma_desc_sw128(sb + k * 32, 16, 1024);
-          umma_f16_ss(tmem_base, ad, bd, idesc, (kb | k) != 0);
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16_ss(d_tmem, umma_desc_pack(alo + k * 2, dhi), umma_desc_pack(blo + k * 2, dhi), idesc,
+                        (kb | k) != 0);
+          umma_commit(smem_u32(&empty_bar[stage]));  // frees the smem slot when these MMAs retire
+          if (kb == p.num_kb - 1) umma_commit(smem_u32(&tmem_full_bar[acc]));
         }
-        umma_commit(smem_u32(&empty_bar[stage]));  // frees the smem slot when these MMAs retire
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit(smem_u32(tmem_full_bar));
     }
   } else {
     // ------------------------------------------------ epilogue (warps 2..5)
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
-    const long long m = (long long)m_tile * BM + row;
-    mbar_wait(smem_u32(tmem_full_bar), 0);
-    tc_fence_after();
-    const bool row_ok = m < p.M;
-    const __half* rv = nullptr;
-    if (p.rowvec && row_ok) rv = p.rowvec + (m / p.rows_per_group) * (long long)p.N;
-    const __half* res = nullptr;
-    const float* res32 = nullptr;
-    if (p.residual && row_ok) {
-      if (p.res_f32) res32 = reinterpret_cast<const float*>(p.residual) + m * p.ldr;
-      else res = reinterpret_cast<const __half*>(p.residual) + m * p.ldr;
-    }
+    const bool issuer = threadIdx.x == 64;
+    int lt = 0;
+    uint32_t n_box = 0;  // staging boxes written so far (selects the buffer)
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int acc = lt & 1;
+      const long long m = (long long)m_tile * BM + row;
+      mbar_wait(smem_u32(&tmem_full_bar[acc]), (lt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc_addr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
+      const bool row_ok = m < p.M;
+      const __half* rv = nullptr;
+      if (p.rowvec && row_ok) rv = p.rowvec + (m / p.rows_per_group) * (long long)p.N;
+      const __half* res = nullptr;
+      const float* res32 = nullptr;
+      if (p.residual && row_ok) {
+        if (p.res_f32) res32 = reinterpret_cast<const float*>(p.residual) + m * p.ldr;
+        else res = reinterpret_cast<const __half*>(p.residual) + m * p.ldr;
+      }
 
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c, r);
-      tmem_ld_wait();
-      if (row_ok) {
+      for (int c = 0; c < BN; c += 32) {
+        // a full 64-column box goes through shared memory and one TMA store; a 32-column remainder
+        // (BN = 160, 32) and fp32 outputs are written from registers
+        const bool staged = p.tma_store && ((c & ~63) + 64 <= BN);
+        uint8_t* box = sC + (n_box & 1) * C_BOX_BYTES;
+        if (staged && (c & 63) == 0) {
+          if (issuer) tma_store_wait_read<1>();  // the store that last used this buffer has read it out
+          named_bar_sync(1, 128);
+        }
+        uint32_t r[32];
+        tmem_ld32(acc_addr + c, r);
+        tmem_ld_wait();
         const int n0 = n_tile * BN + c;
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           const int n = n0 + j;
-          if (n < p.N) {
-            float v[8];
+          float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j + i]) * p.alpha;
+          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j + i]) * p.alpha;
+          if (row_ok && n < p.N) {
             if (p.bias) {
               const uint4 q = *reinterpret_cast<const uint4*>(p.bias + n);
               const __half2* h = reinterpret_cast<const __half2*>(&q);
@@ -220,6 +261,16 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
               v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
               v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
             }
+          }
+          if (staged) {
+            uint4 o;
+            o.x = pack_half2(v[0], v[1]);
+            o.y = pack_half2(v[2], v[3]);
+            o.z = pack_half2(v[4], v[5]);
+            o.w = pack_half2(v[6], v[7]);
+            const int chunk = ((c & 63) + j) >> 3;  // 16-byte chunk inside the 128-byte box row
+            *reinterpret_cast<uint4*>(box + row * 128 + ((chunk ^ (row & 7)) << 4)) = o;
+          } else if (row_ok && n < p.N) {
             if (p.out_kind == TB_OUT_F16) {
               uint4 o;
               o.x = pack_half2(v[0], v[1]);
@@ -242,8 +293,20 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
             }
           }
         }
+        if (staged && (c & 63) == 32) {
+          fence_async_smem();
+          named_bar_sync(1, 128);
+          if (issuer) {
+            tma_store_2d(&tmC, smem_u32(box), n_tile * BN + (c & ~63), m_tile * BM);
+            tma_store_commit();
+          }
+          ++n_box;
+        }
       }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&tmem_empty_bar[acc]));  // 128 arrivals release the accumulator stage
     }
+    if (issuer) tma_store_wait_read<0>();
   }
 
   tc_fence_before();
@@ -255,12 +318,12 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
 
 template <int BN, int STAGES>
 constexpr int gemm_smem_bytes() {
-  return STAGES * (A_STAGE_BYTES + BN * BK * 2) + (2 * STAGES + 2) * 8 + 1024;
+  return STAGES * (A_STAGE_BYTES + BN * BK * 2) + 2 * C_BOX_BYTES + (2 * STAGES + 5) * 8 + 1024;
 }
 
 template <int BN, int STAGES, bool CONV>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, int m_tiles,
-                       cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                       GemmParams& p, int m_tiles, cudaStream_t st) {
   constexpr int smem = gemm_smem_bytes<BN, STAGES>();
   static bool configured = false;
   if (!configured) {
@@ -273,8 +336,10 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
     configured = true;
   }
   p.n_tiles = (p.N + BN - 1) / BN;
-  dim3 grid(p.n_tiles * m_tiles);
-  gemm_tc_kernel<BN, STAGES, CONV><<<grid, 192, smem, st>>>(tmA, tmB, p);
+  p.m_tiles = m_tiles;
+  const int tiles = p.n_tiles * m_tiles;
+  dim3 grid(tiles < num_sms() ? tiles : num_sms());
+  gemm_tc_kernel<BN, STAGES, CONV><<<grid, 192, smem, st>>>(tmA, tmB, tmC, p);
   return check_launch("gemm_tc_kernel");
 }
 
@@ -302,12 +367,24 @@ static int dispatch_gemm(const CUtensorMap& tmA, const void* Bw, long long ldb, 
     int rc = make_tmap_f16(&tmB, Bw, 2, dims, strides, box);
     if (rc) return rc;
   }
+  // fp16 outputs leave through shared memory + TMA tile stores (box 64 columns x 128 rows)
+  CUtensorMap tmC = tmB;
+  p.tma_store = 0;
+  static const bool direct_store = getenv("TB_GEMM_DIRECT_STORE") != nullptr;  // diagnostic switch
+  if (p.out_kind == TB_OUT_F16 && bn >= 64 && !direct_store) {
+    uint64_t dims[2] = {(uint64_t)p.N, (uint64_t)p.M};
+    uint64_t strides[1] = {(uint64_t)p.ldc * 2};
+    uint32_t box[2] = {64u, (uint32_t)BM};
+    int rc = make_tmap_f16(&tmC, p.C, 2, dims, strides, box);
+    if (rc) return rc;
+    p.tma_store = 1;
+  }
   switch (bn) {
-    case 256: return launch_gemm<256, 4, CONV>(tmA, tmB, p, m_tiles, st);
-    case 160: return launch_gemm<160, 3, CONV>(tmA, tmB, p, m_tiles, st);
-    case 128: return launch_gemm<128, 3, CONV>(tmA, tmB, p, m_tiles, st);
-    case 64: return launch_gemm<64, 4, CONV>(tmA, tmB, p, m_tiles, st);
-    default: return launch_gemm<32, 4, CONV>(tmA, tmB, p, m_tiles, st);
+    case 256: return launch_gemm<256, 4, CONV>(tmA, tmB, tmC, p, m_tiles, st);
+    case 160: return launch_gemm<160, 4, CONV>(tmA, tmB, tmC, p, m_tiles, st);
+    case 128: return launch_gemm<128, 4, CONV>(tmA, tmB, tmC, p, m_tiles, st);
+    case 64: return launch_gemm<64, 4, CONV>(tmA, tmB, tmC, p, m_tiles, st);
+    default: return launch_gemm<32, 4, CONV>(tmA, tmB, tmC, p, m_tiles, st);
   }
 }
 

@@ -49,6 +49,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
+// named barrier over a subset of the CTA's warps (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int n) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+
 // ---------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_async_smem() {  // generic-proxy smem writes -> async proxy
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -95,6 +100,21 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, 
       "%4, %5, %6, %7}], [%2];" ::"r"(dst),
       "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
+}
+
+// smem -> global tile store (bulk async group); the tensor map clips rows / columns past the tensor bounds
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// wait until at most N of this thread's bulk groups still have to READ their shared-memory source
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
 // ---------------------------------------------------------------- TMEM
@@ -206,6 +226,24 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// The same descriptor split in two 32-bit words, so an MMA loop advances an operand with ONE integer add on
+// the low word (byte offset >> 4) and keeps the constant high word in a uniform register.
+// IMPORTANT (measured, scripts/micro/mma_issue.cu): tcgen05.mma must be issued from warp-uniform code
+// (whole warp in the branch, `if (elect_one())` around the MMAs).  Issued from a divergent `if (lane == 0)`
+// region the compiler wraps every UTCHMMA in an ELECT / R2UR / BRA.U.ANY sequence that costs ~45-80 cycles
+// per instruction; issued uniformly it costs one UIADD3 + UTCHMMA and reaches the 128*N/256-cycle floor.
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+__device__ __forceinline__ uint32_t umma_desc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint64_t umma_desc_pack(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
   return d;
 }
 

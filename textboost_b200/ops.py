@@ -64,7 +64,7 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, *, bias=None, rowvec=None, residua
     return out
 
 
-def attn_fwd(q, k, v, heads, scale=None, out=None):
+def attn_fwd(q, k, v, heads, scale=None, out=None, causal=False):
     """q [B,Nq,*] k,v [B,Nk,*] fp16 views whose last dim holds heads*d columns (row stride free).
     Returns (o [B,Nq,heads*d], lse [B,heads,Nq])."""
     B, Nq, Ch = q.shape
@@ -77,11 +77,11 @@ def attn_fwd(q, k, v, heads, scale=None, out=None):
         out = torch.empty((B, Nq, Ch), device=q.device, dtype=F16)
     lse = torch.empty((B, heads, Nq), device=q.device, dtype=F32)
     C.call("tb_attn_fwd_f16", C.ptr(q), q.stride(1), C.ptr(k), k.stride(1), C.ptr(v), v.stride(1),
-           C.ptr(out), out.stride(1), C.ptr(lse), B, heads, Nq, Nk, d, scale, C.stream_ptr())
+           C.ptr(out), out.stride(1), C.ptr(lse), B, heads, Nq, Nk, d, scale, int(causal), C.stream_ptr())
     return out, lse
 
 
-def attn_bwd(q, k, v, o, do, lse, heads, scale=None, need_dq=True, dk=None, dv=None):
+def attn_bwd(q, k, v, o, do, lse, heads, scale=None, need_dq=True, dk=None, dv=None, causal=False):
     """Returns (dq_acc fp32 [B,Nq,C] or None, dk, dv fp16 [B,Nk,C])."""
     B, Nq, Ch = q.shape
     Nk = k.shape[1]
@@ -97,7 +97,7 @@ def attn_bwd(q, k, v, o, do, lse, heads, scale=None, need_dq=True, dk=None, dv=N
     C.call("tb_attn_bwd_f16", C.ptr(q), q.stride(1), C.ptr(k), k.stride(1), C.ptr(v), v.stride(1),
            C.ptr(o), o.stride(1), C.ptr(do), do.stride(1), C.ptr(lse), C.ptr(delta), C.ptr(dq),
            dq.stride(1) if dq is not None else 0, C.ptr(dk), dk.stride(1),
-           C.ptr(dv), dv.stride(1), B, heads, Nq, Nk, d, scale, C.stream_ptr())
+           C.ptr(dv), dv.stride(1), B, heads, Nq, Nk, d, scale, int(causal), C.stream_ptr())
     if need_dq:
         C.launch_count += 1  # the dQ accumulator memset node
     return dq, dk, dv

@@ -23,6 +23,7 @@ from . import _cabi as C
 from . import ops
 from .clip import ClipEngine
 from .dp import GradSync
+from .optim import FusedAdamW
 from .unet import UNetEngine
 
 F16 = torch.float16
@@ -51,32 +52,33 @@ class TextBoostTrainer:
                  mixed_precision="fp16", process_group=None):
         self.unet, self.te, self.te0 = unet, text_encoder, original_text_encoder
         self.dev = text_encoder.device
-        self.lr, self.emb_lr = learning_rate, emb_learning_rate
-        self.b1, self.b2, self.wd, self.eps = adam_beta1, adam_beta2, adam_weight_decay, adam_epsilon
-        self.max_grad_norm = max_grad_norm if max_grad_norm is not None else 0.0
         self.kpl_weight, self.kpl_kind = kpl_weight, {"cos": 0, "mse": 1}[kpl_type]
         self.v_pred = {"epsilon": False, "v_prediction": True}[prediction_type]
-        self.mixing = mixing
         assert kpl_weight <= 0 or original_text_encoder is not None
-        st = text_encoder.state
-        self.exp_avg = torch.zeros_like(st.params)
-        self.exp_avg_sq = torch.zeros_like(st.params)
-        # [0] loss scale [1] growth tracker [2] found_inf [3] sum g^2 [4] step [5] frozen-row decay ...
-        self.opt_state = torch.zeros(16, device=self.dev, dtype=F32)
-        self.opt_state[0] = 65536.0 if mixed_precision == "fp16" else 1.0
-        self.opt_state[5] = 1.0
-        text_encoder.decay = self.opt_state[5:6]
-        if mean_norm is None:
-            # train_textboost.py:1017: mean row norm of the resized embedding matrix
-            n = text_encoder.tok_base.norm(dim=-1).sum() + st.rows().norm(dim=-1).sum()
-            mean_norm = float(n / (text_encoder.tok_base.shape[0] + st.n_rows))
-        self.mean_norm = mean_norm
-        self.acp = alphas_cumprod(device=self.dev)
-        self.loss = torch.zeros(1, device=self.dev, dtype=F32)
-        self.added_norm = torch.zeros(1, device=self.dev, dtype=F32)
         self.sync = GradSync(process_group)
         self.world = self.sync.world
+        self.opt = FusedAdamW(text_encoder, lr=learning_rate, emb_lr=emb_learning_rate,
+                              betas=(adam_beta1, adam_beta2), weight_decay=adam_weight_decay, eps=adam_epsilon,
+                              max_grad_norm=max_grad_norm, mean_norm=mean_norm, mixing=mixing,
+                              mixed_precision=mixed_precision, world_size=self.world)
+        self.acp = alphas_cumprod(device=self.dev)
+        self.loss = torch.zeros(1, device=self.dev, dtype=F32)
         self._graph = None
+
+    # optimiser state under the names the tests / bench use
+    lr = property(lambda self: self.opt.param_groups[1]["lr"])
+    emb_lr = property(lambda self: self.opt.param_groups[0]["lr"])
+    b1 = property(lambda self: self.opt.betas[0])
+    b2 = property(lambda self: self.opt.betas[1])
+    wd = property(lambda self: self.opt.weight_decay)
+    eps = property(lambda self: self.opt.eps)
+    max_grad_norm = property(lambda self: self.opt.max_grad_norm)
+    mixing = property(lambda self: self.opt.mixing)
+    mean_norm = property(lambda self: self.opt.mean_norm)
+    opt_state = property(lambda self: self.opt.state)
+    added_norm = property(lambda self: self.opt.added_norm)
+    exp_avg = property(lambda self: self.opt.exp_avg)
+    exp_avg_sq = property(lambda self: self.opt.exp_avg_sq)
 
     # ------------------------------------------------------------------ pieces (also used by tests)
     def forward_backward(self, latents, noise, timesteps, input_ids, prior_ids=None):
@@ -109,15 +111,7 @@ class TextBoostTrainer:
         self.sync.all_reduce_(self.te.state.grads)
 
     def optimizer_step(self):
-        st = self.te.state
-        if self.mixing is not None and st.n_b:
-            parity = 1 if self.mixing == "object" else 0  # train_textboost.py:1119-1126
-            C.call("tb_optim_mix_mask", C.ptr(st.b_segment(st.grads)), st.n_b, st.D, st.r, parity,
-                   C.stream_ptr())
-        C.call("tb_adamw_fused_step", C.ptr(st.params), C.ptr(st.grads), C.ptr(self.exp_avg),
-               C.ptr(self.exp_avg_sq), st.n_lora, st.n_rows, st.D, self.lr, self.emb_lr, self.b1, self.b2,
-               self.eps, self.wd, self.max_grad_norm, 1.0 / self.world, self.mean_norm,
-               C.ptr(self.opt_state), C.ptr(self.added_norm), C.stream_ptr())
+        self.opt.step()
 
     # ------------------------------------------------------------------ the step
     def step(self, latents, noise, timesteps, input_ids, prior_ids=None):
