@@ -227,8 +227,17 @@ def kernel_family_timing(trainer, bt):
     ops.gemm = wrap("gemm", saved["gemm"], f_gemm)
     ops.attn_fwd = wrap("attn_fwd", saved["attn_fwd"], f_attn_fwd)
     ops.attn_bwd = wrap("attn_bwd", saved["attn_bwd"], f_attn_bwd)
+    step_args = (bt["latents"], bt["noise"], bt["timesteps"], bt["input_ids"], bt["prior_ids"])
     try:
-        trainer.step(bt["latents"], bt["noise"], bt["timesteps"], bt["input_ids"], bt["prior_ids"])
+        # two untimed eager passes refill the caching allocator after the graph's private pool is gone
+        # (a cudaMalloc between the two events would be billed to the kernel), then the GPU is parked
+        # behind a sleep kernel so the host runs ahead and the bracketed kernels execute back to back.
+        for _ in range(2):
+            trainer.step(*step_args)
+        torch.cuda.synchronize()
+        rec.clear()
+        torch.cuda._sleep(int(0.3 * 1.9e9))
+        trainer.step(*step_args)
         torch.cuda.synchronize()
     finally:
         for n, f in saved.items():

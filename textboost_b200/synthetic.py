@@ -231,3 +231,75 @@ def build_trainer(model: str = "sd15", device="cuda", seed: int = 42, n_added: i
     if keep_sd:
         tr.synthetic.update(unet_sd=usd, clip_sd=csd)
     return tr
+
+
+# ---------------------------------------------------------------------------------- offline stand-ins
+class LiteralTokenizer:
+    """Duck-typed tokenizer for a box with no vocab.json / merges.txt: whitespace words map to stable ids in
+    [1000, 40000]; BOS/EOS are CLIP's.  Implements exactly what textboost.utils.add_token uses
+    (encode / add_tokens / convert_tokens_to_ids / __len__) plus __call__ -> padded [1, L] ids."""
+
+    def __init__(self, vocab_size: int = 49408, model_max_length: int = 77):
+        self.base, self.model_max_length = vocab_size, model_max_length
+        self.added: Dict[str, int] = {}
+
+    def __len__(self):
+        return self.base + len(self.added)
+
+    def _word(self, w: str) -> int:
+        if w in self.added:
+            return self.added[w]
+        h = 0
+        for c in w.encode():
+            h = (h * 131 + c) % 39001
+        return 1000 + h
+
+    def encode(self, text: str, add_special_tokens: bool = True):
+        ids = [self._word(w) for w in text.split()]
+        return [BOS] + ids + [EOS] if add_special_tokens else ids
+
+    def add_tokens(self, tokens) -> int:
+        n = 0
+        for t in ([tokens] if isinstance(tokens, str) else tokens):
+            if t not in self.added:
+                self.added[t] = len(self)
+                n += 1
+        return n
+
+    def convert_tokens_to_ids(self, tokens):
+        if isinstance(tokens, str):
+            return self._word(tokens)
+        return [self._word(t) for t in tokens]
+
+    def __call__(self, text: str):
+        ids = self.encode(text)[:self.model_max_length]
+        row = torch.full((1, self.model_max_length), EOS, dtype=torch.int64)
+        row[0, :len(ids)] = torch.tensor(ids)
+        return row
+
+
+def write_pretrained(directory: str, model: str = "tiny", seed: int = 0, prediction_type: str = "epsilon"):
+    """Write a random-init checkpoint in the diffusers directory layout (unet/, text_encoder/, scheduler/)
+    that train_textboost.py's from_pretrained calls read (train_textboost.py:633-656)."""
+    import json
+    import os
+    from safetensors.torch import save_file
+    from . import text_encoder as te_mod
+    from . import unet_model
+    ucfg, ccfg = model_configs(model)
+    usd = {k: v.contiguous() for k, v in random_unet_sd(ucfg, "cpu", seed).items()}
+    csd = {k: v.contiguous() for k, v in random_clip_sd(ccfg, ccfg.vocab_size, "cpu", seed + 1).items()}
+    os.makedirs(os.path.join(directory, "unet"), exist_ok=True)
+    os.makedirs(os.path.join(directory, "text_encoder"), exist_ok=True)
+    os.makedirs(os.path.join(directory, "scheduler"), exist_ok=True)
+    save_file(usd, os.path.join(directory, "unet", "diffusion_pytorch_model.safetensors"), metadata={"format": "pt"})
+    with open(os.path.join(directory, "unet", "config.json"), "w") as f:
+        json.dump(unet_model.config_to_dict(ucfg), f, indent=2)
+    save_file(csd, os.path.join(directory, "text_encoder", "model.safetensors"), metadata={"format": "pt"})
+    with open(os.path.join(directory, "text_encoder", "config.json"), "w") as f:
+        json.dump({**te_mod.config_to_dict(ccfg), "architectures": ["CLIPTextModel"],
+                   "model_type": "clip_text_model"}, f, indent=2)
+    with open(os.path.join(directory, "scheduler", "scheduler_config.json"), "w") as f:
+        json.dump({"_class_name": "DDPMScheduler", "num_train_timesteps": 1000, "beta_start": 0.00085,
+                   "beta_end": 0.012, "beta_schedule": "scaled_linear", "prediction_type": prediction_type}, f)
+    return usd, csd

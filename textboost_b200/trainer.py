@@ -82,30 +82,54 @@ class TextBoostTrainer:
 
     # ------------------------------------------------------------------ pieces (also used by tests)
     def forward_backward(self, latents, noise, timesteps, input_ids, prior_ids=None):
-        """Everything up to (not including) the all-reduce: fills te.state.grads, self.loss."""
+        """Everything up to (not including) the all-reduce: fills te.state.grads, self.loss.
+
+        The knowledge-preservation branch (trainable + frozen encoder on the prior prompts, the KPL term and
+        its backward, train_textboost.py:1096-1106) does not depend on the UNet, so it is enqueued on a side
+        stream and overlaps the UNet forward / activation-backward; the two branches meet before the
+        instance-prompt encoder backward.  Inside capture() the fork / join become graph edges."""
         te, unet = self.te, self.unet
         B = latents.shape[0]
         use_kpl = self.kpl_weight > 0 and prior_ids is not None
-        te.pack_lora()
-        noisy, target = ops.add_noise(latents, noise, timesteps, self.acp, self.v_pred)
-        ids = torch.cat([input_ids, prior_ids], 0) if use_kpl else input_ids
-        h = te.forward(ids, save_for_backward=True)  # fp32 [B(+Bp), L, D]
-        Bt, L, D = h.shape
-        ehs = ops.cast_f32_f16(h[:B].view(B * L, D)).view(B, L, D)
-        pred = unet.forward(noisy, timesteps, ehs)
-        self.loss.zero_()
         scale = self.opt_state[0:1]
-        dpred = ops.mse_fwd_bwd(pred, target, self.loss, 1.0, scale)
-        d_h = torch.zeros((Bt, L, D), device=self.dev, dtype=F32)
-        unet.backward(dpred, d_h[:B])
+        main = torch.cuda.current_stream()
+        te.pack_lora()
+        self.loss.zero_()
         if use_kpl:
-            h0 = self.te0.forward(prior_ids)
-            Mp = (Bt - B) * L
-            C.call("tb_kpl_fwd_bwd", C.ptr(h[B:]), C.ptr(h0), Mp, D, self.kpl_kind, float(self.kpl_weight),
-                   C.ptr(scale), C.ptr(self.loss), C.ptr(d_h[B:]), C.stream_ptr())
-        te.backward(d_h)
+            side = self._side_stream()
+            self._loss_kpl.zero_()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                hp = te.forward(prior_ids, save_for_backward=True)
+                ctx_p = te.pop_ctx()
+                h0 = self.te0.forward(prior_ids)
+                Bp, L, D = hp.shape
+                d_hp = torch.zeros((Bp, L, D), device=self.dev, dtype=F32)
+                C.call("tb_kpl_fwd_bwd", C.ptr(hp), C.ptr(h0), Bp * L, D, self.kpl_kind, float(self.kpl_weight),
+                       C.ptr(scale), C.ptr(self._loss_kpl), C.ptr(d_hp), C.stream_ptr())
+                te.backward(d_hp, ctx=ctx_p)
+        noisy, target = ops.add_noise(latents, noise, timesteps, self.acp, self.v_pred)
+        h = te.forward(input_ids, save_for_backward=True)  # fp32 [B, L, D]
+        ctx_i = te.pop_ctx()
+        _, L, D = h.shape
+        ehs = ops.cast_f32_f16(h.view(B * L, D)).view(B, L, D)
+        pred = unet.forward(noisy, timesteps, ehs)
+        dpred = ops.mse_fwd_bwd(pred, target, self.loss, 1.0, scale)
+        d_h = torch.zeros((B, L, D), device=self.dev, dtype=F32)
+        unet.backward(dpred, d_h)
+        if use_kpl:
+            main.wait_stream(side)  # gradient accumulation into state.grads is serialised from here on
+            self.loss.add_(self._loss_kpl)
+            C.launch_count += 1
+        te.backward(d_h, ctx=ctx_i)
         self._pred = pred
         return self.loss
+
+    def _side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+            self._loss_kpl = torch.zeros(1, device=self.dev, dtype=F32)
+        return self._side
 
     def all_reduce(self):
         self.sync.all_reduce_(self.te.state.grads)

@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""train_textboost.py — the reference CLI (/root/reference/train_textboost.py) over the B200 TextBoost step.
+
+Every flag of the reference's ``parse_args`` (:49-450) is kept with its name, type and default, including the
+quirks (``--disable_weighted_sample`` is store_true with default True, so the SNR-weighted timestep sampler
+of :991-997 is unreachable there; ``--no-disable_weighted_sample`` is added here to reach it).  ``main``
+follows the reference's set-up order (:598-939) through this package's mirrors of its classes —
+``TextBoostModel`` / ``UNet2DConditionModel`` ``.from_pretrained``, ``add_token``,
+``add_augmentation_tokens``, ``LoraConfig`` + ``add_adapter`` — and replaces the loop body (:1041-1149) with
+``TextBoostTrainer.step`` (one CUDA graph; one all-reduce of the flat LoRA + added-row gradient buffer).
+Launch one process per GPU with torchrun, as the reference does (README.md:82).
+
+Outputs are the reference's: ``<output_dir>/text_encoder/adapter_{config.json,model.safetensors}``,
+``<output_dir>/<token>.bin`` per added token, ``checkpoint-N/`` directories (here with a working resume).
+
+Out of scope this round: the image dataset / PIL augmentation / VAE encode front end and
+the validation sampler.  Latents therefore come from ``--latents_file`` (a ``torch.save``d dict with
+``latents`` [N,4,h,w] fp32 — already scaled by the VAE factor — ``input_ids`` [N,77] and optional
+``prior_ids`` [P,77]) or ``--synthetic_data``; both flags are additions, everything else is the reference's.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import logging
+import os
+import shutil
+import time
+import warnings
+
+import torch
+
+logger = logging.getLogger("textboost")
+
+# (name, kwargs) in the reference's order; help strings omitted on purpose (see the reference for prose)
+_FLAGS = [
+    ("pretrained_model_name_or_path", dict(type=str, default=None, required=True)),
+    ("revision", dict(type=str, default=None)), ("variant", dict(type=str, default=None)),
+    ("tokenizer_name", dict(type=str, default=None)), ("instance_data_dir", dict(type=str, default=None)),
+    ("instance", dict(type=str)), ("class_data_dir", dict(type=str, default=None)),
+    ("instance_token", dict(type=str, default=None)), ("class_token", dict(type=str, nargs="+", default=None)),
+    ("with_image_prior", dict(default=False, action="store_true")),
+    ("image_ppl_weight", dict(type=float, default=1.0)), ("kpl_weight", dict(type=float, default=0.1)),
+    ("kpl_type", dict(type=str, default="cos")), ("num_prior_images", dict(type=int, default=200)),
+    ("output_dir", dict(type=str, default="dreambooth-model")), ("seed", dict(type=int, default=42)),
+    ("resolution", dict(type=int, default=512)), ("center_crop", dict(default=False, action="store_true")),
+    ("train_batch_size", dict(type=int, default=1)), ("sample_batch_size", dict(type=int, default=4)),
+    ("max_train_steps", dict(type=int, default=500)), ("checkpointing_steps", dict(type=int, default=100)),
+    ("checkpoints_total_limit", dict(type=int, default=None)),
+    ("resume_from_checkpoint", dict(type=str, default=None)),
+    ("gradient_accumulation_steps", dict(type=int, default=1)),
+    ("gradient_checkpointing", dict(action="store_true")),
+    ("learning_rate", dict(type=float, default=5e-5)), ("emb_learning_rate", dict(type=float, default=1e-3)),
+    ("scale_lr", dict(action="store_true", default=False)), ("lr_scheduler", dict(type=str, default="constant")),
+    ("lr_warmup_steps", dict(type=int, default=500)), ("dataloader_num_workers", dict(type=int, default=2)),
+    ("adam_beta1", dict(type=float, default=0.9)), ("adam_beta2", dict(type=float, default=0.999)),
+    ("adam_weight_decay", dict(type=float, default=1e-2)), ("adam_epsilon", dict(type=float, default=1e-08)),
+    ("max_grad_norm", dict(default=1.0, type=float)), ("hub_token", dict(type=str, default=None)),
+    ("logging_dir", dict(type=str, default="logs")), ("allow_tf32", dict(action="store_true")),
+    ("report_to", dict(type=str, default="tensorboard")),
+    ("validation_prompts", dict(type=str, nargs="+", default=None)),
+    ("num_validation_images", dict(type=int, default=4)), ("validation_steps", dict(type=int, default=100)),
+    ("mixed_precision", dict(type=str, default=None, choices=["no", "fp16", "bf16"])),
+    ("prior_generation_precision", dict(type=str, default=None, choices=["no", "fp32", "fp16", "bf16"])),
+    ("concepts_list", dict(type=str, default=None)),
+    ("text_encoder_use_attention_mask", dict(action="store_true")),
+    ("skip_save_text_encoder", dict(action="store_true")),
+    ("class_labels_conditioning", dict(default=None)),
+    ("validation_scheduler", dict(type=str, default="DPMSolverMultistepScheduler",
+                                  choices=["DPMSolverMultistepScheduler", "DDPMScheduler"])),
+    ("no_safe_serialization", dict(action="store_true")),
+    ("placeholder_token", dict(type=str, default="<dog>")), ("initializer_token", dict(type=str, default="dog")),
+    ("unet_params_to_train", dict(type=str, default="none",
+                                  choices=["none", "crossattn_kv", "crossattn", "attn", "all"])),
+    ("augment", dict(default="none")), ("augment_ops", dict(type=str, default="object")),
+    ("augment_p", dict(type=float, default=0.8)), ("augment_prompt", dict(type=int, default=1)),
+    ("augment_inversion", dict(action="store_true", default=False)), ("num_samples", dict(type=int, default=None)),
+    ("lora_rank", dict(type=int, default=4)),
+    ("disable_weighted_sample", dict(action="store_true", default=True)),
+    ("null_prob", dict(type=float, default=0.1)), ("template", dict(type=str, default="textboost")),
+    ("mixing", dict(action="store_true", default=False)),
+]
+
+
+def parse_args(input_args=None):
+    parser = argparse.ArgumentParser(description="TextBoost training on B200 (reference CLI surface).")
+    for name, kw in _FLAGS:
+        parser.add_argument("--" + name, **kw)
+    # additions (not in the reference)
+    parser.add_argument("--no-disable_weighted_sample", dest="disable_weighted_sample", action="store_false",
+                        help="reach the SNR-weighted timestep sampler of train_textboost.py:991-997")
+    parser.add_argument("--latents_file", type=str, default=None,
+                        help="torch.save'd {'latents','input_ids'[, 'prior_ids']} replacing the image/VAE front end")
+    parser.add_argument("--synthetic_data", action="store_true",
+                        help="synthetic latents + literal prompt ids (BASELINE.json workload)")
+    parser.add_argument("--null_embedding", type=str, default=None,
+                        help="[77, hidden] tensor file; default: assets/null_emb_sd21base.pt when the width "
+                             "matches, else the frozen encoder's output for the empty prompt (SURVEY.md D6)")
+    parser.add_argument("--log_every", type=int, default=10, help="host read-back period of the loss scalar")
+    args = parser.parse_args(input_args)
+
+    # post-parse validation: train_textboost.py:435-448
+    if args.with_image_prior:
+        if args.class_data_dir is None:
+            raise ValueError("You must specify a data directory for class images.")
+        if args.class_token is None:
+            raise ValueError("You must specify prompt for class images.")
+    else:
+        if args.class_data_dir is not None:
+            warnings.warn("You need not use --class_data_dir without --with_image_prior.")
+        if args.class_token is not None:
+            warnings.warn("You need not use --class_token without --with_image_prior.")
+    if args.augment_inversion and not bool(args.augment_prompt):
+        raise ValueError("You need to use --augment_prompt=1 with --augment_prompt.")
+    return args
+
+
+# ------------------------------------------------------------------------------------ helpers
+def _unsupported(args):
+    """Modes of the reference CLI outside the hot path built here: fail loudly."""
+    if args.with_image_prior:
+        raise NotImplementedError("--with_image_prior (image prior batch) is not built (SURVEY.md §8 f4)")
+    if args.unet_params_to_train != "none":
+        raise NotImplementedError("--unet_params_to_train: the UNet is frozen on this path (SURVEY.md §8 f4)")
+    if args.lora_rank <= 0:
+        raise NotImplementedError("--lora_rank 0 (full text-encoder fine-tune) is not built (SURVEY.md §8 f4)")
+    if args.gradient_accumulation_steps != 1:
+        raise NotImplementedError("gradient accumulation is not supported (the reference forbids it with >1 process)")
+    if args.lr_scheduler != "constant":
+        raise NotImplementedError("only the reference's constant LR schedule is built")
+    if args.mixed_precision not in (None, "fp16"):
+        raise NotImplementedError("the B200 path computes in fp16 with fp32 master weights (--mixed_precision fp16)")
+    if args.validation_prompts:
+        warnings.warn("validation sampling is out of scope (SURVEY.md §8 f3): --validation_prompts ignored")
+
+
+def load_scheduler_config(path):
+    """diffusers DDPMScheduler config (scheduler/scheduler_config.json) -> dict with the fields the step uses."""
+    cfg = {"num_train_timesteps": 1000, "beta_start": 0.00085, "beta_end": 0.012,
+           "beta_schedule": "scaled_linear", "prediction_type": "epsilon"}
+    f = os.path.join(path, "scheduler", "scheduler_config.json")
+    if os.path.exists(f):
+        with open(f) as fh:
+            raw = json.load(fh)
+        cfg.update({k: raw[k] for k in cfg if k in raw})
+    if cfg["beta_schedule"] != "scaled_linear":
+        raise NotImplementedError(f"beta_schedule {cfg['beta_schedule']!r}: SD checkpoints use scaled_linear")
+    return cfg
+
+
+def load_tokenizer(args):
+    """transformers tokenizer when its files exist; otherwise the literal-id stand-in used by the synthetic
+    workload (no vocab.json / merges.txt exist offline)."""
+    from textboost_b200 import synthetic
+    d = args.tokenizer_name or os.path.join(args.pretrained_model_name_or_path, "tokenizer")
+    if os.path.exists(os.path.join(d, "vocab.json")):
+        from transformers import AutoTokenizer
+        return AutoTokenizer.from_pretrained(d, use_fast=False)
+    return synthetic.LiteralTokenizer()
+
+
+def save_learned_embeddings(text_encoder, added_tokens, aug_token_dict, directory):
+    """train_textboost.py:1188-1209 / :1245-1266: one ``{token}.bin`` per added token (placeholder rows saved
+    as [D], augmentation rows as [1, D])."""
+    os.makedirs(directory, exist_ok=True)
+    weight = text_encoder.get_input_embeddings().weight
+    for token, token_id in added_tokens.items():
+        name = token.replace("<", "").replace(">", "")
+        torch.save({token: weight[token_id].detach().cpu()}, os.path.join(directory, f"{name}.bin"))
+    for token, token_id in (aug_token_dict or {}).items():
+        name = token.replace("<", "").replace(">", "")
+        torch.save({token: weight[token_id:token_id + 1].detach().cpu()}, os.path.join(directory, f"{name}.bin"))
+
+
+def save_checkpoint(trainer, text_encoder, step, directory, gen_state):
+    os.makedirs(directory, exist_ok=True)
+    torch.save({"step": step, "params": trainer.te.state.params.detach().cpu(),
+                "optimizer": {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in trainer.opt.state_dict().items()},
+                "generator": gen_state}, os.path.join(directory, "state.pt"))
+    text_encoder.save_pretrained(os.path.join(directory, "text_encoder"))
+
+
+def load_checkpoint(trainer, directory, device):
+    st = torch.load(os.path.join(directory, "state.pt"), map_location="cpu", weights_only=False)
+    trainer.te.state.params.copy_(st["params"].to(device))
+    trainer.opt.load_state_dict({k: (v.to(device) if torch.is_tensor(v) else v) for k, v in st["optimizer"].items()})
+    return st["step"], st["generator"]
+
+
+def _rotate_checkpoints(output_dir, limit):
+    if limit is None:
+        return
+    ck = sorted((d for d in os.listdir(output_dir) if d.startswith("checkpoint")), key=lambda x: int(x.split("-")[1]))
+    if len(ck) >= limit:
+        for d in ck[:len(ck) - limit + 1]:
+            shutil.rmtree(os.path.join(output_dir, d))
+
+
+# ------------------------------------------------------------------------------------ main
+def main(args):
+    from textboost_b200 import dp, synthetic
+    from textboost_b200.lora import LoraConfig
+    from textboost_b200.text_encoder import TextBoostModel
+    from textboost_b200.trainer import TextBoostTrainer, timestep_probs
+    from textboost_b200.unet_model import UNet2DConditionModel
+    from textboost_b200.utils import add_augmentation_tokens, add_token
+    import copy
+
+    _unsupported(args)
+    if not torch.cuda.is_available():
+        raise SystemExit("train_textboost.py needs a B200: the CUDA library is the product, there is no CPU path")
+    rank, world, local_rank = dp.init_from_env()
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    is_main = rank == 0
+    os.makedirs(args.output_dir, exist_ok=True)
+    logging.basicConfig(level=logging.INFO if is_main else logging.WARNING,
+                        format="%(asctime)s - %(levelname)s - %(name)s - %(message)s",
+                        handlers=[logging.StreamHandler()] + (
+                            [logging.FileHandler(os.path.join(args.output_dir, "training.log"))] if is_main else []))
+    if args.seed is not None:  # same seed on every rank (train_textboost.py:598-601, SURVEY.md trap 10)
+        torch.manual_seed(args.seed)
+
+    if args.concepts_list is None:  # train_textboost.py:602-615
+        args.concepts_list = [{"instance_token": args.instance_token, "class_token": args.class_token,
+                               "instance_data_dir": args.instance_data_dir, "class_data_dir": args.class_data_dir,
+                               "placeholder_token": args.placeholder_token, "initializer_token": args.initializer_token}]
+    else:
+        with open(args.concepts_list) as f:
+            args.concepts_list = json.load(f)
+
+    path = args.pretrained_model_name_or_path
+    tokenizer = load_tokenizer(args)
+    sched = load_scheduler_config(path)
+    text_encoder = TextBoostModel.from_pretrained(path, subfolder="text_encoder", revision=args.revision,
+                                                  variant=args.variant)
+    unet = UNet2DConditionModel.from_pretrained(path, subfolder="unet", revision=args.revision, variant=args.variant)
+
+    # null embedding (train_textboost.py:649 + SURVEY.md D6)
+    D = text_encoder.config.hidden_size
+    asset = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets", "null_emb_sd21base.pt")
+    null = None
+    if args.null_embedding is not None:
+        null = torch.load(args.null_embedding, map_location="cpu", weights_only=True)
+    elif os.path.exists(asset):
+        cand = torch.load(asset, map_location="cpu", weights_only=True)
+        null = cand if cand.shape[-1] == D else None
+    if null is None:  # derive it: the frozen encoder's hidden states for the empty prompt
+        probe = copy.deepcopy(text_encoder).to(device)
+        ids = torch.full((1, text_encoder.config.max_position_embeddings), 49407, dtype=torch.int64)
+        ids[0, 0] = 49406
+        with torch.no_grad():
+            null = probe(ids.to(device))[0][0].float().cpu()
+        del probe
+    text_encoder.set_null_embedding(null)
+    original_text_encoder = copy.deepcopy(text_encoder).eval().requires_grad_(False)
+
+    # placeholder / augmentation tokens (train_textboost.py:659-694)
+    added_tokens, placeholder_token_ids = {}, []
+    for concept in args.concepts_list:
+        toks, ids = add_token(text_encoder, tokenizer, concept["placeholder_token"], concept["initializer_token"])
+        placeholder_token_ids += ids
+        added_tokens.update(dict(zip(toks, ids)))
+        concept["instance_token"] = concept["placeholder_token"] = toks
+    aug_token_dict = {}
+    if args.augment_inversion:
+        _, aug_token_dict = add_augmentation_tokens(text_encoder, tokenizer,
+                                                    aug_type="style" if args.augment_ops == "style" else "object")
+
+    unet.eval().requires_grad_(False)
+    text_encoder.requires_grad_(False)
+    text_encoder.text_model.encoder.requires_grad_(True)
+    text_encoder.add_adapter(LoraConfig(r=args.lora_rank, lora_alpha=args.lora_rank, init_lora_weights="gaussian",
+                                        target_modules=["q_proj", "k_proj", "v_proj"]))
+    text_encoder.get_input_embeddings().requires_grad_(True)
+    n_lora = sum(p.numel() for n, p in text_encoder.named_parameters() if "lora" in n)
+    logger.info(f"trainable: {n_lora} LoRA floats + {len(added_tokens) + len(aug_token_dict)} embedding rows")
+
+    if args.scale_lr:  # train_textboost.py:818-821
+        args.learning_rate *= args.gradient_accumulation_steps * args.train_batch_size * world
+
+    # mean row norm of the resized embedding matrix, before training (train_textboost.py:1003-1021)
+    mean_norm = text_encoder.get_input_embeddings().weight.norm(dim=-1).mean().item()
+
+    text_encoder.to(device)
+    unet.to(device, dtype=torch.float16)
+    original_text_encoder.to(device, dtype=torch.float16)
+    trainer = TextBoostTrainer(
+        unet.engine, text_encoder.engine, original_text_encoder.engine if args.kpl_weight > 0 else None,
+        learning_rate=args.learning_rate, emb_learning_rate=args.emb_learning_rate, adam_beta1=args.adam_beta1,
+        adam_beta2=args.adam_beta2, adam_weight_decay=args.adam_weight_decay, adam_epsilon=args.adam_epsilon,
+        max_grad_norm=args.max_grad_norm, kpl_weight=args.kpl_weight, kpl_type=args.kpl_type,
+        prediction_type=sched["prediction_type"],
+        mixing=("style" if args.augment_ops == "style" else "object") if args.mixing else None,
+        mean_norm=mean_norm, mixed_precision=args.mixed_precision or "fp16")
+
+    # ---- data (front end out of scope: latents file or synthetic)
+    B = args.train_batch_size
+    latent = args.resolution // 8
+    if args.latents_file:
+        data = torch.load(args.latents_file, map_location="cpu", weights_only=True)
+        lat_all, ids_all = data["latents"].float(), data["input_ids"].long()
+        prior_all = data.get("prior_ids")
+    elif args.synthetic_data:
+        n = max(B * world, 8)
+        g = torch.Generator().manual_seed(args.seed)
+        lat_all = torch.randn(n, 4, latent, latent, generator=g)
+        ids_all = synthetic.instance_ids(n, placeholder_token_ids[0], text_encoder.config.max_position_embeddings)
+        prior_all = synthetic.prior_ids(max(args.num_prior_images, B * world), args.seed + 1,
+                                        text_encoder.config.max_position_embeddings, args.null_prob)
+    else:
+        raise NotImplementedError("the image dataset + VAE-encode front end is not built (SURVEY.md §8 f1): pass "
+                                  "--latents_file or --synthetic_data")
+    if args.kpl_weight > 0 and prior_all is None:
+        raise ValueError("kpl_weight > 0 needs prior prompts ('prior_ids' in --latents_file)")
+    lat_all, ids_all = lat_all.to(device), ids_all.to(device)
+    prior_all = prior_all.to(device) if prior_all is not None else None
+    gen = torch.Generator(device=device)
+    gen.manual_seed(args.seed)
+    T = sched["num_train_timesteps"]
+    p_t = None if args.disable_weighted_sample else timestep_probs(trainer.acp)
+
+    step = 0
+    if args.resume_from_checkpoint:  # train_textboost.py:960-981, made to work
+        ck = args.resume_from_checkpoint
+        if ck == "latest":
+            dirs = sorted((d for d in os.listdir(args.output_dir) if d.startswith("checkpoint")),
+                          key=lambda x: int(x.split("-")[1]))
+            ck = os.path.join(args.output_dir, dirs[-1]) if dirs else None
+        if ck is None or not os.path.isdir(ck):
+            logger.info(f"Checkpoint '{args.resume_from_checkpoint}' does not exist. Starting a new training run.")
+        else:
+            step, gstate = load_checkpoint(trainer, ck, device)
+            gen.set_state(gstate)
+            logger.info(f"Resuming from checkpoint {ck} at step {step}")
+
+    def draw(step_idx):
+        """rank r takes rows [r*B, (r+1)*B) of the step's global batch (dataset.py:846-870 sharding)."""
+        n = lat_all.shape[0]
+        idx = (torch.arange(B * world, device=device) + step_idx * B * world) % n
+        idx = idx[rank * B:(rank + 1) * B]
+        lat, ids = lat_all[idx], ids_all[idx]
+        noise = torch.randn(lat.shape, generator=gen, device=device)
+        if p_t is None:
+            t = torch.randint(0, T, (B,), generator=gen, device=device)
+        else:
+            t = torch.multinomial(p_t, B, replacement=True, generator=gen)
+        pri = None
+        if prior_all is not None and args.kpl_weight > 0:
+            pidx = (torch.arange(B * world, device=device) + step_idx * B * world) % prior_all.shape[0]
+            pri = prior_all[pidx[rank * B:(rank + 1) * B]]
+        return lat, noise, t, ids, pri
+
+    logger.info("***** Running training *****")
+    logger.info(f"  Instantaneous batch size per device = {B}")
+    logger.info(f"  Total train batch size (w. parallel) = {B * world}")
+    logger.info(f"  Total optimization steps = {args.max_train_steps}")
+    logger.info(f"  Mean norm: {mean_norm}")
+    run = trainer.step  # first step eager (configures kernel attributes), then the captured CUDA graph
+    start = time.perf_counter()
+    loss_val = float("nan")
+    first = step
+    while step < args.max_train_steps:
+        loss = run(*draw(step))
+        if step == first and args.max_train_steps - step > 3:
+            run = trainer.capture(*draw(step), warmup=0)
+        step += 1
+        if step % args.log_every == 0 or step == args.max_train_steps:
+            loss_val = loss.item()  # the reference syncs every step (:1230); here every --log_every steps
+            logger.info(f"step {step} loss {loss_val:.6f} lr {args.learning_rate} "
+                        f"added_embedding_norm {trainer.added_norm.item():.4f}")
+        if is_main and step % args.checkpointing_steps == 0:
+            _rotate_checkpoints(args.output_dir, args.checkpoints_total_limit)
+            ck = os.path.join(args.output_dir, f"checkpoint-{step}")
+            save_checkpoint(trainer, text_encoder, step, ck, gen.get_state())
+            save_learned_embeddings(text_encoder, added_tokens, aug_token_dict, ck)
+            logger.info(f"Saved state to {ck}")
+    torch.cuda.synchronize()
+    if is_main:
+        if args.lora_rank > 0:
+            text_encoder.to(torch.float32).save_pretrained(os.path.join(args.output_dir, "text_encoder"),
+                                                           safe_serialization=not args.no_safe_serialization)
+        save_learned_embeddings(text_encoder, added_tokens, aug_token_dict, args.output_dir)
+    logger.info(f"Training took {time.perf_counter() - start:.2f} seconds")
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    return loss_val
+
+
+if __name__ == "__main__":
+    main(parse_args())
