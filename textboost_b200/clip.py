@@ -196,8 +196,11 @@ class ClipEngine:
             if self.r:
                 C.call("tb_lora_down", C.ptr(y_ext), self.Kext, C.ptr(st.A(l)), M, D, st.T * self.r, RPAD, s)
             qkv = ops.gemm(y_ext, L["wqkv"], bias=L["bqkv"])
-            o = torch.empty((M, D), device=self.device, dtype=F16)
-            C.call("tb_clip_attn_fwd", C.ptr(qkv), C.ptr(o), B, Lq, D, self.heads, s)
+            # causal softmax(QK^T/sqrt(64))V on the tcgen05 flash kernels, reading q/k/v in place from the fused
+            # projection output (transformers CLIPAttention under the causal mask, text_encoder.py:62-69)
+            q3 = qkv.view(B, Lq, 3 * D)
+            o, lse = ops.attn_fwd(q3[..., :D], q3[..., D:2 * D], q3[..., 2 * D:], self.heads, causal=True)
+            o = o.view(M, D)
             x2 = ops.gemm(o, L["wo"], bias=L["bo"], residual=x, out_kind=C.TB_OUT_F32)
             y2, st2 = ops.layernorm(x2, *L["ln2"], eps=self.cfg.layer_norm_eps)
             u = ops.gemm(y2, L["wf1"], bias=L["bf1"])
@@ -205,7 +208,7 @@ class ClipEngine:
             C.call("tb_act_fwd_f16", C.ptr(u), C.ptr(a), u.numel(), self.act, s)
             x3 = ops.gemm(a, L["wf2"], bias=L["bf2"], residual=x2, out_kind=C.TB_OUT_F32)
             if save_for_backward:
-                saved.append((x, st1, y_ext, qkv, x2, st2, u))
+                saved.append((x, st1, y_ext, qkv, x2, st2, u, o, lse))
             x = x3
         out, stf = ops.layernorm(x, *self.lnf, eps=self.cfg.layer_norm_eps, out_dtype=F32)
         C.call("tb_null_override", C.ptr(ids), C.ptr(self.null_embedding), C.ptr(out), B, Lq, D, EOS_ID,
@@ -236,7 +239,7 @@ class ClipEngine:
         g = ops.layernorm_bwd(d_out, xf, self.lnf[0], stf)
         for l in reversed(range(self.nl)):
             L = self.layers[l]
-            x, st1, y_ext, qkv, x2, st2, u = saved[l]
+            x, st1, y_ext, qkv, x2, st2, u, o, lse = saved[l]
             g16 = ops.cast_f32_f16(g)
             da = ops.gemm(g16, L["wf2_t"])
             du = torch.empty_like(da)
@@ -246,7 +249,11 @@ class ClipEngine:
             g16 = ops.cast_f32_f16(g)
             do = ops.gemm(g16, L["wo_t"])
             dqkv = torch.empty_like(qkv)
-            C.call("tb_clip_attn_bwd", C.ptr(qkv), C.ptr(do), C.ptr(dqkv), B, Lq, D, self.heads, s)
+            q3, d3 = qkv.view(B, Lq, 3 * D), dqkv.view(B, Lq, 3 * D)
+            dq, _, _ = ops.attn_bwd(q3[..., :D], q3[..., D:2 * D], q3[..., 2 * D:], o.view(B, Lq, D),
+                                    do.view(B, Lq, D), lse, self.heads, dk=d3[..., D:2 * D], dv=d3[..., 2 * D:],
+                                    causal=True)
+            ops.cast_f32_f16(dq.view(M, D), out=dqkv[:, :D])
             dy_ext = ops.gemm(dqkv, L["wqkv_t"])
             if self.r:
                 C.call("tb_lora_grad", C.ptr(dqkv), C.ptr(y_ext), C.ptr(dy_ext), self.Kext,

@@ -3,8 +3,9 @@
 //
 //   C[M,N] = epilogue( A[M,K] * B[N,K]^T )      A, B fp16 K-major, accumulate fp32 in TMEM.
 //
-// CTA = 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane issues
-// tcgen05.mma), warps 2..5 = epilogue (tcgen05.ld -> registers -> fused bias/act/residual -> HBM).
+// CTA = 320 threads: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane issues
+// tcgen05.mma), warps 2..9 = epilogue (tcgen05.ld -> registers -> fused bias/act/residual -> smem box ->
+// TMA store), two warps per TMEM lane quarter, software-pipelined over 32-column chunks.
 // PERSISTENT: one CTA per SM walks the 128 x BN output tiles (n fastest, so concurrently running CTAs
 // share the A tile through L2).  Three pipelines run across tile boundaries: the STAGES-deep smem ring
 // (TMA <-> MMA, full/empty mbarriers), a two-deep TMEM accumulator ring (MMA <-> epilogue,
@@ -58,7 +59,7 @@ constexpr int tmem_cols() {
 }
 
 template <int BN, int STAGES, bool CONV>
-__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                          const __grid_constant__ CUtensorMap tmB,
                                                          const __grid_constant__ CUtensorMap tmC,
                                                          const GemmParams p) {
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tmem_full_bar[a]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[a]), 128);
+      mbar_init(smem_u32(&tmem_empty_bar[a]), 256);
     }
     mbar_fence_init();
   }
@@ -176,10 +177,17 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
       }
     }
   } else {
-    // ------------------------------------------------ epilogue (warps 2..5)
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    // ------------------------------------------------ epilogue (warps 2..9, two warps per TMEM lane quarter)
+    // Warp w may touch TMEM lanes 32*(w%4)..+31.  The two warps of a quarter split every 64-column box:
+    // half 0 takes columns [0,32), half 1 [32,64) of each box, so each SM sub-partition always has two
+    // epilogue warps to interleave.  Per warp the chunk loop is software-pipelined: the tcgen05.ld of chunk
+    // i+1 and the residual loads of chunk i+1 are in flight while chunk i is converted and stored.
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
     const bool issuer = threadIdx.x == 64;
+    constexpr int NCH = BN / 32;           // 32-column chunks per tile
+    constexpr int MY_MAX = (NCH + 1) / 2;  // chunks per warp (half 0 takes the odd one out)
     int lt = 0;
     uint32_t n_box = 0;  // staging boxes written so far (selects the buffer)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
@@ -187,8 +195,6 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
       const int m_tile = tile / p.n_tiles;
       const int acc = lt & 1;
       const long long m = (long long)m_tile * BM + row;
-      mbar_wait(smem_u32(&tmem_full_bar[acc]), (lt >> 1) & 1);
-      tc_fence_after();
       const uint32_t acc_addr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
       const bool row_ok = m < p.M;
       const __half* rv = nullptr;
@@ -199,112 +205,133 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
         if (p.res_f32) res32 = reinterpret_cast<const float*>(p.residual) + m * p.ldr;
         else res = reinterpret_cast<const __half*>(p.residual) + m * p.ldr;
       }
-
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        // a full 64-column box goes through shared memory and one TMA store; a 32-column remainder
-        // (BN = 160, 32) and fp32 outputs are written from registers
-        const bool staged = p.tma_store && ((c & ~63) + 64 <= BN);
-        uint8_t* box = sC + (n_box & 1) * C_BOX_BYTES;
-        if (staged && (c & 63) == 0) {
-          if (issuer) tma_store_wait_read<1>();  // the store that last used this buffer has read it out
-          named_bar_sync(1, 128);
+      const int ncol0 = n_tile * BN;
+      uint32_t r[2][32];
+      uint4 rq[2][4];
+      auto load_res = [&](int c, uint4* q) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = ncol0 + c + 8 * j;
+          q[j] = (res && n < p.N) ? *reinterpret_cast<const uint4*>(res + n) : make_uint4(0, 0, 0, 0);
         }
-        uint32_t r[32];
-        tmem_ld32(acc_addr + c, r);
-        tmem_ld_wait();
-        const int n0 = n_tile * BN + c;
+      };
+      if (half < NCH) load_res(half * 32, rq[0]);  // residual of the first chunk: before the accumulator wait
+      mbar_wait(smem_u32(&tmem_full_bar[acc]), (lt >> 1) & 1);
+      tc_fence_after();
+      if (half < NCH) tmem_ld32(acc_addr + half * 32, r[0]);
+
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          const int n = n0 + j;
-          float v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j + i]) * p.alpha;
-          if (row_ok && n < p.N) {
-            if (p.bias) {
-              const uint4 q = *reinterpret_cast<const uint4*>(p.bias + n);
-              const __half2* h = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 f = __half22float2(h[i]);
-                v[2 * i] += f.x;
-                v[2 * i + 1] += f.y;
-              }
-            }
-            if (rv) {
-              const uint4 q = *reinterpret_cast<const uint4*>(rv + n);
-              const __half2* h = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 f = __half22float2(h[i]);
-                v[2 * i] += f.x;
-                v[2 * i + 1] += f.y;
-              }
-            }
-            if (p.act != TB_ACT_NONE) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], p.act);
-            }
-            if (res) {
-              const uint4 q = *reinterpret_cast<const uint4*>(res + n);
-              const __half2* h = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 f = __half22float2(h[i]);
-                v[2 * i] += f.x;
-                v[2 * i + 1] += f.y;
-              }
-            }
-            if (res32) {
-              const float4 a0 = *reinterpret_cast<const float4*>(res32 + n);
-              const float4 a1 = *reinterpret_cast<const float4*>(res32 + n + 4);
-              v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
-              v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
-            }
+      for (int i = 0; i < MY_MAX; ++i) {
+        const int c = (2 * i + half) * 32;  // first column of this warp's chunk inside the tile
+        const int cn = c + 64;              // its next chunk
+        const bool have = c < BN;
+        const bool staged = p.tma_store && ((c & ~63) + 64 <= BN);  // full 64-column box: smem + TMA store
+        uint8_t* box = sC + (n_box & 1) * C_BOX_BYTES;
+        if (have) {
+          tmem_ld_wait32(r[i & 1]);
+          if (i + 1 < MY_MAX && cn < BN) {
+            tmem_ld32(acc_addr + cn, r[(i + 1) & 1]);
+            load_res(cn, rq[(i + 1) & 1]);
           }
-          if (staged) {
-            uint4 o;
-            o.x = pack_half2(v[0], v[1]);
-            o.y = pack_half2(v[2], v[3]);
-            o.z = pack_half2(v[4], v[5]);
-            o.w = pack_half2(v[6], v[7]);
-            const int chunk = ((c & 63) + j) >> 3;  // 16-byte chunk inside the 128-byte box row
-            *reinterpret_cast<uint4*>(box + row * 128 + ((chunk ^ (row & 7)) << 4)) = o;
-          } else if (row_ok && n < p.N) {
-            if (p.out_kind == TB_OUT_F16) {
+          const uint32_t* rr = r[i & 1];
+          const int n0 = ncol0 + c;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const int n = n0 + j;
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(rr[j + k]);
+            if (p.alpha != 1.f) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[k] *= p.alpha;
+            }
+            if (row_ok && n < p.N) {
+              if (p.bias) {
+                const uint4 q = *reinterpret_cast<const uint4*>(p.bias + n);
+                const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float2 f = __half22float2(h[k]);
+                  v[2 * k] += f.x;
+                  v[2 * k + 1] += f.y;
+                }
+              }
+              if (rv) {
+                const uint4 q = *reinterpret_cast<const uint4*>(rv + n);
+                const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float2 f = __half22float2(h[k]);
+                  v[2 * k] += f.x;
+                  v[2 * k + 1] += f.y;
+                }
+              }
+              if (p.act != TB_ACT_NONE) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = apply_act(v[k], p.act);
+              }
+              if (res) {
+                const __half2* h = reinterpret_cast<const __half2*>(&rq[i & 1][j >> 3]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float2 f = __half22float2(h[k]);
+                  v[2 * k] += f.x;
+                  v[2 * k + 1] += f.y;
+                }
+              }
+              if (res32) {
+                const float4 a0 = *reinterpret_cast<const float4*>(res32 + n);
+                const float4 a1 = *reinterpret_cast<const float4*>(res32 + n + 4);
+                v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
+                v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+              }
+            }
+            if (staged) {
               uint4 o;
               o.x = pack_half2(v[0], v[1]);
               o.y = pack_half2(v[2], v[3]);
               o.z = pack_half2(v[4], v[5]);
               o.w = pack_half2(v[6], v[7]);
-              *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C) + m * p.ldc + n) = o;
-            } else {
-              float* cp = reinterpret_cast<float*>(p.C) + m * p.ldc + n;
-              float4 o0 = make_float4(v[0], v[1], v[2], v[3]);
-              float4 o1 = make_float4(v[4], v[5], v[6], v[7]);
-              if (p.out_kind == TB_OUT_F32_ACC) {
-                const float4 a0 = *reinterpret_cast<const float4*>(cp);
-                const float4 a1 = *reinterpret_cast<const float4*>(cp + 4);
-                o0.x += a0.x; o0.y += a0.y; o0.z += a0.z; o0.w += a0.w;
-                o1.x += a1.x; o1.y += a1.y; o1.z += a1.z; o1.w += a1.w;
+              const int chunk = ((c & 63) + j) >> 3;  // 16-byte chunk inside the 128-byte box row
+              *reinterpret_cast<uint4*>(box + row * 128 + ((chunk ^ (row & 7)) << 4)) = o;
+            } else if (row_ok && n < p.N) {
+              if (p.out_kind == TB_OUT_F16) {
+                uint4 o;
+                o.x = pack_half2(v[0], v[1]);
+                o.y = pack_half2(v[2], v[3]);
+                o.z = pack_half2(v[4], v[5]);
+                o.w = pack_half2(v[6], v[7]);
+                *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C) + m * p.ldc + n) = o;
+              } else {
+                float* cp = reinterpret_cast<float*>(p.C) + m * p.ldc + n;
+                float4 o0 = make_float4(v[0], v[1], v[2], v[3]);
+                float4 o1 = make_float4(v[4], v[5], v[6], v[7]);
+                if (p.out_kind == TB_OUT_F32_ACC) {
+                  const float4 a0 = *reinterpret_cast<const float4*>(cp);
+                  const float4 a1 = *reinterpret_cast<const float4*>(cp + 4);
+                  o0.x += a0.x; o0.y += a0.y; o0.z += a0.z; o0.w += a0.w;
+                  o1.x += a1.x; o1.y += a1.y; o1.z += a1.z; o1.w += a1.w;
+                }
+                *reinterpret_cast<float4*>(cp) = o0;
+                *reinterpret_cast<float4*>(cp + 4) = o1;
               }
-              *reinterpret_cast<float4*>(cp) = o0;
-              *reinterpret_cast<float4*>(cp + 4) = o1;
             }
           }
         }
-        if (staged && (c & 63) == 32) {
+        // box i of the tile (columns [64i, 64i+64)) is complete once both halves have written their chunk
+        if (p.tma_store && 64 * i + 64 <= BN) {
           fence_async_smem();
-          named_bar_sync(1, 128);
+          if (issuer) tma_store_wait_read<0>();  // the previous box's store has read its buffer out
+          named_bar_sync(1, 256);
           if (issuer) {
-            tma_store_2d(&tmC, smem_u32(box), n_tile * BN + (c & ~63), m_tile * BM);
+            tma_store_2d(&tmC, smem_u32(box), ncol0 + 64 * i, m_tile * BM);
             tma_store_commit();
           }
           ++n_box;
         }
       }
       tc_fence_before();
-      mbar_arrive(smem_u32(&tmem_empty_bar[acc]));  // 128 arrivals release the accumulator stage
+      mbar_arrive(smem_u32(&tmem_empty_bar[acc]));  // 256 arrivals release the accumulator stage
     }
     if (issuer) tma_store_wait_read<0>();
   }
@@ -339,7 +366,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   p.m_tiles = m_tiles;
   const int tiles = p.n_tiles * m_tiles;
   dim3 grid(tiles < num_sms() ? tiles : num_sms());
-  gemm_tc_kernel<BN, STAGES, CONV><<<grid, 192, smem, st>>>(tmA, tmB, tmC, p);
+  gemm_tc_kernel<BN, STAGES, CONV><<<grid, 320, smem, st>>>(tmA, tmB, tmC, p);
   return check_launch("gemm_tc_kernel");
 }
 

@@ -74,25 +74,40 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, const __half* __re
     }
   }
   const size_t base = (size_t)b * g.HW * g.C + (size_t)v * 8;
-  for (int p = p0 + pl; p < p1; p += g.k) {
-    float xf[8];
-    unpack8(*reinterpret_cast<const uint4*>(x + base + (size_t)p * g.C), xf);
-    if (MODE == 0) {
+  // four pixels per trip: all loads are issued before the arithmetic, so each thread keeps 4 (MODE 0) or 8
+  // (MODE 1) 16-byte loads in flight
+  for (int p = p0 + pl; p < p1; p += 4 * g.k) {
+    uint4 qx[4], qd[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        s1[i] += xf[i];
-        s2[i] += xf[i] * xf[i];
+    for (int u = 0; u < 4; ++u) {
+      const int pp = p + u * g.k;
+      if (pp < p1) {
+        qx[u] = *reinterpret_cast<const uint4*>(x + base + (size_t)pp * g.C);
+        if (MODE == 1) qd[u] = *reinterpret_cast<const uint4*>(dy + base + (size_t)pp * g.C);
       }
-    } else {
-      float df[8];
-      unpack8(*reinterpret_cast<const uint4*>(dy + base + (size_t)p * g.C), df);
+    }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float dz = df[i];
-        if (silu) dz *= silu_grad(xf[i] * a[i] + bb[i]);
-        const float dxh = dz * gm[i];
-        s1[i] += dxh;
-        s2[i] += dxh * (xf[i] - mean[i]) * rstd[i];
+    for (int u = 0; u < 4; ++u) {
+      if (p + u * g.k >= p1) break;
+      float xf[8];
+      unpack8(qx[u], xf);
+      if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s1[i] += xf[i];
+          s2[i] += xf[i] * xf[i];
+        }
+      } else {
+        float df[8];
+        unpack8(qd[u], df);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float dz = df[i];
+          if (silu) dz *= silu_grad(xf[i] * a[i] + bb[i]);
+          const float dxh = dz * gm[i];
+          s1[i] += dxh;
+          s2[i] += dxh * (xf[i] - mean[i]) * rstd[i];
+        }
       }
     }
   }
@@ -150,37 +165,54 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, const __half* __re
     }
   }
   const size_t base = (size_t)b * g.HW * g.C + (size_t)v * 8;
-  for (int p = p0 + pl; p < p1; p += g.k) {
-    float xf[8], o[8];
-    unpack8(*reinterpret_cast<const uint4*>(x + base + (size_t)p * g.C), xf);
-    if (MODE == 0) {
+  for (int p = p0 + pl; p < p1; p += 4 * g.k) {
+    uint4 qx[4], qd[4], qa[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float z = xf[i] * a[i] + bb[i];
-        o[i] = silu ? silu_f(z) : z;
-      }
-    } else {
-      float df[8];
-      unpack8(*reinterpret_cast<const uint4*>(dy + base + (size_t)p * g.C), df);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float dz = df[i];
-        if (silu) dz *= silu_grad(xf[i] * a[i] + bb[i]);
-        const float xh = (xf[i] - mean[i]) * rstd[i];
-        o[i] = rstd[i] * (dz * gm[i] - m1[i] - xh * m2[i]);
-      }
-      if (add) {
-        float af[8];
-        unpack8(*reinterpret_cast<const uint4*>(add + base + (size_t)p * g.C), af);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] += af[i];
+    for (int u = 0; u < 4; ++u) {
+      const int pp = p + u * g.k;
+      if (pp < p1) {
+        qx[u] = *reinterpret_cast<const uint4*>(x + base + (size_t)pp * g.C);
+        if (MODE == 1) {
+          qd[u] = *reinterpret_cast<const uint4*>(dy + base + (size_t)pp * g.C);
+          if (add) qa[u] = *reinterpret_cast<const uint4*>(add + base + (size_t)pp * g.C);
+        }
       }
     }
-    *reinterpret_cast<uint4*>(out + base + (size_t)p * g.C) = pack8(o);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int pp = p + u * g.k;
+      if (pp >= p1) break;
+      float xf[8], o[8];
+      unpack8(qx[u], xf);
+      if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float z = xf[i] * a[i] + bb[i];
+          o[i] = silu ? silu_f(z) : z;
+        }
+      } else {
+        float df[8];
+        unpack8(qd[u], df);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float dz = df[i];
+          if (silu) dz *= silu_grad(xf[i] * a[i] + bb[i]);
+          const float xh = (xf[i] - mean[i]) * rstd[i];
+          o[i] = rstd[i] * (dz * gm[i] - m1[i] - xh * m2[i]);
+        }
+        if (add) {
+          float af[8];
+          unpack8(qa[u], af);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] += af[i];
+        }
+      }
+      *reinterpret_cast<uint4*>(out + base + (size_t)pp * g.C) = pack8(o);
+    }
   }
 }
 
-static int gn_geom(GnGeom& g, int HW, int C, int G) {
+static int gn_geom(GnGeom& g, int B, int HW, int C, int G) {
   TB_REQUIRE(C % 8 == 0 && G > 0 && C % G == 0, TB_E_SHAPE, "groupnorm: C=%d G=%d unsupported", C, G);
   g.HW = HW;
   g.C = C;
@@ -189,7 +221,11 @@ static int gn_geom(GnGeom& g, int HW, int C, int G) {
   g.nvec = C / 8;
   TB_REQUIRE(g.nvec <= 1024, TB_E_SHAPE, "groupnorm: C=%d too wide", C);
   g.k = g.nvec >= 256 ? 1 : 256 / g.nvec;
-  int per_thread = 16;
+  // pixels per CTA: aim at >= 4 CTAs per SM over the whole batch (the small 8x8 / 16x16 levels otherwise run on
+  // a few dozen CTAs, each a chain of dependent loads), at most 16 pixels per thread
+  const int want_x = (4 * num_sms() + B - 1) / B;
+  int per_thread = (HW + want_x * g.k - 1) / (want_x * g.k);
+  per_thread = per_thread < 1 ? 1 : per_thread > 16 ? 16 : per_thread;
   g.ppc = g.k * per_thread;
   return TB_OK;
 }
@@ -341,7 +377,7 @@ extern "C" int tb_groupnorm_fwd_f16(const void* x, const void* gamma, const void
   if (rc) return rc;
   TB_REQUIRE(x && gamma && beta && y && stats, TB_E_ARG, "tb_groupnorm_fwd_f16: null pointer");
   GnGeom g;
-  if ((rc = gn_geom(g, HW, C, G))) return rc;
+  if ((rc = gn_geom(g, B, HW, C, G))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(stats, 0, (size_t)B * G * 2 * sizeof(float), st);
   TB_REQUIRE(e == cudaSuccess, TB_E_CUDA, "groupnorm memset: %s", cudaGetErrorString(e));
@@ -364,7 +400,7 @@ extern "C" int tb_groupnorm_bwd_f16(const void* dy, const void* x, const void* g
   TB_REQUIRE(dy && x && gamma && beta && stats && dstats && dx, TB_E_ARG,
              "tb_groupnorm_bwd_f16: null pointer");
   GnGeom g;
-  if ((rc = gn_geom(g, HW, C, G))) return rc;
+  if ((rc = gn_geom(g, B, HW, C, G))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(dstats, 0, (size_t)B * G * 2 * sizeof(float), st);
   TB_REQUIRE(e == cudaSuccess, TB_E_CUDA, "groupnorm memset: %s", cudaGetErrorString(e));
