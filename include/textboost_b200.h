@@ -64,6 +64,13 @@ const char* tb_last_error(void);
 /* 0 if the current device is sm_100 and the library can run, else TB_E_ARCH */
 int tb_check_device(void);
 
+/* Optional split-K scratch for under-filled GEMM / conv problems (few output tiles, long K): `ptr` is a
+ * caller-owned device buffer (256-byte aligned, >= 128 KiB; 64 MiB covers every SD shape) that tb_gemm_f16 /
+ * tb_conv3x3_f16 calls enqueued on `stream` may use between their own start and end.  One region per stream:
+ * calls on different streams can run concurrently.  ptr == NULL unregisters.  Without a workspace the kernels
+ * never split (same results up to fp32 summation order).  The library still never allocates. */
+int tb_set_workspace(void* stream, void* ptr, size_t bytes);
+
 /* ---- dense contraction on tcgen05/TMEM -------------------------------------------------------
  * C[M,N] = epilogue(A[M,K] * B[N,K]^T).  A, B fp16 row-major (K contiguous; lda/ldb in elements,
  * multiples of 8).  Replaces every nn.Linear / 1x1 conv forward and input-gradient (dgrad uses the

@@ -67,6 +67,41 @@ def test_gemm_epilogues_and_strides():
         assert relerr(out, f(a.float() @ w.float().t() + bias.float())) < TOL_GEMM
 
 
+@pytest.mark.parametrize("M,N,K", [(616, 768, 3072), (512, 1280, 2560), (77, 2560, 768), (8, 1280, 1280),
+                                   (1232, 784, 2304), (300, 160, 4096)])
+def test_gemm_split_k(M, N, K):
+    """Under-filled problems (few tiles, long K) take the split-K path (per-stream workspace registered by the
+    binding): same result as the unsplit kernel up to fp32 summation order, identical between replays (the
+    partials are added in split order), every fused epilogue still applied by the fixing CTA."""
+    import os
+    from textboost_b200 import _cabi as C, ops
+    g = torch.Generator(device=dev).manual_seed(M * 7 + N + K)
+    a = torch.randn(M, K, device=dev, dtype=F16, generator=g)
+    w = torch.randn(N, K, device=dev, dtype=F16, generator=g) / K ** 0.5
+    bias = torch.randn(N, device=dev, dtype=F16, generator=g)
+    res = torch.randn(M, N, device=dev, dtype=torch.float32, generator=g)
+    ref = F.gelu(a.float() @ w.float().t() + bias.float()) + res
+    out = ops.gemm(a, w, bias=bias, residual=res, act=C.TB_ACT_GELU, out_kind=C.TB_OUT_F32)
+    assert relerr(out, ref) < 1e-3
+    out2 = ops.gemm(a, w, bias=bias, residual=res, act=C.TB_ACT_GELU, out_kind=C.TB_OUT_F32)
+    assert torch.equal(out, out2)
+    h = ops.gemm(a, w, bias=bias)  # fp16 output through the TMA-store boxes
+    assert relerr(h, a.float() @ w.float().t() + bias.float()) < TOL_GEMM
+    acc = torch.full((M, N), 2.0, device=dev, dtype=torch.float32)
+    ops.gemm(a, w, out=acc, out_kind=C.TB_OUT_F32_ACC)
+    assert relerr(acc, a.float() @ w.float().t() + 2.0) < 1e-3
+    # without a workspace the same call runs unsplit: results agree to fp32 reassociation
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        C.stream_ptr()  # registers a workspace for s ...
+        C.call("tb_set_workspace", C.c_void_p(s.cuda_stream), C.c_void_p(0), 0)  # ... and drops it again
+        C._workspaces[(s.device.index, s.cuda_stream)] = None
+        plain = ops.gemm(a, w, bias=bias, residual=res, act=C.TB_ACT_GELU, out_kind=C.TB_OUT_F32)
+    s.synchronize()
+    assert relerr(plain, out) < 1e-5
+
+
 def test_gemm_rejects_bad_arguments():
     from textboost_b200 import ops
     a = torch.randn(16, 20, device=dev, dtype=F16)  # K % 8 != 0
@@ -94,6 +129,22 @@ def test_conv3x3(B, H, W, Cin, Cout):
         ref.backward(dy.permute(0, 3, 1, 2).float())
         dx = ops.conv3x3(dy, _conv_dgrad_weight(wt))
         assert relerr(dx, xr.grad.permute(0, 2, 3, 1)) < TOL_GEMM
+
+
+def test_conv3x3_split_k_deep_levels():
+    """The 8x8 / 16x16 UNet levels (M = 512 / 2048 pixels, K = 9*1280): split along K."""
+    from textboost_b200 import ops
+    torch.manual_seed(3)
+    for (B, H, Cin, Cout) in ((8, 8, 1280, 1280), (2, 16, 640, 320), (8, 8, 2560, 1280)):
+        x = torch.randn(B, H, H, Cin, device=dev, dtype=F16)
+        w4 = torch.randn(Cout, Cin, 3, 3, device=dev, dtype=F16) / (9 * Cin) ** 0.5
+        bias = torch.randn(Cout, device=dev, dtype=F16)
+        res = torch.randn(B, H, H, Cout, device=dev, dtype=F16)
+        wk = w4.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous()
+        y = ops.conv3x3(x, wk, bias=bias, residual=res)
+        ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w4.float(), bias.float(), padding=1).permute(0, 2, 3, 1) + res.float()
+        assert relerr(y, ref) < TOL_GEMM
+        assert torch.equal(y, ops.conv3x3(x, wk, bias=bias, residual=res))
 
 
 def test_strided_conv_and_upsample_paths():

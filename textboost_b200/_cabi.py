@@ -39,6 +39,7 @@ _SIGNATURES = {
     "tb_version": [],
     "tb_last_error": [],
     "tb_check_device": [],
+    "tb_set_workspace": [c_void_p, c_void_p, c_size_t],
     "tb_gemm_f16": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
                     POINTER(Epilogue), c_void_p],
     "tb_conv3x3_f16": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
@@ -118,7 +119,7 @@ def last_error() -> str:
 
 # kernels (and memset nodes) one call of each entry point enqueues; entry points not listed launch one
 _KERNELS_PER_CALL = {"tb_groupnorm_fwd_f16": 3, "tb_groupnorm_bwd_f16": 3, "tb_attn_bwd_f16": 2,
-                     "tb_adamw_fused_step": 3, "tb_version": 0, "tb_check_device": 0,
+                     "tb_adamw_fused_step": 3, "tb_version": 0, "tb_check_device": 0, "tb_set_workspace": 1,
                      "tb_attn_debug_trace": 0}
 launch_count = 0  # GPU launches enqueued through this binding since import (bench.py reports the delta)
 
@@ -131,9 +132,21 @@ def call(name: str, *args):
     launch_count += _KERNELS_PER_CALL.get(name, 1)
 
 
+WORKSPACE_BYTES = 64 << 20
+_workspaces = {}  # (device index, stream handle) -> tensor kept alive for the library
+
+
 def stream_ptr():
+    """Handle of torch's current stream.  The first use of a stream registers a split-K workspace for it
+    (tb_set_workspace): the library never allocates, PyTorch owns the memory."""
     import torch
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+    s = torch.cuda.current_stream()
+    key = (s.device.index, s.cuda_stream)
+    if key not in _workspaces:
+        buf = torch.empty(WORKSPACE_BYTES, device=s.device, dtype=torch.uint8)
+        _workspaces[key] = buf
+        call("tb_set_workspace", c_void_p(s.cuda_stream), c_void_p(buf.data_ptr()), WORKSPACE_BYTES)
+    return c_void_p(s.cuda_stream)
 
 
 def ptr(t):

@@ -50,11 +50,26 @@ __global__ void lora_down_kernel(__half* __restrict__ y_ext, long long ld, const
   float acc[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-  for (int c = lane; c < D; c += 32) {
-    const float v = __half2float(row[c]);
+  // 8 consecutive columns per lane and trip: one 16-byte load of y, two float4 loads of each A row (L1-resident)
+  for (int c = lane * 8; c < D; c += 256) {
+    const uint4 q = *reinterpret_cast<const uint4*>(row + c);
+    const __half2* h = reinterpret_cast<const __half2*>(&q);
+    float v[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (j < R) acc[j] += v * A[(long long)j * D + c];
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(h[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < R) {
+        const float4 a0 = *reinterpret_cast<const float4*>(A + (long long)j * D + c);
+        const float4 a1 = *reinterpret_cast<const float4*>(A + (long long)j * D + c + 4);
+        acc[j] += v[0] * a0.x + v[1] * a0.y + v[2] * a0.z + v[3] * a0.w + v[4] * a1.x + v[5] * a1.y +
+                  v[6] * a1.z + v[7] * a1.w;
+      }
+    }
   }
 #pragma unroll
   for (int j = 0; j < 16; ++j) acc[j] = warp_sum_c(acc[j]);
@@ -89,43 +104,76 @@ __global__ void lora_pack_kernel(const float* __restrict__ Bm, __half* __restric
 }
 
 // LoRA gradients for one layer (accumulating, fp32):
-//   dB_t[n, j] += sum_m dY[m, t*D+n] * xa[m, t*r+j]
+//   dB_t[n, j] += scaling * sum_m dY[m, t*D+n] * xa[m, t*r+j]
 //   dA[tj, c]  += sum_m dxa[m, tj] * y[m, c]
 // dY [M, T*D] fp16, xa = y_ext[:, D:D+R], y = y_ext[:, :D], dxa = dA_ext[:, D:D+R] (all fp16).
-// grid.x covers T*D (dB rows) then D (dA columns); one warp per output row, lanes over m.
+// A thread owns two adjacent columns (of dY for dB, of y for dA), so every warp reads 128 contiguous bytes per
+// row; the rows are split over grid.y and the partial sums meet in fp32 atomics; the r-wide xa / dxa rows of the
+// CTA's row chunk are staged in shared memory (every thread reads the same entry: broadcast).
+constexpr int LG_ROWS = 48;  // rows per CTA
 __global__ void lora_grad_kernel(const __half* __restrict__ dY, const __half* __restrict__ y_ext,
                                  const __half* __restrict__ dA_ext, long long ld, float* __restrict__ dB,
                                  float* __restrict__ dA, int M, int T, int D, int r, float scaling) {
-  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
+  __shared__ float sxa[LG_ROWS][16];
+  __shared__ float sdx[LG_ROWS][16];
+  const int m0 = blockIdx.y * LG_ROWS;
+  const int rows = min(LG_ROWS, M - m0);
   const int R = T * r;
-  if (w < T * D) {
-    const int t = w / D;
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int m = lane; m < M; m += 32) {
-      const float g = __half2float(dY[(long long)m * (T * D) + w]);
-      for (int j = 0; j < r; ++j) acc[j] += g * __half2float(y_ext[(long long)m * ld + D + t * r + j]);
-    }
-    for (int j = 0; j < r; ++j) {
-      const float s = warp_sum_c(acc[j]);
-      if (lane == 0) dB[(long long)w * r + j] += scaling * s;
-    }
-  } else if (w < T * D + D) {
-    const int c = w - T * D;
-    float acc[16];
+  for (int i = threadIdx.x; i < rows * 16; i += blockDim.x) {
+    const int mm = i >> 4, j = i & 15;
+    sxa[mm][j] = j < R ? __half2float(y_ext[(long long)(m0 + mm) * ld + D + j]) : 0.f;
+    sdx[mm][j] = j < R ? __half2float(dA_ext[(long long)(m0 + mm) * ld + D + j]) : 0.f;
+  }
+  __syncthreads();
+  const int col = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (col < T * D) {
+    const int t = col / D;
+    float a0[8], a1[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-    for (int m = lane; m < M; m += 32) {
-      const float yv = __half2float(y_ext[(long long)m * ld + c]);
+    for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.f;
+    const __half* src = dY + (long long)m0 * (T * D) + col;
+#pragma unroll 4
+    for (int mm = 0; mm < rows; ++mm) {
+      const float2 g = __half22float2(*reinterpret_cast<const __half2*>(src + (long long)mm * (T * D)));
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (j < R) acc[j] += yv * __half2float(dA_ext[(long long)m * ld + D + j]);
+      for (int j = 0; j < 8; ++j) {
+        if (j < r) {
+          const float xa = sxa[mm][t * r + j];
+          a0[j] += g.x * xa;
+          a1[j] += g.y * xa;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < r) {
+        atomicAdd(&dB[(long long)col * r + j], scaling * a0[j]);
+        atomicAdd(&dB[(long long)(col + 1) * r + j], scaling * a1[j]);
+      }
+    }
+  } else if (col < T * D + D) {
+    const int c = col - T * D;
+    float a0[16], a1[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a0[j] = a1[j] = 0.f;
+    const __half* src = y_ext + (long long)m0 * ld + c;
+#pragma unroll 4
+    for (int mm = 0; mm < rows; ++mm) {
+      const float2 yv = __half22float2(*reinterpret_cast<const __half2*>(src + (long long)mm * ld));
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (j < R) {
+          const float dx = sdx[mm][j];
+          a0[j] += yv.x * dx;
+          a1[j] += yv.y * dx;
+        }
+      }
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       if (j < R) {
-        const float s = warp_sum_c(acc[j]);
-        if (lane == 0) dA[(long long)j * D + c] += s;
+        atomicAdd(&dA[(long long)j * D + c], a0[j]);
+        atomicAdd(&dA[(long long)j * D + c + 1], a1[j]);
       }
     }
   }
@@ -385,8 +433,10 @@ extern "C" int tb_lora_grad(const void* dY, const void* y_ext, const void* dA_ex
                             float* dA, int M, int T, int D, int r, float scaling, void* stream) {
   TB_ENTER();
   TB_REQUIRE(dY && y_ext && dA_ext && dB && dA && r <= 8 && T * r <= 16, TB_E_ARG, "tb_lora_grad: bad args");
-  const int warps = T * D + D;
-  lora_grad_kernel<<<(warps + 7) / 8, 256, 0, st>>>((const __half*)dY, (const __half*)y_ext,
+  TB_REQUIRE(D % 2 == 0 && ld % 2 == 0, TB_E_ALIGN, "tb_lora_grad: D and ld must be even");
+  const int pairs = (T * D + D) / 2;
+  dim3 grid((pairs + 127) / 128, (M + LG_ROWS - 1) / LG_ROWS);
+  lora_grad_kernel<<<grid, 128, 0, st>>>((const __half*)dY, (const __half*)y_ext,
                                                    (const __half*)dA_ext, ld, dB, dA, M, T, D, r, scaling);
   return check_launch("lora_grad_kernel");
 }

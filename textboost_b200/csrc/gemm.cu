@@ -37,6 +37,12 @@ struct GemmParams {
   int act;
   int out_kind;
   int tma_store;      // fp16 output through shared memory + TMA tile stores (full 128-byte lines)
+  // split-K (under-filled problems): a work item = (tile, split); every split parks its fp32 partial tile in `ws`,
+  // bumps counters[tile], and the last arriver adds the partials in split order and runs the epilogue
+  int splits;         // 1 = off
+  int kb_per_split;
+  float* ws;          // [num_tiles * splits][128][BN] fp32
+  int* counters;      // [num_tiles], zero between launches (the fixing CTA resets its tile's counter)
 };
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -79,10 +85,11 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
   uint64_t* tmem_full_bar = bars + 2 * STAGES;       // [2]
   uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  volatile uint32_t* split_flag = tmem_slot + 1;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int num_work = p.m_tiles * p.n_tiles * p.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -110,7 +117,10 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
     // ------------------------------------------------ TMA producer (warp-uniform; one elected lane issues)
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+      const int tile = work / p.splits;
+      const int kb0 = (work - tile * p.splits) * p.kb_per_split;
+      const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
       int cw = 0, ch = 0, cb = 0;
@@ -120,7 +130,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
         ch = (p0 / p.W) % p.H;
         cb = p0 / (p.W * p.H);
       }
-      for (int kb = 0; kb < p.num_kb; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
         if (elect_one()) {
           const uint32_t fb = smem_u32(&full_bar[stage]);
@@ -151,12 +161,14 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
     int stage = 0;
     uint32_t phase = 0;
     int lt = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+    for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++lt) {
+      const int kb0 = (work % p.splits) * p.kb_per_split;
+      const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
       const int acc = lt & 1;
       mbar_wait(smem_u32(&tmem_empty_bar[acc]), ((lt >> 1) & 1) ^ 1);  // epilogue drained this stage
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
@@ -165,9 +177,9 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             umma_f16_ss(d_tmem, umma_desc_pack(alo + k * 2, dhi), umma_desc_pack(blo + k * 2, dhi), idesc,
-                        (kb | k) != 0);
+                        ((kb - kb0) | k) != 0);
           umma_commit(smem_u32(&empty_bar[stage]));  // frees the smem slot when these MMAs retire
-          if (kb == p.num_kb - 1) umma_commit(smem_u32(&tmem_full_bar[acc]));
+          if (kb == kb1 - 1) umma_commit(smem_u32(&tmem_full_bar[acc]));
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -190,11 +202,43 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
     constexpr int MY_MAX = (NCH + 1) / 2;  // chunks per warp (half 0 takes the odd one out)
     int lt = 0;
     uint32_t n_box = 0;  // staging boxes written so far (selects the buffer)
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+    for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++lt) {
+      const int tile = work / p.splits;
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
       const int acc = lt & 1;
       const long long m = (long long)m_tile * BM + row;
+      bool from_ws = false;  // split-K fix-up: the accumulator chunks come from the fp32 workspace
+      if (p.splits > 1) {
+        // ---- park this split's partial tile, then find out whether we are the last split of the tile
+        const uint32_t a_addr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
+        float* slot = p.ws + ((size_t)work * BM + row) * BN;
+        mbar_wait(smem_u32(&tmem_full_bar[acc]), (lt >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = half * 32; c < BN; c += 64) {
+          uint32_t t[32];
+          tmem_ld32(a_addr + c, t);
+          tmem_ld_wait32(t);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            __stcg(reinterpret_cast<float4*>(slot + c + j),
+                   make_float4(__uint_as_float(t[j]), __uint_as_float(t[j + 1]), __uint_as_float(t[j + 2]),
+                               __uint_as_float(t[j + 3])));
+        }
+        tc_fence_before();
+        mbar_arrive(smem_u32(&tmem_empty_bar[acc]));  // the accumulator stage is free again
+        __threadfence();
+        named_bar_sync(2, 256);
+        if (issuer) *split_flag = atomicAdd(p.counters + tile, 1) == p.splits - 1;
+        named_bar_sync(2, 256);
+        const bool last = *split_flag != 0;
+        named_bar_sync(2, 256);  // everyone has read the flag before the next work item overwrites it
+        if (!last) continue;
+        __threadfence();
+        if (issuer) p.counters[tile] = 0;  // ready for the next launch
+        from_ws = true;
+      }
       const uint32_t acc_addr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
       const bool row_ok = m < p.M;
       const __half* rv = nullptr;
@@ -215,10 +259,29 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
           q[j] = (res && n < p.N) ? *reinterpret_cast<const uint4*>(res + n) : make_uint4(0, 0, 0, 0);
         }
       };
+      // sum of the parked partials of one 32-column chunk, in split order (deterministic)
+      const float* ws_row = p.ws + ((size_t)tile * p.splits * BM + row) * BN;
+      auto load_ws = [&](int c, uint32_t* dst) {
+        float a[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] = 0.f;
+        for (int sp = 0; sp < p.splits; ++sp) {
+          const float* src = ws_row + (size_t)sp * BM * BN + c;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 f = __ldcg(reinterpret_cast<const float4*>(src + j));
+            a[j] += f.x; a[j + 1] += f.y; a[j + 2] += f.z; a[j + 3] += f.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dst[j] = __float_as_uint(a[j]);
+      };
       if (half < NCH) load_res(half * 32, rq[0]);  // residual of the first chunk: before the accumulator wait
-      mbar_wait(smem_u32(&tmem_full_bar[acc]), (lt >> 1) & 1);
-      tc_fence_after();
-      if (half < NCH) tmem_ld32(acc_addr + half * 32, r[0]);
+      if (!from_ws) {
+        mbar_wait(smem_u32(&tmem_full_bar[acc]), (lt >> 1) & 1);
+        tc_fence_after();
+        if (half < NCH) tmem_ld32(acc_addr + half * 32, r[0]);
+      }
 
 #pragma unroll
       for (int i = 0; i < MY_MAX; ++i) {
@@ -228,10 +291,15 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
         const bool staged = p.tma_store && ((c & ~63) + 64 <= BN);  // full 64-column box: smem + TMA store
         uint8_t* box = sC + (n_box & 1) * C_BOX_BYTES;
         if (have) {
-          tmem_ld_wait32(r[i & 1]);
-          if (i + 1 < MY_MAX && cn < BN) {
-            tmem_ld32(acc_addr + cn, r[(i + 1) & 1]);
-            load_res(cn, rq[(i + 1) & 1]);
+          if (from_ws) {
+            load_ws(c, r[i & 1]);
+            if (i + 1 < MY_MAX && cn < BN) load_res(cn, rq[(i + 1) & 1]);
+          } else {
+            tmem_ld_wait32(r[i & 1]);
+            if (i + 1 < MY_MAX && cn < BN) {
+              tmem_ld32(acc_addr + cn, r[(i + 1) & 1]);
+              load_res(cn, rq[(i + 1) & 1]);
+            }
           }
           const uint32_t* rr = r[i & 1];
           const int n0 = ncol0 + c;
@@ -330,8 +398,10 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
           ++n_box;
         }
       }
-      tc_fence_before();
-      mbar_arrive(smem_u32(&tmem_empty_bar[acc]));  // 256 arrivals release the accumulator stage
+      if (!from_ws) {
+        tc_fence_before();
+        mbar_arrive(smem_u32(&tmem_empty_bar[acc]));  // 256 arrivals release the accumulator stage
+      }
     }
     if (issuer) tma_store_wait_read<0>();
   }
@@ -342,6 +412,46 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------ host side
+
+// ---- split-K workspace registry: one region per stream (two streams may run split GEMMs concurrently)
+struct Workspace {
+  void* stream;
+  char* base;
+  size_t bytes;
+};
+constexpr int MAX_WS = 16;
+constexpr size_t WS_COUNTER_BYTES = 64 * 1024;  // int counters for up to 16384 tiles, then the fp32 partials
+static Workspace g_ws[MAX_WS];
+static int g_nws = 0;
+
+static const Workspace* find_ws(void* stream) {
+  for (int i = 0; i < g_nws; ++i)
+    if (g_ws[i].stream == stream) return &g_ws[i];
+  return nullptr;
+}
+
+// Decide the split-K factor for an under-filled problem (tiles <= half the SMs and a long K loop).
+static void plan_split(GemmParams& p, int bn, int tiles, cudaStream_t st) {
+  p.splits = 1;
+  p.kb_per_split = p.num_kb;
+  p.ws = nullptr;
+  p.counters = nullptr;
+  static const bool off = getenv("TB_GEMM_NO_SPLITK") != nullptr;  // diagnostic switch
+  const Workspace* w = find_ws((void*)st);
+  if (off || !w || tiles * 2 > num_sms() || p.num_kb < 8) return;
+  int s = num_sms() / tiles;
+  if (s > p.num_kb / 4) s = p.num_kb / 4;
+  if (s > 16) s = 16;
+  if (s < 2) return;
+  const int kbps = (p.num_kb + s - 1) / s;
+  s = (p.num_kb + kbps - 1) / kbps;  // every split owns at least one k block
+  const size_t need = (size_t)tiles * s * BM * bn * sizeof(float);
+  if (s < 2 || tiles > (int)(WS_COUNTER_BYTES / sizeof(int)) || WS_COUNTER_BYTES + need > w->bytes) return;
+  p.splits = s;
+  p.kb_per_split = kbps;
+  p.counters = reinterpret_cast<int*>(w->base);
+  p.ws = reinterpret_cast<float*>(w->base + WS_COUNTER_BYTES);
+}
 
 template <int BN, int STAGES>
 constexpr int gemm_smem_bytes() {
@@ -364,7 +474,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   }
   p.n_tiles = (p.N + BN - 1) / BN;
   p.m_tiles = m_tiles;
-  const int tiles = p.n_tiles * m_tiles;
+  plan_split(p, BN, p.n_tiles * m_tiles, st);
+  const int tiles = p.n_tiles * m_tiles * p.splits;
   dim3 grid(tiles < num_sms() ? tiles : num_sms());
   gemm_tc_kernel<BN, STAGES, CONV><<<grid, 320, smem, st>>>(tmA, tmB, tmC, p);
   return check_launch("gemm_tc_kernel");
@@ -385,7 +496,11 @@ static int pick_bn(int N) {
 template <bool CONV>
 static int dispatch_gemm(const CUtensorMap& tmA, const void* Bw, long long ldb, GemmParams& p,
                          int m_tiles, cudaStream_t st) {
-  const int bn = pick_bn(p.N);
+  int bn = pick_bn(p.N);
+  // under-filled problems are split along K; 128-wide tiles keep the fix-up (splits x 128 x BN fp32) small
+  if (bn == 256 && p.N % 128 == 0 && m_tiles * ((p.N + 255) / 256) * 2 <= num_sms() && p.num_kb >= 8 &&
+      find_ws((void*)st))
+    bn = 128;
   CUtensorMap tmB;
   {
     uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
@@ -453,6 +568,32 @@ static int fill_epilogue(GemmParams& p, void* C, long long ldc, const tb_epilogu
 }  // namespace tb
 
 using namespace tb;
+
+extern "C" int tb_set_workspace(void* stream, void* ptr, size_t bytes) {
+  int rc = tb_check_device();
+  if (rc) return rc;
+  TB_REQUIRE(ptr == nullptr || ((uintptr_t)ptr % 256 == 0 && bytes > 2 * WS_COUNTER_BYTES), TB_E_ARG,
+             "tb_set_workspace: pointer must be 256-byte aligned and larger than %zu bytes",
+             2 * WS_COUNTER_BYTES);
+  int slot = -1;
+  for (int i = 0; i < g_nws; ++i)
+    if (g_ws[i].stream == stream) slot = i;
+  if (slot < 0) {
+    TB_REQUIRE(ptr != nullptr, TB_E_ARG, "tb_set_workspace: no workspace registered for this stream");
+    TB_REQUIRE(g_nws < MAX_WS, TB_E_ARG, "tb_set_workspace: more than %d streams", MAX_WS);
+    slot = g_nws++;
+  }
+  g_ws[slot].stream = stream;
+  g_ws[slot].base = (char*)ptr;
+  g_ws[slot].bytes = ptr ? bytes : 0;
+  if (ptr) {
+    cudaError_t e = cudaMemsetAsync(ptr, 0, WS_COUNTER_BYTES, (cudaStream_t)stream);
+    TB_REQUIRE(e == cudaSuccess, TB_E_CUDA, "tb_set_workspace memset: %s", cudaGetErrorString(e));
+  } else {
+    g_ws[slot] = g_ws[--g_nws];
+  }
+  return TB_OK;
+}
 
 extern "C" int tb_gemm_f16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
                            int64_t ldc, int M, int N, int K, const tb_epilogue* ep, void* stream) {
