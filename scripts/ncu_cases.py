@@ -110,7 +110,29 @@ def case_geglu():
 
 
 CASES = {k[5:]: v for k, v in globals().items() if k.startswith("case_")}
+TIME = "--time" in sys.argv
+if TIME:
+    sys.argv.remove("--time")
 want = sys.argv[1:] or list(CASES)
+if TIME:  # plain CUDA-event timing (L2-warm, 20 launches back to back): quick A/B between builds
+    for n in want:
+        f = CASES[n]()
+        for _ in range(3):
+            f()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()  # 20 launches in one graph: no host launch latency in the number
+        with torch.cuda.graph(g):
+            for _ in range(20):
+                f()
+        g.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"{n:14s} {1e3 * e0.elapsed_time(e1) / 20:9.1f} us / call")
+    sys.exit(0)
 fns = [(n, CASES[n]()) for n in want]
 for n, f in fns:
     f()

@@ -45,7 +45,11 @@ struct GemmParams {
   int* counters;      // [num_tiles], zero between launches (the fixing CTA resets its tile's counter)
 };
 
-__device__ __forceinline__ float apply_act(float x, int act) {
+// Deliberately NOT inlined: the epilogue is unrolled 16x8 elements and an inlined three-way activation (erff
+// alone is ~35 instructions) blew the kernel up to ~14k SASS instructions, whose instruction-cache misses
+// ("no_instructions" was the top stall reason in ncu) cost more than the activation ever does.  Only the
+// time-embedding MLP uses a GEMM-fused activation on the hot path.
+__device__ __noinline__ float apply_act(float x, int act) {
   switch (act) {
     case TB_ACT_SILU: return x / (1.f + __expf(-x));
     case TB_ACT_QUICK_GELU: return x / (1.f + __expf(-1.702f * x));
@@ -64,7 +68,7 @@ constexpr int tmem_cols() {
   return BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
 }
 
-template <int BN, int STAGES, bool CONV>
+template <int BN, int STAGES, bool CONV, bool FAST>
 __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                          const __grid_constant__ CUtensorMap tmB,
                                                          const __grid_constant__ CUtensorMap tmC,
@@ -86,6 +90,8 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
   uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   volatile uint32_t* split_flag = tmem_slot + 1;
+  // FAST: bias[n] + rowvec[image, n] of the current tile (16-byte aligned: read as float4)
+  float* sBV = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 2) + 15) & ~static_cast<uintptr_t>(15));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -202,6 +208,92 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
     constexpr int MY_MAX = (NCH + 1) / 2;  // chunks per warp (half 0 takes the odd one out)
     int lt = 0;
     uint32_t n_box = 0;  // staging boxes written so far (selects the buffer)
+    if constexpr (FAST) {
+      // ---- FAST epilogue (the UNet's common case, chosen by the host): fp16 output through the TMA-store
+      // boxes, alpha = 1, no activation, optional bias / per-image row vector / fp16 residual, M % 128 == 0,
+      // N % BN == 0, a tile never straddles two images.  ~110 instructions per 32-column chunk instead of ~460:
+      // bias + rowvec are summed once per tile into shared memory (fp32, broadcast reads), the accumulator is
+      // rounded to fp16 once and the residual is added in half2 — the reference adds its residual to the
+      // fp16-rounded conv / linear output the same way.
+      const int epi_tid = threadIdx.x - 64;
+      for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++lt) {
+        const int n_tile = work % p.n_tiles;
+        const int m_tile = work / p.n_tiles;
+        const int acc = lt & 1;
+        const long long m = (long long)m_tile * BM + row;
+        const int ncol0 = n_tile * BN;
+        const uint32_t acc_addr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
+        const __half* res = p.residual ? reinterpret_cast<const __half*>(p.residual) + m * p.ldr + ncol0 : nullptr;
+        named_bar_sync(3, 256);  // every warp has finished reading the previous tile's sBV
+        if (epi_tid < BN) {
+          float bv = p.bias ? __half2float(p.bias[ncol0 + epi_tid]) : 0.f;
+          if (p.rowvec)
+            bv += __half2float(p.rowvec[((long long)m_tile * BM / p.rows_per_group) * p.N + ncol0 + epi_tid]);
+          sBV[epi_tid] = bv;
+        }
+        uint4 rq[4], rq_next[4];
+        if (res && half < NCH) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rq[j] = *reinterpret_cast<const uint4*>(res + half * 32 + 8 * j);
+        }
+        named_bar_sync(3, 256);
+        mbar_wait(smem_u32(&tmem_full_bar[acc]), (lt >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int i = 0; i < MY_MAX; ++i) {
+          const int c = (2 * i + half) * 32;
+          const bool have = c < BN;
+          const bool staged = (c & ~63) + 64 <= BN;
+          uint8_t* box = sC + (n_box & 1) * C_BOX_BYTES;
+          if (have) {
+            uint32_t r[32];
+            tmem_ld32(acc_addr + c, r);
+            if (res && c + 64 < BN) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) rq_next[j] = *reinterpret_cast<const uint4*>(res + c + 64 + 8 * j);
+            }
+            tmem_ld_wait32(r);
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const float4 b0 = *reinterpret_cast<const float4*>(sBV + c + j);
+              const float4 b1 = *reinterpret_cast<const float4*>(sBV + c + j + 4);
+              uint4 o;
+              o.x = pack_half2(__uint_as_float(r[j]) + b0.x, __uint_as_float(r[j + 1]) + b0.y);
+              o.y = pack_half2(__uint_as_float(r[j + 2]) + b0.z, __uint_as_float(r[j + 3]) + b0.w);
+              o.z = pack_half2(__uint_as_float(r[j + 4]) + b1.x, __uint_as_float(r[j + 5]) + b1.y);
+              o.w = pack_half2(__uint_as_float(r[j + 6]) + b1.z, __uint_as_float(r[j + 7]) + b1.w);
+              if (res) {
+                const uint4 q = rq[j >> 3];
+                *reinterpret_cast<__half2*>(&o.x) = __hadd2(*reinterpret_cast<const __half2*>(&o.x), *reinterpret_cast<const __half2*>(&q.x));
+                *reinterpret_cast<__half2*>(&o.y) = __hadd2(*reinterpret_cast<const __half2*>(&o.y), *reinterpret_cast<const __half2*>(&q.y));
+                *reinterpret_cast<__half2*>(&o.z) = __hadd2(*reinterpret_cast<const __half2*>(&o.z), *reinterpret_cast<const __half2*>(&q.z));
+                *reinterpret_cast<__half2*>(&o.w) = __hadd2(*reinterpret_cast<const __half2*>(&o.w), *reinterpret_cast<const __half2*>(&q.w));
+              }
+              if (staged) {
+                const int chunk = ((c & 63) + j) >> 3;
+                *reinterpret_cast<uint4*>(box + row * 128 + ((chunk ^ (row & 7)) << 4)) = o;
+              } else {
+                *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C) + m * p.ldc + ncol0 + c + j) = o;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rq[j] = rq_next[j];
+          }
+          if (64 * i + 64 <= BN) {
+            fence_async_smem();
+            if (issuer) tma_store_wait_read<0>();
+            named_bar_sync(1, 256);
+            if (issuer) {
+              tma_store_2d(&tmC, smem_u32(box), ncol0 + 64 * i, m_tile * BM);
+              tma_store_commit();
+            }
+            ++n_box;
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+      }
+    } else
     for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++lt) {
       const int tile = work / p.splits;
       const int n_tile = tile % p.n_tiles;
@@ -250,8 +342,12 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
         else res = reinterpret_cast<const __half*>(p.residual) + m * p.ldr;
       }
       const int ncol0 = n_tile * BN;
-      uint32_t r[2][32];
-      uint4 rq[2][4];
+      // The chunk loop is deliberately ROLLED (one copy of the ~600-instruction chunk body): fully unrolled and
+      // software-pipelined, the epilogue was 11-14k SASS instructions and ncu's top stall reason was
+      // "no_instructions" (instruction-cache misses on straight-line code run once per tile).  Latency is hidden
+      // by the second epilogue warp of each sub-partition and by prefetching the next chunk's residual.
+      uint32_t r[32];
+      uint4 rq[4], rq_next[4];
       auto load_res = [&](int c, uint4* q) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -261,30 +357,14 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
       };
       // sum of the parked partials of one 32-column chunk, in split order (deterministic)
       const float* ws_row = p.ws + ((size_t)tile * p.splits * BM + row) * BN;
-      auto load_ws = [&](int c, uint32_t* dst) {
-        float a[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) a[j] = 0.f;
-        for (int sp = 0; sp < p.splits; ++sp) {
-          const float* src = ws_row + (size_t)sp * BM * BN + c;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 f = __ldcg(reinterpret_cast<const float4*>(src + j));
-            a[j] += f.x; a[j + 1] += f.y; a[j + 2] += f.z; a[j + 3] += f.w;
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) dst[j] = __float_as_uint(a[j]);
-      };
-      if (half < NCH) load_res(half * 32, rq[0]);  // residual of the first chunk: before the accumulator wait
+      if (half < NCH) load_res(half * 32, rq);  // residual of the first chunk: before the accumulator wait
       if (!from_ws) {
         mbar_wait(smem_u32(&tmem_full_bar[acc]), (lt >> 1) & 1);
         tc_fence_after();
-        if (half < NCH) tmem_ld32(acc_addr + half * 32, r[0]);
       }
 
-#pragma unroll
-      for (int i = 0; i < MY_MAX; ++i) {
+#pragma unroll 1
+      for (int i = 0; i < (p.tma_store == 3 ? 0 : MY_MAX); ++i) {
         const int c = (2 * i + half) * 32;  // first column of this warp's chunk inside the tile
         const int cn = c + 64;              // its next chunk
         const bool have = c < BN;
@@ -292,67 +372,78 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
         uint8_t* box = sC + (n_box & 1) * C_BOX_BYTES;
         if (have) {
           if (from_ws) {
-            load_ws(c, r[i & 1]);
-            if (i + 1 < MY_MAX && cn < BN) load_res(cn, rq[(i + 1) & 1]);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = 0;
+#pragma unroll 1
+            for (int sp = 0; sp < p.splits; ++sp) {
+              const float* src = ws_row + (size_t)sp * BM * BN + c;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 f = __ldcg(reinterpret_cast<const float4*>(src + j));
+                r[j] = __float_as_uint(__uint_as_float(r[j]) + f.x);
+                r[j + 1] = __float_as_uint(__uint_as_float(r[j + 1]) + f.y);
+                r[j + 2] = __float_as_uint(__uint_as_float(r[j + 2]) + f.z);
+                r[j + 3] = __float_as_uint(__uint_as_float(r[j + 3]) + f.w);
+              }
+            }
           } else {
-            tmem_ld_wait32(r[i & 1]);
-            if (i + 1 < MY_MAX && cn < BN) {
-              tmem_ld32(acc_addr + cn, r[(i + 1) & 1]);
-              load_res(cn, rq[(i + 1) & 1]);
+            tmem_ld32(acc_addr + c, r);
+          }
+          if (cn < BN) load_res(cn, rq_next);
+          // every global load of the chunk is issued here, before the TMEM wait and the arithmetic, so their
+          // latencies overlap (left inside the per-group branches they were each exposed in turn)
+          const int n0 = ncol0 + c;
+          uint4 qb[4], qv[4];
+          float4 q32[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int n = n0 + 8 * j;
+            const bool ok = row_ok && n < p.N;
+            qb[j] = (p.bias && ok) ? __ldg(reinterpret_cast<const uint4*>(p.bias + n)) : make_uint4(0, 0, 0, 0);
+            qv[j] = (rv && ok) ? __ldg(reinterpret_cast<const uint4*>(rv + n)) : make_uint4(0, 0, 0, 0);
+            if (res32 && ok) {
+              q32[2 * j] = *reinterpret_cast<const float4*>(res32 + n);
+              q32[2 * j + 1] = *reinterpret_cast<const float4*>(res32 + n + 4);
+            } else {
+              q32[2 * j] = q32[2 * j + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
           }
-          const uint32_t* rr = r[i & 1];
-          const int n0 = ncol0 + c;
+          if (!from_ws) tmem_ld_wait32(r);
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             const int n = n0 + j;
             float v[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(rr[j + k]);
+            for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(r[j + k]);
             if (p.alpha != 1.f) {
 #pragma unroll
               for (int k = 0; k < 8; ++k) v[k] *= p.alpha;
             }
-            if (row_ok && n < p.N) {
-              if (p.bias) {
-                const uint4 q = *reinterpret_cast<const uint4*>(p.bias + n);
-                const __half2* h = reinterpret_cast<const __half2*>(&q);
+            {
+              const __half2* hb = reinterpret_cast<const __half2*>(&qb[j >> 3]);
+              const __half2* hv = reinterpret_cast<const __half2*>(&qv[j >> 3]);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const float2 f = __half22float2(h[k]);
-                  v[2 * k] += f.x;
-                  v[2 * k + 1] += f.y;
-                }
+              for (int k = 0; k < 4; ++k) {
+                const float2 fb = __half22float2(hb[k]), fv = __half22float2(hv[k]);
+                v[2 * k] += fb.x + fv.x;
+                v[2 * k + 1] += fb.y + fv.y;
               }
-              if (rv) {
-                const uint4 q = *reinterpret_cast<const uint4*>(rv + n);
-                const __half2* h = reinterpret_cast<const __half2*>(&q);
+            }
+            if (p.act != TB_ACT_NONE) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const float2 f = __half22float2(h[k]);
-                  v[2 * k] += f.x;
-                  v[2 * k + 1] += f.y;
-                }
-              }
-              if (p.act != TB_ACT_NONE) {
+              for (int k = 0; k < 8; ++k) v[k] = apply_act(v[k], p.act);
+            }
+            if (p.residual) {
+              const __half2* h = reinterpret_cast<const __half2*>(&rq[j >> 3]);
+              const float4 a0 = q32[2 * (j >> 3)], a1 = q32[2 * (j >> 3) + 1];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = apply_act(v[k], p.act);
+              for (int k = 0; k < 4; ++k) {
+                const float2 f = __half22float2(h[k]);
+                v[2 * k] += f.x;
+                v[2 * k + 1] += f.y;
               }
-              if (res) {
-                const __half2* h = reinterpret_cast<const __half2*>(&rq[i & 1][j >> 3]);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const float2 f = __half22float2(h[k]);
-                  v[2 * k] += f.x;
-                  v[2 * k + 1] += f.y;
-                }
-              }
-              if (res32) {
-                const float4 a0 = *reinterpret_cast<const float4*>(res32 + n);
-                const float4 a1 = *reinterpret_cast<const float4*>(res32 + n + 4);
-                v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
-                v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
-              }
+              v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
+              v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
             }
             if (staged) {
               uint4 o;
@@ -385,11 +476,13 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
               }
             }
           }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rq[j] = rq_next[j];
         }
         // box i of the tile (columns [64i, 64i+64)) is complete once both halves have written their chunk
         if (p.tma_store && 64 * i + 64 <= BN) {
           fence_async_smem();
-          if (issuer) tma_store_wait_read<0>();  // the previous box's store has read its buffer out
+          if (issuer && p.tma_store != 2) tma_store_wait_read<0>();  // the previous box's store has read its buffer out
           named_bar_sync(1, 256);
           if (issuer) {
             tma_store_2d(&tmC, smem_u32(box), ncol0 + 64 * i, m_tile * BM);
@@ -455,16 +548,16 @@ static void plan_split(GemmParams& p, int bn, int tiles, cudaStream_t st) {
 
 template <int BN, int STAGES>
 constexpr int gemm_smem_bytes() {
-  return STAGES * (A_STAGE_BYTES + BN * BK * 2) + 2 * C_BOX_BYTES + (2 * STAGES + 5) * 8 + 1024;
+  return STAGES * (A_STAGE_BYTES + BN * BK * 2) + 2 * C_BOX_BYTES + (2 * STAGES + 5) * 8 + 16 + 256 * 4 + 1024;
 }
 
-template <int BN, int STAGES, bool CONV>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
-                       GemmParams& p, int m_tiles, cudaStream_t st) {
+template <int BN, int STAGES, bool CONV, bool FAST>
+static int launch_gemm_v(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                         GemmParams& p, int m_tiles, cudaStream_t st) {
   constexpr int smem = gemm_smem_bytes<BN, STAGES>();
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, CONV>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, CONV, FAST>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(gemm<%d,%d>): %s", BN, STAGES, cudaGetErrorString(e));
@@ -472,13 +565,24 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     }
     configured = true;
   }
+  const int tiles = p.n_tiles * m_tiles * p.splits;
+  dim3 grid(tiles < num_sms() ? tiles : num_sms());
+  gemm_tc_kernel<BN, STAGES, CONV, FAST><<<grid, 320, smem, st>>>(tmA, tmB, tmC, p);
+  return check_launch("gemm_tc_kernel");
+}
+
+template <int BN, int STAGES, bool CONV>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                       GemmParams& p, int m_tiles, cudaStream_t st) {
   p.n_tiles = (p.N + BN - 1) / BN;
   p.m_tiles = m_tiles;
   plan_split(p, BN, p.n_tiles * m_tiles, st);
-  const int tiles = p.n_tiles * m_tiles * p.splits;
-  dim3 grid(tiles < num_sms() ? tiles : num_sms());
-  gemm_tc_kernel<BN, STAGES, CONV><<<grid, 320, smem, st>>>(tmA, tmB, tmC, p);
-  return check_launch("gemm_tc_kernel");
+  static const bool no_fast = getenv("TB_GEMM_NO_FAST_EPILOGUE") != nullptr;  // diagnostic switch
+  const bool fast = BN >= 64 && !no_fast && p.splits == 1 && p.tma_store == 1 && p.out_kind == TB_OUT_F16 &&
+                    p.alpha == 1.f && p.act == TB_ACT_NONE && !p.res_f32 && p.N % BN == 0 && p.M % BM == 0 &&
+                    (!p.rowvec || p.rows_per_group % BM == 0);
+  if (fast) return launch_gemm_v<BN, STAGES, CONV, true>(tmA, tmB, tmC, p, m_tiles, st);
+  return launch_gemm_v<BN, STAGES, CONV, false>(tmA, tmB, tmC, p, m_tiles, st);
 }
 
 // Choose the N tile: 256 when N is a multiple of 256 or large, 160 for the 320/640/960/1920 family,
@@ -520,6 +624,10 @@ static int dispatch_gemm(const CUtensorMap& tmA, const void* Bw, long long ldb, 
     int rc = make_tmap_f16(&tmC, p.C, 2, dims, strides, box);
     if (rc) return rc;
     p.tma_store = 1;
+    static const bool nowait = getenv("TB_GEMM_EXPERIMENT_NOWAIT") != nullptr;  // timing experiment only (races)
+    if (nowait) p.tma_store = 2;
+    static const bool noepi = getenv("TB_GEMM_EXPERIMENT_NOEPI") != nullptr;  // timing experiment only
+    if (noepi) p.tma_store = 3;
   }
   switch (bn) {
     case 256: return launch_gemm<256, 4, CONV>(tmA, tmB, tmC, p, m_tiles, st);
