@@ -31,12 +31,22 @@ for r in raw[2:]:
     for w in WANT:
         if w in col:
             print(f"   {w:68s} {r[col[w]]:>14s} {units[col[w]]}")
+STALLS = "smsp__pcsamp_warps_issue_stalled_"
+print("\n== stall reasons (pc sampling, % of samples) and issue rate")
+for r in kern:
+    items = [(h[len(STALLS):], float(r[i] or 0)) for h, i in col.items() if h.startswith(STALLS) and "not_issued" not in h]
+    tot = sum(v for _, v in items) or 1
+    topr = ", ".join(f"{n} {100 * v / tot:.0f}%" for n, v in sorted(items, key=lambda x: -x[1])[:6])
+    ipc = r[col["sm__inst_executed.avg.per_cycle_active"]] if "sm__inst_executed.avg.per_cycle_active" in col else "?"
+    inst = r[col["smsp__inst_executed.sum"]] if "smsp__inst_executed.sum" in col else "?"
+    print(f"   [{r[col['ID']]}] IPC/SM {ipc}  warp-instr {inst}: {topr}")
 src = run("--page", "source", "--csv")
 blocks = src.split('"Kernel Name",')[1:]
 for k, blk in enumerate(blocks):
     rows = list(csv.reader(io.StringIO('"Kernel Name",' + blk)))
     h = rows[1]
-    body = [r for r in rows[2:] if len(r) == len(h)]
+    ends = [i for i, r in enumerate(rows) if i > 1 and r and r[0] == "Address"]  # a second view repeats the table
+    body = [r for r in rows[2:(ends[0] if ends else len(rows))] if len(r) == len(h)]
     i_src, i_s = h.index("Source"), h.index("Warp Stall Sampling (All Samples)")
     i_ex = h.index("Instructions Executed")
     tot = sum(int(r[i_s]) for r in body) or 1

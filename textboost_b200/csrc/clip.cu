@@ -307,12 +307,12 @@ __global__ void clip_attn_kernel(const __half* __restrict__ qkv, const __half* _
 
 // ------------------------------------------------------------------ activations (fc1 -> act -> fc2)
 __device__ __forceinline__ float act_fwd(float u, int kind) {
-  if (kind == TB_ACT_QUICK_GELU) return u / (1.f + __expf(-1.702f * u));
+  if (kind == TB_ACT_QUICK_GELU) return __fdividef(u, 1.f + __expf(-1.702f * u));
   return 0.5f * u * (1.f + erff(u * 0.70710678118654752f));
 }
 __device__ __forceinline__ float act_bwd(float u, int kind) {
   if (kind == TB_ACT_QUICK_GELU) {
-    const float s = 1.f / (1.f + __expf(-1.702f * u));
+    const float s = __fdividef(1.f, 1.f + __expf(-1.702f * u));
     return s * (1.f + 1.702f * u * (1.f - s));
   }
   const float cdf = 0.5f * (1.f + erff(u * 0.70710678118654752f));

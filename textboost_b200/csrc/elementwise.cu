@@ -221,7 +221,7 @@ __global__ void silu_kernel(const __half* __restrict__ x, __half* __restrict__ y
     float f[8];
     unpack8e(*reinterpret_cast<const uint4*>(x + i * 8), f);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = f[k] / (1.f + __expf(-f[k]));
+    for (int k = 0; k < 8; ++k) f[k] = __fdividef(f[k], 1.f + __expf(-f[k]));
     *reinterpret_cast<uint4*>(y + i * 8) = pack8e(f);
   }
 }

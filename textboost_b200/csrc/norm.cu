@@ -26,9 +26,12 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   o.w = pack_half2(f[6], f[7]);
   return o;
 }
-__device__ __forceinline__ float silu_f(float z) { return z / (1.f + __expf(-z)); }
+// MUFU.RCP-based division: the IEEE divide expands to ~8 instructions per element and made GroupNorm+SiLU
+// issue-bound (IPC 1.8, "wait" the top stall) instead of HBM-bound; the approximation error (~1 ulp fp32) is far
+// below the fp16 rounding of the result.
+__device__ __forceinline__ float silu_f(float z) { return __fdividef(z, 1.f + __expf(-z)); }
 __device__ __forceinline__ float silu_grad(float z) {
-  const float s = 1.f / (1.f + __expf(-z));
+  const float s = __fdividef(1.f, 1.f + __expf(-z));
   return s * (1.f + z * (1.f - s));
 }
 
@@ -41,11 +44,14 @@ struct GnGeom {
 
 // MODE 0: forward statistics  (sum x, sum x^2)
 // MODE 1: backward statistics (sum dz*gamma, sum dz*gamma*xhat)
+// Per-channel constants are folded so that each kernel carries four of them (A = rstd*gamma, Bz = beta - mean*A,
+// ...): with z = x*A + Bz the normalised value times gamma is z - beta, so the backward sums are
+// s1 += dz*gamma, s2 += dz*(z - beta) and no mean / rstd registers are needed in the loops.
 template <int MODE>
-__global__ void gn_stats_kernel(const __half* __restrict__ x, const __half* __restrict__ dy,
-                                const __half* __restrict__ gamma, const __half* __restrict__ beta,
-                                const float* __restrict__ fstats, float* __restrict__ out, GnGeom g,
-                                float eps, int silu) {
+__global__ void __launch_bounds__(320, MODE == 0 ? 2 : 1)
+gn_stats_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, const __half* __restrict__ gamma,
+                const __half* __restrict__ beta, const float* __restrict__ fstats, float* __restrict__ out,
+                GnGeom g, float eps, int silu) {
   extern __shared__ float sg[];  // [G][2]
   const int b = blockIdx.y;
   const int v = threadIdx.x % g.nvec, pl = threadIdx.x / g.nvec;
@@ -56,30 +62,27 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, const __half* __re
   float s1[8], s2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
-  float a[8], bb[8], gm[8], mean[8], rstd[8];
+  float A[8], Bz[8], gm[8], bt[8];
   if (MODE == 1) {
     const float n = (float)g.HW * g.cpg;
-    float gf[8], bf[8];
-    unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), gf);
-    unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), bf);
+    unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), gm);
+    unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), bt);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int grp = (v * 8 + i) / g.cpg;
       const float su = fstats[(b * g.G + grp) * 2], sq = fstats[(b * g.G + grp) * 2 + 1];
-      mean[i] = su / n;
-      rstd[i] = rsqrtf(fmaxf(sq / n - mean[i] * mean[i], 0.f) + eps);
-      gm[i] = gf[i];
-      a[i] = rstd[i] * gf[i];
-      bb[i] = bf[i] - mean[i] * a[i];
+      const float mean = su / n;
+      const float rstd = rsqrtf(fmaxf(sq / n - mean * mean, 0.f) + eps);
+      A[i] = rstd * gm[i];
+      Bz[i] = bt[i] - mean * A[i];
     }
   }
   const size_t base = (size_t)b * g.HW * g.C + (size_t)v * 8;
-  // four pixels per trip: all loads are issued before the arithmetic, so each thread keeps 4 (MODE 0) or 8
-  // (MODE 1) 16-byte loads in flight
-  for (int p = p0 + pl; p < p1; p += 4 * g.k) {
-    uint4 qx[4], qd[4];
+  constexpr int U = MODE == 0 ? 8 : 4;  // pixels per trip: 8 (MODE 0) or 4+4 (MODE 1) 16-byte loads in flight
+  for (int p = p0 + pl; p < p1; p += U * g.k) {
+    uint4 qx[U], qd[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int pp = p + u * g.k;
       if (pp < p1) {
         qx[u] = *reinterpret_cast<const uint4*>(x + base + (size_t)pp * g.C);
@@ -87,7 +90,7 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, const __half* __re
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       if (p + u * g.k >= p1) break;
       float xf[8];
       unpack8(qx[u], xf);
@@ -102,11 +105,11 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, const __half* __re
         unpack8(qd[u], df);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
+          const float z = xf[i] * A[i] + Bz[i];
           float dz = df[i];
-          if (silu) dz *= silu_grad(xf[i] * a[i] + bb[i]);
-          const float dxh = dz * gm[i];
-          s1[i] += dxh;
-          s2[i] += dxh * (xf[i] - mean[i]) * rstd[i];
+          if (silu) dz *= silu_grad(z);
+          s1[i] += dz * gm[i];
+          s2[i] += dz * (z - bt[i]);
         }
       }
     }
@@ -132,19 +135,19 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, const __half* __re
   for (int i = threadIdx.x; i < 2 * g.G; i += blockDim.x) atomicAdd(&out[(size_t)b * g.G * 2 + i], sg[i]);
 }
 
-// MODE 0: y = act(xhat*gamma + beta);  MODE 1: dx = rstd*(dz*gamma - S1/n - xhat*S2/n)
+// MODE 0: y = act(x*A + Bz);  MODE 1: dx = rstd*(dz*gamma - S1/n - xhat*S2/n) = dz*A - x*P + Q (+ add)
 template <int MODE>
-__global__ void gn_apply_kernel(const __half* __restrict__ x, const __half* __restrict__ dy,
-                                const __half* __restrict__ gamma, const __half* __restrict__ beta,
-                                const float* __restrict__ fstats, const float* __restrict__ bstats,
-                                const __half* __restrict__ add, __half* __restrict__ out, GnGeom g,
-                                float eps, int silu) {
+__global__ void __launch_bounds__(320, MODE == 0 ? 2 : 1)
+gn_apply_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, const __half* __restrict__ gamma,
+                const __half* __restrict__ beta, const float* __restrict__ fstats,
+                const float* __restrict__ bstats, const __half* __restrict__ add, __half* __restrict__ out,
+                GnGeom g, float eps, int silu) {
   const int b = blockIdx.y;
   const int v = threadIdx.x % g.nvec, pl = threadIdx.x / g.nvec;
   const int p0 = blockIdx.x * g.ppc;
   const int p1 = min(p0 + g.ppc, g.HW);
   const float n = (float)g.HW * g.cpg;
-  float a[8], bb[8], gm[8], mean[8], rstd[8], m1[8], m2[8];
+  float A[8], Bz[8], P[8], Q[8];
   {
     float gf[8], bf[8];
     unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), gf);
@@ -153,22 +156,23 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, const __half* __re
     for (int i = 0; i < 8; ++i) {
       const int grp = (v * 8 + i) / g.cpg;
       const float su = fstats[(b * g.G + grp) * 2], sq = fstats[(b * g.G + grp) * 2 + 1];
-      mean[i] = su / n;
-      rstd[i] = rsqrtf(fmaxf(sq / n - mean[i] * mean[i], 0.f) + eps);
-      gm[i] = gf[i];
-      a[i] = rstd[i] * gf[i];
-      bb[i] = bf[i] - mean[i] * a[i];
+      const float mean = su / n;
+      const float rstd = rsqrtf(fmaxf(sq / n - mean * mean, 0.f) + eps);
+      A[i] = rstd * gf[i];
+      Bz[i] = bf[i] - mean * A[i];
       if (MODE == 1) {
-        m1[i] = bstats[(b * g.G + grp) * 2] / n;
-        m2[i] = bstats[(b * g.G + grp) * 2 + 1] / n;
+        const float m1 = bstats[(b * g.G + grp) * 2] / n, m2 = bstats[(b * g.G + grp) * 2 + 1] / n;
+        P[i] = rstd * rstd * m2;
+        Q[i] = mean * P[i] - rstd * m1;
       }
     }
   }
   const size_t base = (size_t)b * g.HW * g.C + (size_t)v * 8;
-  for (int p = p0 + pl; p < p1; p += 4 * g.k) {
-    uint4 qx[4], qd[4], qa[4];
+  constexpr int U = MODE == 0 ? 8 : 4;
+  for (int p = p0 + pl; p < p1; p += U * g.k) {
+    uint4 qx[U], qd[U], qa[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int pp = p + u * g.k;
       if (pp < p1) {
         qx[u] = *reinterpret_cast<const uint4*>(x + base + (size_t)pp * g.C);
@@ -179,7 +183,7 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, const __half* __re
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int pp = p + u * g.k;
       if (pp >= p1) break;
       float xf[8], o[8];
@@ -187,7 +191,7 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, const __half* __re
       if (MODE == 0) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float z = xf[i] * a[i] + bb[i];
+          const float z = xf[i] * A[i] + Bz[i];
           o[i] = silu ? silu_f(z) : z;
         }
       } else {
@@ -196,9 +200,8 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, const __half* __re
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float dz = df[i];
-          if (silu) dz *= silu_grad(xf[i] * a[i] + bb[i]);
-          const float xh = (xf[i] - mean[i]) * rstd[i];
-          o[i] = rstd[i] * (dz * gm[i] - m1[i] - xh * m2[i]);
+          if (silu) dz *= silu_grad(xf[i] * A[i] + Bz[i]);
+          o[i] = dz * A[i] - xf[i] * P[i] + Q[i];
         }
         if (add) {
           float af[8];
@@ -219,7 +222,7 @@ static int gn_geom(GnGeom& g, int B, int HW, int C, int G) {
   g.G = G;
   g.cpg = C / G;
   g.nvec = C / 8;
-  TB_REQUIRE(g.nvec <= 1024, TB_E_SHAPE, "groupnorm: C=%d too wide", C);
+  TB_REQUIRE(g.nvec <= 320, TB_E_SHAPE, "groupnorm: C=%d too wide (C <= 2560)", C);
   g.k = g.nvec >= 256 ? 1 : 256 / g.nvec;
   // pixels per CTA: aim at >= 4 CTAs per SM over the whole batch (the small 8x8 / 16x16 levels otherwise run on
   // a few dozen CTAs, each a chain of dependent loads), at most 16 pixels per thread
@@ -265,7 +268,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 constexpr int LN_MAXV = 5;  // C <= 1280: at most 5 vectors of 8 per lane
 
 // one warp per row; the row stays in registers (two-pass mean / variance)
-template <typename XT, typename WT, typename YT>
+template <int MV, typename XT, typename WT, typename YT>
 __global__ void ln_fwd_kernel(const XT* __restrict__ x, long long ldx, const WT* __restrict__ gamma,
                               const WT* __restrict__ beta, YT* __restrict__ y, long long ldy,
                               float* __restrict__ stats, int M, int C, float eps) {
@@ -273,10 +276,10 @@ __global__ void ln_fwd_kernel(const XT* __restrict__ x, long long ldx, const WT*
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
   const int nvec = C / 8;
-  float v[LN_MAXV][8];
+  float v[MV][8];
   float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < LN_MAXV; ++j) {
+  for (int j = 0; j < MV; ++j) {
     const int vi = lane + j * 32;
     if (vi < nvec) {
       load8<XT>(x + row * ldx + vi * 8, v[j]);
@@ -287,7 +290,7 @@ __global__ void ln_fwd_kernel(const XT* __restrict__ x, long long ldx, const WT*
   const float mean = warp_sum(s) / C;
   float q = 0.f;
 #pragma unroll
-  for (int j = 0; j < LN_MAXV; ++j) {
+  for (int j = 0; j < MV; ++j) {
     const int vi = lane + j * 32;
     if (vi < nvec) {
 #pragma unroll
@@ -299,7 +302,7 @@ __global__ void ln_fwd_kernel(const XT* __restrict__ x, long long ldx, const WT*
   }
   const float rstd = rsqrtf(warp_sum(q) / C + eps);
 #pragma unroll
-  for (int j = 0; j < LN_MAXV; ++j) {
+  for (int j = 0; j < MV; ++j) {
     const int vi = lane + j * 32;
     if (vi < nvec) {
       float gf[8], bf[8], o[8];
@@ -317,7 +320,7 @@ __global__ void ln_fwd_kernel(const XT* __restrict__ x, long long ldx, const WT*
 }
 
 // dx = rstd * (dy*gamma - mean(dy*gamma) - xhat * mean(dy*gamma*xhat))  (+ add)
-template <typename DYT, typename XT, typename WT, typename DT>
+template <int MV, typename DYT, typename XT, typename WT, typename DT>
 __global__ void ln_bwd_kernel(const DYT* __restrict__ dy, long long lddy, const XT* __restrict__ x,
                               long long ldx, const WT* __restrict__ gamma,
                               const float* __restrict__ stats, const DT* __restrict__ add,
@@ -327,13 +330,16 @@ __global__ void ln_bwd_kernel(const DYT* __restrict__ dy, long long lddy, const 
   const int lane = threadIdx.x & 31;
   const int nvec = C / 8;
   const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
-  float g[LN_MAXV][8], xh[LN_MAXV][8];
+  float g[MV][8], xh[MV][8];
+  constexpr bool PRE = MV <= 3;
+  float af[PRE ? MV : 1][8];
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int j = 0; j < LN_MAXV; ++j) {
+  for (int j = 0; j < MV; ++j) {
     const int vi = lane + j * 32;
     if (vi < nvec) {
       float df[8], gf[8], xf[8];
+      if (PRE && add) load8<DT>(add + row * (long long)C + vi * 8, af[PRE ? j : 0]);
       load8<DYT>(dy + row * lddy + vi * 8, df);
       load8<WT>(gamma + vi * 8, gf);
       load8<XT>(x + row * ldx + vi * 8, xf);
@@ -349,17 +355,16 @@ __global__ void ln_bwd_kernel(const DYT* __restrict__ dy, long long lddy, const 
   s1 = warp_sum(s1) / C;
   s2 = warp_sum(s2) / C;
 #pragma unroll
-  for (int j = 0; j < LN_MAXV; ++j) {
+  for (int j = 0; j < MV; ++j) {
     const int vi = lane + j * 32;
     if (vi < nvec) {
       float o[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = rstd * (g[j][i] - s1 - xh[j][i] * s2);
       if (add) {
-        float af[8];
-        load8<DT>(add + row * (long long)C + vi * 8, af);
+        if (!PRE) load8<DT>(add + row * (long long)C + vi * 8, af[0]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] += af[i];
+        for (int i = 0; i < 8; ++i) o[i] += af[PRE ? j : 0][i];
       }
       store8<DT>(dx + row * (long long)C + vi * 8, o);
     }
@@ -427,19 +432,27 @@ extern "C" int tb_layernorm_fwd(const void* x, int x_f32, int64_t ldx, const voi
   cudaStream_t st = (cudaStream_t)stream;
   const int wpb = 8;
   const unsigned grid = (unsigned)((M + wpb - 1) / wpb);
-  if (!x_f32 && !w_f32 && !y_f32)
-    ln_fwd_kernel<__half, __half, __half><<<grid, wpb * 32, 0, st>>>(
-        (const __half*)x, ldx, (const __half*)gamma, (const __half*)beta, (__half*)y, ldy, stats, M, C, eps);
-  else if (x_f32 && w_f32 && !y_f32)
-    ln_fwd_kernel<float, float, __half><<<grid, wpb * 32, 0, st>>>(
-        (const float*)x, ldx, (const float*)gamma, (const float*)beta, (__half*)y, ldy, stats, M, C, eps);
-  else if (x_f32 && w_f32 && y_f32)
-    ln_fwd_kernel<float, float, float><<<grid, wpb * 32, 0, st>>>(
-        (const float*)x, ldx, (const float*)gamma, (const float*)beta, (float*)y, ldy, stats, M, C, eps);
-  else {
-    set_error("tb_layernorm_fwd: unsupported type set x_f32=%d w_f32=%d y_f32=%d", x_f32, w_f32, y_f32);
-    return TB_E_ARG;
-  }
+  const int mv = C <= 512 ? 2 : C <= 768 ? 3 : LN_MAXV;  // vectors per lane: short rows keep fewer registers live
+#define TB_LN_FWD(MV)                                                                                          \
+  do {                                                                                                         \
+    if (!x_f32 && !w_f32 && !y_f32)                                                                            \
+      ln_fwd_kernel<MV, __half, __half, __half><<<grid, wpb * 32, 0, st>>>(                                    \
+          (const __half*)x, ldx, (const __half*)gamma, (const __half*)beta, (__half*)y, ldy, stats, M, C, eps); \
+    else if (x_f32 && w_f32 && !y_f32)                                                                         \
+      ln_fwd_kernel<MV, float, float, __half><<<grid, wpb * 32, 0, st>>>(                                      \
+          (const float*)x, ldx, (const float*)gamma, (const float*)beta, (__half*)y, ldy, stats, M, C, eps);   \
+    else if (x_f32 && w_f32 && y_f32)                                                                          \
+      ln_fwd_kernel<MV, float, float, float><<<grid, wpb * 32, 0, st>>>(                                       \
+          (const float*)x, ldx, (const float*)gamma, (const float*)beta, (float*)y, ldy, stats, M, C, eps);    \
+    else {                                                                                                     \
+      set_error("tb_layernorm_fwd: unsupported type set x_f32=%d w_f32=%d y_f32=%d", x_f32, w_f32, y_f32);     \
+      return TB_E_ARG;                                                                                         \
+    }                                                                                                          \
+  } while (0)
+  if (mv == 2) TB_LN_FWD(2);
+  else if (mv == 3) TB_LN_FWD(3);
+  else TB_LN_FWD(LN_MAXV);
+#undef TB_LN_FWD
   return check_launch("ln_fwd_kernel");
 }
 
@@ -455,17 +468,25 @@ extern "C" int tb_layernorm_bwd(const void* dy, int dy_f32, int64_t lddy, const 
   const int wpb = 8;
   const unsigned grid = (unsigned)((M + wpb - 1) / wpb);
   // UNet: everything fp16.  CLIP: x / gamma / add / dx fp32, dy fp16 (from a GEMM) or fp32 (final LN).
-  if (!x_f32)
-    ln_bwd_kernel<__half, __half, __half, __half><<<grid, wpb * 32, 0, st>>>(
-        (const __half*)dy, lddy, (const __half*)x, ldx, (const __half*)gamma, stats, (const __half*)add,
-        (__half*)dx, M, C);
-  else if (!dy_f32)
-    ln_bwd_kernel<__half, float, float, float><<<grid, wpb * 32, 0, st>>>(
-        (const __half*)dy, lddy, (const float*)x, ldx, (const float*)gamma, stats, (const float*)add,
-        (float*)dx, M, C);
-  else
-    ln_bwd_kernel<float, float, float, float><<<grid, wpb * 32, 0, st>>>(
-        (const float*)dy, lddy, (const float*)x, ldx, (const float*)gamma, stats, (const float*)add,
-        (float*)dx, M, C);
+  const int mv = C <= 512 ? 2 : C <= 768 ? 3 : LN_MAXV;
+#define TB_LN_BWD(MV)                                                                                          \
+  do {                                                                                                         \
+    if (!x_f32)                                                                                                \
+      ln_bwd_kernel<MV, __half, __half, __half, __half><<<grid, wpb * 32, 0, st>>>(                            \
+          (const __half*)dy, lddy, (const __half*)x, ldx, (const __half*)gamma, stats, (const __half*)add,     \
+          (__half*)dx, M, C);                                                                                  \
+    else if (!dy_f32)                                                                                          \
+      ln_bwd_kernel<MV, __half, float, float, float><<<grid, wpb * 32, 0, st>>>(                               \
+          (const __half*)dy, lddy, (const float*)x, ldx, (const float*)gamma, stats, (const float*)add,        \
+          (float*)dx, M, C);                                                                                   \
+    else                                                                                                       \
+      ln_bwd_kernel<MV, float, float, float, float><<<grid, wpb * 32, 0, st>>>(                                \
+          (const float*)dy, lddy, (const float*)x, ldx, (const float*)gamma, stats, (const float*)add,         \
+          (float*)dx, M, C);                                                                                   \
+  } while (0)
+  if (mv == 2) TB_LN_BWD(2);
+  else if (mv == 3) TB_LN_BWD(3);
+  else TB_LN_BWD(LN_MAXV);
+#undef TB_LN_BWD
   return check_launch("ln_bwd_kernel");
 }
