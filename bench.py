@@ -232,12 +232,16 @@ def kernel_family_timing(trainer, bt):
         # two untimed eager passes refill the caching allocator after the graph's private pool is gone
         # (a cudaMalloc between the two events would be billed to the kernel), then the GPU is parked
         # behind a sleep kernel so the host runs ahead and the bracketed kernels execute back to back.
+        def local_step():  # rank-local: no all-reduce (the other ranks are not in this code path)
+            trainer.forward_backward(*step_args)
+            trainer.optimizer_step()
+
         for _ in range(2):
-            trainer.step(*step_args)
+            local_step()
         torch.cuda.synchronize()
         rec.clear()
         torch.cuda._sleep(int(0.3 * 1.9e9))
-        trainer.step(*step_args)
+        local_step()
         torch.cuda.synchronize()
     finally:
         for n, f in saved.items():
@@ -269,6 +273,9 @@ def run_ours(args):
         raise SystemExit("bench.py needs a B200: the CUDA library is the product and has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import faulthandler  # a hung collective must show where, and must not burn the GPU lease
+        faulthandler.dump_traceback_later(args.hang_timeout, exit=True)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -387,8 +394,20 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        # The captured graphs hold the NCCL communicator: with them alive destroy_process_group() blocks (measured:
+        # both ranks sat in it until the watchdog fired).  Drop the graphs, meet at a barrier, and leave without
+        # tearing NCCL down -- the result line is already flushed.
+        tr._graph = None
+        replay = None  # noqa: F841
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        import faulthandler
+        faulthandler.cancel_dump_traceback_later()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 
@@ -402,6 +421,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-images", type=int, default=1, help="images per CPU-baseline step (bounded sample)")
     ap.add_argument("--ref-budget-s", type=float, default=240.0)
+    ap.add_argument("--hang-timeout", type=float, default=240.0,
+                    help="multi-GPU only: dump all Python stacks and exit if the run takes longer than this")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -21,6 +21,8 @@
 // TMEM lane quarter w & 3 and the 64-column half w >> 2), warp 8 = TMA producer, warp 9 = MMA issuer.
 // Sixteen softmax warps per SM (two CTAs) are what it takes to keep the MUFU pipe busy: with one thread
 // per row the per-thread TMEM-load / exp latency chain leaves it ~40 % utilised (ncu, profiles/).
+#include <stdlib.h>
+
 #include "host_util.h"
 #include "sm100.cuh"
 
@@ -45,6 +47,7 @@ struct AttnParams {
   __half* dV;
   long long lddv;
   int n_inner;               // fwd: kv tiles; bwd: q tiles
+  int experiment;            // timing experiments only (TB_ATTN_EXPERIMENT): 1 = skip the dQ reds
   long long* trace;          // debug: clock64 timestamps of CTA (0,0,0), [iter][event][warp]; normally null
 };
 
@@ -563,15 +566,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const bool kv_ok = kv0 + row < p.Nk;
     const long long bh = (long long)b * p.heads + h;
     uint32_t ph_dq = 0;
+    // L_i (half 0) / delta_i (half 1) of this thread's query row: loaded one q tile ahead, so the global-load
+    // latency is off the per-iteration critical path (it used to sit between two barriers)
+    auto load_ld = [&](int q) -> float {
+      // +inf makes exp2(. - L) == 0 for padding queries
+      if (half == 0) return q < p.Nq ? p.lse[bh * p.Nq + q] : INFINITY;
+      return q < p.Nq ? p.delta[bh * p.Nq + q] : 0.f;
+    };
+    float ld_next = load_ld(i_begin * 128 + row);
     for (int i = i_begin; i < p.n_inner; ++i) {
       const int it = i - i_begin;
       const int q0 = i * 128;
-      {
-        const int q = q0 + row;
-        // +inf makes exp2(. - L) == 0 for padding queries
-        if (half == 0) sL[row] = q < p.Nq ? p.lse[bh * p.Nq + q] : INFINITY;
-        else sD[row] = q < p.Nq ? p.delta[bh * p.Nq + q] : 0.f;
-      }
+      if (half == 0) sL[row] = ld_next;
+      else sD[row] = ld_next;
+      if (i + 1 < p.n_inner) ld_next = load_ld(q0 + 128 + row);
       named_bar_sync(1, 256);
       // causal: query column c sees this key row iff q0 + c >= kv0 + row
       const int cmin = p.causal ? (kv0 + row - q0) : 0;
@@ -654,7 +662,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             uint32_t r[16];
             tmem_ld16(lane_addr + X_COL + c, r);
             tmem_ld_wait();
-            if (q_ok) {
+            if (q_ok && !p.experiment) {
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 if (cbase + c + g * 4 < p.d) {
@@ -850,6 +858,10 @@ extern "C" int tb_attn_bwd_f16(const void* q, int64_t ldq, const void* k, int64_
   p.dK = (__half*)dK; p.lddk = lddk;
   p.dV = (__half*)dV; p.lddv = lddv;
   p.n_inner = (Nq + 127) / 128;
+  {
+    static const char* ex = getenv("TB_ATTN_EXPERIMENT");
+    p.experiment = ex ? atoi(ex) : 0;
+  }
   const int nb = (d + 63) / 64;
   if (nb == 1) return launch_attn_bwd<1, 1>(tq, tk, tv, tdo, p, B, st);
   if (nb == 2) return launch_attn_bwd<2, 1>(tq, tk, tv, tdo, p, B, st);

@@ -383,8 +383,14 @@ def main(args):
         save_learned_embeddings(text_encoder, added_tokens, aug_token_dict, args.output_dir)
     logger.info(f"Training took {time.perf_counter() - start:.2f} seconds")
     if world > 1:
+        # the captured graph holds the NCCL communicator: release it before the ranks part (destroying the process
+        # group with the graph alive blocks), and leave NCCL teardown to process exit
+        trainer._graph = None
+        run = None  # noqa: F841
+        torch.cuda.synchronize()
         torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+        logging.shutdown()
+        os._exit(0)
     return loss_val
 
 
