@@ -41,6 +41,20 @@ PER_GPU_BATCH = 8
 LATENT = 64
 
 
+def read_traffic(family):
+    """DRAM bytes per launch of a kernel family from the committed ncu capture (profiles/r*_traffic.json, written
+    by scripts/traffic_from_ncu.py); None when no capture is committed."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    if not files:
+        return None, None
+    with open(files[-1]) as f:
+        d = json.load(f)
+    if family not in d:
+        return None, None
+    return d[family]["traffic_bytes_per_launch"], os.path.relpath(files[-1], ROOT)
+
+
 def read_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -199,13 +213,13 @@ def kernel_family_timing(trainer, bt):
     from textboost_b200 import ops
     rec = []
 
-    def wrap(name, fn, flops_of):
+    def wrap(name, fn, flops_of, bytes_of=None):
         def inner(*a, **kw):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             out = fn(*a, **kw)
             e1.record()
-            rec.append((name, flops_of(*a, **kw), e0, e1))
+            rec.append((name, flops_of(*a, **kw), e0, e1, bytes_of(*a, **kw) if bytes_of else 0.0))
             return out
         return inner
 
@@ -216,6 +230,16 @@ def kernel_family_timing(trainer, bt):
     def f_gemm(a, w, **kw):
         return 2.0 * a.shape[0] * a.shape[1] * w.shape[0]
 
+    def b_gemm(a, w, residual=None, out_kind=0, **kw):  # algorithmic bytes: A + W + C (+ residual), each once
+        M, K, N = a.shape[0], a.shape[1], w.shape[0]
+        osz = 2 if out_kind == 0 else 4
+        rb = residual.numel() * residual.element_size() if residual is not None else 0
+        return 2.0 * (M * K + N * K) + osz * M * N + rb
+
+    def b_conv(x, w, residual=None, **kw):
+        B, H, W, Cin = x.shape
+        return 2.0 * (x.numel() + w.numel() + B * H * W * w.shape[0]) + (2.0 * residual.numel() if residual is not None else 0)
+
     def f_attn_fwd(q, k, v, heads, **kw):
         return 4.0 * q.shape[0] * q.shape[1] * k.shape[1] * q.shape[2]
 
@@ -223,8 +247,8 @@ def kernel_family_timing(trainer, bt):
         return (8.0 if need_dq else 6.0) * q.shape[0] * q.shape[1] * k.shape[1] * q.shape[2]
 
     saved = {n: getattr(ops, n) for n in ("conv3x3", "gemm", "attn_fwd", "attn_bwd")}
-    ops.conv3x3 = wrap("conv3x3_igemm", saved["conv3x3"], f_conv)
-    ops.gemm = wrap("gemm", saved["gemm"], f_gemm)
+    ops.conv3x3 = wrap("conv3x3_igemm", saved["conv3x3"], f_conv, b_conv)
+    ops.gemm = wrap("gemm", saved["gemm"], f_gemm, b_gemm)
     ops.attn_fwd = wrap("attn_fwd", saved["attn_fwd"], f_attn_fwd)
     ops.attn_bwd = wrap("attn_bwd", saved["attn_bwd"], f_attn_bwd)
     step_args = (bt["latents"], bt["noise"], bt["timesteps"], bt["input_ids"], bt["prior_ids"])
@@ -247,11 +271,12 @@ def kernel_family_timing(trainer, bt):
         for n, f in saved.items():
             setattr(ops, n, f)
     fam = {}
-    for name, fl, e0, e1 in rec:
-        d = fam.setdefault(name, {"ms": 0.0, "tflop": 0.0, "launches": 0})
+    for name, fl, e0, e1, nbytes in rec:
+        d = fam.setdefault(name, {"ms": 0.0, "tflop": 0.0, "launches": 0, "bytes": 0.0})
         d["ms"] += e0.elapsed_time(e1)
         d["tflop"] += fl / 1e12
         d["launches"] += 1
+        d["bytes"] += nbytes
     return fam
 
 
@@ -363,6 +388,7 @@ def run_ours(args):
         value = images / (ms / 1e3)
         dom = max(fam, key=lambda k: fam[k]["ms"])
         d = fam[dom]
+        traffic, traffic_src = read_traffic(dom)
         achieved = d["tflop"] / (d["ms"] / 1e3)
         step_tf = value * TFLOP_PER_IMG[use_kpl]
         line = {
@@ -379,7 +405,10 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {
                 "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["tf_sustained"],
-                "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"], "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"], "traffic": traffic,
+                "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, family average)",
+                "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch_avg": d.get("bytes", 0.0) / d["launches"],
                 "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "launches_per_step": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
                 "flop_per_launch_avg": d["tflop"] * 1e12 / d["launches"],

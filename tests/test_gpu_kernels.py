@@ -179,7 +179,8 @@ TOL_ATTN = 3e-3
 @pytest.mark.parametrize("B,H,Nq,Nk,d", [(1, 1, 128, 128, 64), (1, 2, 128, 128, 40), (2, 2, 256, 256, 40),
                                          (1, 2, 256, 77, 40), (1, 2, 64, 64, 160), (2, 2, 256, 256, 160),
                                          (1, 2, 256, 77, 160), (1, 2, 300, 200, 80), (2, 8, 1024, 1024, 80),
-                                         (1, 8, 4096, 4096, 40), (2, 8, 4096, 77, 40), (1, 5, 2304, 2304, 64)])
+                                         (1, 8, 4096, 4096, 40), (2, 8, 4096, 77, 40), (1, 5, 2304, 2304, 64),
+                                         (1, 4, 1024, 77, 160), (2, 8, 1024, 77, 80), (8, 8, 4096, 77, 40)])
 def test_attention_fwd_bwd(B, H, Nq, Nk, d):
     from textboost_b200 import ops
     g = torch.Generator(device=dev).manual_seed(Nq + Nk + d)
@@ -209,7 +210,8 @@ def test_attention_fwd_bwd(B, H, Nq, Nk, d):
     assert relerr(dk, kr.grad.transpose(1, 2).reshape(B, Nk, Cc)) < TOL_ATTN
     assert relerr(dv, vr.grad.transpose(1, 2).reshape(B, Nk, Cc)) < TOL_ATTN
     dq2, dk2, dv2 = ops.attn_bwd(q, k, v, o, do, lse, H, need_dq=False)  # first cross-attention: dK/dV only
-    assert dq2 is None and torch.equal(dk2, dk) and torch.equal(dv2, dv)
+    # (under-filled grids split the Q loop over CTAs that meet in fp32 red.adds: equal up to summation order)
+    assert dq2 is None and relerr(dk2, dk) < 1e-3 and relerr(dv2, dv) < 1e-3
 
 
 @pytest.mark.parametrize("B,H,N,d", [(2, 12, 77, 64), (3, 2, 128, 64), (1, 2, 300, 40), (16, 16, 77, 64)])

@@ -47,6 +47,8 @@ struct AttnParams {
   __half* dV;
   long long lddv;
   int n_inner;               // fwd: kv tiles; bwd: q tiles
+  int qsplit;                // bwd: CTAs per KV tile, each owning a contiguous range of Q tiles (1 = whole loop)
+  float* dkv_ws;             // bwd, qsplit > 1: fp32 [2][B][Nk][heads*d] accumulators (dV, dK) filled with red.add
   int experiment;            // timing experiments only (TB_ATTN_EXPERIMENT): 1 = skip the dQ reds
   long long* trace;          // debug: clock64 timestamps of CTA (0,0,0), [iter][event][warp]; normally null
 };
@@ -371,6 +373,25 @@ __global__ void attn_delta_kernel(const __half* __restrict__ O, const __half* __
   }
 }
 
+// q-split backward: fp32 accumulators [2][rows][C] (dV, dK) -> fp16 dV / dK with their row strides
+__global__ void attn_dkv_finish_kernel(const float* __restrict__ ws, __half* __restrict__ dK, long long lddk,
+                                       __half* __restrict__ dV, long long lddv, long long rows, int C) {
+  const long long nvec = rows * (C / 4);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int which = i >= nvec;
+    const long long j = which ? i - nvec : i;
+    const long long r = j / (C / 4);
+    const int c = (int)(j % (C / 4)) * 4;
+    const float4 f = *reinterpret_cast<const float4*>(ws + (which * rows + r) * C + c);
+    __half* dst = which ? dK + r * lddk + c : dV + r * lddv + c;
+    uint2 o;
+    o.x = pack_half2(f.x, f.y);
+    o.y = pack_half2(f.z, f.w);
+    *reinterpret_cast<uint2*>(dst) = o;
+  }
+}
+
 // CTA owns one 128-row KV tile of one (b, h) and loops over the Q tiles.
 //   S^T = K Q^T ; P^T = exp2(S^T*c - L) ; dP^T = V dO^T ; dS^T = P^T o (dP^T - delta)
 //   dV += P^T dO ; dK += dS^T Q ; dQ_i = dS K  (red.add into the fp32 dQ accumulator)
@@ -410,10 +431,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kv0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  // blockIdx.x = kv tile * qsplit + q split: under-filled launches (cross attention: one KV tile per (b,h)) are
+  // split along the Q loop so the grid covers the machine; the splits meet in fp32 red.adds on dkv_ws
+  const int kv0 = (blockIdx.x / p.qsplit) * 128, h = blockIdx.y, b = blockIdx.z;
+  const int qs = blockIdx.x % p.qsplit;
   const uint32_t DK_COL = DV_COL + p.dn;
-  // causal: q tiles entirely before this kv tile see none of its keys
-  const int i_begin = p.causal ? kv0 / 128 : 0;
+  const int q_per = (p.n_inner + p.qsplit - 1) / p.qsplit;
+  // causal: q tiles entirely before this kv tile see none of its keys (never combined with qsplit > 1)
+  const int i_begin = p.causal ? kv0 / 128 : qs * q_per;
+  const int i_end = p.causal ? p.n_inner : min(p.n_inner, i_begin + q_per);
 
   if (threadIdx.x == 288) {
     mbar_init(smem_u32(bar_kv), 1);
@@ -450,7 +476,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
     __syncwarp();
-    for (int i = i_begin; i < p.n_inner; ++i) {
+    for (int i = i_begin; i < i_end; ++i) {
       const int it = i - i_begin;
       const int s = it % STAGES;
       const uint32_t ph = (it / STAGES) & 1;
@@ -482,7 +508,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t k_mn = umma_desc_lo(smem_u32(sK), ABOX), ds_mn = umma_desc_lo(smem_u32(sDS), ABOX);
     uint32_t ph_dqfree = 0;
     mbar_wait(smem_u32(bar_kv), 0);
-    for (int i = i_begin; i < p.n_inner; ++i) {
+    for (int i = i_begin; i < i_end; ++i) {
       const int it = i - i_begin;
       const int s = it % STAGES;
       const uint32_t ph = (it / STAGES) & 1;
@@ -574,12 +600,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       return q < p.Nq ? p.delta[bh * p.Nq + q] : 0.f;
     };
     float ld_next = load_ld(i_begin * 128 + row);
-    for (int i = i_begin; i < p.n_inner; ++i) {
+    for (int i = i_begin; i < i_end; ++i) {
       const int it = i - i_begin;
       const int q0 = i * 128;
       if (half == 0) sL[row] = ld_next;
       else sD[row] = ld_next;
-      if (i + 1 < p.n_inner) ld_next = load_ld(q0 + 128 + row);
+      if (i + 1 < i_end) ld_next = load_ld(q0 + 128 + row);
       named_bar_sync(1, 256);
       // causal: query column c sees this key row iff q0 + c >= kv0 + row
       const int cmin = p.causal ? (kv0 + row - q0) : 0;
@@ -688,7 +714,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_ld16(lane_addr + DV_COL + c, rv);
       tmem_ld16(lane_addr + DK_COL + c, rk);
       tmem_ld_wait();
-      if (kv_ok) {
+      if (kv_ok && p.qsplit > 1) {
+        const long long Cc = (long long)p.heads * p.d;
+        float* wv = p.dkv_ws + ((long long)b * p.Nk + kv0 + row) * Cc + h * p.d;
+        float* wk = wv + (long long)gridDim.z * p.Nk * Cc;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (c + g * 4 < p.d) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wv + c + g * 4),
+                         "f"(__uint_as_float(rv[g * 4 + 0])), "f"(__uint_as_float(rv[g * 4 + 1])),
+                         "f"(__uint_as_float(rv[g * 4 + 2])), "f"(__uint_as_float(rv[g * 4 + 3]))
+                         : "memory");
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wk + c + g * 4),
+                         "f"(__uint_as_float(rk[g * 4 + 0]) * p.scale), "f"(__uint_as_float(rk[g * 4 + 1]) * p.scale),
+                         "f"(__uint_as_float(rk[g * 4 + 2]) * p.scale), "f"(__uint_as_float(rk[g * 4 + 3]) * p.scale)
+                         : "memory");
+          }
+        }
+      } else if (kv_ok) {
         __half* dv = p.dV + ((long long)b * p.Nk + kv0 + row) * p.lddv + h * p.d;
         __half* dk = p.dK + ((long long)b * p.Nk + kv0 + row) * p.lddk + h * p.d;
 #pragma unroll
@@ -781,7 +824,7 @@ static int launch_attn_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const C
     }
     configured = true;
   }
-  dim3 grid((p.Nk + 127) / 128, p.heads, B);
+  dim3 grid(((p.Nk + 127) / 128) * p.qsplit, p.heads, B);
   attn_bwd_kernel<NB, STAGES><<<grid, 320, smem, st>>>(tq, tk, tv, tdo, p);
   return check_launch("attn_bwd_kernel");
 }
@@ -863,7 +906,34 @@ extern "C" int tb_attn_bwd_f16(const void* q, int64_t ldq, const void* k, int64_
     p.experiment = ex ? atoi(ex) : 0;
   }
   const int nb = (d + 63) / 64;
-  if (nb == 1) return launch_attn_bwd<1, 1>(tq, tk, tv, tdo, p, B, st);
-  if (nb == 2) return launch_attn_bwd<2, 1>(tq, tk, tv, tdo, p, B, st);
-  return launch_attn_bwd<3, 1>(tq, tk, tv, tdo, p, B, st);
+  // under-filled grid (cross attention: a single KV tile per (b, h)) -> split the Q loop over several CTAs
+  p.qsplit = 1;
+  p.dkv_ws = nullptr;
+  {
+    static const bool off = getenv("TB_ATTN_NO_QSPLIT") != nullptr;  // diagnostic switch
+    const int ctas = ((Nk + 127) / 128) * heads * B;
+    const int per_sm = nb == 1 ? 2 : 1;  // resident CTAs per SM
+    const Workspace* w = find_ws(stream);
+    const size_t need = 2ull * B * Nk * heads * d * sizeof(float);
+    if (!off && !causal && w && ctas * 2 <= num_sms() * per_sm && p.n_inner >= 4 && (heads * d) % 4 == 0 &&
+        WS_COUNTER_BYTES + need <= w->bytes && lddk % 4 == 0 && lddv % 4 == 0) {
+      int qsp = (num_sms() * per_sm) / ctas;
+      if (qsp > p.n_inner / 2) qsp = p.n_inner / 2;
+      if (qsp >= 2) {
+        p.qsplit = qsp;
+        p.dkv_ws = reinterpret_cast<float*>(w->base + WS_COUNTER_BYTES);
+        cudaError_t e = cudaMemsetAsync(p.dkv_ws, 0, need, st);
+        TB_REQUIRE(e == cudaSuccess, TB_E_CUDA, "tb_attn_bwd_f16: memset dkv_ws: %s", cudaGetErrorString(e));
+      }
+    }
+  }
+  if (nb == 1) rc = launch_attn_bwd<1, 1>(tq, tk, tv, tdo, p, B, st);
+  else if (nb == 2) rc = launch_attn_bwd<2, 1>(tq, tk, tv, tdo, p, B, st);
+  else rc = launch_attn_bwd<3, 1>(tq, tk, tv, tdo, p, B, st);
+  if (rc || p.qsplit == 1) return rc;
+  const long long rows = (long long)B * Nk;
+  const long long nvec = 2 * rows * (heads * d / 4);
+  attn_dkv_finish_kernel<<<(unsigned)((nvec + 255) / 256 > 1184 ? 1184 : (nvec + 255) / 256), 256, 0, st>>>(
+      p.dkv_ws, (__half*)dK, lddk, (__half*)dV, lddv, rows, heads * d);
+  return check_launch("attn_dkv_finish_kernel");
 }

@@ -506,23 +506,6 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
 
 // ------------------------------------------------------------------------------------ host side
 
-// ---- split-K workspace registry: one region per stream (two streams may run split GEMMs concurrently)
-struct Workspace {
-  void* stream;
-  char* base;
-  size_t bytes;
-};
-constexpr int MAX_WS = 16;
-constexpr size_t WS_COUNTER_BYTES = 64 * 1024;  // int counters for up to 16384 tiles, then the fp32 partials
-static Workspace g_ws[MAX_WS];
-static int g_nws = 0;
-
-static const Workspace* find_ws(void* stream) {
-  for (int i = 0; i < g_nws; ++i)
-    if (g_ws[i].stream == stream) return &g_ws[i];
-  return nullptr;
-}
-
 // Decide the split-K factor for an under-filled problem (tiles <= half the SMs and a long K loop).
 static void plan_split(GemmParams& p, int bn, int tiles, cudaStream_t st) {
   p.splits = 1;
@@ -676,32 +659,6 @@ static int fill_epilogue(GemmParams& p, void* C, long long ldc, const tb_epilogu
 }  // namespace tb
 
 using namespace tb;
-
-extern "C" int tb_set_workspace(void* stream, void* ptr, size_t bytes) {
-  int rc = tb_check_device();
-  if (rc) return rc;
-  TB_REQUIRE(ptr == nullptr || ((uintptr_t)ptr % 256 == 0 && bytes > 2 * WS_COUNTER_BYTES), TB_E_ARG,
-             "tb_set_workspace: pointer must be 256-byte aligned and larger than %zu bytes",
-             2 * WS_COUNTER_BYTES);
-  int slot = -1;
-  for (int i = 0; i < g_nws; ++i)
-    if (g_ws[i].stream == stream) slot = i;
-  if (slot < 0) {
-    TB_REQUIRE(ptr != nullptr, TB_E_ARG, "tb_set_workspace: no workspace registered for this stream");
-    TB_REQUIRE(g_nws < MAX_WS, TB_E_ARG, "tb_set_workspace: more than %d streams", MAX_WS);
-    slot = g_nws++;
-  }
-  g_ws[slot].stream = stream;
-  g_ws[slot].base = (char*)ptr;
-  g_ws[slot].bytes = ptr ? bytes : 0;
-  if (ptr) {
-    cudaError_t e = cudaMemsetAsync(ptr, 0, WS_COUNTER_BYTES, (cudaStream_t)stream);
-    TB_REQUIRE(e == cudaSuccess, TB_E_CUDA, "tb_set_workspace memset: %s", cudaGetErrorString(e));
-  } else {
-    g_ws[slot] = g_ws[--g_nws];
-  }
-  return TB_OK;
-}
 
 extern "C" int tb_gemm_f16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
                            int64_t ldc, int M, int N, int K, const tb_epilogue* ep, void* stream) {

@@ -63,7 +63,46 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
   return TB_OK;
 }
 
+constexpr int MAX_WS = 16;
+static Workspace g_ws[MAX_WS];
+static int g_nws = 0;
+
+const Workspace* find_ws(void* stream) {
+  for (int i = 0; i < g_nws; ++i)
+    if (g_ws[i].stream == stream) return &g_ws[i];
+  return nullptr;
+}
+
 }  // namespace tb
+
+using namespace tb;
+
+extern "C" int tb_set_workspace(void* stream, void* ptr, size_t bytes) {
+  int rc = tb_check_device();
+  if (rc) return rc;
+  TB_REQUIRE(ptr == nullptr || ((uintptr_t)ptr % 256 == 0 && bytes > 2 * WS_COUNTER_BYTES), TB_E_ARG,
+             "tb_set_workspace: pointer must be 256-byte aligned and larger than %zu bytes",
+             2 * WS_COUNTER_BYTES);
+  int slot = -1;
+  for (int i = 0; i < g_nws; ++i)
+    if (g_ws[i].stream == stream) slot = i;
+  if (slot < 0) {
+    TB_REQUIRE(ptr != nullptr, TB_E_ARG, "tb_set_workspace: no workspace registered for this stream");
+    TB_REQUIRE(g_nws < MAX_WS, TB_E_ARG, "tb_set_workspace: more than %d streams", MAX_WS);
+    slot = g_nws++;
+  }
+  g_ws[slot].stream = stream;
+  g_ws[slot].base = (char*)ptr;
+  g_ws[slot].bytes = ptr ? bytes : 0;
+  if (ptr) {
+    cudaError_t e = cudaMemsetAsync(ptr, 0, WS_COUNTER_BYTES, (cudaStream_t)stream);
+    TB_REQUIRE(e == cudaSuccess, TB_E_CUDA, "tb_set_workspace memset: %s", cudaGetErrorString(e));
+  } else {
+    g_ws[slot] = g_ws[--g_nws];
+  }
+  return TB_OK;
+}
+
 
 extern "C" int tb_version(void) { return TB_ABI_VERSION; }
 

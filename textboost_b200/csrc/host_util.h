@@ -19,6 +19,18 @@ int check_launch(const char* what);
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                   const uint64_t* strides_bytes, const uint32_t* box);
 
+// Per-stream scratch registered by the caller (tb_set_workspace): split-K partial tiles (gemm.cu) and the fp32
+// dK/dV accumulators of the q-split attention backward (attn.cu).  The first WS_COUNTER_BYTES hold the split-K
+// tile counters and stay zero between launches; everything after is free-for-all scratch, valid only between the
+// start and end of one C-ABI call on that stream.
+struct Workspace {
+  void* stream;
+  char* base;
+  size_t bytes;
+};
+constexpr size_t WS_COUNTER_BYTES = 64 * 1024;
+const Workspace* find_ws(void* stream);
+
 inline int num_sms() {
   static int n = 0;
   if (!n) {
