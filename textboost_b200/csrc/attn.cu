@@ -349,27 +349,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 __global__ void attn_delta_kernel(const __half* __restrict__ O, const __half* __restrict__ dO,
                                   long long ldo, long long lddo, float* __restrict__ delta, int B,
                                   int Nq, int heads, int d) {
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
+  // all 32 lanes stream the row (one 16-byte vector of O and dO each per trip); the per-vector partial dot
+  // products meet in shared memory and lane h sums head h's d/8 vectors.  (Looping over heads with only d/8
+  // lanes active, as before, left 27 of 32 lanes idle at d = 40.)
+  __shared__ float part[8][160];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + w;
   if (row >= (long long)B * Nq) return;
   const int b = row / Nq, q = row % Nq;
-  const int vec_per_head = d / 8;
-  for (int hh = 0; hh < heads; ++hh) {
+  const int vph = d / 8, nvec = heads * vph;
+  for (int v = lane; v < nvec; v += 32) {
+    const uint4 a = *reinterpret_cast<const uint4*>(O + row * ldo + v * 8);
+    const uint4 g = *reinterpret_cast<const uint4*>(dO + row * lddo + v * 8);
+    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+    const __half2* gh = reinterpret_cast<const __half2*>(&g);
     float acc = 0.f;
-    for (int v = lane; v < vec_per_head; v += 32) {
-      const uint4 a = *reinterpret_cast<const uint4*>(O + row * ldo + hh * d + v * 8);
-      const uint4 g = *reinterpret_cast<const uint4*>(dO + row * lddo + hh * d + v * 8);
-      const __half2* ah = reinterpret_cast<const __half2*>(&a);
-      const __half2* gh = reinterpret_cast<const __half2*>(&g);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 x = __half22float2(ah[i]), y = __half22float2(gh[i]);
-        acc += x.x * y.x + x.y * y.y;
-      }
+    for (int i = 0; i < 4; ++i) {
+      const float2 x = __half22float2(ah[i]), y = __half22float2(gh[i]);
+      acc += x.x * y.x + x.y * y.y;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) delta[((long long)b * heads + hh) * Nq + q] = acc;
+    part[w][v] = acc;
+  }
+  __syncwarp();
+  for (int hh = lane; hh < heads; hh += 32) {
+    float acc = 0.f;
+    for (int v = 0; v < vph; ++v) acc += part[w][hh * vph + v];
+    delta[((long long)b * heads + hh) * Nq + q] = acc;
   }
 }
 
@@ -871,6 +877,7 @@ extern "C" int tb_attn_bwd_f16(const void* q, int64_t ldq, const void* k, int64_
   if (rc) return rc;
   TB_REQUIRE(ldo % 8 == 0 && lddo % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0 && lddq % 4 == 0,
              TB_E_ALIGN, "tb_attn_bwd_f16: stride alignment");
+  TB_REQUIRE(heads * d <= 1280, TB_E_SHAPE, "tb_attn_bwd_f16: heads*d = %d > 1280", heads * d);
   cudaStream_t st = (cudaStream_t)stream;
   {
     const long long rows = (long long)B * Nq;

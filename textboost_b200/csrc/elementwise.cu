@@ -275,9 +275,11 @@ __global__ void conv_in_kernel(const __half* __restrict__ x, const __half* __res
                                const __half* __restrict__ bias, __half* __restrict__ y, int B, int H,
                                int W, int Cin, int Cout) {
   extern __shared__ __half sw[];  // [Cin*9][Cout]
-  for (int i = threadIdx.x; i < Cout * Cin * 9; i += blockDim.x) {
-    const int co = i / (Cin * 9), r = i % (Cin * 9);
-    sw[r * Cout + co] = w[i];
+  // staged [Cin*9][Cout] with consecutive threads writing consecutive shared addresses (the transposing order used
+  // before put a whole warp on one bank), by a grid of only a few CTAs per SM (each CTA stages the table once)
+  for (int j = threadIdx.x; j < Cout * Cin * 9; j += blockDim.x) {
+    const int r = j / Cout, co = j - r * Cout;
+    sw[j] = w[co * (Cin * 9) + r];
   }
   __syncthreads();
   const int cv = Cout / 8;
@@ -313,9 +315,9 @@ __global__ void conv_out_kernel(const __half* __restrict__ h, const __half* __re
                                 const __half* __restrict__ bias, __half* __restrict__ y, int B, int H,
                                 int W, int Cin) {
   extern __shared__ __half sw[];  // [COUT][9][Cin]
-  for (int i = threadIdx.x; i < COUT * Cin * 9; i += blockDim.x) {
-    const int co = i / (Cin * 9), r = i % (Cin * 9), ci = r / 9, tap = r % 9;
-    sw[(co * 9 + tap) * Cin + ci] = w[i];
+  for (int j = threadIdx.x; j < COUT * Cin * 9; j += blockDim.x) {  // conflict-free: j is the shared index
+    const int ct = j / Cin, ci = j - ct * Cin, co = ct / 9, tap = ct - co * 9;
+    sw[j] = w[(co * Cin + ci) * 9 + tap];
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -361,9 +363,9 @@ template <int COUT>
 __global__ void conv_out_bwd_kernel(const __half* __restrict__ dy, const __half* __restrict__ w,
                                     __half* __restrict__ dh, int B, int H, int W, int Cin) {
   extern __shared__ __half sw[];  // [COUT][9][Cin]
-  for (int i = threadIdx.x; i < COUT * Cin * 9; i += blockDim.x) {
-    const int co = i / (Cin * 9), r = i % (Cin * 9), ci = r / 9, tap = r % 9;
-    sw[(co * 9 + tap) * Cin + ci] = w[i];
+  for (int j = threadIdx.x; j < COUT * Cin * 9; j += blockDim.x) {  // conflict-free: j is the shared index
+    const int ct = j / Cin, ci = j - ct * Cin, co = ct / 9, tap = ct - co * 9;
+    sw[j] = w[(co * Cin + ci) * 9 + tap];
   }
   __syncthreads();
   const int cv = Cin / 8;
@@ -503,7 +505,9 @@ extern "C" int tb_conv_in_f16(const void* x_nchw, const void* w, const void* bia
   TB_REQUIRE(x_nchw && w && bias && y_nhwc, TB_E_ARG, "tb_conv_in_f16: null pointer");
   TB_REQUIRE(Cin <= 8 && Cout % 8 == 0 && Cout * Cin * 9 * 2 <= 48 * 1024, TB_E_SHAPE,
              "tb_conv_in_f16: Cin=%d Cout=%d unsupported", Cin, Cout);
-  conv_in_kernel<<<grid_for((long long)B * H * W * (Cout / 8), 256), 256, Cout * Cin * 9 * 2, st>>>(
+  unsigned grid = grid_for((long long)B * H * W * (Cout / 8), 256);
+  if (grid > 4u * num_sms()) grid = 4u * num_sms();
+  conv_in_kernel<<<grid, 256, Cout * Cin * 9 * 2, st>>>(
       (const __half*)x_nchw, (const __half*)w, (const __half*)bias, (__half*)y_nhwc, B, H, W, Cin, Cout);
   return check_launch("conv_in_kernel");
 }
@@ -515,7 +519,7 @@ extern "C" int tb_conv_out_f16(const void* h_nhwc, const void* w, const void* bi
              "tb_conv_out_f16: Cin=%d Cout=%d unsupported (Cout must be 4)", Cin, Cout);
   const long long npix = (long long)B * H * W;
   long long blocks = (npix + 7) / 8;
-  if (blocks > 16 * num_sms()) blocks = 16 * num_sms();
+  if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
   conv_out_kernel<4><<<(unsigned)blocks, 256, Cout * Cin * 9 * 2, st>>>(
       (const __half*)h_nhwc, (const __half*)w, (const __half*)bias, (__half*)y_nchw, B, H, W, Cin);
   return check_launch("conv_out_kernel");
@@ -526,7 +530,9 @@ extern "C" int tb_conv_out_bwd_f16(const void* dy_nchw, const void* w, void* dh_
   TB_REQUIRE(dy_nchw && w && dh_nhwc, TB_E_ARG, "tb_conv_out_bwd_f16: null pointer");
   TB_REQUIRE(Cout == 4 && Cin % 8 == 0 && Cout * Cin * 9 * 2 <= 48 * 1024, TB_E_SHAPE,
              "tb_conv_out_bwd_f16: Cin=%d Cout=%d unsupported", Cin, Cout);
-  conv_out_bwd_kernel<4><<<grid_for((long long)B * H * W * (Cin / 8), 256), 256, Cout * Cin * 9 * 2, st>>>(
+  unsigned grid = grid_for((long long)B * H * W * (Cin / 8), 256);
+  if (grid > 4u * num_sms()) grid = 4u * num_sms();
+  conv_out_bwd_kernel<4><<<grid, 256, Cout * Cin * 9 * 2, st>>>(
       (const __half*)dy_nchw, (const __half*)w, (__half*)dh_nhwc, B, H, W, Cin);
   return check_launch("conv_out_bwd_kernel");
 }
