@@ -252,6 +252,23 @@ def test_step_sd15_vs_oracle():
     assert abs(r["grad_norm"] - r["grad_norm_ref"]) < 2e-3 * r["grad_norm_ref"]
 
 
+def test_step_sd21_openclip_h_vs_oracle():
+    """configs[4]: SD-2.x UNet (head_dim 64, linear projections, 1024-wide context) + OpenCLIP-H text encoder
+    (23 layers, gelu), v-prediction, KPL (mse); 32x32 latents keep the fp32 oracle fast."""
+    from oracle import harness
+    from textboost_b200 import synthetic
+    tr = synthetic.build_trainer("sd21", dev, seed=5, n_added=2, lora_b_std=0.02, keep_sd=True, learning_rate=1e-4,
+                                 prediction_type="v_prediction", kpl_type="mse")
+    bt = synthetic.batch(2, 32, 9, 49408, dev)
+    bt["input_ids"][0, 5] = 49409
+    r = harness.compare_step(tr, bt, device=dev)
+    print({k: v for k, v in r.items() if isinstance(v, float)})
+    assert abs(r["loss"] - r["loss_ref"]) < 1e-3 * abs(r["loss_ref"])
+    assert r["pred_rel"] < 3e-3
+    assert r["lora_grad_rel_l2"] < 5e-3 and r["lora_grad_cos"] > 0.99999
+    assert r["row_grad_rel"] < 5e-3
+
+
 def test_step_graph_replay_matches_eager_and_trains():
     """The captured CUDA graph computes the same step as the eager path; the loss goes down over steps;
     the GradScaler never skips at the default scale; host-facing API returns the same loss."""
@@ -273,6 +290,35 @@ def test_step_graph_replay_matches_eager_and_trains():
     host = [a.cpu().pin_memory() if a is not None else None for a in args]
     l_host = tr.step_from_host(*host)
     assert abs(l_host - tr.loss.item()) == 0.0
+
+
+def test_data_parallel_identity_on_the_cuda_path():
+    """SURVEY.md §8e on the product path: 2 ranks x B/2 rows, SUM of the flat gradient buffers, 1/world inside
+    the fused optimiser  ==  1 rank x B rows.  (The ranks are emulated in sequence on one GPU; the NCCL leg
+    itself is exercised by bench.py --gpus N / scripts/dp2_check.sh.)"""
+    from textboost_b200 import synthetic
+    kw = dict(seed=3, n_added=2, lora_b_std=0.02, kpl_weight=0.1, learning_rate=1e-3)
+    full, ra, rb = (synthetic.build_trainer("tiny", dev, **kw) for _ in range(3))
+    bt = synthetic.batch(4, 16, 5, full.synthetic["clip_cfg"].vocab_size, dev)
+    keys = ("latents", "noise", "timesteps", "input_ids", "prior_ids")
+    full.forward_backward(*(bt[k] for k in keys))
+    ra.forward_backward(*(bt[k][:2].contiguous() for k in keys))
+    rb.forward_backward(*(bt[k][2:].contiguous() for k in keys))
+    g_sum = ra.te.state.grads + rb.te.state.grads  # what the all-reduce (SUM) leaves on every rank
+    g_full = full.te.state.grads.clone()
+    assert ((0.5 * g_sum - g_full).norm() / g_full.norm()).item() < 2e-3
+    assert abs(0.5 * (ra.loss.item() + rb.loss.item()) - full.loss.item()) < 1e-3 * abs(full.loss.item())
+    ra.te.state.grads.copy_(g_sum)
+    ra.opt.world_size = 2
+    ra.optimizer_step()
+    full.optimizer_step()
+    torch.cuda.synchronize()
+    # Adam's first step is ~lr*sign(g): compare the parameter UPDATES, away from g ~ 0
+    d_dp = ra.te.state.params - rb.te.state.params
+    d_full = full.te.state.params - rb.te.state.params
+    big = g_full.abs() > 1e-3 * g_full.abs().max()
+    assert ((d_dp - d_full)[big].abs().max() / d_full[big].abs().max()).item() < 2e-2
+    assert abs(ra.opt_state[7].item() - full.opt_state[7].item()) < 2e-3 * full.opt_state[7].item()  # grad norm
 
 
 def test_empty_prompt_batch_gives_zero_instance_gradient():
