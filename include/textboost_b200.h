@@ -65,7 +65,7 @@ const char* tb_last_error(void);
 int tb_check_device(void);
 
 /* Optional split-K scratch for under-filled GEMM / conv problems (few output tiles, long K): `ptr` is a
- * caller-owned device buffer (256-byte aligned, >= 128 KiB; 64 MiB covers every SD shape) that tb_gemm_f16 /
+ * caller-owned device buffer (256-byte aligned, >= 128 KiB; 32 MiB covers every SD shape) that tb_gemm_f16 /
  * tb_conv3x3_f16 calls enqueued on `stream` may use between their own start and end.  One region per stream:
  * calls on different streams can run concurrently.  ptr == NULL unregisters.  Without a workspace the kernels
  * never split (same results up to fp32 summation order).  The library still never allocates. */

@@ -132,7 +132,7 @@ def call(name: str, *args):
     launch_count += _KERNELS_PER_CALL.get(name, 1)
 
 
-WORKSPACE_BYTES = 64 << 20
+WORKSPACE_BYTES = 32 << 20
 _workspaces = {}  # (device index, stream handle) -> tensor kept alive for the library
 
 

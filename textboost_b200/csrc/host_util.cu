@@ -63,7 +63,7 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
   return TB_OK;
 }
 
-constexpr int MAX_WS = 16;
+constexpr int MAX_WS = 64;  // PyTorch hands out streams from a pool of 32 per device and priority
 static Workspace g_ws[MAX_WS];
 static int g_nws = 0;
 
