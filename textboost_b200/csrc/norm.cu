@@ -42,6 +42,57 @@ struct GnGeom {
   int HW, C, G, cpg, nvec, k, ppc;  // ppc = pixels per CTA
 };
 
+// Per-group statistics of the 8 channels a thread owns.  With cpg >= 8 (every SD level: C/32 >= 10) eight
+// consecutive channels span at most two groups, so mean / rstd (and the backward means) are computed for two
+// groups and selected per channel — no per-channel integer or IEEE divisions (they were ~30 % of all
+// instructions of these kernels: 32 FCHK/CALL division sequences and 8 integer divisions per thread).
+struct GnGroupConst {
+  float mean[8], rstd[8], m1[8], m2[8];
+};
+template <bool BWD>
+__device__ __forceinline__ void gn_group_consts(GnGroupConst& k, const GnGeom& g, int b, int v,
+                                                const float* __restrict__ fstats,
+                                                const float* __restrict__ bstats, float eps) {
+  const float inv_n = 1.f / ((float)g.HW * g.cpg);
+  const int c0 = v * 8;
+  const int g0 = c0 / g.cpg;
+  if (g.cpg >= 8) {
+    const int r0 = c0 - g0 * g.cpg;
+    const int g1 = min(g0 + 1, g.G - 1);
+    float mean2[2], rstd2[2], a2[2] = {0.f, 0.f}, b2[2] = {0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int grp = t ? g1 : g0;
+      const float2 st = *reinterpret_cast<const float2*>(fstats + (b * g.G + grp) * 2);
+      mean2[t] = st.x * inv_n;
+      rstd2[t] = rsqrtf(fmaxf(st.y * inv_n - mean2[t] * mean2[t], 0.f) + eps);
+      if (BWD) {
+        const float2 bs = *reinterpret_cast<const float2*>(bstats + (b * g.G + grp) * 2);
+        a2[t] = bs.x * inv_n;
+        b2[t] = bs.y * inv_n;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int t = (r0 + i) >= g.cpg;
+      k.mean[i] = mean2[t];
+      k.rstd[i] = rstd2[t];
+      k.m1[i] = a2[t];
+      k.m2[i] = b2[t];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int grp = (c0 + i) / g.cpg;
+      const float su = fstats[(b * g.G + grp) * 2], sq = fstats[(b * g.G + grp) * 2 + 1];
+      k.mean[i] = su * inv_n;
+      k.rstd[i] = rsqrtf(fmaxf(sq * inv_n - k.mean[i] * k.mean[i], 0.f) + eps);
+      k.m1[i] = BWD ? bstats[(b * g.G + grp) * 2] * inv_n : 0.f;
+      k.m2[i] = BWD ? bstats[(b * g.G + grp) * 2 + 1] * inv_n : 0.f;
+    }
+  }
+}
+
 // MODE 0: forward statistics  (sum x, sum x^2)
 // MODE 1: backward statistics (sum dz*gamma, sum dz*gamma*xhat)
 // Per-channel constants are folded so that each kernel carries four of them (A = rstd*gamma, Bz = beta - mean*A,
@@ -64,17 +115,14 @@ gn_stats_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, con
   for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
   float A[8], Bz[8], gm[8], bt[8];
   if (MODE == 1) {
-    const float n = (float)g.HW * g.cpg;
     unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), gm);
     unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), bt);
+    GnGroupConst k;
+    gn_group_consts<false>(k, g, b, v, fstats, nullptr, eps);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int grp = (v * 8 + i) / g.cpg;
-      const float su = fstats[(b * g.G + grp) * 2], sq = fstats[(b * g.G + grp) * 2 + 1];
-      const float mean = su / n;
-      const float rstd = rsqrtf(fmaxf(sq / n - mean * mean, 0.f) + eps);
-      A[i] = rstd * gm[i];
-      Bz[i] = bt[i] - mean * A[i];
+      A[i] = k.rstd[i] * gm[i];
+      Bz[i] = bt[i] - k.mean[i] * A[i];
     }
   }
   const size_t base = (size_t)b * g.HW * g.C + (size_t)v * 8;
@@ -146,24 +194,20 @@ gn_apply_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, con
   const int v = threadIdx.x % g.nvec, pl = threadIdx.x / g.nvec;
   const int p0 = blockIdx.x * g.ppc;
   const int p1 = min(p0 + g.ppc, g.HW);
-  const float n = (float)g.HW * g.cpg;
   float A[8], Bz[8], P[8], Q[8];
   {
     float gf[8], bf[8];
     unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), gf);
     unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), bf);
+    GnGroupConst k;
+    gn_group_consts<MODE == 1>(k, g, b, v, fstats, bstats, eps);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int grp = (v * 8 + i) / g.cpg;
-      const float su = fstats[(b * g.G + grp) * 2], sq = fstats[(b * g.G + grp) * 2 + 1];
-      const float mean = su / n;
-      const float rstd = rsqrtf(fmaxf(sq / n - mean * mean, 0.f) + eps);
-      A[i] = rstd * gf[i];
-      Bz[i] = bf[i] - mean * A[i];
+      A[i] = k.rstd[i] * gf[i];
+      Bz[i] = bf[i] - k.mean[i] * A[i];
       if (MODE == 1) {
-        const float m1 = bstats[(b * g.G + grp) * 2] / n, m2 = bstats[(b * g.G + grp) * 2 + 1] / n;
-        P[i] = rstd * rstd * m2;
-        Q[i] = mean * P[i] - rstd * m1;
+        P[i] = k.rstd[i] * k.rstd[i] * k.m2[i];
+        Q[i] = k.mean[i] * P[i] - k.rstd[i] * k.m1[i];
       }
     }
   }
