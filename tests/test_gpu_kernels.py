@@ -259,7 +259,8 @@ def test_groupnorm_fwd_bwd(B, HW, Cc, silu):
     assert relerr(dx, xr.grad.transpose(1, 2) + add.float()) < 3e-3
 
 
-@pytest.mark.parametrize("M,Cc,f32", [(512, 320, False), (77, 1280, False), (616, 768, True), (154, 1024, True)])
+@pytest.mark.parametrize("M,Cc,f32", [(512, 320, False), (77, 1280, False), (616, 768, True), (154, 1024, True),
+                                      (130, 320, False), (1001, 640, False), (3, 640, False), (37, 128, True)])
 def test_layernorm_fwd_bwd(M, Cc, f32):
     from textboost_b200 import ops
     torch.manual_seed(M + Cc)

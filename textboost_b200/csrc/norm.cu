@@ -312,30 +312,42 @@ __device__ __forceinline__ float warp_sum(float v) {
 constexpr int LN_MAXV = 5;  // C <= 1280: at most 5 vectors of 8 per lane
 
 // one warp per row; the row stays in registers (two-pass mean / variance)
-template <int MV, typename XT, typename WT, typename YT>
+// LPR lanes cooperate on one row (32 / LPR rows per warp), MV vectors of 8 per lane: C = 320 -> 8 lanes x 5
+// vectors (4 rows per warp), C = 640 -> 16 x 5, otherwise a whole warp per row.  With a warp per row and 40
+// vectors per row, 24 of 32 lanes idled through the second vector trip.
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int LPR, int MV, typename XT, typename WT, typename YT>
 __global__ void ln_fwd_kernel(const XT* __restrict__ x, long long ldx, const WT* __restrict__ gamma,
                               const WT* __restrict__ beta, YT* __restrict__ y, long long ldy,
                               float* __restrict__ stats, int M, int C, float eps) {
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
-  const int lane = threadIdx.x & 31;
+  constexpr int RPW = 32 / LPR;
+  const long long row_raw = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + (threadIdx.x & 31) / LPR;
+  const bool row_ok = row_raw < M;
+  const long long row = row_ok ? row_raw : M - 1;  // out-of-range lanes shadow the last row (shuffles stay warp-wide)
+  const int lane = (threadIdx.x & 31) % LPR;
   const int nvec = C / 8;
   float v[MV][8];
   float s = 0.f;
 #pragma unroll
   for (int j = 0; j < MV; ++j) {
-    const int vi = lane + j * 32;
+    const int vi = lane + j * LPR;
     if (vi < nvec) {
       load8<XT>(x + row * ldx + vi * 8, v[j]);
 #pragma unroll
       for (int i = 0; i < 8; ++i) s += v[j][i];
     }
   }
-  const float mean = warp_sum(s) / C;
+  const float mean = group_sum<LPR>(s) / C;
   float q = 0.f;
 #pragma unroll
   for (int j = 0; j < MV; ++j) {
-    const int vi = lane + j * 32;
+    const int vi = lane + j * LPR;
     if (vi < nvec) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -344,34 +356,36 @@ __global__ void ln_fwd_kernel(const XT* __restrict__ x, long long ldx, const WT*
       }
     }
   }
-  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+  const float rstd = rsqrtf(group_sum<LPR>(q) / C + eps);
 #pragma unroll
   for (int j = 0; j < MV; ++j) {
-    const int vi = lane + j * 32;
+    const int vi = lane + j * LPR;
     if (vi < nvec) {
       float gf[8], bf[8], o[8];
       load8<WT>(gamma + vi * 8, gf);
       load8<WT>(beta + vi * 8, bf);
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = (v[j][i] - mean) * rstd * gf[i] + bf[i];
-      store8<YT>(y + row * ldy + vi * 8, o);
+      if (row_ok) store8<YT>(y + row * ldy + vi * 8, o);
     }
   }
-  if (lane == 0 && stats) {
+  if (lane == 0 && stats && row_ok) {
     stats[row * 2] = mean;
     stats[row * 2 + 1] = rstd;
   }
 }
 
 // dx = rstd * (dy*gamma - mean(dy*gamma) - xhat * mean(dy*gamma*xhat))  (+ add)
-template <int MV, typename DYT, typename XT, typename WT, typename DT>
+template <int LPR, int MV, typename DYT, typename XT, typename WT, typename DT>
 __global__ void ln_bwd_kernel(const DYT* __restrict__ dy, long long lddy, const XT* __restrict__ x,
                               long long ldx, const WT* __restrict__ gamma,
                               const float* __restrict__ stats, const DT* __restrict__ add,
                               DT* __restrict__ dx, int M, int C) {
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
-  const int lane = threadIdx.x & 31;
+  constexpr int RPW = 32 / LPR;
+  const long long row_raw = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + (threadIdx.x & 31) / LPR;
+  const bool row_ok = row_raw < M;
+  const long long row = row_ok ? row_raw : M - 1;  // out-of-range lanes shadow the last row (shuffles stay warp-wide)
+  const int lane = (threadIdx.x & 31) % LPR;
   const int nvec = C / 8;
   const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
   float g[MV][8], xh[MV][8];
@@ -380,7 +394,7 @@ __global__ void ln_bwd_kernel(const DYT* __restrict__ dy, long long lddy, const 
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int j = 0; j < MV; ++j) {
-    const int vi = lane + j * 32;
+    const int vi = lane + j * LPR;
     if (vi < nvec) {
       float df[8], gf[8], xf[8];
       if (PRE && add) load8<DT>(add + row * (long long)C + vi * 8, af[PRE ? j : 0]);
@@ -396,11 +410,11 @@ __global__ void ln_bwd_kernel(const DYT* __restrict__ dy, long long lddy, const 
       }
     }
   }
-  s1 = warp_sum(s1) / C;
-  s2 = warp_sum(s2) / C;
+  s1 = group_sum<LPR>(s1) / C;
+  s2 = group_sum<LPR>(s2) / C;
 #pragma unroll
   for (int j = 0; j < MV; ++j) {
-    const int vi = lane + j * 32;
+    const int vi = lane + j * LPR;
     if (vi < nvec) {
       float o[8];
 #pragma unroll
@@ -410,7 +424,7 @@ __global__ void ln_bwd_kernel(const DYT* __restrict__ dy, long long lddy, const 
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] += af[PRE ? j : 0][i];
       }
-      store8<DT>(dx + row * (long long)C + vi * 8, o);
+      if (row_ok) store8<DT>(dx + row * (long long)C + vi * 8, o);
     }
   }
 }
@@ -475,27 +489,31 @@ extern "C" int tb_layernorm_fwd(const void* x, int x_f32, int64_t ldx, const voi
   TB_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0, TB_E_ALIGN, "tb_layernorm_fwd: ldx/ldy alignment");
   cudaStream_t st = (cudaStream_t)stream;
   const int wpb = 8;
-  const unsigned grid = (unsigned)((M + wpb - 1) / wpb);
+  const int lpr = C == 320 ? 8 : C == 640 ? 16 : 32;
+  const int rpb = wpb * (32 / lpr);  // rows per block
+  const unsigned grid = (unsigned)((M + rpb - 1) / rpb);
   const int mv = C <= 512 ? 2 : C <= 768 ? 3 : LN_MAXV;  // vectors per lane: short rows keep fewer registers live
-#define TB_LN_FWD(MV)                                                                                          \
+#define TB_LN_FWD(LPR, MV)                                                                                          \
   do {                                                                                                         \
     if (!x_f32 && !w_f32 && !y_f32)                                                                            \
-      ln_fwd_kernel<MV, __half, __half, __half><<<grid, wpb * 32, 0, st>>>(                                    \
+      ln_fwd_kernel<LPR, MV, __half, __half, __half><<<grid, wpb * 32, 0, st>>>(                                    \
           (const __half*)x, ldx, (const __half*)gamma, (const __half*)beta, (__half*)y, ldy, stats, M, C, eps); \
     else if (x_f32 && w_f32 && !y_f32)                                                                         \
-      ln_fwd_kernel<MV, float, float, __half><<<grid, wpb * 32, 0, st>>>(                                      \
+      ln_fwd_kernel<LPR, MV, float, float, __half><<<grid, wpb * 32, 0, st>>>(                                      \
           (const float*)x, ldx, (const float*)gamma, (const float*)beta, (__half*)y, ldy, stats, M, C, eps);   \
     else if (x_f32 && w_f32 && y_f32)                                                                          \
-      ln_fwd_kernel<MV, float, float, float><<<grid, wpb * 32, 0, st>>>(                                       \
+      ln_fwd_kernel<LPR, MV, float, float, float><<<grid, wpb * 32, 0, st>>>(                                       \
           (const float*)x, ldx, (const float*)gamma, (const float*)beta, (float*)y, ldy, stats, M, C, eps);    \
     else {                                                                                                     \
       set_error("tb_layernorm_fwd: unsupported type set x_f32=%d w_f32=%d y_f32=%d", x_f32, w_f32, y_f32);     \
       return TB_E_ARG;                                                                                         \
     }                                                                                                          \
   } while (0)
-  if (mv == 2) TB_LN_FWD(2);
-  else if (mv == 3) TB_LN_FWD(3);
-  else TB_LN_FWD(LN_MAXV);
+  if (lpr == 8) TB_LN_FWD(8, 5);
+  else if (lpr == 16) TB_LN_FWD(16, 5);
+  else if (mv == 2) TB_LN_FWD(32, 2);
+  else if (mv == 3) TB_LN_FWD(32, 3);
+  else TB_LN_FWD(32, LN_MAXV);
 #undef TB_LN_FWD
   return check_launch("ln_fwd_kernel");
 }
@@ -510,27 +528,31 @@ extern "C" int tb_layernorm_bwd(const void* dy, int dy_f32, int64_t lddy, const 
   TB_REQUIRE(x_f32 || !dy_f32, TB_E_ARG, "tb_layernorm_bwd: fp32 dy requires the fp32 (CLIP) type set");
   cudaStream_t st = (cudaStream_t)stream;
   const int wpb = 8;
-  const unsigned grid = (unsigned)((M + wpb - 1) / wpb);
+  const int lpr = C == 320 ? 8 : C == 640 ? 16 : 32;
+  const int rpb = wpb * (32 / lpr);  // rows per block
+  const unsigned grid = (unsigned)((M + rpb - 1) / rpb);
   // UNet: everything fp16.  CLIP: x / gamma / add / dx fp32, dy fp16 (from a GEMM) or fp32 (final LN).
   const int mv = C <= 512 ? 2 : C <= 768 ? 3 : LN_MAXV;
-#define TB_LN_BWD(MV)                                                                                          \
+#define TB_LN_BWD(LPR, MV)                                                                                          \
   do {                                                                                                         \
     if (!x_f32)                                                                                                \
-      ln_bwd_kernel<MV, __half, __half, __half, __half><<<grid, wpb * 32, 0, st>>>(                            \
+      ln_bwd_kernel<LPR, MV, __half, __half, __half, __half><<<grid, wpb * 32, 0, st>>>(                            \
           (const __half*)dy, lddy, (const __half*)x, ldx, (const __half*)gamma, stats, (const __half*)add,     \
           (__half*)dx, M, C);                                                                                  \
     else if (!dy_f32)                                                                                          \
-      ln_bwd_kernel<MV, __half, float, float, float><<<grid, wpb * 32, 0, st>>>(                               \
+      ln_bwd_kernel<LPR, MV, __half, float, float, float><<<grid, wpb * 32, 0, st>>>(                               \
           (const __half*)dy, lddy, (const float*)x, ldx, (const float*)gamma, stats, (const float*)add,        \
           (float*)dx, M, C);                                                                                   \
     else                                                                                                       \
-      ln_bwd_kernel<MV, float, float, float, float><<<grid, wpb * 32, 0, st>>>(                                \
+      ln_bwd_kernel<LPR, MV, float, float, float, float><<<grid, wpb * 32, 0, st>>>(                                \
           (const float*)dy, lddy, (const float*)x, ldx, (const float*)gamma, stats, (const float*)add,         \
           (float*)dx, M, C);                                                                                   \
   } while (0)
-  if (mv == 2) TB_LN_BWD(2);
-  else if (mv == 3) TB_LN_BWD(3);
-  else TB_LN_BWD(LN_MAXV);
+  if (lpr == 8) TB_LN_BWD(8, 5);
+  else if (lpr == 16) TB_LN_BWD(16, 5);
+  else if (mv == 2) TB_LN_BWD(32, 2);
+  else if (mv == 3) TB_LN_BWD(32, 3);
+  else TB_LN_BWD(32, LN_MAXV);
 #undef TB_LN_BWD
   return check_launch("ln_bwd_kernel");
 }
