@@ -67,11 +67,11 @@ def test_gemm_epilogues_and_strides():
         assert relerr(out, f(a.float() @ w.float().t() + bias.float())) < TOL_GEMM
 
 
-@pytest.mark.parametrize("M,N,K", [(616, 768, 3072), (512, 1280, 2560), (77, 2560, 768), (8, 1280, 1280),
-                                   (1232, 784, 2304), (300, 160, 4096)])
+@pytest.mark.parametrize("M,N,K", [(616, 768, 3072), (512, 1280, 10240), (77, 2560, 8192), (8, 1280, 8256),
+                                   (1232, 784, 2304), (300, 160, 16384)])
 def test_gemm_split_k(M, N, K):
-    """Under-filled problems (few tiles, long K) take the split-K path (per-stream workspace registered by the
-    binding): same result as the unsplit kernel up to fp32 summation order, identical between replays (the
+    """Under-filled problems with a very long K loop (>= 128 k-blocks; shorter ones are left alone because the
+    fix-up costs more than it saves) take the split-K path (per-stream workspace registered by the binding): same result as the unsplit kernel up to fp32 summation order, identical between replays (the
     partials are added in split order), every fused epilogue still applied by the fixing CTA."""
     import os
     from textboost_b200 import _cabi as C, ops
@@ -99,7 +99,7 @@ def test_gemm_split_k(M, N, K):
         C._workspaces[(s.device.index, s.cuda_stream)] = None
         plain = ops.gemm(a, w, bias=bias, residual=res, act=C.TB_ACT_GELU, out_kind=C.TB_OUT_F32)
     s.synchronize()
-    assert relerr(plain, out) < 1e-5
+    assert relerr(plain, out) < 1e-4
 
 
 def test_gemm_rejects_bad_arguments():

@@ -514,7 +514,10 @@ static void plan_split(GemmParams& p, int bn, int tiles, cudaStream_t st) {
   p.counters = nullptr;
   static const bool off = getenv("TB_GEMM_NO_SPLITK") != nullptr;  // diagnostic switch
   const Workspace* w = find_ws((void*)st);
-  if (off || !w || tiles * 2 > num_sms() || p.num_kb < 8) return;
+  // Measured (scripts/probe_small_gemm.py): the fix-up (partials to L2, __threadfence, counter round trip, the
+  // last CTA re-reading splits x 64 KB) costs ~8-15 us, so splitting only pays for very long K loops -- the 3x3
+  // convolutions of the 8x8 / 16x16 levels (180-360 k-blocks: 80 -> 32 us).  GEMMs with K <= 5120 lose.
+  if (off || !w || tiles * 2 > num_sms() || p.num_kb < 128) return;
   int s = num_sms() / tiles;
   if (s > p.num_kb / 4) s = p.num_kb / 4;
   if (s > 16) s = 16;
@@ -585,9 +588,7 @@ static int dispatch_gemm(const CUtensorMap& tmA, const void* Bw, long long ldb, 
                          int m_tiles, cudaStream_t st) {
   int bn = pick_bn(p.N);
   // under-filled problems are split along K; 128-wide tiles keep the fix-up (splits x 128 x BN fp32) small
-  if (bn == 256 && p.N % 128 == 0 && m_tiles * ((p.N + 255) / 256) * 2 <= num_sms() && p.num_kb >= 8 &&
-      find_ws((void*)st))
-    bn = 128;
+  if (bn == 256 && p.N % 128 == 0 && m_tiles * ((p.N + 255) / 256) * 2 <= num_sms()) bn = 128;
   CUtensorMap tmB;
   {
     uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
