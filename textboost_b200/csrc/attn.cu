@@ -87,6 +87,39 @@ __device__ __forceinline__ uint32_t exp2_pack(float lo, float hi) {
   return e;
 #endif
 }
+// 2^x on the FMA pipe (no MUFU): x = r + f with r = rint(x) taken from the mantissa of x + 1.5*2^23 and f in
+// [-0.5, 0.5]; 2^f by a degree-4 minimax polynomial (max relative error 2.7e-6, far below the fp16 rounding of
+// P), 2^r added into the exponent field.  The softmax phases are MUFU-bound (16 ex2/clk/SM: 1024 cycles per
+// 128x128 tile, measured ~1830 for the P phase), while the FMA pipe issues 128/clk: moving a share of the
+// exponentials here shortens the phase (the same split FlashAttention-4 uses).  Inputs are <= ~0 here; anything
+// below -126 (masked / padded entries arrive as -inf) returns ~2^-126, which rounds to 0 in fp16.
+#ifndef TB_ATTN_POLY_PACKS
+#define TB_ATTN_POLY_PACKS 1  // of every 4 packed pairs (8 exponentials), how many go to the FMA pipe
+#endif
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  const float xf = x + 12582912.f;
+  const float r = xf - 12582912.f;
+  const float f = x - r;
+  float q = 0.009570101276040077f;
+  q = fmaf(q, f, 0.05591785907745361f);
+  q = fmaf(q, f, 0.240247443318367f);
+  q = fmaf(q, f, 0.6931217908859253f);
+  q = fmaf(q, f, 0.9999992847442627f);
+  return __int_as_float(__float_as_int(q) + (__float_as_int(xf) << 23));
+}
+__device__ __forceinline__ uint32_t exp2_pack_poly(float lo, float hi) {
+  uint32_t e;
+  const float a = exp2_poly(lo), b = exp2_poly(hi);
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(e) : "f"(b), "f"(a));
+  return e;
+}
+// pack k (0..3) of a group of four: the last TB_ATTN_POLY_PACKS packs use the polynomial
+template <int K>
+__device__ __forceinline__ uint32_t exp2_pack_mix(float lo, float hi) {
+  if (K >= 4 - TB_ATTN_POLY_PACKS) return exp2_pack_poly(lo, hi);
+  return exp2_pack(lo, hi);
+}
 __device__ __forceinline__ uint32_t hmul2_u32(uint32_t a, uint32_t b) {
   uint32_t r;
   asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
@@ -781,6 +814,375 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 0) tmem_dealloc_rt(tmem, (uint32_t)p.tmem_cols);
 }
 
+
+// ------------------------------------------------------------------------------------ backward, v2
+// head_dim <= 64, non-causal (every UNet attention).  ONE CTA per SM with 512 TMEM columns and 576 threads:
+// warps 0..15 = softmax / dS / drain (four threads per KV row, 32 query columns each), warp 16 = TMA, warp 17 =
+// MMA.  attn_bwd_kernel runs its five MMAs and three softmax phases of a (kv, q) pair strictly one after the
+// other through a single TMEM buffer and relies on a second resident CTA for overlap (measured: 5.7k cycles per
+// pair per SM against ~1k of MUFU and ~1k of tensor work).  Here nothing the softmax warps need is ever produced
+// on demand:
+//   S^T(i+1) is issued as soon as the P phase has READ S^T(i)          (own buffer, [0,128))
+//   dP^T(i+1) is issued as soon as the dS phase has READ dP^T(i)       (own buffer, [128,256))
+//   dQ(i) has its own accumulator [256,320) and is drained after the P phase of pair i+1
+//   P^T and dS^T live in separate shared-memory tiles, so dV(i) and dK/dQ(i) never block the next phase
+// so the warps run P(i+1) -> drain dQ(i) -> dS(i+1) back to back.  dV at [320,384), dK at [384,448).
+template <int STAGES>
+__global__ void __launch_bounds__(576, 1)
+attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                 const __grid_constant__ CUtensorMap tmDQ, const AttnParams p) {
+  constexpr int TILE = ABOX;
+  constexpr uint32_t S_COL = 0, DP_COL = 128, DQ_COL = 256, DV_COL = 320, DK_COL = 384;
+  constexpr int NSM = 512;  // softmax threads
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + TILE;
+  uint8_t* sQ = sV + TILE;
+  uint8_t* sdO = sQ + STAGES * TILE;
+  uint8_t* sPT = sdO + STAGES * TILE;  // P^T  [128 kv x 128 q] fp16, two swizzled boxes
+  uint8_t* sDS = sPT + 2 * ABOX;       // dS^T, same layout
+  float* sDQ = reinterpret_cast<float*>(sDS + 2 * ABOX);  // [128 q][d] fp32 staging tile of the dQ TMA reduce-add
+  float* sL = sDQ + 128 * 64;                             // [2][128] L_i   (double-buffered by pair parity)
+  float* sD = sL + 256;                                  // [2][128] delta_i
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 256);
+  uint64_t* bar_kv = bars;
+  uint64_t* bar_s = bars + 1;
+  uint64_t* bar_sfree = bars + 2;
+  uint64_t* bar_pt = bars + 3;
+  uint64_t* bar_dv = bars + 4;
+  uint64_t* bar_dp = bars + 5;
+  uint64_t* bar_dpfree = bars + 6;
+  uint64_t* bar_ds = bars + 7;
+  uint64_t* bar_dq = bars + 8;
+  uint64_t* bar_dqfree = bars + 9;
+  uint64_t* q_full = bars + 10;
+  uint64_t* q_empty = bars + 10 + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kv0 = (blockIdx.x / p.qsplit) * 128, h = blockIdx.y, b = blockIdx.z;
+  const int qs = blockIdx.x % p.qsplit;
+  const int q_per = (p.n_inner + p.qsplit - 1) / p.qsplit;
+  const int i_begin = qs * q_per;
+  const int i_end = min(p.n_inner, i_begin + q_per);
+
+  if (threadIdx.x == NSM) {
+    mbar_init(smem_u32(bar_kv), 1);
+    mbar_init(smem_u32(bar_s), 1);
+    mbar_init(smem_u32(bar_sfree), NSM);
+    mbar_init(smem_u32(bar_pt), NSM);
+    mbar_init(smem_u32(bar_dv), 1);
+    mbar_init(smem_u32(bar_dp), 1);
+    mbar_init(smem_u32(bar_dpfree), NSM);
+    mbar_init(smem_u32(bar_ds), NSM);
+    mbar_init(smem_u32(bar_dq), 1);
+    mbar_init(smem_u32(bar_dqfree), NSM);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&q_full[s]), 1);
+      mbar_init(smem_u32(&q_empty[s]), 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc_rt(smem_u32(tmem_slot), 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (i_begin >= i_end) {
+    // (an empty q split: nothing to add to dK / dV / dQ)
+  } else if (warp == 16) {
+    // ---------------------------------------------------------------- TMA producer (warp-uniform)
+    if (elect_one()) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmK);
+      tma_prefetch_desc(&tmV);
+      tma_prefetch_desc(&tmdO);
+      mbar_expect_tx(smem_u32(bar_kv), 2 * TILE);
+      tma_load_4d(smem_u32(sK), &tmK, smem_u32(bar_kv), 0, h, kv0, b);
+      tma_load_4d(smem_u32(sV), &tmV, smem_u32(bar_kv), 0, h, kv0, b);
+    }
+    __syncwarp();
+    for (int i = i_begin; i < i_end; ++i) {
+      const int it = i - i_begin;
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(smem_u32(&q_empty[s]), ph ^ 1);
+      if (elect_one()) {
+        const uint32_t fb = smem_u32(&q_full[s]);
+        mbar_expect_tx(fb, 2 * TILE);
+        tma_load_4d(smem_u32(sQ + s * TILE), &tmQ, fb, 0, h, i * 128, b);
+        tma_load_4d(smem_u32(sdO + s * TILE), &tmdO, fb, 0, h, i * 128, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 17) {
+    // ---------------------------------------------------------------- MMA issuer (warp-uniform)
+    const uint32_t idesc_kk = umma_idesc_f16(128, 128, 0, 0);    // S^T, dP^T : both operands K-major
+    const uint32_t idesc_acc = umma_idesc_f16(128, p.dn, 0, 1);  // dV, dK    : B MN-major
+    const uint32_t idesc_dq = umma_idesc_f16(128, p.dn, 1, 1);   // dQ = dS K : A (dS^T tile) and B MN-major
+    const int nks = p.dn / 16;
+    const uint32_t hi = umma_desc_hi_sw128(1024);
+    const uint32_t k_lo = umma_desc_lo(smem_u32(sK), 16), v_lo = umma_desc_lo(smem_u32(sV), 16);
+    const uint32_t k_mn = umma_desc_lo(smem_u32(sK), ABOX);
+    const uint32_t pt_lo = umma_desc_lo(smem_u32(sPT), 16), ds_lo = umma_desc_lo(smem_u32(sDS), 16);
+    const uint32_t ds_mn = umma_desc_lo(smem_u32(sDS), ABOX);
+    auto issue_s = [&](int s) {  // S^T = K Q^T
+      const uint32_t q_lo = umma_desc_lo(smem_u32(sQ + s * TILE), 16);
+      for (int ks = 0; ks < nks; ++ks) {
+        const uint32_t off = ((ks & 3) * 32) >> 4;
+        umma_f16_ss(tmem + S_COL, umma_desc_pack(k_lo + off, hi), umma_desc_pack(q_lo + off, hi), idesc_kk, ks > 0);
+      }
+      umma_commit(smem_u32(bar_s));
+    };
+    auto issue_dp = [&](int s) {  // dP^T = V dO^T
+      const uint32_t do_lo = umma_desc_lo(smem_u32(sdO + s * TILE), 16);
+      for (int ks = 0; ks < nks; ++ks) {
+        const uint32_t off = ((ks & 3) * 32) >> 4;
+        umma_f16_ss(tmem + DP_COL, umma_desc_pack(v_lo + off, hi), umma_desc_pack(do_lo + off, hi), idesc_kk, ks > 0);
+      }
+      umma_commit(smem_u32(bar_dp));
+    };
+    mbar_wait(smem_u32(bar_kv), 0);
+    mbar_wait(smem_u32(&q_full[0]), 0);
+    tc_fence_after();
+    if (elect_one()) {
+      issue_s(0);
+      issue_dp(0);
+    }
+    __syncwarp();
+    for (int i = i_begin; i < i_end; ++i) {
+      const int it = i - i_begin;
+      const int s = it % STAGES;
+      const uint32_t par = it & 1;
+      const bool more = i + 1 < i_end;
+      const int s1 = (it + 1) % STAGES;
+      const uint32_t q_mn = umma_desc_lo(smem_u32(sQ + s * TILE), ABOX);
+      const uint32_t do_mn = umma_desc_lo(smem_u32(sdO + s * TILE), ABOX);
+      if (more) {  // (a) S^T of the next pair, as soon as this pair's scores have been read
+        mbar_wait(smem_u32(&q_full[s1]), ((it + 1) / STAGES) & 1);
+        mbar_wait(smem_u32(bar_sfree), par);
+        tc_fence_after();
+        if (elect_one()) issue_s(s1);
+        __syncwarp();
+      }
+      // (b) dV += P^T dO
+      mbar_wait(smem_u32(bar_pt), par);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t offp = ((ks >> 2) * ABOX + (ks & 3) * 32) >> 4;
+          umma_f16_ss(tmem + DV_COL, umma_desc_pack(pt_lo + offp, hi), umma_desc_pack(do_mn + ks * 128, hi),
+                      idesc_acc, (it > 0) || (ks > 0));
+        }
+        umma_commit(smem_u32(bar_dv));
+      }
+      __syncwarp();
+      if (more) {  // (c) dP^T of the next pair, as soon as this pair's dP^T has been read
+        mbar_wait(smem_u32(bar_dpfree), par);
+        tc_fence_after();
+        if (elect_one()) issue_dp(s1);
+        __syncwarp();
+      }
+      // (d) dK += dS^T Q ; dQ = dS K (own accumulator: the previous pair's dQ must have been drained)
+      mbar_wait(smem_u32(bar_ds), par);
+      if (it > 0) mbar_wait(smem_u32(bar_dqfree), par ^ 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t offp = ((ks >> 2) * ABOX + (ks & 3) * 32) >> 4;
+          umma_f16_ss(tmem + DK_COL, umma_desc_pack(ds_lo + offp, hi), umma_desc_pack(q_mn + ks * 128, hi),
+                      idesc_acc, (it > 0) || (ks > 0));
+        }
+        if (p.dQacc) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_f16_ss(tmem + DQ_COL, umma_desc_pack(ds_mn + ks * 128, hi), umma_desc_pack(k_mn + ks * 128, hi),
+                        idesc_dq, ks > 0);
+        }
+        umma_commit(smem_u32(bar_dq));
+        umma_commit(smem_u32(&q_empty[s]));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax / dS / drain warps
+    const int quarter = warp & 3, cg = warp >> 2;  // TMEM lane quarter; 32-column group of the q tile
+    const int row = quarter * 32 + lane;           // kv row inside the tile (q row for the dQ drain)
+    const int cb = cg * 32;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    const bool kv_ok = kv0 + row < p.Nk;
+    const long long bh = (long long)b * p.heads + h;
+    auto load_ld = [&](int q) -> float {
+      if (cg == 0) return q < p.Nq ? p.lse[bh * p.Nq + q] : INFINITY;  // +inf: exp2(. - L) == 0 for padding queries
+      if (cg == 1) return q < p.Nq ? p.delta[bh * p.Nq + q] : 0.f;
+      return 0.f;
+    };
+    // dQ(i) leaves through shared memory and ONE TMA reduce-add per pair (whole 128-byte lines added at the L2)
+    // instead of 12 red.global.add.v4.f32 per thread: the reds alone were ~1600 cycles of each ~5000-cycle pair.
+    auto drain_dq = [&](int i_prev, uint32_t par_prev) {
+      mbar_wait(smem_u32(bar_dq), par_prev);  // dK / dQ of that pair retired (also: dS^T may be overwritten)
+      tc_fence_after();
+      if (p.dQacc && cg * 16 < p.dn) {
+        const int c = cg * 16;
+        uint32_t r[16];
+        tmem_ld16(lane_addr + DQ_COL + c, r);
+        tmem_ld_wait();
+        float* dst = sDQ + row * p.d + c;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          if (c + g * 4 < p.d)
+            *reinterpret_cast<float4*>(dst + g * 4) =
+                make_float4(__uint_as_float(r[g * 4 + 0]) * p.scale, __uint_as_float(r[g * 4 + 1]) * p.scale,
+                            __uint_as_float(r[g * 4 + 2]) * p.scale, __uint_as_float(r[g * 4 + 3]) * p.scale);
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(bar_dqfree));  // the dQ accumulator is free for the next pair
+      if (p.dQacc) {
+        fence_async_smem();
+        named_bar_sync(2, NSM);
+        if (threadIdx.x == 0) {
+          tma_reduce_add_3d(&tmDQ, smem_u32(sDQ), h * p.d, i_prev * 128, b);  // rows >= Nq are clipped by the map
+          tma_store_commit();
+        }
+      }
+    };
+
+    float ld_next = load_ld(i_begin * 128 + row);
+    for (int i = i_begin; i < i_end; ++i) {
+      const int it = i - i_begin;
+      const uint32_t par = it & 1;
+      float* sLb = sL + par * 128;
+      float* sDb = sD + par * 128;
+      if (cg == 0) sLb[row] = ld_next;
+      else if (cg == 1) sDb[row] = ld_next;
+      if (i + 1 < i_end) ld_next = load_ld((i + 1) * 128 + row);
+      if (threadIdx.x == 0) tma_store_wait_read<0>();  // the previous reduce-add has read the staging tile
+      named_bar_sync(1, NSM);
+
+      // ---- P phase: P^T = exp2(S^T * c - L)
+      mbar_wait(smem_u32(bar_s), par);
+      tc_fence_after();
+      uint32_t pt[16];  // this thread's 32 entries of P^T as packed fp16, kept for the dS product
+      {
+        uint32_t r[32];
+        tmem_ld32(lane_addr + S_COL + cb, r);
+        tmem_ld_wait32(r);
+        tc_fence_before();
+        mbar_arrive(smem_u32(bar_sfree));  // S^T(i) is in registers: the next pair's scores may overwrite it
+        if (it > 0) mbar_wait(smem_u32(bar_dv), par ^ 1);  // dV(i-1) has finished reading the P^T tile
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float4 l0 = *reinterpret_cast<const float4*>(sLb + cb + g * 8);
+          const float4 l1 = *reinterpret_cast<const float4*>(sLb + cb + g * 8 + 4);
+          uint32_t* o = pt + g * 4;
+          o[0] = exp2_pack_mix<0>(fmaf(__uint_as_float(r[g * 8 + 0]), p.scale_log2, -l0.x),
+                                  fmaf(__uint_as_float(r[g * 8 + 1]), p.scale_log2, -l0.y));
+          o[1] = exp2_pack_mix<1>(fmaf(__uint_as_float(r[g * 8 + 2]), p.scale_log2, -l0.z),
+                                  fmaf(__uint_as_float(r[g * 8 + 3]), p.scale_log2, -l0.w));
+          o[2] = exp2_pack_mix<2>(fmaf(__uint_as_float(r[g * 8 + 4]), p.scale_log2, -l1.x),
+                                  fmaf(__uint_as_float(r[g * 8 + 5]), p.scale_log2, -l1.y));
+          o[3] = exp2_pack_mix<3>(fmaf(__uint_as_float(r[g * 8 + 6]), p.scale_log2, -l1.z),
+                                  fmaf(__uint_as_float(r[g * 8 + 7]), p.scale_log2, -l1.w));
+          if (!kv_ok) o[0] = o[1] = o[2] = o[3] = 0u;
+          *reinterpret_cast<uint4*>(sPT + sw128_off(row, cg * 4 + g)) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(smem_u32(bar_pt));
+
+      // ---- drain dQ of the previous pair (its MMA finished long ago)
+      if (it > 0) drain_dq(i - 1, par ^ 1);
+
+      // ---- dS phase: dS^T = P^T o (dP^T - delta)
+      mbar_wait(smem_u32(bar_dp), par);
+      tc_fence_after();
+      {
+        uint32_t r[32];
+        tmem_ld32(lane_addr + DP_COL + cb, r);
+        tmem_ld_wait32(r);
+        tc_fence_before();
+        mbar_arrive(smem_u32(bar_dpfree));  // dP^T(i) is in registers
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float4 d0 = *reinterpret_cast<const float4*>(sDb + cb + g * 8);
+          const float4 d1 = *reinterpret_cast<const float4*>(sDb + cb + g * 8 + 4);
+          const uint32_t* pp = pt + g * 4;
+          uint4 o;
+          o.x = hmul2_u32(pp[0], pack_half2(__uint_as_float(r[g * 8 + 0]) - d0.x, __uint_as_float(r[g * 8 + 1]) - d0.y));
+          o.y = hmul2_u32(pp[1], pack_half2(__uint_as_float(r[g * 8 + 2]) - d0.z, __uint_as_float(r[g * 8 + 3]) - d0.w));
+          o.z = hmul2_u32(pp[2], pack_half2(__uint_as_float(r[g * 8 + 4]) - d1.x, __uint_as_float(r[g * 8 + 5]) - d1.y));
+          o.w = hmul2_u32(pp[3], pack_half2(__uint_as_float(r[g * 8 + 6]) - d1.z, __uint_as_float(r[g * 8 + 7]) - d1.w));
+          *reinterpret_cast<uint4*>(sDS + sw128_off(row, cg * 4 + g)) = o;
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(smem_u32(bar_ds));
+    }
+    // the last pair's dQ; its bar_dq also covers every MMA the CTA has issued (dV, dK accumulators are final)
+    if (threadIdx.x == 0) tma_store_wait_read<0>();
+    named_bar_sync(1, NSM);
+    drain_dq(i_end - 1, (uint32_t)((i_end - 1 - i_begin) & 1));
+    if (threadIdx.x == 0) tma_store_wait_all<0>();  // every reduce-add has been performed before the CTA retires
+
+    // ------------------------------------------------------------ dV / dK epilogue (16 columns per warp group)
+    const int c = cg * 16;
+    if (c < p.dn) {
+      uint32_t rv[16], rk[16];
+      tmem_ld16(lane_addr + DV_COL + c, rv);
+      tmem_ld16(lane_addr + DK_COL + c, rk);
+      tmem_ld_wait();
+      if (kv_ok && p.qsplit > 1) {
+        const long long Cc = (long long)p.heads * p.d;
+        float* wv = p.dkv_ws + ((long long)b * p.Nk + kv0 + row) * Cc + h * p.d;
+        float* wk = wv + (long long)gridDim.z * p.Nk * Cc;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (c + g * 4 < p.d) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wv + c + g * 4),
+                         "f"(__uint_as_float(rv[g * 4 + 0])), "f"(__uint_as_float(rv[g * 4 + 1])),
+                         "f"(__uint_as_float(rv[g * 4 + 2])), "f"(__uint_as_float(rv[g * 4 + 3]))
+                         : "memory");
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wk + c + g * 4),
+                         "f"(__uint_as_float(rk[g * 4 + 0]) * p.scale), "f"(__uint_as_float(rk[g * 4 + 1]) * p.scale),
+                         "f"(__uint_as_float(rk[g * 4 + 2]) * p.scale), "f"(__uint_as_float(rk[g * 4 + 3]) * p.scale)
+                         : "memory");
+          }
+        }
+      } else if (kv_ok) {
+        __half* dv = p.dV + ((long long)b * p.Nk + kv0 + row) * p.lddv + h * p.d;
+        __half* dk = p.dK + ((long long)b * p.Nk + kv0 + row) * p.lddk + h * p.d;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (c + g * 8 < p.d) {
+            uint4 o;
+            o.x = pack_half2(__uint_as_float(rv[g * 8 + 0]), __uint_as_float(rv[g * 8 + 1]));
+            o.y = pack_half2(__uint_as_float(rv[g * 8 + 2]), __uint_as_float(rv[g * 8 + 3]));
+            o.z = pack_half2(__uint_as_float(rv[g * 8 + 4]), __uint_as_float(rv[g * 8 + 5]));
+            o.w = pack_half2(__uint_as_float(rv[g * 8 + 6]), __uint_as_float(rv[g * 8 + 7]));
+            *reinterpret_cast<uint4*>(dv + c + g * 8) = o;
+            o.x = pack_half2(__uint_as_float(rk[g * 8 + 0]) * p.scale, __uint_as_float(rk[g * 8 + 1]) * p.scale);
+            o.y = pack_half2(__uint_as_float(rk[g * 8 + 2]) * p.scale, __uint_as_float(rk[g * 8 + 3]) * p.scale);
+            o.z = pack_half2(__uint_as_float(rk[g * 8 + 4]) * p.scale, __uint_as_float(rk[g * 8 + 5]) * p.scale);
+            o.w = pack_half2(__uint_as_float(rk[g * 8 + 6]) * p.scale, __uint_as_float(rk[g * 8 + 7]) * p.scale);
+            *reinterpret_cast<uint4*>(dk + c + g * 8) = o;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc_rt(tmem, 512u);
+}
+
 }  // namespace tb
 
 // ------------------------------------------------------------------------------------ host side
@@ -830,6 +1232,32 @@ static int launch_attn_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const C
   dim3 grid((p.Nq + 127) / 128, p.heads, B);
   attn_fwd_kernel<NB, STAGES><<<grid, 320, smem, st>>>(tq, tk, tv, p);
   return check_launch("attn_fwd_kernel");
+}
+
+static int launch_attn_bwd2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                            const CUtensorMap& tdo, const AttnParams& p, int B, cudaStream_t st) {
+  constexpr int STAGES = 2;
+  constexpr int smem = ABOX * (2 + 2 * STAGES) + 4 * ABOX + 128 * 64 * 4 + 2048 + 256 + 1024;
+  CUtensorMap tdq = tq;  // (unused without dQ)
+  if (p.dQacc) {
+    uint64_t dims[3] = {(uint64_t)p.lddq, (uint64_t)p.Nq, (uint64_t)B};
+    uint64_t strides[2] = {(uint64_t)p.lddq * 4, (uint64_t)p.Nq * p.lddq * 4};
+    uint32_t box[3] = {(uint32_t)p.d, 128u, 1u};
+    int rc = make_tmap_f32_plain(&tdq, p.dQacc, 3, dims, strides, box);
+    if (rc) return rc;
+  }
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd2_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(attn_bwd2, %d): %s", smem, cudaGetErrorString(e));
+      return TB_E_CUDA;
+    }
+    configured = true;
+  }
+  dim3 grid(((p.Nk + 127) / 128) * p.qsplit, p.heads, B);
+  attn_bwd2_kernel<STAGES><<<grid, 576, smem, st>>>(tq, tk, tv, tdo, tdq, p);
+  return check_launch("attn_bwd2_kernel");
 }
 
 template <int NB, int STAGES>
@@ -924,6 +1352,7 @@ extern "C" int tb_attn_bwd_f16(const void* q, int64_t ldq, const void* k, int64_
   p.dK = (__half*)dK; p.lddk = lddk;
   p.dV = (__half*)dV; p.lddv = lddv;
   p.n_inner = (Nq + 127) / 128;
+  p.trace = g_attn_trace;
   {
     static const char* ex = getenv("TB_ATTN_EXPERIMENT");
     p.experiment = ex ? atoi(ex) : 0;
@@ -935,13 +1364,18 @@ extern "C" int tb_attn_bwd_f16(const void* q, int64_t ldq, const void* k, int64_
   {
     static const bool off = getenv("TB_ATTN_NO_QSPLIT") != nullptr;  // diagnostic switch
     const int ctas = ((Nk + 127) / 128) * heads * B;
-    const int per_sm = nb == 1 ? 2 : 1;  // resident CTAs per SM
+    static const bool v1q = getenv("TB_ATTN_BWD_V1") != nullptr;
+    const int per_sm = (nb == 1 && (causal || v1q)) ? 2 : 1;  // resident CTAs per SM
     const Workspace* w = find_ws(stream);
     const size_t need = 2ull * B * Nk * heads * d * sizeof(float);
     if (!off && !causal && w && ctas * 2 <= num_sms() * per_sm && p.n_inner >= 4 && (heads * d) % 4 == 0 &&
         WS_COUNTER_BYTES + need <= w->bytes && lddk % 4 == 0 && lddv % 4 == 0) {
       int qsp = (num_sms() * per_sm) / ctas;
       if (qsp > p.n_inner / 2) qsp = p.n_inner / 2;
+      if (qsp >= 2) {
+        const int q_per = (p.n_inner + qsp - 1) / qsp;
+        qsp = (p.n_inner + q_per - 1) / q_per;  // no empty split (its CTA would add an unwritten accumulator)
+      }
       if (qsp >= 2) {
         p.qsplit = qsp;
         p.dkv_ws = reinterpret_cast<float*>(w->base + WS_COUNTER_BYTES);
@@ -950,7 +1384,9 @@ extern "C" int tb_attn_bwd_f16(const void* q, int64_t ldq, const void* k, int64_
       }
     }
   }
-  if (nb == 1) rc = launch_attn_bwd<1, 1>(tq, tk, tv, tdo, p, B, st);
+  static const bool v1 = getenv("TB_ATTN_BWD_V1") != nullptr;  // diagnostic switch: the two-CTA-per-SM kernel
+  if (nb == 1 && !causal && !v1) rc = launch_attn_bwd2(tq, tk, tv, tdo, p, B, st);
+  else if (nb == 1) rc = launch_attn_bwd<1, 1>(tq, tk, tv, tdo, p, B, st);
   else if (nb == 2) rc = launch_attn_bwd<2, 1>(tq, tk, tv, tdo, p, B, st);
   else rc = launch_attn_bwd<3, 1>(tq, tk, tv, tdo, p, B, st);
   if (rc || p.qsplit == 1) return rc;

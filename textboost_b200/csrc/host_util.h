@@ -19,6 +19,11 @@ int check_launch(const char* what);
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                   const uint64_t* strides_bytes, const uint32_t* box);
 
+// Tiled fp32 tensor map without swizzle (row-major box in shared memory): target of the TMA reduce-add that
+// accumulates dQ in the attention backward.
+int make_tmap_f32_plain(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                        const uint64_t* strides_bytes, const uint32_t* box);
+
 // Per-stream scratch registered by the caller (tb_set_workspace): split-K partial tiles (gemm.cu) and the fp32
 // dK/dV accumulators of the q-split attention backward (attn.cu).  The first WS_COUNTER_BYTES hold the split-K
 // tile counters and stay zero between launches; everything after is free-for-all scratch, valid only between the

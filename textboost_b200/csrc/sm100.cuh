@@ -108,6 +108,17 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src,
                "r"(src), "r"(c0), "r"(c1)
                : "memory");
 }
+// smem -> global tile REDUCTION (element-wise add at the L2, whole lines per request); same bulk-group
+// completion mechanism as the tile store
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(m),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_all() {  // the groups have fully completed (writes performed)
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
