@@ -93,8 +93,11 @@ __device__ __forceinline__ uint32_t exp2_pack(float lo, float hi) {
 // 128x128 tile, measured ~1830 for the P phase), while the FMA pipe issues 128/clk: moving a share of the
 // exponentials here shortens the phase (the same split FlashAttention-4 uses).  Inputs are <= ~0 here; anything
 // below -126 (masked / padded entries arrive as -inf) returns ~2^-126, which rounds to 0 in fp16.
+// Measured on the v2 backward (64x64 level): 25 % of the exponentials on the FMA pipe leaves the kernel time
+// unchanged (1197 vs 1205 us) -- the MUFU cycles saved are paid back in issue slots (10 instructions per
+// polynomial exponential) -- so the default keeps every exponential on MUFU; the switch stays for experiments.
 #ifndef TB_ATTN_POLY_PACKS
-#define TB_ATTN_POLY_PACKS 1  // of every 4 packed pairs (8 exponentials), how many go to the FMA pipe
+#define TB_ATTN_POLY_PACKS 0  // of every 4 packed pairs (8 exponentials), how many go to the FMA pipe
 #endif
 __device__ __forceinline__ float exp2_poly(float x) {
   x = fmaxf(x, -126.f);
