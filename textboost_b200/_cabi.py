@@ -12,7 +12,8 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int
                     c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtextboost_b200.so")
+# TB_LIB points at an alternative build of the same library (A/B timing of kernel variants); never a fallback
+LIB_PATH = os.environ.get("TB_LIB") or os.path.join(_HERE, "lib", "libtextboost_b200.so")
 
 TB_ACT_NONE, TB_ACT_SILU, TB_ACT_QUICK_GELU, TB_ACT_GELU = 0, 1, 2, 3
 TB_OUT_F16, TB_OUT_F32, TB_OUT_F32_ACC = 0, 1, 2

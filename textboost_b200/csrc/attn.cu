@@ -99,6 +99,9 @@ __device__ __forceinline__ uint32_t exp2_pack(float lo, float hi) {
 #ifndef TB_ATTN_POLY_PACKS
 #define TB_ATTN_POLY_PACKS 0  // of every 4 packed pairs (8 exponentials), how many go to the FMA pipe
 #endif
+#ifndef TB_ATTN_FWD_POLY_PACKS
+#define TB_ATTN_FWD_POLY_PACKS 0  // the same switch for the forward kernel
+#endif
 __device__ __forceinline__ float exp2_poly(float x) {
   x = fmaxf(x, -126.f);
   const float xf = x + 12582912.f;
@@ -332,9 +335,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const float neg_m = -m_run;
       uint32_t pk[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        pk[i] = exp2_pack(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, neg_m),
-                          fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, neg_m));
+      for (int i = 0; i < 32; ++i) {
+        const float e0 = fmaf(__uint_as_float(r[2 * i]), p.scale_log2, neg_m);
+        const float e1 = fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, neg_m);
+        pk[i] = (i & 3) >= 4 - TB_ATTN_FWD_POLY_PACKS ? exp2_pack_poly(e0, e1) : exp2_pack(e0, e1);
+      }
       tmem_st32(lane_addr + P_COL + half * 32, pk);
       tmem_st_wait();
       tc_fence_before();

@@ -589,6 +589,10 @@ static int dispatch_gemm(const CUtensorMap& tmA, const void* Bw, long long ldb, 
   int bn = pick_bn(p.N);
   // under-filled problems are split along K; 128-wide tiles keep the fix-up (splits x 128 x BN fp32) small
   if (bn == 256 && p.N % 128 == 0 && m_tiles * ((p.N + 255) / 256) * 2 <= num_sms()) bn = 128;
+  // still under half a wave at 128 and too short to split along K: 64-wide tiles (measured with
+  // scripts/probe_small_gemm.py: [616,768]x[768,3072] 21.0 -> 16.7 us, [512,1280]x[1280,1280] 9.5 -> 8.2 us)
+  if (bn == 128 && p.N % 64 == 0 && m_tiles * (p.N / 128) * 2 <= num_sms() && p.num_kb >= 8 && p.num_kb < 128)
+    bn = 64;
   CUtensorMap tmB;
   {
     uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
@@ -613,6 +617,8 @@ static int dispatch_gemm(const CUtensorMap& tmA, const void* Bw, long long ldb, 
     static const bool noepi = getenv("TB_GEMM_EXPERIMENT_NOEPI") != nullptr;  // timing experiment only
     if (noepi) p.tma_store = 3;
   }
+  // (Deeper TMA rings for the under-filled cases -- 6 x 32 KB at BN = 128, 8 x 24 KB at BN = 64 -- were measured
+  // and did not help: those launches are not bound by bytes in flight.)
   switch (bn) {
     case 256: return launch_gemm<256, 4, CONV>(tmA, tmB, tmC, p, m_tiles, st);
     case 160: return launch_gemm<160, 4, CONV>(tmA, tmB, tmC, p, m_tiles, st);
