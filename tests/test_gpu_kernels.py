@@ -131,6 +131,31 @@ def test_conv3x3(B, H, W, Cin, Cout):
         assert relerr(dx, xr.grad.permute(0, 2, 3, 1)) < TOL_GEMM
 
 
+@pytest.mark.parametrize("B,H,Cin,Cout", [(2, 96, 64, 64), (1, 48, 128, 160), (3, 24, 64, 128), (2, 12, 128, 64),
+                                          (1, 12, 1280, 1280), (1, 8, 64, 64), (3, 8, 64, 64), (1, 6, 64, 64)])
+def test_conv3x3_non_power_of_two_planes(B, H, Cin, Cout):
+    """768^2 images (configs[4]): 96 / 48 / 24 / 12-wide planes have no 128-pixel box; the implicit GEMM then runs
+    96- (72-) pixel tiles inside the 128-row MMA.  Also batch sizes that do not fill a tile at the small levels.
+    Bias + time-embedding row vector + fp16 residual as in ResnetBlock2D, forward and input gradient."""
+    from textboost_b200 import ops
+    from textboost_b200.unet import _conv_dgrad_weight, _conv_fwd_weight
+    g = torch.Generator(device=dev).manual_seed(B * 1000 + H * 10 + Cin)
+    x = torch.randn(B, H, H, Cin, device=dev, dtype=F16, generator=g)
+    wt = torch.randn(Cout, Cin, 3, 3, device=dev, dtype=F16, generator=g) / (9 * Cin) ** 0.5
+    bias = torch.randn(Cout, device=dev, dtype=F16, generator=g)
+    temb = torch.randn(B, Cout, device=dev, dtype=F16, generator=g)
+    res = torch.randn(B, H, H, Cout, device=dev, dtype=F16, generator=g)
+    xr = x.permute(0, 3, 1, 2).float().requires_grad_(True)
+    ref = F.conv2d(xr, wt.float(), bias.float(), padding=1) + temb.float()[:, :, None, None] + res.permute(0, 3, 1, 2).float()
+    out = ops.conv3x3(x, _conv_fwd_weight(wt), bias=bias, rowvec=temb, residual=res)
+    assert relerr(out, ref.permute(0, 2, 3, 1)) < TOL_GEMM
+    if Cout % 64 == 0:
+        dy = torch.randn(B, H, H, Cout, device=dev, dtype=F16, generator=g)
+        ref.backward(dy.permute(0, 3, 1, 2).float())
+        dx = ops.conv3x3(dy, _conv_dgrad_weight(wt))
+        assert relerr(dx, xr.grad.permute(0, 2, 3, 1)) < TOL_GEMM
+
+
 def test_conv3x3_split_k_deep_levels():
     """The 8x8 / 16x16 UNet levels (M = 512 / 2048 pixels, K = 9*1280): split along K."""
     from textboost_b200 import ops

@@ -269,6 +269,30 @@ def test_step_sd21_openclip_h_vs_oracle():
     assert r["row_grad_rel"] < 5e-3
 
 
+def test_config5_full_size_768px_step_properties():
+    """configs[4] at its real size: SD-2.x widths + OpenCLIP-H, 768^2 images (96x96 latents), batch 4.  Too big
+    for the fp32 oracle, so size-independent properties: finite loss and gradients, samples independent (rows of
+    the batch-4 UNet forward equal a batch-1 run), the captured graph reproduces the eager loss, loss decreases."""
+    from textboost_b200 import synthetic
+    tr = synthetic.build_trainer("sd21", dev, seed=7, n_added=1, lora_b_std=0.02, learning_rate=1e-3,
+                                 emb_learning_rate=1e-2, prediction_type="v_prediction")
+    bt = synthetic.batch(4, 96, 3, 49408, dev)
+    args = (bt["latents"], bt["noise"], bt["timesteps"], bt["input_ids"], bt["prior_ids"])
+    tr.forward_backward(*args)
+    g = tr.te.state.grads
+    assert torch.isfinite(tr.loss).all() and torch.isfinite(g).all() and g.abs().sum() > 0
+    pred4 = tr._pred.clone()
+    g.zero_()
+    tr.forward_backward(*(a[1:2].contiguous() for a in args))
+    assert relerr(tr._pred, pred4[1:2]) < 3e-3
+    g.zero_()
+    l_eager = tr.step(*args).item()
+    replay = tr.capture(*args, warmup=0)
+    losses = [replay(*args).item() for _ in range(6)]
+    assert abs(losses[0] - l_eager) < 0.2 * abs(l_eager) and losses[-1] < l_eager
+    assert tr.opt_state[8].item() == 0  # no skipped steps
+
+
 def test_step_graph_replay_matches_eager_and_trains():
     """The captured CUDA graph computes the same step as the eager path; the loss goes down over steps;
     the GradScaler never skips at the default scale; host-facing API returns the same loss."""

@@ -24,6 +24,10 @@ struct GemmParams {
   int m_tiles;        // ceil(M / 128)
   // conv geometry (CONV only)
   int H, W, kb_per_tap;
+  // rows of an output tile that hold pixels: 128, or 96 for the 96/48/24/12-wide levels of a 768^2 image, where
+  // no 128-pixel box tiles the plane (the MMA still runs M = 128; rows >= tile_rows are never loaded or stored)
+  int tile_rows;
+  int a_stage_bytes;  // bytes one TMA box of the A operand delivers (tile_rows x 128)
   // epilogue
   void* C;
   long long ldc;
@@ -131,7 +135,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
       const int m_tile = tile / p.n_tiles;
       int cw = 0, ch = 0, cb = 0;
       if (CONV) {
-        const int p0 = m_tile * BM;
+        const int p0 = m_tile * p.tile_rows;
         cw = p0 % p.W;
         ch = (p0 / p.W) % p.H;
         cb = p0 / (p.W * p.H);
@@ -142,7 +146,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
           const uint32_t fb = smem_u32(&full_bar[stage]);
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_STAGE_BYTES;
-          mbar_expect_tx(fb, STAGE_BYTES);
+          mbar_expect_tx(fb, p.a_stage_bytes + B_STAGE_BYTES);
           if (CONV) {
             const int tap = kb / p.kb_per_tap;
             const int c0 = (kb - tap * p.kb_per_tap) * BK;
@@ -220,15 +224,19 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
         const int n_tile = work % p.n_tiles;
         const int m_tile = work / p.n_tiles;
         const int acc = lt & 1;
-        const long long m = (long long)m_tile * BM + row;
+        const long long m = (long long)m_tile * p.tile_rows + row;
         const int ncol0 = n_tile * BN;
         const uint32_t acc_addr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
-        const __half* res = p.residual ? reinterpret_cast<const __half*>(p.residual) + m * p.ldr + ncol0 : nullptr;
+        const __half* res = (p.residual && row < p.tile_rows)
+                                ? reinterpret_cast<const __half*>(p.residual) + m * p.ldr + ncol0
+                                : nullptr;
+        const bool row_live = row < p.tile_rows;
         named_bar_sync(3, 256);  // every warp has finished reading the previous tile's sBV
         if (epi_tid < BN) {
           float bv = p.bias ? __half2float(p.bias[ncol0 + epi_tid]) : 0.f;
           if (p.rowvec)
-            bv += __half2float(p.rowvec[((long long)m_tile * BM / p.rows_per_group) * p.N + ncol0 + epi_tid]);
+            bv += __half2float(
+                p.rowvec[((long long)m_tile * p.tile_rows / p.rows_per_group) * p.N + ncol0 + epi_tid]);
           sBV[epi_tid] = bv;
         }
         uint4 rq[4], rq_next[4];
@@ -272,7 +280,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
               if (staged) {
                 const int chunk = ((c & 63) + j) >> 3;
                 *reinterpret_cast<uint4*>(box + row * 128 + ((chunk ^ (row & 7)) << 4)) = o;
-              } else {
+              } else if (row_live) {
                 *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C) + m * p.ldc + ncol0 + c + j) = o;
               }
             }
@@ -284,7 +292,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
             if (issuer) tma_store_wait_read<0>();
             named_bar_sync(1, 256);
             if (issuer) {
-              tma_store_2d(&tmC, smem_u32(box), ncol0 + 64 * i, m_tile * BM);
+              tma_store_2d(&tmC, smem_u32(box), ncol0 + 64 * i, m_tile * p.tile_rows);
               tma_store_commit();
             }
             ++n_box;
@@ -299,7 +307,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
       const int acc = lt & 1;
-      const long long m = (long long)m_tile * BM + row;
+      const long long m = (long long)m_tile * p.tile_rows + row;
       bool from_ws = false;  // split-K fix-up: the accumulator chunks come from the fp32 workspace
       if (p.splits > 1) {
         // ---- park this split's partial tile, then find out whether we are the last split of the tile
@@ -332,7 +340,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
         from_ws = true;
       }
       const uint32_t acc_addr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
-      const bool row_ok = m < p.M;
+      const bool row_ok = m < p.M && row < p.tile_rows;
       const __half* rv = nullptr;
       if (p.rowvec && row_ok) rv = p.rowvec + (m / p.rows_per_group) * (long long)p.N;
       const __half* res = nullptr;
@@ -485,7 +493,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
           if (issuer && p.tma_store != 2) tma_store_wait_read<0>();  // the previous box's store has read its buffer out
           named_bar_sync(1, 256);
           if (issuer) {
-            tma_store_2d(&tmC, smem_u32(box), ncol0 + 64 * i, m_tile * BM);
+            tma_store_2d(&tmC, smem_u32(box), ncol0 + 64 * i, m_tile * p.tile_rows);
             tma_store_commit();
           }
           ++n_box;
@@ -565,8 +573,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   plan_split(p, BN, p.n_tiles * m_tiles, st);
   static const bool no_fast = getenv("TB_GEMM_NO_FAST_EPILOGUE") != nullptr;  // diagnostic switch
   const bool fast = BN >= 64 && !no_fast && p.splits == 1 && p.tma_store == 1 && p.out_kind == TB_OUT_F16 &&
-                    p.alpha == 1.f && p.act == TB_ACT_NONE && !p.res_f32 && p.N % BN == 0 && p.M % BM == 0 &&
-                    (!p.rowvec || p.rows_per_group % BM == 0);
+                    p.alpha == 1.f && p.act == TB_ACT_NONE && !p.res_f32 && p.N % BN == 0 && p.M % p.tile_rows == 0 &&
+                    (!p.rowvec || p.rows_per_group % p.tile_rows == 0);
   if (fast) return launch_gemm_v<BN, STAGES, CONV, true>(tmA, tmB, tmC, p, m_tiles, st);
   return launch_gemm_v<BN, STAGES, CONV, false>(tmA, tmB, tmC, p, m_tiles, st);
 }
@@ -608,7 +616,7 @@ static int dispatch_gemm(const CUtensorMap& tmA, const void* Bw, long long ldb, 
   if (p.out_kind == TB_OUT_F16 && bn >= 64 && !direct_store) {
     uint64_t dims[2] = {(uint64_t)p.N, (uint64_t)p.M};
     uint64_t strides[1] = {(uint64_t)p.ldc * 2};
-    uint32_t box[2] = {64u, (uint32_t)BM};
+    uint32_t box[2] = {64u, (uint32_t)p.tile_rows};
     int rc = make_tmap_f16(&tmC, p.C, 2, dims, strides, box);
     if (rc) return rc;
     p.tma_store = 1;
@@ -684,6 +692,8 @@ extern "C" int tb_gemm_f16(const void* A, int64_t lda, const void* B, int64_t ld
   p.N = N;
   p.K = K;
   p.num_kb = (K + BK - 1) / BK;
+  p.tile_rows = BM;
+  p.a_stage_bytes = A_STAGE_BYTES;
   rc = fill_epilogue(p, C, ldc, ep);
   if (rc) return rc;
   CUtensorMap tmA;
@@ -703,16 +713,23 @@ extern "C" int tb_conv3x3_f16(const void* x, const void* w, void* y, int B, int 
   TB_REQUIRE(B > 0 && H > 0 && W > 0, TB_E_SHAPE, "tb_conv3x3_f16: bad B/H/W");
   TB_REQUIRE(Cin % 64 == 0 && Cout % 8 == 0, TB_E_SHAPE,
              "tb_conv3x3_f16: Cin %% 64 and Cout %% 8 required (Cin=%d Cout=%d)", Cin, Cout);
-  // 128-pixel tile = box_b images x box_h rows x box_w columns, contiguous in (b,h,w) order.
-  int bw = W < 128 ? W : 128;
-  TB_REQUIRE(128 % bw == 0 && W % bw == 0, TB_E_SHAPE, "tb_conv3x3_f16: W=%d does not tile 128", W);
-  int bh = 128 / bw;
-  if (bh > H) bh = H;
-  TB_REQUIRE(bw == W || bh == 1, TB_E_SHAPE, "tb_conv3x3_f16: tiling");
-  TB_REQUIRE(H % bh == 0 && 128 % (bw * bh) == 0, TB_E_SHAPE,
-             "tb_conv3x3_f16: H=%d does not tile 128 pixels", H);
-  int bb = 128 / (bw * bh);
-  TB_REQUIRE(bb == 1 || bh == H, TB_E_SHAPE, "tb_conv3x3_f16: tiling (batch)");
+  // An output tile = box_b images x box_h rows x box_w columns of pixels, contiguous in (b,h,w) order, as many as
+  // fit in the 128 rows of the MMA: 128 at the power-of-two SD sizes, 96 at the 96 / 48 / 24-wide levels of a
+  // 768^2 image, 72 at its 12x12 level.  rows always divides B*H*W.
+  int bw, bh = 1, bb = 1;
+  if (W >= 128) {
+    bw = W % 128 == 0 ? 128 : 96;
+    TB_REQUIRE(W % bw == 0, TB_E_SHAPE, "tb_conv3x3_f16: W=%d tiles neither 128 nor 96 pixels", W);
+  } else {
+    bw = W;
+    for (int c = 1; c <= H && bw * c <= 128; ++c)
+      if (H % c == 0) bh = c;
+    if (bh == H)
+      for (int c = 1; c <= B && bw * bh * c <= 128; ++c)
+        if (B % c == 0) bb = c;
+  }
+  const int rows = bw * bh * bb;
+  TB_REQUIRE(rows >= 16 && rows <= 128, TB_E_SHAPE, "tb_conv3x3_f16: %dx%d does not tile", H, W);
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = B * H * W;
@@ -722,6 +739,8 @@ extern "C" int tb_conv3x3_f16(const void* x, const void* w, void* y, int B, int 
   p.num_kb = 9 * p.kb_per_tap;
   p.H = H;
   p.W = W;
+  p.tile_rows = rows;
+  p.a_stage_bytes = rows * BK * 2;
   rc = fill_epilogue(p, y, Cout, ep);
   if (rc) return rc;
   CUtensorMap tmA;
@@ -730,6 +749,6 @@ extern "C" int tb_conv3x3_f16(const void* x, const void* w, void* y, int B, int 
   uint32_t box[4] = {(uint32_t)BK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb};
   rc = make_tmap_f16(&tmA, x, 4, dims, strides, box);
   if (rc) return rc;
-  return dispatch_gemm<true>(tmA, w, (long long)9 * Cin, p, (p.M + BM - 1) / BM,
+  return dispatch_gemm<true>(tmA, w, (long long)9 * Cin, p, (p.M + rows - 1) / rows,
                              (cudaStream_t)stream);
 }
