@@ -729,7 +729,7 @@ extern "C" int tb_conv3x3_f16(const void* x, const void* w, void* y, int B, int 
         if (B % c == 0) bb = c;
   }
   const int rows = bw * bh * bb;
-  TB_REQUIRE(rows >= 16 && rows <= 128, TB_E_SHAPE, "tb_conv3x3_f16: %dx%d does not tile", H, W);
+  TB_REQUIRE(rows >= 1 && rows <= 128, TB_E_SHAPE, "tb_conv3x3_f16: %dx%d does not tile", H, W);
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = B * H * W;

@@ -95,7 +95,12 @@ class TextBoostTrainer:
         main = torch.cuda.current_stream()
         te.pack_lora()
         self.loss.zero_()
+        noisy, target = ops.add_noise(latents, noise, timesteps, self.acp, self.v_pred)
+        h = te.forward(input_ids, save_for_backward=True)  # fp32 [B, L, D]
+        ctx_i = te.pop_ctx()
         if use_kpl:
+            # fork AFTER the instance-prompt encoder pass: that pass is on the critical path (the UNet waits for
+            # it) and should not share the SMs with the prior-prompt branch, which has the whole UNet to hide behind
             side = self._side_stream()
             self._loss_kpl.zero_()
             side.wait_stream(main)
@@ -108,9 +113,6 @@ class TextBoostTrainer:
                 C.call("tb_kpl_fwd_bwd", C.ptr(hp), C.ptr(h0), Bp * L, D, self.kpl_kind, float(self.kpl_weight),
                        C.ptr(scale), C.ptr(self._loss_kpl), C.ptr(d_hp), C.stream_ptr())
                 te.backward(d_hp, ctx=ctx_p)
-        noisy, target = ops.add_noise(latents, noise, timesteps, self.acp, self.v_pred)
-        h = te.forward(input_ids, save_for_backward=True)  # fp32 [B, L, D]
-        ctx_i = te.pop_ctx()
         _, L, D = h.shape
         ehs = ops.cast_f32_f16(h.view(B * L, D)).view(B, L, D)
         pred = unet.forward(noisy, timesteps, ehs)
