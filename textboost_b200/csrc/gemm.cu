@@ -579,13 +579,30 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   return launch_gemm_v<BN, STAGES, CONV, false>(tmA, tmB, tmC, p, m_tiles, st);
 }
 
-// Choose the N tile: 256 when N is a multiple of 256 or large, 160 for the 320/640/960/1920 family,
-// else 128 / 64 / 32 by size.
-static int pick_bn(int N) {
-  if (N % 256 == 0) return 256;
-  if (N % 160 == 0) return 160;
-  if (N % 128 == 0) return 128;
-  if (N >= 1024) return 256;
+// Choose the N tile.  Among the tile widths that divide N, minimise  waves x (128 + BN)  where waves =
+// ceil(tiles / SMs): per k-block a CTA moves 128 + BN operand rows, and a persistent grid finishes when its busiest
+// CTA does, so e.g. [2048,1280] takes 128 tiles of 160 (one wave) rather than 80 of 256, and [512,10240] takes 256
+// tiles of 160 (two short rounds) rather than 160 of 256 (two long ones).  Ties go to the wider tile.  Problems
+// that will be split along K (>= 128 k-blocks, under half a wave) stay on >= 128-wide tiles: there the split,
+// not the tile, fills the machine.
+static int pick_bn(int N, int m_tiles, int num_kb) {
+  static const int cands[4] = {256, 160, 128, 64};
+  const int sms = num_sms();
+  int best = 0;
+  long long best_cost = 0;
+  for (int i = 0; i < 4; ++i) {
+    const int c = cands[i];
+    if (N % c != 0) continue;
+    const long long tiles = (long long)m_tiles * (N / c);
+    if (num_kb >= 128 && c < 128 && m_tiles * ((N + 127) / 128) * 2 <= sms) continue;
+    const long long cost = ((tiles + sms - 1) / sms) * (128 + c);
+    if (best == 0 || cost < best_cost) {
+      best = c;
+      best_cost = cost;
+    }
+  }
+  if (best) return best;
+  if (N >= 1024) return 256;  // ragged N: the tensor map clips the last tile
   if (N > 96) return 128;
   if (N > 32) return 64;
   return 32;
@@ -594,13 +611,7 @@ static int pick_bn(int N) {
 template <bool CONV>
 static int dispatch_gemm(const CUtensorMap& tmA, const void* Bw, long long ldb, GemmParams& p,
                          int m_tiles, cudaStream_t st) {
-  int bn = pick_bn(p.N);
-  // under-filled problems are split along K; 128-wide tiles keep the fix-up (splits x 128 x BN fp32) small
-  if (bn == 256 && p.N % 128 == 0 && m_tiles * ((p.N + 255) / 256) * 2 <= num_sms()) bn = 128;
-  // still under half a wave at 128 and too short to split along K: 64-wide tiles (measured with
-  // scripts/probe_small_gemm.py: [616,768]x[768,3072] 21.0 -> 16.7 us, [512,1280]x[1280,1280] 9.5 -> 8.2 us)
-  if (bn == 128 && p.N % 64 == 0 && m_tiles * (p.N / 128) * 2 <= num_sms() && p.num_kb >= 8 && p.num_kb < 128)
-    bn = 64;
+  const int bn = pick_bn(p.N, m_tiles, p.num_kb);
   CUtensorMap tmB;
   {
     uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
