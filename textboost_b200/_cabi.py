@@ -118,9 +118,9 @@ def last_error() -> str:
     return lib().tb_last_error().decode(errors="replace")
 
 
-# kernels (and memset nodes) one call of each entry point enqueues; entry points not listed launch one
-_KERNELS_PER_CALL = {"tb_groupnorm_fwd_f16": 3, "tb_groupnorm_bwd_f16": 3, "tb_attn_bwd_f16": 2,
-                     "tb_adamw_fused_step": 3, "tb_version": 0, "tb_check_device": 0, "tb_set_workspace": 1,
+# KERNELS one call of each entry point enqueues (memset nodes are not counted); entry points not listed launch one
+_KERNELS_PER_CALL = {"tb_groupnorm_fwd_f16": 2, "tb_groupnorm_bwd_f16": 2, "tb_attn_bwd_f16": 2,
+                     "tb_adamw_fused_step": 3, "tb_version": 0, "tb_check_device": 0, "tb_set_workspace": 0,
                      "tb_attn_debug_trace": 0}
 launch_count = 0  # GPU launches enqueued through this binding since import (bench.py reports the delta)
 

@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
       }
 
 #pragma unroll 1
-      for (int i = 0; i < (p.tma_store == 3 ? 0 : MY_MAX); ++i) {
+      for (int i = 0; i < MY_MAX; ++i) {
         const int c = (2 * i + half) * 32;  // first column of this warp's chunk inside the tile
         const int cn = c + 64;              // its next chunk
         const bool have = c < BN;
@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
         // box i of the tile (columns [64i, 64i+64)) is complete once both halves have written their chunk
         if (p.tma_store && 64 * i + 64 <= BN) {
           fence_async_smem();
-          if (issuer && p.tma_store != 2) tma_store_wait_read<0>();  // the previous box's store has read its buffer out
+          if (issuer) tma_store_wait_read<0>();  // the previous box's store has read its buffer out
           named_bar_sync(1, 256);
           if (issuer) {
             tma_store_2d(&tmC, smem_u32(box), ncol0 + 64 * i, m_tile * p.tile_rows);
@@ -631,10 +631,6 @@ static int dispatch_gemm(const CUtensorMap& tmA, const void* Bw, long long ldb, 
     int rc = make_tmap_f16(&tmC, p.C, 2, dims, strides, box);
     if (rc) return rc;
     p.tma_store = 1;
-    static const bool nowait = getenv("TB_GEMM_EXPERIMENT_NOWAIT") != nullptr;  // timing experiment only (races)
-    if (nowait) p.tma_store = 2;
-    static const bool noepi = getenv("TB_GEMM_EXPERIMENT_NOEPI") != nullptr;  // timing experiment only
-    if (noepi) p.tma_store = 3;
   }
   // (Deeper TMA rings for the under-filled cases -- 6 x 32 KB at BN = 128, 8 x 24 KB at BN = 64 -- were measured
   // and did not help: those launches are not bound by bytes in flight.)

@@ -98,8 +98,6 @@ def attn_bwd(q, k, v, o, do, lse, heads, scale=None, need_dq=True, dk=None, dv=N
            C.ptr(o), o.stride(1), C.ptr(do), do.stride(1), C.ptr(lse), C.ptr(delta), C.ptr(dq),
            dq.stride(1) if dq is not None else 0, C.ptr(dk), dk.stride(1),
            C.ptr(dv), dv.stride(1), B, heads, Nq, Nk, d, scale, int(causal), C.stream_ptr())
-    if need_dq:
-        C.launch_count += 1  # the dQ accumulator memset node
     return dq, dk, dv
 
 
