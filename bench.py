@@ -55,6 +55,34 @@ def read_traffic(family):
     return d[family]["traffic_bytes_per_launch"], os.path.relpath(files[-1], ROOT)
 
 
+def read_attention_tensor_pipe():
+    """BASELINE.json's metric also names the attention tensor-pipe %: ncu's
+    sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active of the 64x64 self-attention kernels, from the
+    committed `ncu --set full` summary (a profiler metric cannot be measured inside the timed run)."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_cases_final_summary.txt")))
+    if not files:
+        return None
+    out, cur = {}, None
+    with open(files[-1]) as f:
+        for line in f:
+            m = re.match(r"== \[\d+\] (?:void )?(\w+)", line)
+            if m:
+                cur = m.group(1)
+            elif cur and "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active" in line:
+                if cur.startswith("attn_fwd") and "fwd" not in out:
+                    out["fwd"] = float(line.split()[1])
+                elif cur.startswith("attn_bwd") and "bwd" not in out:
+                    out["bwd"] = float(line.split()[1])
+    if not out:
+        return None
+    return {"tensor_pipe_pct": out, "shape": "self-attention B=8 heads=8 N=4096 d=40 (64x64 level)",
+            "source": os.path.relpath(files[-1], ROOT),
+            "note": "d=40 is padded to 48 and the kernels are bound by the softmax instruction stream / MUFU "
+                    "(16384 exp per 128x128 tile), see DESIGN.md section 4"}
+
+
 def read_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -418,6 +446,7 @@ def run_ours(args):
                 "step": {"achieved": step_tf, "frac": step_tf / peaks["tf_sustained"],
                          "tflop_per_image": TFLOP_PER_IMG[use_kpl]},
             },
+            "attention": read_attention_tensor_pipe(),
             "cpu_baseline": cpu_base,
             "loss": loss_val, "loss_scale": state[0], "skipped_steps": state[8],
         }
