@@ -151,9 +151,17 @@ def test_cli_end_to_end_synthetic_checkpoint(tmp_path):
     kb = "base_model.model.text_model.encoder.layers.0.self_attn.v_proj.lora_B.weight"
     assert ad[kb].abs().sum() > 0  # B left its zero init: the LoRA trained
     assert {"dog.bin", "state.pt", "text_encoder"} <= set(os.listdir(os.path.join(out, "checkpoint-4")))
-    # resume continues from step 8 to 10 without error and rotates nothing
-    loss2 = T.main(T.parse_args(base + ["--max_train_steps", "10", "--resume_from_checkpoint", "latest"]))
+    # resume continues from step 8 to 10 without error and rotates nothing; this time the prior prompts come from a
+    # human-written-prompts JSONL through the reference's prior pipeline (PriorPrompts + ShardedStream)
+    import json
+    jl = tmp_path / "prompts.jsonl"
+    with open(jl, "w") as f:
+        for i in range(9):
+            f.write(json.dumps({"input": f"a photo of a thing {i}", "output": f"thing {i} in the snow"}) + "\n")
+    loss2 = T.main(T.parse_args(base + ["--max_train_steps", "10", "--resume_from_checkpoint", "latest",
+                                        "--prior_prompts_file", str(jl), "--class_token", "dog"]))
     assert loss2 == loss2
+    assert T.RUN_INFO["prior_prompts"] == 18
     # modes outside the built path fail loudly rather than silently training something else
     with pytest.raises(NotImplementedError):
         T.main(T.parse_args(base + ["--lora_rank", "0"]))

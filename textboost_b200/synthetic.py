@@ -271,11 +271,18 @@ class LiteralTokenizer:
             return self._word(tokens)
         return [self._word(t) for t in tokens]
 
-    def __call__(self, text: str):
-        ids = self.encode(text)[:self.model_max_length]
-        row = torch.full((1, self.model_max_length), EOS, dtype=torch.int64)
+    def __call__(self, text: str, truncation=True, padding="max_length", max_length=None, return_tensors="pt"):
+        """The call textboost.dataset.tokenize_prompt makes: padded [1, L] ids (CLIP pads with EOS) + mask."""
+        from types import SimpleNamespace
+        L = max_length or self.model_max_length
+        ids = self.encode(text)
+        if len(ids) > L:
+            ids = ids[:L - 1] + [EOS]
+        row = torch.full((1, L), EOS, dtype=torch.int64)
         row[0, :len(ids)] = torch.tensor(ids)
-        return row
+        mask = torch.zeros((1, L), dtype=torch.int64)
+        mask[0, :len(ids)] = 1
+        return SimpleNamespace(input_ids=row, attention_mask=mask)
 
 
 def write_pretrained(directory: str, model: str = "tiny", seed: int = 0, prediction_type: str = "epsilon"):

@@ -31,6 +31,7 @@ import warnings
 import torch
 
 logger = logging.getLogger("textboost")
+RUN_INFO = {}  # facts about the last main() call (tests and notebooks read it; the log file has the same lines)
 
 # (name, kwargs) in the reference's order; help strings omitted on purpose (see the reference for prose)
 _FLAGS = [
@@ -96,6 +97,9 @@ def parse_args(input_args=None):
     parser.add_argument("--null_embedding", type=str, default=None,
                         help="[77, hidden] tensor file; default: assets/null_emb_sd21base.pt when the width "
                              "matches, else the frozen encoder's output for the empty prompt (SURVEY.md D6)")
+    parser.add_argument("--prior_prompts_file", type=str, default="data/human-written-prompts.jsonl",
+                        help="JSONL of human-written prompts for the knowledge-preservation loss (the path the "
+                             "reference hard-codes, train_textboost.py:893); used when the file exists")
     parser.add_argument("--log_every", type=int, default=10, help="host read-back period of the loss scalar")
     args = parser.parse_args(input_args)
 
@@ -311,8 +315,24 @@ def main(args):
     else:
         raise NotImplementedError("the image dataset + VAE-encode front end is not built (SURVEY.md §8 f1): pass "
                                   "--latents_file or --synthetic_data")
-    if args.kpl_weight > 0 and prior_all is None:
-        raise ValueError("kpl_weight > 0 needs prior prompts ('prior_ids' in --latents_file)")
+    prior_stream = None
+    if args.kpl_weight > 0 and os.path.exists(args.prior_prompts_file):
+        # the reference's prior-prompt pipeline (train_textboost.py:893-909): human-written prompts, null / template
+        # mixing, shuffled + repeated + sharded by rank; batch_size prompts per step
+        from textboost_b200 import prompts as P
+        import itertools
+        src = P.HumanPromptSource(tokenizer, args.prior_prompts_file, num_samples=None)
+        prior_ds = P.PriorPrompts(src, tokenizer, additional_template=args.template,
+                                  additional_category=args.class_token, null_prob=args.null_prob)
+        stream = iter(P.ShardedStream(prior_ds, drop_last=True, rank=rank, world_size=world)
+                      .shuffle(seed=args.seed).repeat())
+        prior_stream = (P.PriorPrompts.collate_fn(list(itertools.islice(stream, args.train_batch_size)))["input_ids"]
+                        for _ in itertools.count())
+        logger.info(f"prior prompts: {len(src)} from {args.prior_prompts_file}")
+        RUN_INFO["prior_prompts"] = len(src)
+    if args.kpl_weight > 0 and prior_all is None and prior_stream is None:
+        raise ValueError("kpl_weight > 0 needs prior prompts: --prior_prompts_file (JSONL) or 'prior_ids' in "
+                         "--latents_file")
     lat_all, ids_all = lat_all.to(device), ids_all.to(device)
     prior_all = prior_all.to(device) if prior_all is not None else None
     gen = torch.Generator(device=device)
@@ -346,7 +366,9 @@ def main(args):
         else:
             t = torch.multinomial(p_t, B, replacement=True, generator=gen)
         pri = None
-        if prior_all is not None and args.kpl_weight > 0:
+        if prior_stream is not None:
+            pri = next(prior_stream).to(device, non_blocking=True)
+        elif prior_all is not None and args.kpl_weight > 0:
             pidx = (torch.arange(B * world, device=device) + step_idx * B * world) % prior_all.shape[0]
             pri = prior_all[pidx[rank * B:(rank + 1) * B]]
         return lat, noise, t, ids, pri
