@@ -14,8 +14,9 @@ SD-1.5 shapes and inputs are synthetic (no checkpoints or datasets exist offline
 One JSON line on stdout (rank 0).  `value`: inputs resident in HBM, whole step replayed as one CUDA graph,
 timed with CUDA events, max over ranks.  `e2e`: the same step through TextBoostTrainer.step_from_host with
 pinned HOST buffers (H2D of the batch and D2H of the loss inside the timed region, one sync per step).
-`roofline`: the dominant kernel family (tcgen05 implicit-GEMM conv3x3), algorithmic FLOPs / CUDA-event time
-of its launches inside an instrumented step, against MEASURED_PEAKS.json.  `cpu_baseline`: the oracle
+`roofline`: the kernel family with the largest share of the step (the tcgen05 GEMM family), algorithmic FLOPs /
+CUDA-event time of its launches inside an instrumented eager step, against MEASURED_PEAKS.json; `traffic` = DRAM
+bytes per launch from the committed ncu capture; `attention` = the attention tensor-pipe % of the metric.  `cpu_baseline`: the oracle
 restatement of the reference step (plain PyTorch fp32, autograd) timed on this box's host cores on a
 bounded sample.
 """

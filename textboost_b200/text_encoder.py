@@ -26,7 +26,6 @@ There is no CPU execution path: calling the model before it is on an sm_100 devi
 from __future__ import annotations
 
 import copy
-import dataclasses
 import json
 import os
 from types import SimpleNamespace
@@ -58,7 +57,7 @@ class _ClipFunction(torch.autograd.Function):
     graph reaches this node; the real gradients are accumulated by the library into engine.state.grads."""
 
     @staticmethod
-    def forward(ctx, anchor, engine, input_ids, want_pooled):
+    def forward(ctx, anchor, engine, input_ids):
         ctx.engine = engine
         out = engine.forward(input_ids, save_for_backward=True)
         ctx.saved = engine.pop_ctx()
@@ -68,7 +67,7 @@ class _ClipFunction(torch.autograd.Function):
     def backward(ctx, d_out):
         ctx.engine.backward(d_out.to(F32).contiguous().clone(), ctx=ctx.saved)
         ctx.saved = None
-        return torch.zeros(1, device=d_out.device, dtype=F32), None, None, None
+        return torch.zeros(1, device=d_out.device, dtype=F32), None, None
 
 
 class _TokenEmbedding:
@@ -423,7 +422,7 @@ class TextBoostModel:
             (self._lora is not None or self._train_embedding)
         if trainable:
             e.pack_lora()
-            h = _ClipFunction.apply(self._anchor, e, ids, False)
+            h = _ClipFunction.apply(self._anchor, e, ids)
         else:
             with torch.no_grad():
                 e.pack_lora()
@@ -452,4 +451,3 @@ def config_to_dict(cfg: ClipConfig) -> dict:
 
 
 __all__ = ["TextBoostModel", "ModelOutput", "config_to_dict"]
-_ = dataclasses  # (ClipConfig is a dataclass; kept for type checkers)
