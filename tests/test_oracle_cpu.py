@@ -227,3 +227,26 @@ def test_lazy_decay_equals_dense_adamw():
         c *= (1 - lr * wd)
     torch.testing.assert_close(w.detach()[:V], w0[:V] * c, rtol=1e-6, atol=1e-7)
     torch.testing.assert_close(w.detach()[V:], rows, rtol=1e-5, atol=1e-6)
+
+
+def test_vae_encoder_oracle_structure():
+    """oracle/vae_ref.py (image half of SURVEY.md §8 f1, groundwork): diffusers key names, the published encoder
+    parameter count of the SD VAE (34,163,592 + 72 for quant_conv), latent geometry and the sampling formula."""
+    from oracle import vae_ref
+    m = vae_ref.AutoencoderKLEncoderRef()
+    keys = set(m.state_dict())
+    assert sum(p.numel() for p in m.encoder.parameters()) == 34_163_592
+    assert sum(p.numel() for p in m.quant_conv.parameters()) == 72
+    for k in ("encoder.conv_in.weight", "encoder.down_blocks.1.resnets.0.conv_shortcut.weight",
+              "encoder.down_blocks.2.downsamplers.0.conv.bias", "encoder.mid_block.attentions.0.to_out.0.weight",
+              "encoder.mid_block.attentions.0.group_norm.weight", "encoder.conv_norm_out.bias", "quant_conv.weight"):
+        assert k in keys, k
+    assert "encoder.down_blocks.3.downsamplers.0.conv.weight" not in keys
+    small = vae_ref.AutoencoderKLEncoderRef(vae_ref.VAEConfig(block_out_channels=(32, 32, 64, 64)))
+    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(0))
+    eps = torch.randn(2, 4, 8, 8, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        mean, std = small.moments(x)
+        z = small.encode_latents(x, eps)
+    assert mean.shape == (2, 4, 8, 8) and (std > 0).all()
+    torch.testing.assert_close(z, (mean + std * eps) * 0.18215)
