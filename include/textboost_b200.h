@@ -167,6 +167,21 @@ int tb_conv_out_f16(const void* h_nhwc, const void* w, const void* bias, void* y
 int tb_conv_out_bwd_f16(const void* dy_nchw, const void* w, void* dh_nhwc, int B, int H, int W, int Cin,
                         int Cout, void* stream);
 
+/* ---- AutoencoderKL encoder helpers (vae.encode(pixel_values).latent_dist.sample() * scaling_factor,
+ * train_textboost.py:1036-1037; the encoder's convolutions / GroupNorms / linears are tb_conv_in_f16,
+ * tb_conv3x3_f16, tb_gemm_f16 and tb_groupnorm_fwd_f16 calls). ---- */
+/* tb_im2col3x3s2_f16 with a selectable low-side padding: pad_lo = 1 is the UNet's Downsample2D, pad_lo = 0 the
+ * VAE's (F.pad(x, (0,1,0,1)) then conv stride 2 pad 0: zeros on the right / bottom edge only). */
+int tb_im2col3x3s2_pad_f16(const void* x, void* col, int B, int H, int W, int C, int pad_lo, void* stream);
+/* In-place row softmax of an fp16 [rows, cols] matrix with row stride ld (fp32 arithmetic): the probabilities of
+ * the single-head mid-block attention between its QK^T and PV GEMMs.  cols % 8 == 0, cols <= 8192. */
+int tb_softmax_rows_f16(void* x, int64_t ld, int64_t rows, int cols, void* stream);
+/* DiagonalGaussianDistribution: moments fp16 channels-last [B*HW, ld] (columns [0,L) mean, [L,2L) logvar, clamped
+ * to [-30,20]); eps fp32 NCHW [B,L,HW].  latents = (mean + exp(logvar/2) * eps) * scaling_factor (fp32 NCHW);
+ * mean / std are optional fp32 NCHW outputs; latents may be NULL when only the moments are wanted. */
+int tb_vae_sample(const void* moments_f16, int64_t ld, const float* eps, float* latents, float* mean, float* std,
+                  int B, int HW, int latent_channels, float scaling_factor, void* stream);
+
 /* ---- CLIP text encoder pieces that are not GEMM / LayerNorm ------------------------------------
  * (transformers CLIPTextTransformer called from textboost/text_encoder.py:62-69; peft LoRA Linear
  * configured at train_textboost.py:702-709.) */

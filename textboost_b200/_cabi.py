@@ -65,6 +65,10 @@ _SIGNATURES = {
     "tb_cast_f32_f16": [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_float, c_void_p],
     "tb_im2col3x3s2_f16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "tb_zero_stuff2x_f16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "tb_im2col3x3s2_pad_f16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "tb_softmax_rows_f16": [c_void_p, c_int64, c_int64, c_int, c_void_p],
+    "tb_vae_sample": [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                      c_void_p],
     "tb_timestep_embedding_f16": [c_void_p, c_void_p, c_int, c_int, c_void_p],
     "tb_silu_f16": [c_void_p, c_void_p, c_int64, c_void_p],
     "tb_add_noise": [c_void_p] * 6 + [c_int, c_int, c_int, c_void_p],

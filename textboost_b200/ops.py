@@ -280,3 +280,32 @@ def conv_out_bwd(dy_nchw, w):
     dh = torch.empty((B, H, W, Cin), device=dy_nchw.device, dtype=F16)
     C.call("tb_conv_out_bwd_f16", C.ptr(dy_nchw), C.ptr(w), C.ptr(dh), B, H, W, Cin, Cout, C.stream_ptr())
     return dh
+
+
+# ---------------------------------------------------------------------------------- AutoencoderKL encoder helpers
+def im2col3x3s2_pad(x, pad_lo):
+    """im2col3x3s2 with pad_lo rows/columns of zeros on the top/left (0: the VAE's right/bottom-only padding)."""
+    B, H, W, Cc = x.shape
+    col = torch.empty((B * (H // 2) * (W // 2), 9 * Cc), device=x.device, dtype=F16)
+    C.call("tb_im2col3x3s2_pad_f16", C.ptr(x), C.ptr(col), B, H, W, Cc, int(pad_lo), C.stream_ptr())
+    return col
+
+
+def softmax_rows_(x):
+    """In-place softmax over the last dim of an fp16 [rows, cols] matrix (row stride free)."""
+    assert x.dtype == F16 and x.dim() == 2 and x.stride(1) == 1
+    C.call("tb_softmax_rows_f16", C.ptr(x), x.stride(0), x.shape[0], x.shape[1], C.stream_ptr())
+    return x
+
+
+def vae_sample(moments, B, HW, latent_channels, eps=None, scaling_factor=1.0, want_moments=False):
+    """moments fp16 [B*HW, >=2L] channels-last -> latents fp32 [B, L, HW] (and optionally mean, std)."""
+    assert moments.dtype == F16 and moments.dim() == 2 and moments.stride(1) == 1
+    lat = torch.empty((B, latent_channels, HW), device=moments.device, dtype=F32) if eps is not None else None
+    mean = torch.empty((B, latent_channels, HW), device=moments.device, dtype=F32) if want_moments else None
+    std = torch.empty_like(mean) if want_moments else None
+    if eps is not None:
+        assert eps.dtype == F32 and eps.is_contiguous() and eps.numel() == B * latent_channels * HW
+    C.call("tb_vae_sample", C.ptr(moments), moments.stride(0), C.ptr(eps), C.ptr(lat), C.ptr(mean), C.ptr(std),
+           B, HW, latent_channels, float(scaling_factor), C.stream_ptr())
+    return lat, mean, std
