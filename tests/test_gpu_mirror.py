@@ -165,3 +165,33 @@ def test_cli_end_to_end_synthetic_checkpoint(tmp_path):
     # modes outside the built path fail loudly rather than silently training something else
     with pytest.raises(NotImplementedError):
         T.main(T.parse_args(base + ["--lora_rank", "0"]))
+
+
+def test_cli_trains_from_images_through_vae_front_end(tmp_path):
+    """The reference's real data path (train_textboost.py:856-890, 1027-1037): instance images -> PairedAugmentation
+    -> TextBoostDataset -> pixel_values -> AutoencoderKL encoder on the GPU -> latents -> the fused step."""
+    import json
+    import make_augment_golden as G
+    import train_textboost as T
+    from textboost_b200 import synthetic
+    ck = str(tmp_path / "model")
+    synthetic.write_pretrained(ck, "tiny", seed=3, vae_channels=(64, 64, 128, 128))
+    imgs = tmp_path / "dog"
+    imgs.mkdir()
+    for i, size in enumerate([(160, 140), (128, 128), (150, 200)]):
+        G.make_image(size, i).save(imgs / f"{i}.png")
+    jl = tmp_path / "prompts.jsonl"
+    with open(jl, "w") as f:
+        for i in range(6):
+            f.write(json.dumps({"input": f"a photo of a thing {i}", "output": "NONE"}) + "\n")
+    out = str(tmp_path / "out")
+    loss = T.main(T.parse_args([
+        "--pretrained_model_name_or_path", ck, "--output_dir", out, "--instance_data_dir", str(imgs),
+        "--resolution", "128", "--train_batch_size", "2", "--max_train_steps", "6", "--learning_rate", "1e-3",
+        "--mixed_precision", "fp16", "--augment", "pda", "--augment_inversion", "--template", "textboost",
+        "--prior_prompts_file", str(jl), "--class_token", "dog", "--log_every", "2", "--seed", "11"]))
+    assert loss == loss and loss < 10
+    assert T.RUN_INFO["instance_images"] == 3 and T.RUN_INFO["prior_prompts"] == 6
+    assert {"text_encoder", "dog.bin", "hflip.bin", "training.log"} <= set(os.listdir(out))
+    with pytest.raises(ValueError):  # no data source at all
+        T.main(T.parse_args(["--pretrained_model_name_or_path", ck, "--output_dir", out, "--max_train_steps", "1"]))

@@ -1,0 +1,156 @@
+"""Image side of the reference's data pipeline: instance images -> augmented, resized, cropped,
+normalised ``pixel_values`` + tokenised prompts, batched the way the training loop consumes them
+(/root/reference/train_textboost.py:872-890, 1027-1037).  Host-only PIL / torchvision work; the pixels then go to
+``textboost_b200.vae`` on the GPU.  Mirrors /root/reference/textboost/dataset.py with the same names and draws:
+
+  get_images_path          dataset.py:96-105
+  TextBoostDataset         dataset.py:272-418   (item dict keys: image, input_ids, attention_mask, original_size,
+                                                 crop_top_left, mask / class_* when present)
+  TextBoostDataset.collate_fn   dataset.py:420-459
+  InstructPix2PixDataset / PriorDataset / Wrapper  -> textboost_b200.prompts (re-exported under the reference names)
+
+Random draws per item, in order: ``random.randint`` for the template, the augmentation pipeline's numpy / random
+draws, torch's RNG for the random crop — identical to the reference so that a seed reproduces its training data
+(tests/golden/dataset_golden.json is generated from the reference classes).
+"""
+from __future__ import annotations
+
+import os
+import random
+from pathlib import Path
+from typing import List, Optional, Sequence
+
+import torch
+from PIL import Image
+from PIL.ImageOps import exif_transpose
+from torchvision.transforms import v2
+
+from .prompts import HumanPromptSource as InstructPix2PixDataset  # noqa: F401  (reference import names)
+from .prompts import PriorPrompts as PriorDataset  # noqa: F401
+from .prompts import ShardedStream as Wrapper  # noqa: F401
+from .prompts import resolve_template, tokenize_prompt
+
+
+def get_images_path(data_root, max_samples: Optional[int] = None) -> List[Path]:
+    """Sorted directory listing, optionally truncated (``--num_samples``)."""
+    root = Path(data_root)
+    if not root.exists():
+        raise ValueError("Data root doesn't exists.")
+    paths = sorted(root.iterdir())
+    return paths if max_samples is None else paths[:max_samples]
+
+
+def _open_rgb(path) -> Image.Image:
+    image = exif_transpose(Image.open(path))
+    return image if image.mode == "RGB" else image.convert("RGB")
+
+
+class TextBoostDataset(torch.utils.data.Dataset):
+    def __init__(self, concepts_list: Sequence[dict], tokenizer, tokenizer_2=None, num_instance=None, template="a {}",
+                 prior_data_root=None, class_token=None, num_prior=None, size=512, center_crop=False,
+                 augment_pipe=None, augment_prior: bool = False):
+        self.size, self.center_crop = size, center_crop
+        self.tokenizer, self.tokenizer_2 = tokenizer, tokenizer_2
+        self.template = resolve_template(template)
+        self.instance_images_path = [(path, concept["instance_token"]) for concept in concepts_list
+                                     for path in get_images_path(concept["instance_data_dir"], num_instance)]
+        self.num_instance_images = self._length = len(self.instance_images_path)
+        self.class_token = class_token
+        self.prior_data_root = None
+        if prior_data_root is not None:
+            self.prior_data_root = Path(prior_data_root)
+            self.prior_data_root.mkdir(parents=True, exist_ok=True)
+            self.class_images_path = list(self.prior_data_root.iterdir())
+            n = len(self.class_images_path)
+            self.num_prior_images = n if num_prior is None else min(n, num_prior)
+            self._length = max(self.num_prior_images, self.num_instance_images)
+        self.resize_fn = v2.Resize(size, interpolation=v2.InterpolationMode.LANCZOS)
+        self.crop = v2.CenterCrop(size) if center_crop else v2.RandomCrop(size)
+        # PIL -> float CHW in [-1, 1]
+        self.image_transforms = v2.Compose([v2.ToImage(), v2.ToDtype(torch.float, scale=True),
+                                            v2.Normalize((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))])
+        self.augment_pipe, self.augment_prior = augment_pipe, augment_prior
+
+    def __len__(self):
+        return self._length
+
+    def _resize_and_crop_image(self, image):
+        """Shorter side to `size` (Lanczos), then a `size` x `size` window: centred, or at a position drawn from
+        torch's RNG.  Returns the window and its top-left corner (y, x)."""
+        image = self.resize_fn(image)
+        if self.center_crop:
+            top = max(0, int(round((image.height - self.size) / 2.0)))
+            left = max(0, int(round((image.width - self.size) / 2.0)))
+            return self.crop(image), top, left
+        top, left, h, w = self.crop.get_params(image, (self.size, self.size))
+        return v2.functional.crop(image, top, left, h, w), top, left
+
+    def _augment(self, image, prompt, sample, mask_key):
+        image, prompt, mask = self.augment_pipe(image, prompt)
+        if mask is not None:
+            sample[mask_key] = torch.as_tensor(mask, dtype=torch.float32).unsqueeze(0)
+        return image, prompt
+
+    def _tokenize_into(self, sample, prompt, prefix=""):
+        t = tokenize_prompt(self.tokenizer, prompt)
+        sample[prefix + "input_ids"], sample[prefix + "attention_mask"] = t.input_ids, t.attention_mask
+        if self.tokenizer_2 is not None and not prefix:
+            t2 = tokenize_prompt(self.tokenizer_2, prompt)
+            sample["input_ids_2"], sample["attention_mask_2"] = t2.input_ids, t2.attention_mask
+
+    def __getitem__(self, index):
+        sample = {}
+        path, instance_token = self.instance_images_path[index % self.num_instance_images]
+        image = _open_rgb(path)
+        which = random.randint(0, len(self.template) - 1)
+        prompt = self.template[which].format(instance_token)
+        if self.augment_pipe is not None:
+            image, prompt = self._augment(image, prompt, sample, "mask")
+        sample["original_size"] = (image.width, image.height)
+        image, top, left = self._resize_and_crop_image(image)
+        sample["image"] = self.image_transforms(image)
+        sample["crop_top_left"] = (top, left)
+        self._tokenize_into(sample, prompt)
+        if self.prior_data_root:
+            self._class_item(sample, index, which)
+        return sample
+
+    def _class_item(self, sample, index, which):
+        """The ``--with_image_prior`` half of an item: a class image with the same template, or with the prompt
+        spelled in its file name (``<n>-<words_with_underscores>.<ext>``) when no class token is given."""
+        path = self.class_images_path[index % self.num_prior_images]
+        image = exif_transpose(Image.open(path)).convert("RGB")
+        if self.class_token is not None:
+            prompt = self.template[which].format(self.class_token)
+        else:
+            prompt = os.path.basename(path).split("-")[1].split(".")[0].replace("_", " ")
+        if self.augment_prior and self.augment_pipe is not None:
+            image, prompt = self._augment(image, prompt, sample, "prior_mask")
+        if "mask" in sample and "prior_mask" not in sample:
+            sample["prior_mask"] = torch.ones_like(sample["mask"])
+        # the reference resizes and crops once, then runs the resize-and-crop helper on the result: with a random
+        # crop that is two draws from torch's RNG, kept so that seeded runs stay aligned
+        image = self.crop(self.resize_fn(image))
+        image, top, left = self._resize_and_crop_image(image)
+        sample["class_image"] = self.image_transforms(image)
+        sample["class_crop_top_left"] = (top, left)
+        self._tokenize_into(sample, prompt, prefix="class_")
+
+    @staticmethod
+    def collate_fn(samples, with_prior_preservation=False):
+        """-> {"input_ids" [n,L], "pixel_values" [n,3,S,S] fp32, "attention_mask" list, "mask" if present}; with
+        prior preservation the class examples are appended after the instance ones (one forward for both)."""
+        keys = [""] + (["class_"] if with_prior_preservation else [])
+        has_mask = "attention_mask" in samples[0]
+        ids = [s[k + "input_ids"] for k in keys for s in samples]
+        pixels = [s["class_image" if k else "image"] for k in keys for s in samples]
+        batch = {"input_ids": torch.cat(ids, dim=0),
+                 "pixel_values": torch.stack(pixels).to(memory_format=torch.contiguous_format).float()}
+        if "mask" in samples[0]:
+            masks = [s["mask"] for s in samples]
+            if "prior_mask" in samples[0]:
+                masks += [s["prior_mask"] for s in samples]
+            batch["mask"] = torch.stack(masks)
+        if has_mask:
+            batch["attention_mask"] = [s[k + "attention_mask"] for k in keys for s in samples]
+        return batch

@@ -113,7 +113,7 @@ class PriorPrompts:
                 "attention_mask": [s["attention_mask"] for s in samples]}
 
 
-class ShardedStream:
+class ShardedStream(torch.utils.data.IterableDataset):
     """Iterable over `source` sharded by rank and DataLoader worker: every epoch the index list is (optionally)
     shuffled with numpy's default_rng(seed + epoch) — cumulatively, the permutation of epoch e is applied to the
     order left by epoch e-1, as in the reference —, trimmed (drop_last) or wrapped to a multiple of world x workers,

@@ -141,6 +141,23 @@ def random_unet_sd(cfg: UNetConfig, device, seed=0, dtype=torch.float16):
     return sd
 
 
+def random_vae_sd(cfg=None, device="cpu", seed=0, dtype=torch.float32):
+    """Random AutoencoderKL encoder weights (fp32 on disk, as SD checkpoints ship them): N(0, 1/fan_in) convs /
+    linears, norm affine 1 + N(0,.1), small biases."""
+    from . import vae
+    cfg = cfg or vae.VAEConfig()
+    g = torch.Generator(device=device).manual_seed(seed)
+    sd = {}
+    for k, shp in vae.vae_encoder_shapes(cfg).items():
+        if len(shp) == 1:
+            base = 1.0 if ("norm" in k and k.endswith("weight")) else 0.0
+            t = base + (0.1 if base else 0.05) * torch.randn(shp, generator=g, device=device)
+        else:
+            t = torch.randn(shp, generator=g, device=device) / math.sqrt(math.prod(shp[1:]))
+        sd[k] = t.to(dtype)
+    return sd
+
+
 def random_clip_sd(cfg: ClipConfig, vocab: int, device, seed=0):
     g = torch.Generator(device=device).manual_seed(seed)
     sd = {}
@@ -285,9 +302,11 @@ class LiteralTokenizer:
         return SimpleNamespace(input_ids=row, attention_mask=mask)
 
 
-def write_pretrained(directory: str, model: str = "tiny", seed: int = 0, prediction_type: str = "epsilon"):
-    """Write a random-init checkpoint in the diffusers directory layout (unet/, text_encoder/, scheduler/)
-    that train_textboost.py's from_pretrained calls read (train_textboost.py:633-656)."""
+def write_pretrained(directory: str, model: str = "tiny", seed: int = 0, prediction_type: str = "epsilon",
+                     vae_channels=None):
+    """Write a random-init checkpoint in the diffusers directory layout (unet/, text_encoder/, scheduler/, and
+    vae/ when `vae_channels` = its block_out_channels is given) that train_textboost.py's from_pretrained calls
+    read (train_textboost.py:633-656)."""
     import json
     import os
     from safetensors.torch import save_file
@@ -306,6 +325,15 @@ def write_pretrained(directory: str, model: str = "tiny", seed: int = 0, predict
     with open(os.path.join(directory, "text_encoder", "config.json"), "w") as f:
         json.dump({**te_mod.config_to_dict(ccfg), "architectures": ["CLIPTextModel"],
                    "model_type": "clip_text_model"}, f, indent=2)
+    if vae_channels:  # vae/ in the diffusers layout (fp32 weights; encoder + quant_conv keys only)
+        from . import vae
+        vcfg = vae.VAEConfig(block_out_channels=tuple(vae_channels))
+        os.makedirs(os.path.join(directory, "vae"), exist_ok=True)
+        vsd = {k: v.contiguous() for k, v in random_vae_sd(vcfg, "cpu", seed + 2).items()}
+        save_file(vsd, os.path.join(directory, "vae", "diffusion_pytorch_model.safetensors"),
+                  metadata={"format": "pt"})
+        with open(os.path.join(directory, "vae", "config.json"), "w") as f:
+            json.dump(vae.config_to_dict(vcfg), f, indent=2)
     with open(os.path.join(directory, "scheduler", "scheduler_config.json"), "w") as f:
         json.dump({"_class_name": "DDPMScheduler", "num_train_timesteps": 1000, "beta_start": 0.00085,
                    "beta_end": 0.012, "beta_schedule": "scaled_linear", "prediction_type": prediction_type}, f)

@@ -55,6 +55,54 @@ class VAEConfig:
 _EPS = 1e-6
 
 
+def config_to_dict(cfg: VAEConfig) -> dict:
+    """The keys of a diffusers ``vae/config.json`` this engine reads."""
+    return {"_class_name": "AutoencoderKL", "in_channels": cfg.in_channels, "latent_channels": cfg.latent_channels,
+            "block_out_channels": list(cfg.block_out_channels), "layers_per_block": cfg.layers_per_block,
+            "norm_num_groups": cfg.norm_num_groups, "scaling_factor": cfg.scaling_factor}
+
+
+def vae_encoder_shapes(cfg: VAEConfig) -> Dict[str, Tuple[int, ...]]:
+    """diffusers state-dict keys and shapes of ``AutoencoderKL.encoder`` + ``quant_conv`` (what the engine loads)."""
+    ch = cfg.block_out_channels
+    L2 = 2 * cfg.latent_channels
+    out: Dict[str, Tuple[int, ...]] = {}
+
+    def conv(name, cout, cin, k):
+        out[name + ".weight"], out[name + ".bias"] = (cout, cin, k, k), (cout,)
+
+    def vec(name, c):
+        out[name + ".weight"], out[name + ".bias"] = (c,), (c,)
+
+    def resnet(p, cin, cout):
+        vec(p + "norm1", cin)
+        conv(p + "conv1", cout, cin, 3)
+        vec(p + "norm2", cout)
+        conv(p + "conv2", cout, cout, 3)
+        if cin != cout:
+            conv(p + "conv_shortcut", cout, cin, 1)
+
+    conv("encoder.conv_in", ch[0], cfg.in_channels, 3)
+    cin = ch[0]
+    for i, c in enumerate(ch):
+        for j in range(cfg.layers_per_block):
+            resnet(f"encoder.down_blocks.{i}.resnets.{j}.", cin if j == 0 else c, c)
+        if i != len(ch) - 1:
+            conv(f"encoder.down_blocks.{i}.downsamplers.0.conv", c, c, 3)
+        cin = c
+    c = ch[-1]
+    resnet("encoder.mid_block.resnets.0.", c, c)
+    resnet("encoder.mid_block.resnets.1.", c, c)
+    a = "encoder.mid_block.attentions.0."
+    vec(a + "group_norm", c)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        out[a + n + ".weight"], out[a + n + ".bias"] = (c, c), (c,)
+    vec("encoder.conv_norm_out", c)
+    conv("encoder.conv_out", L2, c, 3)
+    conv("quant_conv", L2, L2, 1)
+    return out
+
+
 class _Resnet:
     def __init__(self, sd, p, groups):
         self.G = groups

@@ -13,10 +13,12 @@ Launch one process per GPU with torchrun, as the reference does (README.md:82).
 Outputs are the reference's: ``<output_dir>/text_encoder/adapter_{config.json,model.safetensors}``,
 ``<output_dir>/<token>.bin`` per added token, ``checkpoint-N/`` directories (here with a working resume).
 
-Out of scope this round: the image dataset / PIL augmentation / VAE encode front end and
-the validation sampler.  Latents therefore come from ``--latents_file`` (a ``torch.save``d dict with
-``latents`` [N,4,h,w] fp32 — already scaled by the VAE factor — ``input_ids`` [N,77] and optional
-``prior_ids`` [P,77]) or ``--synthetic_data``; both flags are additions, everything else is the reference's.
+Data: with ``--instance_data_dir`` / ``--concepts_list`` the reference's front end runs —
+``TextBoostDataset`` + ``PairedAugmentation`` (textboost_b200.dataset / .augment, same draws as the reference) ->
+``pixel_values`` -> the B200 AutoencoderKL encoder (textboost_b200.vae) -> latents, every step.  ``--latents_file``
+(a ``torch.save``d dict with ``latents`` [N,4,h,w] fp32 — already scaled by the VAE factor — ``input_ids`` [N,77]
+and optional ``prior_ids`` [P,77]) and ``--synthetic_data`` bypass it; both flags are additions, everything else is
+the reference's.  Out of scope (§8 f3): the validation sampler.
 """
 from __future__ import annotations
 
@@ -163,6 +165,35 @@ def load_tokenizer(args):
     return synthetic.LiteralTokenizer()
 
 
+def build_image_batches(args, tokenizer, rank, world):
+    """The reference's train dataloader (train_textboost.py:856-890): PairedAugmentation -> TextBoostDataset ->
+    Wrapper(drop_last=False).shuffle(seed).repeat() sharded by rank -> DataLoader(batch_size, collate_fn).  Returns an
+    endless iterator of {"pixel_values" [B,3,S,S] fp32 in [-1,1], "input_ids" [B,L], "attention_mask"}."""
+    from textboost_b200.dataset import TextBoostDataset, Wrapper
+    if args.augment in ("pda", "paug"):
+        from textboost_b200.augment import PairedAugmentation
+        augment_pipe = PairedAugmentation(hflip="inversion" if args.augment_inversion else "false",
+                                          augment_prompt=args.augment_prompt, inversion=args.augment_inversion,
+                                          p=args.augment_p, ops=args.augment_ops)
+    elif args.augment == "custom_diff":
+        raise NotImplementedError("--augment custom_diff: the reference imports a CustomDiffAugment class that its "
+                                  "own textboost.augment package does not define (train_textboost.py:867)")
+    else:
+        augment_pipe = None
+    dataset = TextBoostDataset(concepts_list=args.concepts_list, tokenizer=tokenizer, num_instance=args.num_samples,
+                               template=args.template, prior_data_root=None, class_token=args.class_token,
+                               num_prior=args.num_prior_images, size=args.resolution, center_crop=args.center_crop,
+                               augment_pipe=augment_pipe)
+    if len(dataset) == 0:
+        raise ValueError("no instance images found")
+    stream = Wrapper(dataset, drop_last=False, rank=rank, world_size=world).shuffle(seed=args.seed).repeat()
+    loader = torch.utils.data.DataLoader(stream, batch_size=args.train_batch_size,
+                                         collate_fn=lambda ex: TextBoostDataset.collate_fn(ex, False),
+                                         num_workers=args.dataloader_num_workers)
+    RUN_INFO["instance_images"] = len(dataset)
+    return iter(loader)
+
+
 def save_learned_embeddings(text_encoder, added_tokens, aug_token_dict, directory):
     """train_textboost.py:1188-1209 / :1245-1266: one ``{token}.bin`` per added token (placeholder rows saved
     as [D], augmentation rows as [1, D])."""
@@ -223,6 +254,10 @@ def main(args):
                         handlers=[logging.StreamHandler()] + (
                             [logging.FileHandler(os.path.join(args.output_dir, "training.log"))] if is_main else []))
     if args.seed is not None:  # same seed on every rank (train_textboost.py:598-601, SURVEY.md trap 10)
+        import random
+        import numpy as np
+        random.seed(args.seed)  # accelerate.set_seed: python, numpy and torch streams (the augmentation draws from
+        np.random.seed(args.seed)  # the first two, the random crop from the third)
         torch.manual_seed(args.seed)
 
     if args.concepts_list is None:  # train_textboost.py:602-615
@@ -298,10 +333,22 @@ def main(args):
         mixing=("style" if args.augment_ops == "style" else "object") if args.mixing else None,
         mean_norm=mean_norm, mixed_precision=args.mixed_precision or "fp16")
 
-    # ---- data (front end out of scope: latents file or synthetic)
+    # ---- data: the image front end (dataset -> augmentation -> VAE encoder), a latents file, or synthetic latents
     B = args.train_batch_size
     latent = args.resolution // 8
-    if args.latents_file:
+    vae = image_batches = None
+    if not args.latents_file and not args.synthetic_data:
+        if not all(c.get("instance_data_dir") for c in args.concepts_list):
+            raise ValueError("no training data: pass --instance_data_dir / --concepts_list (image front end), "
+                             "--latents_file or --synthetic_data")
+        from textboost_b200.vae import AutoencoderKL
+        vae = AutoencoderKL.from_pretrained(path, subfolder="vae", revision=args.revision, variant=args.variant)
+        vae.eval().requires_grad_(False)
+        vae.to(device, dtype=torch.float32)
+        image_batches = build_image_batches(args, tokenizer, rank, world)
+        lat_all = ids_all = prior_all = None
+        logger.info(f"image front end: {RUN_INFO['instance_images']} instance images, augment={args.augment}")
+    elif args.latents_file:
         data = torch.load(args.latents_file, map_location="cpu", weights_only=True)
         lat_all, ids_all = data["latents"].float(), data["input_ids"].long()
         prior_all = data.get("prior_ids")
@@ -312,9 +359,6 @@ def main(args):
         ids_all = synthetic.instance_ids(n, placeholder_token_ids[0], text_encoder.config.max_position_embeddings)
         prior_all = synthetic.prior_ids(max(args.num_prior_images, B * world), args.seed + 1,
                                         text_encoder.config.max_position_embeddings, args.null_prob)
-    else:
-        raise NotImplementedError("the image dataset + VAE-encode front end is not built (SURVEY.md §8 f1): pass "
-                                  "--latents_file or --synthetic_data")
     prior_stream = None
     if args.kpl_weight > 0 and os.path.exists(args.prior_prompts_file):
         # the reference's prior-prompt pipeline (train_textboost.py:893-909): human-written prompts, null / template
@@ -333,7 +377,8 @@ def main(args):
     if args.kpl_weight > 0 and prior_all is None and prior_stream is None:
         raise ValueError("kpl_weight > 0 needs prior prompts: --prior_prompts_file (JSONL) or 'prior_ids' in "
                          "--latents_file")
-    lat_all, ids_all = lat_all.to(device), ids_all.to(device)
+    if image_batches is None:
+        lat_all, ids_all = lat_all.to(device), ids_all.to(device)
     prior_all = prior_all.to(device) if prior_all is not None else None
     gen = torch.Generator(device=device)
     gen.manual_seed(args.seed)
@@ -356,10 +401,16 @@ def main(args):
 
     def draw(step_idx):
         """rank r takes rows [r*B, (r+1)*B) of the step's global batch (dataset.py:846-870 sharding)."""
-        n = lat_all.shape[0]
-        idx = (torch.arange(B * world, device=device) + step_idx * B * world) % n
-        idx = idx[rank * B:(rank + 1) * B]
-        lat, ids = lat_all[idx], ids_all[idx]
+        if image_batches is not None:  # train_textboost.py:1027-1037: pixels -> VAE posterior sample * scaling_factor
+            batch = next(image_batches)
+            pixels = batch["pixel_values"].to(device, non_blocking=True)
+            lat = vae.engine.encode_latents(pixels, generator=gen)
+            ids = batch["input_ids"].to(device, non_blocking=True)
+        else:
+            n = lat_all.shape[0]
+            idx = (torch.arange(B * world, device=device) + step_idx * B * world) % n
+            idx = idx[rank * B:(rank + 1) * B]
+            lat, ids = lat_all[idx], ids_all[idx]
         noise = torch.randn(lat.shape, generator=gen, device=device)
         if p_t is None:
             t = torch.randint(0, T, (B,), generator=gen, device=device)
