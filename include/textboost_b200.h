@@ -182,6 +182,25 @@ int tb_softmax_rows_f16(void* x, int64_t ld, int64_t rows, int cols, void* strea
 int tb_vae_sample(const void* moments_f16, int64_t ld, const float* eps, float* latents, float* mean, float* std,
                   int B, int HW, int latent_channels, float scaling_factor, void* stream);
 
+/* ---- validation / inference sampler (diffusers StableDiffusionPipeline + DPMSolverMultistepScheduler, reached from
+ * train_textboost.py:453-531 log_validation and inference.py:84-105).  The UNet forward of every denoising step is the
+ * tb_gemm_f16 / tb_conv3x3_f16 / tb_attn_fwd_f16 ... calls of the training path; these are the steps in between. ---- */
+/* One fused launch per denoising step: classifier-free guidance e = e_u + g (e_c - e_u) on the UNet output of the
+ * [uncond | cond] doubled batch (eps fp16 [2n]); data prediction m0 at (alpha_i, sigma_i) for epsilon or
+ * v-prediction; DPM-Solver++ update x <- c_x x + c_d0 m0 + c_d1 (m0 - m_prev)  (c_d1 = 0: first order; midpoint
+ * second order otherwise; the coefficients are host scalars of the sigma schedule).  x fp32 [n] in place, m_out fp32
+ * [n], and x as fp16 into both halves of unet_in [2n] (may be NULL on the last step). */
+int tb_dpm_cfg_step(float* x, const void* eps_f16, const float* m_prev, float* m_out, void* unet_in_f16, int64_t n,
+                    float guidance_scale, float alpha_i, float sigma_i, int v_prediction, float c_x, float c_d0,
+                    float c_d1, void* stream);
+/* vae.decode input: z = post_quant_conv(latents / scaling_factor), 1x1 conv with w fp32 [L,L], bias fp32 [L];
+ * latents fp32 NCHW [B,L,HW] -> z fp16 NCHW (read by tb_conv_in_f16 of the decoder). */
+int tb_vae_decode_in(const float* latents, const float* w, const float* bias, void* z_f16, int B,
+                     int latent_channels, int HW, float inv_scaling_factor, void* stream);
+/* VaeImageProcessor.postprocess: (x/2 + 0.5).clamp(0,1) * 255 rounded half-to-even -> uint8 [npix, channels] from fp16
+ * channels-last rows with stride ld. */
+int tb_image_u8(const void* x_f16, int64_t ld, void* out_u8, int64_t npix, int channels, void* stream);
+
 /* ---- CLIP text encoder pieces that are not GEMM / LayerNorm ------------------------------------
  * (transformers CLIPTextTransformer called from textboost/text_encoder.py:62-69; peft LoRA Linear
  * configured at train_textboost.py:702-709.) */

@@ -4,7 +4,7 @@
     latents = vae.encode(pixel_values).latent_dist.sample() * vae.config.scaling_factor      (fp32, no grad)
 
 restated in plain PyTorch with the diffusers state-dict key names (``encoder.*``, ``quant_conv.*``), for the image
-half of SURVEY.md §8 f1 (not built on the CUDA side yet).  SD-1.x / 2.x VAE config: in 3, latent 4,
+half of SURVEY.md §8 f1, and its decoder half (``AutoencoderKLRef``) for the validation / inference sampler of §8 f3.  SD-1.x / 2.x VAE config: in 3, latent 4,
 block_out_channels (128, 256, 512, 512), 2 resnets per block, GroupNorm(32, eps 1e-6), SiLU, downsample = pad
 (0,1,0,1) + conv3x3 stride 2, mid block = resnet, single-head attention over 512 channels, resnet; conv_out -> 8
 channels (mean | logvar), quant_conv 1x1; scaling_factor 0.18215.
@@ -117,6 +117,52 @@ class Encoder(nn.Module):
         return self.conv_out(F.silu(self.conv_norm_out(x)))
 
 
+class UpBlock(nn.Module):
+    """diffusers UpDecoderBlock2D: layers_per_block + 1 resnets, then nearest 2x upsample + conv3x3 (Upsample2D)."""
+
+    def __init__(self, cin, cout, n, groups, up):
+        super().__init__()
+        self.resnets = nn.ModuleList([Resnet(cin if j == 0 else cout, cout, groups) for j in range(n)])
+        self.upsamplers = nn.ModuleList([Upsample(cout)]) if up else None
+
+    def forward(self, x):
+        for r in self.resnets:
+            x = r(x)
+        if self.upsamplers is not None:
+            x = self.upsamplers[0](x)
+        return x
+
+
+class Upsample(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, padding=1)
+
+    def forward(self, x):
+        return self.conv(F.interpolate(x, scale_factor=2.0, mode="nearest"))
+
+
+class Decoder(nn.Module):
+    def __init__(self, cfg: VAEConfig):
+        super().__init__()
+        ch = tuple(reversed(cfg.block_out_channels))
+        self.conv_in = nn.Conv2d(cfg.latent_channels, ch[0], 3, padding=1)
+        self.mid_block = MidBlock(ch[0], cfg.norm_num_groups)
+        blocks, cin = [], ch[0]
+        for i, c in enumerate(ch):
+            blocks.append(UpBlock(cin, c, cfg.layers_per_block + 1, cfg.norm_num_groups, up=i != len(ch) - 1))
+            cin = c
+        self.up_blocks = nn.ModuleList(blocks)
+        self.conv_norm_out = nn.GroupNorm(cfg.norm_num_groups, ch[-1], eps=1e-6)
+        self.conv_out = nn.Conv2d(ch[-1], cfg.in_channels, 3, padding=1)
+
+    def forward(self, z):
+        x = self.mid_block(self.conv_in(z))
+        for b in self.up_blocks:
+            x = b(x)
+        return self.conv_out(F.silu(self.conv_norm_out(x)))
+
+
 class AutoencoderKLEncoderRef(nn.Module):
     def __init__(self, cfg: VAEConfig = VAEConfig()):
         super().__init__()
@@ -134,3 +180,26 @@ class AutoencoderKLEncoderRef(nn.Module):
         """train_textboost.py:1036-1037 with the Gaussian sample made explicit: (mean + std * eps) * scaling_factor."""
         mean, std = self.moments(pixel_values)
         return (mean + std * eps) * self.cfg.scaling_factor
+
+
+class AutoencoderKLRef(AutoencoderKLEncoderRef):
+    """Encoder + decoder (diffusers AutoencoderKL: 83,653,863 parameters for the SD config).  ``decode_latents`` is what
+    StableDiffusionPipeline does at the end of sampling (train_textboost.py:512-513 via ``pipeline(...)``, and
+    /root/reference/inference.py:99-105): ``vae.decode(latents / scaling_factor).sample`` -> (x/2 + .5).clamp(0, 1)."""
+
+    def __init__(self, cfg: VAEConfig = VAEConfig()):
+        super().__init__(cfg)
+        self.decoder = Decoder(cfg)
+        self.post_quant_conv = nn.Conv2d(cfg.latent_channels, cfg.latent_channels, 1)
+
+    def decode(self, z):
+        return self.decoder(self.post_quant_conv(z))
+
+    def decode_latents(self, latents):
+        image = self.decode(latents / self.cfg.scaling_factor)
+        return (image / 2 + 0.5).clamp(0, 1)
+
+    @staticmethod
+    def to_uint8(image01):
+        """VaeImageProcessor.postprocess(output_type="pil") up to the PIL wrap: NCHW [0,1] -> NHWC uint8."""
+        return (image01.permute(0, 2, 3, 1).float() * 255).round().to(torch.uint8)

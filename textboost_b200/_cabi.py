@@ -69,6 +69,10 @@ _SIGNATURES = {
     "tb_softmax_rows_f16": [c_void_p, c_int64, c_int64, c_int, c_void_p],
     "tb_vae_sample": [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                       c_void_p],
+    "tb_dpm_cfg_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_int,
+                        c_float, c_float, c_float, c_void_p],
+    "tb_vae_decode_in": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p],
+    "tb_image_u8": [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p],
     "tb_timestep_embedding_f16": [c_void_p, c_void_p, c_int, c_int, c_void_p],
     "tb_silu_f16": [c_void_p, c_void_p, c_int64, c_void_p],
     "tb_add_noise": [c_void_p] * 6 + [c_int, c_int, c_int, c_void_p],

@@ -309,3 +309,35 @@ def vae_sample(moments, B, HW, latent_channels, eps=None, scaling_factor=1.0, wa
     C.call("tb_vae_sample", C.ptr(moments), moments.stride(0), C.ptr(eps), C.ptr(lat), C.ptr(mean), C.ptr(std),
            B, HW, latent_channels, float(scaling_factor), C.stream_ptr())
     return lat, mean, std
+
+
+# ---------------------------------------------------------------------------------- sampler helpers
+def dpm_cfg_step(x, eps, m_prev, m_out, unet_in, guidance_scale, alpha_i, sigma_i, v_prediction, c_x, c_d0, c_d1):
+    """In place on x fp32 [B,...]: CFG + data prediction + DPM-Solver++ update (see tb_dpm_cfg_step)."""
+    n = x.numel()
+    assert x.dtype == F32 and x.is_contiguous() and eps.dtype == F16 and eps.is_contiguous() and eps.numel() == 2 * n
+    assert m_out.dtype == F32 and m_out.numel() == n and (m_prev is None or m_prev.numel() == n)
+    assert unet_in is None or (unet_in.dtype == F16 and unet_in.is_contiguous() and unet_in.numel() == 2 * n)
+    C.call("tb_dpm_cfg_step", C.ptr(x), C.ptr(eps), C.ptr(m_prev), C.ptr(m_out), C.ptr(unet_in), n,
+           float(guidance_scale), float(alpha_i), float(sigma_i), int(v_prediction), float(c_x), float(c_d0),
+           float(c_d1), C.stream_ptr())
+    return x
+
+
+def vae_decode_in(latents, w, bias, scaling_factor):
+    """latents fp32 [B,L,h,w] -> post_quant_conv(latents / scaling_factor) as fp16 NCHW."""
+    B, L = latents.shape[:2]
+    HW = latents.numel() // (B * L)
+    assert latents.dtype == F32 and latents.is_contiguous() and w.dtype == F32 and bias.dtype == F32
+    z = torch.empty(latents.shape, device=latents.device, dtype=F16)
+    C.call("tb_vae_decode_in", C.ptr(latents), C.ptr(w), C.ptr(bias), C.ptr(z), B, L, HW, 1.0 / scaling_factor,
+           C.stream_ptr())
+    return z
+
+
+def image_u8(rows, npix, channels=3):
+    """fp16 channels-last rows [npix, >=channels] in [-1,1] -> uint8 [npix, channels]."""
+    assert rows.dtype == F16 and rows.dim() == 2 and rows.stride(1) == 1 and rows.shape[0] == npix
+    out = torch.empty((npix, channels), device=rows.device, dtype=torch.uint8)
+    C.call("tb_image_u8", C.ptr(rows), rows.stride(0), C.ptr(out), npix, channels, C.stream_ptr())
+    return out

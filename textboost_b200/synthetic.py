@@ -141,14 +141,17 @@ def random_unet_sd(cfg: UNetConfig, device, seed=0, dtype=torch.float16):
     return sd
 
 
-def random_vae_sd(cfg=None, device="cpu", seed=0, dtype=torch.float32):
+def random_vae_sd(cfg=None, device="cpu", seed=0, dtype=torch.float32, with_decoder=False):
     """Random AutoencoderKL encoder weights (fp32 on disk, as SD checkpoints ship them): N(0, 1/fan_in) convs /
     linears, norm affine 1 + N(0,.1), small biases."""
     from . import vae
     cfg = cfg or vae.VAEConfig()
     g = torch.Generator(device=device).manual_seed(seed)
     sd = {}
-    for k, shp in vae.vae_encoder_shapes(cfg).items():
+    shapes = dict(vae.vae_encoder_shapes(cfg))
+    if with_decoder:
+        shapes.update(vae.vae_decoder_shapes(cfg))
+    for k, shp in shapes.items():
         if len(shp) == 1:
             base = 1.0 if ("norm" in k and k.endswith("weight")) else 0.0
             t = base + (0.1 if base else 0.05) * torch.randn(shp, generator=g, device=device)
@@ -325,11 +328,11 @@ def write_pretrained(directory: str, model: str = "tiny", seed: int = 0, predict
     with open(os.path.join(directory, "text_encoder", "config.json"), "w") as f:
         json.dump({**te_mod.config_to_dict(ccfg), "architectures": ["CLIPTextModel"],
                    "model_type": "clip_text_model"}, f, indent=2)
-    if vae_channels:  # vae/ in the diffusers layout (fp32 weights; encoder + quant_conv keys only)
+    if vae_channels:  # vae/ in the diffusers layout (fp32 weights, as SD checkpoints ship them)
         from . import vae
         vcfg = vae.VAEConfig(block_out_channels=tuple(vae_channels))
         os.makedirs(os.path.join(directory, "vae"), exist_ok=True)
-        vsd = {k: v.contiguous() for k, v in random_vae_sd(vcfg, "cpu", seed + 2).items()}
+        vsd = {k: v.contiguous() for k, v in random_vae_sd(vcfg, "cpu", seed + 2, with_decoder=True).items()}
         save_file(vsd, os.path.join(directory, "vae", "diffusion_pytorch_model.safetensors"),
                   metadata={"format": "pt"})
         with open(os.path.join(directory, "vae", "config.json"), "w") as f:

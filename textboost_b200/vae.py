@@ -103,6 +103,47 @@ def vae_encoder_shapes(cfg: VAEConfig) -> Dict[str, Tuple[int, ...]]:
     return out
 
 
+def vae_decoder_shapes(cfg: VAEConfig) -> Dict[str, Tuple[int, ...]]:
+    """diffusers state-dict keys and shapes of ``AutoencoderKL.decoder`` + ``post_quant_conv``."""
+    ch = tuple(reversed(cfg.block_out_channels))
+    L = cfg.latent_channels
+    out: Dict[str, Tuple[int, ...]] = {}
+
+    def conv(name, cout, cin, k):
+        out[name + ".weight"], out[name + ".bias"] = (cout, cin, k, k), (cout,)
+
+    def vec(name, c):
+        out[name + ".weight"], out[name + ".bias"] = (c,), (c,)
+
+    def resnet(p, cin, cout):
+        vec(p + "norm1", cin)
+        conv(p + "conv1", cout, cin, 3)
+        vec(p + "norm2", cout)
+        conv(p + "conv2", cout, cout, 3)
+        if cin != cout:
+            conv(p + "conv_shortcut", cout, cin, 1)
+
+    conv("decoder.conv_in", ch[0], L, 3)
+    c = ch[0]
+    resnet("decoder.mid_block.resnets.0.", c, c)
+    resnet("decoder.mid_block.resnets.1.", c, c)
+    a = "decoder.mid_block.attentions.0."
+    vec(a + "group_norm", c)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        out[a + n + ".weight"], out[a + n + ".bias"] = (c, c), (c,)
+    cin = ch[0]
+    for i, c in enumerate(ch):
+        for j in range(cfg.layers_per_block + 1):
+            resnet(f"decoder.up_blocks.{i}.resnets.{j}.", cin if j == 0 else c, c)
+        if i != len(ch) - 1:
+            conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", c, c, 3)
+        cin = c
+    vec("decoder.conv_norm_out", ch[-1])
+    conv("decoder.conv_out", cfg.in_channels, ch[-1], 3)
+    conv("post_quant_conv", L, L, 1)
+    return out
+
+
 class _Resnet:
     def __init__(self, sd, p, groups):
         self.G = groups
@@ -258,6 +299,107 @@ class VAEEncoderEngine:
         return torch.cat(out).view(B, L, h, w)
 
 
+class _Up:
+    """diffusers Upsample2D: nearest-neighbour 2x, then conv3x3."""
+
+    def __init__(self, sd, p):
+        self.wk = _conv_fwd_weight(sd[p + "conv.weight"])
+        self.b = sd[p + "conv.bias"]
+
+    def forward(self, x):
+        return ops.conv3x3(ops.upsample2x(x), self.wk, bias=self.b)
+
+
+class VAEDecoderEngine:
+    """``vae.decode(latents / scaling_factor).sample`` + the image post-processing of StableDiffusionPipeline, forward
+    only: the last stage of the validation / inference sampler (train_textboost.py:512-513,
+    /root/reference/inference.py:99-105).  `sd` maps diffusers keys (decoder.*, post_quant_conv.*) to CUDA tensors.
+
+    post_quant_conv (1x1 over 4 channels) runs fused with the 1/scaling_factor and the fp16 cast in front of conv_in
+    (it cannot be folded into conv_in's weights: its bias would leak into the zero padding); conv_out (128 -> 3) is
+    zero-padded to 64 output channels for the tensor-core conv and only the first three columns are read back."""
+
+    PAD_OUT = 64
+
+    def __init__(self, cfg: VAEConfig, sd: Dict[str, torch.Tensor], max_chunk: int = 4):
+        self.cfg, self.max_chunk = cfg, max_chunk
+        G = cfg.norm_num_groups
+        ch = tuple(reversed(cfg.block_out_channels))
+        L = cfg.latent_channels
+        self.pq_w = sd["post_quant_conv.weight"].detach().to(F32).reshape(L, L).contiguous()
+        self.pq_b = sd["post_quant_conv.bias"].detach().to(F32).contiguous()
+        sd = {k[len("decoder."):]: v.detach().to(dtype=F16).contiguous() for k, v in sd.items()
+              if k.startswith("decoder.")}
+        self.conv_in_w, self.conv_in_b = sd["conv_in.weight"], sd["conv_in.bias"]
+        self.mid = (_Resnet(sd, "mid_block.resnets.0.", G), _MidAttention(sd, "mid_block.attentions.0.", G),
+                    _Resnet(sd, "mid_block.resnets.1.", G))
+        self.up = []
+        for i in range(len(ch)):
+            p = f"up_blocks.{i}."
+            res = [_Resnet(sd, f"{p}resnets.{j}.", G) for j in range(cfg.layers_per_block + 1)]
+            up = _Up(sd, f"{p}upsamplers.0.") if i != len(ch) - 1 else None
+            self.up.append((res, up))
+        self.norm_out = (sd["conv_norm_out.weight"], sd["conv_norm_out.bias"])
+        w = sd["conv_out.weight"]
+        w_pad = torch.zeros((self.PAD_OUT,) + tuple(w.shape[1:]), device=w.device, dtype=F16)
+        w_pad[:cfg.in_channels] = w
+        b_pad = torch.zeros(self.PAD_OUT, device=w.device, dtype=F16)
+        b_pad[:cfg.in_channels] = sd["conv_out.bias"]
+        self.out_w, self.out_b = _conv_fwd_weight(w_pad), b_pad
+
+    @property
+    def upscale(self) -> int:
+        return 2 ** (len(self.cfg.block_out_channels) - 1)
+
+    def _image_rows(self, latents, scaling_factor):
+        """latents fp32 [b,L,h,w] -> fp16 rows [b*H*W, PAD_OUT]; columns [0,3) are the image in [-1,1] (unclamped)."""
+        z = ops.vae_decode_in(latents, self.pq_w, self.pq_b, scaling_factor)
+        x = ops.conv_in(z, self.conv_in_w, self.conv_in_b)
+        r0, attn, r1 = self.mid
+        x = r1.forward(attn.forward(r0.forward(x)))
+        for res, up in self.up:
+            for r in res:
+                x = r.forward(x)
+            if up is not None:
+                x = up.forward(x)
+        h, _ = ops.groupnorm(x, *self.norm_out, self.cfg.norm_num_groups, _EPS, True)
+        return ops.conv3x3(h, self.out_w, bias=self.out_b).view(-1, self.PAD_OUT)
+
+    def _check(self, latents):
+        if latents.dim() != 4 or latents.shape[1] != self.cfg.latent_channels:
+            raise ValueError(f"expected latents [B,{self.cfg.latent_channels},h,w], got {tuple(latents.shape)}")
+        if not latents.is_cuda:
+            raise RuntimeError("VAEDecoderEngine runs on the CUDA device only (no CPU path)")
+
+    def _chunks(self, latents):
+        self._check(latents)
+        latents = latents.to(F32).contiguous()
+        for i in range(0, latents.shape[0], self.max_chunk):
+            yield latents[i:i + self.max_chunk]
+
+    def decode(self, z, scaling_factor: float = 1.0):
+        """diffusers ``vae.decode(z).sample`` for z = latents / scaling_factor (or pass latents and the factor):
+        fp16 [B,3,H,W], unclamped."""
+        f, Cimg = self.upscale, self.cfg.in_channels
+        out = []
+        for lat in self._chunks(z):
+            b, _, h, w = lat.shape
+            rows = self._image_rows(lat, scaling_factor)
+            out.append(rows[:, :Cimg].reshape(b, h * f, w * f, Cimg).permute(0, 3, 1, 2))
+        return torch.cat(out)
+
+    def decode_u8(self, latents):
+        """Scaled latents (as the sampler leaves them) -> uint8 [B,H,W,3] images: decode(latents / scaling_factor),
+        (x/2 + .5).clamp(0,1) * 255 rounded."""
+        f, Cimg = self.upscale, self.cfg.in_channels
+        out = []
+        for lat in self._chunks(latents):
+            b, _, h, w = lat.shape
+            rows = self._image_rows(lat, self.cfg.scaling_factor)
+            out.append(ops.image_u8(rows, rows.shape[0], Cimg).view(b, h * f, w * f, Cimg))
+        return torch.cat(out)
+
+
 # --------------------------------------------------------------------------------------------------------------
 # Host mirror of the slice of diffusers.AutoencoderKL the reference touches.
 class _Posterior:
@@ -295,6 +437,11 @@ class _EncoderOutput:
         self.latent_dist = latent_dist
 
 
+class _DecoderOutput:
+    def __init__(self, sample):
+        self.sample = sample
+
+
 class _Config(dict):
     __getattr__ = dict.__getitem__
 
@@ -306,8 +453,9 @@ class AutoencoderKL:
     def __init__(self, cfg: VAEConfig, state_dict: Dict[str, torch.Tensor]):
         self._cfg = cfg
         self.config = _Config(dataclasses.asdict(cfg))
-        self._sd = {k: v for k, v in state_dict.items() if k.startswith(("encoder.", "quant_conv."))}
+        self._sd = dict(state_dict)
         self.engine: Optional[VAEEncoderEngine] = None
+        self.decoder_engine: Optional[VAEDecoderEngine] = None
         self.dtype = torch.float32  # what callers cast pixel_values to (train_textboost.py:1027)
 
     @classmethod
@@ -337,10 +485,22 @@ class AutoencoderKL:
     def to(self, device=None, dtype=None):
         if device is not None and torch.device(device).type == "cuda":
             sd = {k: v.to(device) for k, v in self._sd.items()}
-            self.engine = VAEEncoderEngine(self._cfg, sd)
+            if "encoder.conv_in.weight" in sd:
+                self.engine = VAEEncoderEngine(self._cfg, sd)
+            if "decoder.conv_in.weight" in sd:
+                self.decoder_engine = VAEDecoderEngine(self._cfg, sd)
         return self
 
     def encode(self, pixel_values):
         if self.engine is None:
-            raise RuntimeError("AutoencoderKL.encode: call .to('cuda') first (no CPU path)")
+            raise RuntimeError("AutoencoderKL.encode: call .to('cuda') first (no CPU path), on a checkpoint that has "
+                               "the encoder weights")
         return _EncoderOutput(_Posterior(self.engine, pixel_values))
+
+    def decode(self, z, return_dict=True):
+        """``vae.decode(latents / scaling_factor)`` -> object with ``.sample`` fp16 [B,3,H,W] (or a 1-tuple)."""
+        if self.decoder_engine is None:
+            raise RuntimeError("AutoencoderKL.decode: call .to('cuda') first (no CPU path), on a checkpoint that has "
+                               "the decoder weights")
+        sample = self.decoder_engine.decode(z)
+        return _DecoderOutput(sample) if return_dict else (sample,)
