@@ -159,6 +159,7 @@ class ClipEngine:
         self.lnf = (g32("text_model.final_layer_norm.weight"), g32("text_model.final_layer_norm.bias"))
         self.null_embedding = torch.zeros((cfg.max_position_embeddings, D), device=self.device, dtype=F32)
         self.use_fixed_special = False
+        self.null_override = True  # False: plain CLIPTextModel forward (inference.py's pipeline), inference only
         self.decay = torch.ones(1, device=self.device, dtype=F32)  # lazy weight decay of frozen rows (D8)
         self._ctx = []  # saved forward contexts, most recent last (one per forward awaiting its backward)
 
@@ -211,8 +212,11 @@ class ClipEngine:
                 saved.append((x, st1, y_ext, qkv, x2, st2, u, o, lse))
             x = x3
         out, stf = ops.layernorm(x, *self.lnf, eps=self.cfg.layer_norm_eps, out_dtype=F32)
-        C.call("tb_null_override", C.ptr(ids), C.ptr(self.null_embedding), C.ptr(out), B, Lq, D, EOS_ID,
-               int(self.use_fixed_special), 0, s)
+        if self.null_override:
+            C.call("tb_null_override", C.ptr(ids), C.ptr(self.null_embedding), C.ptr(out), B, Lq, D, EOS_ID,
+                   int(self.use_fixed_special), 0, s)
+        elif save_for_backward:
+            raise NotImplementedError("training runs through TextBoostModel (null-embedding override on)")
         if save_for_backward:
             self._ctx.append((ids, saved, x, stf))
         return out.view(B, Lq, D)

@@ -120,6 +120,7 @@ class _Encoder:
 
 class TextBoostModel:
     config_class = ClipConfig
+    _null_override = True
 
     def __init__(self, config: ClipConfig, state_dict: Optional[Dict[str, torch.Tensor]] = None):
         self.config = config if isinstance(config, ClipConfig) else ClipConfig(**config)
@@ -341,6 +342,7 @@ class TextBoostModel:
                                   n_base=self._n_base, seed=self._seed)
         self._engine.null_embedding = self.null_embedding.to(device)
         self._engine.use_fixed_special = self._use_fixed_special_embedding
+        self._engine.null_override = self._null_override
         self._anchor = torch.zeros(1, device=device, dtype=F32, requires_grad=True)
         # host copies of what now lives in the engine's flat buffer would go stale: drop them
         for k in [k for k in self._sd if "lora_" in k]:
@@ -436,6 +438,15 @@ class TextBoostModel:
         return out if (return_dict if return_dict is not None else True) else tuple(out)
 
     __call__ = forward
+
+
+class CLIPTextModel(TextBoostModel):
+    """The stock ``transformers.CLIPTextModel`` surface of /root/reference/inference.py:46-58 (pipeline.text_encoder
+    + ``load_adapter`` / ``set_adapter``): the same engine without the null-embedding override, inference only."""
+    _null_override = False
+
+    def set_null_embedding(self, null_embedding):
+        raise AttributeError("CLIPTextModel has no null embedding: use TextBoostModel")
 
 
 def _save_tensors(sd, directory, stem, safe):

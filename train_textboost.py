@@ -18,7 +18,8 @@ Data: with ``--instance_data_dir`` / ``--concepts_list`` the 
 ``pixel_values`` -> the B200 AutoencoderKL encoder (textboost_b200.vae) -> latents, every step.  ``--latents_file``
 (a ``torch.save``d dict with ``latents`` [N,4,h,w] fp32 — already scaled by the VAE factor — ``input_ids`` [N,77]
 and optional ``prior_ids`` [P,77]) and ``--synthetic_data`` bypass it; both flags are additions, everything else is
-the reference's.  Out of scope (§8 f3): the validation sampler.
+the reference's.  ``--validation_prompts`` samples images every ``--validation_steps`` steps with the B200 sampler
+(textboost_b200.pipeline, §8 f3) and writes ``validation_<step>.jpg``.
 """
 from __future__ import annotations
 
@@ -136,8 +137,8 @@ def _unsupported(args):
         raise NotImplementedError("only the reference's constant LR schedule is built")
     if args.mixed_precision not in (None, "fp16"):
         raise NotImplementedError("the B200 path computes in fp16 with fp32 master weights (--mixed_precision fp16)")
-    if args.validation_prompts:
-        warnings.warn("validation sampling is out of scope (SURVEY.md §8 f3): --validation_prompts ignored")
+    if args.validation_prompts and args.validation_scheduler != "DPMSolverMultistepScheduler":
+        raise NotImplementedError("--validation_scheduler: only the default DPMSolverMultistepScheduler is built")
 
 
 def load_scheduler_config(path):
@@ -192,6 +193,28 @@ def build_image_batches(args, tokenizer, rank, world):
                                          num_workers=args.dataloader_num_workers)
     RUN_INFO["instance_images"] = len(dataset)
     return iter(loader)
+
+
+def log_validation(text_encoder, tokenizer, unet, vae, args, device, global_step):
+    """train_textboost.py:453-531: sample ``num_validation_images`` images per validation prompt with the modules being
+    trained (25 DPM-Solver++ steps, guidance 7.5); ``<i>`` in a prompt stands for concept i's placeholder tokens."""
+    from textboost_b200.pipeline import DiffusionPipeline, DPMSolverMultistepScheduler
+    logger.info(f"Running validation... \n Generating {args.num_validation_images} images with prompt:"
+                f" {args.validation_prompts}.")
+    pipeline = DiffusionPipeline.from_pretrained(args.pretrained_model_name_or_path, vae=vae, tokenizer=tokenizer,
+                                                 text_encoder=text_encoder, unet=unet, safety_checker=None,
+                                                 revision=args.revision, variant=args.variant)
+    pipeline.scheduler = DPMSolverMultistepScheduler.from_config(pipeline.scheduler.config)
+    pipeline.set_progress_bar_config(disable=True)
+    generator = None if args.seed is None else torch.Generator(device=device).manual_seed(args.seed)
+    images = []
+    for validation_prompt in args.validation_prompts:
+        for i, placeholder in enumerate(args.placeholder_token):
+            validation_prompt = validation_prompt.replace(f"<{i}>", " ".join(placeholder))
+        images.extend(pipeline(prompt=validation_prompt, num_images_per_prompt=args.num_validation_images,
+                               num_inference_steps=25, generator=generator).images)
+    RUN_INFO.setdefault("validation_steps", []).append(global_step)
+    return images
 
 
 def save_learned_embeddings(text_encoder, added_tokens, aug_token_dict, directory):
@@ -301,6 +324,7 @@ def main(args):
         placeholder_token_ids += ids
         added_tokens.update(dict(zip(toks, ids)))
         concept["instance_token"] = concept["placeholder_token"] = toks
+    args.placeholder_token = [c["placeholder_token"] for c in args.concepts_list]  # train_textboost.py:662-676
     aug_token_dict = {}
     if args.augment_inversion:
         _, aug_token_dict = add_augmentation_tokens(text_encoder, tokenizer,
@@ -442,6 +466,16 @@ def main(args):
             loss_val = loss.item()  # the reference syncs every step (:1230); here every --log_every steps
             logger.info(f"step {step} loss {loss_val:.6f} lr {args.learning_rate} "
                         f"added_embedding_norm {trainer.added_norm.item():.4f}")
+        if is_main and args.validation_prompts and step % args.validation_steps == 0:  # train_textboost.py:1213-1228
+            if vae is None or vae.decoder_engine is None:
+                from textboost_b200.vae import AutoencoderKL
+                vae = AutoencoderKL.from_pretrained(path, subfolder="vae", revision=args.revision,
+                                                    variant=args.variant).to(device, dtype=torch.float32)
+            images = log_validation(text_encoder, tokenizer, unet, vae, args, device, step)
+            if images:
+                from inference import make_image_grid
+                grid = make_image_grid(images, len(args.validation_prompts), args.num_validation_images)
+                grid.save(os.path.join(args.output_dir, f"validation_{step}.jpg"))
         if is_main and step % args.checkpointing_steps == 0:
             _rotate_checkpoints(args.output_dir, args.checkpoints_total_limit)
             ck = os.path.join(args.output_dir, f"checkpoint-{step}")
