@@ -1,6 +1,7 @@
-"""Generates tests/golden/cli_flags.json: the flag table of the reference CLI
-(/root/reference/train_textboost.py:49-428 ``parse_args``), extracted from its AST in this container
-(the module itself cannot be imported: accelerate / diffusers / peft are not installed).
+"""Generates tests/golden/cli_flags.json and inference_flags.json: the flag tables of the reference CLIs
+(/root/reference/train_textboost.py:49-428 ``parse_args`` and /root/reference/inference.py:21-43), extracted from
+their ASTs in this container (the modules themselves cannot be imported: accelerate / diffusers / peft are not
+installed).
 
     python tests/golden/make_cli_flags.py
 """
@@ -12,8 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = "/root/reference/train_textboost.py"
 
 
-def main():
-    tree = ast.parse(open(SRC).read())
+def extract(src):
+    tree = ast.parse(open(src).read())
     flags = {}
     for node in ast.walk(tree):
         if isinstance(node, ast.Call) and getattr(node.func, "attr", "") == "add_argument":
@@ -27,9 +28,17 @@ def main():
                 except ValueError:
                     spec[k.arg] = ast.unparse(k.value)  # type=str / int / float
             flags[name] = spec
+    return flags
+
+
+def main():
+    flags = extract(SRC)
     with open(os.path.join(HERE, "cli_flags.json"), "w") as f:
         json.dump({"source": "train_textboost.py:49-428", "flags": flags}, f, indent=1, sort_keys=True)
-    print(len(flags), "flags")
+    inf = extract("/root/reference/inference.py")
+    with open(os.path.join(HERE, "inference_flags.json"), "w") as f:
+        json.dump({"source": "inference.py:21-43", "flags": inf}, f, indent=1, sort_keys=True)
+    print(len(flags), "+", len(inf), "flags")
 
 
 if __name__ == "__main__":

@@ -156,3 +156,38 @@ def test_denoise_loop_matches_oracle_sampler(monkeypatch, guidance, steps):
         pipe.prepare_latents(3, 64, 64, "cpu", generator=gens[:2])
     with pytest.raises(ValueError):
         pipe.prepare_latents(3, 64, 64, "cpu", latents=torch.zeros(1, 4, 8, 8))
+
+
+def test_inference_cli_flags_match_reference_table(tmp_path):
+    """inference.py keeps the reference's positional argument and flags (tests/golden/inference_flags.json, extracted
+    from /root/reference/inference.py's AST); --num_inference_steps / --guidance_scale are additions."""
+    import argparse
+    import os
+    import inference as I
+    with open(os.path.join(os.path.dirname(__file__), "golden", "inference_flags.json")) as f:
+        gold = json.load(f)["flags"]
+    parser_actions = {}
+    real = argparse.ArgumentParser.add_argument
+
+    def spy(self, *names, **kw):
+        parser_actions[names[0]] = kw
+        return real(self, *names, **kw)
+
+    argparse.ArgumentParser.add_argument = spy
+    try:
+        a = I.parse_args(["some/dir"])
+    finally:
+        argparse.ArgumentParser.add_argument = real
+    for name, spec in gold.items():
+        kw = parser_actions[name]
+        for k, v in spec.items():
+            got = kw.get(k)
+            assert (got.__name__ if k == "type" else got) == v, (name, k, got, v)
+    assert set(parser_actions) - set(gold) == {"--num_inference_steps", "--guidance_scale", "-h"} - {"-h"}
+    assert a.path == "some/dir" and a.seeds == [0, 1, 2, 3] and a.prompt == "photo of a <dog> dog"
+    assert a.model == "stabilityai/stable-diffusion-2-1-base"  # short names map to hub ids (inference.py:15-20, 41-42)
+    d = tmp_path / "sd21base"
+    d.mkdir()
+    assert I.parse_args(["x", "--model", str(d)]).model == str(d)  # ... unless they are local directories
+    g = I.make_image_grid([__import__("PIL.Image").Image.new("RGB", (8, 6))] * 6, 2, 3)
+    assert g.size == (24, 12)
