@@ -19,9 +19,8 @@ with a same-shaped gradient buffer: that buffer is what the single NCCL all-redu
 """
 from __future__ import annotations
 
-import ctypes
 import dataclasses
-from typing import Dict, Optional, Sequence
+from typing import Dict, Optional
 
 import torch
 

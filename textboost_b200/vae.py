@@ -26,7 +26,6 @@ from typing import Dict, Optional, Tuple
 
 import torch
 
-from . import _cabi as C
 from . import ops
 from .unet import _Conv3, _Linear, _conv_fwd_weight
 
