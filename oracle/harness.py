@@ -115,7 +115,8 @@ def compare_step(trainer, batch: Dict[str, torch.Tensor], device="cpu", dtype=to
         b["prior_ids"] if use_kpl else None, n_base=V, kpl_weight=trainer.kpl_weight, kpl_type=kind,
         prediction_type="v_prediction" if trainer.v_pred else "epsilon",
         optimizer=opt if with_optimizer else None, max_grad_norm=trainer.max_grad_norm,
-        mixing=trainer.mixing, mean_norm=trainer.mean_norm)
+        mixing=trainer.mixing, mean_norm=trainer.mean_norm,
+        image_ppl_weight=getattr(trainer, "image_prior_weight", None))
     scale = trainer.opt_state[0].item()
     loss = trainer.forward_backward(batch["latents"], batch["noise"], batch["timesteps"], batch["input_ids"],
                                     batch["prior_ids"] if use_kpl else None)

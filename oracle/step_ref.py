@@ -4,6 +4,7 @@ Follows /root/reference/train_textboost.py line by line:
   :1041-1052  noise / timesteps / add_noise           (inputs here, so both samplers are testable)
   :1054-1067  encode_prompt -> unet(...).sample
   :1070-1075  target (epsilon | v_prediction)
+  :1077-1094  --with_image_prior: [instance | class] halves, loss = mse(instance) + image_ppl_weight * mse(class)
   :1085-1090  loss = mse(pred.float(), target.float()).mean()
   :1096-1106  knowledge-preservation loss (cos | mse) on the prior prompts, weight kpl_weight
   :1108       backward
@@ -30,8 +31,9 @@ def lora_named_parameters(te):
 
 
 def forward_loss(unet, te, te0, latents, noise, timesteps, input_ids, prior_ids=None, kpl_weight=0.1,
-                 kpl_type="cos", prediction_type="epsilon"):
-    """Returns (loss, model_pred, encoder_hidden_states)."""
+                 kpl_type="cos", prediction_type="epsilon", image_ppl_weight=None):
+    """Returns (loss, model_pred, encoder_hidden_states).  image_ppl_weight (not None = --with_image_prior,
+    :1077-1094): the batch is [instance | class] halves, loss = mse(instance) + image_ppl_weight * mse(class)."""
     noisy = ddpm_ref.add_noise(latents, noise, timesteps)
     ehs = te(input_ids)
     pred = unet(noisy, timesteps, ehs)
@@ -41,7 +43,13 @@ def forward_loss(unet, te, te0, latents, noise, timesteps, input_ids, prior_ids=
         target = ddpm_ref.get_velocity(latents, noise, timesteps)
     else:
         raise ValueError(prediction_type)
-    loss = F.mse_loss(pred.float(), target.float(), reduction="none").mean()
+    if image_ppl_weight is not None:
+        pred_i, pred_c = torch.chunk(pred, 2, dim=0)
+        target_i, target_c = torch.chunk(target, 2, dim=0)
+        prior_loss = F.mse_loss(pred_c.float(), target_c.float(), reduction="mean")
+        loss = F.mse_loss(pred_i.float(), target_i.float(), reduction="none").mean() + image_ppl_weight * prior_loss
+    else:
+        loss = F.mse_loss(pred.float(), target.float(), reduction="none").mean()
     if kpl_weight > 0.0 and prior_ids is not None:
         h = te(prior_ids).float()
         with torch.no_grad():
@@ -57,7 +65,7 @@ def forward_loss(unet, te, te0, latents, noise, timesteps, input_ids, prior_ids=
 def reference_step(unet, te, te0, latents, noise, timesteps, input_ids, prior_ids=None, *,
                    n_base: int, kpl_weight=0.1, kpl_type="cos", prediction_type="epsilon",
                    optimizer: Optional[torch.optim.Optimizer] = None, max_grad_norm=1.0, mixing=None,
-                   mean_norm: Optional[float] = None) -> Dict[str, torch.Tensor]:
+                   mean_norm: Optional[float] = None, image_ppl_weight=None) -> Dict[str, torch.Tensor]:
     """Runs forward + backward (+ the optimiser tail when `optimizer` is given).
 
     n_base = min(added_token_ids): rows below it never train.  Returns loss, pred, d(ehs) and the
@@ -68,7 +76,7 @@ def reference_step(unet, te, te0, latents, noise, timesteps, input_ids, prior_id
         p.grad = None
     emb.grad = None
     loss, pred, ehs = forward_loss(unet, te, te0, latents, noise, timesteps, input_ids, prior_ids,
-                                   kpl_weight, kpl_type, prediction_type)
+                                   kpl_weight, kpl_type, prediction_type, image_ppl_weight)
     ehs.retain_grad()
     loss.backward()
     if emb.grad is not None:

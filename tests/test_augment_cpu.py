@@ -138,3 +138,32 @@ def test_cli_image_batches_shapes_sharding_and_determinism(tmp_path):
     with __import__("pytest").raises(NotImplementedError):
         batches(0, 1, 1, ("--augment", "custom_diff"))
     random.seed(0)
+
+
+def test_cli_image_batches_with_image_prior(tmp_path):
+    """--with_image_prior: class examples are appended after the instance ones ([2B, ...]), prompts from the class
+    token through the same template draw (dataset.py:393-418, 420-459)."""
+    import train_textboost as T
+    from textboost_b200.synthetic import LiteralTokenizer
+    inst, cls = tmp_path / "dog", tmp_path / "class"
+    inst.mkdir()
+    cls.mkdir()
+    for i in range(2):
+        G.make_image((70 + 10 * i, 64), i).save(inst / f"{i}.png")
+    for i in range(3):
+        G.make_image((64, 72), 10 + i).save(cls / f"{i}-a_photo_of_dog.png")
+    args = T.parse_args(["--pretrained_model_name_or_path", "x", "--instance_data_dir", str(inst), "--resolution", "32",
+                         "--train_batch_size", "2", "--with_image_prior", "--class_data_dir", str(cls),
+                         "--class_token", "dog", "--template", "a {}", "--seed", "1"])
+    args.concepts_list = [{"instance_token": "<dog>", "instance_data_dir": str(inst)}]
+    G.seed_all(1)
+    b = next(T.build_image_batches(args, LiteralTokenizer(), 0, 1))
+    assert b["pixel_values"].shape == (4, 3, 32, 32) and b["input_ids"].shape == (4, 77)
+    assert len(b["attention_mask"]) == 4
+    tok = LiteralTokenizer()
+    assert b["input_ids"][0].tolist() == tok("a <dog>").input_ids[0].tolist()
+    # --class_token is nargs="+" in the reference (train_textboost.py:96-101), so the class prompt formats a LIST
+    assert b["input_ids"][2].tolist() == b["input_ids"][3].tolist() == tok("a ['dog']").input_ids[0].tolist()
+    with __import__("pytest").raises(ValueError):
+        T._unsupported(T.parse_args(["--pretrained_model_name_or_path", "x", "--with_image_prior", "--class_data_dir",
+                                     str(cls), "--class_token", "dog", "--synthetic_data"]))

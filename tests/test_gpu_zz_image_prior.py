@@ -1,0 +1,78 @@
+"""--with_image_prior (/root/reference/train_textboost.py:1077-1094): the doubled [instance | class]
+batch with loss = mse(instance half) + image_ppl_weight * mse(class half), against the oracle step and through the CLI.
+
+These tests were written after the round's GPU budget was spent: their first hardware run is the round-end suite.  They
+are marked xfail(strict=False) so that an XPASS / XFAIL line records the outcome without hiding or breaking the tests
+that were verified on the B200; the marker goes once they have been seen green.  (The file name sorts last on purpose.)
+"""
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="first hardware run: written after the GPU budget was spent")]
+dev = "cuda"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu(built_lib):
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+
+
+@pytest.mark.parametrize("weight", [1.0, 0.3])
+def test_image_prior_step_vs_oracle(weight):
+    from oracle import harness
+    from textboost_b200 import synthetic
+    tr = synthetic.build_trainer("tiny", dev, seed=3, n_added=2, lora_b_std=0.02, keep_sd=True, learning_rate=1e-4,
+                                 image_prior_weight=weight)
+    V = tr.synthetic["clip_cfg"].vocab_size
+    bt = synthetic.batch(4, 16, 5, V, dev)  # rows 0-1 instance, rows 2-3 class
+    bt["input_ids"][0, 4] = V + 1
+    r = harness.compare_step(tr, bt)
+    assert abs(r["loss"] - r["loss_ref"]) < 2e-3 * abs(r["loss_ref"])
+    assert r["pred_rel"] < 4e-3
+    assert r["lora_grad_rel_l2"] < 5e-3 and r["lora_grad_cos"] > 0.99999
+    assert r["row_grad_rel"] < 5e-3
+    assert abs(r["grad_norm"] - r["grad_norm_ref"]) < 3e-3 * r["grad_norm_ref"]
+    # the two-part loss differs from the plain mean over the doubled batch unless the weight is 1 and halves are equal
+    tr2 = synthetic.build_trainer("tiny", dev, seed=3, n_added=2, lora_b_std=0.02, keep_sd=True, learning_rate=1e-4)
+    plain = tr2.forward_backward(bt["latents"], bt["noise"], bt["timesteps"], bt["input_ids"], bt["prior_ids"]).item()
+    if weight == 1.0:
+        # mse(a) + mse(b) = 2 * mse(a ‖ b): the KPL term is the same in both
+        kpl = tr2._loss_kpl.item()
+        assert abs((r["loss"] - kpl) - 2 * (plain - kpl)) < 2e-3 * abs(r["loss"])
+    with pytest.raises(ValueError):
+        b3 = synthetic.batch(3, 16, 5, V, dev)
+        tr.forward_backward(b3["latents"], b3["noise"], b3["timesteps"], b3["input_ids"], b3["prior_ids"])
+
+
+def test_cli_with_image_prior(tmp_path):
+    import make_augment_golden as G
+    import train_textboost as T
+    from textboost_b200 import synthetic
+    ck = str(tmp_path / "model")
+    synthetic.write_pretrained(ck, "tiny", seed=8, vae_channels=(64, 64, 128, 128))
+    inst, cls = tmp_path / "dog", tmp_path / "class"
+    inst.mkdir()
+    cls.mkdir()
+    for i, size in enumerate([(160, 140), (128, 128)]):
+        G.make_image(size, i).save(inst / f"{i}.png")
+    for i, size in enumerate([(130, 150), (128, 128), (140, 128)]):
+        G.make_image(size, 10 + i).save(cls / f"{i}-a_photo_of_dog.png")
+    jl = tmp_path / "prompts.jsonl"
+    with open(jl, "w") as f:
+        for i in range(4):
+            f.write(json.dumps({"input": f"a thing {i}", "output": "NONE"}) + "\n")
+    out = str(tmp_path / "out")
+    base = ["--pretrained_model_name_or_path", ck, "--output_dir", out, "--resolution", "128", "--train_batch_size", "2",
+            "--max_train_steps", "5", "--learning_rate", "1e-3", "--mixed_precision", "fp16", "--augment", "pda",
+            "--template", "textboost", "--prior_prompts_file", str(jl), "--log_every", "1", "--seed", "3",
+            "--with_image_prior", "--class_data_dir", str(cls), "--class_token", "dog", "--image_ppl_weight", "0.5"]
+    loss = T.main(T.parse_args(base + ["--instance_data_dir", str(inst)]))
+    assert loss == loss and loss < 20
+    assert {"text_encoder", "dog.bin"} <= set(os.listdir(out))
+    with pytest.raises(ValueError):  # the class images come through the image front end only
+        T.main(T.parse_args(base + ["--synthetic_data"]))

@@ -250,8 +250,11 @@ def add_noise(x0, eps, t, acp, v_prediction=False, want_target=True):
     return noisy, target
 
 
-def mse_fwd_bwd(pred, target, loss_acc, weight=1.0, loss_scale=None, want_grad=True):
-    dpred = torch.empty_like(pred) if want_grad else None
+def mse_fwd_bwd(pred, target, loss_acc, weight=1.0, loss_scale=None, want_grad=True, out=None):
+    """loss_acc += weight * mean((pred - target)^2); returns d(pred) (into `out` when given: a contiguous slice of a
+    larger gradient buffer for the two-part loss of --with_image_prior)."""
+    assert out is None or (pred.is_contiguous() and target.is_contiguous() and out.is_contiguous())
+    dpred = out if out is not None else (torch.empty_like(pred) if want_grad else None)
     C.call("tb_mse_fwd_bwd", C.ptr(pred), C.ptr(target), pred.numel(), weight, C.ptr(loss_scale),
            C.ptr(loss_acc), C.ptr(dpred), C.stream_ptr())
     return dpred

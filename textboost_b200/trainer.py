@@ -49,8 +49,11 @@ class TextBoostTrainer:
                  emb_learning_rate=1e-3, adam_beta1=0.9, adam_beta2=0.999, adam_weight_decay=1e-2,
                  adam_epsilon=1e-8, max_grad_norm=1.0, kpl_weight=0.1, kpl_type="cos",
                  prediction_type="epsilon", mixing=None, mean_norm: Optional[float] = None,
-                 mixed_precision="fp16", process_group=None):
+                 mixed_precision="fp16", process_group=None, image_prior_weight: Optional[float] = None):
         self.unet, self.te, self.te0 = unet, text_encoder, original_text_encoder
+        # --with_image_prior (train_textboost.py:1077-1094): the batch is [instance | class] halves and the loss is
+        # mse(instance half) + image_prior_weight * mse(class half); None = the plain single-part loss
+        self.image_prior_weight = image_prior_weight
         self.dev = text_encoder.device
         self.kpl_weight, self.kpl_kind = kpl_weight, {"cos": 0, "mse": 1}[kpl_type]
         self.v_pred = {"epsilon": False, "v_prediction": True}[prediction_type]
@@ -116,7 +119,16 @@ class TextBoostTrainer:
         _, L, D = h.shape
         ehs = ops.cast_f32_f16(h.view(B * L, D)).view(B, L, D)
         pred = unet.forward(noisy, timesteps, ehs)
-        dpred = ops.mse_fwd_bwd(pred, target, self.loss, 1.0, scale)
+        if self.image_prior_weight is None:
+            dpred = ops.mse_fwd_bwd(pred, target, self.loss, 1.0, scale)
+        else:
+            if B % 2:
+                raise ValueError("with an image prior the batch is [instance | class] halves: even batch size")
+            half = B // 2
+            dpred = torch.empty_like(pred)
+            ops.mse_fwd_bwd(pred[:half], target[:half], self.loss, 1.0, scale, out=dpred[:half])
+            ops.mse_fwd_bwd(pred[half:], target[half:], self.loss, float(self.image_prior_weight), scale,
+                            out=dpred[half:])
         d_h = torch.zeros((B, L, D), device=self.dev, dtype=F32)
         unet.backward(dpred, d_h)
         if use_kpl:

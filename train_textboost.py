@@ -125,8 +125,9 @@ def parse_args(input_args=None):
 # ------------------------------------------------------------------------------------ helpers
 def _unsupported(args):
     """Modes of the reference CLI outside the hot path built here: fail loudly."""
-    if args.with_image_prior:
-        raise NotImplementedError("--with_image_prior (image prior batch) is not built (SURVEY.md §8 f4)")
+    if args.with_image_prior and (args.latents_file or args.synthetic_data):
+        raise ValueError("--with_image_prior takes its class images from --class_data_dir through the image front "
+                         "end: it cannot be combined with --latents_file / --synthetic_data")
     if args.unet_params_to_train != "none":
         raise NotImplementedError("--unet_params_to_train: the UNet is frozen on this path (SURVEY.md §8 f4)")
     if args.lora_rank <= 0:
@@ -169,7 +170,8 @@ def load_tokenizer(args):
 def build_image_batches(args, tokenizer, rank, world):
     """The reference's train dataloader (train_textboost.py:856-890): PairedAugmentation -> TextBoostDataset ->
     Wrapper(drop_last=False).shuffle(seed).repeat() sharded by rank -> DataLoader(batch_size, collate_fn).  Returns an
-    endless iterator of {"pixel_values" [B,3,S,S] fp32 in [-1,1], "input_ids" [B,L], "attention_mask"}."""
+    endless iterator of {"pixel_values" [B,3,S,S] fp32 in [-1,1], "input_ids" [B,L], "attention_mask"}; with
+    --with_image_prior the class examples follow the instance ones in the same batch ([2B, ...])."""
     from textboost_b200.dataset import TextBoostDataset, Wrapper
     if args.augment in ("pda", "paug"):
         from textboost_b200.augment import PairedAugmentation
@@ -182,14 +184,16 @@ def build_image_batches(args, tokenizer, rank, world):
     else:
         augment_pipe = None
     dataset = TextBoostDataset(concepts_list=args.concepts_list, tokenizer=tokenizer, num_instance=args.num_samples,
-                               template=args.template, prior_data_root=None, class_token=args.class_token,
+                               template=args.template,
+                               prior_data_root=args.class_data_dir if args.with_image_prior else None,
+                               class_token=args.class_token,
                                num_prior=args.num_prior_images, size=args.resolution, center_crop=args.center_crop,
                                augment_pipe=augment_pipe)
     if len(dataset) == 0:
         raise ValueError("no instance images found")
     stream = Wrapper(dataset, drop_last=False, rank=rank, world_size=world).shuffle(seed=args.seed).repeat()
     loader = torch.utils.data.DataLoader(stream, batch_size=args.train_batch_size,
-                                         collate_fn=lambda ex: TextBoostDataset.collate_fn(ex, False),
+                                         collate_fn=lambda ex: TextBoostDataset.collate_fn(ex, args.with_image_prior),
                                          num_workers=args.dataloader_num_workers)
     RUN_INFO["instance_images"] = len(dataset)
     return iter(loader)
@@ -355,7 +359,8 @@ def main(args):
         max_grad_norm=args.max_grad_norm, kpl_weight=args.kpl_weight, kpl_type=args.kpl_type,
         prediction_type=sched["prediction_type"],
         mixing=("style" if args.augment_ops == "style" else "object") if args.mixing else None,
-        mean_norm=mean_norm, mixed_precision=args.mixed_precision or "fp16")
+        mean_norm=mean_norm, mixed_precision=args.mixed_precision or "fp16",
+        image_prior_weight=args.image_ppl_weight if args.with_image_prior else None)
 
     # ---- data: the image front end (dataset -> augmentation -> VAE encoder), a latents file, or synthetic latents
     B = args.train_batch_size
@@ -436,10 +441,11 @@ def main(args):
             idx = idx[rank * B:(rank + 1) * B]
             lat, ids = lat_all[idx], ids_all[idx]
         noise = torch.randn(lat.shape, generator=gen, device=device)
+        bsz = lat.shape[0]  # 2B with --with_image_prior (train_textboost.py:1045)
         if p_t is None:
-            t = torch.randint(0, T, (B,), generator=gen, device=device)
+            t = torch.randint(0, T, (bsz,), generator=gen, device=device)
         else:
-            t = torch.multinomial(p_t, B, replacement=True, generator=gen)
+            t = torch.multinomial(p_t, bsz, replacement=True, generator=gen)
         pri = None
         if prior_stream is not None:
             pri = next(prior_stream).to(device, non_blocking=True)
