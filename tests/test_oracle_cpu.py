@@ -250,3 +250,22 @@ def test_vae_encoder_oracle_structure():
         z = small.encode_latents(x, eps)
     assert mean.shape == (2, 4, 8, 8) and (std > 0).all()
     torch.testing.assert_close(z, (mean + std * eps) * 0.18215)
+
+
+def test_image_prior_loss_semantics():
+    """--with_image_prior (train_textboost.py:1077-1094): the batch is [instance | class] halves and
+    loss = mse(instance) + image_ppl_weight * mse(class); with weight 1 that is twice the plain mean over the batch,
+    with weight 0 the class half gets no gradient at all."""
+    unet, te, te0, ccfg = _tiny_step_models()
+    V = ccfg.vocab_size
+    lat, noise, t, ids, pr = _tiny_batch(4, V)
+    plain, pred, _ = step_ref.forward_loss(unet, te, te0, lat, noise, t, ids, None, kpl_weight=0.0)
+    both, _, _ = step_ref.forward_loss(unet, te, te0, lat, noise, t, ids, None, kpl_weight=0.0, image_ppl_weight=1.0)
+    torch.testing.assert_close(both, 2 * plain, rtol=1e-5, atol=0)
+    w = 0.3
+    mixed, _, _ = step_ref.forward_loss(unet, te, te0, lat, noise, t, ids, None, kpl_weight=0.0, image_ppl_weight=w)
+    want = ((pred[:2] - noise[:2]) ** 2).mean() + w * ((pred[2:] - noise[2:]) ** 2).mean()
+    torch.testing.assert_close(mixed, want, rtol=1e-5, atol=0)
+    out = step_ref.reference_step(unet, te, te0, lat, noise, t, ids, None, n_base=V, kpl_weight=0.0,
+                                  image_ppl_weight=0.0)
+    assert out["d_ehs"][:2].abs().max() > 0 and out["d_ehs"][2:].abs().max() == 0
