@@ -201,6 +201,22 @@ int tb_vae_decode_in(const float* latents, const float* w, const float* bias, vo
  * channels-last rows with stride ld. */
 int tb_image_u8(const void* x_f16, int64_t ld, void* out_u8, int64_t npix, int channels, void* stream);
 
+/* ---- image front end (TextBoostDataset's Resize(LANCZOS) -> crop -> ToImage/ToDtype/Normalize,
+ * /root/reference/textboost/dataset.py:326-351, 386-388), byte-exact on a decoded uint8 image resident in HBM. ---- */
+/* Pillow's antialiased 8-bit resize (src/libImaging/Resample.c: horizontal then vertical pass, 22-bit fixed-point
+ * weights, uint8 intermediate) of src [src_h, src_w, channels] to out_w x out_h, restricted to the crop window
+ * [top, top+crop_h) x [left, left+crop_w) of the resized image, then out = ((float)byte * scale - mean) / std as fp32
+ * [channels, crop_h, crop_w] (scale = (float)(1/255.0): torchvision ToDtype; mean = std = 0.5: Normalize) and / or the
+ * cropped bytes [crop_h, crop_w, channels].  bounds_* int32 [out, 2] = (first input index, tap count) and kk_* int32
+ * [out, ksize] are the weight tables of each axis, computed on the host in double precision exactly as Pillow's
+ * precompute_coeffs / normalize_coeffs_8bpc.  [row0, row0+nrows) = source rows the crop window's vertical taps touch;
+ * mid_u8 = caller-owned scratch of nrows * crop_w * channels bytes. */
+int tb_resize_crop_normalize_u8(const void* src_u8, int src_h, int src_w, int channels, const int32_t* bounds_x,
+                                const int32_t* kk_x, int ksize_x, int out_w, const int32_t* bounds_y,
+                                const int32_t* kk_y, int ksize_y, int out_h, int row0, int nrows, int top, int left,
+                                int crop_h, int crop_w, float scale, float mean, float std, void* mid_u8,
+                                float* out_f32_chw, void* out_u8_hwc, void* stream);
+
 /* ---- CLIP text encoder pieces that are not GEMM / LayerNorm ------------------------------------
  * (transformers CLIPTextTransformer called from textboost/text_encoder.py:62-69; peft LoRA Linear
  * configured at train_textboost.py:702-709.) */
