@@ -1,0 +1,93 @@
+"""Byte-exact GPU image tail: tb_resize_crop_normalize_u8 against Pillow + torchvision themselves
+(the installed libraries travel with the image) — identical bytes after the resize, identical float bits after the
+normalisation — and the training CLI with --gpu_image_transforms.
+
+Written after the round's GPU budget was spent: first hardware run is the round-end suite, hence xfail(strict=False)
+(see tests/test_gpu_zz_image_prior.py); the arithmetic and indexing are pinned on the CPU by tests/test_resample_cpu.py.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="first hardware run: written after the GPU budget was spent")]
+dev = "cuda"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu(built_lib):
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+
+
+@pytest.mark.parametrize("w,h,size,center", [(90, 70, 32, False), (70, 90, 32, True), (64, 64, 64, False),
+                                             (1024, 768, 512, False), (700, 1000, 512, True), (300, 300, 512, False)])
+def test_kernel_equals_pillow_and_torchvision_bitwise(w, h, size, center):
+    from PIL import Image
+    from torchvision.transforms import v2
+    from textboost_b200 import image_ops
+    a = np.random.RandomState(w + h).randint(0, 256, (h, w, 3), dtype=np.uint8)
+    resized = v2.Resize(size, interpolation=v2.InterpolationMode.LANCZOS)(Image.fromarray(a))
+    if center:
+        top = max(0, int(round((resized.height - size) / 2.0)))
+        left = max(0, int(round((resized.width - size) / 2.0)))
+    else:
+        torch.manual_seed(w)
+        top, left, _, _ = v2.RandomCrop.get_params(resized, (size, size))
+    window = v2.functional.crop(resized, top, left, size, size)
+    want = v2.Compose([v2.ToImage(), v2.ToDtype(torch.float, scale=True), v2.Normalize((0.5,) * 3, (0.5,) * 3)])(window)
+    got = image_ops.resize_crop_normalize(torch.from_numpy(a).to(dev), image_ops.shorter_side_size(w, h, size),
+                                          top, left, size, size)
+    assert got.shape == (3, size, size) and got.dtype == torch.float32
+    assert torch.equal(got.cpu(), want)
+
+
+def test_batch_to_pixel_values_matches_host_dataset(tmp_path):
+    import make_augment_golden as G
+    from textboost_b200 import augment, dataset, image_ops
+    from textboost_b200.synthetic import LiteralTokenizer
+    inst, _, _ = G.write_image_dirs(str(tmp_path))
+    concepts = [{"instance_data_dir": inst, "instance_token": "<sks> dog"}]
+
+    def batch(device_transforms):
+        ds = dataset.TextBoostDataset(concepts, LiteralTokenizer(), template="textboost", size=32,
+                                      augment_pipe=augment.PairedAugmentation(**G.PIPES[2]),
+                                      device_transforms=device_transforms, cache_decoded=device_transforms)
+        G.seed_all(4)
+        return dataset.TextBoostDataset.collate_fn([ds[i] for i in range(5)], False)
+
+    host, devb = batch(False), batch(True)
+    px = image_ops.batch_to_pixel_values(devb["sources"], dev)
+    assert torch.equal(px.cpu(), host["pixel_values"]) and torch.equal(host["input_ids"], devb["input_ids"])
+
+
+def test_cli_with_gpu_image_transforms(tmp_path):
+    import make_augment_golden as G
+    import train_textboost as T
+    from textboost_b200 import synthetic
+    ck = str(tmp_path / "model")
+    synthetic.write_pretrained(ck, "tiny", seed=12, vae_channels=(64, 64, 128, 128))
+    imgs = tmp_path / "dog"
+    imgs.mkdir()
+    for i, size in enumerate([(160, 140), (128, 128), (150, 200)]):
+        G.make_image(size, i).save(imgs / f"{i}.png")
+    jl = tmp_path / "prompts.jsonl"
+    with open(jl, "w") as f:
+        for i in range(4):
+            f.write(json.dumps({"input": f"a thing {i}", "output": "NONE"}) + "\n")
+
+    def run(out, extra):
+        return T.main(T.parse_args([
+            "--pretrained_model_name_or_path", ck, "--output_dir", str(tmp_path / out), "--instance_data_dir",
+            str(imgs), "--resolution", "128", "--train_batch_size", "2", "--max_train_steps", "5", "--learning_rate",
+            "1e-3", "--mixed_precision", "fp16", "--augment", "pda", "--augment_inversion", "--template", "textboost",
+            "--prior_prompts_file", str(jl), "--log_every", "1", "--seed", "21", *extra]))
+
+    loss_gpu = run("a", ["--gpu_image_transforms"])
+    loss_host = run("b", [])
+    assert loss_gpu == loss_gpu and os.path.exists(tmp_path / "a" / "dog.bin")
+    # same seeds, same pixels, same latents noise stream: the two runs agree to the step's run-to-run noise
+    assert abs(loss_gpu - loss_host) < 2e-2 * abs(loss_host)

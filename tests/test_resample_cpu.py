@@ -108,3 +108,48 @@ def test_kernel_arithmetic_equals_torchvision_pipeline_bitwise(w, h, size, cente
     got, u8 = kernel_standin(a, image_ops.shorter_side_size(w, h, size), top, left, size, size)
     assert np.array_equal(u8, np.asarray(window))
     assert torch.equal(torch.from_numpy(got), want)
+
+
+@pytest.mark.parametrize("center_crop,with_aug,prior", [(False, True, False), (True, False, False), (False, True, True)])
+def test_dataset_device_transforms_mode_is_the_same_data(tmp_path, center_crop, with_aug, prior):
+    """TextBoostDataset(device_transforms=True): same prompts, same crop positions, same random-stream state, and the
+    kernel arithmetic applied to its "source" + geometry gives the host mode's "image" bit for bit."""
+    import random
+    import make_augment_golden as G
+    from textboost_b200 import augment, dataset
+    from textboost_b200.synthetic import LiteralTokenizer
+    inst, inst2, cls = G.write_image_dirs(str(tmp_path))
+    concepts = [{"instance_data_dir": inst, "instance_token": "<sks> dog"}]
+
+    def items(device_transforms, cache):
+        pipe = augment.PairedAugmentation(**G.PIPES[2]) if with_aug else None
+        ds = dataset.TextBoostDataset(concepts, LiteralTokenizer(), template="textboost", size=32,
+                                      center_crop=center_crop, augment_pipe=pipe, class_token="dog",
+                                      prior_data_root=cls if prior else None, augment_prior=prior and with_aug,
+                                      device_transforms=device_transforms, cache_decoded=cache)
+        G.seed_all(9)
+        out = [ds[i] for i in range(6)]
+        return out, (float(np.random.random()), random.random(), float(torch.rand(1))), ds
+
+    host, draws_h, _ = items(False, False)
+    devi, draws_d, ds = items(True, True)
+    assert draws_h == draws_d
+    for a, b in zip(host, devi):
+        assert "image" not in b and b["source"].dtype == torch.uint8 and b["source"].shape[2] == 3
+        assert a["crop_top_left"] == b["crop_top_left"] and a["original_size"] == b["original_size"]
+        assert torch.equal(a["input_ids"], b["input_ids"]) and b["crop_size"] == 32
+        top, left = b["crop_top_left"]
+        got, _ = kernel_standin(b["source"].numpy(), b["resize_to"], top, left, 32, 32)
+        assert torch.equal(torch.from_numpy(got), a["image"])
+        if prior:
+            top, left = b["class_crop_top_left"]
+            got, _ = kernel_standin(b["class_source"].numpy(), b["class_resize_to"], top, left, 32, 32)
+            assert torch.equal(torch.from_numpy(got), a["class_image"])
+            assert torch.equal(a["class_input_ids"], b["class_input_ids"])
+    batch = dataset.TextBoostDataset.collate_fn(devi[:2], prior)
+    assert "pixel_values" not in batch and len(batch["sources"]) == (4 if prior else 2)
+    assert batch["input_ids"].shape == (4 if prior else 2, 77)
+    assert set(batch["sources"][0]) == {"source", "resize_to", "crop_top_left", "crop_size"}
+    if prior:
+        assert torch.equal(batch["sources"][2]["source"], devi[0]["class_source"])
+    assert len(ds._decoded) == 3  # each file decoded once

@@ -48,8 +48,15 @@ def _open_rgb(path) -> Image.Image:
 class TextBoostDataset(torch.utils.data.Dataset):
     def __init__(self, concepts_list: Sequence[dict], tokenizer, tokenizer_2=None, num_instance=None, template="a {}",
                  prior_data_root=None, class_token=None, num_prior=None, size=512, center_crop=False,
-                 augment_pipe=None, augment_prior: bool = False):
+                 augment_pipe=None, augment_prior: bool = False, device_transforms: bool = False,
+                 cache_decoded: bool = False):
+        """device_transforms (addition): stop after the augmentation and return the uint8 image ("source" [H,W,3]) with
+        the resize / crop geometry ("resize_to", "crop_top_left", "crop_size") instead of "image"; the byte-exact GPU
+        tail (textboost_b200.image_ops) produces the same ``pixel_values``.  The random streams are consumed exactly
+        as without it.  cache_decoded (addition): keep the decoded RGB source images (a handful in this workload)
+        instead of re-opening the files for every item; the pixels are the same."""
         self.size, self.center_crop = size, center_crop
+        self.device_transforms, self._decoded = device_transforms, ({} if cache_decoded else None)
         self.tokenizer, self.tokenizer_2 = tokenizer, tokenizer_2
         self.template = resolve_template(template)
         self.instance_images_path = [(path, concept["instance_token"]) for concept in concepts_list
@@ -73,6 +80,37 @@ class TextBoostDataset(torch.utils.data.Dataset):
 
     def __len__(self):
         return self._length
+
+    def _open(self, path):
+        if self._decoded is None:
+            return _open_rgb(path)
+        if path not in self._decoded:
+            self._decoded[path] = _open_rgb(path)
+            self._decoded[path].load()
+        return self._decoded[path].copy()
+
+    def _geometry(self, image):
+        """What `_resize_and_crop_image` would do to `image`, without doing it: (resized (w, h), top, left), drawing the
+        random crop position from torch's RNG exactly as RandomCrop.get_params does on the resized image."""
+        from .image_ops import shorter_side_size
+        w, h = shorter_side_size(image.width, image.height, self.size)
+        if self.center_crop:
+            return (w, h), max(0, int(round((h - self.size) / 2.0))), max(0, int(round((w - self.size) / 2.0)))
+        top, left, _, _ = self.crop.get_params(torch.empty((3, h, w), dtype=torch.uint8), (self.size, self.size))
+        return (w, h), top, left
+
+    def _finish(self, sample, image, prefix=""):
+        """Resize / crop / normalise on the host (reference behaviour) or record the geometry for the GPU tail."""
+        if not self.device_transforms:
+            image, top, left = self._resize_and_crop_image(image)
+            sample["class_image" if prefix else "image"] = self.image_transforms(image)
+            sample[prefix + "crop_top_left"] = (top, left)
+            return
+        import numpy as np
+        resize_to, top, left = self._geometry(image)
+        sample[prefix + "source"] = torch.from_numpy(np.array(image, dtype=np.uint8))  # [H, W, 3], writable copy
+        sample[prefix + "resize_to"], sample[prefix + "crop_size"] = resize_to, self.size
+        sample[prefix + "crop_top_left"] = (top, left)
 
     def _resize_and_crop_image(self, image):
         """Shorter side to `size` (Lanczos), then a `size` x `size` window: centred, or at a position drawn from
@@ -101,15 +139,13 @@ class TextBoostDataset(torch.utils.data.Dataset):
     def __getitem__(self, index):
         sample = {}
         path, instance_token = self.instance_images_path[index % self.num_instance_images]
-        image = _open_rgb(path)
+        image = self._open(path)
         which = random.randint(0, len(self.template) - 1)
         prompt = self.template[which].format(instance_token)
         if self.augment_pipe is not None:
             image, prompt = self._augment(image, prompt, sample, "mask")
         sample["original_size"] = (image.width, image.height)
-        image, top, left = self._resize_and_crop_image(image)
-        sample["image"] = self.image_transforms(image)
-        sample["crop_top_left"] = (top, left)
+        self._finish(sample, image)
         self._tokenize_into(sample, prompt)
         if self.prior_data_root:
             self._class_item(sample, index, which)
@@ -130,10 +166,8 @@ class TextBoostDataset(torch.utils.data.Dataset):
             sample["prior_mask"] = torch.ones_like(sample["mask"])
         # the reference resizes and crops once, then runs the resize-and-crop helper on the result: with a random
         # crop that is two draws from torch's RNG, kept so that seeded runs stay aligned
-        image = self.crop(self.resize_fn(image))
-        image, top, left = self._resize_and_crop_image(image)
-        sample["class_image"] = self.image_transforms(image)
-        sample["class_crop_top_left"] = (top, left)
+        image = self.crop(self.resize_fn(image))  # (this first pass stays on the host: it is a size x size image after it)
+        self._finish(sample, image, prefix="class_")
         self._tokenize_into(sample, prompt, prefix="class_")
 
     @staticmethod
@@ -143,9 +177,13 @@ class TextBoostDataset(torch.utils.data.Dataset):
         keys = [""] + (["class_"] if with_prior_preservation else [])
         has_mask = "attention_mask" in samples[0]
         ids = [s[k + "input_ids"] for k in keys for s in samples]
-        pixels = [s["class_image" if k else "image"] for k in keys for s in samples]
-        batch = {"input_ids": torch.cat(ids, dim=0),
-                 "pixel_values": torch.stack(pixels).to(memory_format=torch.contiguous_format).float()}
+        batch = {"input_ids": torch.cat(ids, dim=0)}
+        if "source" in samples[0]:  # device_transforms: uint8 sources + geometry, finished by image_ops on the GPU
+            batch["sources"] = [{n: s[k + n] for n in ("source", "resize_to", "crop_top_left", "crop_size")}
+                                for k in keys for s in samples]
+        else:
+            pixels = [s["class_image" if k else "image"] for k in keys for s in samples]
+            batch["pixel_values"] = torch.stack(pixels).to(memory_format=torch.contiguous_format).float()
         if "mask" in samples[0]:
             masks = [s["mask"] for s in samples]
             if "prior_mask" in samples[0]:

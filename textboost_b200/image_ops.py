@@ -121,14 +121,14 @@ def resize_crop_normalize(src: torch.Tensor, out_size: Tuple[int, int], top: int
     return out
 
 
-def batch_to_pixel_values(samples: Sequence[dict], device, key: str = "source") -> torch.Tensor:
-    """Items of ``TextBoostDataset(device_transforms=True)`` -> ``pixel_values`` fp32 [B, 3, S, S] on `device`: one
-    H2D copy of each augmented uint8 image, then the resize / crop / normalise kernels write straight into the batch."""
-    prefix = "class_" if key.startswith("class_") else ""
-    S = samples[0][prefix + "crop_size"]
-    batch = torch.empty((len(samples), 3, S, S), device=device, dtype=torch.float32)
-    for i, s in enumerate(samples):
-        src = s[key].to(device, non_blocking=True)
-        top, left = s[prefix + "crop_top_left"]
-        resize_crop_normalize(src, s[prefix + "resize_to"], top, left, S, S, out=batch[i])
+def batch_to_pixel_values(sources: Sequence[dict], device) -> torch.Tensor:
+    """``batch["sources"]`` of ``TextBoostDataset(device_transforms=True).collate_fn`` -> ``pixel_values`` fp32
+    [B, 3, S, S] on `device`: one H2D copy of each augmented uint8 image, then the resize / crop / normalise kernels write
+    straight into the batch."""
+    S = sources[0]["crop_size"]
+    batch = torch.empty((len(sources), 3, S, S), device=device, dtype=torch.float32)
+    for i, s in enumerate(sources):
+        src = s["source"].to(device, non_blocking=True)
+        top, left = s["crop_top_left"]
+        resize_crop_normalize(src, tuple(s["resize_to"]), int(top), int(left), S, S, out=batch[i])
     return batch

@@ -104,6 +104,10 @@ def parse_args(input_args=None):
                         help="JSONL of human-written prompts for the knowledge-preservation loss (the path the "
                              "reference hard-codes, train_textboost.py:893); used when the file exists")
     parser.add_argument("--log_every", type=int, default=10, help="host read-back period of the loss scalar")
+    parser.add_argument("--gpu_image_transforms", action="store_true",
+                        help="finish each image on the GPU: the dataset stops after the PIL augmentation and the "
+                             "Lanczos resize / crop / normalise run as byte-exact CUDA kernels (same pixel_values); "
+                             "decoded source images are cached")
     args = parser.parse_args(input_args)
 
     # post-parse validation: train_textboost.py:435-448
@@ -170,7 +174,8 @@ def load_tokenizer(args):
 def build_image_batches(args, tokenizer, rank, world):
     """The reference's train dataloader (train_textboost.py:856-890): PairedAugmentation -> TextBoostDataset ->
     Wrapper(drop_last=False).shuffle(seed).repeat() sharded by rank -> DataLoader(batch_size, collate_fn).  Returns an
-    endless iterator of {"pixel_values" [B,3,S,S] fp32 in [-1,1], "input_ids" [B,L], "attention_mask"}; with
+    endless iterator of {"pixel_values" [B,3,S,S] fp32 in [-1,1] (or "sources" with --gpu_image_transforms),
+    "input_ids" [B,L], "attention_mask"}; with
     --with_image_prior the class examples follow the instance ones in the same batch ([2B, ...])."""
     from textboost_b200.dataset import TextBoostDataset, Wrapper
     if args.augment in ("pda", "paug"):
@@ -188,7 +193,8 @@ def build_image_batches(args, tokenizer, rank, world):
                                prior_data_root=args.class_data_dir if args.with_image_prior else None,
                                class_token=args.class_token,
                                num_prior=args.num_prior_images, size=args.resolution, center_crop=args.center_crop,
-                               augment_pipe=augment_pipe)
+                               augment_pipe=augment_pipe, device_transforms=args.gpu_image_transforms,
+                               cache_decoded=args.gpu_image_transforms)
     if len(dataset) == 0:
         raise ValueError("no instance images found")
     stream = Wrapper(dataset, drop_last=False, rank=rank, world_size=world).shuffle(seed=args.seed).repeat()
@@ -432,7 +438,11 @@ def main(args):
         """rank r takes rows [r*B, (r+1)*B) of the step's global batch (dataset.py:846-870 sharding)."""
         if image_batches is not None:  # train_textboost.py:1027-1037: pixels -> VAE posterior sample * scaling_factor
             batch = next(image_batches)
-            pixels = batch["pixel_values"].to(device, non_blocking=True)
+            if "sources" in batch:  # --gpu_image_transforms: resize / crop / normalise on the GPU, byte-exact
+                from textboost_b200.image_ops import batch_to_pixel_values
+                pixels = batch_to_pixel_values(batch["sources"], device)
+            else:
+                pixels = batch["pixel_values"].to(device, non_blocking=True)
             lat = vae.engine.encode_latents(pixels, generator=gen)
             ids = batch["input_ids"].to(device, non_blocking=True)
         else:
