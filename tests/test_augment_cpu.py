@@ -167,3 +167,36 @@ def test_cli_image_batches_with_image_prior(tmp_path):
     with __import__("pytest").raises(ValueError):
         T._unsupported(T.parse_args(["--pretrained_model_name_or_path", "x", "--with_image_prior", "--class_data_dir",
                                      str(cls), "--class_token", "dog", "--synthetic_data"]))
+
+
+def test_image_stream_under_real_dataloader_workers(tmp_path):
+    """Wrapper / ShardedStream as an IterableDataset inside torch's DataLoader with worker processes: every
+    (rank, worker) pair takes its own stride of the shuffled epoch (dataset.py:846-870), batches keep their shape."""
+    import torch
+    import train_textboost as T
+    from textboost_b200 import dataset, prompts
+    from textboost_b200.synthetic import LiteralTokenizer
+    d = tmp_path / "imgs"
+    d.mkdir()
+    for i in range(8):
+        G.make_image((40 + i, 40), i).save(d / f"{i:02d}.png")
+    ds = dataset.TextBoostDataset([{"instance_token": "<dog>", "instance_data_dir": str(d)}], LiteralTokenizer(),
+                                  size=32, center_crop=True, template="a {}")
+    seen = {}
+    for rank in (0, 1):
+        stream = prompts.ShardedStream(ds, drop_last=False, rank=rank, world_size=2).shuffle(seed=3)  # one epoch
+        loader = torch.utils.data.DataLoader(stream, batch_size=1, num_workers=2,
+                                             collate_fn=lambda ex: dataset.TextBoostDataset.collate_fn(ex, False))
+        seen[rank] = [b["pixel_values"] for b in loader]
+        assert all(p.shape == (1, 3, 32, 32) for p in seen[rank])
+    # 8 images over 2 ranks x 2 workers: each rank sees 4 distinct images, the two ranks together all 8
+    def key(p):
+        return round(float(p.double().sum()), 4)
+    k0, k1 = {key(p) for p in seen[0]}, {key(p) for p in seen[1]}
+    assert len(seen[0]) == len(seen[1]) == 4 and len(k0) == len(k1) == 4 and not (k0 & k1)
+    args = T.parse_args(["--pretrained_model_name_or_path", "x", "--instance_data_dir", str(d), "--resolution", "32",
+                         "--train_batch_size", "3", "--dataloader_num_workers", "2", "--center_crop"])
+    args.concepts_list = [{"instance_token": "<dog>", "instance_data_dir": str(d)}]
+    it = T.build_image_batches(args, LiteralTokenizer(), 0, 1)
+    assert [next(it)["pixel_values"].shape for _ in range(4)] == [(3, 3, 32, 32)] * 4  # endless: repeat() wraps epochs
+    del it
