@@ -153,3 +153,44 @@ def test_dataset_device_transforms_mode_is_the_same_data(tmp_path, center_crop, 
     if prior:
         assert torch.equal(batch["sources"][2]["source"], devi[0]["class_source"])
     assert len(ds._decoded) == 3  # each file decoded once
+
+
+# ------------------------------------------------------------------ geometry / colour ops of the augmentation
+@pytest.mark.parametrize("w,h", [(64, 64), (90, 70), (70, 90), (128, 96), (33, 33)])
+def test_affine_and_colour_oracles_are_byte_exact_vs_the_real_ops(w, h):
+    """oracle/pil_affine_ref.py against the real augmentation ops (PIL + torchvision underneath) for the same draws:
+    adjust_scale (edge pad + bicubic affine + centre crop, incl. the (h, w) swap on non-square images),
+    horizontal_translate (edge pad + nearest affine + centre crop), grayscale."""
+    import random
+    from PIL import ImageOps
+    from oracle import pil_affine_ref as A
+    from textboost_b200 import augment
+    a = _img(w, h, seed=7 * w + h)
+    img = Image.fromarray(a)
+    assert np.array_equal(A.grayscale(a), np.asarray(ImageOps.grayscale(img).convert("RGB")))
+    for seed in range(8):
+        np.random.seed(seed)
+        random.seed(seed)
+        ref, _ = augment.adjust_scale(img, "p", False)
+        np.random.seed(seed)
+        scale = np.random.uniform(0.34, 1.4)
+        assert np.array_equal(A.adjust_scale(a, scale), np.asarray(ref)), ("adjust_scale", seed, scale)
+        np.random.seed(seed)
+        ref, _ = augment.horizontal_translate(img, "p", False)
+        np.random.seed(seed)
+        direction = np.random.randint(0, 2)
+        shift = int(np.random.uniform(low=0.15, high=0.3) * w)
+        got = A.horizontal_translate(a, shift, -1 if direction == 0 else 1)
+        assert np.array_equal(got, np.asarray(ref)), ("horizontal_translate", seed, direction, shift)
+
+
+@pytest.mark.parametrize("scale", [0.34, 0.5, 0.77, 1.0, 1.21, 1.4])
+def test_affine_bicubic_oracle_vs_pillow_transform(scale):
+    from torchvision.transforms.v2.functional._geometry import _get_inverse_affine_matrix
+    from oracle import pil_affine_ref as A
+    a = _img(57, 41, seed=int(scale * 100))
+    ref = np.asarray(v2.functional.affine(Image.fromarray(a), angle=0, translate=(0, 0), scale=scale, shear=0,
+                                          interpolation=Image.BICUBIC))
+    m = _get_inverse_affine_matrix([57 * 0.5, 41 * 0.5], 0.0, [0.0, 0.0], scale, [0.0, 0.0])
+    assert np.allclose(m, A.scale_matrix(57, 41, scale), rtol=0, atol=1e-12)
+    assert np.array_equal(A.affine_bicubic(a, m), ref)
