@@ -30,7 +30,57 @@ import PIL.ImageOps
 from PIL import Image
 from torchvision.transforms import v2
 
+from .image_plan import ImagePlan
+
 _F = v2.functional
+
+
+# ---- image primitives: executed with PIL / torchvision on a PIL image, recorded on an ImagePlan (deferred to the GPU)
+def _pad_edge(image, pad_x, pad_y):
+    if isinstance(image, ImagePlan):
+        return image.pad_edge(pad_x, pad_y)
+    return _F.pad(image, (pad_x, pad_y), padding_mode="edge")
+
+
+def _affine(image, translate, scale, bicubic):
+    """Scale about the centre and / or shift; torchvision's default interpolation for this call is NEAREST."""
+    if isinstance(image, ImagePlan):
+        from torchvision.transforms.v2.functional._geometry import _get_inverse_affine_matrix
+        w, h = image.size
+        matrix = _get_inverse_affine_matrix([w * 0.5, h * 0.5], 0.0, [float(translate[0]), float(translate[1])],
+                                            scale, [0.0, 0.0])
+        return image.affine(matrix, "bicubic" if bicubic else "nearest")
+    if bicubic:
+        return _F.affine(image, angle=0, translate=translate, scale=scale, shear=0, interpolation=Image.BICUBIC)
+    return _F.affine(image, angle=0, translate=translate, scale=scale, shear=0)
+
+
+def _center_crop(image, output_size):
+    if isinstance(image, ImagePlan):
+        return image.center_crop(output_size[0], output_size[1])
+    return _F.center_crop(image, output_size)
+
+
+def _to_grayscale(image):
+    if isinstance(image, ImagePlan):
+        return image.grayscale()
+    return PIL.ImageOps.grayscale(image).convert("RGB")
+
+
+def _framed_tiles(cell, n):
+    """`cell` repeated n x n, each copy with its outermost pixel ring set to black."""
+    if isinstance(cell, ImagePlan):
+        return cell.collage(n)
+    px = np.asarray(cell).copy()
+    px[[0, -1], :] = 0
+    px[:, [0, -1]] = 0
+    return Image.fromarray(np.tile(px, (n, n, 1)))
+
+
+def _pil_only(image, what):
+    if isinstance(image, ImagePlan):
+        raise NotImplementedError(f"{what} is not part of the deferred (GPU) augmentation path: PairedAugmentation "
+                                  "never schedules it")
 
 
 class _Words(NamedTuple):
@@ -61,9 +111,9 @@ def adjust_scale(image, prompt, inversion=False):
     a, b = image.size  # (sic) the reference names these (h, w); PIL gives (width, height)
     pad_a, pad_b = round((a / s - a) / 2), round((b / s - b) / 2)
     if pad_a > 0 and pad_b > 0:
-        image = _F.pad(image, (pad_b, pad_a), padding_mode="edge")
-    image = _F.affine(image, angle=0, translate=(0, 0), scale=s, shear=0, interpolation=Image.BICUBIC)
-    image = _F.center_crop(image, (a, b))
+        image = _pad_edge(image, pad_b, pad_a)
+    image = _affine(image, (0, 0), s, bicubic=True)
+    image = _center_crop(image, (a, b))
     if inversion:
         words = "<zoom-out_0> <zoom-out_1>" if s < 0.6 else "<zoom-in_0> <zoom-in_1>" if s > 1.2 else ""
     elif s <= 0.6:
@@ -81,6 +131,7 @@ _ROTATIONS = ((90, _Words("90 degrees counter clockwise rotated ", "<rot90_0> <r
 
 def rotate(image, prompt, inversion=False):
     angle, words = _ROTATIONS[np.random.randint(0, 2)]
+    _pil_only(image, "rotate")
     image = _F.rotate(image, angle=angle)
     if inversion:
         return image, _either_end(prompt, words.tokens, "")
@@ -103,9 +154,9 @@ def horizontal_translate(image, prompt, inversion=False):
     sign, words = _SHIFTS[np.random.randint(0, 2)]
     w, h = image.size
     shift = int(np.random.uniform(low=0.15, high=0.3) * w)
-    image = _F.pad(image, (shift, 0), padding_mode="edge")
-    image = _F.affine(image, angle=0, translate=[sign * shift, 0], scale=1, shear=0)
-    image = _F.center_crop(image, [w, h])  # (sic) output_size is (height, width); equal for the square inputs used
+    image = _pad_edge(image, shift, 0)
+    image = _affine(image, [sign * shift, 0], 1, bicubic=False)
+    image = _center_crop(image, [w, h])  # (sic) output_size is (height, width); equal for the square inputs used
     return image, _back(prompt, words.pick(inversion), sep="")
 
 
@@ -135,18 +186,21 @@ def adjust_brightness(image, prompt, inversion=False, size=None):
         factor, words = np.random.uniform(0.4, 0.6), _Words("dimmed", "<dimmed>")
     else:
         factor, words = np.random.uniform(1.3, 1.5), _Words("bright", "<bright>")
+    _pil_only(image, "adjust_brightness")
     image = PIL.ImageEnhance.Brightness(image).enhance(factor)
     return image, _either_end(prompt, words.pick(inversion), "")
 
 
 def grayscale(image, prompt, inversion=False, size=None):
     del size
-    image = PIL.ImageOps.grayscale(image).convert("RGB")
+    image = _to_grayscale(image)
     return image, _back(prompt, _Words("grayscale", "<grayscale_0> <grayscale_1>").pick(inversion))
 
 
 def jpeg_compression(image, prompt, inversion=False):
-    image = _F.jpeg(image, quality=np.random.randint(25, 75))
+    quality = np.random.randint(25, 75)
+    _pil_only(image, "jpeg_compression")
+    image = _F.jpeg(image, quality=quality)
     return image, _either_end(prompt, _Words("JPEG", "<jpeg_0> <jpeg_1>").pick(inversion), " ")
 
 
@@ -156,10 +210,7 @@ def square_photo_collage(image, prompt, inversion=False):
     n = np.random.randint(2, 4)
     w, h = image.size
     cell_w, cell_h = w // n, h // n
-    cell = np.asarray(image.resize((cell_h, cell_w), Image.BICUBIC)).copy()  # array [cell_w, cell_h, 3]
-    cell[[0, -1], :] = 0
-    cell[:, [0, -1]] = 0
-    image = Image.fromarray(np.tile(cell, (n, n, 1)))
+    image = _framed_tiles(image.resize((cell_h, cell_w), Image.BICUBIC), n)  # PIL size (cell_h, cell_w): (sic)
     return image, _front(prompt, _Words("photo collage of ", "<collage_0> <collage_1> ").pick(inversion))
 
 
@@ -197,7 +248,8 @@ class PairedAugmentation:
         return image, (captioned if self.augment_prompt else prompt)
 
     def __call__(self, image, prompt):
-        assert isinstance(image, PIL.Image.Image), f"Invalid image type ({type(image)}). Must be PIL.Image.Image."
+        assert isinstance(image, (PIL.Image.Image, ImagePlan)), \
+            f"Invalid image type ({type(image)}). Must be PIL.Image.Image."
         if self.hflip and np.random.rand() < 0.5:
             image = image.transpose(Image.FLIP_LEFT_RIGHT)
         image, prompt = self._stage(self.geometric_ops, self.p, image, prompt)
