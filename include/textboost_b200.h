@@ -217,6 +217,22 @@ int tb_resize_crop_normalize_u8(const void* src_u8, int src_h, int src_w, int ch
                                 int crop_h, int crop_w, float scale, float mean, float std, void* mid_u8,
                                 float* out_f32_chw, void* out_u8_hwc, void* stream);
 
+/* ---- exact image primitives of the deferred augmentation (PIL / torchvision calls inside
+ * /root/reference/textboost/augment/paired_augmentation.py), uint8 [H, W, channels] images in HBM. ---- */
+/* out[y,x] = src[(y mod tile_h) + offset_y, mirror((x mod tile_w)) + offset_x]; outside the source: nearest edge pixel
+ * (clamp_to_edge: v2.functional.pad(..., "edge")) or zero (crop / center_crop padding); frame = 1 blanks the outer
+ * pixel ring of every tile (square_photo_collage, :236-260); tile_w = tile_h = 0: no tiling. */
+int tb_img_gather_u8(const void* src, int src_h, int src_w, int channels, void* out, int out_h, int out_w,
+                     int offset_x, int offset_y, int clamp_to_edge, int flip_x, int tile_w, int tile_h, int frame,
+                     void* stream);
+/* Pillow Image.transform(size, AFFINE, matrix6, BICUBIC | NEAREST) at the input size (v2.functional.affine in
+ * adjust_scale :27-31 and horizontal_translate :117-123): double-precision coordinates, a = -1 cubic over the clamped
+ * 4x4 neighbourhood, truncating store, zero outside.  matrix6 is a HOST pointer to the six inverse-affine doubles. */
+int tb_img_affine_u8(const void* src, int H, int W, int channels, void* out, const double* matrix6, int bicubic,
+                     void* stream);
+/* PIL.ImageOps.grayscale(img).convert("RGB") (:155): L = (19595 R + 38470 G + 7471 B + 0x8000) >> 16 on RGB triples. */
+int tb_img_grayscale_u8(const void* src, void* out, int64_t npix, void* stream);
+
 /* ---- CLIP text encoder pieces that are not GEMM / LayerNorm ------------------------------------
  * (transformers CLIPTextTransformer called from textboost/text_encoder.py:62-69; peft LoRA Linear
  * configured at train_textboost.py:702-709.) */

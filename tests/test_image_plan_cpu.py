@@ -74,3 +74,82 @@ def test_pipeline_streams_recorded_equal_eager(cfg):
         assert np.array_equal(plan_standin.run(plan), np.asarray(img)), plan
         n_ops += len(plan.ops)
     assert n_ops > 0 or kw["p"] == 0
+
+
+def _gather_standin(src, out_h, out_w, ox, oy, clamp, flip, tw, th, frame):
+    """numpy transcription of img_gather_u8_kernel."""
+    H, W, _ = src.shape
+    ys, xs = np.mgrid[0:out_h, 0:out_w]
+    zero = np.zeros((out_h, out_w), bool)
+    if tw > 0:
+        xs, ys = xs % tw, ys % th
+        if frame:
+            zero |= (xs == 0) | (ys == 0) | (xs == tw - 1) | (ys == th - 1)
+    if flip:
+        xs = out_w - 1 - xs
+    sx, sy = xs + ox, ys + oy
+    if clamp:
+        sx, sy = np.clip(sx, 0, W - 1), np.clip(sy, 0, H - 1)
+    else:
+        zero |= (sx < 0) | (sx >= W) | (sy < 0) | (sy >= H)
+        sx, sy = np.clip(sx, 0, W - 1), np.clip(sy, 0, H - 1)
+    out = src[sy, sx]
+    out[zero] = 0
+    return out
+
+
+@pytest.mark.parametrize("size", [(40, 40), (52, 31), (31, 52)])
+def test_gather_parameters_of_the_index_primitives(size):
+    """image_plan.gather_params + the gather kernel's index rule == the oracle for pad / crop / centre crop (incl. the
+    zero-padding case) / mirror / framed collage."""
+    from textboost_b200.image_plan import gather_params, op_output_size
+    a = np.asarray(G.make_image(size, 3))
+    H, W, _ = a.shape
+    ops = [("pad_edge", 5, 0), ("pad_edge", 3, 7), ("crop", 4, 6, 20, 17), ("center_crop", 20, 24),
+           ("center_crop", W, H), ("center_crop", H + 5, W - 3), ("center_crop", 61, 63), ("flip_lr",), ("collage", 2),
+           ("collage", 3)]
+    for op in ops:
+        w, h = op_output_size(op, W, H)
+        got = _gather_standin(a, h, w, *gather_params(op, W, H))
+        assert np.array_equal(got, plan_standin.apply_op(a, op)), op
+    with pytest.raises(ValueError):
+        gather_params(("grayscale",), W, H)
+
+
+def test_dataset_device_augment_mode_is_the_same_data(tmp_path):
+    """TextBoostDataset(device_augment=True): items carry an ImagePlan; executing it with the pinned oracles and
+    finishing with the kernel arithmetic gives the host pipeline's "image" bit for bit; prompts, crop positions and
+    the random streams are unchanged."""
+    from test_resample_cpu import kernel_standin
+    from textboost_b200 import augment, dataset
+    from textboost_b200.image_plan import ImagePlan
+    from textboost_b200.synthetic import LiteralTokenizer
+    inst, _, cls = G.write_image_dirs(str(tmp_path))
+    concepts = [{"instance_data_dir": inst, "instance_token": "<sks> dog"}]
+
+    def items(device_augment, prior):
+        ds = dataset.TextBoostDataset(concepts, LiteralTokenizer(), template="textboost", size=32,
+                                      augment_pipe=augment.PairedAugmentation(**G.PIPES[2]), class_token="dog",
+                                      prior_data_root=cls if prior else None, device_augment=device_augment)
+        G.seed_all(31)
+        out = [ds[i] for i in range(9)]
+        return out, (float(np.random.random()), random.random(), float(torch.rand(1)))
+
+    for prior in (False, True):
+        host, end_h = items(False, prior)
+        plan, end_p = items(True, prior)
+        assert end_h == end_p
+        n_ops = 0
+        for a, b in zip(host, plan):
+            assert isinstance(b["source"], ImagePlan) and "image" not in b
+            assert torch.equal(a["input_ids"], b["input_ids"]) and a["crop_top_left"] == b["crop_top_left"]
+            assert a["original_size"] == b["original_size"]
+            top, left = b["crop_top_left"]
+            got, _ = kernel_standin(plan_standin.run(b["source"]), b["resize_to"], top, left, 32, 32)
+            assert torch.equal(torch.from_numpy(got), a["image"])
+            n_ops += len(b["source"].ops)
+            if prior:  # class images stay on the host path up to the tail
+                assert isinstance(b["class_source"], torch.Tensor)
+        assert n_ops > 5
+    batch = dataset.TextBoostDataset.collate_fn(plan[:3], True)
+    assert len(batch["sources"]) == 6 and isinstance(batch["sources"][0]["source"], ImagePlan)

@@ -73,6 +73,10 @@ _SIGNATURES = {
                         c_float, c_float, c_float, c_void_p],
     "tb_vae_decode_in": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p],
     "tb_image_u8": [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p],
+    "tb_img_gather_u8": [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                         c_int, c_void_p],
+    "tb_img_affine_u8": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p],
+    "tb_img_grayscale_u8": [c_void_p, c_void_p, c_int64, c_void_p],
     "tb_resize_crop_normalize_u8": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p,
                                     c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                     c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p],

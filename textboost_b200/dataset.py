@@ -49,14 +49,20 @@ class TextBoostDataset(torch.utils.data.Dataset):
     def __init__(self, concepts_list: Sequence[dict], tokenizer, tokenizer_2=None, num_instance=None, template="a {}",
                  prior_data_root=None, class_token=None, num_prior=None, size=512, center_crop=False,
                  augment_pipe=None, augment_prior: bool = False, device_transforms: bool = False,
-                 cache_decoded: bool = False):
+                 cache_decoded: bool = False, device_augment: bool = False):
         """device_transforms (addition): stop after the augmentation and return the uint8 image ("source" [H,W,3]) with
         the resize / crop geometry ("resize_to", "crop_top_left", "crop_size") instead of "image"; the byte-exact GPU
         tail (textboost_b200.image_ops) produces the same ``pixel_values``.  The random streams are consumed exactly
         as without it.  cache_decoded (addition): keep the decoded RGB source images (a handful in this workload)
-        instead of re-opening the files for every item; the pixels are the same."""
+        instead of re-opening the files for every item; the pixels are the same.  device_augment (addition, implies
+        the other two): instance images become `ImagePlan`s — the augmentation pipeline draws its random numbers and
+        edits the caption as always but only RECORDS its image operations, which then run as exact GPU kernels
+        (textboost_b200.image_plan.run_plan); "source" is the plan."""
         self.size, self.center_crop = size, center_crop
+        self.device_augment = device_augment
+        device_transforms, cache_decoded = device_transforms or device_augment, cache_decoded or device_augment
         self.device_transforms, self._decoded = device_transforms, ({} if cache_decoded else None)
+        self._bases = {}
         self.tokenizer, self.tokenizer_2 = tokenizer, tokenizer_2
         self.template = resolve_template(template)
         self.instance_images_path = [(path, concept["instance_token"]) for concept in concepts_list
@@ -89,6 +95,14 @@ class TextBoostDataset(torch.utils.data.Dataset):
             self._decoded[path].load()
         return self._decoded[path].copy()
 
+    def _open_plan(self, path):
+        """The decoded image as the base of a deferred ImagePlan (one uint8 tensor per file, shared by every item)."""
+        import numpy as np
+        from .image_plan import ImagePlan
+        if path not in self._bases:
+            self._bases[path] = torch.from_numpy(np.array(_open_rgb(path), dtype=np.uint8))
+        return ImagePlan(self._bases[path])
+
     def _geometry(self, image):
         """What `_resize_and_crop_image` would do to `image`, without doing it: (resized (w, h), top, left), drawing the
         random crop position from torch's RNG exactly as RandomCrop.get_params does on the resized image."""
@@ -108,7 +122,11 @@ class TextBoostDataset(torch.utils.data.Dataset):
             return
         import numpy as np
         resize_to, top, left = self._geometry(image)
-        sample[prefix + "source"] = torch.from_numpy(np.array(image, dtype=np.uint8))  # [H, W, 3], writable copy
+        from .image_plan import ImagePlan
+        if isinstance(image, ImagePlan):
+            sample[prefix + "source"] = image
+        else:
+            sample[prefix + "source"] = torch.from_numpy(np.array(image, dtype=np.uint8))  # [H, W, 3], writable copy
         sample[prefix + "resize_to"], sample[prefix + "crop_size"] = resize_to, self.size
         sample[prefix + "crop_top_left"] = (top, left)
 
@@ -139,7 +157,7 @@ class TextBoostDataset(torch.utils.data.Dataset):
     def __getitem__(self, index):
         sample = {}
         path, instance_token = self.instance_images_path[index % self.num_instance_images]
-        image = self._open(path)
+        image = self._open_plan(path) if self.device_augment else self._open(path)
         which = random.randint(0, len(self.template) - 1)
         prompt = self.template[which].format(instance_token)
         if self.augment_pipe is not None:

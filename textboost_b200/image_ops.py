@@ -121,6 +121,22 @@ def resize_crop_normalize(src: torch.Tensor, out_size: Tuple[int, int], top: int
     return out
 
 
+def resize_u8(src: torch.Tensor, out_size: Tuple[int, int], filter_name: str = "bicubic") -> torch.Tensor:
+    """Pillow's antialiased resize of a uint8 [H, W, C] image on the GPU -> uint8 [out_h, out_w, C] (the BICUBIC
+    ``Image.resize`` inside the crop / collage augmentations)."""
+    assert src.is_cuda and src.dtype == torch.uint8 and src.dim() == 3 and src.is_contiguous()
+    H, W, Cc = src.shape
+    out_w, out_h = out_size
+    bx, kx, ksx, _ = _tables_on(src.device, W, out_w, filter_name)
+    by, ky, ksy, _ = _tables_on(src.device, H, out_h, filter_name)
+    out = torch.empty((out_h, out_w, Cc), device=src.device, dtype=torch.uint8)
+    mid = torch.empty(H * out_w * Cc, device=src.device, dtype=torch.uint8)
+    C.call("tb_resize_crop_normalize_u8", C.ptr(src), H, W, Cc, C.ptr(bx), C.ptr(kx), ksx, out_w, C.ptr(by),
+           C.ptr(ky), ksy, out_h, 0, H, 0, 0, out_h, out_w, _SCALE_255, 0.5, 0.5, C.ptr(mid), None, C.ptr(out),
+           C.stream_ptr())
+    return out
+
+
 def batch_to_pixel_values(sources: Sequence[dict], device) -> torch.Tensor:
     """``batch["sources"]`` of ``TextBoostDataset(device_transforms=True).collate_fn`` -> ``pixel_values`` fp32
     [B, 3, S, S] on `device`: one H2D copy of each augmented uint8 image, then the resize / crop / normalise kernels write
@@ -128,7 +144,11 @@ def batch_to_pixel_values(sources: Sequence[dict], device) -> torch.Tensor:
     S = sources[0]["crop_size"]
     batch = torch.empty((len(sources), 3, S, S), device=device, dtype=torch.float32)
     for i, s in enumerate(sources):
-        src = s["source"].to(device, non_blocking=True)
+        if isinstance(s["source"], torch.Tensor):
+            src = s["source"].to(device, non_blocking=True)
+        else:  # an ImagePlan: the augmentation itself was deferred; run its primitives on the GPU first
+            from .image_plan import run_plan
+            src = run_plan(s["source"], device)
         top, left = s["crop_top_left"]
         resize_crop_normalize(src, tuple(s["resize_to"]), int(top), int(left), S, S, out=batch[i])
     return batch

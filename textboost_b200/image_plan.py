@@ -115,3 +115,69 @@ def op_output_size(op: tuple, width: int, height: int) -> Tuple[int, int]:
     if kind in ("affine", "flip_lr", "grayscale"):
         return width, height
     raise ValueError(f"unknown image op {kind!r}")
+
+
+def gather_params(op: tuple, width: int, height: int) -> Tuple[int, int, int, int, int, int, int]:
+    """(offset_x, offset_y, clamp_to_edge, flip_x, tile_w, tile_h, frame) of `tb_img_gather_u8` for the pure index
+    primitives applied to a width x height image."""
+    kind = op[0]
+    if kind == "pad_edge":
+        return -op[1], -op[2], 1, 0, 0, 0, 0
+    if kind == "crop":
+        return op[1], op[2], 0, 0, 0, 0, 0
+    if kind == "center_crop":  # torchvision: zero-pad the short axes (floor on the left / top), cut at round(. / 2)
+        out_h, out_w = op[1], op[2]
+        px, py = max(out_w - width, 0), max(out_h - height, 0)
+        left = int(round((width + px - out_w) / 2.0)) - px // 2
+        top = int(round((height + py - out_h) / 2.0)) - py // 2
+        return left, top, 0, 0, 0, 0, 0
+    if kind == "flip_lr":
+        return 0, 0, 0, 1, 0, 0, 0
+    if kind == "collage":
+        return 0, 0, 0, 0, width, height, 1
+    raise ValueError(f"not an index primitive: {kind!r}")
+
+
+# ------------------------------------------------------------------------------------------------ GPU executor
+_device_bases = {}  # (device, data_ptr of the host base) -> uint8 tensor on the device (decoded images are few)
+
+
+def _base_on(device, base: torch.Tensor) -> torch.Tensor:
+    key = (str(device), base.data_ptr(), tuple(base.shape))
+    if key not in _device_bases:
+        if len(_device_bases) >= 256:
+            _device_bases.clear()
+        _device_bases[key] = (base, base.to(device))  # the host tensor is kept so its address stays unique
+    return _device_bases[key][1]
+
+
+def run_plan(plan: ImagePlan, device) -> torch.Tensor:
+    """Execute the recorded primitives on the GPU: uint8 [plan.height, plan.width, 3] on `device`.  One kernel per
+    primitive (csrc/augment.cu; the resize is image_ops' two-pass kernel writing bytes); the decoded base image is
+    uploaded once and stays resident."""
+    import ctypes
+
+    from . import _cabi as C
+    from . import image_ops
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("run_plan runs on the CUDA device only (no CPU path)")
+    img = _base_on(device, plan.base)
+    for op in plan.ops:
+        H, W, Cc = img.shape
+        w, h = op_output_size(op, W, H)
+        kind = op[0]
+        if kind == "resize":
+            img = image_ops.resize_u8(img, (w, h), op[3])
+            continue
+        out = torch.empty((h, w, Cc), device=device, dtype=torch.uint8)
+        if kind == "affine":
+            m = (ctypes.c_double * 6)(*op[1:7])
+            C.call("tb_img_affine_u8", C.ptr(img), H, W, Cc, C.ptr(out), m, int(op[7] == "bicubic"), C.stream_ptr())
+        elif kind == "grayscale":
+            C.call("tb_img_grayscale_u8", C.ptr(img), C.ptr(out), H * W, C.stream_ptr())
+        else:
+            C.call("tb_img_gather_u8", C.ptr(img), H, W, Cc, C.ptr(out), h, w, *gather_params(op, W, H),
+                   C.stream_ptr())
+        img = out
+    return img

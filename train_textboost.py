@@ -108,7 +108,13 @@ def parse_args(input_args=None):
                         help="finish each image on the GPU: the dataset stops after the PIL augmentation and the "
                              "Lanczos resize / crop / normalise run as byte-exact CUDA kernels (same pixel_values); "
                              "decoded source images are cached")
+    parser.add_argument("--gpu_augment", action="store_true",
+                        help="also run the augmentation's image operations on the GPU: PairedAugmentation draws its "
+                             "random numbers and edits the caption as always but records its image operations, which "
+                             "run as exact CUDA kernels on the decoded image resident in HBM (implies "
+                             "--gpu_image_transforms)")
     args = parser.parse_args(input_args)
+    args.gpu_image_transforms = args.gpu_image_transforms or args.gpu_augment
 
     # post-parse validation: train_textboost.py:435-448
     if args.with_image_prior:
@@ -194,7 +200,7 @@ def build_image_batches(args, tokenizer, rank, world):
                                class_token=args.class_token,
                                num_prior=args.num_prior_images, size=args.resolution, center_crop=args.center_crop,
                                augment_pipe=augment_pipe, device_transforms=args.gpu_image_transforms,
-                               cache_decoded=args.gpu_image_transforms)
+                               cache_decoded=args.gpu_image_transforms, device_augment=args.gpu_augment)
     if len(dataset) == 0:
         raise ValueError("no instance images found")
     stream = Wrapper(dataset, drop_last=False, rank=rank, world_size=world).shuffle(seed=args.seed).repeat()
