@@ -173,7 +173,8 @@ def run_plan(plan: ImagePlan, device) -> torch.Tensor:
         out = torch.empty((h, w, Cc), device=device, dtype=torch.uint8)
         if kind == "affine":
             m = (ctypes.c_double * 6)(*op[1:7])
-            C.call("tb_img_affine_u8", C.ptr(img), H, W, Cc, C.ptr(out), m, int(op[7] == "bicubic"), C.stream_ptr())
+            C.call("tb_img_affine_u8", C.ptr(img), H, W, Cc, C.ptr(out), ctypes.cast(m, ctypes.c_void_p),
+                   int(op[7] == "bicubic"), C.stream_ptr())
         elif kind == "grayscale":
             C.call("tb_img_grayscale_u8", C.ptr(img), C.ptr(out), H * W, C.stream_ptr())
         else:
