@@ -101,7 +101,7 @@ class TextBoostDataset(torch.utils.data.Dataset):
         from .image_plan import ImagePlan
         if path not in self._bases:
             self._bases[path] = torch.from_numpy(np.array(_open_rgb(path), dtype=np.uint8))
-        return ImagePlan(self._bases[path])
+        return ImagePlan(self._bases[path], key=str(path))
 
     def _geometry(self, image):
         """What `_resize_and_crop_image` would do to `image`, without doing it: (resized (w, h), top, left), drawing the

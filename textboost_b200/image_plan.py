@@ -33,9 +33,11 @@ _FILTER_NAMES = {Image.BICUBIC: "bicubic", Image.LANCZOS: "lanczos"}
 class ImagePlan:
     mode = "RGB"
 
-    def __init__(self, base: torch.Tensor, ops: Tuple[tuple, ...] = (), size: Tuple[int, int] = None):
+    def __init__(self, base: torch.Tensor, ops: Tuple[tuple, ...] = (), size: Tuple[int, int] = None, key=None):
+        """key: a stable identity of the decoded base image (the file path): lets the executor keep ONE device copy
+        per file however many times the plan object is re-created or pickled across DataLoader workers."""
         assert base.dtype == torch.uint8 and base.dim() == 3 and base.shape[2] == 3, "base: uint8 [H, W, 3]"
-        self.base, self.ops = base, tuple(ops)
+        self.base, self.ops, self.key = base, tuple(ops), key
         self._size = (int(base.shape[1]), int(base.shape[0])) if size is None else (int(size[0]), int(size[1]))
 
     # ---- the PIL surface the augmentation and the dataset read
@@ -55,7 +57,7 @@ class ImagePlan:
         return self  # immutable: every operation returns a new plan
 
     def _then(self, op: tuple, size: Tuple[int, int]) -> "ImagePlan":
-        return ImagePlan(self.base, self.ops + (op,), size)
+        return ImagePlan(self.base, self.ops + (op,), size, self.key)
 
     def transpose(self, method) -> "ImagePlan":
         if method != Image.FLIP_LEFT_RIGHT:
@@ -139,16 +141,18 @@ def gather_params(op: tuple, width: int, height: int) -> Tuple[int, int, int, in
 
 
 # ------------------------------------------------------------------------------------------------ GPU executor
-_device_bases = {}  # (device, data_ptr of the host base) -> uint8 tensor on the device (decoded images are few)
+_device_bases = {}  # (device, plan.key) -> uint8 tensor on the device: the handful of decoded source images
 
 
-def _base_on(device, base: torch.Tensor) -> torch.Tensor:
-    key = (str(device), base.data_ptr(), tuple(base.shape))
+def _base_on(device, plan: "ImagePlan") -> torch.Tensor:
+    if plan.key is None:
+        return plan.base.to(device)
+    key = (str(device), plan.key, tuple(plan.base.shape))
     if key not in _device_bases:
-        if len(_device_bases) >= 256:
+        if len(_device_bases) >= 1024:
             _device_bases.clear()
-        _device_bases[key] = (base, base.to(device))  # the host tensor is kept so its address stays unique
-    return _device_bases[key][1]
+        _device_bases[key] = plan.base.to(device)
+    return _device_bases[key]
 
 
 def run_plan(plan: ImagePlan, device) -> torch.Tensor:
@@ -162,7 +166,7 @@ def run_plan(plan: ImagePlan, device) -> torch.Tensor:
     device = torch.device(device)
     if device.type != "cuda":
         raise RuntimeError("run_plan runs on the CUDA device only (no CPU path)")
-    img = _base_on(device, plan.base)
+    img = _base_on(device, plan)
     for op in plan.ops:
         H, W, Cc = img.shape
         w, h = op_output_size(op, W, H)
