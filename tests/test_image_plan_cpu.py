@@ -127,17 +127,18 @@ def test_dataset_device_augment_mode_is_the_same_data(tmp_path):
     inst, _, cls = G.write_image_dirs(str(tmp_path))
     concepts = [{"instance_data_dir": inst, "instance_token": "<sks> dog"}]
 
-    def items(device_augment, prior):
+    def items(device_augment, prior, center=False):
         ds = dataset.TextBoostDataset(concepts, LiteralTokenizer(), template="textboost", size=32,
                                       augment_pipe=augment.PairedAugmentation(**G.PIPES[2]), class_token="dog",
-                                      prior_data_root=cls if prior else None, device_augment=device_augment)
+                                      prior_data_root=cls if prior else None, device_augment=device_augment,
+                                      center_crop=center, augment_prior=prior and center)
         G.seed_all(31)
         out = [ds[i] for i in range(9)]
         return out, (float(np.random.random()), random.random(), float(torch.rand(1)))
 
-    for prior in (False, True):
-        host, end_h = items(False, prior)
-        plan, end_p = items(True, prior)
+    for prior, center in ((False, False), (True, False), (True, True)):
+        host, end_h = items(False, prior, center)
+        plan, end_p = items(True, prior, center)
         assert end_h == end_p
         n_ops = 0
         for a, b in zip(host, plan):
@@ -148,8 +149,13 @@ def test_dataset_device_augment_mode_is_the_same_data(tmp_path):
             got, _ = kernel_standin(plan_standin.run(b["source"]), b["resize_to"], top, left, 32, 32)
             assert torch.equal(torch.from_numpy(got), a["image"])
             n_ops += len(b["source"].ops)
-            if prior:  # class images stay on the host path up to the tail
-                assert isinstance(b["class_source"], torch.Tensor)
+            if prior:  # class images are deferred too: Lanczos resize + first crop recorded, tail on top
+                assert isinstance(b["class_source"], ImagePlan) and b["class_source"].size == (32, 32)
+                assert torch.equal(a["class_input_ids"], b["class_input_ids"])
+                assert a["class_crop_top_left"] == b["class_crop_top_left"]
+                top, left = b["class_crop_top_left"]
+                got, _ = kernel_standin(plan_standin.run(b["class_source"]), b["class_resize_to"], top, left, 32, 32)
+                assert torch.equal(torch.from_numpy(got), a["class_image"])
         assert n_ops > 5
     batch = dataset.TextBoostDataset.collate_fn(plan[:3], True)
     assert len(batch["sources"]) == 6 and isinstance(batch["sources"][0]["source"], ImagePlan)

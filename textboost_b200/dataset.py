@@ -173,7 +173,7 @@ class TextBoostDataset(torch.utils.data.Dataset):
         """The ``--with_image_prior`` half of an item: a class image with the same template, or with the prompt
         spelled in its file name (``<n>-<words_with_underscores>.<ext>``) when no class token is given."""
         path = self.class_images_path[index % self.num_prior_images]
-        image = exif_transpose(Image.open(path)).convert("RGB")
+        image = self._open_plan(path) if self.device_augment else exif_transpose(Image.open(path)).convert("RGB")
         if self.class_token is not None:
             prompt = self.template[which].format(self.class_token)
         else:
@@ -184,9 +184,27 @@ class TextBoostDataset(torch.utils.data.Dataset):
             sample["prior_mask"] = torch.ones_like(sample["mask"])
         # the reference resizes and crops once, then runs the resize-and-crop helper on the result: with a random
         # crop that is two draws from torch's RNG, kept so that seeded runs stay aligned
-        image = self.crop(self.resize_fn(image))  # (this first pass stays on the host: it is a size x size image after it)
+        image = self._first_class_crop(image)
         self._finish(sample, image, prefix="class_")
         self._tokenize_into(sample, prompt, prefix="class_")
+
+    def _first_class_crop(self, image):
+        """``self.crop(self.resize_fn(image))`` (dataset.py:408-409), eagerly on a PIL image or recorded on a plan.  The
+        random crop of this call is the transform's own forward: it draws only for the axes that need cropping (unlike
+        `get_params`, which `_resize_and_crop_image` uses)."""
+        from .image_plan import ImagePlan
+        if not isinstance(image, ImagePlan):
+            return self.crop(self.resize_fn(image))
+        from .image_ops import shorter_side_size
+        w, h = shorter_side_size(image.width, image.height, self.size)
+        image = image.resize((w, h), Image.LANCZOS)
+        if self.center_crop:
+            top, left = int(round((h - self.size) / 2.0)), int(round((w - self.size) / 2.0))
+        else:
+            params = self.crop.make_params([torch.empty((3, h, w), dtype=torch.uint8)])
+            assert not params["needs_pad"]
+            top, left = params["top"], params["left"]
+        return image.crop((left, top, left + self.size, top + self.size))
 
     @staticmethod
     def collate_fn(samples, with_prior_preservation=False):
