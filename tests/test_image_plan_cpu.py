@@ -159,3 +159,39 @@ def test_dataset_device_augment_mode_is_the_same_data(tmp_path):
         assert n_ops > 5
     batch = dataset.TextBoostDataset.collate_fn(plan[:3], True)
     assert len(batch["sources"]) == 6 and isinstance(batch["sources"][0]["source"], ImagePlan)
+
+
+def test_host_plumbing_of_the_image_calls_end_to_end(tmp_path, monkeypatch):
+    """batch_to_pixel_values / run_plan / resize_u8 / resize_crop_normalize driven on CPU tensors through a fake
+    `_cabi.call` that works on the raw pointers it is given (tests/cabi_standin.py): argument order of the C calls,
+    buffer sizes, table upload, the plan executor's op mapping — the batch must equal the host pipeline's bits."""
+    import cabi_standin
+    from textboost_b200 import augment, dataset, image_ops, image_plan
+    from textboost_b200.synthetic import LiteralTokenizer
+    cabi_standin.install(monkeypatch)
+    inst, _, cls = G.write_image_dirs(str(tmp_path))
+    concepts = [{"instance_data_dir": inst, "instance_token": "<sks> dog"}]
+
+    def batch(mode, prior):
+        ds = dataset.TextBoostDataset(concepts, LiteralTokenizer(), template="textboost", size=32,
+                                      augment_pipe=augment.PairedAugmentation(**G.PIPES[2]), class_token="dog",
+                                      prior_data_root=cls if prior else None,
+                                      device_transforms=mode == "tail", cache_decoded=mode == "tail",
+                                      device_augment=mode == "plan")
+        G.seed_all(17)
+        return dataset.TextBoostDataset.collate_fn([ds[i] for i in range(6)], prior)
+
+    for prior in (False, True):
+        host = batch("host", prior)
+        for mode in ("tail", "plan"):
+            b = batch(mode, prior)
+            px = image_ops.batch_to_pixel_values(b["sources"], "cpu")
+            assert px.shape == host["pixel_values"].shape and torch.equal(px, host["pixel_values"]), (mode, prior)
+            assert torch.equal(b["input_ids"], host["input_ids"])
+    # one decoded base per file stays cached under its path key
+    assert all(k[1].endswith(".png") for k in image_plan._device_bases)
+    # resize_u8 alone, down and up, against Pillow
+    a = np.asarray(G.make_image((60, 44), 2))
+    for size in ((30, 22), (75, 50)):
+        got = image_ops.resize_u8(torch.from_numpy(a.copy()), size, "bicubic").numpy()
+        assert np.array_equal(got, np.asarray(Image.fromarray(a).resize(size, Image.BICUBIC)))

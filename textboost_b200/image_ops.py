@@ -98,13 +98,17 @@ def source_rows(bounds_y: np.ndarray, top: int, crop_h: int) -> Tuple[int, int]:
     return row0, int((window[:, 0] + window[:, 1]).max()) - row0
 
 
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} runs on the CUDA device only (no CPU path)")
+
+
 def resize_crop_normalize(src: torch.Tensor, out_size: Tuple[int, int], top: int, left: int, crop_h: int, crop_w: int,
                           out: torch.Tensor = None, filter_name: str = "lanczos", mean: float = 0.5,
                           std: float = 0.5) -> torch.Tensor:
     """src uint8 [H, W, C] on the GPU -> fp32 [C, crop_h, crop_w]: the crop window of the (out_w, out_h) resized image,
     normalised as ToDtype(float, scale=True) + Normalize(mean, std)."""
-    if not src.is_cuda:
-        raise RuntimeError("resize_crop_normalize runs on the CUDA device only (no CPU path)")
+    _require_cuda(src, "resize_crop_normalize")
     assert src.dtype == torch.uint8 and src.dim() == 3 and src.is_contiguous()
     H, W, Cc = src.shape
     out_w, out_h = out_size
@@ -124,7 +128,8 @@ def resize_crop_normalize(src: torch.Tensor, out_size: Tuple[int, int], top: int
 def resize_u8(src: torch.Tensor, out_size: Tuple[int, int], filter_name: str = "bicubic") -> torch.Tensor:
     """Pillow's antialiased resize of a uint8 [H, W, C] image on the GPU -> uint8 [out_h, out_w, C] (the BICUBIC
     ``Image.resize`` inside the crop / collage augmentations)."""
-    assert src.is_cuda and src.dtype == torch.uint8 and src.dim() == 3 and src.is_contiguous()
+    _require_cuda(src, "resize_u8")
+    assert src.dtype == torch.uint8 and src.dim() == 3 and src.is_contiguous()
     H, W, Cc = src.shape
     out_w, out_h = out_size
     bx, kx, ksx, _ = _tables_on(src.device, W, out_w, filter_name)

@@ -164,9 +164,8 @@ def run_plan(plan: ImagePlan, device) -> torch.Tensor:
     from . import _cabi as C
     from . import image_ops
     device = torch.device(device)
-    if device.type != "cuda":
-        raise RuntimeError("run_plan runs on the CUDA device only (no CPU path)")
     img = _base_on(device, plan)
+    image_ops._require_cuda(img, "run_plan")
     for op in plan.ops:
         H, W, Cc = img.shape
         w, h = op_output_size(op, W, H)
