@@ -1,0 +1,126 @@
+"""TEST INFRASTRUCTURE ONLY: compiles the KERNEL SOURCE of the byte-exact image kernels (csrc/image.cu, csrc/augment.cu)
+for the host with g++ and runs it single-threaded, so that the CPU suite checks the very lines of CUDA C that run on the
+GPU — index arithmetic, integer accumulation, rounding order — against PIL / torchvision, not a transcription of them.
+
+How: the text of each .cu file up to the end of its `namespace tb { ... }` block (kernels and device helpers; the
+extern "C" launch wrappers are left out) is compiled behind a shim that defines __global__ / __device__ away, provides
+blockIdx / blockDim / gridDim / threadIdx for ONE thread of ONE block (every kernel here is a grid-stride loop, so that
+thread visits every element), maps __ldg to a load and the explicitly rounded intrinsics (__dadd_rn, __fmul_rn, ...) to
+the plain IEEE operation under -ffp-contract=off.  Nothing here is on the product path."""
+import ctypes
+import os
+import subprocess
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "textboost_b200", "csrc")
+
+SHIM = r"""
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#define __global__
+#define __device__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+struct emu_dim3 { unsigned x, y, z; };
+static emu_dim3 blockIdx = {0, 0, 0}, threadIdx = {0, 0, 0}, blockDim = {1, 1, 1}, gridDim = {1, 1, 1};
+template <typename T> static inline T __ldg(const T* p) { return *p; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+namespace tb { static inline int num_sms() { return 1; } }
+"""
+
+DRIVERS = r"""
+extern "C" void emu_resample_h(const unsigned char* src, long long stride, const int* bounds, const int* kk, int ksize,
+                               int row0, int nrows, int left, int cw, int channels, unsigned char* mid) {
+  tb::resample_h_u8_kernel(src, stride, bounds, kk, ksize, row0, nrows, left, cw, channels, mid);
+}
+extern "C" void emu_resample_v(const unsigned char* mid, const int* bounds, const int* kk, int ksize, int row0, int top,
+                               int ch, int cw, int channels, float scale, float mean, float std, float* out,
+                               unsigned char* u8) {
+  tb::resample_v_norm_kernel(mid, bounds, kk, ksize, row0, top, ch, cw, channels, scale, mean, std, out, u8);
+}
+extern "C" void emu_gather(const unsigned char* src, int sh, int sw, int channels, unsigned char* out, int oh, int ow,
+                           int ox, int oy, int clamp, int flip, int tw, int th, int frame) {
+  tb::img_gather_u8_kernel(src, sh, sw, channels, out, oh, ow, ox, oy, clamp, flip, tw, th, frame);
+}
+extern "C" void emu_affine(const unsigned char* src, int H, int W, int channels, unsigned char* out, const double* m,
+                           int bicubic) {
+  tb::img_affine_u8_kernel(src, H, W, channels, out, m[0], m[1], m[2], m[3], m[4], m[5], bicubic);
+}
+extern "C" void emu_grayscale(const unsigned char* src, unsigned char* out, long long npix) {
+  tb::img_grayscale_u8_kernel(src, out, npix);
+}
+"""
+
+
+def _kernel_text(name):
+    text = open(os.path.join(CSRC, name)).read()
+    end = text.index("}  // namespace tb") + len("}  // namespace tb")
+    return "\n".join(l for l in text[:end].splitlines() if not l.startswith("#include"))
+
+
+_lib = None
+
+
+def lib():
+    """ctypes handle of the host build of the image kernels (compiled once per process into a temp dir)."""
+    global _lib
+    if _lib is None:
+        d = tempfile.mkdtemp(prefix="tb_kernel_emu_")
+        src = os.path.join(d, "emu.cpp")
+        with open(src, "w") as f:
+            f.write(SHIM + _kernel_text("image.cu") + "\n" + _kernel_text("augment.cu") + "\n" + DRIVERS)
+        so = os.path.join(d, "emu.so")
+        subprocess.run(["g++", "-O1", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC", "-std=c++17",
+                        "-Wno-unknown-pragmas", "-o", so, src], check=True, capture_output=True, text=True)
+        _lib = ctypes.CDLL(so)
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def fakes():
+    """Drop-in replacements for tests/cabi_standin.py's numpy fakes that run the real kernel source instead."""
+    import numpy as np
+
+    import cabi_standin as S
+    L = lib()
+
+    def tb_resize_crop_normalize_u8(src, H, W, C, bx, kx, ksx, out_w, by, ky, ksy, out_h, row0, nrows, top, left, ch,
+                                    cw, scale, mean, std, mid, out_f32, out_u8, stream):
+        L.emu_resample_h(ctypes.c_void_p(S._addr(src)), ctypes.c_longlong(W * C), ctypes.c_void_p(S._addr(bx)),
+                         ctypes.c_void_p(S._addr(kx)), ksx, row0, nrows, left, cw, C, ctypes.c_void_p(S._addr(mid)))
+        L.emu_resample_v(ctypes.c_void_p(S._addr(mid)), ctypes.c_void_p(S._addr(by)), ctypes.c_void_p(S._addr(ky)),
+                         ksy, row0, top, ch, cw, C, ctypes.c_float(scale), ctypes.c_float(mean), ctypes.c_float(std),
+                         ctypes.c_void_p(S._addr(out_f32)), ctypes.c_void_p(S._addr(out_u8)))
+        return 0
+
+    def tb_img_gather_u8(src, sh, sw, C, out, oh, ow, ox, oy, clamp, flip, tw, th, frame, stream):
+        L.emu_gather(ctypes.c_void_p(S._addr(src)), sh, sw, C, ctypes.c_void_p(S._addr(out)), oh, ow, ox, oy, clamp,
+                     flip, tw, th, frame)
+        return 0
+
+    def tb_img_affine_u8(src, H, W, C, out, matrix6, bicubic, stream):
+        L.emu_affine(ctypes.c_void_p(S._addr(src)), H, W, C, ctypes.c_void_p(S._addr(out)),
+                     ctypes.c_void_p(S._addr(matrix6)), bicubic)
+        return 0
+
+    def tb_img_grayscale_u8(src, out, npix, stream):
+        L.emu_grayscale(ctypes.c_void_p(S._addr(src)), ctypes.c_void_p(S._addr(out)), ctypes.c_longlong(npix))
+        return 0
+
+    return {f.__name__: f for f in (tb_resize_crop_normalize_u8, tb_img_gather_u8, tb_img_affine_u8,
+                                    tb_img_grayscale_u8)}
+
+
+def install(monkeypatch):
+    import cabi_standin as S
+    S.install(monkeypatch)
+    monkeypatch.setattr(S, "FAKES", fakes())

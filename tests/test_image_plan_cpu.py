@@ -195,3 +195,66 @@ def test_host_plumbing_of_the_image_calls_end_to_end(tmp_path, monkeypatch):
     for size in ((30, 22), (75, 50)):
         got = image_ops.resize_u8(torch.from_numpy(a.copy()), size, "bicubic").numpy()
         assert np.array_equal(got, np.asarray(Image.fromarray(a).resize(size, Image.BICUBIC)))
+
+
+# ---------------------------------------------------------------- the CUDA kernel SOURCE itself, compiled for the host
+def test_kernel_source_on_host_end_to_end_equals_the_host_pipeline(tmp_path, monkeypatch):
+    """Same as the plumbing test above, but the C calls now run the actual kernel source of csrc/image.cu and
+    csrc/augment.cu (host build, one emulated thread: tests/kernel_host_emulation.py): the lines that run on the GPU
+    reproduce PIL + torchvision bit for bit through the whole image path, with and without the class-image half."""
+    import kernel_host_emulation
+    from textboost_b200 import augment, dataset, image_ops
+    from textboost_b200.synthetic import LiteralTokenizer
+    kernel_host_emulation.install(monkeypatch)
+    inst, _, cls = G.write_image_dirs(str(tmp_path))
+    concepts = [{"instance_data_dir": inst, "instance_token": "<sks> dog"}]
+
+    def batch(mode, prior, cfg):
+        ds = dataset.TextBoostDataset(concepts, LiteralTokenizer(), template="textboost", size=32,
+                                      augment_pipe=augment.PairedAugmentation(**G.PIPES[cfg]), class_token="dog",
+                                      prior_data_root=cls if prior else None, augment_prior=prior,
+                                      device_transforms=mode == "tail", cache_decoded=mode == "tail",
+                                      device_augment=mode == "plan")
+        G.seed_all(23 + cfg)
+        return dataset.TextBoostDataset.collate_fn([ds[i] for i in range(8)], prior)
+
+    n_ops = 0
+    for prior, cfg in ((False, 2), (True, 2), (False, 1), (False, 4)):
+        host = batch("host", prior, cfg)
+        for mode in ("tail", "plan"):
+            b = batch(mode, prior, cfg)
+            px = image_ops.batch_to_pixel_values(b["sources"], "cpu")
+            assert torch.equal(px, host["pixel_values"]), (mode, prior, cfg)
+            if mode == "plan":
+                n_ops += sum(len(s["source"].ops) for s in b["sources"])
+    assert n_ops > 20
+
+
+@pytest.mark.parametrize("size", [(64, 64), (96, 72), (50, 81), (200, 150)])
+def test_kernel_source_on_host_every_primitive_vs_pillow(size, monkeypatch):
+    """Every primitive through run_plan with the host build of the kernel source, against the pinned oracles — and the
+    affine / resize ones directly against PIL."""
+    import kernel_host_emulation
+    from PIL import Image
+    from torchvision.transforms import v2
+    from torchvision.transforms.v2.functional._geometry import _get_inverse_affine_matrix
+    from textboost_b200.image_plan import run_plan
+    kernel_host_emulation.install(monkeypatch)
+    img = G.make_image(size, 5)
+    base = _plan_of(img)
+    w, h = size
+    mats = {s: _get_inverse_affine_matrix([w * 0.5, h * 0.5], 0.0, [0.0, 0.0], s, [0.0, 0.0]) for s in (0.41, 0.9, 1.37)}
+    m_shift = _get_inverse_affine_matrix([w * 0.5, h * 0.5], 0.0, [-11.0, 0.0], 1.0, [0.0, 0.0])
+    plans = [base.pad_edge(7, 0), base.pad_edge(3, 9), base.crop((4, 6, 30, 29)), base.center_crop(20, 24),
+             base.center_crop(h + 6, w - 5), base.transpose(Image.FLIP_LEFT_RIGHT), base.grayscale(), base.collage(2),
+             base.collage(3), base.affine(m_shift, "nearest"), base.resize((w // 2, h // 3), Image.BICUBIC),
+             base.resize((w + 13, h + 5), Image.BICUBIC), base.resize((w // 2, h // 2), Image.LANCZOS)]
+    plans += [base.affine(m, "bicubic") for m in mats.values()]
+    for plan in plans:
+        got = run_plan(plan, "cpu").numpy()
+        assert np.array_equal(got, plan_standin.run(plan)), plan
+    for s, m in mats.items():
+        ref = v2.functional.affine(img, angle=0, translate=(0, 0), scale=s, shear=0, interpolation=Image.BICUBIC)
+        assert np.array_equal(run_plan(base.affine(m, "bicubic"), "cpu").numpy(), np.asarray(ref)), s
+    ref = np.asarray(img.resize((w // 2, h // 2), Image.LANCZOS))
+    assert np.array_equal(run_plan(base.resize((w // 2, h // 2), Image.LANCZOS), "cpu").numpy(), ref)
