@@ -90,8 +90,19 @@ def install(monkeypatch):
     from textboost_b200 import _cabi, image_ops
 
     def call(name, *args):
-        plain = [a.value if isinstance(a, (ctypes.c_int, ctypes.c_float, ctypes.c_double)) else a for a in args]
-        rc = FAKES[name](*plain)
+        # what ctypes itself would enforce with the declared argtypes: arity, Python ints for the integer slots (a numpy
+        # integer is rejected by c_int), numbers for c_float, pointers / None / addresses for c_void_p
+        sig = _cabi._SIGNATURES[name]
+        assert len(args) == len(sig), (name, len(args), len(sig))
+        for i, (a, t) in enumerate(zip(args, sig)):
+            if t in (ctypes.c_int, ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t):
+                assert type(a) is int, (name, i, type(a))
+            elif t is ctypes.c_float:
+                assert type(a) in (float, int), (name, i, type(a))
+            elif t is ctypes.c_void_p:
+                assert a is None or type(a) is int or isinstance(a, (ctypes.c_void_p, ctypes.Array, ctypes._Pointer)), \
+                    (name, i, type(a))
+        rc = FAKES[name](*args)
         assert rc == 0
 
     monkeypatch.setattr(_cabi, "call", call)
