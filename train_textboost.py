@@ -148,6 +148,14 @@ def _unsupported(args):
         raise NotImplementedError("only the reference's constant LR schedule is built")
     if args.mixed_precision not in (None, "fp16"):
         raise NotImplementedError("the B200 path computes in fp16 with fp32 master weights (--mixed_precision fp16)")
+    if args.text_encoder_use_attention_mask:
+        # train_textboost.py:1058 hands encode_prompt the collated attention_mask, which is a Python LIST
+        # (dataset.py:428, 455): the reference itself fails on `.to(device)` there
+        raise NotImplementedError("--text_encoder_use_attention_mask: the reference's own path fails with this flag "
+                                  "(the collated mask is a list); only the causal-mask path exists")
+    if args.report_to not in (None, "tensorboard"):
+        warnings.warn(f"--report_to {args.report_to}: no tracker is attached here; metrics go to "
+                      "<output_dir>/training.log and RUN_INFO")
     if args.validation_prompts and args.validation_scheduler != "DPMSolverMultistepScheduler":
         raise NotImplementedError("--validation_scheduler: only the default DPMSolverMultistepScheduler is built")
 
