@@ -88,8 +88,6 @@ def _p(a):
 
 def fakes():
     """Drop-in replacements for tests/cabi_standin.py's numpy fakes that run the real kernel source instead."""
-    import numpy as np
-
     import cabi_standin as S
     L = lib()
 
