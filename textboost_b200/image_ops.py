@@ -86,6 +86,8 @@ _device_tables: Dict[tuple, tuple] = {}
 def _tables_on(device, in_size, out_size, filter_name):
     key = (str(device), in_size, out_size, filter_name)
     if key not in _device_tables:
+        if len(_device_tables) >= 512:  # arbitrary source sizes: bound the cache (a few KB to ~100 KB per entry)
+            _device_tables.clear()
         b, w, k = resample_tables(in_size, out_size, filter_name)
         _device_tables[key] = (torch.from_numpy(b).to(device), torch.from_numpy(w).to(device), k, b)
     return _device_tables[key]
