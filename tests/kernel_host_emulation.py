@@ -58,6 +58,70 @@ extern "C" void emu_grayscale(const unsigned char* src, unsigned char* out, long
 """
 
 
+# second host build: the fp16 elementwise kernels of csrc/vae.cu and csrc/sampler.cu (grid-stride ones only; the row
+# softmax is a cooperative 256-thread kernel and is not run here).  __half is the compiler's IEEE binary16 (_Float16).
+SHIM_F16 = r"""
+typedef _Float16 __half;
+struct __half2 { __half x, y; };
+struct float2 { float x, y; };
+struct uint4 { unsigned x, y, z, w; };
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+static inline float __half2float(__half h) { return (float)h; }
+static inline __half __float2half_rn(float f) { return (__half)f; }
+static inline __half __float2half(float f) { return (__half)f; }
+static inline float2 __half22float2(__half2 h) { return float2{(float)h.x, (float)h.y}; }
+#define __shared__ static
+#define __expf(x) expf(x)
+static inline void __syncthreads() {}
+static inline float __shfl_xor_sync(unsigned, float v, int) { return v; }
+namespace tb {
+static inline uint32_t pack_half2(float a, float b) {
+  __half2 h{(__half)a, (__half)b};
+  uint32_t u;
+  memcpy(&u, &h, 4);
+  return u;
+}
+}
+"""
+
+DRIVERS_F16 = r"""
+extern "C" void emu_im2col_pad(const void* x, void* col, int B, int H, int W, int C, int pad_lo) {
+  tb::im2col3x3s2_pad_kernel((const __half*)x, (__half*)col, B, H, W, C, pad_lo);
+}
+extern "C" void emu_vae_sample(const void* m, long long ld, const float* eps, float* lat, float* mean, float* sd, int HW,
+                               int L, long long total, float scale) {
+  tb::vae_sample_kernel((const __half*)m, ld, eps, lat, mean, sd, HW, L, total, scale);
+}
+extern "C" void emu_dpm_cfg_step(float* x, const void* eps, const float* m_prev, float* m_out, void* unet_in, long long n,
+                                 float g, float a_i, float s_i, int v_pred, float c_x, float c_d0, float c_d1) {
+  tb::dpm_cfg_step_kernel(x, (const __half*)eps, m_prev, m_out, (__half*)unet_in, n, g, a_i, s_i, v_pred, c_x, c_d0, c_d1);
+}
+extern "C" void emu_vae_decode_in(const float* lat, const float* w, const float* b, void* z, int L, int HW,
+                                  long long total, float inv_scale) {
+  tb::vae_decode_in_kernel(lat, w, b, (__half*)z, L, HW, total, inv_scale);
+}
+extern "C" void emu_image_u8(const void* x, long long ld, unsigned char* out, long long npix, int channels) {
+  tb::image_u8_kernel((const __half*)x, ld, out, npix, channels);
+}
+"""
+
+_lib_f16 = None
+
+
+def lib_f16():
+    global _lib_f16
+    if _lib_f16 is None:
+        d = tempfile.mkdtemp(prefix="tb_kernel_emu16_")
+        src = os.path.join(d, "emu16.cpp")
+        with open(src, "w") as f:
+            f.write(SHIM + SHIM_F16 + _kernel_text("vae.cu") + "\n" + _kernel_text("sampler.cu") + "\n" + DRIVERS_F16)
+        so = os.path.join(d, "emu16.so")
+        subprocess.run(["g++", "-O1", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC", "-std=c++17",
+                        "-Wno-unknown-pragmas", "-o", so, src], check=True, capture_output=True, text=True)
+        _lib_f16 = ctypes.CDLL(so)
+    return _lib_f16
+
+
 def _kernel_text(name):
     text = open(os.path.join(CSRC, name)).read()
     end = text.index("}  // namespace tb") + len("}  // namespace tb")
