@@ -211,3 +211,26 @@ def test_cli_rejects_what_the_reference_cannot_run():
                                             "--synthetic_data"]))
     with pytest.warns(UserWarning):
         T._unsupported(T.parse_args(base + ["--report_to", "wandb"]))
+
+
+def test_scalar_tracker_writes_tensorboard_events(tmp_path):
+    """accelerator.log / tracker.writer.add_images of the reference (train_textboost.py:1018-1019, 1150, 1232, 518) as
+    TensorBoard event files under <output_dir>/<logging_dir>/textboost; other trackers and non-main ranks are no-ops."""
+    import glob
+    pytest.importorskip("tensorboard")
+    from PIL import Image
+    import train_textboost as T
+    base = ["--pretrained_model_name_or_path", "x", "--output_dir", str(tmp_path)]
+    t = T.ScalarTracker(T.parse_args(base), True)
+    t.log({"loss": 1.5, "lr": 1e-4, "added_embedding_norm": 0.3}, 1)
+    t.images("validation", [Image.new("RGB", (8, 8))] * 2, 1)
+    t.close()
+    events = glob.glob(os.path.join(str(tmp_path), "logs", "textboost", "events*"))
+    assert events and os.path.getsize(events[0]) > 0
+    from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+    acc = EventAccumulator(os.path.dirname(events[0]))
+    acc.Reload()
+    assert {"loss", "lr", "added_embedding_norm"} <= set(acc.Tags()["scalars"])
+    assert acc.Scalars("loss")[0].step == 1 and abs(acc.Scalars("loss")[0].value - 1.5) < 1e-6
+    assert T.ScalarTracker(T.parse_args(base), False).writer is None
+    assert T.ScalarTracker(T.parse_args(base + ["--report_to", "wandb"]), True).writer is None

@@ -19,7 +19,8 @@ Data: with ``--instance_data_dir`` / ``--concepts_list`` the 
 (a ``torch.save``d dict with ``latents`` [N,4,h,w] fp32 — already scaled by the VAE factor — ``input_ids`` [N,77]
 and optional ``prior_ids`` [P,77]) and ``--synthetic_data`` bypass it; both flags are additions, everything else is
 the reference's.  ``--validation_prompts`` samples images every ``--validation_steps`` steps with the B200 sampler
-(textboost_b200.pipeline, §8 f3) and writes ``validation_<step>.jpg``.
+(textboost_b200.pipeline, §8 f3) and writes ``validation_<step>.jpg``.  ``--report_to tensorboard`` (the default) writes
+loss / lr / added_embedding_norm scalars and the validation images as event files under ``<output_dir>/logs/textboost``.
 """
 from __future__ import annotations
 
@@ -239,6 +240,37 @@ def log_validation(text_encoder, tokenizer, unet, vae, args, device, global_step
                                num_inference_steps=25, generator=generator).images)
     RUN_INFO.setdefault("validation_steps", []).append(global_step)
     return images
+
+
+class ScalarTracker:
+    """accelerate's tracker slice the reference uses (train_textboost.py:556-567, 944-945, 1018-1019, 1150, 1232, 1270):
+    ``log({name: value}, step)`` and validation images, written as TensorBoard event files under
+    ``<output_dir>/<logging_dir>/textboost`` when ``--report_to tensorboard`` (the default) and the package imports;
+    otherwise a no-op (the training log and RUN_INFO carry the same numbers)."""
+
+    def __init__(self, args, enabled: bool):
+        self.writer = None
+        if enabled and args.report_to == "tensorboard":
+            try:
+                from torch.utils.tensorboard import SummaryWriter
+                self.writer = SummaryWriter(log_dir=os.path.join(args.output_dir, args.logging_dir, "textboost"))
+            except Exception as e:  # a missing / broken tensorboard must never stop a training run
+                warnings.warn(f"tensorboard tracker unavailable ({e}); metrics stay in training.log")
+
+    def log(self, values: dict, step: int):
+        if self.writer is not None:
+            for name, value in values.items():
+                self.writer.add_scalar(name, float(value), global_step=step)
+
+    def images(self, tag: str, images, step: int):
+        if self.writer is not None and images:
+            import numpy as np
+            self.writer.add_images(tag, np.stack([np.asarray(img) for img in images]), step, dataformats="NHWC")
+
+    def close(self):
+        if self.writer is not None:
+            self.writer.close()
+            self.writer = None
 
 
 def save_learned_embeddings(text_encoder, added_tokens, aug_token_dict, directory):
@@ -478,6 +510,8 @@ def main(args):
             pri = prior_all[pidx[rank * B:(rank + 1) * B]]
         return lat, noise, t, ids, pri
 
+    tracker = ScalarTracker(args, is_main)
+    tracker.log({"mean_norm": mean_norm}, 0)
     logger.info("***** Running training *****")
     logger.info(f"  Instantaneous batch size per device = {B}")
     logger.info(f"  Total train batch size (w. parallel) = {B * world}")
@@ -494,14 +528,17 @@ def main(args):
         step += 1
         if step % args.log_every == 0 or step == args.max_train_steps:
             loss_val = loss.item()  # the reference syncs every step (:1230); here every --log_every steps
+            added_norm = trainer.added_norm.item()
             logger.info(f"step {step} loss {loss_val:.6f} lr {args.learning_rate} "
-                        f"added_embedding_norm {trainer.added_norm.item():.4f}")
+                        f"added_embedding_norm {added_norm:.4f}")
+            tracker.log({"loss": loss_val, "lr": args.learning_rate, "added_embedding_norm": added_norm}, step)
         if is_main and args.validation_prompts and step % args.validation_steps == 0:  # train_textboost.py:1213-1228
             if vae is None or vae.decoder_engine is None:
                 from textboost_b200.vae import AutoencoderKL
                 vae = AutoencoderKL.from_pretrained(path, subfolder="vae", revision=args.revision,
                                                     variant=args.variant).to(device, dtype=torch.float32)
             images = log_validation(text_encoder, tokenizer, unet, vae, args, device, step)
+            tracker.images("validation", images, step)
             if images:
                 from inference import make_image_grid
                 grid = make_image_grid(images, len(args.validation_prompts), args.num_validation_images)
@@ -518,6 +555,7 @@ def main(args):
             text_encoder.to(torch.float32).save_pretrained(os.path.join(args.output_dir, "text_encoder"),
                                                            safe_serialization=not args.no_safe_serialization)
         save_learned_embeddings(text_encoder, added_tokens, aug_token_dict, args.output_dir)
+    tracker.close()
     logger.info(f"Training took {time.perf_counter() - start:.2f} seconds")
     if world > 1:
         # the captured graph holds the NCCL communicator: release it before the ranks part (destroying the process
