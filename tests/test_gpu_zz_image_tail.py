@@ -84,7 +84,8 @@ def test_cli_with_gpu_image_transforms(tmp_path):
             "--pretrained_model_name_or_path", ck, "--output_dir", str(tmp_path / out), "--instance_data_dir",
             str(imgs), "--resolution", "128", "--train_batch_size", "2", "--max_train_steps", "5", "--learning_rate",
             "1e-3", "--mixed_precision", "fp16", "--augment", "pda", "--augment_inversion", "--template", "textboost",
-            "--prior_prompts_file", str(jl), "--log_every", "1", "--seed", "21", *extra]))
+            "--prior_prompts_file", str(jl), "--log_every", "1", "--seed", "21", "--dataloader_num_workers", "0",
+            *extra]))
 
     loss_gpu = run("a", ["--gpu_image_transforms"])
     loss_host = run("b", [])
@@ -167,7 +168,8 @@ def test_cli_with_gpu_augment(tmp_path):
             "--pretrained_model_name_or_path", ck, "--output_dir", str(tmp_path / out), "--instance_data_dir",
             str(imgs), "--resolution", "128", "--train_batch_size", "2", "--max_train_steps", "5", "--learning_rate",
             "1e-3", "--mixed_precision", "fp16", "--augment", "pda", "--augment_inversion", "--augment_p", "0.9",
-            "--template", "textboost", "--prior_prompts_file", str(jl), "--log_every", "1", "--seed", "22", *extra]))
+            "--template", "textboost", "--prior_prompts_file", str(jl), "--log_every", "1", "--seed", "22",
+            "--dataloader_num_workers", "0", *extra]))
 
     loss_gpu = run("a", ["--gpu_augment"])
     loss_host = run("b", [])

@@ -258,3 +258,36 @@ def test_kernel_source_on_host_every_primitive_vs_pillow(size, monkeypatch):
         assert np.array_equal(run_plan(base.affine(m, "bicubic"), "cpu").numpy(), np.asarray(ref)), s
     ref = np.asarray(img.resize((w // 2, h // 2), Image.LANCZOS))
     assert np.array_equal(run_plan(base.resize((w // 2, h // 2), Image.LANCZOS), "cpu").numpy(), ref)
+
+
+def test_cli_image_batches_gpu_augment_equals_host_batches(tmp_path, monkeypatch):
+    """train_textboost.build_image_batches with --gpu_augment (no workers) vs the plain host loader with
+    --dataloader_num_workers 0: identical input_ids and, through the kernel source on the host, identical pixel_values —
+    what tests/test_gpu_zz_image_tail.py::test_cli_with_gpu_augment relies on."""
+    import kernel_host_emulation
+    import train_textboost as T
+    from textboost_b200 import image_ops
+    from textboost_b200.synthetic import LiteralTokenizer
+    kernel_host_emulation.install(monkeypatch)
+    d = tmp_path / "imgs"
+    d.mkdir()
+    for i, size in enumerate([(80, 64), (64, 64), (70, 90)]):
+        G.make_image(size, i).save(d / f"{i}.png")
+
+    def batches(extra):
+        args = T.parse_args(["--pretrained_model_name_or_path", "x", "--instance_data_dir", str(d), "--resolution", "32",
+                             "--train_batch_size", "2", "--augment", "pda", "--augment_inversion", "--augment_p", "0.9",
+                             "--seed", "5", "--template", "textboost", "--dataloader_num_workers", "0", *extra])
+        args.concepts_list = [{"instance_token": ["<dog>"], "instance_data_dir": str(d)}]
+        G.seed_all(5)
+        it = T.build_image_batches(args, LiteralTokenizer(), 0, 1)
+        return [next(it) for _ in range(4)], T.RUN_INFO["dataloader_workers"]
+
+    host, w_host = batches([])
+    plan, w_plan = batches(["--gpu_augment"])
+    assert w_host == 0 and w_plan == 0
+    args = T.parse_args(["--pretrained_model_name_or_path", "x", "--gpu_augment"])
+    assert args.gpu_image_transforms is True
+    for a, b in zip(host, plan):
+        assert torch.equal(a["input_ids"], b["input_ids"])
+        assert torch.equal(image_ops.batch_to_pixel_values(b["sources"], "cpu"), a["pixel_values"])
