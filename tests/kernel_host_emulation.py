@@ -179,6 +179,51 @@ def lib_elementwise():
     return _lib_elementwise
 
 
+# fourth host build: the AdamW arithmetic of csrc/optim.cu (mixing mask, inf / norm reduction, unscale + clip + AdamW
+# update).  With one emulated lane per warp the shuffles contribute nothing and the vote is the lane's own predicate; the
+# finishing kernel (one warp per embedding row, block-wide scalar bookkeeping) is cooperative and is not run here.
+SHIM_OPTIM = r"""
+static inline float __shfl_xor_sync(unsigned, float v, int) { (void)v; return 0.f; }
+static inline int __any_sync(unsigned, int p) { return p; }
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+static inline float atomicAdd(float* p, float v) { float o = *p; *p += v; return o; }
+static inline void __syncthreads() {}
+#define __shared__ static
+using std::isfinite;
+"""
+
+DRIVERS_OPTIM = r"""
+extern "C" void emu_mix_mask(float* g, long long n, int D, int r, int parity) { tb::optim_mix_mask_kernel(g, n, D, r, parity); }
+extern "C" void emu_adamw_reduce_update(float* p, float* g, float* m, float* v, long long n_lora, int n_rows, int D,
+                                        float lr_lora, float lr_emb, float beta1, float beta2, float eps, float wd,
+                                        float max_norm, float inv_world, float* state) {
+  tb::AdamCfg c;
+  c.n_lora = n_lora; c.n_rows = n_rows; c.D = D; c.n_total = n_lora + (long long)n_rows * D;
+  c.lr_lora = lr_lora; c.lr_emb = lr_emb; c.beta1 = beta1; c.beta2 = beta2; c.eps = eps; c.wd = wd;
+  c.max_norm = max_norm; c.inv_world = inv_world; c.mean_norm = 0.f;
+  c.growth_factor = 2.f; c.backoff_factor = 0.5f; c.growth_interval = 2000;
+  tb::optim_reduce_kernel(g, c, state);
+  tb::optim_update_kernel(p, g, m, v, c, state);
+}
+"""
+
+_lib_optim = None
+
+
+def lib_optim():
+    global _lib_optim
+    if _lib_optim is None:
+        d = tempfile.mkdtemp(prefix="tb_kernel_emu_opt_")
+        src = os.path.join(d, "emu_opt.cpp")
+        with open(src, "w") as f:
+            f.write(SHIM + SHIM_OPTIM + _kernel_text("optim.cu") + "\n" + DRIVERS_OPTIM)
+        so = os.path.join(d, "emu_opt.so")
+        subprocess.run(["g++", "-O1", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC", "-std=c++17",
+                        "-Wno-unknown-pragmas", "-o", so, src], check=True, capture_output=True, text=True)
+        _lib_optim = ctypes.CDLL(so)
+    return _lib_optim
+
+
 _lib_f16 = None
 
 

@@ -185,3 +185,57 @@ def test_direct_convolution_kernel_sources():
     dh = torch.empty(2, 6, 5, 16, dtype=torch.float16)
     L.emu_conv_out_bwd4(_p(dy), _p(wo), _p(dh), 2, 6, 5, 16)
     _close16(dh, F.conv_transpose2d(dy.float(), wo.float(), padding=1).permute(0, 2, 3, 1))
+
+
+# ------------------------------------------------------------------ csrc/optim.cu: the AdamW arithmetic (a11-a13)
+def test_adamw_kernel_source_vs_torch_adamw_and_clip():
+    """optim_reduce_kernel + optim_update_kernel (host build) against GradScaler-unscale + clip_grad_norm_(LoRA only) +
+    torch.optim.AdamW with two learning rates, over three steps; then an inf gradient must leave everything untouched
+    and zero the gradient buffer.  The scalar bookkeeping of optim_finish_kernel is done by hand here."""
+    L = K.lib_optim()
+    g = torch.Generator().manual_seed(0)
+    n_lora, n_rows, D = 96, 2, 16
+    n = n_lora + n_rows * D
+    p0 = torch.randn(n, generator=g)
+    p, m, v = p0.clone(), torch.zeros(n), torch.zeros(n)
+    ref_lora = torch.nn.Parameter(p0[:n_lora].clone())
+    ref_rows = torch.nn.Parameter(p0[n_lora:].clone())
+    lr, lr_emb, wd, scale, max_norm = 5e-3, 1e-2, 1e-2, 65536.0, 1.0
+    opt = torch.optim.AdamW([{"params": [ref_rows], "lr": lr_emb}, {"params": [ref_lora], "lr": lr}], betas=(0.9, 0.999),
+                            weight_decay=wd, eps=1e-8)
+    state = torch.zeros(16)
+    state[0], state[5] = scale, 1.0
+    f = ctypes.c_float
+
+    def step(grad_scaled):
+        L.emu_adamw_reduce_update(_p(p), _p(grad_scaled), _p(m), _p(v), ctypes.c_longlong(n_lora), n_rows, D, f(lr),
+                                  f(lr_emb), f(0.9), f(0.999), f(1e-8), f(wd), f(max_norm), f(1.0), _p(state))
+
+    for s in range(3):
+        grad = torch.randn(n, generator=g) * (3.0 if s == 0 else 0.2)  # step 0 exceeds the clip threshold
+        gs = (grad * scale).clone()
+        step(gs)
+        assert gs.abs().max() == 0  # zero_grad folded into the update
+        ref_lora.grad, ref_rows.grad = grad[:n_lora].clone(), grad[n_lora:].clone()
+        norm = torch.nn.utils.clip_grad_norm_([ref_lora], max_norm)
+        assert abs(math_sqrt(state[3].item()) / scale - norm.item()) < 1e-4 * norm.item()
+        opt.step()
+        state[4] += 1  # what optim_finish_kernel does after a good step
+        state[2] = state[3] = 0
+        torch.testing.assert_close(p[:n_lora], ref_lora.detach(), rtol=2e-5, atol=2e-6)
+        torch.testing.assert_close(p[n_lora:], ref_rows.detach(), rtol=2e-5, atol=2e-6)
+    before = p.clone(), m.clone(), v.clone()
+    bad = torch.randn(n, generator=g) * scale
+    bad[5] = float("inf")
+    step(bad)
+    assert state[2] == 1.0 and bad.abs().max() == 0
+    assert torch.equal(p, before[0]) and torch.equal(m, before[1]) and torch.equal(v, before[2])
+    # --mixing mask: lora_B blocks are [D][r]; rows of one parity are zeroed (train_textboost.py:1119-1126)
+    gb = torch.ones(2 * 8 * 4)
+    L.emu_mix_mask(_p(gb), ctypes.c_longlong(gb.numel()), 8, 4, 1)
+    assert torch.equal(gb.view(2, 8, 4)[:, 1::2], torch.zeros(2, 4, 4)) and gb.view(2, 8, 4)[:, 0::2].min() == 1
+
+
+def math_sqrt(x):
+    import math
+    return math.sqrt(x)
