@@ -224,6 +224,56 @@ def lib_optim():
     return _lib_optim
 
 
+# fifth host build: the one-block-per-row / grid-stride kernels of csrc/clip.cu (token + position gather with the lazy
+# decay scalar, sparse embedding-row gradient, LoRA weight packing, activation forward / backward, the TextBoostModel
+# null-embedding override and its gradient mask).  Drivers walk blockIdx.x over the rows.
+DRIVERS_CLIP = r"""
+extern "C" void emu_clip_embed(const long long* ids, const float* base, const float* added, const float* decay,
+                               const float* pos, float* x, int M, int L, int D, int n_base) {
+  for (int m = 0; m < M; ++m) { blockIdx.x = m; tb::clip_embed_kernel(ids, base, added, decay, pos, x, M, L, D, n_base); }
+  blockIdx.x = 0;
+}
+extern "C" void emu_clip_embed_grad(const long long* ids, const float* g, float* rows, int M, int D, int n_base) {
+  for (int m = 0; m < M; ++m) { blockIdx.x = m; tb::clip_embed_grad_kernel(ids, g, rows, M, D, n_base); }
+  blockIdx.x = 0;
+}
+extern "C" void emu_lora_pack(const float* B, void* wext, void* wext_t, int T, int D, int r, int rpad, float scaling) {
+  tb::lora_pack_kernel(B, (__half*)wext, (__half*)wext_t, T, D, r, rpad, scaling);
+}
+extern "C" void emu_act(const void* u, const void* g, void* out, long long n, int kind, int bwd) {
+  if (bwd) tb::act_kernel<true>((const __half*)u, (const __half*)g, (__half*)out, n, kind);
+  else tb::act_kernel<false>((const __half*)u, nullptr, (__half*)out, n, kind);
+}
+extern "C" void emu_null_override(const long long* ids, const float* null_emb, float* h, int B, int L, int D, int eos,
+                                  int use_fixed, int bwd) {
+  for (int m = 0; m < B * L; ++m) {
+    blockIdx.x = m;
+    if (bwd) tb::null_override_kernel<true>(ids, null_emb, h, L, D, eos, use_fixed);
+    else tb::null_override_kernel<false>(ids, null_emb, h, L, D, eos, use_fixed);
+  }
+  blockIdx.x = 0;
+}
+"""
+
+_lib_clip = None
+
+
+def lib_clip():
+    global _lib_clip
+    if _lib_clip is None:
+        d = tempfile.mkdtemp(prefix="tb_kernel_emu_clip_")
+        src = os.path.join(d, "emu_clip.cpp")
+        header = '#include "%s"\n' % os.path.join(ROOT, "include", "textboost_b200.h")
+        with open(src, "w") as f:
+            f.write(SHIM + SHIM_ELEMENTWISE + "#include <algorithm>\nusing std::min; using std::max;\n" + header
+                    + _kernel_text("clip.cu") + "\n" + DRIVERS_CLIP)
+        so = os.path.join(d, "emu_clip.so")
+        subprocess.run(["g++", "-O1", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC", "-std=c++17",
+                        "-Wno-unknown-pragmas", "-o", so, src], check=True, capture_output=True, text=True)
+        _lib_clip = ctypes.CDLL(so)
+    return _lib_clip
+
+
 _lib_f16 = None
 
 

@@ -239,3 +239,75 @@ def test_adamw_kernel_source_vs_torch_adamw_and_clip():
 def math_sqrt(x):
     import math
     return math.sqrt(x)
+
+
+# ------------------------------------------------------------------ csrc/clip.cu: embedding, LoRA packing, override
+def test_clip_embedding_and_override_kernel_sources():
+    """a1 / a5 / a11: token + position gather with the lazy decay scalar and the added rows, the sparse embedding-row
+    gradient (added rows only), the TextBoostModel null-embedding override and its gradient mask
+    (text_encoder.py:71-86)."""
+    L = K.lib_clip()
+    g = torch.Generator().manual_seed(0)
+    V, n_added, D, Lq, B = 50, 3, 16, 7, 4
+    base, added, pos = torch.randn(V, D, generator=g), torch.randn(n_added, D, generator=g), torch.randn(Lq, D, generator=g)
+    decay = torch.tensor([0.97])
+    ids = torch.randint(0, V + n_added, (B, Lq), generator=g)
+    ids[1, 2], ids[2, 5] = V + 1, V
+    x = torch.empty(B * Lq, D)
+    L.emu_clip_embed(_p(ids), _p(base), _p(added), _p(decay), _p(pos), _p(x), B * Lq, Lq, D, V)
+    table = torch.cat([base * 0.97, added])
+    torch.testing.assert_close(x.view(B, Lq, D), table[ids] + pos, rtol=1e-6, atol=1e-6)
+    gout = torch.randn(B * Lq, D, generator=g)
+    rows = torch.zeros(n_added, D)
+    L.emu_clip_embed_grad(_p(ids), _p(gout), _p(rows), B * Lq, D, V)
+    ref = torch.zeros(V + n_added, D).index_add_(0, ids.view(-1), gout)[V:]
+    torch.testing.assert_close(rows, ref, rtol=1e-6, atol=1e-6)
+    EOS = 49407
+    ids2 = torch.randint(0, 40, (B, Lq), generator=g)
+    ids2[1, 1] = EOS  # the empty prompt: BOS, EOS, ...
+    null = torch.randn(Lq, D, generator=g)
+    for fixed in (0, 1):
+        h = torch.randn(B, Lq, D, generator=g)
+        want = h.clone()
+        want[1] = null
+        if fixed:
+            want[:, 0] = null[0]
+        L.emu_null_override(_p(ids2), _p(null), _p(h), B, Lq, D, EOS, fixed, 0)
+        assert torch.equal(h, want)
+        dh = torch.ones(B, Lq, D)
+        L.emu_null_override(_p(ids2), None, _p(dh), B, Lq, D, EOS, fixed, 1)
+        mask = torch.ones(B, Lq, D)
+        mask[1] = 0
+        if fixed:
+            mask[:, 0] = 0
+        assert torch.equal(dh, mask)
+
+
+def test_lora_pack_and_activation_kernel_sources():
+    """a4: the LoRA B blocks packed (scaled) into the K-extension of the fused QKV weight and its transpose;
+    a3: quick_gelu / gelu forward and derivative."""
+    from textboost_b200 import _cabi
+    L = K.lib_clip()
+    g = torch.Generator().manual_seed(1)
+    T, D, r, RPAD = 3, 8, 4, 16
+    Bm = torch.randn(T, D, r, generator=g)
+    Kd = D + RPAD
+    wext = torch.full((T * D, Kd), 7.0, dtype=torch.float16)
+    wext_t = torch.full((Kd, T * D), 7.0, dtype=torch.float16)
+    L.emu_lora_pack(_p(Bm), _p(wext), _p(wext_t), T, D, r, RPAD, ctypes.c_float(0.5))
+    want = torch.zeros(T * D, RPAD)
+    for t in range(T):
+        want[t * D:(t + 1) * D, t * r:(t + 1) * r] = 0.5 * Bm[t]
+    assert torch.equal(wext[:, D:], want.half()) and torch.equal(wext_t[D:], want.half().t())
+    assert (wext[:, :D] == 7).all() and (wext_t[:D] == 7).all()  # the frozen weight block is not touched
+    u = _h(200, seed=2, scale=2.0)
+    gy = _h(200, seed=3)
+    for kind, fn in ((_cabi.TB_ACT_QUICK_GELU, lambda x: x * torch.sigmoid(1.702 * x)), (_cabi.TB_ACT_GELU, F.gelu)):
+        out = torch.empty(200, dtype=torch.float16)
+        L.emu_act(_p(u), None, _p(out), ctypes.c_longlong(200), kind, 0)
+        uf = u.float().requires_grad_(True)
+        y = fn(uf)
+        _close16(out, y.detach())
+        L.emu_act(_p(u), _p(gy), _p(out), ctypes.c_longlong(200), kind, 1)
+        y.backward(gy.float())
+        _close16(out, uf.grad)
