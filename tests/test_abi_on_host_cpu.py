@@ -1,0 +1,191 @@
+"""The SIMT half of the C ABI on the CPU: the product source of csrc/{norm,elementwise,clip,optim,vae,sampler,image,
+augment}.cu — kernels AND extern "C" entry points — built for the host behind a block emulator (every CUDA thread an OS
+thread, real barriers / shuffles / atomics; tests/kernel_host_emulation.py) and bound to the product's own ctypes
+layer.  `ops.*`, `FusedAdamW` and `C.call` then run unchanged on CPU tensors, so the CPU suite exercises the argument
+checks, launch geometry, dispatch and kernel code of 44 entry points against the oracle formulas.  The tcgen05 entry
+points (GEMM, conv3x3, attention) need the hardware and are covered by the `-m gpu` tests only."""
+import ctypes
+from types import SimpleNamespace
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import kernel_host_emulation as K
+
+
+@pytest.fixture()
+def abi(monkeypatch):
+    return K.install_abi(monkeypatch)
+
+
+def _h(*shape, seed=0, scale=1.0, shift=0.0):
+    return (torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale + shift).half()
+
+
+def _close(a, b, tol):
+    d = (a.float() - b.float()).abs().max().item()
+    assert d <= tol * max(1.0, b.float().abs().max().item()), d
+
+
+@pytest.mark.parametrize("B,HW,C,G,silu", [(2, 40, 64, 32, True), (1, 72, 320, 32, False), (2, 9, 640, 32, True)])
+def test_groupnorm_entry_points(abi, B, HW, C, G, silu):
+    """tb_groupnorm_{fwd,bwd}_f16 incl. the two-group fast path (cpg >= 8) and the generic one (cpg = 2)."""
+    from textboost_b200 import ops
+    x = _h(B, HW, C, seed=C, scale=1.5, shift=0.3)
+    gamma, beta = _h(C, seed=1, scale=0.1, shift=1.0), _h(C, seed=2, scale=0.1)
+    y, stats = ops.groupnorm(x, gamma, beta, G, 1e-5, silu)
+    xf = x.float().transpose(1, 2).requires_grad_(True)
+    ref = F.group_norm(xf, G, gamma.float(), beta.float(), 1e-5)
+    ref = F.silu(ref) if silu else ref
+    _close(y, ref.detach().transpose(1, 2), 2e-3)
+    dy, add = _h(B, HW, C, seed=3), _h(B, HW, C, seed=4)
+    dx = ops.groupnorm_bwd(dy, x, gamma, beta, stats, G, 1e-5, silu, add=add)
+    ref.backward(dy.float().transpose(1, 2))
+    _close(dx, xf.grad.transpose(1, 2) + add.float(), 3e-3)
+
+
+@pytest.mark.parametrize("M,C,f32", [(13, 320, False), (9, 640, False), (10, 128, False), (11, 768, True), (6, 1024, True)])
+def test_layernorm_entry_points(abi, M, C, f32):
+    """tb_layernorm_{fwd,bwd}: every lanes-per-row / vectors-per-lane instantiation, fp16 (UNet) and fp32 (CLIP) sets."""
+    from textboost_b200 import ops
+    dt = torch.float32 if f32 else torch.float16
+    g = torch.Generator().manual_seed(C)
+    x = (torch.randn(M, C, generator=g) * 1.3 + 0.2).to(dt)
+    gamma, beta = (1 + 0.1 * torch.randn(C, generator=g)).to(dt), (0.1 * torch.randn(C, generator=g)).to(dt)
+    y, stats = ops.layernorm(x, gamma, beta, eps=1e-5)
+    xf = x.float().requires_grad_(True)
+    ref = F.layer_norm(xf, (C,), gamma.float(), beta.float(), 1e-5)
+    _close(y, ref.detach(), 2e-3)
+    dy = torch.randn(M, C, generator=g).half()
+    add = torch.randn(M, C, generator=g).to(dt)
+    dx = ops.layernorm_bwd(dy, x, gamma, stats, add=add)
+    ref.backward(dy.float())
+    assert dx.dtype == dt
+    _close(dx, xf.grad + add.float(), 3e-3)
+
+
+def test_mse_and_kpl_entry_points(abi):
+    from textboost_b200 import _cabi as C
+    from textboost_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    pred, target = _h(2, 4, 8, 8, seed=1), torch.randn(2, 4, 8, 8, generator=g)
+    loss, scale = torch.zeros(1), torch.tensor([128.0])
+    dpred = ops.mse_fwd_bwd(pred, target, loss, 0.5, scale)
+    pf = pred.float().requires_grad_(True)
+    ref = 0.5 * F.mse_loss(pf, target)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item()) + 1e-7
+    _close(dpred, pf.grad * 128.0, 2e-3)
+    M, D = 10, 96
+    h = torch.randn(M, D, generator=g)
+    h0 = h + 0.3 * torch.randn(M, D, generator=g)
+    for kind, fn in ((0, lambda a: (1 - F.cosine_similarity(a, h0, dim=-1)).mean()), (1, lambda a: F.mse_loss(a, h0))):
+        acc, dh = torch.zeros(1), torch.zeros(M, D)
+        C.call("tb_kpl_fwd_bwd", C.ptr(h), C.ptr(h0), M, D, kind, 0.1, C.ptr(scale), C.ptr(acc), C.ptr(dh),
+               C.stream_ptr())
+        hf = h.clone().requires_grad_(True)
+        ref = 0.1 * fn(hf)
+        ref.backward()
+        assert abs(acc.item() - ref.item()) < 1e-5 * abs(ref.item()) + 1e-8
+        torch.testing.assert_close(dh, hf.grad * 128.0, rtol=1e-4, atol=1e-6)
+
+
+def test_fused_adamw_class_over_the_real_entry_point(abi):
+    """textboost_b200.optim.FusedAdamW (product class) -> tb_optim_mix_mask + tb_adamw_fused_step (all three kernels
+    incl. the cooperative finishing one) vs GradScaler semantics + clip_grad_norm_(LoRA) + torch.optim.AdamW + the
+    added-row renorm of train_textboost.py:1138-1149; then a skipped (inf) step halves the loss scale."""
+    from textboost_b200.optim import FusedAdamW
+    g = torch.Generator().manual_seed(0)
+    D, r, T, n_rows, layers = 16, 4, 3, 2, 2
+    n_a, n_b = layers * T * r * D, layers * T * D * r
+    n_lora = n_a + n_b
+    n = n_lora + n_rows * D
+    params = torch.randn(n, generator=g) * 0.5
+    params[n_lora:] *= 4  # long rows: the renorm must act
+    state = SimpleNamespace(params=params, grads=torch.zeros(n), n_lora=n_lora, n_rows=n_rows, D=D, r=r, n_b=n_b,
+                            rows=lambda buf=None: (params if buf is None else buf)[n_lora:].view(n_rows, D),
+                            b_segment=lambda buf: buf[n_a:n_lora])
+    engine = SimpleNamespace(state=state, tok_base=torch.randn(50, D, generator=g), decay=None)
+    opt = FusedAdamW(engine, lr=5e-3, emb_lr=1e-2, mean_norm=2.0, mixing="object")
+    ref_lora = torch.nn.Parameter(params[:n_lora].clone())
+    ref_rows = torch.nn.Parameter(params[n_lora:].clone())
+    ref = torch.optim.AdamW([{"params": [ref_rows], "lr": 1e-2}, {"params": [ref_lora], "lr": 5e-3}], weight_decay=1e-2)
+    for step in range(3):
+        grad = torch.randn(n, generator=g) * (2.0 if step == 0 else 0.1)
+        state.grads.copy_(grad * 65536.0)
+        opt.step()
+        gl = grad[:n_lora].clone()
+        gl[n_a:].view(-1, D, r)[:, 1::2, :] = 0  # --mixing object: odd rows of every lora_B block
+        ref_lora.grad, ref_rows.grad = gl, grad[n_lora:].clone()
+        norm = torch.nn.utils.clip_grad_norm_([ref_lora], 1.0)
+        ref.step()
+        with torch.no_grad():
+            rows = ref_rows.view(n_rows, D)
+            v = rows.norm(dim=-1, keepdim=True)
+            rows.copy_(torch.minimum(torch.full_like(v, 2.0), v) / v * rows)
+        assert state.grads.abs().max() == 0
+        assert abs(opt.state[7].item() - norm.item()) < 1e-4 * norm.item()
+        assert abs(opt.added_norm.item() - v.mean().item()) < 1e-4 * v.mean().item()
+        torch.testing.assert_close(params[:n_lora], ref_lora.detach(), rtol=2e-5, atol=2e-6)
+        torch.testing.assert_close(params[n_lora:], ref_rows.detach(), rtol=2e-5, atol=2e-6)
+    assert opt.state[4] == 3 and opt.state[1] == 3 and opt.state[0] == 65536.0
+    assert abs(opt.state[5].item() - (1 - 1e-2 * 1e-2) ** 3) < 1e-6  # lazy decay scalar of the frozen rows
+    before = params.clone()
+    state.grads.copy_(torch.randn(n, generator=g))
+    state.grads[7] = float("nan")
+    opt.step()
+    assert torch.equal(params, before) and opt.state[0] == 32768.0 and opt.state[8] == 1 and opt.state[4] == 3
+
+
+def test_softmax_and_direct_conv_entry_points(abi):
+    from textboost_b200 import ops
+    buf = _h(20, 80, seed=5, scale=4.0)
+    x = buf[:, :72]
+    ref = torch.softmax(x.float(), -1)
+    keep = buf[:, 72:].clone()
+    ops.softmax_rows_(x)
+    _close(x, ref, 1e-3)
+    assert torch.equal(buf[:, 72:], keep)
+    h, w, b = _h(1, 6, 5, 64, seed=6), _h(4, 64, 3, 3, seed=7, scale=0.1), _h(4, seed=8, scale=0.1)
+    y = ops.conv_out(h, w, b)  # one warp per pixel
+    _close(y, F.conv2d(h.float().permute(0, 3, 1, 2), w.float(), b.float(), padding=1), 3e-3)
+    dy = _h(1, 4, 6, 5, seed=9)
+    _close(ops.conv_out_bwd(dy, w), F.conv_transpose2d(dy.float(), w.float(), padding=1).permute(0, 2, 3, 1), 3e-3)
+
+
+def test_legacy_causal_attention_entry_points(abi):
+    """tb_clip_attn_{fwd,bwd}: causal softmax(QK^T/8)V over 77 tokens, head_dim 64 (the CUDA-core kernel kept in the
+    ABI), against torch's SDPA and autograd."""
+    from textboost_b200 import _cabi as C
+    B, L, heads = 1, 21, 2
+    D = heads * 64
+    qkv = _h(B * L, 3 * D, seed=10, scale=0.5)
+    out = torch.empty(B * L, D, dtype=torch.float16)
+    C.call("tb_clip_attn_fwd", C.ptr(qkv), C.ptr(out), B, L, D, heads, C.stream_ptr())
+    q, k, v = (t.float().view(B, L, heads, 64).transpose(1, 2).requires_grad_(True) for t in qkv.split(D, dim=1))
+    ref = F.scaled_dot_product_attention(q, k, v, is_causal=True)
+    _close(out.view(B, L, heads, 64).transpose(1, 2), ref.detach(), 3e-3)
+    dO = _h(B * L, D, seed=11)
+    dqkv = torch.empty(B * L, 3 * D, dtype=torch.float16)
+    C.call("tb_clip_attn_bwd", C.ptr(qkv), C.ptr(dO), C.ptr(dqkv), B, L, D, heads, C.stream_ptr())
+    ref.backward(dO.float().view(B, L, heads, 64).transpose(1, 2))
+    want = torch.cat([t.grad.transpose(1, 2).reshape(B * L, D) for t in (q, k, v)], dim=1)
+    _close(dqkv, want, 4e-3)
+
+
+def test_entry_point_argument_checks_and_error_text(abi):
+    """Negative TB_E_* codes with a message through tb_last_error, as the Python layer surfaces them."""
+    from textboost_b200 import _cabi as C
+    from textboost_b200 import ops
+    with pytest.raises(RuntimeError, match="groupnorm: C=60"):
+        ops.groupnorm(_h(1, 4, 60), _h(60), _h(60), 32, 1e-5, True)
+    with pytest.raises(RuntimeError, match="cols=70"):
+        ops.softmax_rows_(_h(4, 70))
+    with pytest.raises(RuntimeError, match="second-order update needs m_prev"):
+        x = torch.zeros(8)
+        ops.dpm_cfg_step(x, torch.zeros(16, dtype=torch.float16), None, torch.zeros(8), None, 7.5, 1.0, 1.0, False, 1.0,
+                         1.0, 0.5)
+    with pytest.raises(RuntimeError, match="tb_conv_out_f16"):
+        ops.conv_out(_h(1, 4, 4, 64), _h(8, 64, 3, 3), _h(8))
+    assert C.launch_count > 0
