@@ -189,3 +189,106 @@ def test_entry_point_argument_checks_and_error_text(abi):
     with pytest.raises(RuntimeError, match="tb_conv_out_f16"):
         ops.conv_out(_h(1, 4, 4, 64), _h(8, 64, 3, 3), _h(8))
     assert C.launch_count > 0
+
+
+def test_unet_data_movement_and_elementwise_wrappers(abi):
+    """ops.* of the UNet's HBM-bound work through their entry points: GEGLU (+bwd), nearest upsample (+bwd), the skip
+    concat / split built on tb_copy2d_f16, fp32->fp16 cast into a strided view, Downsample2D lowering (im2col) and its
+    backward (zero stuffing), timestep embedding, SiLU, DDPM add_noise / velocity target, conv_in."""
+    import ops_standin
+    from oracle import ddpm_ref, unet_ref
+    from textboost_b200 import ops
+    h = _h(6, 48, seed=1)
+    hf = h.float().requires_grad_(True)
+    ref = hf[:, :24] * F.gelu(hf[:, 24:])
+    _close(ops.geglu(h), ref.detach(), 2e-3)
+    dg = _h(6, 24, seed=2)
+    ref.backward(dg.float())
+    _close(ops.geglu_bwd(dg, h), hf.grad, 2e-3)
+    x = _h(2, 3, 5, 16, seed=3)
+    assert torch.equal(ops.upsample2x(x), ops_standin.upsample2x(x))
+    dy = _h(2, 6, 10, 16, seed=4)
+    _close(ops.upsample2x_bwd(dy), dy.float().view(2, 3, 2, 5, 2, 16).sum((2, 4)), 2e-3)
+    a, b = _h(2, 3, 5, 16, seed=5), _h(2, 3, 5, 24, seed=6)
+    cat = ops.concat_channels(a, b)
+    assert torch.equal(cat, torch.cat([a, b], -1))
+    a2, b2 = ops.split_channels(cat, 16)
+    assert torch.equal(a2, a) and torch.equal(b2, b)
+    acc = a.reshape(-1, 16).clone()
+    ops.copy2d(acc, a.reshape(-1, 16), accumulate=True)
+    _close(acc, 2 * a.reshape(-1, 16).float(), 2e-3)
+    f = torch.randn(5, 16, generator=torch.Generator().manual_seed(7))
+    out = torch.zeros(5, 40, dtype=torch.float16)
+    ops.cast_f32_f16(f, out=out[:, 8:24], scale=0.5)
+    assert torch.equal(out[:, 8:24], (f * 0.5).half()) and out[:, :8].abs().max() == 0 and out[:, 24:].abs().max() == 0
+    xd = _h(2, 8, 6, 16, seed=8)
+    assert torch.equal(ops.im2col3x3s2(xd), ops_standin.im2col3x3s2_pad(xd, 1))
+    assert torch.equal(ops.im2col3x3s2_pad(xd, 0), ops_standin.im2col3x3s2_pad(xd, 0))
+    dz = _h(2, 4, 3, 8, seed=9)
+    want = torch.zeros(2, 8, 6, 8, dtype=torch.float16)
+    want[:, ::2, ::2] = dz
+    assert torch.equal(ops.zero_stuff2x(dz), want)
+    t = torch.tensor([0, 1, 500, 999], dtype=torch.int64)
+    _close(ops.timestep_embedding(t, 64), unet_ref.timestep_embedding(t, 64), 2e-3)
+    s = _h(4, 64, seed=10, scale=3.0)
+    _close(ops.silu(s), F.silu(s.float()), 2e-3)
+    g = torch.Generator().manual_seed(11)
+    x0, eps = torch.randn(4, 4, 8, 8, generator=g), torch.randn(4, 4, 8, 8, generator=g)
+    acp = ddpm_ref.alphas_cumprod()
+    noisy, target = ops.add_noise(x0, eps, t, acp, v_prediction=True)
+    _close(noisy, ddpm_ref.add_noise(x0, eps, t), 2e-3)
+    torch.testing.assert_close(target, ddpm_ref.get_velocity(x0, eps, t), rtol=1e-6, atol=1e-6)
+    xi, w, bias = _h(2, 4, 6, 5, seed=12), _h(16, 4, 3, 3, seed=13, scale=0.2), _h(16, seed=14, scale=0.1)
+    _close(ops.conv_in(xi, w, bias), F.conv2d(xi.float(), w.float(), bias.float(), padding=1).permute(0, 2, 3, 1), 2e-3)
+
+
+def test_vae_sampler_and_image_wrappers(abi, monkeypatch):
+    """The late-built entry points through ops / image_ops / image_plan on CPU tensors: Gaussian sample, post_quant_conv
+    input, uint8 write-out, the fused CFG + DPM-Solver++ step, the byte-exact resize / crop / normalise tail and a
+    recorded augmentation plan — the last two against PIL / torchvision bit for bit."""
+    import make_augment_golden as G
+    import numpy as np
+    import ops_standin
+    import plan_standin
+    from PIL import Image
+    from torchvision.transforms import v2
+    from textboost_b200 import augment, image_ops, ops
+    from textboost_b200.image_plan import ImagePlan, run_plan
+    monkeypatch.setattr(image_ops, "_require_cuda", lambda t, what: None)
+    g = torch.Generator().manual_seed(1)
+    rows = torch.randn(3 * 40, 64, generator=g).half()
+    eps = torch.randn(3, 4, 40, generator=g)
+    lat, mean, std = ops.vae_sample(rows, 3, 40, 4, eps=eps, scaling_factor=0.18215, want_moments=True)
+    lat_r, mean_r, std_r = ops_standin.vae_sample(rows, 3, 40, 4, eps=eps, scaling_factor=0.18215, want_moments=True)
+    assert torch.equal(mean, mean_r)
+    torch.testing.assert_close(std, std_r, rtol=2e-7, atol=0)
+    torch.testing.assert_close(lat, lat_r, rtol=1e-6, atol=1e-7)
+    latents = torch.randn(2, 4, 5, 7, generator=g)
+    w, b = torch.randn(4, 4, generator=g) * 0.5, torch.randn(4, generator=g) * 0.1
+    _close(ops.vae_decode_in(latents, w, b, 0.18215), ops_standin.vae_decode_in(latents, w, b, 0.18215), 2e-3)
+    px = (torch.randn(300, 64, generator=g) * 0.8).half()
+    assert torch.equal(ops.image_u8(px, 300, 3), ops_standin.image_u8(px, 300, 3))
+    x = torch.randn(2, 4, 8, 8, generator=g) * 10
+    xr = x.clone()
+    e = torch.randn(4, 4, 8, 8, generator=g).half()
+    m0, m0r = torch.zeros_like(x), torch.zeros_like(x)
+    uin, uin_r = torch.zeros(4, 4, 8, 8, dtype=torch.float16), torch.zeros(4, 4, 8, 8, dtype=torch.float16)
+    ops.dpm_cfg_step(x, e, None, m0, uin, 7.5, 0.07, 0.99, False, 0.8, 0.3, 0.0)
+    ops_standin.dpm_cfg_step(xr, e, None, m0r, uin_r, 7.5, 0.07, 0.99, False, 0.8, 0.3, 0.0)
+    torch.testing.assert_close(x, xr, rtol=1e-5, atol=1e-4)
+    img = G.make_image((90, 70), 3)
+    a = np.asarray(img)
+    resized = v2.Resize(32, interpolation=v2.InterpolationMode.LANCZOS)(img)
+    window = v2.functional.crop(resized, 0, 5, 32, 32)
+    want = v2.Compose([v2.ToImage(), v2.ToDtype(torch.float, scale=True), v2.Normalize((0.5,) * 3, (0.5,) * 3)])(window)
+    got = image_ops.resize_crop_normalize(torch.from_numpy(a.copy()), image_ops.shorter_side_size(90, 70, 32), 0, 5, 32, 32)
+    assert torch.equal(got, want)
+    pipe = augment.PairedAugmentation(**G.PIPES[2])
+    G.seed_all(3)
+    eager = [pipe(G.make_image((64, 64), i), "a dog")[0] for i in range(6)]
+    G.seed_all(3)
+    plans = [pipe(ImagePlan(torch.from_numpy(np.array(G.make_image((64, 64), i), dtype=np.uint8))), "a dog")[0]
+             for i in range(6)]
+    assert sum(len(p.ops) for p in plans) > 3
+    for im, plan in zip(eager, plans):
+        assert np.array_equal(run_plan(plan, "cpu").numpy(), np.asarray(im)), plan
