@@ -292,3 +292,36 @@ def test_vae_sampler_and_image_wrappers(abi, monkeypatch):
     assert sum(len(p.ops) for p in plans) > 3
     for im, plan in zip(eager, plans):
         assert np.array_equal(run_plan(plan, "cpu").numpy(), np.asarray(im)), plan
+
+
+def test_lora_entry_points(abi):
+    """a4: tb_lora_down (xa = LN(x) A^T into the K-extension columns), tb_lora_grad (dB, dA accumulated in fp32 from
+    the fused-QKV gradient) and tb_lora_dx (the A^T path of the input gradient), T = 3 targets of rank 4."""
+    from textboost_b200 import _cabi as C
+    g = torch.Generator().manual_seed(0)
+    M, D, T, r, RPAD = 70, 64, 3, 4, 16
+    R, ld = T * r, D + RPAD
+    A = torch.randn(R, D, generator=g) * 0.3
+    y_ext = torch.full((M, ld), 9.0, dtype=torch.float16)
+    y_ext[:, :D] = _h(M, D, seed=1)
+    C.call("tb_lora_down", C.ptr(y_ext), ld, C.ptr(A), M, D, R, RPAD, C.stream_ptr())
+    y = y_ext[:, :D].float()
+    _close(y_ext[:, D:D + R], y @ A.t(), 2e-3)
+    assert y_ext[:, D + R:].abs().max() == 0
+    dY = _h(M, T * D, seed=2)
+    dA_ext = torch.zeros(M, ld, dtype=torch.float16)
+    dA_ext[:, :D] = _h(M, D, seed=3)
+    dA_ext[:, D:D + R] = _h(M, R, seed=4)
+    dB, dA = torch.ones(T * D, r), torch.ones(R, D)  # accumulate on top of what is there
+    C.call("tb_lora_grad", C.ptr(dY), C.ptr(y_ext), C.ptr(dA_ext), ld, C.ptr(dB), C.ptr(dA), M, T, D, r, 0.5,
+           C.stream_ptr())
+    xa, dxa = y_ext[:, D:D + R].float(), dA_ext[:, D:D + R].float()
+    want_b = torch.cat([0.5 * dY[:, t * D:(t + 1) * D].float().t() @ xa[:, t * r:(t + 1) * r] for t in range(T)]) + 1
+    torch.testing.assert_close(dB, want_b, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(dA, dxa.t() @ y + 1, rtol=1e-4, atol=1e-4)
+    before = dA_ext[:, :D].float().clone()
+    C.call("tb_lora_dx", C.ptr(dA_ext), ld, C.ptr(A), M, D, R, C.stream_ptr())
+    _close(dA_ext[:, :D], before + dxa @ A, 2e-3)
+    with pytest.raises(RuntimeError, match="tb_lora_grad"):
+        C.call("tb_lora_grad", C.ptr(dY), C.ptr(y_ext), C.ptr(dA_ext), ld, C.ptr(dB), C.ptr(dA), M, T, D, 9, 0.5,
+               C.stream_ptr())
