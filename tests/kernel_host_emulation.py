@@ -357,29 +357,35 @@ static inline uint32_t pack_half2(float a, float b) {
 float sg[1 << 16];
 __half sw[1 << 17];
 }
-// run f() as gridDim blocks of `threads` threads
+// run f() as gridDim blocks of `threads` threads: one pool of OS threads per launch walks the blocks in order; thread 0
+// installs the block's barriers between two launch-wide phases
 static void emu_launch(unsigned gx, unsigned gy, unsigned threads, const std::function<void()>& f) {
   gridDim = {gx, gy, 1};
   blockDim = {threads, 1, 1};
-  const unsigned warps = (threads + 31) / 32;
-  for (unsigned by = 0; by < gy; ++by)
-    for (unsigned bx = 0; bx < gx; ++bx) {
-      blockIdx = {bx, by, 0};
-      std::barrier<> block_bar(threads);
-      emu_block_bar = &block_bar;
-      emu_warp_bar.clear();
-      for (unsigned w = 0; w < warps; ++w)
-        emu_warp_bar.emplace_back(new std::barrier<>(std::min(32u, threads - 32 * w)));
-      std::vector<std::thread> pool;
-      for (unsigned t = 0; t < threads; ++t)
-        pool.emplace_back([&, t] {
-          threadIdx = {t, 0, 0};
-          f();
-          emu_warp_bar[t >> 5]->arrive_and_drop();  // a finished thread no longer takes part in barriers
-          emu_block_bar->arrive_and_drop();
-        });
-      for (auto& th : pool) th.join();
-    }
+  const unsigned warps = (threads + 31) / 32, nblocks = gx * gy;
+  std::barrier<> phase(threads);
+  std::unique_ptr<std::barrier<>> block_bar;
+  std::vector<std::thread> pool;
+  for (unsigned t = 0; t < threads; ++t)
+    pool.emplace_back([&, t] {
+      threadIdx = {t, 0, 0};
+      for (unsigned b = 0; b < nblocks; ++b) {
+        if (t == 0) {
+          blockIdx = {b % gx, b / gx, 0};
+          block_bar.reset(new std::barrier<>(threads));
+          emu_block_bar = block_bar.get();
+          emu_warp_bar.clear();
+          for (unsigned w = 0; w < warps; ++w)
+            emu_warp_bar.emplace_back(new std::barrier<>(std::min(32u, threads - 32 * w)));
+        }
+        phase.arrive_and_wait();
+        f();
+        emu_warp_bar[t >> 5]->arrive_and_drop();  // a finished thread no longer takes part in the block's barriers
+        emu_block_bar->arrive_and_drop();
+        phase.arrive_and_wait();
+      }
+    });
+  for (auto& th : pool) th.join();
 }
 """
 

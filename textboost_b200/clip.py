@@ -180,7 +180,7 @@ class ClipEngine:
     # ------------------------------------------------------------------ forward
     def forward(self, input_ids: torch.Tensor, save_for_backward: bool = False) -> torch.Tensor:
         """input_ids int64 [B, L] on the device -> last_hidden_state fp32 [B, L, D] (after the override)."""
-        assert input_ids.dtype == torch.int64 and input_ids.is_cuda
+        assert input_ids.dtype == torch.int64 and input_ids.device.type == self.device.type
         ids = input_ids.contiguous()
         B, Lq = ids.shape
         D, M = self.D, B * Lq
