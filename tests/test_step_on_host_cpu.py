@@ -10,6 +10,9 @@ import torch
 
 import engine_standin
 
+# a stuck barrier in the block emulator must fail the test, not hang the suite
+pytestmark = pytest.mark.timeout(900)
+
 
 def _compare(monkeypatch, B, **trainer_kw):
     from oracle import harness
