@@ -14,7 +14,7 @@ import torch.nn.functional as F
 import kernel_host_emulation as K
 
 # a stuck barrier in the block emulator must fail the test, not hang the suite
-pytestmark = pytest.mark.timeout(600)
+pytestmark = pytest.mark.timeout(600, method="thread")
 
 
 @pytest.fixture()

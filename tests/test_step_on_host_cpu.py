@@ -11,7 +11,7 @@ import torch
 import engine_standin
 
 # a stuck barrier in the block emulator must fail the test, not hang the suite
-pytestmark = pytest.mark.timeout(900)
+pytestmark = pytest.mark.timeout(900, method="thread")
 
 
 def _compare(monkeypatch, B, **trainer_kw):
