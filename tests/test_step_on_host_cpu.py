@@ -54,3 +54,19 @@ def test_image_prior_step_on_cpu_matches_oracle(monkeypatch):
     with pytest.raises(ValueError):
         tr.forward_backward(bt["latents"][:3], bt["noise"][:3], bt["timesteps"][:3], bt["input_ids"][:3],
                             bt["prior_ids"][:3])
+
+
+def test_sd2x_shaped_step_on_cpu_matches_oracle(monkeypatch):
+    """The SD-2.x branches at toy widths: linear (not 1x1-conv) Transformer2D projections, head_dim 64, and the OpenCLIP
+    text encoder's erf-gelu, with v-prediction — what tests/test_gpu_step.py::test_step_sd21_openclip_h_vs_oracle covers
+    at full width on the GPU."""
+    from textboost_b200 import synthetic
+    from textboost_b200.clip import ClipConfig
+    from textboost_b200.unet import UNetConfig
+    small = (UNetConfig(block_out_channels=(64, 128, 128, 128), attention_head_dim=(1, 2, 2, 2), cross_attention_dim=128,
+                        use_linear_projection=True, sample_size=16),
+             ClipConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2,
+                        hidden_act="gelu"))
+    monkeypatch.setattr(synthetic, "model_configs", lambda model: small)
+    r, tr, _ = _compare(monkeypatch, 2, prediction_type="v_prediction", kpl_type="mse")
+    _check(r, tr)
