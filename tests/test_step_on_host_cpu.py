@@ -70,3 +70,36 @@ def test_sd2x_shaped_step_on_cpu_matches_oracle(monkeypatch):
     monkeypatch.setattr(synthetic, "model_configs", lambda model: small)
     r, tr, _ = _compare(monkeypatch, 2, prediction_type="v_prediction", kpl_type="mse")
     _check(r, tr)
+
+
+def test_three_steps_track_the_oracle(monkeypatch):
+    """Optimiser state and the re-packed LoRA weights across steps: three product steps against three oracle steps from
+    the same start.  Adam moves every parameter by ~lr per step whatever the gradient's size, so parameters may differ
+    by a couple of lr where a gradient is ~0; the losses must keep tracking."""
+    from oracle import harness, step_ref
+    from textboost_b200 import synthetic
+    engine_standin.install(monkeypatch)
+    tr = synthetic.build_trainer("tiny", "cpu", seed=2, n_added=1, lora_b_std=0.02, keep_sd=True, learning_rate=1e-3,
+                                 emb_learning_rate=1e-2)
+    unet, te, te0, opt = harness.twin_of(tr, "cpu", torch.float32)
+    V = tr.synthetic["clip_cfg"].vocab_size
+    bt = synthetic.batch(2, 8, 5, V, "cpu")
+    losses, refs = [], []
+    for _ in range(3):
+        losses.append(tr.step(bt["latents"], bt["noise"], bt["timesteps"], bt["input_ids"], bt["prior_ids"]).item())
+        refs.append(step_ref.reference_step(unet, te, te0, bt["latents"], bt["noise"], bt["timesteps"], bt["input_ids"],
+                                            bt["prior_ids"], n_base=V, kpl_weight=tr.kpl_weight, kpl_type="cos",
+                                            optimizer=opt, max_grad_norm=tr.max_grad_norm,
+                                            mean_norm=tr.mean_norm)["loss"].item())
+    for a, b in zip(losses, refs):
+        assert abs(a - b) < 5e-3 * abs(b), (losses, refs)
+    assert tr.opt_state[4].item() == 3 and tr.opt_state[8].item() == 0
+    st, r, worst = tr.te.state, tr.te.state.r, 0.0
+    for l, lyr in enumerate(te.text_model.encoder.layers):
+        for ti, t in enumerate(harness.LORA_TARGETS):
+            m = getattr(lyr.self_attn, t)
+            worst = max(worst, (st.A(l)[ti * r:(ti + 1) * r] - m.lora_A["default"].weight).abs().max().item(),
+                        (st.B(l)[ti] - m.lora_B["default"].weight).abs().max().item())
+    assert worst <= 3 * 2.1 * tr.lr, worst
+    emb = te.get_input_embeddings().weight.detach()
+    assert harness.rel_max(st.rows(), emb[V:]) < 5e-2
