@@ -357,35 +357,74 @@ static inline uint32_t pack_half2(float a, float b) {
 float sg[1 << 16];
 __half sw[1 << 17];
 }
-// run f() as gridDim blocks of `threads` threads: one pool of OS threads per launch walks the blocks in order; thread 0
-// installs the block's barriers between two launch-wide phases
+// A process-wide pool of OS threads (never torn down: the workers sleep on a barrier until the process exits) runs every
+// launch: worker t plays CUDA thread t of each block in turn; thread 0 installs the block's barriers between two
+// launch-wide phases.  Blocks of more threads than the pool holds are not used by these kernels.
+constexpr unsigned EMU_MAX_THREADS = 320;
+struct EmuPool {
+  std::barrier<> go{EMU_MAX_THREADS + 1}, done{EMU_MAX_THREADS + 1};
+  const std::function<void(unsigned)>* job = nullptr;
+  EmuPool() {
+    for (unsigned t = 0; t < EMU_MAX_THREADS; ++t)
+      std::thread([this, t] {
+        for (;;) {
+          go.arrive_and_wait();
+          (*job)(t);
+          done.arrive_and_wait();
+        }
+      }).detach();
+  }
+  void run(const std::function<void(unsigned)>& j) {
+    job = &j;
+    go.arrive_and_wait();
+    done.arrive_and_wait();
+  }
+};
+static EmuPool& emu_pool() {
+  static EmuPool* p = new EmuPool;
+  return *p;
+}
 static void emu_launch(unsigned gx, unsigned gy, unsigned threads, const std::function<void()>& f) {
+  if (threads > EMU_MAX_THREADS) abort();
   gridDim = {gx, gy, 1};
   blockDim = {threads, 1, 1};
   const unsigned warps = (threads + 31) / 32, nblocks = gx * gy;
   std::barrier<> phase(threads);
   std::unique_ptr<std::barrier<>> block_bar;
-  std::vector<std::thread> pool;
-  for (unsigned t = 0; t < threads; ++t)
-    pool.emplace_back([&, t] {
-      threadIdx = {t, 0, 0};
-      for (unsigned b = 0; b < nblocks; ++b) {
-        if (t == 0) {
-          blockIdx = {b % gx, b / gx, 0};
-          block_bar.reset(new std::barrier<>(threads));
-          emu_block_bar = block_bar.get();
-          emu_warp_bar.clear();
-          for (unsigned w = 0; w < warps; ++w)
-            emu_warp_bar.emplace_back(new std::barrier<>(std::min(32u, threads - 32 * w)));
-        }
-        phase.arrive_and_wait();
-        f();
-        emu_warp_bar[t >> 5]->arrive_and_drop();  // a finished thread no longer takes part in the block's barriers
-        emu_block_bar->arrive_and_drop();
-        phase.arrive_and_wait();
+  emu_pool().run([&](unsigned t) {
+    if (t >= threads) return;
+    threadIdx = {t, 0, 0};
+    for (unsigned b = 0; b < nblocks; ++b) {
+      if (t == 0) {
+        blockIdx = {b % gx, b / gx, 0};
+        block_bar.reset(new std::barrier<>(threads));
+        emu_block_bar = block_bar.get();
+        emu_warp_bar.clear();
+        for (unsigned w = 0; w < warps; ++w)
+          emu_warp_bar.emplace_back(new std::barrier<>(std::min(32u, threads - 32 * w)));
       }
-    });
-  for (auto& th : pool) th.join();
+      phase.arrive_and_wait();
+      f();
+      emu_warp_bar[t >> 5]->arrive_and_drop();  // a finished thread no longer takes part in the block's barriers
+      emu_block_bar->arrive_and_drop();
+      phase.arrive_and_wait();
+    }
+  });
+}
+// kernels without shared memory, barriers or shuffles: every CUDA thread is independent, so one host thread plays them
+// all in turn (atomics stay atomic)
+static void emu_launch_serial(unsigned gx, unsigned gy, unsigned threads, const std::function<void()>& f) {
+  gridDim = {gx, gy, 1};
+  blockDim = {threads, 1, 1};
+  for (unsigned by = 0; by < gy; ++by)
+    for (unsigned bx = 0; bx < gx; ++bx) {
+      blockIdx = {bx, by, 0};
+      for (unsigned t = 0; t < threads; ++t) {
+        threadIdx = {t, 0, 0};
+        f();
+      }
+    }
+  threadIdx = {0, 0, 0};
 }
 """
 
@@ -445,6 +484,27 @@ def lib_norm():
 # stream>>>(args);` is rewritten textually into `emu_launch(grid, block, [&] { kernel(args); });`; the handful of runtime
 # calls the entry points make (cudaMemsetAsync, cudaFuncSetAttribute, tb_check_device, check_launch, set_error) are
 # shimmed.  The tcgen05 files (gemm.cu, attn.cu) are not part of it.
+_COOPERATIVE_TOKENS = ("__syncthreads", "__shfl", "__shared__", "__any_sync", "warp_sum", "group_sum")
+
+
+def _is_cooperative(kernel: str, text: str) -> bool:
+    """Does the kernel's body use shared memory, barriers or warp shuffles (directly or through the warp-sum helpers)?"""
+    import re
+    base = kernel.split("<")[0].split("::")[-1]
+    m = re.search(r"__global__[^;{]*?\b" + re.escape(base) + r"\s*\(", text)
+    if not m:
+        return True
+    k = text.index("{", m.end())
+    depth, q = 0, k
+    while True:
+        depth += {"{": 1, "}": -1}.get(text[q], 0)
+        if depth == 0:
+            break
+        q += 1
+    body = text[k:q]
+    return any(tok in body for tok in _COOPERATIVE_TOKENS)
+
+
 def _rewrite_launches(text: str) -> str:
     out, i = [], 0
     while True:
@@ -482,7 +542,8 @@ def _rewrite_launches(text: str) -> str:
             q += 1
         args = text[p + 1:q]
         out.append(text[i:k])
-        out.append(f"emu_launch({parts[0].strip()}, {parts[1].strip()}, [&] {{ {name}({args}); }})")
+        launcher = "emu_launch" if _is_cooperative(name, text) else "emu_launch_serial"
+        out.append(f"{launcher}({parts[0].strip()}, {parts[1].strip()}, [&] {{ {name}({args}); }})")
         i = q + 1
 
 
@@ -512,6 +573,9 @@ float smf[1 << 18];
 #undef TB_REQUIRE
 #define TB_REQUIRE(cond, code, ...) do { if (!(cond)) { tb::set_error(__VA_ARGS__); return (code); } } while (0)
 static void emu_launch(dim3 grid, dim3 block, const std::function<void()>& f) { emu_launch(grid.x, grid.y, block.x, f); }
+static void emu_launch_serial(dim3 grid, dim3 block, const std::function<void()>& f) {
+  emu_launch_serial(grid.x, grid.y, block.x, f);
+}
 """
 
 ABI_FILES = ["norm.cu", "elementwise.cu", "clip.cu", "optim.cu", "vae.cu", "sampler.cu", "image.cu", "augment.cu"]
