@@ -236,20 +236,26 @@ int tb_img_grayscale_u8(const void* src, void* out, int64_t npix, void* stream);
 /* ---- CLIP text encoder pieces that are not GEMM / LayerNorm ------------------------------------
  * (transformers CLIPTextTransformer called from textboost/text_encoder.py:62-69; peft LoRA Linear
  * configured at train_textboost.py:702-709.) */
-/* x[m,:] = tok(ids[m]) + pos[m % L]; tok(id) = id < n_base ? base[id] * (*decay) : added[id - n_base]. */
+/* x[m,:] = tok(ids[m]) + pos[m % L]; tok(id) = id < n_base ? base[id] * (*decay) : added[id - n_base].
+ * An id outside [0, n_base + n_rows) -- torch's embedding lookup raises for it -- fills its row with NaN instead of
+ * dereferencing (the loss turns NaN and the GradScaler skips the step). */
 int tb_clip_embed(const int64_t* ids, const float* base, const float* added, const float* decay,
-                  const float* pos, float* x, int M, int L, int D, int n_base, void* stream);
+                  const float* pos, float* x, int M, int L, int D, int n_base, int n_rows, void* stream);
 /* grad_rows[id - n_base, :] += g[m, :] for id >= n_base only (train_textboost.py:1109-1117). */
 int tb_clip_embed_grad(const int64_t* ids, const float* g, float* grad_rows, int M, int D, int n_base,
                        void* stream);
-/* LoRA fused into the QKV GEMM as a K-extension: y_ext[:, D:D+R] = y_ext[:, :D] @ A^T (A fp32 [R, D]). */
+/* peft LoRA Linear (tuners/lora/layer.py, y = W x + b + (alpha/r) B A x; configured at train_textboost.py:702-709)
+ * fused into a projection GEMM as a K-extension.  A fused weight stacks nblk row blocks of D outputs (q | k | v:
+ * nblk 3; out_proj: nblk 1); bit b of tmask says block b carries LoRA; T = popcount(tmask), rank r <= 16,
+ * R = T*r <= RPAD <= 64 extension columns.
+ * y_ext[:, D:D+R] = y_ext[:, :D] @ A^T (A fp32 [R, D]); columns D+R..D+RPAD-1 are zeroed. */
 int tb_lora_down(void* y_ext, int64_t ld, const float* A, int M, int D, int R, int RPAD, void* stream);
-/* write scaling*B (fp32 [T][D][r]) into the extension block of Wext [T*D, D+RPAD] and WextT. */
-int tb_lora_pack(const float* B, void* Wext, void* WextT, int T, int D, int r, int RPAD, float scaling,
-                 void* stream);
-/* dB [T][D][r] += scaling * dY^T xa ;  dA [T*r][D] += dxa^T y   (accumulating, fp32). */
+/* write scaling*B (fp32 [T][D][r]) into the extension block of Wext [nblk*D, D+RPAD] and WextT [D+RPAD, nblk*D]. */
+int tb_lora_pack(const float* B, void* Wext, void* WextT, int nblk, int tmask, int D, int r, int RPAD,
+                 float scaling, void* stream);
+/* dB [T][D][r] += scaling * dY^T xa ;  dA [T*r][D] += dxa^T y   (accumulating, fp32); dY is [M, nblk*D]. */
 int tb_lora_grad(const void* dY, const void* y_ext, const void* dA_ext, int64_t ld, float* dB, float* dA,
-                 int M, int T, int D, int r, float scaling, void* stream);
+                 int M, int nblk, int tmask, int D, int r, float scaling, void* stream);
 /* dA_ext[:, :D] += dA_ext[:, D:D+R] @ A. */
 int tb_lora_dx(void* dA_ext, int64_t ld, const float* A, int M, int D, int R, void* stream);
 /* causal attention over L <= 128 tokens, head_dim 64; qkv [B*L, 3D] fused; dqkv laid out like qkv. */

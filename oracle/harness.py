@@ -18,7 +18,12 @@ import torch
 
 from . import clip_ref, step_ref, unet_ref
 
-LORA_TARGETS = ("q_proj", "k_proj", "v_proj")
+LORA_TARGETS = ("q_proj", "k_proj", "v_proj")  # the reference's targets (train_textboost.py:705)
+
+
+def targets_of(trainer):
+    """LoRA targets of the product engine, in the order of its flat trainable buffer."""
+    return tuple(getattr(trainer.te, "targets", LORA_TARGETS)) or LORA_TARGETS
 
 
 def _unet_cfg(c) -> unet_ref.UNetConfig:
@@ -43,15 +48,24 @@ def rel_max(a: torch.Tensor, b: torch.Tensor) -> float:
     return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
 
 
-def twin_of(trainer, device="cpu", dtype=torch.float32):
-    """(unet, te, te0, optimizer) oracle modules with the trainer's current weights."""
+def pass_fraction(a: torch.Tensor, b: torch.Tensor, rtol=1e-3, atol=1e-4) -> float:
+    """fraction of elements with |a - b| <= atol + rtol |b| (torch.allclose's criterion, the north star's
+    rtol 1e-3 / atol 1e-4), reported rather than asserted as all-or-nothing."""
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).abs() <= atol + rtol * b.abs()).float().mean().item()
+
+
+def twin_of(trainer, device="cpu", dtype=torch.float32, frozen_dtype=None):
+    """(unet, te, te0, optimizer) oracle modules with the trainer's current weights.  frozen_dtype (fp16): the
+    reference's weight_dtype cast of the UNet and the frozen text encoder (train_textboost.py:937-939)."""
+    frozen_dtype = dtype if frozen_dtype is None else frozen_dtype
     syn = trainer.synthetic
     assert "unet_sd" in syn, "build the trainer with keep_sd=True"
     ucfg, ccfg = syn["unet_cfg"], syn["clip_cfg"]
     V, n_added, r = ccfg.vocab_size, syn["n_added"], syn["lora_r"]
     unet = unet_ref.UNet2DConditionModelRef(_unet_cfg(ucfg))
     unet.load_state_dict({k: v.detach().to("cpu", torch.float32) for k, v in syn["unet_sd"].items()})
-    unet = unet.to(device, dtype).requires_grad_(False)
+    unet = unet.to(device, frozen_dtype).requires_grad_(False)
     csd = {k: v.detach().to("cpu", torch.float32) for k, v in syn["clip_sd"].items()}
     te_eng = trainer.te
     null = te_eng.null_embedding.detach().to("cpu", torch.float32)
@@ -60,7 +74,7 @@ def twin_of(trainer, device="cpu", dtype=torch.float32):
         te0 = clip_ref.TextBoostModelRef(_clip_cfg(ccfg))
         te0.load_state_dict(csd, strict=False)
         te0.set_null_embedding(null.clone())
-        te0 = te0.to(device, dtype).requires_grad_(False)
+        te0 = te0.to(device, frozen_dtype).requires_grad_(False)
     te = clip_ref.TextBoostModelRef(_clip_cfg(ccfg))
     te.load_state_dict(csd, strict=False)
     te.resize_token_embeddings(V + n_added)
@@ -70,10 +84,10 @@ def twin_of(trainer, device="cpu", dtype=torch.float32):
     te.set_null_embedding(null.clone())
     te.requires_grad_(False)
     if r:
-        te.add_adapter(r=r)
+        te.add_adapter(r=r, lora_alpha=getattr(te_eng, "scaling", 1.0) * r, target_modules=targets_of(trainer))
         with torch.no_grad():
             for l, lyr in enumerate(te.text_model.encoder.layers):
-                for ti, t in enumerate(LORA_TARGETS):
+                for ti, t in enumerate(targets_of(trainer)):
                     m = getattr(lyr.self_attn, t)
                     m.lora_A["default"].weight.copy_(st.A(l)[ti * r:(ti + 1) * r].cpu())
                     m.lora_B["default"].weight.copy_(st.B(l)[ti].cpu())
@@ -91,7 +105,7 @@ def lora_grads_flat(trainer, ref_grads: Dict[str, torch.Tensor], buf: torch.Tens
     r = st.r
     ours, refs, worst = [], [], 0.0
     for l in range(st.n_layers):
-        for ti, t in enumerate(LORA_TARGETS):
+        for ti, t in enumerate(targets_of(trainer)):
             n = f"text_model.encoder.layers.{l}.self_attn.{t}."
             ra = ref_grads[n + "lora_A.default.weight"]
             rb = ref_grads[n + "lora_B.default.weight"]
@@ -102,9 +116,37 @@ def lora_grads_flat(trainer, ref_grads: Dict[str, torch.Tensor], buf: torch.Tens
     return torch.cat(ours), torch.cat(refs), worst
 
 
+def _reference_fp16_policy(trainer, b, V, kind, use_kpl, device):
+    """The same step through torch's own fp16 kernels under the reference's precision policy (step_ref
+    mixed_precision="fp16"): returns (pred, LoRA grad vector, added-row grads) on the CPU."""
+    unet, te, te0, _ = twin_of(trainer, device, torch.float32, frozen_dtype=torch.float16)
+    ref = step_ref.reference_step(
+        unet, te, te0, b["latents"].float(), b["noise"].float(), b["timesteps"], b["input_ids"],
+        b["prior_ids"] if use_kpl else None, n_base=V, kpl_weight=trainer.kpl_weight, kpl_type=kind,
+        prediction_type="v_prediction" if trainer.v_pred else "epsilon", optimizer=None, mixing=trainer.mixing,
+        image_ppl_weight=getattr(trainer, "image_prior_weight", None), mixed_precision="fp16",
+        loss_scale=65536.0)
+    _, gr, _ = lora_grads_flat(trainer, ref["grad_lora"], trainer.te.state.grads)
+    rows = ref["grad_rows"].detach().float().cpu() if ref["grad_rows"] is not None else None
+    return ref["pred"].detach().float().cpu(), gr, rows
+
+
 def compare_step(trainer, batch: Dict[str, torch.Tensor], device="cpu", dtype=torch.float32,
-                 with_optimizer=True) -> Dict[str, float]:
-    """Run one step on the product (trainer, CUDA) and on the oracle twin; return error metrics."""
+                 with_optimizer=True, fp16_reference=False) -> Dict[str, float]:
+    """Run one step on the product (trainer, CUDA) and on the oracle twin; return error metrics.
+
+    fp16_reference (device must be CUDA): also run the oracle under the reference's fp16 policy and report the
+    north star's elementwise criterion (rtol 1e-3 / atol 1e-4) three ways -- ours vs fp32 oracle, torch-fp16 vs
+    fp32 oracle, ours vs torch-fp16 -- as pass fractions (keys tol_*)."""
+    ref16 = None
+    if fp16_reference:
+        V0 = trainer.synthetic["clip_cfg"].vocab_size
+        use_kpl0 = trainer.kpl_weight > 0 and trainer.te0 is not None
+        b0 = {k: v.to(device) for k, v in batch.items()}
+        ref16 = _reference_fp16_policy(trainer, b0, V0, {0: "cos", 1: "mse"}[trainer.kpl_kind], use_kpl0, device)
+        del b0
+        if torch.cuda.is_available():
+            torch.cuda.empty_cache()
     unet, te, te0, opt = twin_of(trainer, device, dtype)
     V = trainer.synthetic["clip_cfg"].vocab_size
     kind = {0: "cos", 1: "mse"}[trainer.kpl_kind]
@@ -133,9 +175,20 @@ def compare_step(trainer, batch: Dict[str, torch.Tensor], device="cpu", dtype=to
     out["lora_grad_cos"] = torch.nn.functional.cosine_similarity(go, gr, dim=0).item()
     out["lora_grad_worst_tensor_rel"] = worst
     out["lora_grad_ours"], out["lora_grad_ref"] = go, gr
+    out["pred_ref"] = ref["pred"].detach().float().cpu()
     if ref["grad_rows"] is not None and st.n_rows:
         out["row_grad_rel"] = rel_max(st.rows(g), ref["grad_rows"])
         out["row_grad_ours"], out["row_grad_ref"] = st.rows(g).detach().cpu(), ref["grad_rows"].detach().cpu()
+    if ref16 is not None:
+        p16, g16, r16 = ref16
+        pairs = {"pred": (trainer._pred, ref["pred"], p16), "lora_grad": (go, gr, g16)}
+        if r16 is not None and st.n_rows:
+            pairs["row_grad"] = (st.rows(g), ref["grad_rows"], r16)
+        for name, (ours, r32, r16v) in pairs.items():
+            out[f"tol_{name}_ours_vs_fp32"] = pass_fraction(ours, r32)
+            out[f"tol_{name}_torch16_vs_fp32"] = pass_fraction(r16v, r32)
+            out[f"tol_{name}_ours_vs_torch16"] = pass_fraction(ours, r16v)
+            out[f"rel_{name}_torch16_vs_fp32"] = rel_max(r16v, r32)
     if with_optimizer:
         trainer.all_reduce()
         trainer.optimizer_step()
@@ -147,7 +200,7 @@ def compare_step(trainer, batch: Dict[str, torch.Tensor], device="cpu", dtype=to
         p_ours, p_ref = [], []
         r = st.r
         for l, lyr in enumerate(te.text_model.encoder.layers):
-            for ti, t in enumerate(LORA_TARGETS):
+            for ti, t in enumerate(targets_of(trainer)):
                 m = getattr(lyr.self_attn, t)
                 p_ours += [st.A(l)[ti * r:(ti + 1) * r].detach().cpu().flatten(), st.B(l)[ti].detach().cpu().flatten()]
                 p_ref += [m.lora_A["default"].weight.detach().cpu().flatten(),

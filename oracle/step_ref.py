@@ -13,11 +13,17 @@ Follows /root/reference/train_textboost.py line by line:
   :1128-1133  clip_grad_norm_(text_model.encoder.parameters(), max_grad_norm)   (LoRA only)
   :1134-1136  AdamW step (embedding lr = emb_learning_rate, LoRA lr = learning_rate), zero_grad
   :1138-1149  renormalise the added rows to norm <= mean_norm
-The fp16 autocast / GradScaler of accelerate is NOT modelled: the oracle is the exact-arithmetic
-(fp32, or fp64 when the caller casts the modules) statement of the same function.
+By default the fp16 autocast / GradScaler of accelerate is NOT modelled: the oracle is the exact-arithmetic
+(fp32, or fp64 when the caller casts the modules) statement of the same function.  With
+``mixed_precision="fp16"`` (GPU only) the same statements run under the reference's precision policy
+(:928-939, :1063-1066): trainable text encoder fp32 under autocast(fp16) with fp32
+outputs, UNet and frozen text encoder cast to fp16 by the caller and run without autocast, fp32 loss, scaled
+backward + unscale -- i.e. what torch's own fp16 kernels make of the reference path.  Tests use it to report the
+north star's rtol 1e-3 / atol 1e-4 criterion against "the reference fp16 path" as well as against fp32.
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Dict, Optional
 
 import torch
@@ -31,12 +37,20 @@ def lora_named_parameters(te):
 
 
 def forward_loss(unet, te, te0, latents, noise, timesteps, input_ids, prior_ids=None, kpl_weight=0.1,
-                 kpl_type="cos", prediction_type="epsilon", image_ppl_weight=None):
+                 kpl_type="cos", prediction_type="epsilon", image_ppl_weight=None, mixed_precision=None):
     """Returns (loss, model_pred, encoder_hidden_states).  image_ppl_weight (not None = --with_image_prior,
     :1077-1094): the batch is [instance | class] halves, loss = mse(instance) + image_ppl_weight * mse(class)."""
+    assert mixed_precision in (None, "fp16")
+    amp = (lambda: torch.autocast(latents.device.type, dtype=torch.float16)) if mixed_precision else \
+        contextlib.nullcontext
     noisy = ddpm_ref.add_noise(latents, noise, timesteps)
-    ehs = te(input_ids)
-    pred = unet(noisy, timesteps, ehs)
+    with amp():
+        ehs = te(input_ids)
+    ehs = ehs.float()  # accelerate's convert_outputs_to_fp32
+    if mixed_precision:
+        pred = unet(noisy.half(), timesteps, ehs.half())  # :1063-1066 (weight_dtype casts)
+    else:
+        pred = unet(noisy, timesteps, ehs)
     if prediction_type == "epsilon":
         target = noise
     elif prediction_type == "v_prediction":
@@ -51,7 +65,9 @@ def forward_loss(unet, te, te0, latents, noise, timesteps, input_ids, prior_ids=
     else:
         loss = F.mse_loss(pred.float(), target.float(), reduction="none").mean()
     if kpl_weight > 0.0 and prior_ids is not None:
-        h = te(prior_ids).float()
+        with amp():
+            h = te(prior_ids)
+        h = h.float()
         with torch.no_grad():
             h0 = te0(prior_ids).float()
         if kpl_type == "cos":
@@ -65,7 +81,8 @@ def forward_loss(unet, te, te0, latents, noise, timesteps, input_ids, prior_ids=
 def reference_step(unet, te, te0, latents, noise, timesteps, input_ids, prior_ids=None, *,
                    n_base: int, kpl_weight=0.1, kpl_type="cos", prediction_type="epsilon",
                    optimizer: Optional[torch.optim.Optimizer] = None, max_grad_norm=1.0, mixing=None,
-                   mean_norm: Optional[float] = None, image_ppl_weight=None) -> Dict[str, torch.Tensor]:
+                   mean_norm: Optional[float] = None, image_ppl_weight=None, mixed_precision=None,
+                   loss_scale: float = 1.0) -> Dict[str, torch.Tensor]:
     """Runs forward + backward (+ the optimiser tail when `optimizer` is given).
 
     n_base = min(added_token_ids): rows below it never train.  Returns loss, pred, d(ehs) and the
@@ -76,9 +93,17 @@ def reference_step(unet, te, te0, latents, noise, timesteps, input_ids, prior_id
         p.grad = None
     emb.grad = None
     loss, pred, ehs = forward_loss(unet, te, te0, latents, noise, timesteps, input_ids, prior_ids,
-                                   kpl_weight, kpl_type, prediction_type, image_ppl_weight)
+                                   kpl_weight, kpl_type, prediction_type, image_ppl_weight, mixed_precision)
     ehs.retain_grad()
-    loss.backward()
+    (loss * loss_scale).backward()  # GradScaler.scale(loss).backward(); unscale_ precedes clipping (:1128-1133)
+    if loss_scale != 1.0:
+        inv = 1.0 / loss_scale
+        ehs.grad.mul_(inv)
+        if emb.grad is not None:
+            emb.grad.mul_(inv)
+        for _, p in lora_named_parameters(te):
+            if p.grad is not None:
+                p.grad.mul_(inv)
     if emb.grad is not None:
         emb.grad[:n_base] = 0  # :1109-1117
     if mixing is not None:  # :1119-1126

@@ -50,6 +50,47 @@ def make_weights(hidden, heads, layers, inter, n_added, seed=1234):
     return sd
 
 
+# LoRA goldens: the reference class has no peft here, but peft's LoRA Linear is linear algebra on the weight:
+# y = x (W + s B A)^T + b, so the REFERENCE class run on merged weights W' gives the LoRA forward, and
+#   dL/dA = s B^T (dL/dW'),   dL/dB = s (dL/dW') A^T
+# gives the LoRA gradients from the reference's own autograd (train_textboost.py:702-709 configures r, alpha,
+# targets; peft tuners/lora/layer.py Linear.forward is the arithmetic).
+QKV = ("q_proj", "k_proj", "v_proj")
+LORA_CASES = {
+    # name: (weights case, targets, r, lora_alpha, batch rows of make_inputs used, layers whose LoRA gradients
+    #        are stored -- None = all; the rank-16 full-size case keeps three layers so the file stays ~1.6 MB)
+    "small_quickgelu_qkv_r4": ("small_quickgelu", QKV, 4, 4, 4, None),
+    "small_gelu_qkvo_r8": ("small_gelu", QKV + ("out_proj",), 8, 16, 4, None),
+    "clip_l_qkv_r4": ("clip_l", QKV, 4, 4, 2, None),    # BASELINE.json configs[0]: CLIP-L, rank 4, bs 2, 77 tokens
+    "clip_l_qkvo_r16": ("clip_l", QKV + ("out_proj",), 16, 16, 2, (0, 6, 11)),
+}
+FULL_CASES = {"clip_l": (768, 12, 12, 3072, "quick_gelu", 2)}
+
+
+def case_cfg(case):
+    return CASES[case] if case in CASES else FULL_CASES[case]
+
+
+def make_lora(hidden, layers, targets, r, seed=77):
+    """{(layer, target): (A [r, hidden], B [hidden, r])}: A ~ N(0, 1/r) as peft's gaussian init, B ~ N(0, 0.02)
+    (non-zero so that dL/dA is not identically zero)."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for l in range(layers):
+        for t in targets:
+            out[(l, t)] = (torch.randn(r, hidden, generator=g) / r, 0.02 * torch.randn(hidden, r, generator=g))
+    return out
+
+
+def lora_sd(lora):
+    """the same factors under peft's state-dict names (what ClipEngine / the oracle load)."""
+    sd = {}
+    for (l, t), (A, B) in lora.items():
+        p = f"text_model.encoder.layers.{l}.self_attn.{t}."
+        sd[p + "lora_A.default.weight"], sd[p + "lora_B.default.weight"] = A, B
+    return sd
+
+
 def make_inputs(hidden, n_added, seed=99):
     g = torch.Generator().manual_seed(seed)
     ids = torch.full((4, L), 49407, dtype=torch.int64)
@@ -101,6 +142,51 @@ def main():
                        "transformers": __import__("transformers").__version__,
                        "torch": str(torch.__version__), "reference": "textboost/text_encoder.py:17-87"}
         path = os.path.join(HERE, f"clip_textboost_{name}.pt")
+        torch.save(out, path)
+        print("wrote", path, os.path.getsize(path), "bytes")
+
+    for name, (case, targets, r, alpha, rows, glayers) in LORA_CASES.items():
+        hidden, heads, layers, inter, act, n_added = case_cfg(case)
+        cfg = CLIPTextConfig(vocab_size=VOCAB + n_added, hidden_size=hidden, intermediate_size=inter,
+                             num_hidden_layers=layers, num_attention_heads=heads,
+                             max_position_embeddings=L, hidden_act=act, projection_dim=hidden,
+                             bos_token_id=49406, eos_token_id=49407, pad_token_id=1)
+        cfg._attn_implementation = "eager"
+        sd = make_weights(hidden, heads, layers, inter, n_added)
+        lora = make_lora(hidden, layers, targets, r)
+        s = alpha / r
+        merged = dict(sd)
+        for (l, t), (A, B) in lora.items():
+            k = f"text_model.encoder.layers.{l}.self_attn.{t}.weight"
+            merged[k] = sd[k] + s * (B @ A)
+        m = TextBoostModel(cfg).eval()
+        m.load_state_dict(merged, strict=False)
+        ids, null, dout = make_inputs(hidden, n_added)
+        ids, dout = ids[:rows], dout[:rows]
+        m.set_null_embedding(null.clone())
+        m.requires_grad_(False)
+        emb = m.get_input_embeddings().weight
+        emb.requires_grad_(True)
+        ws = {}
+        for (l, t) in lora:
+            w = getattr(m.text_model.encoder.layers[l].self_attn, t).weight
+            w.requires_grad_(True)
+            ws[(l, t)] = w
+        y = m(ids, return_dict=False)[0]
+        (y * dout).sum().backward()
+        flat = []
+        for (l, t), (A, B) in lora.items():      # (layer, target) order, A then B
+            if glayers is not None and l not in glayers:
+                continue
+            dW = ws[(l, t)].grad
+            flat += [(s * B.t() @ dW).flatten(), (s * dW @ A.t()).flatten()]
+        out = {"out_fixed": y.detach().clone(), "grad_added_rows_fixed": emb.grad[VOCAB:].detach().clone(),
+               "lora_grads_flat": torch.cat(flat),
+               "meta": {"case": case, "targets": targets, "r": r, "lora_alpha": alpha, "rows": rows, "grad_layers": glayers,
+                        "transformers": __import__("transformers").__version__, "torch": str(torch.__version__),
+                        "reference": "textboost/text_encoder.py:17-87 on merged weights W + (alpha/r) B A",
+                        "order": "for layer: for target: dA [r, D] then dB [D, r]"}}
+        path = os.path.join(HERE, f"clip_textboost_lora_{name}.pt")
         torch.save(out, path)
         print("wrote", path, os.path.getsize(path), "bytes")
 

@@ -229,16 +229,17 @@ def lib_optim():
 # null-embedding override and its gradient mask).  Drivers walk blockIdx.x over the rows.
 DRIVERS_CLIP = r"""
 extern "C" void emu_clip_embed(const long long* ids, const float* base, const float* added, const float* decay,
-                               const float* pos, float* x, int M, int L, int D, int n_base) {
-  for (int m = 0; m < M; ++m) { blockIdx.x = m; tb::clip_embed_kernel(ids, base, added, decay, pos, x, M, L, D, n_base); }
+                               const float* pos, float* x, int M, int L, int D, int n_base, int n_rows) {
+  for (int m = 0; m < M; ++m) { blockIdx.x = m; tb::clip_embed_kernel(ids, base, added, decay, pos, x, M, L, D, n_base, n_rows); }
   blockIdx.x = 0;
 }
 extern "C" void emu_clip_embed_grad(const long long* ids, const float* g, float* rows, int M, int D, int n_base) {
   for (int m = 0; m < M; ++m) { blockIdx.x = m; tb::clip_embed_grad_kernel(ids, g, rows, M, D, n_base); }
   blockIdx.x = 0;
 }
-extern "C" void emu_lora_pack(const float* B, void* wext, void* wext_t, int T, int D, int r, int rpad, float scaling) {
-  tb::lora_pack_kernel(B, (__half*)wext, (__half*)wext_t, T, D, r, rpad, scaling);
+extern "C" void emu_lora_pack(const float* B, void* wext, void* wext_t, int nblk, int tmask, int D, int r, int rpad,
+                              float scaling) {
+  tb::lora_pack_kernel(B, (__half*)wext, (__half*)wext_t, nblk, tmask, D, r, rpad, scaling);
 }
 extern "C" void emu_act(const void* u, const void* g, void* out, long long n, int kind, int bwd) {
   if (bwd) tb::act_kernel<true>((const __half*)u, (const __half*)g, (__half*)out, n, kind);

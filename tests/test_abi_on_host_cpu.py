@@ -297,34 +297,41 @@ def test_vae_sampler_and_image_wrappers(abi, monkeypatch):
         assert np.array_equal(run_plan(plan, "cpu").numpy(), np.asarray(im)), plan
 
 
-def test_lora_entry_points(abi):
+@pytest.mark.parametrize("nblk,tmask,r", [(3, 0b111, 4), (3, 0b101, 16), (1, 0b1, 8)])
+def test_lora_entry_points(abi, nblk, tmask, r):
     """a4: tb_lora_down (xa = LN(x) A^T into the K-extension columns), tb_lora_grad (dB, dA accumulated in fp32 from
-    the fused-QKV gradient) and tb_lora_dx (the A^T path of the input gradient), T = 3 targets of rank 4."""
+    the fused projection gradient) and tb_lora_dx (the A^T path of the input gradient): the reference's three targets
+    at rank 4, a subset of the fused q|k|v blocks at rank 16, and the single out_proj block at rank 8."""
     from textboost_b200 import _cabi as C
     g = torch.Generator().manual_seed(0)
-    M, D, T, r, RPAD = 70, 64, 3, 4, 16
-    R, ld = T * r, D + RPAD
+    blocks = [b for b in range(nblk) if (tmask >> b) & 1]
+    T = len(blocks)
+    M, D = 70, 64
+    R = T * r
+    RPAD = (R + 15) // 16 * 16
+    ld = D + RPAD
     A = torch.randn(R, D, generator=g) * 0.3
     y_ext = torch.full((M, ld), 9.0, dtype=torch.float16)
     y_ext[:, :D] = _h(M, D, seed=1)
     C.call("tb_lora_down", C.ptr(y_ext), ld, C.ptr(A), M, D, R, RPAD, C.stream_ptr())
     y = y_ext[:, :D].float()
     _close(y_ext[:, D:D + R], y @ A.t(), 2e-3)
-    assert y_ext[:, D + R:].abs().max() == 0
-    dY = _h(M, T * D, seed=2)
+    assert RPAD == R or y_ext[:, D + R:].abs().max() == 0
+    dY = _h(M, nblk * D, seed=2)
     dA_ext = torch.zeros(M, ld, dtype=torch.float16)
     dA_ext[:, :D] = _h(M, D, seed=3)
     dA_ext[:, D:D + R] = _h(M, R, seed=4)
     dB, dA = torch.ones(T * D, r), torch.ones(R, D)  # accumulate on top of what is there
-    C.call("tb_lora_grad", C.ptr(dY), C.ptr(y_ext), C.ptr(dA_ext), ld, C.ptr(dB), C.ptr(dA), M, T, D, r, 0.5,
+    C.call("tb_lora_grad", C.ptr(dY), C.ptr(y_ext), C.ptr(dA_ext), ld, C.ptr(dB), C.ptr(dA), M, nblk, tmask, D, r, 0.5,
            C.stream_ptr())
     xa, dxa = y_ext[:, D:D + R].float(), dA_ext[:, D:D + R].float()
-    want_b = torch.cat([0.5 * dY[:, t * D:(t + 1) * D].float().t() @ xa[:, t * r:(t + 1) * r] for t in range(T)]) + 1
+    want_b = torch.cat([0.5 * dY[:, b * D:(b + 1) * D].float().t() @ xa[:, t * r:(t + 1) * r]
+                        for t, b in enumerate(blocks)]) + 1
     torch.testing.assert_close(dB, want_b, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(dA, dxa.t() @ y + 1, rtol=1e-4, atol=1e-4)
     before = dA_ext[:, :D].float().clone()
     C.call("tb_lora_dx", C.ptr(dA_ext), ld, C.ptr(A), M, D, R, C.stream_ptr())
     _close(dA_ext[:, :D], before + dxa @ A, 2e-3)
     with pytest.raises(RuntimeError, match="tb_lora_grad"):
-        C.call("tb_lora_grad", C.ptr(dY), C.ptr(y_ext), C.ptr(dA_ext), ld, C.ptr(dB), C.ptr(dA), M, T, D, 9, 0.5,
-               C.stream_ptr())
+        C.call("tb_lora_grad", C.ptr(dY), C.ptr(y_ext), C.ptr(dA_ext), ld, C.ptr(dB), C.ptr(dA), M, nblk, tmask, D, 17,
+               0.5, C.stream_ptr())

@@ -62,6 +62,54 @@ def test_clip_engine_matches_reference_golden(case, fixed):
     assert relerr(g, gold[f"grad_added_rows_{key}"]) < 3e-3
 
 
+def _lora_engine_vs_golden(name, dev):
+    """ClipEngine with the golden's LoRA factors on the golden's inputs -> (errors dict)."""
+    import make_golden
+    from textboost_b200.clip import ClipConfig, ClipEngine
+    case, targets, r, alpha, rows, glayers = make_golden.LORA_CASES[name]
+    hidden, heads, layers, inter, act, n_added = make_golden.case_cfg(case)
+    gold = torch.load(os.path.join(GOLDEN, f"clip_textboost_lora_{name}.pt"))
+    sd = make_golden.make_weights(hidden, heads, layers, inter, n_added)
+    lora = make_golden.make_lora(hidden, layers, targets, r)
+    sd.update(make_golden.lora_sd(lora))
+    cfg = ClipConfig(hidden_size=hidden, intermediate_size=inter, num_hidden_layers=layers,
+                     num_attention_heads=heads, hidden_act=act)
+    eng = ClipEngine(cfg, sd, dev, lora_r=r, lora_alpha=alpha, n_base=make_golden.VOCAB, lora_targets=targets)
+    ids, null, dout = make_golden.make_inputs(hidden, n_added)
+    ids, dout = ids[:rows], dout[:rows]
+    eng.set_null_embedding(null)
+    eng.pack_lora()
+    y = eng.forward(ids.to(dev), save_for_backward=True)
+    eng.state.grads.zero_()
+    eng.backward(dout.to(dev).clone())
+    st = eng.state
+    flat = []
+    for l in range(layers):
+        if glayers is not None and l not in glayers:
+            continue
+        for ti in range(len(targets)):
+            flat += [st.A(l, st.grads)[ti * r:(ti + 1) * r].flatten(), st.B(l, st.grads)[ti].flatten()]
+    flat = torch.cat(flat).cpu()
+    ref = gold["lora_grads_flat"]
+    return {"out": relerr(y, gold["out_fixed"]), "rows": relerr(st.rows(st.grads), gold["grad_added_rows_fixed"]),
+            "lora_rel_l2": ((flat - ref).norm() / ref.norm()).item(),
+            "lora_cos": torch.nn.functional.cosine_similarity(flat, ref, dim=0).item(),
+            "y": y, "gold": gold}
+
+
+@pytest.mark.parametrize("name", ["small_quickgelu_qkv_r4", "small_gelu_qkvo_r8", "clip_l_qkv_r4", "clip_l_qkvo_r16"])
+def test_clip_engine_lora_matches_reference_golden(name):
+    """ClipEngine (CUDA, LoRA fused into the projection GEMMs) == the REFERENCE class run on merged weights
+    (tests/golden/make_golden.py): last hidden state, LoRA dA / dB and added-row gradients.  clip_l_qkv_r4 is
+    BASELINE.json configs[0] (CLIP-L, rank 4 on q/k/v, bs 2, 77 tokens); the qkvo cases cover the north star's
+    "QKV/out projections" wording and ranks up to 16.  fp16 GEMM operands vs the fp32 reference: 3e-3."""
+    e = _lora_engine_vs_golden(name, dev)
+    print({k: v for k, v in e.items() if isinstance(v, float)})
+    assert e["out"] < 2e-3
+    assert e["rows"] < 3e-3
+    assert e["lora_rel_l2"] < 3e-3 and e["lora_cos"] > 0.99999
+
+
 @pytest.mark.parametrize("name", ["clip_l", "openclip_h"])
 def test_clip_engine_lora_grads_vs_oracle(name):
     """Full-size CLIP-L / OpenCLIP-H with rank-4 LoRA: outputs, dA, dB and added-row gradients vs the oracle."""
@@ -250,6 +298,36 @@ def test_step_sd15_vs_oracle():
     assert r["lora_grad_rel_l2"] < 3e-3 and r["lora_grad_cos"] > 0.99999
     assert r["row_grad_rel"] < 3e-3
     assert abs(r["grad_norm"] - r["grad_norm_ref"]) < 2e-3 * r["grad_norm_ref"]
+
+
+def test_step_sd15_b8_vs_oracle_with_stated_tolerance_report():
+    """BASELINE.json configs[1]+[2] at its REAL size: SD-1.5 widths, 64x64 latents, CLIP-L rank-4 LoRA, KPL on,
+    batch 8, against the fp32 oracle on the same GPU (it fits in 180 GB).  Also runs the oracle under the
+    reference's fp16 policy (torch's own fp16 kernels: UNet / frozen encoder in fp16, trainable encoder under
+    autocast, GradScaler-style scaled backward) and REPORTS the north star's elementwise criterion rtol 1e-3 /
+    atol 1e-4 three ways.  An fp16 pipeline through ~60 layers cannot meet that criterion elementwise against
+    exact arithmetic -- torch's own fp16 path does not -- so the assertion is that our path passes it at least as
+    often as torch-fp16 does (minus 2 points), on top of the max / L2 error bounds."""
+    import json
+    from oracle import harness
+    from textboost_b200 import synthetic
+    tr = synthetic.build_trainer("sd15", dev, seed=42, n_added=2, lora_b_std=0.02, keep_sd=True, learning_rate=1e-4)
+    bt = synthetic.batch(8, 64, 7, 49408, dev)
+    bt["input_ids"][1, 4] = 49409
+    bt["prior_ids"][5, 1:] = synthetic.EOS
+    r = harness.compare_step(tr, bt, device=dev, fp16_reference=True)
+    rep = {k: v for k, v in r.items() if isinstance(v, float)}
+    print(json.dumps(rep, indent=1))
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/parity_b8.json", "w") as f:
+        json.dump(rep, f, indent=1)
+    assert abs(r["loss"] - r["loss_ref"]) < 1e-3 * abs(r["loss_ref"])
+    assert r["pred_rel"] < 3e-3
+    assert r["lora_grad_rel_l2"] < 3e-3 and r["lora_grad_cos"] > 0.99999
+    assert r["row_grad_rel"] < 3e-3
+    assert abs(r["grad_norm"] - r["grad_norm_ref"]) < 2e-3 * r["grad_norm_ref"]
+    for q in ("pred", "lora_grad", "row_grad"):
+        assert r[f"tol_{q}_ours_vs_fp32"] >= r[f"tol_{q}_torch16_vs_fp32"] - 0.02, (q, rep)
 
 
 def test_step_sd21_openclip_h_vs_oracle():

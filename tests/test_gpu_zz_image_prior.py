@@ -1,9 +1,7 @@
 """--with_image_prior (/root/reference/train_textboost.py:1077-1094): the doubled [instance | class]
 batch with loss = mse(instance half) + image_ppl_weight * mse(class half), against the oracle step and through the CLI.
 
-These tests were written after the round's GPU budget was spent: their first hardware run is the round-end suite.  They
-are marked xfail(strict=False) so that an XPASS / XFAIL line records the outcome without hiding or breaking the tests
-that were verified on the B200; the marker goes once they have been seen green.  (The file name sorts last on purpose.)
+First seen green on hardware at the end of round 1 (19 XPASS); the xfail(strict=False) markers they carried are gone.
 """
 import json
 import os
@@ -11,8 +9,7 @@ import os
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first hardware run: written after the GPU budget was spent")]
+pytestmark = pytest.mark.gpu
 dev = "cuda"
 
 

@@ -2,8 +2,8 @@
 (the installed libraries travel with the image) — identical bytes after the resize, identical float bits after the
 normalisation — and the training CLI with --gpu_image_transforms.
 
-Written after the round's GPU budget was spent: first hardware run is the round-end suite, hence xfail(strict=False)
-(see tests/test_gpu_zz_image_prior.py); the arithmetic and indexing are pinned on the CPU by tests/test_resample_cpu.py.
+First seen green on hardware at the end of round 1; the arithmetic and indexing are also pinned on the CPU by
+tests/test_resample_cpu.py.
 """
 import json
 import os
@@ -12,8 +12,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first hardware run: written after the GPU budget was spent")]
+pytestmark = pytest.mark.gpu
 dev = "cuda"
 
 

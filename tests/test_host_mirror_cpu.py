@@ -234,3 +234,21 @@ def test_scalar_tracker_writes_tensorboard_events(tmp_path):
     assert acc.Scalars("loss")[0].step == 1 and abs(acc.Scalars("loss")[0].value - 1.5) < 1e-6
     assert T.ScalarTracker(T.parse_args(base), False).writer is None
     assert T.ScalarTracker(T.parse_args(base + ["--report_to", "wandb"]), True).writer is None
+
+
+def test_tokenizer_is_never_a_silent_fallback(tmp_path):
+    """a checkpoint without vocab.json / merges.txt must raise, not train on hashed ids; the literal
+    stand-in needs the marker a synthetic checkpoint carries, or the explicit --synthetic_data opt-in."""
+    from textboost_b200 import synthetic
+    real = tmp_path / "real_ckpt" / "tokenizer"
+    real.mkdir(parents=True)
+    with pytest.raises(OSError):
+        synthetic.load_tokenizer(str(real))
+    with pytest.raises(OSError):
+        synthetic.load_tokenizer(str(tmp_path / "real_ckpt" / "renamed_tokenizer"))
+    assert isinstance(synthetic.load_tokenizer(str(real), allow_literal=True), synthetic.LiteralTokenizer)
+    synthetic.write_literal_tokenizer_marker(str(tmp_path / "syn_ckpt"))
+    assert isinstance(synthetic.load_tokenizer(str(tmp_path / "syn_ckpt" / "tokenizer")), synthetic.LiteralTokenizer)
+    (real / "vocab.json").write_text("{}")
+    with pytest.raises(OSError):
+        synthetic.load_tokenizer(str(real))  # vocab.json without merges.txt

@@ -254,9 +254,17 @@ def test_clip_embedding_and_override_kernel_sources():
     ids = torch.randint(0, V + n_added, (B, Lq), generator=g)
     ids[1, 2], ids[2, 5] = V + 1, V
     x = torch.empty(B * Lq, D)
-    L.emu_clip_embed(_p(ids), _p(base), _p(added), _p(decay), _p(pos), _p(x), B * Lq, Lq, D, V)
+    L.emu_clip_embed(_p(ids), _p(base), _p(added), _p(decay), _p(pos), _p(x), B * Lq, Lq, D, V, n_added)
     table = torch.cat([base * 0.97, added])
     torch.testing.assert_close(x.view(B, Lq, D), table[ids] + pos, rtol=1e-6, atol=1e-6)
+    # ids outside [0, V + n_added) -- and added ids on an engine without added rows -- never dereference: NaN rows
+    bad = ids.clone()
+    bad[0, 1], bad[3, 3] = V + n_added, -1
+    L.emu_clip_embed(_p(bad), _p(base), _p(added), _p(decay), _p(pos), _p(x), B * Lq, Lq, D, V, n_added)
+    xb = x.view(B, Lq, D)
+    assert torch.isnan(xb[0, 1]).all() and torch.isnan(xb[3, 3]).all() and torch.isfinite(xb[1]).all()
+    L.emu_clip_embed(_p(ids), _p(base), None, _p(decay), _p(pos), _p(x), B * Lq, Lq, D, V, 0)
+    assert torch.isnan(x.view(B, Lq, D)[1, 2]).all() and torch.isfinite(x.view(B, Lq, D)[0]).all() == bool((ids[0] < V).all())
     gout = torch.randn(B * Lq, D, generator=g)
     rows = torch.zeros(n_added, D)
     L.emu_clip_embed_grad(_p(ids), _p(gout), _p(rows), B * Lq, D, V)
@@ -294,12 +302,19 @@ def test_lora_pack_and_activation_kernel_sources():
     Kd = D + RPAD
     wext = torch.full((T * D, Kd), 7.0, dtype=torch.float16)
     wext_t = torch.full((Kd, T * D), 7.0, dtype=torch.float16)
-    L.emu_lora_pack(_p(Bm), _p(wext), _p(wext_t), T, D, r, RPAD, ctypes.c_float(0.5))
+    L.emu_lora_pack(_p(Bm), _p(wext), _p(wext_t), T, 7, D, r, RPAD, ctypes.c_float(0.5))
     want = torch.zeros(T * D, RPAD)
     for t in range(T):
         want[t * D:(t + 1) * D, t * r:(t + 1) * r] = 0.5 * Bm[t]
     assert torch.equal(wext[:, D:], want.half()) and torch.equal(wext_t[D:], want.half().t())
     assert (wext[:, :D] == 7).all() and (wext_t[:D] == 7).all()  # the frozen weight block is not touched
+    # a subset of the fused blocks (q and v of q|k|v carry LoRA): the i-th set bit of the mask owns B_i and the
+    # extension columns [i*r, (i+1)*r); the k block's extension stays zero
+    L.emu_lora_pack(_p(Bm), _p(wext), _p(wext_t), 3, 0b101, D, r, RPAD, ctypes.c_float(2.0))
+    want = torch.zeros(3 * D, RPAD)
+    want[0:D, 0:r] = 2.0 * Bm[0]
+    want[2 * D:3 * D, r:2 * r] = 2.0 * Bm[1]
+    assert torch.equal(wext[:, D:], want.half()) and torch.equal(wext_t[D:], want.half().t())
     u = _h(200, seed=2, scale=2.0)
     gy = _h(200, seed=3)
     for kind, fn in ((_cabi.TB_ACT_QUICK_GELU, lambda x: x * torch.sigmoid(1.702 * x)), (_cabi.TB_ACT_GELU, F.gelu)):

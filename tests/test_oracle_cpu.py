@@ -13,7 +13,7 @@ GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 
 def build_oracle_clip(case):
-    hidden, heads, layers, inter, act, n_added = make_golden.CASES[case]
+    hidden, heads, layers, inter, act, n_added = make_golden.case_cfg(case)
     cfg = clip_ref.ClipTextConfig(vocab_size=make_golden.VOCAB + n_added, hidden_size=hidden,
                                   intermediate_size=inter, num_hidden_layers=layers,
                                   num_attention_heads=heads, hidden_act=act)
@@ -48,6 +48,46 @@ def test_clip_oracle_matches_reference_golden(case, fixed):
     assert torch.equal(y[2], null)
     if fixed:
         assert torch.equal(y[:, 0], null[0].expand(4, -1))
+
+
+@pytest.mark.parametrize("name", list(make_golden.LORA_CASES))
+def test_clip_lora_oracle_matches_reference_golden(name):
+    """oracle/clip_ref.py's peft-LoRA restatement (LoraLinear) against the REFERENCE class run on merged weights
+    W + (alpha/r) B A (tests/golden/make_golden.py): output, dA / dB (derived from the reference's dL/dW'), and the
+    added-row embedding gradients.  Pins SURVEY.md §8 a4 to reference-run outputs, incl. full-size CLIP-L at
+    BASELINE.json configs[0] (rank 4, bs 2, 77 tokens) and the out_proj / rank-16 variants."""
+    case, targets, r, alpha, rows, glayers = make_golden.LORA_CASES[name]
+    gold = torch.load(os.path.join(GOLDEN, f"clip_textboost_lora_{name}.pt"))
+    m, sd, cfg = build_oracle_clip(case)
+    n_added = make_golden.case_cfg(case)[5]
+    lora = make_golden.make_lora(cfg.hidden_size, cfg.num_hidden_layers, targets, r)
+    m.requires_grad_(False)
+    m.add_adapter(r=r, lora_alpha=alpha, target_modules=targets)
+    missing, unexpected = m.load_state_dict(
+        make_golden.lora_sd(lora), strict=False)
+    assert not unexpected
+    ids, null, dout = make_golden.make_inputs(cfg.hidden_size, n_added)
+    ids, dout = ids[:rows], dout[:rows]
+    m.set_null_embedding(null.clone())
+    emb = m.get_input_embeddings().weight
+    emb.requires_grad_(True)
+    y = m(ids)
+    (y * dout).sum().backward()
+    # merged (W + sBA rounded to fp32) vs factored arithmetic: fp32 rounding through up to 12 layers
+    torch.testing.assert_close(y, gold["out_fixed"], rtol=1e-4, atol=1e-5 * gold["out_fixed"].abs().max().item())
+    gr = gold["grad_added_rows_fixed"]
+    torch.testing.assert_close(emb.grad[make_golden.VOCAB:], gr, rtol=1e-4, atol=5e-5 * gr.abs().max().item())
+    flat = []
+    for (l, t) in lora:
+        if glayers is not None and l not in glayers:
+            continue
+        mod = getattr(m.text_model.encoder.layers[l].self_attn, t)
+        flat += [mod.lora_A["default"].weight.grad.flatten(), mod.lora_B["default"].weight.grad.flatten()]
+    flat = torch.cat(flat)
+    ref = gold["lora_grads_flat"]
+    assert flat.shape == ref.shape
+    assert ((flat - ref).norm() / ref.norm()).item() < 5e-5  # fp32 rounding (merged vs factored weights)
+    torch.testing.assert_close(flat, ref, rtol=1e-3, atol=5e-5 * ref.abs().max().item())
 
 
 def test_lora_restatement_equals_merged_weights():

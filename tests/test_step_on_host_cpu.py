@@ -103,3 +103,41 @@ def test_three_steps_track_the_oracle(monkeypatch):
     assert worst <= 3 * 2.1 * tr.lr, worst
     emb = te.get_input_embeddings().weight.detach()
     assert harness.rel_max(st.rows(), emb[V:]) < 5e-2
+
+
+@pytest.mark.parametrize("name", ["small_quickgelu_qkv_r4", "small_gelu_qkvo_r8"])
+def test_clip_engine_lora_on_cpu_matches_reference_golden(monkeypatch, name):
+    """The product ClipEngine (LoRA fused into the QKV and out-projection GEMMs as K extensions; SIMT LoRA kernels
+    from the product source) against the REFERENCE class run on merged weights (tests/golden/make_golden.py): the
+    reference's q/k/v rank-4 configuration and the north star's "QKV/out projections" at rank 8, alpha 16."""
+    import os
+    import make_golden
+    from textboost_b200.clip import ClipConfig, ClipEngine
+    engine_standin.install(monkeypatch)
+    case, targets, r, alpha, rows, glayers = make_golden.LORA_CASES[name]
+    hidden, heads, layers, inter, act, n_added = make_golden.case_cfg(case)
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", f"clip_textboost_lora_{name}.pt"))
+    sd = make_golden.make_weights(hidden, heads, layers, inter, n_added)
+    sd.update(make_golden.lora_sd(make_golden.make_lora(hidden, layers, targets, r)))
+    cfg = ClipConfig(hidden_size=hidden, intermediate_size=inter, num_hidden_layers=layers,
+                     num_attention_heads=heads, hidden_act=act)
+    eng = ClipEngine(cfg, sd, "cpu", lora_r=r, lora_alpha=alpha, n_base=make_golden.VOCAB, lora_targets=targets)
+    assert eng.targets == tuple(targets) and eng.scaling == alpha / r
+    ids, null, dout = make_golden.make_inputs(hidden, n_added)
+    ids, dout = ids[:rows], dout[:rows]
+    eng.set_null_embedding(null)
+    eng.pack_lora()
+    y = eng.forward(ids, save_for_backward=True)
+    eng.state.grads.zero_()
+    eng.backward(dout.clone())
+    st = eng.state
+    flat = torch.cat([t for l in range(layers) for ti in range(len(targets))
+                      for t in (st.A(l, st.grads)[ti * r:(ti + 1) * r].flatten(), st.B(l, st.grads)[ti].flatten())])
+    ref = gold["lora_grads_flat"]
+
+    def rel(a, b):
+        return ((a - b).abs().max() / b.abs().max()).item()
+    assert rel(y, gold["out_fixed"]) < 2e-3
+    assert rel(st.rows(st.grads), gold["grad_added_rows_fixed"]) < 3e-3
+    assert ((flat - ref).norm() / ref.norm()).item() < 3e-3
+    assert torch.nn.functional.cosine_similarity(flat, ref, dim=0).item() > 0.99999

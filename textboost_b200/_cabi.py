@@ -87,11 +87,11 @@ _SIGNATURES = {
     "tb_conv_in_f16": [c_void_p] * 4 + [c_int] * 5 + [c_void_p],
     "tb_conv_out_f16": [c_void_p] * 4 + [c_int] * 5 + [c_void_p],
     "tb_conv_out_bwd_f16": [c_void_p] * 3 + [c_int] * 5 + [c_void_p],
-    "tb_clip_embed": [c_void_p] * 6 + [c_int] * 4 + [c_void_p],
+    "tb_clip_embed": [c_void_p] * 6 + [c_int] * 5 + [c_void_p],
     "tb_clip_embed_grad": [c_void_p] * 3 + [c_int] * 3 + [c_void_p],
     "tb_lora_down": [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
-    "tb_lora_pack": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p],
-    "tb_lora_grad": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+    "tb_lora_pack": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p],
+    "tb_lora_grad": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                      c_float, c_void_p],
     "tb_lora_dx": [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p],
     "tb_clip_attn_fwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],

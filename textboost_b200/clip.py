@@ -12,10 +12,14 @@ weights), fp32 accumulation.
 LoRA is not a separate pair of tiny GEMMs: with xa = LN(x) A^T (r columns per target) appended to the
 GEMM's K dimension and scaling*B appended to the weight, one tcgen05 GEMM computes
   [q|k|v] = [LN(x) | xa] [W | sB]^T + b
-and the same trick with the transposed operand gives dLN(x) and dxa in one dgrad GEMM.
+and the same trick with the transposed operand gives dLN(x) and dxa in one dgrad GEMM.  The reference's
+targets are q/k/v (train_textboost.py:705); out_proj (BASELINE.json's "QKV/out projections", the first entry
+of the reference's commented-out wider list, :702-708) extends the out-projection GEMM the same way:
+  x2 = [o | o A_o^T] [W_o | s B_o]^T + b_o + x.    Any subset of {q,k,v,out}_proj, rank 1..16.
 
-Trainable state lives in ONE flat fp32 buffer  [A (layers x 3r x D) | B (layers x 3 x D x r) | added rows]
-with a same-shaped gradient buffer: that buffer is what the single NCCL all-reduce and the fused AdamW see.
+Trainable state lives in ONE flat fp32 buffer  [A (layers x T r x D) | B (layers x T x D x r) | added rows]
+(T targets in the order q, k, v, out) with a same-shaped gradient buffer: that buffer is what the single NCCL
+all-reduce and the fused AdamW see.
 """
 from __future__ import annotations
 
@@ -30,7 +34,7 @@ from . import ops
 F16 = torch.float16
 F32 = torch.float32
 EOS_ID = 49407  # hard-coded in textboost/text_encoder.py:71
-RPAD = 16       # K-extension columns reserved for the LoRA down-projections (3 targets x r <= 16)
+RMAX = 16       # largest LoRA rank (K extension = targets x r columns, rounded up to 16, <= 64)
 
 
 @dataclasses.dataclass
@@ -54,15 +58,30 @@ class ClipConfig:
                           num_attention_heads=16, hidden_act="gelu")
 
 
-LORA_TARGETS = ("q_proj", "k_proj", "v_proj")
+LORA_TARGETS = ("q_proj", "k_proj", "v_proj")                  # the reference's configuration (:705)
+SUPPORTED_TARGETS = ("q_proj", "k_proj", "v_proj", "out_proj")  # canonical order of the trainable state
+
+
+def canonical_targets(targets) -> tuple:
+    targets = tuple(targets)
+    bad = [t for t in targets if t not in SUPPORTED_TARGETS]
+    if bad or not targets or len(set(targets)) != len(targets):
+        raise NotImplementedError(
+            f"LoRA target_modules={list(targets)}: the fused path covers any subset of {list(SUPPORTED_TARGETS)} "
+            "(fc1 / fc2 of the reference's commented-out list, train_textboost.py:702-708, are not built)")
+    return tuple(t for t in SUPPORTED_TARGETS if t in targets)
+
+
+def _pad16(n: int) -> int:
+    return (n + 15) // 16 * 16
 
 
 class TrainableState:
     """Flat fp32 parameter / gradient buffers shared by the encoder, the all-reduce and the optimiser."""
 
-    def __init__(self, n_layers: int, D: int, r: int, n_rows: int, device):
+    def __init__(self, n_layers: int, D: int, r: int, n_rows: int, device, n_targets: int = 3):
         self.n_layers, self.D, self.r, self.n_rows = n_layers, D, r, n_rows
-        self.T = len(LORA_TARGETS) if r > 0 else 0
+        self.T = n_targets if r > 0 else 0
         self.n_a = n_layers * self.T * r * D
         self.n_b = n_layers * self.T * D * r
         self.n_lora = self.n_a + self.n_b
@@ -93,7 +112,8 @@ class ClipEngine:
     """sd: HF ``text_model.*`` keys (fp32).  LoRA keys in peft naming are honoured if present."""
 
     def __init__(self, cfg: ClipConfig, sd: Dict[str, torch.Tensor], device, lora_r: int = 0,
-                 lora_alpha: Optional[int] = None, n_base: Optional[int] = None, seed: int = 0):
+                 lora_alpha: Optional[int] = None, n_base: Optional[int] = None, seed: int = 0,
+                 lora_targets=LORA_TARGETS):
         self.cfg = cfg
         self.device = torch.device(device)
         D, nl = cfg.hidden_size, cfg.num_hidden_layers
@@ -102,8 +122,16 @@ class ClipEngine:
         self.r = lora_r
         self.scaling = (lora_alpha if lora_alpha is not None else lora_r) / lora_r if lora_r else 0.0
         self.act = C.TB_ACT_QUICK_GELU if cfg.hidden_act == "quick_gelu" else C.TB_ACT_GELU
-        self.Kext = D + (RPAD if lora_r else 0)
-        assert 3 * lora_r <= RPAD
+        if not 0 <= lora_r <= RMAX:
+            raise NotImplementedError(f"LoRA rank {lora_r}: the K-extension path covers ranks 1..{RMAX}")
+        self.targets = canonical_targets(lora_targets) if lora_r else ()
+        qkv_t = [t for t in self.targets if t != "out_proj"]
+        self.Tq = len(qkv_t)                                  # LoRA targets inside the fused QKV GEMM
+        self.qkv_mask = sum(1 << LORA_TARGETS.index(t) for t in qkv_t)
+        self.has_o = "out_proj" in self.targets
+        self.Rq, self.Ro = _pad16(self.Tq * lora_r), (_pad16(lora_r) if self.has_o else 0)
+        self.Kext = D + self.Rq                               # K of the fused QKV GEMM
+        self.Ko = D + self.Ro                                 # K of the out-projection GEMM
 
         def g32(k):
             return sd[k].detach().to(device=self.device, dtype=F32).contiguous()
@@ -120,7 +148,7 @@ class ClipEngine:
         self.tok_base = emb[:self.n_base].contiguous()
         n_rows = emb.shape[0] - self.n_base
         self.pos = g32("text_model.embeddings.position_embedding.weight")
-        self.state = TrainableState(nl, D, lora_r, n_rows, self.device)
+        self.state = TrainableState(nl, D, lora_r, n_rows, self.device, len(self.targets))
         if n_rows:
             self.state.rows().copy_(emb[self.n_base:])
         self.layers = []
@@ -141,12 +169,18 @@ class ClipEngine:
             wext_t[:D] = wqkv.t()
             L["wqkv"], L["wqkv_t"], L["bqkv"] = wext, wext_t, torch.cat(bs, 0)
             for name, key in (("o", "self_attn.out_proj"), ("f1", "mlp.fc1"), ("f2", "mlp.fc2")):
-                w = g16(p + key + ".weight")
+                w = g16(base_key(p + key, "weight"))
                 L["w" + name], L["w" + name + "_t"] = w, w.t().contiguous()
-                L["b" + name] = g16(p + key + ".bias")
+                L["b" + name] = g16(base_key(p + key, "bias"))
+            if self.has_o:  # [W_o | s B_o] and its transpose, extension filled by pack_lora
+                wo = torch.zeros((D, self.Ko), device=self.device, dtype=F16)
+                wo[:, :D] = L["wo"]
+                wo_t = torch.zeros((self.Ko, D), device=self.device, dtype=F16)
+                wo_t[:D] = L["wo_t"]
+                L["wo"], L["wo_t"] = wo, wo_t
             self.layers.append(L)
             if lora_r:
-                for ti, t in enumerate(LORA_TARGETS):
+                for ti, t in enumerate(self.targets):
                     ka = f"{p}self_attn.{t}.lora_A.default.weight"
                     kb = f"{p}self_attn.{t}.lora_B.default.weight"
                     if ka in sd:
@@ -174,8 +208,12 @@ class ClipEngine:
             return
         st = self.state
         for l, L in enumerate(self.layers):
-            C.call("tb_lora_pack", C.ptr(st.B(l)), C.ptr(L["wqkv"]), C.ptr(L["wqkv_t"]), st.T, self.D,
-                   self.r, RPAD, self.scaling, C.stream_ptr())
+            if self.Tq:
+                C.call("tb_lora_pack", C.ptr(st.B(l)), C.ptr(L["wqkv"]), C.ptr(L["wqkv_t"]), 3, self.qkv_mask,
+                       self.D, self.r, self.Rq, self.scaling, C.stream_ptr())
+            if self.has_o:
+                C.call("tb_lora_pack", C.ptr(st.B(l)[self.Tq]), C.ptr(L["wo"]), C.ptr(L["wo_t"]), 1, 1, self.D,
+                       self.r, self.Ro, self.scaling, C.stream_ptr())
 
     # ------------------------------------------------------------------ forward
     def forward(self, input_ids: torch.Tensor, save_for_backward: bool = False) -> torch.Tensor:
@@ -188,19 +226,23 @@ class ClipEngine:
         s = C.stream_ptr()
         x = torch.empty((M, D), device=self.device, dtype=F32)
         C.call("tb_clip_embed", C.ptr(ids), C.ptr(self.tok_base), C.ptr(st.rows() if st.n_rows else None),
-               C.ptr(self.decay), C.ptr(self.pos), C.ptr(x), M, Lq, D, self.n_base, s)
+               C.ptr(self.decay), C.ptr(self.pos), C.ptr(x), M, Lq, D, self.n_base, st.n_rows, s)
         saved = []
         for l, L in enumerate(self.layers):
             y_ext = torch.empty((M, self.Kext), device=self.device, dtype=F16)
             _, st1 = ops.layernorm(x, *L["ln1"], eps=self.cfg.layer_norm_eps, out=y_ext[:, :D])
-            if self.r:
-                C.call("tb_lora_down", C.ptr(y_ext), self.Kext, C.ptr(st.A(l)), M, D, st.T * self.r, RPAD, s)
+            if self.Tq:
+                C.call("tb_lora_down", C.ptr(y_ext), self.Kext, C.ptr(st.A(l)), M, D, self.Tq * self.r, self.Rq, s)
             qkv = ops.gemm(y_ext, L["wqkv"], bias=L["bqkv"])
             # causal softmax(QK^T/sqrt(64))V on the tcgen05 flash kernels, reading q/k/v in place from the fused
             # projection output (transformers CLIPAttention under the causal mask, text_encoder.py:62-69)
             q3 = qkv.view(B, Lq, 3 * D)
-            o, lse = ops.attn_fwd(q3[..., :D], q3[..., D:2 * D], q3[..., 2 * D:], self.heads, causal=True)
-            o = o.view(M, D)
+            # the attention writes straight into the first D columns of the out-projection's (extended) A operand
+            o = torch.empty((M, self.Ko), device=self.device, dtype=F16)
+            _, lse = ops.attn_fwd(q3[..., :D], q3[..., D:2 * D], q3[..., 2 * D:], self.heads, causal=True,
+                                  out=o.view(B, Lq, self.Ko)[..., :D])
+            if self.has_o:
+                C.call("tb_lora_down", C.ptr(o), self.Ko, C.ptr(st.A(l)[self.Tq * self.r:]), M, D, self.r, self.Ro, s)
             x2 = ops.gemm(o, L["wo"], bias=L["bo"], residual=x, out_kind=C.TB_OUT_F32)
             y2, st2 = ops.layernorm(x2, *L["ln2"], eps=self.cfg.layer_norm_eps)
             u = ops.gemm(y2, L["wf1"], bias=L["bf1"])
@@ -250,19 +292,24 @@ class ClipEngine:
             dy2 = ops.gemm(du, L["wf1_t"])
             g = ops.layernorm_bwd(dy2, x2, L["ln2"][0], st2, add=g, out=g)
             g16 = ops.cast_f32_f16(g)
-            do = ops.gemm(g16, L["wo_t"])
+            do = ops.gemm(g16, L["wo_t"])  # [M, Ko]: d(o) and, in the extension columns, d(o A_o^T)
+            if self.has_o:
+                ro = self.Tq * self.r
+                C.call("tb_lora_grad", C.ptr(g16), C.ptr(o), C.ptr(do), self.Ko, C.ptr(st.B(l, st.grads)[self.Tq]),
+                       C.ptr(st.A(l, st.grads)[ro:]), M, 1, 1, D, self.r, self.scaling, s)
+                C.call("tb_lora_dx", C.ptr(do), self.Ko, C.ptr(st.A(l)[ro:]), M, D, self.r, s)
             dqkv = torch.empty_like(qkv)
             q3, d3 = qkv.view(B, Lq, 3 * D), dqkv.view(B, Lq, 3 * D)
-            dq, _, _ = ops.attn_bwd(q3[..., :D], q3[..., D:2 * D], q3[..., 2 * D:], o.view(B, Lq, D),
-                                    do.view(B, Lq, D), lse, self.heads, dk=d3[..., D:2 * D], dv=d3[..., 2 * D:],
-                                    causal=True)
+            dq, _, _ = ops.attn_bwd(q3[..., :D], q3[..., D:2 * D], q3[..., 2 * D:], o.view(B, Lq, self.Ko)[..., :D],
+                                    do.view(B, Lq, self.Ko)[..., :D], lse, self.heads, dk=d3[..., D:2 * D],
+                                    dv=d3[..., 2 * D:], causal=True)
             ops.cast_f32_f16(dq.view(M, D), out=dqkv[:, :D])
             dy_ext = ops.gemm(dqkv, L["wqkv_t"])
-            if self.r:
+            if self.Tq:
                 C.call("tb_lora_grad", C.ptr(dqkv), C.ptr(y_ext), C.ptr(dy_ext), self.Kext,
-                       C.ptr(st.B(l, st.grads)), C.ptr(st.A(l, st.grads)), M, st.T, D, self.r,
+                       C.ptr(st.B(l, st.grads)), C.ptr(st.A(l, st.grads)), M, 3, self.qkv_mask, D, self.r,
                        self.scaling, s)
-                C.call("tb_lora_dx", C.ptr(dy_ext), self.Kext, C.ptr(st.A(l)), M, D, st.T * self.r, s)
+                C.call("tb_lora_dx", C.ptr(dy_ext), self.Kext, C.ptr(st.A(l)), M, D, self.Tq * self.r, s)
             g = ops.layernorm_bwd(dy_ext[:, :D], x, L["ln1"][0], st1, add=g, out=g)
             saved[l] = None
         if st.n_rows:

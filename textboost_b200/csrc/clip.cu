@@ -16,12 +16,18 @@ __device__ __forceinline__ float warp_sum_c(float v) {
 }
 
 // x[m,:] = tok(ids[m]) + pos[m % L];  tok(id) = id < n_base ? base[id]*decay : added[id-n_base]
+// An id outside [0, n_base + n_rows) (torch's embedding lookup raises for it) never dereferences: its row is
+// filled with NaN, so the loss turns NaN and the GradScaler skips the step instead of reading foreign memory.
 __global__ void clip_embed_kernel(const long long* __restrict__ ids, const float* __restrict__ base,
                                   const float* __restrict__ added, const float* __restrict__ decay,
                                   const float* __restrict__ pos, float* __restrict__ x, int M, int L, int D,
-                                  int n_base) {
+                                  int n_base, int n_rows) {
   const int m = blockIdx.x;
   const long long id = ids[m];
+  if (id < 0 || id >= (long long)n_base + n_rows || (id >= n_base && !added)) {
+    for (int c = threadIdx.x; c < D; c += blockDim.x) x[(long long)m * D + c] = nanf("");
+    return;
+  }
   const float dc = decay ? *decay : 1.f;
   const float* src = id < n_base ? base + id * (long long)D : added + (id - n_base) * (long long)D;
   const float sc = id < n_base ? dc : 1.f;
@@ -40,103 +46,125 @@ __global__ void clip_embed_grad_kernel(const long long* __restrict__ ids, const 
 }
 
 // xa[m, j] = sum_c y[m,c] * A[j,c]  -> written as fp16 into the K-extension columns of the GEMM A operand
-// (columns D .. D+R-1 of a row of stride ld; columns D+R .. D+RPAD-1 are zeroed).
+// (columns D .. D+R-1 of a row of stride ld; columns D+R .. D+RPAD-1 are zeroed).  R <= LORA_RMAX, processed 16
+// down-projection rows at a time (the activation row is re-read from L1 per group).
+constexpr int LORA_RMAX = 64;  // widest K extension: four fused targets x rank 16
 __global__ void lora_down_kernel(__half* __restrict__ y_ext, long long ld, const float* __restrict__ A,
                                  int M, int D, int R, int RPAD) {
   const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (m >= M) return;
   const int lane = threadIdx.x & 31;
   __half* row = y_ext + (long long)m * ld;
-  float acc[16];
+  for (int j0 = 0; j0 < RPAD; j0 += 16) {
+    float acc[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-  // 8 consecutive columns per lane and trip: one 16-byte load of y, two float4 loads of each A row (L1-resident)
-  for (int c = lane * 8; c < D; c += 256) {
-    const uint4 q = *reinterpret_cast<const uint4*>(row + c);
-    const __half2* h = reinterpret_cast<const __half2*>(&q);
-    float v[8];
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    if (j0 < R) {
+      // 8 consecutive columns per lane and trip: one 16-byte load of y, two float4 loads of each A row (L1-resident)
+      for (int c = lane * 8; c < D; c += 256) {
+        const uint4 q = *reinterpret_cast<const uint4*>(row + c);
+        const __half2* h = reinterpret_cast<const __half2*>(&q);
+        float v[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = __half22float2(h[i]);
-      v[2 * i] = f.x;
-      v[2 * i + 1] = f.y;
-    }
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __half22float2(h[i]);
+          v[2 * i] = f.x;
+          v[2 * i + 1] = f.y;
+        }
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      if (j < R) {
-        const float4 a0 = *reinterpret_cast<const float4*>(A + (long long)j * D + c);
-        const float4 a1 = *reinterpret_cast<const float4*>(A + (long long)j * D + c + 4);
-        acc[j] += v[0] * a0.x + v[1] * a0.y + v[2] * a0.z + v[3] * a0.w + v[4] * a1.x + v[5] * a1.y +
-                  v[6] * a1.z + v[7] * a1.w;
+        for (int j = 0; j < 16; ++j) {
+          if (j0 + j < R) {
+            const float4 a0 = *reinterpret_cast<const float4*>(A + (long long)(j0 + j) * D + c);
+            const float4 a1 = *reinterpret_cast<const float4*>(A + (long long)(j0 + j) * D + c + 4);
+            acc[j] += v[0] * a0.x + v[1] * a0.y + v[2] * a0.z + v[3] * a0.w + v[4] * a1.x + v[5] * a1.y +
+                      v[6] * a1.z + v[7] * a1.w;
+          }
+        }
       }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = warp_sum_c(acc[j]);
     }
-  }
+    if (lane < 16 && j0 + lane < RPAD) {
+      float v = 0.f;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = warp_sum_c(acc[j]);
-  if (lane < RPAD) {
-    float v = 0.f;
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (j == lane && j < R) v = acc[j];
-    row[D + lane] = __float2half(v);
+      for (int j = 0; j < 16; ++j)
+        if (j == lane && j0 + j < R) v = acc[j];
+      row[D + j0 + lane] = __float2half(v);
+    }
   }
 }
 
-// Pack the LoRA up-projections into the extension columns of the fused QKV weight and its transpose:
-//   Wext[t*D + n, D + t*r + j]   = scaling * B_t[n, j]        (forward operand, [T*D, D+RPAD])
-//   WextT[D + t*r + j, t*D + n]  = scaling * B_t[n, j]        (dgrad operand,  [D+RPAD, T*D])
-// everything else inside the extension block is zero.  B is [T][D][r] fp32.
+// Pack the LoRA up-projections into the extension columns of a fused projection weight and its transpose.  The
+// weight stacks `nblk` row blocks of D output features (q | k | v, or the single out_proj block); bit b of `tmask`
+// says block b carries LoRA, and the i-th set bit owns B_i (Bm is [T][D][r] over the set bits, in order) and the
+// extension columns [i*r, (i+1)*r):
+//   Wext[b*D + n, D + i*r + j]   = scaling * B_i[n, j]        (forward operand, [nblk*D, D+RPAD])
+//   WextT[D + i*r + j, b*D + n]  = scaling * B_i[n, j]        (dgrad operand,  [D+RPAD, nblk*D])
+// everything else inside the extension block is zero.
+__device__ __forceinline__ int lora_bits(int m) {  // (<= 8 blocks; plain arithmetic so the source also builds for the host)
+  int c = 0;
+  for (int b = 0; b < 8; ++b) c += (m >> b) & 1;
+  return c;
+}
+__device__ __forceinline__ int lora_slot(int tmask, int b) {  // index among the set bits, or -1
+  return ((tmask >> b) & 1) ? lora_bits(tmask & ((1 << b) - 1)) : -1;
+}
 __global__ void lora_pack_kernel(const float* __restrict__ Bm, __half* __restrict__ Wext,
-                                 __half* __restrict__ WextT, int T, int D, int r, int RPAD, float scaling) {
+                                 __half* __restrict__ WextT, int nblk, int tmask, int D, int r, int RPAD,
+                                 float scaling) {
   const int K = D + RPAD;
-  const long long total = (long long)T * D * RPAD;
+  const long long total = (long long)nblk * D * RPAD;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int e = (int)(i % RPAD);
-    const long long row = i / RPAD;  // t*D + n
-    const int t = (int)(row / D), n = (int)(row % D);
+    const long long row = i / RPAD;  // b*D + n
+    const int b = (int)(row / D), n = (int)(row % D);
+    const int t = lora_slot(tmask, b);
     float v = 0.f;
-    if (e >= t * r && e < (t + 1) * r) v = scaling * Bm[((long long)t * D + n) * r + (e - t * r)];
+    if (t >= 0 && e >= t * r && e < (t + 1) * r) v = scaling * Bm[((long long)t * D + n) * r + (e - t * r)];
     const __half hv = __float2half(v);
     Wext[row * K + D + e] = hv;
-    WextT[(long long)(D + e) * (T * D) + row] = hv;
+    WextT[(long long)(D + e) * (nblk * D) + row] = hv;
   }
 }
 
-// LoRA gradients for one layer (accumulating, fp32):
-//   dB_t[n, j] += scaling * sum_m dY[m, t*D+n] * xa[m, t*r+j]
-//   dA[tj, c]  += sum_m dxa[m, tj] * y[m, c]
-// dY [M, T*D] fp16, xa = y_ext[:, D:D+R], y = y_ext[:, :D], dxa = dA_ext[:, D:D+R] (all fp16).
+// LoRA gradients for one fused projection of one layer (accumulating, fp32):
+//   dB_i[n, j] += scaling * sum_m dY[m, b_i*D+n] * xa[m, i*r+j]        (b_i = the i-th set bit of tmask)
+//   dA[ij, c]  += sum_m dxa[m, ij] * y[m, c]
+// dY [M, nblk*D] fp16, xa = y_ext[:, D:D+R], y = y_ext[:, :D], dxa = dA_ext[:, D:D+R] (all fp16), R = T*r <= 64.
 // A thread owns two adjacent columns (of dY for dB, of y for dA), so every warp reads 128 contiguous bytes per
-// row; the rows are split over grid.y and the partial sums meet in fp32 atomics; the r-wide xa / dxa rows of the
+// row; the rows are split over grid.y and the partial sums meet in fp32 atomics; the R-wide xa / dxa rows of the
 // CTA's row chunk are staged in shared memory (every thread reads the same entry: broadcast).
 constexpr int LG_ROWS = 48;  // rows per CTA
 __global__ void lora_grad_kernel(const __half* __restrict__ dY, const __half* __restrict__ y_ext,
                                  const __half* __restrict__ dA_ext, long long ld, float* __restrict__ dB,
-                                 float* __restrict__ dA, int M, int T, int D, int r, float scaling) {
-  __shared__ float sxa[LG_ROWS][16];
-  __shared__ float sdx[LG_ROWS][16];
+                                 float* __restrict__ dA, int M, int nblk, int tmask, int D, int r, float scaling) {
+  __shared__ float sxa[LG_ROWS][LORA_RMAX];
+  __shared__ float sdx[LG_ROWS][LORA_RMAX];
   const int m0 = blockIdx.y * LG_ROWS;
   const int rows = min(LG_ROWS, M - m0);
-  const int R = T * r;
-  for (int i = threadIdx.x; i < rows * 16; i += blockDim.x) {
-    const int mm = i >> 4, j = i & 15;
+  const int R = lora_bits(tmask) * r;
+  for (int i = threadIdx.x; i < rows * LORA_RMAX; i += blockDim.x) {
+    const int mm = i / LORA_RMAX, j = i % LORA_RMAX;
     sxa[mm][j] = j < R ? __half2float(y_ext[(long long)(m0 + mm) * ld + D + j]) : 0.f;
     sdx[mm][j] = j < R ? __half2float(dA_ext[(long long)(m0 + mm) * ld + D + j]) : 0.f;
   }
   __syncthreads();
   const int col = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
-  if (col < T * D) {
-    const int t = col / D;
-    float a0[8], a1[8];
+  const int NY = nblk * D;
+  if (col < NY) {
+    const int t = lora_slot(tmask, col / D);
+    if (t < 0) return;
+    const int n = col % D;
+    float a0[16], a1[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.f;
-    const __half* src = dY + (long long)m0 * (T * D) + col;
+    for (int j = 0; j < 16; ++j) a0[j] = a1[j] = 0.f;
+    const __half* src = dY + (long long)m0 * NY + col;
 #pragma unroll 4
     for (int mm = 0; mm < rows; ++mm) {
-      const float2 g = __half22float2(*reinterpret_cast<const __half2*>(src + (long long)mm * (T * D)));
+      const float2 g = __half22float2(*reinterpret_cast<const __half2*>(src + (long long)mm * NY));
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 16; ++j) {
         if (j < r) {
           const float xa = sxa[mm][t * r + j];
           a0[j] += g.x * xa;
@@ -144,36 +172,39 @@ __global__ void lora_grad_kernel(const __half* __restrict__ dY, const __half* __
         }
       }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (j < r) {
-        atomicAdd(&dB[(long long)col * r + j], scaling * a0[j]);
-        atomicAdd(&dB[(long long)(col + 1) * r + j], scaling * a1[j]);
-      }
-    }
-  } else if (col < T * D + D) {
-    const int c = col - T * D;
-    float a0[16], a1[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) a0[j] = a1[j] = 0.f;
-    const __half* src = y_ext + (long long)m0 * ld + c;
-#pragma unroll 4
-    for (int mm = 0; mm < rows; ++mm) {
-      const float2 yv = __half22float2(*reinterpret_cast<const __half2*>(src + (long long)mm * ld));
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (j < R) {
-          const float dx = sdx[mm][j];
-          a0[j] += yv.x * dx;
-          a1[j] += yv.y * dx;
-        }
-      }
-    }
+    float* dst = dB + ((long long)t * D + n) * r;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      if (j < R) {
-        atomicAdd(&dA[(long long)j * D + c], a0[j]);
-        atomicAdd(&dA[(long long)j * D + c + 1], a1[j]);
+      if (j < r) {
+        atomicAdd(&dst[j], scaling * a0[j]);
+        atomicAdd(&dst[r + j], scaling * a1[j]);
+      }
+    }
+  } else if (col < NY + D) {
+    const int c = col - NY;
+    const __half* src = y_ext + (long long)m0 * ld + c;
+    for (int j0 = 0; j0 < R; j0 += 16) {
+      float a0[16], a1[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) a0[j] = a1[j] = 0.f;
+#pragma unroll 4
+      for (int mm = 0; mm < rows; ++mm) {
+        const float2 yv = __half22float2(*reinterpret_cast<const __half2*>(src + (long long)mm * ld));
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (j0 + j < R) {
+            const float dx = sdx[mm][j0 + j];
+            a0[j] += yv.x * dx;
+            a1[j] += yv.y * dx;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (j0 + j < R) {
+          atomicAdd(&dA[(long long)(j0 + j) * D + c], a0[j]);
+          atomicAdd(&dA[(long long)(j0 + j) * D + c + 1], a1[j]);
+        }
       }
     }
   }
@@ -183,8 +214,8 @@ __global__ void lora_grad_kernel(const __half* __restrict__ dY, const __half* __
 __global__ void lora_dx_kernel(__half* __restrict__ dA_ext, long long ld, const float* __restrict__ A,
                                int M, int D, int R) {
   const int m = blockIdx.x;
-  __shared__ float sx[16];
-  if (threadIdx.x < 16) sx[threadIdx.x] = threadIdx.x < R ? __half2float(dA_ext[(long long)m * ld + D + threadIdx.x]) : 0.f;
+  __shared__ float sx[LORA_RMAX];
+  if (threadIdx.x < LORA_RMAX) sx[threadIdx.x] = threadIdx.x < R ? __half2float(dA_ext[(long long)m * ld + D + threadIdx.x]) : 0.f;
   __syncthreads();
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
     float v = __half2float(dA_ext[(long long)m * ld + c]);
@@ -400,10 +431,12 @@ using namespace tb;
   cudaStream_t st = (cudaStream_t)stream
 
 extern "C" int tb_clip_embed(const int64_t* ids, const float* base, const float* added, const float* decay,
-                             const float* pos, float* x, int M, int L, int D, int n_base, void* stream) {
+                             const float* pos, float* x, int M, int L, int D, int n_base, int n_rows,
+                             void* stream) {
   TB_ENTER();
   TB_REQUIRE(ids && base && pos && x, TB_E_ARG, "tb_clip_embed: null pointer");
-  clip_embed_kernel<<<M, 256, 0, st>>>((const long long*)ids, base, added, decay, pos, x, M, L, D, n_base);
+  TB_REQUIRE(n_rows >= 0 && (n_rows == 0 || added), TB_E_ARG, "tb_clip_embed: n_rows = %d without added rows", n_rows);
+  clip_embed_kernel<<<M, 256, 0, st>>>((const long long*)ids, base, added, decay, pos, x, M, L, D, n_base, n_rows);
   return check_launch("clip_embed_kernel");
 }
 extern "C" int tb_clip_embed_grad(const int64_t* ids, const float* g, float* grad_rows, int M, int D,
@@ -416,33 +449,43 @@ extern "C" int tb_clip_embed_grad(const int64_t* ids, const float* g, float* gra
 extern "C" int tb_lora_down(void* y_ext, int64_t ld, const float* A, int M, int D, int R, int RPAD,
                             void* stream) {
   TB_ENTER();
-  TB_REQUIRE(y_ext && A && R <= 16 && RPAD <= 16 && R <= RPAD, TB_E_ARG, "tb_lora_down: bad args (R=%d)", R);
+  TB_REQUIRE(y_ext && A && R >= 1 && R <= LORA_RMAX && RPAD <= LORA_RMAX && R <= RPAD && RPAD % 8 == 0, TB_E_ARG,
+             "tb_lora_down: bad args (R=%d RPAD=%d; R <= RPAD <= %d)", R, RPAD, LORA_RMAX);
+  TB_REQUIRE(D % 8 == 0 && ld % 8 == 0, TB_E_ALIGN, "tb_lora_down: D and ld must be multiples of 8");
   lora_down_kernel<<<(M + 7) / 8, 256, 0, st>>>((__half*)y_ext, ld, A, M, D, R, RPAD);
   return check_launch("lora_down_kernel");
 }
-extern "C" int tb_lora_pack(const float* Bm, void* Wext, void* WextT, int T, int D, int r, int RPAD,
+static int lora_mask_ok(int nblk, int tmask, int r, int RPAD) {
+  if (nblk < 1 || nblk > 8 || tmask <= 0 || tmask >= (1 << nblk) || r < 1 || r > 16) return 0;
+  int T = 0;
+  for (int b = 0; b < nblk; ++b) T += (tmask >> b) & 1;
+  return T * r <= RPAD && RPAD <= LORA_RMAX;
+}
+extern "C" int tb_lora_pack(const float* Bm, void* Wext, void* WextT, int nblk, int tmask, int D, int r, int RPAD,
                             float scaling, void* stream) {
   TB_ENTER();
-  TB_REQUIRE(Bm && Wext && WextT && T * r <= RPAD, TB_E_ARG, "tb_lora_pack: bad args");
-  const long long total = (long long)T * D * RPAD;
-  lora_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Bm, (__half*)Wext, (__half*)WextT, T, D,
-                                                                   r, RPAD, scaling);
+  TB_REQUIRE(Bm && Wext && WextT && lora_mask_ok(nblk, tmask, r, RPAD), TB_E_ARG,
+             "tb_lora_pack: bad args (nblk=%d tmask=%d r=%d RPAD=%d)", nblk, tmask, r, RPAD);
+  const long long total = (long long)nblk * D * RPAD;
+  lora_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Bm, (__half*)Wext, (__half*)WextT, nblk, tmask,
+                                                                   D, r, RPAD, scaling);
   return check_launch("lora_pack_kernel");
 }
 extern "C" int tb_lora_grad(const void* dY, const void* y_ext, const void* dA_ext, int64_t ld, float* dB,
-                            float* dA, int M, int T, int D, int r, float scaling, void* stream) {
+                            float* dA, int M, int nblk, int tmask, int D, int r, float scaling, void* stream) {
   TB_ENTER();
-  TB_REQUIRE(dY && y_ext && dA_ext && dB && dA && r <= 8 && T * r <= 16, TB_E_ARG, "tb_lora_grad: bad args");
+  TB_REQUIRE(dY && y_ext && dA_ext && dB && dA && lora_mask_ok(nblk, tmask, r, LORA_RMAX), TB_E_ARG,
+             "tb_lora_grad: bad args (nblk=%d tmask=%d r=%d)", nblk, tmask, r);
   TB_REQUIRE(D % 2 == 0 && ld % 2 == 0, TB_E_ALIGN, "tb_lora_grad: D and ld must be even");
-  const int pairs = (T * D + D) / 2;
+  const int pairs = (nblk * D + D) / 2;
   dim3 grid((pairs + 127) / 128, (M + LG_ROWS - 1) / LG_ROWS);
-  lora_grad_kernel<<<grid, 128, 0, st>>>((const __half*)dY, (const __half*)y_ext,
-                                                   (const __half*)dA_ext, ld, dB, dA, M, T, D, r, scaling);
+  lora_grad_kernel<<<grid, 128, 0, st>>>((const __half*)dY, (const __half*)y_ext, (const __half*)dA_ext, ld, dB, dA,
+                                         M, nblk, tmask, D, r, scaling);
   return check_launch("lora_grad_kernel");
 }
 extern "C" int tb_lora_dx(void* dA_ext, int64_t ld, const float* A, int M, int D, int R, void* stream) {
   TB_ENTER();
-  TB_REQUIRE(dA_ext && A && R <= 16, TB_E_ARG, "tb_lora_dx: bad args");
+  TB_REQUIRE(dA_ext && A && R >= 1 && R <= LORA_RMAX, TB_E_ARG, "tb_lora_dx: bad args (R=%d)", R);
   lora_dx_kernel<<<M, 256, 0, st>>>((__half*)dA_ext, ld, A, M, D, R);
   return check_launch("lora_dx_kernel");
 }

@@ -91,9 +91,16 @@ constexpr int MAX_WS = 64;  // PyTorch hands out streams from a pool of 32 per d
 static Workspace g_ws[MAX_WS];
 static int g_nws = 0;
 
+static int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) cudaGetLastError();
+  return dev;
+}
+
 const Workspace* find_ws(void* stream) {
+  const int dev = current_device();
   for (int i = 0; i < g_nws; ++i)
-    if (g_ws[i].stream == stream) return &g_ws[i];
+    if (g_ws[i].stream == stream && g_ws[i].device == dev) return &g_ws[i];
   return nullptr;
 }
 
@@ -108,13 +115,15 @@ extern "C" int tb_set_workspace(void* stream, void* ptr, size_t bytes) {
              "tb_set_workspace: pointer must be 256-byte aligned and larger than %zu bytes",
              2 * WS_COUNTER_BYTES);
   int slot = -1;
+  const int dev = current_device();
   for (int i = 0; i < g_nws; ++i)
-    if (g_ws[i].stream == stream) slot = i;
+    if (g_ws[i].stream == stream && g_ws[i].device == dev) slot = i;
   if (slot < 0) {
     TB_REQUIRE(ptr != nullptr, TB_E_ARG, "tb_set_workspace: no workspace registered for this stream");
     TB_REQUIRE(g_nws < MAX_WS, TB_E_ARG, "tb_set_workspace: more than %d streams", MAX_WS);
     slot = g_nws++;
   }
+  g_ws[slot].device = dev;
   g_ws[slot].stream = stream;
   g_ws[slot].base = (char*)ptr;
   g_ws[slot].bytes = ptr ? bytes : 0;

@@ -29,6 +29,7 @@ int make_tmap_f32_plain(CUtensorMap* out, const void* base, int rank, const uint
 // tile counters and stay zero between launches; everything after is free-for-all scratch, valid only between the
 // start and end of one C-ABI call on that stream.
 struct Workspace {
+  int device;    // the table is keyed on (device, stream): the default stream's handle is 0 on every device
   void* stream;
   char* base;
   size_t bytes;

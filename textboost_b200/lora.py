@@ -1,7 +1,8 @@
-"""peft.LoraConfig stand-in for the one configuration the reference uses
-(/root/reference/train_textboost.py:702-709): rank-r LoRA on the CLIP attention q/k/v projections,
-lora_alpha = r, gaussian init, dropout 0.  The arithmetic (peft tuners/lora/layer.py Linear.forward,
-y = W x + b + (alpha/r) B(A(x))) is fused into the QKV GEMM by textboost_b200.clip.ClipEngine."""
+"""peft.LoraConfig stand-in for the reference's use of it (/root/reference/train_textboost.py:702-709): rank-r
+LoRA on the CLIP attention projections, lora_alpha = r, gaussian init, dropout 0.  Default targets are the
+reference's q/k/v; any subset of {q,k,v,out}_proj and any rank 1..16 (``--lora_rank``, run_textboost_db.py:137) is
+accepted.  The arithmetic (peft tuners/lora/layer.py Linear.forward, y = W x + b + (alpha/r) B(A(x))) is fused into
+the projection GEMMs by textboost_b200.clip.ClipEngine."""
 from __future__ import annotations
 
 import dataclasses
@@ -9,7 +10,8 @@ import json
 import os
 from typing import Sequence, Union
 
-SUPPORTED_TARGETS = ("q_proj", "k_proj", "v_proj")
+DEFAULT_TARGETS = ("q_proj", "k_proj", "v_proj")
+SUPPORTED_TARGETS = ("q_proj", "k_proj", "v_proj", "out_proj")
 
 
 @dataclasses.dataclass
@@ -17,17 +19,18 @@ class LoraConfig:
     r: int = 8
     lora_alpha: int = 8
     init_lora_weights: Union[bool, str] = True   # "gaussian": A ~ N(0, (1/r)^2), B = 0
-    target_modules: Sequence[str] = SUPPORTED_TARGETS
+    target_modules: Sequence[str] = DEFAULT_TARGETS
     lora_dropout: float = 0.0
     bias: str = "none"
 
     def validate(self):
-        if sorted(self.target_modules) != sorted(SUPPORTED_TARGETS):
+        t = list(self.target_modules)
+        if not t or len(set(t)) != len(t) or any(m not in SUPPORTED_TARGETS for m in t):
             raise NotImplementedError(
-                f"target_modules={list(self.target_modules)}: the fused LoRA path covers the reference's "
-                f"configuration {list(SUPPORTED_TARGETS)} (train_textboost.py:705)")
-        if not 0 < self.r <= 5:
-            raise NotImplementedError("LoRA rank must be 1..5 (three targets share a 16-column K extension)")
+                f"target_modules={t}: the fused LoRA path covers any subset of {list(SUPPORTED_TARGETS)} "
+                "(the reference uses q/k/v, train_textboost.py:705; fc1 / fc2 of its commented-out list are not built)")
+        if not 0 < self.r <= 16:
+            raise NotImplementedError("LoRA rank must be 1..16 (K extension of the projection GEMMs: <= 64 columns)")
         if self.lora_dropout != 0.0 or self.bias != "none":
             raise NotImplementedError("lora_dropout / bias are not used by the reference path")
 

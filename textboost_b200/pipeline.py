@@ -307,10 +307,7 @@ DiffusionPipeline = StableDiffusionPipeline  # the name the reference imports (t
 
 
 def load_tokenizer(path, subfolder="tokenizer"):
-    """CLIPTokenizer when the checkpoint ships vocab files, else the literal stand-in of synthetic checkpoints."""
-    d = os.path.join(path, subfolder)
-    if os.path.exists(os.path.join(d, "vocab.json")):
-        from transformers import CLIPTokenizer
-        return CLIPTokenizer.from_pretrained(d)
-    from .synthetic import LiteralTokenizer
-    return LiteralTokenizer()
+    """CLIP tokenizer of the checkpoint; the literal stand-in only for a synthetic checkpoint (marker file written by
+    synthetic.write_pretrained).  Missing tokenizer files on a real checkpoint raise OSError."""
+    from .synthetic import load_tokenizer as _load
+    return _load(os.path.join(path, subfolder))

@@ -224,7 +224,7 @@ def model_configs(model: str):
 
 def build_trainer(model: str = "sd15", device="cuda", seed: int = 42, n_added: int = 1, lora_r: int = 4,
                   kpl_weight: float = 0.1, lora_b_std: float = 0.0, keep_sd: bool = False,
-                  **trainer_kw) -> TextBoostTrainer:
+                  lora_targets=("q_proj", "k_proj", "v_proj"), lora_alpha=None, **trainer_kw) -> TextBoostTrainer:
     """Random-init TextBoost trainer.  n_added rows are appended to the vocabulary and initialised from an
     existing row (utils.add_token, textboost/utils.py:117-166).  keep_sd=True stashes the generated
     state dicts on ``trainer.synthetic`` so a checker can rebuild the same model elsewhere."""
@@ -240,7 +240,8 @@ def build_trainer(model: str = "sd15", device="cuda", seed: int = 42, n_added: i
     emb = csd["text_model.embeddings.token_embedding.weight"]
     csd_t = dict(csd)
     csd_t["text_model.embeddings.token_embedding.weight"] = torch.cat([emb, emb[1929:1929 + n_added]], 0)
-    te = ClipEngine(ccfg, csd_t, device, lora_r=lora_r, n_base=ccfg.vocab_size, seed=seed + 3)
+    te = ClipEngine(ccfg, csd_t, device, lora_r=lora_r, lora_alpha=lora_alpha, n_base=ccfg.vocab_size, seed=seed + 3,
+                    lora_targets=lora_targets)
     te.set_null_embedding(null)
     if lora_b_std > 0:  # step-0 dL/dA is exactly 0 with B = 0 (SURVEY.md trap 13): tests use B != 0
         g = torch.Generator(device=device).manual_seed(seed + 4)
@@ -305,6 +306,54 @@ class LiteralTokenizer:
         return SimpleNamespace(input_ids=row, attention_mask=mask)
 
 
+LITERAL_MARKER = "literal_tokenizer.json"
+
+
+def write_literal_tokenizer_marker(directory: str, vocab_size: int = 49408):
+    """tokenizer/literal_tokenizer.json: the explicit opt-in that lets load_tokenizer hand out the LiteralTokenizer
+    for a synthetic checkpoint.  A real checkpoint without vocab.json / merges.txt raises instead of silently
+    training on hashed ids."""
+    import json
+    import os
+    os.makedirs(os.path.join(directory, "tokenizer"), exist_ok=True)
+    with open(os.path.join(directory, "tokenizer", LITERAL_MARKER), "w") as f:
+        json.dump({"tokenizer_class": "LiteralTokenizer", "vocab_size": vocab_size, "model_max_length": 77}, f)
+
+
+def load_tokenizer(name_or_dir: str, allow_literal: bool = False):
+    """The reference's ``AutoTokenizer.from_pretrained(..., subfolder="tokenizer", use_fast=False)``
+    (/root/reference/train_textboost.py:630-638) for a tokenizer directory or hub id.
+
+    * directory with vocab.json + merges.txt -> transformers' CLIP tokenizer;
+    * directory holding the literal marker written by write_pretrained (a synthetic checkpoint), or
+      allow_literal=True (--synthetic_data) -> LiteralTokenizer;
+    * a name that is not a local directory -> AutoTokenizer.from_pretrained(name) (needs the hub / a cache);
+    * anything else -> OSError.  Never a silent fallback: hashed ids on a real checkpoint would train garbage."""
+    import json
+    import os
+    if os.path.isdir(name_or_dir):
+        if os.path.exists(os.path.join(name_or_dir, "vocab.json")):
+            if not os.path.exists(os.path.join(name_or_dir, "merges.txt")):
+                raise OSError(f"{name_or_dir}: vocab.json without merges.txt")
+            from transformers import AutoTokenizer
+            return AutoTokenizer.from_pretrained(name_or_dir, use_fast=False)
+        marker = os.path.join(name_or_dir, LITERAL_MARKER)
+        if os.path.exists(marker):
+            with open(marker) as f:
+                m = json.load(f)
+            return LiteralTokenizer(m.get("vocab_size", 49408), m.get("model_max_length", 77))
+        if allow_literal:
+            return LiteralTokenizer()
+        raise OSError(f"{name_or_dir}: no vocab.json / merges.txt (and no {LITERAL_MARKER} marker of a synthetic "
+                      "checkpoint); refusing to fall back to the literal stand-in tokenizer")
+    if allow_literal:  # --synthetic_data: the explicit opt-in
+        return LiteralTokenizer()
+    if os.path.isdir(os.path.dirname(os.path.abspath(name_or_dir))) and os.sep in name_or_dir:
+        raise OSError(f"{name_or_dir}: tokenizer directory not found")  # <checkpoint>/tokenizer is missing
+    from transformers import AutoTokenizer
+    return AutoTokenizer.from_pretrained(name_or_dir, use_fast=False)
+
+
 def write_pretrained(directory: str, model: str = "tiny", seed: int = 0, prediction_type: str = "epsilon",
                      vae_channels=None):
     """Write a random-init checkpoint in the diffusers directory layout (unet/, text_encoder/, scheduler/, and
@@ -337,6 +386,7 @@ def write_pretrained(directory: str, model: str = "tiny", seed: int = 0, predict
                   metadata={"format": "pt"})
         with open(os.path.join(directory, "vae", "config.json"), "w") as f:
             json.dump(vae.config_to_dict(vcfg), f, indent=2)
+    write_literal_tokenizer_marker(directory)
     with open(os.path.join(directory, "scheduler", "scheduler_config.json"), "w") as f:
         json.dump({"_class_name": "DDPMScheduler", "num_train_timesteps": 1000, "beta_start": 0.00085,
                    "beta_end": 0.012, "beta_schedule": "scaled_linear", "prediction_type": prediction_type}, f)

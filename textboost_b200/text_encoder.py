@@ -33,7 +33,7 @@ from typing import Dict, Iterator, Optional, Tuple
 
 import torch
 
-from .clip import EOS_ID, LORA_TARGETS, ClipConfig, ClipEngine
+from .clip import EOS_ID, LORA_TARGETS, ClipConfig, ClipEngine, canonical_targets
 from .lora import LoraConfig
 
 F32 = torch.float32
@@ -252,7 +252,7 @@ class TextBoostModel:
         r, D = adapter_config.r, self.config.hidden_size
         g = torch.Generator().manual_seed(self._seed + 7)
         for l in range(self.config.num_hidden_layers):
-            for t in LORA_TARGETS:
+            for t in canonical_targets(adapter_config.target_modules):
                 p = f"text_model.encoder.layers.{l}.self_attn.{t}."
                 for kind in ("weight", "bias"):
                     self._sd[p + "base_layer." + kind] = self._sd.pop(p + kind)
@@ -338,8 +338,9 @@ class TextBoostModel:
     def _materialize(self, device):
         r = self._lora.r if self._lora is not None else 0
         alpha = self._lora.lora_alpha if self._lora is not None else None
+        targets = self._lora.target_modules if self._lora is not None else LORA_TARGETS
         self._engine = ClipEngine(self.config, self._sd, device, lora_r=r, lora_alpha=alpha,
-                                  n_base=self._n_base, seed=self._seed)
+                                  n_base=self._n_base, seed=self._seed, lora_targets=targets)
         self._engine.null_embedding = self.null_embedding.to(device)
         self._engine.use_fixed_special = self._use_fixed_special_embedding
         self._engine.null_override = self._null_override
@@ -363,7 +364,7 @@ class TextBoostModel:
         st = e.state
         r = st.r
         for l in range(e.nl):
-            for ti, t in enumerate(LORA_TARGETS if r else ()):
+            for ti, t in enumerate(e.targets):
                 p = f"text_model.encoder.layers.{l}.self_attn.{t}."
                 yield (p + "lora_A.default.weight", st.A(l)[ti * r:(ti + 1) * r],
                        st.A(l, st.grads)[ti * r:(ti + 1) * r])

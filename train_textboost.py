@@ -176,14 +176,13 @@ def load_scheduler_config(path):
 
 
 def load_tokenizer(args):
-    """transformers tokenizer when its files exist; otherwise the literal-id stand-in used by the synthetic
-    workload (no vocab.json / merges.txt exist offline)."""
+    """The reference's tokenizer load (train_textboost.py:630-638): --tokenizer_name (directory or hub id) or
+    <checkpoint>/tokenizer.  The literal-id stand-in is handed out only for a synthetic checkpoint (marker file
+    written by synthetic.write_pretrained) or under --synthetic_data; a real checkpoint whose tokenizer files are
+    missing raises OSError."""
     from textboost_b200 import synthetic
     d = args.tokenizer_name or os.path.join(args.pretrained_model_name_or_path, "tokenizer")
-    if os.path.exists(os.path.join(d, "vocab.json")):
-        from transformers import AutoTokenizer
-        return AutoTokenizer.from_pretrained(d, use_fast=False)
-    return synthetic.LiteralTokenizer()
+    return synthetic.load_tokenizer(d, allow_literal=bool(getattr(args, "synthetic_data", False)))
 
 
 def build_image_batches(args, tokenizer, rank, world):
