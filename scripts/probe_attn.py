@@ -33,6 +33,14 @@ for (B, H, Nq, Nk, d) in [(8, 8, 4096, 4096, 40), (8, 8, 4096, 77, 40), (8, 8, 1
         k, v = kv[..., :C], kv[..., C:]
     do = torch.randn(B, Nq, C, device=dev, dtype=torch.float16)
     o, lse = ops.attn_fwd(q, k, v, H)
+    if B * H * Nq * Nk <= 8 * 8 * 4096 * 4096:
+        def hd(t):
+            return t.reshape(B, -1, H, d).transpose(1, 2)
+        oref = torch.nn.functional.scaled_dot_product_attention(hd(q).float(), hd(k).float(), hd(v).float())
+        err = ((o.float().view(B, Nq, H, d).transpose(1, 2) - oref).abs().max() / oref.abs().max()).item()
+        del oref
+    else:
+        err = float("nan")
     tf = time_it(lambda: ops.attn_fwd(q, k, v, H))
     tb = time_it(lambda: ops.attn_bwd(q, k, v, o, do, lse, H))
     fl = 4.0 * B * H * Nq * Nk * d
@@ -42,4 +50,4 @@ for (B, H, Nq, Nk, d) in [(8, 8, 4096, 4096, 40), (8, 8, 4096, 77, 40), (8, 8, 1
     qh, kh, vh = heads(q), heads(k), heads(v)
     tt = time_it(lambda: torch.nn.functional.scaled_dot_product_attention(qh, kh, vh))
     print(f"attn B={B} H={H} Nq={Nq} Nk={Nk} d={d}: fwd {tf:.3f} ms ({fl / tf / 1e9:.0f} TF/s) bwd {tb:.3f} ms "
-          f"({2 * fl / tb / 1e9:.0f} TF/s alg) | torch sdpa fwd {tt:.3f} ms", flush=True)
+          f"({2 * fl / tb / 1e9:.0f} TF/s alg) | torch sdpa fwd {tt:.3f} ms | fwd err {err:.1e}", flush=True)

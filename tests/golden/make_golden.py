@@ -24,7 +24,10 @@ L = 77
 
 
 def make_weights(hidden, heads, layers, inter, n_added, seed=1234):
-    """HF-keyed fp32 state dict, deterministic."""
+    """HF-keyed fp32 state dict, deterministic.  Projection / MLP weights ~ N(0, 0.08) at the toy widths and
+    N(0, 0.03) at full width (per-layer gain 0.08 sqrt(128) ~ 0.03 sqrt(768) ~ 0.9: a 12-layer random net with gain
+    2.2 per layer is ill-conditioned and would test fp16 error amplification, not the encoder)."""
+    wstd = 0.08 if hidden <= 256 else 0.03
     g = torch.Generator().manual_seed(seed)
     sd = {}
 
@@ -36,14 +39,14 @@ def make_weights(hidden, heads, layers, inter, n_added, seed=1234):
     for l in range(layers):
         p = f"text_model.encoder.layers.{l}."
         for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
-            sd[p + f"self_attn.{n}.weight"] = rn(hidden, hidden, std=0.08)
+            sd[p + f"self_attn.{n}.weight"] = rn(hidden, hidden, std=wstd)
             sd[p + f"self_attn.{n}.bias"] = rn(hidden)
         for n in ("layer_norm1", "layer_norm2"):
             sd[p + n + ".weight"] = 1.0 + rn(hidden, std=0.1)
             sd[p + n + ".bias"] = rn(hidden)
-        sd[p + "mlp.fc1.weight"] = rn(inter, hidden, std=0.08)
+        sd[p + "mlp.fc1.weight"] = rn(inter, hidden, std=wstd)
         sd[p + "mlp.fc1.bias"] = rn(inter)
-        sd[p + "mlp.fc2.weight"] = rn(hidden, inter, std=0.08)
+        sd[p + "mlp.fc2.weight"] = rn(hidden, inter, std=wstd if hidden <= 256 else wstd / 2)
         sd[p + "mlp.fc2.bias"] = rn(hidden)
     sd["text_model.final_layer_norm.weight"] = 1.0 + rn(hidden, std=0.1)
     sd["text_model.final_layer_norm.bias"] = rn(hidden)

@@ -205,7 +205,11 @@ TOL_ATTN = 3e-3
                                          (1, 2, 256, 77, 40), (1, 2, 64, 64, 160), (2, 2, 256, 256, 160),
                                          (1, 2, 256, 77, 160), (1, 2, 300, 200, 80), (2, 8, 1024, 1024, 80),
                                          (1, 8, 4096, 4096, 40), (2, 8, 4096, 77, 40), (1, 5, 2304, 2304, 64),
-                                         (1, 4, 1024, 77, 160), (2, 8, 1024, 77, 80), (8, 8, 4096, 77, 40)])
+                                         (1, 4, 1024, 77, 160), (2, 8, 1024, 77, 80), (8, 8, 4096, 77, 40),
+                                         # the two-query-tile forward kernel: a lone first tile (Nq = 384), padding
+                                         # keys in the last KV tile, head_dim 64 / 80 / 96, 2 and 3 KV stages
+                                         (1, 2, 384, 300, 40), (1, 2, 576, 576, 64), (1, 2, 300, 333, 80),
+                                         (2, 1, 512, 1000, 96), (1, 3, 1280, 256, 48)])
 def test_attention_fwd_bwd(B, H, Nq, Nk, d):
     from textboost_b200 import ops
     g = torch.Generator(device=dev).manual_seed(Nq + Nk + d)
@@ -237,6 +241,32 @@ def test_attention_fwd_bwd(B, H, Nq, Nk, d):
     dq2, dk2, dv2 = ops.attn_bwd(q, k, v, o, do, lse, H, need_dq=False)  # first cross-attention: dK/dV only
     # (under-filled grids split the Q loop over CTAs that meet in fp32 red.adds: equal up to summation order)
     assert dq2 is None and relerr(dk2, dk) < 1e-3 and relerr(dv2, dv) < 1e-3
+
+
+@pytest.mark.parametrize("d", [40, 80])
+def test_attention_fwd_growing_row_maximum(d):
+    """The forward kernels keep a stale reference maximum until the row maximum grows by more than 2^8 and then
+    rescale O and the row sum in TMEM: later KV tiles carry much larger scores here, so every row rescales several
+    times; a row of all-equal scores and a constant V check the row sum itself."""
+    from textboost_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(d)
+    B, H, N = 1, 2, 1024
+    Cc = H * d
+    q = torch.randn(B, N, Cc, device=dev, dtype=F16, generator=g)
+    k = torch.randn(B, N, Cc, device=dev, dtype=F16, generator=g)
+    v = torch.randn(B, N, Cc, device=dev, dtype=F16, generator=g)
+    k[:, 256:512] *= 4.0
+    k[:, 640:] *= 12.0   # scores up to ~ +-80 in the last tiles
+    q[:, 7] = 0          # an all-equal row: uniform softmax
+    o, lse = ops.attn_fwd(q, k, v, H)
+
+    def heads(t):
+        return t.reshape(B, -1, H, d).transpose(1, 2).float()
+    s = (heads(q) @ heads(k).transpose(-1, -2)) * d ** -0.5
+    oref = (torch.softmax(s, -1) @ heads(v)).transpose(1, 2).reshape(B, N, Cc)
+    assert relerr(o, oref) < TOL_ATTN
+    assert (lse - torch.logsumexp(s, -1) * math.log2(math.e)).abs().max().item() < 2e-2
+    assert (o[:, 7].float() - v.float().view(B, N, H, d).mean(1).reshape(B, Cc)).abs().max().item() < 2e-3
 
 
 @pytest.mark.parametrize("B,H,N,d", [(2, 12, 77, 64), (3, 2, 128, 64), (1, 2, 300, 40), (16, 16, 77, 64)])

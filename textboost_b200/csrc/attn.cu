@@ -23,6 +23,8 @@
 // per row the per-thread TMEM-load / exp latency chain leaves it ~40 % utilised (ncu, profiles/).
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "host_util.h"
 #include "sm100.cuh"
 
@@ -383,6 +385,355 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc_rt(tmem, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------ forward, v2
+// Long, non-causal sequences with head_dim <= 112 (every UNet self-attention level that matters: 64x64 at d = 40,
+// 32x32 at d = 80, and head_dim 64 of SD-2.x).  attn_fwd_kernel serialises  S MMA -> softmax -> PV MMA  inside a
+// CTA and leans on a second resident CTA for overlap; measured 1756 cycles per 128x128 tile per SM against the
+// 1024-cycle exponential bound (and 1.5x behind cuDNN's fused kernel).  Here ONE CTA per SM owns TWO query tiles
+// (256 rows) of a (b, h) and ping-pongs them through the tensor core:
+//   * TMEM: S0 [0,128) S1 [128,256) (P_t, packed fp16, overwrites the first 64 columns of S_t), O0, O1 at
+//     256 + t*dn, row sums L0, L1 (the ones-tile MMA) behind them  (<= 512 columns for dn <= 112);
+//   * warps 0-3 = softmax of tile 0, warps 4-7 = softmax of tile 1, ONE THREAD PER ROW: the row maximum needs no
+//     exchange between threads, hence no CTA-level barrier anywhere in the loop;
+//   * warp 8 = TMA (K/V ring), warp 9 = MMA issuer.  Issue order per KV tile j:
+//       [P0(j) ready] PV0(j), S0(j+1)   [P1(j) ready] PV1(j), S1(j+1)
+//     so while the softmax warps of tile 0 work on S0(j+1), the tensor core runs PV1(j) and S1(j+1), and vice versa;
+//     tcgen05.mma executes in issue order, so S_t(j+1) complete implies PV_t(j) complete (O_t may be rescaled).
+//   * the scores are read from TMEM in two passes of four 32-column chunks (max, then exp) so a thread never holds
+//     more than two chunks; P leaves chunk by chunk (16 packed columns) behind the chunk that has been consumed;
+//   * scale-and-subtract runs as packed fp32x2 FMAs (FFMA2: one instruction per two scores), the exponentials as
+//     MUFU.EX2, and -- TB_ATTN_FWD2_POLY of every 8 packed pairs -- as a degree-3 polynomial on the FMA pipe
+//     (Cody-Waite split + exponent insertion, all packed): the loop is bound by the 16 ex2/clk/SM of the MUFU, so
+//     moving a share of the exponentials to the FMA pipe shortens it (FlashAttention-4's split).
+#ifndef TB_ATTN_FWD2_POLY
+#define TB_ATTN_FWD2_POLY 0
+#endif
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t sub_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// two exponentials 2^e0, 2^e1 (e <= ~8) as a packed fp16 pair, on MUFU
+__device__ __forceinline__ uint32_t exp2_pair_mufu(uint64_t e) {
+  float e0, e1;
+  unpack_f32x2(e, e0, e1);
+  return exp2_pack(e0, e1);
+}
+// the same on the FMA / ALU pipes: x = r + f, r = rint(x) from the magic-number add, 2^f by a degree-3 minimax
+// polynomial on [-0.5, 0.5] (max relative error 1.0e-4, a fifth of an fp16 ulp of P), 2^r into the exponent field.
+__device__ __forceinline__ uint32_t exp2_pair_poly(uint64_t e) {
+  float e0, e1;
+  unpack_f32x2(e, e0, e1);
+  e = pack_f32x2(fmaxf(e0, -125.f), fmaxf(e1, -125.f));
+  const uint64_t magic = pack_f32x2(12582912.f, 12582912.f);
+  const uint64_t xf = add_f32x2(e, magic);
+  const uint64_t fr = sub_f32x2(e, sub_f32x2(xf, magic));
+  uint64_t q = pack_f32x2(0.05550410866f, 0.05550410866f);
+  q = fma_f32x2(q, fr, pack_f32x2(0.2402265069f, 0.2402265069f));
+  q = fma_f32x2(q, fr, pack_f32x2(0.6931471806f, 0.6931471806f));
+  q = fma_f32x2(q, fr, pack_f32x2(1.0f, 1.0f));
+  float q0, q1, x0, x1;
+  unpack_f32x2(q, q0, q1);
+  unpack_f32x2(xf, x0, x1);
+  const float r0 = __int_as_float(__float_as_int(q0) + (__float_as_int(x0) << 23));
+  const float r1 = __int_as_float(__float_as_int(q1) + (__float_as_int(x1) << 23));
+  uint32_t o;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(o) : "f"(r1), "f"(r0));
+  return o;
+}
+
+template <int NB, int STAGES>
+__global__ void __launch_bounds__(384, 1)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  constexpr int TILE = NB * ABOX;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;                  // two query tiles
+  uint8_t* sK = sQ + 2 * TILE;
+  uint8_t* sV = sK + STAGES * TILE;
+  uint8_t* sOnes = sV + STAGES * TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + ABOX);
+  uint64_t* bar_q = bars;              // [2]
+  uint64_t* bar_s = bars + 2;          // [2]
+  uint64_t* bar_p = bars + 4;          // [2]
+  uint64_t* bar_o = bars + 6;          // [2]
+  uint64_t* kv_full = bars + 8;
+  uint64_t* kv_empty = bars + 8 + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+  const int n_kv = p.n_inner;
+  const bool two = q0 + 128 < p.Nq;  // the second query tile holds rows
+  const uint32_t O_COL = 256, L_COL = 256 + 2 * p.dn;
+
+  if (threadIdx.x == 288) {
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(smem_u32(&bar_q[t]), 1);
+      mbar_init(smem_u32(&bar_s[t]), 1);
+      mbar_init(smem_u32(&bar_p[t]), 128);
+      mbar_init(smem_u32(&bar_o[t]), 1);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&kv_full[s]), 1);
+      mbar_init(smem_u32(&kv_empty[s]), 1);
+    }
+    mbar_fence_init();
+  }
+  {
+    const uint4 ones = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+    for (int i = threadIdx.x; i < ABOX / 16; i += 384) reinterpret_cast<uint4*>(sOnes)[i] = ones;
+    fence_async_smem();
+  }
+  if (warp == 0) tmem_alloc_rt(smem_u32(tmem_slot), 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 8) {
+    // ---------------------------------------------------------------- TMA producer
+    if (elect_one()) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmK);
+      tma_prefetch_desc(&tmV);
+      for (int t = 0; t < (two ? 2 : 1); ++t) {
+        mbar_expect_tx(smem_u32(&bar_q[t]), TILE);
+        for (int x = 0; x < NB; ++x)
+          tma_load_4d(smem_u32(sQ + t * TILE + x * ABOX), &tmQ, smem_u32(&bar_q[t]), x * 64, h, q0 + t * 128, b);
+      }
+    }
+    __syncwarp();
+    for (int j = 0; j < n_kv; ++j) {
+      const int s = j % STAGES;
+      const uint32_t ph = (j / STAGES) & 1;
+      mbar_wait(smem_u32(&kv_empty[s]), ph ^ 1);
+      if (elect_one()) {
+        const uint32_t fb = smem_u32(&kv_full[s]);
+        mbar_expect_tx(fb, 2 * TILE);
+        for (int x = 0; x < NB; ++x) {
+          tma_load_4d(smem_u32(sK + s * TILE + x * ABOX), &tmK, fb, x * 64, h, j * 128, b);
+          tma_load_4d(smem_u32(sV + s * TILE + x * ABOX), &tmV, fb, x * 64, h, j * 128, b);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 9) {
+    // ---------------------------------------------------------------- MMA issuer
+    const uint32_t idesc_s = umma_idesc_f16(128, 128, 0, 0);
+    const uint32_t idesc_o = umma_idesc_f16(128, p.dn, 0, 1);  // B = V is MN-major
+    const uint32_t idesc_l = umma_idesc_f16(128, 16, 0, 1);
+    const int nks = p.dn / 16;
+    const int nt = two ? 2 : 1;
+    const uint32_t hi = umma_desc_hi_sw128(1024);
+    const uint32_t ones_lo = umma_desc_lo(smem_u32(sOnes), ABOX);
+    auto issue_s = [&](int t, int s) {  // S_t = Q_t K(s)^T
+      const uint32_t q_lo = umma_desc_lo(smem_u32(sQ + t * TILE), 16);
+      const uint32_t k_lo = umma_desc_lo(smem_u32(sK + s * TILE), 16);
+      for (int ks = 0; ks < nks; ++ks) {
+        const uint32_t off = ((ks >> 2) * ABOX + (ks & 3) * 32) >> 4;
+        umma_f16_ss(tmem + t * 128, umma_desc_pack(q_lo + off, hi), umma_desc_pack(k_lo + off, hi), idesc_s, ks > 0);
+      }
+      umma_commit(smem_u32(&bar_s[t]));
+    };
+    mbar_wait(smem_u32(&kv_full[0]), 0);
+    for (int t = 0; t < nt; ++t) {
+      mbar_wait(smem_u32(&bar_q[t]), 0);
+      tc_fence_after();
+      if (elect_one()) issue_s(t, 0);
+      __syncwarp();
+    }
+    for (int j = 0; j < n_kv; ++j) {
+      const int s = j % STAGES;
+      const bool more = j + 1 < n_kv;
+      const int s1 = (j + 1) % STAGES;
+      const uint32_t v_lo = umma_desc_lo(smem_u32(sV + s * TILE), ABOX);
+      if (more) mbar_wait(smem_u32(&kv_full[s1]), ((j + 1) / STAGES) & 1);
+      // keys past Nk have P == 0: skip their k-steps
+      const int kvalid = min(128, p.Nk - j * 128);
+      const int nkk = (kvalid + 15) >> 4;
+      for (int t = 0; t < nt; ++t) {
+        mbar_wait(smem_u32(&bar_p[t]), j & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t pcol = tmem + t * 128;
+          for (int ks = 0; ks < nkk; ++ks) {
+            umma_f16_ts(tmem + O_COL + t * p.dn, pcol + ks * 8, umma_desc_pack(v_lo + ks * 128, hi), idesc_o,
+                        (j > 0) || (ks > 0));
+            umma_f16_ts(tmem + L_COL + t * 16, pcol + ks * 8, umma_desc_pack(ones_lo + ks * 128, hi), idesc_l,
+                        (j > 0) || (ks > 0));
+          }
+          if (more) issue_s(t, s1);
+          else umma_commit(smem_u32(&bar_o[t]));
+          if (t == nt - 1) umma_commit(smem_u32(&kv_empty[s]));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 8 && (warp < 4 || two)) {
+    // ---------------------------------------------------------------- softmax warps: one thread per query row
+    const int t = warp >> 2, quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t s_col = lane_addr + t * 128;            // S_t, and P_t over its first 64 columns
+    const uint32_t o_col = lane_addr + O_COL + t * p.dn;
+    const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2);
+    float m_run = 0.f;
+    // one KV tile; MASKED (a compile-time flag, so the full tiles carry no per-element selects) = the last tile when
+    // Nk is not a multiple of 128: columns >= limit are padding keys
+    auto tile = [&](int j, auto masked_tag) {
+      constexpr bool MASKED = decltype(masked_tag)::value;
+      const int limit = p.Nk - j * 128;
+      mbar_wait(smem_u32(&bar_s[t]), j & 1);
+      tc_fence_after();
+      // ---- pass 1: row maximum
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      {
+        uint32_t ra[32], rb[32];
+        tmem_ld32(s_col, ra);
+        tmem_ld_wait32(ra);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t* cur = (c & 1) ? rb : ra;
+          uint32_t* nxt = (c & 1) ? ra : rb;
+          if (c < 3) tmem_ld32(s_col + (c + 1) * 32, nxt);
+          if (MASKED) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= limit) cur[i] = 0xff800000u;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            mx0 = fmax3(mx0, __uint_as_float(cur[i]), __uint_as_float(cur[i + 1]));
+            mx1 = fmax3(mx1, __uint_as_float(cur[i + 2]), __uint_as_float(cur[i + 3]));
+            mx2 = fmax3(mx2, __uint_as_float(cur[i + 4]), __uint_as_float(cur[i + 5]));
+            mx3 = fmax3(mx3, __uint_as_float(cur[i + 6]), __uint_as_float(cur[i + 7]));
+          }
+          if (c < 3) tmem_ld_wait32(nxt);
+        }
+      }
+      const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+      if (j == 0) {
+        m_run = m_tile;
+      } else {
+        // lazy rescale: keep the old reference maximum unless the row maximum grew by more than 2^8
+        const bool need = m_tile > m_run + 8.f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = need ? exp2f(m_run - m_tile) : 1.f;
+          // S_t(j) complete implies PV_t(j-1) complete (issue order): O_t and L_t are stable
+          for (int c = 0; c < p.dn; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(o_col + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st16(o_col + c, v);
+          }
+          {
+            uint32_t v[16];
+            tmem_ld16(lane_addr + L_COL + t * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st16(lane_addr + L_COL + t * 16, v);
+          }
+        }
+        if (need) m_run = m_tile;
+      }
+      // ---- pass 2: P = exp2(S*c - m), packed fp16, written over the consumed score columns
+      const uint64_t negm2 = pack_f32x2(-m_run, -m_run);
+      {
+        uint32_t ra[32], rb[32];
+        tmem_ld32(s_col, ra);
+        tmem_ld_wait32(ra);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t* cur = (c & 1) ? rb : ra;
+          uint32_t* nxt = (c & 1) ? ra : rb;
+          if (c < 3) tmem_ld32(s_col + (c + 1) * 32, nxt);
+          if (MASKED) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= limit) cur[i] = 0xff800000u;
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint64_t e = fma_f32x2(pack_f32x2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1])), sc2, negm2);
+            pk[i] = (i & 7) >= 8 - TB_ATTN_FWD2_POLY ? exp2_pair_poly(e) : exp2_pair_mufu(e);
+          }
+          // chunk c+1 (columns 32c+32 ..) is already in flight: P columns [16c, 16c+16) only cover consumed scores
+          if (c < 3) tmem_ld_wait32(nxt);
+          tmem_st16(s_col + c * 16, pk);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bar_p[t]));
+    };
+    const int n_full = p.Nk / 128;  // tiles without padding keys
+    for (int j = 0; j < n_full; ++j) tile(j, std::false_type{});
+    if (n_full < n_kv) tile(n_full, std::true_type{});
+    // ---- epilogue: O / L
+    mbar_wait(smem_u32(&bar_o[t]), 0);
+    tc_fence_after();
+    float l;
+    {
+      uint32_t v[8];
+      tmem_ld8(lane_addr + L_COL + t * 16, v);
+      tmem_ld_wait();
+      l = __uint_as_float(v[0]);
+    }
+    const float inv_l = 1.f / l;
+    const int q = q0 + t * 128 + row;
+    const bool ok = q < p.Nq;
+    __half* op = p.O + ((long long)b * p.Nq + q) * p.ldo + h * p.d;
+    for (int c = 0; c < p.dn; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(o_col + c, v);
+      tmem_ld_wait();
+      if (ok) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (c + g * 8 < p.d) {
+            uint4 o;
+            o.x = pack_half2(__uint_as_float(v[g * 8 + 0]) * inv_l, __uint_as_float(v[g * 8 + 1]) * inv_l);
+            o.y = pack_half2(__uint_as_float(v[g * 8 + 2]) * inv_l, __uint_as_float(v[g * 8 + 3]) * inv_l);
+            o.z = pack_half2(__uint_as_float(v[g * 8 + 4]) * inv_l, __uint_as_float(v[g * 8 + 5]) * inv_l);
+            o.w = pack_half2(__uint_as_float(v[g * 8 + 6]) * inv_l, __uint_as_float(v[g * 8 + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(op + c + g * 8) = o;
+          }
+        }
+      }
+    }
+    if (ok && p.lse) p.lse[((long long)b * p.heads + h) * p.Nq + q] = m_run + log2f(l);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc_rt(tmem, 512u);
 }
 
 // ------------------------------------------------------------------------------------ backward
@@ -1242,6 +1593,25 @@ static int launch_attn_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const C
   return check_launch("attn_fwd_kernel");
 }
 
+template <int NB, int STAGES>
+static int launch_attn_fwd2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                            const AttnParams& p, int B, cudaStream_t st) {
+  constexpr int smem = NB * ABOX * (2 + 2 * STAGES) + ABOX + 256 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd2_kernel<NB, STAGES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(attn_fwd2<%d,%d>, %d): %s", NB, STAGES, smem, cudaGetErrorString(e));
+      return TB_E_CUDA;
+    }
+    configured = true;
+  }
+  dim3 grid((p.Nq + 255) / 256, p.heads, B);
+  attn_fwd2_kernel<NB, STAGES><<<grid, 384, smem, st>>>(tq, tk, tv, p);
+  return check_launch("attn_fwd2_kernel");
+}
+
 static int launch_attn_bwd2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                             const CUtensorMap& tdo, const AttnParams& p, int B, cudaStream_t st) {
   constexpr int STAGES = 2;
@@ -1312,6 +1682,12 @@ extern "C" int tb_attn_fwd_f16(const void* q, int64_t ldq, const void* k, int64_
   p.n_inner = (Nk + 127) / 128;
   const int nb = (d + 63) / 64;
   cudaStream_t st = (cudaStream_t)stream;
+  // long non-causal sequences: the two-query-tile ping-pong kernel (one CTA per SM)
+  static const bool v1 = getenv("TB_ATTN_FWD_V1") != nullptr;  // diagnostic switch: the two-CTA-per-SM kernel
+  if (!v1 && !causal && p.dn <= 112 && Nq >= 256 && Nk >= 256) {
+    if (nb == 1) return launch_attn_fwd2<1, 3>(tq, tk, tv, p, B, st);
+    return launch_attn_fwd2<2, 2>(tq, tk, tv, p, B, st);
+  }
   if (nb == 1) return launch_attn_fwd<1, 2>(tq, tk, tv, p, B, st);
   if (nb == 2) return launch_attn_fwd<2, 1>(tq, tk, tv, p, B, st);
   return launch_attn_fwd<3, 1>(tq, tk, tv, p, B, st);
