@@ -64,5 +64,7 @@ int main() {
   run<1, 48, false>(d); run<8, 48, false>(d); run<16, 48, false>(d); run<32, 48, false>(d);
   run<8, 16, false>(d); run<16, 16, false>(d); run<16, 128, false>(d); run<32, 128, false>(d); run<16, 256, false>(d);
   run<8, 48, true>(d); run<16, 48, true>(d); run<32, 48, true>(d); run<16, 64, true>(d); run<16, 16, true>(d);
+  run<32, 16, true>(d); run<32, 32, true>(d); run<32, 64, true>(d); run<32, 80, true>(d); run<32, 96, true>(d); run<32, 128, true>(d);
+  run<32, 64, false>(d); run<32, 32, false>(d);
   return 0;
 }

@@ -21,8 +21,11 @@ def time_it(fn, iters=10):
     return e0.elapsed_time(e1) / iters
 
 
-for (B, H, Nq, Nk, d) in [(8, 8, 4096, 4096, 40), (8, 8, 4096, 77, 40), (8, 8, 1024, 1024, 80), (8, 8, 1024, 77, 80),
-                          (8, 8, 256, 256, 160), (8, 8, 256, 77, 160), (16, 12, 77, 77, 64), (4, 5, 9216, 9216, 64)]:
+SHAPES = [(8, 8, 4096, 4096, 40), (8, 8, 4096, 77, 40), (8, 8, 1024, 1024, 80), (8, 8, 1024, 77, 80),
+          (8, 8, 256, 256, 160), (8, 8, 256, 77, 160), (16, 12, 77, 77, 64), (4, 5, 9216, 9216, 64)]
+if len(sys.argv) > 1 and sys.argv[1] == "self":  # the long self-attention shapes only
+    SHAPES = [s for s in SHAPES if s[2] == s[3] and s[2] >= 1024]
+for (B, H, Nq, Nk, d) in SHAPES:
     C = H * d
     if Nq == Nk:
         qkv = torch.randn(B, Nq, 3 * C, device=dev, dtype=torch.float16)

@@ -388,27 +388,39 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------ forward, v2
-// Long, non-causal sequences with head_dim <= 112 (every UNet self-attention level that matters: 64x64 at d = 40,
+// Long, non-causal sequences with head_dim <= 128 (every UNet self-attention level that matters: 64x64 at d = 40,
 // 32x32 at d = 80, and head_dim 64 of SD-2.x).  attn_fwd_kernel serialises  S MMA -> softmax -> PV MMA  inside a
 // CTA and leans on a second resident CTA for overlap; measured 1756 cycles per 128x128 tile per SM against the
 // 1024-cycle exponential bound (and 1.5x behind cuDNN's fused kernel).  Here ONE CTA per SM owns TWO query tiles
 // (256 rows) of a (b, h) and ping-pongs them through the tensor core:
-//   * TMEM: S0 [0,128) S1 [128,256) (P_t, packed fp16, overwrites the first 64 columns of S_t), O0, O1 at
-//     256 + t*dn, row sums L0, L1 (the ones-tile MMA) behind them  (<= 512 columns for dn <= 112);
-//   * warps 0-3 = softmax of tile 0, warps 4-7 = softmax of tile 1, ONE THREAD PER ROW: the row maximum needs no
-//     exchange between threads, hence no CTA-level barrier anywhere in the loop;
-//   * warp 8 = TMA (K/V ring), warp 9 = MMA issuer.  Issue order per KV tile j:
-//       [P0(j) ready] PV0(j), S0(j+1)   [P1(j) ready] PV1(j), S1(j+1)
-//     so while the softmax warps of tile 0 work on S0(j+1), the tensor core runs PV1(j) and S1(j+1), and vice versa;
-//     tcgen05.mma executes in issue order, so S_t(j+1) complete implies PV_t(j) complete (O_t may be rescaled).
+//   * warps 0-3 = softmax of tile 0, warps 4-7 = softmax of tile 1, ONE THREAD PER ROW: the row maximum and the row
+//     sum need no exchange between threads, hence no CTA-level barrier anywhere in the loop; warp 8 = TMA (K/V
+//     ring), warp 9 = MMA issuer;
+//   * head_dim <= 64 (SPLIT): TMEM = S0 [0,128) S1 [128,256) P0 [256,320) P1 [320,384) O0 [384,448) O1 [448,512).
+//     P has its own columns, so S_t(j+1) = Q_t K(j+1)^T is issued as soon as the softmax warps have READ S_t(j)
+//     (bar_sfree), a whole exp pass before they need it: the softmax warps never wait for the tensor core, the two
+//     tiles only compete for the MUFU.  (Measured with P aliasing S, i.e. S_t(j+1) behind PV_t(j): 1230 cycles from
+//     "P published" to "next S seen" per tile -- wake-up + 19 MMAs + commit latency -- of a 3170-cycle iteration.)
+//   * head_dim 65..128: P_t overwrites the first 64 columns of S_t (no room for separate P columns next to two
+//     O accumulators), issue order  [P0(j)] PV0(j), S0(j+1)  [P1(j)] PV1(j), S1(j+1);
+//     tcgen05.mma executes in issue order, so S_t(j+1) complete implies PV_t(j) complete (O_t may be rescaled);
 //   * the scores are read from TMEM in two passes of four 32-column chunks (max, then exp) so a thread never holds
-//     more than two chunks; P leaves chunk by chunk (16 packed columns) behind the chunk that has been consumed;
-//   * scale-and-subtract runs as packed fp32x2 FMAs (FFMA2: one instruction per two scores), the exponentials as
-//     MUFU.EX2, and -- TB_ATTN_FWD2_POLY of every 8 packed pairs -- as a degree-3 polynomial on the FMA pipe
-//     (Cody-Waite split + exponent insertion, all packed): the loop is bound by the 16 ex2/clk/SM of the MUFU, so
-//     moving a share of the exponentials to the FMA pipe shortens it (FlashAttention-4's split).
+//     more than two chunks (TMEM reads run at ~700 B/clk/SM, scripts/micro/softmax_pipes.cu); P leaves chunk by
+//     chunk (16 packed columns);
+//   * scale-and-subtract runs as packed fp32x2 FMAs (FFMA2: one issue slot per two scores), the exponentials as
+//     MUFU.EX2 and -- TB_ATTN_FWD2_POLY of every 8 packed pairs -- as a degree-3 polynomial on the FMA pipe
+//     (Cody-Waite split + exponent insertion, packed): the loop is bound by the 16 ex2/clk/SM of the MUFU, so
+//     moving a share of the exponentials to the FMA pipe shortens it (FlashAttention-4's split);
+//   * the row sum is accumulated in fp32 registers from the unrounded exponentials (as FlashAttention does): the
+//     ones-tile MMA of attn_fwd_kernel costs 8 extra tcgen05.mma per tile at ~14 cycles each.
 #ifndef TB_ATTN_FWD2_POLY
-#define TB_ATTN_FWD2_POLY 0
+#define TB_ATTN_FWD2_POLY 2
+#endif
+// The two softmax warp groups have identical loops; started together they run in lockstep (both in the max pass,
+// then both in the exp pass) and the MUFU idles during the max pass.  Tile 1 starts TB_ATTN_FWD2_SKEW cycles late, so
+// that its max pass falls into the exp pass of tile 0 and vice versa (the offset persists: the loops are symmetric).
+#ifndef TB_ATTN_FWD2_SKEW
+#define TB_ATTN_FWD2_SKEW 1000
 #endif
 __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
   uint64_t r;
@@ -433,15 +445,16 @@ __device__ __forceinline__ uint64_t sub_f32x2(uint64_t a, uint64_t b) {
   asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
-// two exponentials 2^e0, 2^e1 (e <= ~8) as a packed fp16 pair, on MUFU
-__device__ __forceinline__ uint32_t exp2_pair_mufu(uint64_t e) {
+// two exponentials 2^e0, 2^e1 (e <= ~8) on MUFU
+__device__ __forceinline__ void exp2_pair_mufu(uint64_t e, float& p0, float& p1) {
   float e0, e1;
   unpack_f32x2(e, e0, e1);
-  return exp2_pack(e0, e1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(e0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(e1));
 }
 // the same on the FMA / ALU pipes: x = r + f, r = rint(x) from the magic-number add, 2^f by a degree-3 minimax
 // polynomial on [-0.5, 0.5] (max relative error 1.0e-4, a fifth of an fp16 ulp of P), 2^r into the exponent field.
-__device__ __forceinline__ uint32_t exp2_pair_poly(uint64_t e) {
+__device__ __forceinline__ void exp2_pair_poly(uint64_t e, float& p0, float& p1) {
   float e0, e1;
   unpack_f32x2(e, e0, e1);
   e = pack_f32x2(fmaxf(e0, -125.f), fmaxf(e1, -125.f));
@@ -455,11 +468,8 @@ __device__ __forceinline__ uint32_t exp2_pair_poly(uint64_t e) {
   float q0, q1, x0, x1;
   unpack_f32x2(q, q0, q1);
   unpack_f32x2(xf, x0, x1);
-  const float r0 = __int_as_float(__float_as_int(q0) + (__float_as_int(x0) << 23));
-  const float r1 = __int_as_float(__float_as_int(q1) + (__float_as_int(x1) << 23));
-  uint32_t o;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(o) : "f"(r1), "f"(r0));
-  return o;
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(x0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(x1) << 23));
 }
 
 template <int NB, int STAGES>
@@ -467,27 +477,30 @@ __global__ void __launch_bounds__(384, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   constexpr int TILE = NB * ABOX;
+  constexpr bool SPLIT = NB == 1;  // P in its own TMEM columns
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;                  // two query tiles
   uint8_t* sK = sQ + 2 * TILE;
   uint8_t* sV = sK + STAGES * TILE;
-  uint8_t* sOnes = sV + STAGES * TILE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + ABOX);
-  uint64_t* bar_q = bars;              // [2]
-  uint64_t* bar_s = bars + 2;          // [2]
-  uint64_t* bar_p = bars + 4;          // [2]
-  uint64_t* bar_o = bars + 6;          // [2]
-  uint64_t* kv_full = bars + 8;
-  uint64_t* kv_empty = bars + 8 + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * STAGES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + STAGES * TILE);
+  uint64_t* bar_q = bars;              // [2]  Q_t landed
+  uint64_t* bar_s = bars + 2;          // [2]  S_t(j) complete                      (MMA -> softmax)
+  uint64_t* bar_p = bars + 4;          // [2]  P_t(j) stored                        (softmax -> MMA)
+  uint64_t* bar_o = bars + 6;          // [2]  last PV_t complete
+  uint64_t* bar_sfree = bars + 8;      // [2]  S_t(j) is in registers               (softmax -> MMA, SPLIT)
+  uint64_t* bar_pfree = bars + 10;     // [2]  PV_t(j) complete: P_t / O_t are free (MMA -> softmax, SPLIT)
+  uint64_t* kv_full = bars + 12;
+  uint64_t* kv_empty = bars + 12 + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12 + 2 * STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
   const int n_kv = p.n_inner;
   const bool two = q0 + 128 < p.Nq;  // the second query tile holds rows
-  const uint32_t O_COL = 256, L_COL = 256 + 2 * p.dn;
+  const uint32_t P_COL = SPLIT ? 256 : 0, P_STRIDE = SPLIT ? 64 : 128;
+  const uint32_t O_COL = SPLIT ? 384 : 256, O_STRIDE = SPLIT ? 64 : p.dn;
 
   if (threadIdx.x == 288) {
     for (int t = 0; t < 2; ++t) {
@@ -495,17 +508,14 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_init(smem_u32(&bar_s[t]), 1);
       mbar_init(smem_u32(&bar_p[t]), 128);
       mbar_init(smem_u32(&bar_o[t]), 1);
+      mbar_init(smem_u32(&bar_sfree[t]), 128);
+      mbar_init(smem_u32(&bar_pfree[t]), 1);
     }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&kv_full[s]), 1);
-      mbar_init(smem_u32(&kv_empty[s]), 1);
+      mbar_init(smem_u32(&kv_empty[s]), two ? 2 : 1);  // one commit per MMA warp
     }
     mbar_fence_init();
-  }
-  {
-    const uint4 ones = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
-    for (int i = threadIdx.x; i < ABOX / 16; i += 384) reinterpret_cast<uint4*>(sOnes)[i] = ones;
-    fence_async_smem();
   }
   if (warp == 0) tmem_alloc_rt(smem_u32(tmem_slot), 512u);
   tc_fence_before();
@@ -540,56 +550,81 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       __syncwarp();
     }
-  } else if (warp == 9) {
-    // ---------------------------------------------------------------- MMA issuer
+  } else if (warp == 9 || (warp == 10 && two)) {
+    // ---------------------------------------------------------------- MMA issuers: warp 9 -> tile 0, warp 10 -> tile 1
+    // (one issuing warp per query tile: a single warp serialising  wait, S_0', wait, PV_0, wait, S_1', wait, PV_1  was
+    // measured busy for the whole 2900-cycle iteration -- every mbarrier wake-up and issue burst of that lone warp
+    // costs 80-150 cycles more than the tensor pipe needs -- and was the bottleneck of the kernel)
+    const int t = warp - 9;
     const uint32_t idesc_s = umma_idesc_f16(128, 128, 0, 0);
     const uint32_t idesc_o = umma_idesc_f16(128, p.dn, 0, 1);  // B = V is MN-major
-    const uint32_t idesc_l = umma_idesc_f16(128, 16, 0, 1);
     const int nks = p.dn / 16;
-    const int nt = two ? 2 : 1;
     const uint32_t hi = umma_desc_hi_sw128(1024);
-    const uint32_t ones_lo = umma_desc_lo(smem_u32(sOnes), ABOX);
-    auto issue_s = [&](int t, int s) {  // S_t = Q_t K(s)^T
-      const uint32_t q_lo = umma_desc_lo(smem_u32(sQ + t * TILE), 16);
-      const uint32_t k_lo = umma_desc_lo(smem_u32(sK + s * TILE), 16);
-      for (int ks = 0; ks < nks; ++ks) {
+    const uint32_t q_lo = umma_desc_lo(smem_u32(sQ + t * TILE), 16);
+    const uint32_t k_lo0 = umma_desc_lo(smem_u32(sK), 16);       // stage 0; stage s adds s * TILE / 16
+    const uint32_t v_lo0 = umma_desc_lo(smem_u32(sV), ABOX);
+    const uint32_t s_tm = tmem + t * 128, p_tm = tmem + P_COL + t * P_STRIDE, o_tm = tmem + O_COL + t * O_STRIDE;
+    // The issue sequences are straight-line code with compile-time operand offsets (the KV loop is unrolled over the
+    // ring stages, the k-steps over their maximum with a predicate): measured with runtime loops and per-step
+    // descriptor arithmetic, this lone warp needed ~480 cycles to issue 3 MMAs + a commit.
+    auto issue_s = [&](uint32_t k_lo) {  // S_t = Q_t K^T
+#pragma unroll
+      for (int ks = 0; ks < NB * 4; ++ks) {
         const uint32_t off = ((ks >> 2) * ABOX + (ks & 3) * 32) >> 4;
-        umma_f16_ss(tmem + t * 128, umma_desc_pack(q_lo + off, hi), umma_desc_pack(k_lo + off, hi), idesc_s, ks > 0);
+        if (ks < nks) umma_f16_ss(s_tm, umma_desc_pack(q_lo + off, hi), umma_desc_pack(k_lo + off, hi), idesc_s, ks > 0);
       }
       umma_commit(smem_u32(&bar_s[t]));
     };
     mbar_wait(smem_u32(&kv_full[0]), 0);
-    for (int t = 0; t < nt; ++t) {
-      mbar_wait(smem_u32(&bar_q[t]), 0);
-      tc_fence_after();
-      if (elect_one()) issue_s(t, 0);
-      __syncwarp();
-    }
-    for (int j = 0; j < n_kv; ++j) {
-      const int s = j % STAGES;
-      const bool more = j + 1 < n_kv;
-      const int s1 = (j + 1) % STAGES;
-      const uint32_t v_lo = umma_desc_lo(smem_u32(sV + s * TILE), ABOX);
-      if (more) mbar_wait(smem_u32(&kv_full[s1]), ((j + 1) / STAGES) & 1);
-      // keys past Nk have P == 0: skip their k-steps
-      const int kvalid = min(128, p.Nk - j * 128);
-      const int nkk = (kvalid + 15) >> 4;
-      for (int t = 0; t < nt; ++t) {
+    mbar_wait(smem_u32(&bar_q[t]), 0);
+    tc_fence_after();
+    if (elect_one()) issue_s(k_lo0);
+    __syncwarp();
+    for (int j0 = 0; j0 < n_kv; j0 += STAGES) {
+#pragma unroll
+      for (int s = 0; s < STAGES; ++s) {
+        const int j = j0 + s;
+        if (j >= n_kv) break;
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int s1 = (s + 1) % STAGES;
+        const bool more = j + 1 < n_kv;
+        const uint32_t v_lo = v_lo0 + s * (TILE >> 4);
+        const uint32_t k_lo1 = k_lo0 + s1 * (TILE >> 4);
+        const uint32_t ph = (j0 / STAGES) & 1;                       // phase of ring slot s at iteration j
+        const uint32_t ph1 = s1 == 0 ? ph ^ 1 : ph;                  // ... of slot s1 at iteration j + 1
+        // keys past Nk have P == 0: skip their k-steps
+        const int kvalid = min(128, p.Nk - j * 128);
+        if (t == 0) TB_TRACE(j, 0);
+        if (more) mbar_wait(smem_u32(&kv_full[s1]), ph1);
+        if (SPLIT && more) {  // the next scores of this tile, as soon as the current ones have been read
+          mbar_wait(smem_u32(&bar_sfree[t]), j & 1);
+          tc_fence_after();
+          if (t == 0) TB_TRACE(j, 1);  // S_0(j) free
+          if (elect_one()) issue_s(k_lo1);
+          __syncwarp();
+          if (t == 0) TB_TRACE(j, 2);  // S_0(j+1) issued
+        }
         mbar_wait(smem_u32(&bar_p[t]), j & 1);
         tc_fence_after();
+        if (t == 0) TB_TRACE(j, 4);  // P_0(j) seen by the MMA warp
         if (elect_one()) {
-          const uint32_t pcol = tmem + t * 128;
-          for (int ks = 0; ks < nkk; ++ks) {
-            umma_f16_ts(tmem + O_COL + t * p.dn, pcol + ks * 8, umma_desc_pack(v_lo + ks * 128, hi), idesc_o,
-                        (j > 0) || (ks > 0));
-            umma_f16_ts(tmem + L_COL + t * 16, pcol + ks * 8, umma_desc_pack(ones_lo + ks * 128, hi), idesc_l,
-                        (j > 0) || (ks > 0));
+          if (kvalid == 128) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              umma_f16_ts(o_tm, p_tm + ks * 8, umma_desc_pack(v_lo + ks * 128, hi), idesc_o, (j > 0) || (ks > 0));
+          } else {
+            const int nkk = (kvalid + 15) >> 4;
+            for (int ks = 0; ks < nkk; ++ks)
+              umma_f16_ts(o_tm, p_tm + ks * 8, umma_desc_pack(v_lo + ks * 128, hi), idesc_o, (j > 0) || (ks > 0));
           }
-          if (more) issue_s(t, s1);
-          else umma_commit(smem_u32(&bar_o[t]));
-          if (t == nt - 1) umma_commit(smem_u32(&kv_empty[s]));
+          if (SPLIT) umma_commit(smem_u32(&bar_pfree[t]));
+          if (!SPLIT && more) issue_s(k_lo1);
+          if (!more) umma_commit(smem_u32(&bar_o[t]));
+          umma_commit(smem_u32(&kv_empty[s]));
         }
         __syncwarp();
+        if (t == 0) TB_TRACE(j, 6);  // PV_0(j) + commits issued
       }
     }
   } else if (warp < 8 && (warp < 4 || two)) {
@@ -597,17 +632,25 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int t = warp >> 2, quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-    const uint32_t s_col = lane_addr + t * 128;            // S_t, and P_t over its first 64 columns
-    const uint32_t o_col = lane_addr + O_COL + t * p.dn;
+    const uint32_t s_col = lane_addr + t * 128;
+    const uint32_t p_col = lane_addr + P_COL + t * P_STRIDE;
+    const uint32_t o_col = lane_addr + O_COL + t * O_STRIDE;
     const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2);
-    float m_run = 0.f;
+    float m_run = 0.f, l_run = 0.f;
+    if (TB_ATTN_FWD2_SKEW > 0 && t == 1) {
+      const long long t_start = clock64();
+      while (clock64() - t_start < TB_ATTN_FWD2_SKEW) {
+      }
+    }
     // one KV tile; MASKED (a compile-time flag, so the full tiles carry no per-element selects) = the last tile when
     // Nk is not a multiple of 128: columns >= limit are padding keys
     auto tile = [&](int j, auto masked_tag) {
       constexpr bool MASKED = decltype(masked_tag)::value;
       const int limit = p.Nk - j * 128;
+      TB_TRACE(j, 3);
       mbar_wait(smem_u32(&bar_s[t]), j & 1);
       tc_fence_after();
+      TB_TRACE(j, 4);
       // ---- pass 1: row maximum
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
       {
@@ -635,14 +678,19 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
       const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+      TB_TRACE(j, 5);
       if (j == 0) {
         m_run = m_tile;
       } else {
         // lazy rescale: keep the old reference maximum unless the row maximum grew by more than 2^8
         const bool need = m_tile > m_run + 8.f;
         if (__any_sync(0xffffffffu, need)) {
+          if (SPLIT) {  // PV_t(j-1) must have retired before O_t is rescaled
+            mbar_wait(smem_u32(&bar_pfree[t]), (j - 1) & 1);
+            tc_fence_after();
+          }
           const float alpha = need ? exp2f(m_run - m_tile) : 1.f;
-          // S_t(j) complete implies PV_t(j-1) complete (issue order): O_t and L_t are stable
+          // (!SPLIT: S_t(j) complete implies PV_t(j-1) complete by issue order)
           for (int c = 0; c < p.dn; c += 16) {
             uint32_t v[16];
             tmem_ld16(o_col + c, v);
@@ -651,19 +699,13 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
             tmem_st16(o_col + c, v);
           }
-          {
-            uint32_t v[16];
-            tmem_ld16(lane_addr + L_COL + t * 16, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st16(lane_addr + L_COL + t * 16, v);
-          }
+          l_run *= alpha;
         }
         if (need) m_run = m_tile;
       }
-      // ---- pass 2: P = exp2(S*c - m), packed fp16, written over the consumed score columns
+      // ---- pass 2: P = exp2(S*c - m), packed fp16
       const uint64_t negm2 = pack_f32x2(-m_run, -m_run);
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
       {
         uint32_t ra[32], rb[32];
         tmem_ld32(s_col, ra);
@@ -682,31 +724,40 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const uint64_t e = fma_f32x2(pack_f32x2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1])), sc2, negm2);
-            pk[i] = (i & 7) >= 8 - TB_ATTN_FWD2_POLY ? exp2_pair_poly(e) : exp2_pair_mufu(e);
+            float p0, p1;
+            if ((i & 7) >= 8 - TB_ATTN_FWD2_POLY) exp2_pair_poly(e, p0, p1);
+            else exp2_pair_mufu(e, p0, p1);
+            if (i & 1) { l2 += p0; l3 += p1; } else { l0 += p0; l1 += p1; }
+            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pk[i]) : "f"(p1), "f"(p0));
           }
-          // chunk c+1 (columns 32c+32 ..) is already in flight: P columns [16c, 16c+16) only cover consumed scores
           if (c < 3) tmem_ld_wait32(nxt);
-          tmem_st16(s_col + c * 16, pk);
+          if (SPLIT && c == 2) {  // the last chunk of S_t(j) is in registers: the next scores may overwrite it
+            tc_fence_before();
+            mbar_arrive(smem_u32(&bar_sfree[t]));
+          }
+          if (SPLIT && c == 0 && j > 0) {  // PV_t(j-1) has retired: P_t may be overwritten (waited for as late as
+            mbar_wait(smem_u32(&bar_pfree[t]), (j - 1) & 1);  // possible: a quarter of the exp pass is done by now)
+            tc_fence_after();
+          }
+          // !SPLIT: chunk c+1 (columns 32c+32 ..) is already in registers: P columns [16c, 16c+16) only cover
+          // consumed scores
+          tmem_st16(p_col + c * 16, pk);
         }
       }
+      l_run += (l0 + l1) + (l2 + l3);
+      TB_TRACE(j, 6);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(smem_u32(&bar_p[t]));
+      TB_TRACE(j, 7);
     };
     const int n_full = p.Nk / 128;  // tiles without padding keys
     for (int j = 0; j < n_full; ++j) tile(j, std::false_type{});
     if (n_full < n_kv) tile(n_full, std::true_type{});
-    // ---- epilogue: O / L
+    // ---- epilogue: O / l
     mbar_wait(smem_u32(&bar_o[t]), 0);
     tc_fence_after();
-    float l;
-    {
-      uint32_t v[8];
-      tmem_ld8(lane_addr + L_COL + t * 16, v);
-      tmem_ld_wait();
-      l = __uint_as_float(v[0]);
-    }
-    const float inv_l = 1.f / l;
+    const float inv_l = 1.f / l_run;
     const int q = q0 + t * 128 + row;
     const bool ok = q < p.Nq;
     __half* op = p.O + ((long long)b * p.Nq + q) * p.ldo + h * p.d;
@@ -728,7 +779,298 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
     }
-    if (ok && p.lse) p.lse[((long long)b * p.heads + h) * p.Nq + q] = m_run + log2f(l);
+    if (ok && p.lse) p.lse[((long long)b * p.heads + h) * p.Nq + q] = m_run + log2f(l_run);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc_rt(tmem, 512u);
+}
+
+// ------------------------------------------------------------------------------------ forward, v2 with two threads per row
+// Same schedule as attn_fwd2_kernel (two query tiles per CTA, P in its own TMEM columns and S_t(j+1) issued as soon
+// as S_t(j) has been read when head_dim <= 64, one MMA-issuing warp per tile), but SIXTEEN softmax warps: warp w ->
+// tile w >> 3, TMEM lane quarter w & 3, column half (w >> 2) & 1, i.e. two threads per row with 64 scores each.
+// ncu on the one-thread-per-row kernel (profiles/r02_*): issue slots 51 % busy, XU 51 %, no pipe saturated -- two
+// warps per scheduler cannot cover the fixed-latency ("wait" 29 %), MUFU-result and MIO stalls of this instruction
+// stream.  Four warps per scheduler can; the price is the exchange of the two half-row maxima through shared
+// memory, synchronised by a 64-thread named barrier PER WARP PAIR (not per tile), and a single pass over the scores
+// (64 registers) instead of two.
+template <int NB, int STAGES>
+__global__ void __launch_bounds__(640, 1)
+attn_fwd2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  constexpr int TILE = NB * ABOX;
+  constexpr bool SPLIT = NB == 1;  // P in its own TMEM columns
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;                  // two query tiles
+  uint8_t* sK = sQ + 2 * TILE;
+  uint8_t* sV = sK + STAGES * TILE;
+  float* sX = reinterpret_cast<float*>(sV + STAGES * TILE);  // [2 parities][2 tiles][2 halves][128] half-row maxima / sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sX + 2 * 2 * 2 * 128);
+  uint64_t* bar_q = bars;              // [2]  Q_t landed
+  uint64_t* bar_s = bars + 2;          // [2]  S_t(j) complete                      (MMA -> softmax)
+  uint64_t* bar_p = bars + 4;          // [2]  P_t(j) stored                        (softmax -> MMA)
+  uint64_t* bar_o = bars + 6;          // [2]  last PV_t complete
+  uint64_t* bar_sfree = bars + 8;      // [2]  S_t(j) is in registers               (softmax -> MMA, SPLIT)
+  uint64_t* bar_pfree = bars + 10;     // [2]  PV_t(j) complete: P_t / O_t are free (MMA -> softmax, SPLIT)
+  uint64_t* kv_full = bars + 12;
+  uint64_t* kv_empty = bars + 12 + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12 + 2 * STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+  const int n_kv = p.n_inner;
+  const bool two = q0 + 128 < p.Nq;  // the second query tile holds rows
+  const uint32_t P_COL = SPLIT ? 256 : 0, P_STRIDE = SPLIT ? 64 : 128;
+  const uint32_t O_COL = SPLIT ? 384 : 256, O_STRIDE = SPLIT ? 64 : p.dn;
+
+  if (threadIdx.x == 512) {
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(smem_u32(&bar_q[t]), 1);
+      mbar_init(smem_u32(&bar_s[t]), 1);
+      mbar_init(smem_u32(&bar_p[t]), 256);
+      mbar_init(smem_u32(&bar_o[t]), 1);
+      mbar_init(smem_u32(&bar_sfree[t]), 256);
+      mbar_init(smem_u32(&bar_pfree[t]), 1);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&kv_full[s]), 1);
+      mbar_init(smem_u32(&kv_empty[s]), two ? 2 : 1);  // one commit per MMA warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc_rt(smem_u32(tmem_slot), 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 16) {
+    // ---------------------------------------------------------------- TMA producer
+    if (elect_one()) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmK);
+      tma_prefetch_desc(&tmV);
+      for (int t = 0; t < (two ? 2 : 1); ++t) {
+        mbar_expect_tx(smem_u32(&bar_q[t]), TILE);
+        for (int x = 0; x < NB; ++x)
+          tma_load_4d(smem_u32(sQ + t * TILE + x * ABOX), &tmQ, smem_u32(&bar_q[t]), x * 64, h, q0 + t * 128, b);
+      }
+    }
+    __syncwarp();
+    for (int j = 0; j < n_kv; ++j) {
+      const int s = j % STAGES;
+      const uint32_t ph = (j / STAGES) & 1;
+      mbar_wait(smem_u32(&kv_empty[s]), ph ^ 1);
+      if (elect_one()) {
+        const uint32_t fb = smem_u32(&kv_full[s]);
+        mbar_expect_tx(fb, 2 * TILE);
+        for (int x = 0; x < NB; ++x) {
+          tma_load_4d(smem_u32(sK + s * TILE + x * ABOX), &tmK, fb, x * 64, h, j * 128, b);
+          tma_load_4d(smem_u32(sV + s * TILE + x * ABOX), &tmV, fb, x * 64, h, j * 128, b);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 17 || (warp == 18 && two)) {
+    // ---------------------------------------------------------------- MMA issuers: warp 17 -> tile 0, warp 18 -> tile 1
+    const int t = warp - 17;
+    const uint32_t idesc_s = umma_idesc_f16(128, 128, 0, 0);
+    const uint32_t idesc_o = umma_idesc_f16(128, p.dn, 0, 1);  // B = V is MN-major
+    const int nks = p.dn / 16;
+    const uint32_t hi = umma_desc_hi_sw128(1024);
+    const uint32_t q_lo = umma_desc_lo(smem_u32(sQ + t * TILE), 16);
+    const uint32_t k_lo0 = umma_desc_lo(smem_u32(sK), 16);       // stage 0; stage s adds s * TILE / 16
+    const uint32_t v_lo0 = umma_desc_lo(smem_u32(sV), ABOX);
+    const uint32_t s_tm = tmem + t * 128, p_tm = tmem + P_COL + t * P_STRIDE, o_tm = tmem + O_COL + t * O_STRIDE;
+    auto issue_s = [&](uint32_t k_lo) {  // S_t = Q_t K^T
+#pragma unroll
+      for (int ks = 0; ks < NB * 4; ++ks) {
+        const uint32_t off = ((ks >> 2) * ABOX + (ks & 3) * 32) >> 4;
+        if (ks < nks) umma_f16_ss(s_tm, umma_desc_pack(q_lo + off, hi), umma_desc_pack(k_lo + off, hi), idesc_s, ks > 0);
+      }
+      umma_commit(smem_u32(&bar_s[t]));
+    };
+    mbar_wait(smem_u32(&kv_full[0]), 0);
+    mbar_wait(smem_u32(&bar_q[t]), 0);
+    tc_fence_after();
+    if (elect_one()) issue_s(k_lo0);
+    __syncwarp();
+    for (int j0 = 0; j0 < n_kv; j0 += STAGES) {
+#pragma unroll
+      for (int s = 0; s < STAGES; ++s) {
+        const int j = j0 + s;
+        if (j >= n_kv) break;
+        const int s1 = (s + 1) % STAGES;
+        const bool more = j + 1 < n_kv;
+        const uint32_t v_lo = v_lo0 + s * (TILE >> 4);
+        const uint32_t k_lo1 = k_lo0 + s1 * (TILE >> 4);
+        const uint32_t ph = (j0 / STAGES) & 1;                       // phase of ring slot s at iteration j
+        const uint32_t ph1 = s1 == 0 ? ph ^ 1 : ph;                  // ... of slot s1 at iteration j + 1
+        const int kvalid = min(128, p.Nk - j * 128);                 // keys past Nk have P == 0: skip their k-steps
+        if (more) mbar_wait(smem_u32(&kv_full[s1]), ph1);
+        if (SPLIT && more) {  // the next scores of this tile, as soon as the current ones have been read
+          mbar_wait(smem_u32(&bar_sfree[t]), j & 1);
+          tc_fence_after();
+          if (elect_one()) issue_s(k_lo1);
+          __syncwarp();
+        }
+        mbar_wait(smem_u32(&bar_p[t]), j & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          if (kvalid == 128) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              umma_f16_ts(o_tm, p_tm + ks * 8, umma_desc_pack(v_lo + ks * 128, hi), idesc_o, (j > 0) || (ks > 0));
+          } else {
+            const int nkk = (kvalid + 15) >> 4;
+            for (int ks = 0; ks < nkk; ++ks)
+              umma_f16_ts(o_tm, p_tm + ks * 8, umma_desc_pack(v_lo + ks * 128, hi), idesc_o, (j > 0) || (ks > 0));
+          }
+          if (SPLIT) umma_commit(smem_u32(&bar_pfree[t]));
+          if (!SPLIT && more) issue_s(k_lo1);
+          if (!more) umma_commit(smem_u32(&bar_o[t]));
+          umma_commit(smem_u32(&kv_empty[s]));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 16 && (warp < 8 || two)) {
+    // ---------------------------------------------------------------- softmax warps: two threads per query row
+    const int t = warp >> 3, quarter = warp & 3, half = (warp >> 2) & 1;
+    const int row = quarter * 32 + lane;
+    const int pair_bar = 1 + t * 4 + quarter;  // named barrier of the two warps that share these 32 rows
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t s_col = lane_addr + t * 128 + half * 64;
+    const uint32_t p_col = lane_addr + P_COL + t * P_STRIDE + half * 32;
+    const uint32_t o_col = lane_addr + O_COL + t * O_STRIDE;
+    const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2);
+    float m_run = 0.f, l_run = 0.f;  // l_run: this thread's 64 columns only
+    auto tile = [&](int j, auto masked_tag) {
+      constexpr bool MASKED = decltype(masked_tag)::value;
+      const int limit = p.Nk - j * 128 - half * 64;  // this thread's columns >= limit are padding keys
+      float* xmine = sX + (((j & 1) * 2 + t) * 2 + half) * 128 + row;
+      const float* xother = sX + (((j & 1) * 2 + t) * 2 + (half ^ 1)) * 128 + row;
+      mbar_wait(smem_u32(&bar_s[t]), j & 1);
+      tc_fence_after();
+      uint32_t r[64];
+      tmem_ld32(s_col, r);
+      tmem_ld32(s_col + 32, r + 32);
+      tmem_ld_wait();
+      if (SPLIT) {  // S_t(j) is in registers: the next scores may overwrite it
+        tc_fence_before();
+        mbar_arrive(smem_u32(&bar_sfree[t]));
+      }
+      if (MASKED) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i >= limit) r[i] = 0xff800000u;
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 64; i += 8) {
+        mx0 = fmax3(mx0, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+        mx2 = fmax3(mx2, __uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
+        mx3 = fmax3(mx3, __uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
+      }
+      float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      *xmine = mx;
+      named_bar_sync(pair_bar, 64);  // (!SPLIT: both halves of these rows hold their scores: P may overwrite S)
+      mx = fmaxf(mx, *xother);
+      const float m_tile = mx * p.scale_log2;
+      if (j == 0) {
+        m_run = m_tile;
+      } else {
+        // lazy rescale: keep the old reference maximum unless the row maximum grew by more than 2^8
+        const bool need = m_tile > m_run + 8.f;
+        if (__any_sync(0xffffffffu, need)) {
+          if (SPLIT) {  // PV_t(j-1) must have retired before O_t is rescaled
+            mbar_wait(smem_u32(&bar_pfree[t]), (j - 1) & 1);
+            tc_fence_after();
+          }
+          const float alpha = need ? exp2f(m_run - m_tile) : 1.f;
+          // (!SPLIT: S_t(j) complete implies PV_t(j-1) complete by issue order.)  The halves alternate 16-column chunks.
+          for (int c = half * 16; c < p.dn; c += 32) {
+            uint32_t v[16];
+            tmem_ld16(o_col + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st16(o_col + c, v);
+          }
+          l_run *= alpha;
+        }
+        if (need) m_run = m_tile;
+      }
+      // ---- P = exp2(S*c - m), packed fp16
+      const uint64_t negm2 = pack_f32x2(-m_run, -m_run);
+      uint64_t la = pack_f32x2(0.f, 0.f), lb = pack_f32x2(0.f, 0.f);
+      uint32_t pk[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const uint64_t e = fma_f32x2(pack_f32x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sc2, negm2);
+        float p0, p1;
+        if ((i & 7) >= 8 - TB_ATTN_FWD2_POLY) exp2_pair_poly(e, p0, p1);
+        else exp2_pair_mufu(e, p0, p1);
+        if (i & 1) lb = add_f32x2(lb, pack_f32x2(p0, p1));
+        else la = add_f32x2(la, pack_f32x2(p0, p1));
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pk[i]) : "f"(p1), "f"(p0));
+      }
+      {
+        float a0, a1, b0, b1;
+        unpack_f32x2(la, a0, a1);
+        unpack_f32x2(lb, b0, b1);
+        l_run += (a0 + a1) + (b0 + b1);
+      }
+      if (SPLIT && j > 0) {  // PV_t(j-1) has retired: P_t may be overwritten
+        mbar_wait(smem_u32(&bar_pfree[t]), (j - 1) & 1);
+        tc_fence_after();
+      }
+      tmem_st32(p_col, pk);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bar_p[t]));
+    };
+    const int n_full = p.Nk / 128;  // tiles without padding keys
+    for (int j = 0; j < n_full; ++j) tile(j, std::false_type{});
+    if (n_full < n_kv) tile(n_full, std::true_type{});
+    // ---- epilogue: O / l
+    {
+      float* xmine = sX + (((n_kv & 1) * 2 + t) * 2 + half) * 128 + row;
+      const float* xother = sX + (((n_kv & 1) * 2 + t) * 2 + (half ^ 1)) * 128 + row;
+      *xmine = l_run;
+      named_bar_sync(pair_bar, 64);
+      l_run += *xother;
+    }
+    mbar_wait(smem_u32(&bar_o[t]), 0);
+    tc_fence_after();
+    const float inv_l = 1.f / l_run;
+    const int q = q0 + t * 128 + row;
+    const bool ok = q < p.Nq;
+    __half* op = p.O + ((long long)b * p.Nq + q) * p.ldo + h * p.d;
+    for (int c = half * 16; c < p.dn; c += 32) {
+      uint32_t v[16];
+      tmem_ld16(o_col + c, v);
+      tmem_ld_wait();
+      if (ok) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (c + g * 8 < p.d) {
+            uint4 o;
+            o.x = pack_half2(__uint_as_float(v[g * 8 + 0]) * inv_l, __uint_as_float(v[g * 8 + 1]) * inv_l);
+            o.y = pack_half2(__uint_as_float(v[g * 8 + 2]) * inv_l, __uint_as_float(v[g * 8 + 3]) * inv_l);
+            o.z = pack_half2(__uint_as_float(v[g * 8 + 4]) * inv_l, __uint_as_float(v[g * 8 + 5]) * inv_l);
+            o.w = pack_half2(__uint_as_float(v[g * 8 + 6]) * inv_l, __uint_as_float(v[g * 8 + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(op + c + g * 8) = o;
+          }
+        }
+      }
+    }
+    if (ok && half == 0 && p.lse) p.lse[((long long)b * p.heads + h) * p.Nq + q] = m_run + log2f(l_run);
   }
 
   tc_fence_before();
@@ -1596,7 +1938,7 @@ static int launch_attn_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const C
 template <int NB, int STAGES>
 static int launch_attn_fwd2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                             const AttnParams& p, int B, cudaStream_t st) {
-  constexpr int smem = NB * ABOX * (2 + 2 * STAGES) + ABOX + 256 + 1024;
+  constexpr int smem = NB * ABOX * (2 + 2 * STAGES) + 512 + 1024;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd2_kernel<NB, STAGES>,
@@ -1610,6 +1952,25 @@ static int launch_attn_fwd2(const CUtensorMap& tq, const CUtensorMap& tk, const 
   dim3 grid((p.Nq + 255) / 256, p.heads, B);
   attn_fwd2_kernel<NB, STAGES><<<grid, 384, smem, st>>>(tq, tk, tv, p);
   return check_launch("attn_fwd2_kernel");
+}
+
+template <int NB, int STAGES>
+static int launch_attn_fwd2h(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                             const AttnParams& p, int B, cudaStream_t st) {
+  constexpr int smem = NB * ABOX * (2 + 2 * STAGES) + 4096 + 512 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd2h_kernel<NB, STAGES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(attn_fwd2h<%d,%d>, %d): %s", NB, STAGES, smem, cudaGetErrorString(e));
+      return TB_E_CUDA;
+    }
+    configured = true;
+  }
+  dim3 grid((p.Nq + 255) / 256, p.heads, B);
+  attn_fwd2h_kernel<NB, STAGES><<<grid, 640, smem, st>>>(tq, tk, tv, p);
+  return check_launch("attn_fwd2h_kernel");
 }
 
 static int launch_attn_bwd2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
@@ -1684,9 +2045,14 @@ extern "C" int tb_attn_fwd_f16(const void* q, int64_t ldq, const void* k, int64_
   cudaStream_t st = (cudaStream_t)stream;
   // long non-causal sequences: the two-query-tile ping-pong kernel (one CTA per SM)
   static const bool v1 = getenv("TB_ATTN_FWD_V1") != nullptr;  // diagnostic switch: the two-CTA-per-SM kernel
-  if (!v1 && !causal && p.dn <= 112 && Nq >= 256 && Nk >= 256) {
-    if (nb == 1) return launch_attn_fwd2<1, 3>(tq, tk, tv, p, B, st);
-    return launch_attn_fwd2<2, 2>(tq, tk, tv, p, B, st);
+  if (!v1 && !causal && p.dn <= 128 && Nq >= 256 && Nk >= 256) {
+    static const bool one_thread = getenv("TB_ATTN_FWD2_ONE_THREAD_PER_ROW") != nullptr;  // diagnostic switch
+    if (one_thread) {
+      if (nb == 1) return launch_attn_fwd2<1, 4>(tq, tk, tv, p, B, st);
+      return launch_attn_fwd2<2, 2>(tq, tk, tv, p, B, st);
+    }
+    if (nb == 1) return launch_attn_fwd2h<1, 4>(tq, tk, tv, p, B, st);
+    return launch_attn_fwd2h<2, 2>(tq, tk, tv, p, B, st);
   }
   if (nb == 1) return launch_attn_fwd<1, 2>(tq, tk, tv, p, B, st);
   if (nb == 2) return launch_attn_fwd<2, 1>(tq, tk, tv, p, B, st);
