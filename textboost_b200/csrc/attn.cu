@@ -796,8 +796,17 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 // stream.  Four warps per scheduler can; the price is the exchange of the two half-row maxima through shared
 // memory, synchronised by a 64-thread named barrier PER WARP PAIR (not per tile), and a single pass over the scores
 // (64 registers) instead of two.
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 template <int NB, int STAGES>
-__global__ void __launch_bounds__(640, 1)
+__global__ void __launch_bounds__(608, 1)
 attn_fwd2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   constexpr int TILE = NB * ABOX;
@@ -949,11 +958,12 @@ attn_fwd2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const uint32_t o_col = lane_addr + O_COL + t * O_STRIDE;
     const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2);
     float m_run = 0.f, l_run = 0.f;  // l_run: this thread's 64 columns only
+    const uint32_t sx_base = smem_u32(sX);
     auto tile = [&](int j, auto masked_tag) {
       constexpr bool MASKED = decltype(masked_tag)::value;
       const int limit = p.Nk - j * 128 - half * 64;  // this thread's columns >= limit are padding keys
-      float* xmine = sX + (((j & 1) * 2 + t) * 2 + half) * 128 + row;
-      const float* xother = sX + (((j & 1) * 2 + t) * 2 + (half ^ 1)) * 128 + row;
+      const uint32_t xmine = sx_base + ((((j & 1) * 2 + t) * 2 + half) * 128 + row) * 4;
+      const uint32_t xother = sx_base + ((((j & 1) * 2 + t) * 2 + (half ^ 1)) * 128 + row) * 4;
       mbar_wait(smem_u32(&bar_s[t]), j & 1);
       tc_fence_after();
       uint32_t r[64];
@@ -978,9 +988,9 @@ attn_fwd2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         mx3 = fmax3(mx3, __uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
       }
       float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      *xmine = mx;
+      st_shared_f32(xmine, mx);
       named_bar_sync(pair_bar, 64);  // (!SPLIT: both halves of these rows hold their scores: P may overwrite S)
-      mx = fmaxf(mx, *xother);
+      mx = fmaxf(mx, ld_shared_f32(xother));
       const float m_tile = mx * p.scale_log2;
       if (j == 0) {
         m_run = m_tile;
@@ -1040,11 +1050,11 @@ attn_fwd2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     if (n_full < n_kv) tile(n_full, std::true_type{});
     // ---- epilogue: O / l
     {
-      float* xmine = sX + (((n_kv & 1) * 2 + t) * 2 + half) * 128 + row;
-      const float* xother = sX + (((n_kv & 1) * 2 + t) * 2 + (half ^ 1)) * 128 + row;
-      *xmine = l_run;
+      const uint32_t xmine = sx_base + ((((n_kv & 1) * 2 + t) * 2 + half) * 128 + row) * 4;
+      const uint32_t xother = sx_base + ((((n_kv & 1) * 2 + t) * 2 + (half ^ 1)) * 128 + row) * 4;
+      st_shared_f32(xmine, l_run);
       named_bar_sync(pair_bar, 64);
-      l_run += *xother;
+      l_run += ld_shared_f32(xother);
     }
     mbar_wait(smem_u32(&bar_o[t]), 0);
     tc_fence_after();
@@ -1969,7 +1979,7 @@ static int launch_attn_fwd2h(const CUtensorMap& tq, const CUtensorMap& tk, const
     configured = true;
   }
   dim3 grid((p.Nq + 255) / 256, p.heads, B);
-  attn_fwd2h_kernel<NB, STAGES><<<grid, 640, smem, st>>>(tq, tk, tv, p);
+  attn_fwd2h_kernel<NB, STAGES><<<grid, 608, smem, st>>>(tq, tk, tv, p);
   return check_launch("attn_fwd2h_kernel");
 }
 
