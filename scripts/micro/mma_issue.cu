@@ -10,7 +10,7 @@ __device__ __forceinline__ uint64_t desc_pack(uint32_t lo, uint32_t hi) {
   return d;
 }
 
-template <int NMMA, int N, bool TS>
+template <int NMMA, int N, bool TS, int AMN = 0>
 __global__ void __launch_bounds__(128) k(long long* out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -23,9 +23,9 @@ __global__ void __launch_bounds__(128) k(long long* out) {
   tc_fence_before(); __syncthreads(); tc_fence_after();
   const uint32_t tmem = slot;
   if (threadIdx.x < 32) {
-    constexpr uint32_t idesc = umma_idesc_f16(128, N, 0, TS ? 1 : 0);
+    constexpr uint32_t idesc = umma_idesc_f16(128, N, AMN, (TS || AMN) ? 1 : 0);
     const uint32_t a = smem_u32(smem), b = smem_u32(smem + 32768);
-    const uint64_t da = umma_desc_sw128(a, 16, 1024), db = umma_desc_sw128(b, TS ? 16384 : 16, 1024);
+    const uint64_t da = umma_desc_sw128(a, AMN ? 16384 : 16, 1024), db = umma_desc_sw128(b, (TS || AMN) ? 16384 : 16, 1024);
     const uint32_t alo = (uint32_t)da, blo = (uint32_t)db, hi = (uint32_t)(da >> 32);
     for (int rep = 0; rep < 3; ++rep) {
       long long t0 = clock64();
@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(128) k(long long* out) {
 #pragma unroll
         for (int i = 0; i < NMMA; ++i) {
           if (TS) umma_f16_ts(tmem + 256, tmem + (i & 7) * 8, desc_pack(blo + (i & 7) * 128, hi), idesc, i > 0);
+          else if (AMN) umma_f16_ss(tmem + 256, desc_pack(alo + (i & 7) * 128, hi), desc_pack(blo + (i & 7) * 128, hi), idesc, i > 0);
           else umma_f16_ss(tmem + 256, desc_pack(alo + (i & 3) * 2, hi), desc_pack(blo + (i & 3) * 2, hi), idesc, i > 0);
         }
       }
@@ -49,10 +50,11 @@ __global__ void __launch_bounds__(128) k(long long* out) {
   if (threadIdx.x < 32) tmem_dealloc<512>(tmem);
 }
 
-template <int NMMA, int N, bool TS>
+template <int NMMA, int N, bool TS, int AMN = 0>
 void run(long long* d) {
-  cudaFuncSetAttribute(k<NMMA, N, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 70000);
-  k<NMMA, N, TS><<<1, 128, 70000>>>(d);
+  cudaFuncSetAttribute(k<NMMA, N, TS, AMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 70000);
+  k<NMMA, N, TS, AMN><<<1, 128, 70000>>>(d);
+  if (AMN) printf("[A MN-major, B MN-major] ");
   long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
   cudaError_t e = cudaGetLastError();
   printf("%s N=%3d n_mma=%2d: issue %5lld cyc (%.1f/mma), retire %5lld cyc (%.1f/mma) %s\n", TS ? "TS" : "SS", N, NMMA, h[0],
@@ -66,5 +68,6 @@ int main() {
   run<8, 48, true>(d); run<16, 48, true>(d); run<32, 48, true>(d); run<16, 64, true>(d); run<16, 16, true>(d);
   run<32, 16, true>(d); run<32, 32, true>(d); run<32, 64, true>(d); run<32, 80, true>(d); run<32, 96, true>(d); run<32, 128, true>(d);
   run<32, 64, false>(d); run<32, 32, false>(d);
+  run<32, 48, false, 1>(d); run<32, 64, false, 1>(d); run<32, 128, false, 1>(d);
   return 0;
 }

@@ -66,6 +66,11 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int chunk16) {
   if (p.trace && lane == 0 && (j) < 16 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)    \
   p.trace[((j) * 8 + (e)) * 10 + warp] = clock64()
 
+// the same for the 19-warp backward kernel: [iter][event][warp] with 20 warp slots
+#define TB_TRACE3(j, e)                                                                             \
+  if (p.trace && lane == 0 && (j) < 16 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)    \
+  p.trace[((j) * 8 + (e)) * 20 + warp] = clock64()
+
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float r;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -1894,6 +1899,439 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == 0) tmem_dealloc_rt(tmem, 512u);
 }
 
+// ------------------------------------------------------------------------------------ backward, v3
+// head_dim <= 64, non-causal (every UNet attention at 64x64 / 96x96, and the cross attentions).  Same loop as
+// attn_bwd2_kernel -- one CTA per SM owns a 128-key KV tile of one (b, h), walks the query tiles, keeps dK / dV in
+// TMEM and reduce-adds dQ tile by tile -- but with the lessons of the forward rewrite (profiles/r02_*):
+//   * scores are computed as S = Q_i K^T / dP = dO_i V^T (rows = queries), not transposed: a thread owns a query row,
+//     so the row's log-sum-exp L and delta are two REGISTERS per pair instead of 16 shared-memory vector loads per
+//     thread per pair, and scale-and-subtract is one packed FFMA2 per two scores with broadcast scalars;
+//     P and dS go to shared memory as [q][kv] tiles, read by the dV / dK MMAs as MN-major A operands (P^T, dS^T)
+//     and by the dQ MMA as a K-major one;
+//   * TWO MMA-issuing warps: one for the score MMAs (S, dP: they feed the softmax warps), one for the gradient MMAs
+//     (dV, dK, dQ: they consume P and dS).  A single issuing warp pays ~100 cycles per mbarrier wake-up and per issue
+//     burst and was the bottleneck of the forward kernel at 22 MMAs per iteration; a pair here is 30;
+//   * no CTA-wide named barrier in the loop: the dQ tile leaves per 32-row slab (the four warps of a TMEM lane
+//     quarter: 128-thread barrier, one TMA reduce-add each);
+//   * all shared-memory traffic of the softmax warps is explicit st.shared (the generic stores of v2 resolved the
+//     address space at run time).
+// TMEM: S [0,128)  dP [128,256)  dQ [256,320)  dV [320,384)  dK [384,448).
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4f(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t hmul2_sub(uint32_t pp, uint64_t dp2, uint64_t delta2) {
+  // P (packed fp16 pair) * (dP - delta) (fp32 pair, rounded to fp16)
+  float a, b;
+  unpack_f32x2(sub_f32x2(dp2, delta2), a, b);
+  uint32_t h;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));
+  return hmul2_u32(pp, h);
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(608, 1)
+attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                 const __grid_constant__ CUtensorMap tmDQ, const AttnParams p) {
+  constexpr int TILE = ABOX;
+  constexpr uint32_t S_COL = 0, DP_COL = 128, DQ_COL = 256, DV_COL = 320, DK_COL = 384;
+  constexpr int NSM = 512;  // softmax threads
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + TILE;
+  uint8_t* sQ = sV + TILE;
+  uint8_t* sdO = sQ + STAGES * TILE;
+  uint8_t* sP = sdO + STAGES * TILE;   // P   [128 q x 128 kv] fp16, two swizzled 64-column boxes
+  uint8_t* sDS = sP + 2 * ABOX;        // dS, same layout
+  float* sDQ = reinterpret_cast<float*>(sDS + 2 * ABOX);  // 2 KB per softmax warp: fp32 staging of the dQ reduce-adds
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDQ + 128 * 64);
+  uint64_t* bar_kv = bars;
+  uint64_t* bar_s = bars + 1;       // S(i) complete                           (MMA-A -> softmax)
+  uint64_t* bar_sfree = bars + 2;   // S(i) is in registers                    (softmax -> MMA-A)
+  uint64_t* bar_p = bars + 3;       // P(i) in shared memory                   (softmax -> MMA-B)
+  uint64_t* bar_dv = bars + 4;      // dV(i) has read P(i)                     (MMA-B -> softmax)
+  uint64_t* bar_dp = bars + 5;      // dP(i) complete                          (MMA-A -> softmax)
+  uint64_t* bar_dpfree = bars + 6;  // dP(i) is in registers                   (softmax -> MMA-A)
+  uint64_t* bar_ds = bars + 7;      // dS(i) in shared memory                  (softmax -> MMA-B)
+  uint64_t* bar_dq = bars + 8;      // dK(i), dQ(i) complete: dS(i) read       (MMA-B -> softmax)
+  uint64_t* bar_dqfree = bars + 9;  // dQ(i) drained                           (softmax -> MMA-B)
+  uint64_t* q_full = bars + 10;
+  uint64_t* q_empty = bars + 10 + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kv0 = (blockIdx.x / p.qsplit) * 128, h = blockIdx.y, b = blockIdx.z;
+  const int qs = blockIdx.x % p.qsplit;
+  const int q_per = (p.n_inner + p.qsplit - 1) / p.qsplit;
+  const int i_begin = qs * q_per;
+  const int i_end = min(p.n_inner, i_begin + q_per);
+  const int n_it = i_end - i_begin;
+
+  if (threadIdx.x == NSM) {
+    mbar_init(smem_u32(bar_kv), 1);
+    mbar_init(smem_u32(bar_s), 1);
+    mbar_init(smem_u32(bar_sfree), NSM);
+    mbar_init(smem_u32(bar_p), NSM);
+    mbar_init(smem_u32(bar_dv), 1);
+    mbar_init(smem_u32(bar_dp), 1);
+    mbar_init(smem_u32(bar_dpfree), NSM);
+    mbar_init(smem_u32(bar_ds), NSM);
+    mbar_init(smem_u32(bar_dq), 1);
+    mbar_init(smem_u32(bar_dqfree), NSM);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&q_full[s]), 1);
+      mbar_init(smem_u32(&q_empty[s]), 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc_rt(smem_u32(tmem_slot), 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t hi = umma_desc_hi_sw128(1024);
+  const int nks = p.dn / 16;
+
+  if (n_it <= 0) {
+    // (an empty q split: nothing to add to dK / dV / dQ)
+  } else if (warp == 16) {
+    // ---------------------------------------------------------------- TMA producer
+    if (elect_one()) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmK);
+      tma_prefetch_desc(&tmV);
+      tma_prefetch_desc(&tmdO);
+      mbar_expect_tx(smem_u32(bar_kv), 2 * TILE);
+      tma_load_4d(smem_u32(sK), &tmK, smem_u32(bar_kv), 0, h, kv0, b);
+      tma_load_4d(smem_u32(sV), &tmV, smem_u32(bar_kv), 0, h, kv0, b);
+    }
+    __syncwarp();
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(smem_u32(&q_empty[s]), ph ^ 1);
+      if (elect_one()) {
+        const uint32_t fb = smem_u32(&q_full[s]);
+        mbar_expect_tx(fb, 2 * TILE);
+        tma_load_4d(smem_u32(sQ + s * TILE), &tmQ, fb, 0, h, (i_begin + it) * 128, b);
+        tma_load_4d(smem_u32(sdO + s * TILE), &tmdO, fb, 0, h, (i_begin + it) * 128, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 17) {
+    // ---------------------------------------------------------------- MMA-A: S = Q_i K^T, dP = dO_i V^T
+    const uint32_t idesc_kk = umma_idesc_f16(128, 128, 0, 0);  // both operands K-major
+    const uint32_t k_lo = umma_desc_lo(smem_u32(sK), 16), v_lo = umma_desc_lo(smem_u32(sV), 16);
+    const uint32_t q_lo0 = umma_desc_lo(smem_u32(sQ), 16), do_lo0 = umma_desc_lo(smem_u32(sdO), 16);
+    auto issue = [&](uint32_t d_tm, uint32_t a_lo, uint32_t b_lo, uint64_t* bar) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        if (ks < nks) umma_f16_ss(d_tm, umma_desc_pack(a_lo + ks * 2, hi), umma_desc_pack(b_lo + ks * 2, hi), idesc_kk, ks > 0);
+      umma_commit(smem_u32(bar));
+    };
+    mbar_wait(smem_u32(bar_kv), 0);
+    mbar_wait(smem_u32(&q_full[0]), 0);
+    tc_fence_after();
+    if (elect_one()) {
+      issue(tmem + S_COL, q_lo0, k_lo, bar_s);
+      issue(tmem + DP_COL, do_lo0, v_lo, bar_dp);
+    }
+    __syncwarp();
+    for (int it0 = 0; it0 + 1 < n_it; it0 += STAGES) {
+#pragma unroll
+      for (int s = 0; s < STAGES; ++s) {
+        const int it = it0 + s;
+        if (it + 1 >= n_it) break;
+        const int s1 = (s + 1) % STAGES;
+        const uint32_t ph1 = ((it + 1) / STAGES) & 1;
+        const uint32_t par = it & 1;
+        mbar_wait(smem_u32(&q_full[s1]), ph1);
+        TB_TRACE3(it, 0);
+        mbar_wait(smem_u32(bar_sfree), par);  // S(it) has been read: the next scores may overwrite it
+        tc_fence_after();
+        TB_TRACE3(it, 1);
+        if (elect_one()) issue(tmem + S_COL, q_lo0 + s1 * (TILE >> 4), k_lo, bar_s);
+        __syncwarp();
+        TB_TRACE3(it, 2);
+        mbar_wait(smem_u32(bar_dpfree), par);
+        tc_fence_after();
+        TB_TRACE3(it, 3);
+        if (elect_one()) issue(tmem + DP_COL, do_lo0 + s1 * (TILE >> 4), v_lo, bar_dp);
+        __syncwarp();
+        TB_TRACE3(it, 4);
+      }
+    }
+  } else if (warp == 18) {
+    // ---------------------------------------------------------------- MMA-B: dV += P^T dO, dK += dS^T Q, dQ = dS K
+    // The softmax warps publish dS(i) and P(i+1) together, so per pair this warp issues dK(i), dQ(i), dV(i+1) back to
+    // back (24 MMAs) after one pair of waits.
+    const uint32_t idesc_acc = umma_idesc_f16(128, p.dn, 1, 1);  // A = P / dS read MN-major (transposed), B MN-major
+    const uint32_t idesc_dq = umma_idesc_f16(128, p.dn, 0, 1);   // A = dS K-major, B = K MN-major
+    const uint32_t p_mn = umma_desc_lo(smem_u32(sP), ABOX), ds_mn = umma_desc_lo(smem_u32(sDS), ABOX);
+    const uint32_t ds_lo = umma_desc_lo(smem_u32(sDS), 16);
+    const uint32_t k_mn = umma_desc_lo(smem_u32(sK), ABOX);
+    const uint32_t q_mn0 = umma_desc_lo(smem_u32(sQ), ABOX), do_mn0 = umma_desc_lo(smem_u32(sdO), ABOX);
+    auto issue_dv = [&](int it, uint32_t do_mn) {
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)
+        umma_f16_ss(tmem + DV_COL, umma_desc_pack(p_mn + ks * 128, hi), umma_desc_pack(do_mn + ks * 128, hi), idesc_acc,
+                    (it > 0) || (ks > 0));
+      umma_commit(smem_u32(bar_dv));
+    };
+    mbar_wait(smem_u32(&q_full[0]), 0);
+    mbar_wait(smem_u32(bar_p), 0);
+    tc_fence_after();
+    if (elect_one()) issue_dv(0, do_mn0);
+    __syncwarp();
+    for (int it0 = 0; it0 < n_it; it0 += STAGES) {
+#pragma unroll
+      for (int s = 0; s < STAGES; ++s) {
+        const int it = it0 + s;
+        if (it >= n_it) break;
+        const int s1 = (s + 1) % STAGES;
+        const uint32_t par = it & 1;
+        const uint32_t q_mn = q_mn0 + s * (TILE >> 4);
+        TB_TRACE3(it, 0);
+        mbar_wait(smem_u32(bar_ds), par);
+        if (it > 0) mbar_wait(smem_u32(bar_dqfree), par ^ 1);  // the previous pair's dQ has been drained
+        tc_fence_after();
+        TB_TRACE3(it, 1);
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_f16_ss(tmem + DK_COL, umma_desc_pack(ds_mn + ks * 128, hi), umma_desc_pack(q_mn + ks * 128, hi),
+                        idesc_acc, (it > 0) || (ks > 0));
+          if (p.dQacc) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint32_t off = ((ks >> 2) * ABOX + (ks & 3) * 32) >> 4;
+              umma_f16_ss(tmem + DQ_COL, umma_desc_pack(ds_lo + off, hi), umma_desc_pack(k_mn + ks * 128, hi), idesc_dq,
+                          ks > 0);
+            }
+          }
+          umma_commit(smem_u32(bar_dq));
+          umma_commit(smem_u32(&q_empty[s]));
+        }
+        __syncwarp();
+        TB_TRACE3(it, 2);
+        if (it + 1 < n_it) {
+          mbar_wait(smem_u32(&q_full[s1]), ((it + 1) / STAGES) & 1);  // (long complete)
+          mbar_wait(smem_u32(bar_p), par ^ 1);
+          tc_fence_after();
+          TB_TRACE3(it, 3);
+          if (elect_one()) issue_dv(it + 1, do_mn0 + s1 * (TILE >> 4));
+          __syncwarp();
+          TB_TRACE3(it, 4);
+        }
+      }
+    }
+  } else if (warp < 16) {
+    // ---------------------------------------------------------------- softmax / dS / drain warps
+    // four threads per query row: warp w -> TMEM lane quarter w & 3, 32-column group w >> 2
+    const int quarter = warp & 3, cg = warp >> 2;
+    const int row = quarter * 32 + lane;  // query row inside the tile; kv row for the dK / dV epilogue
+    const int cb = cg * 32;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    const long long bh = (long long)b * p.heads + h;
+    const uint32_t sp_base = smem_u32(sP), sds_base = smem_u32(sDS);
+    const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2);
+    const int kvalid = p.Nk - kv0;  // columns >= kvalid of this KV tile are padding keys
+    // Per iteration `it` a thread finishes pair it (dS(it) = P(it) o (dP(it) - delta)), starts pair it+1
+    // (P(it+1) = exp2(S(it+1) c - L)) and moves its share of dQ(it-1) out: three independent instruction streams
+    // (ALU / FMA, MUFU-bound, memory) in ONE pass with one proxy fence and no barrier wider than a warp, so the four
+    // warps of an SM sub-partition drift apart and overlap each other's MUFU and ALU phases.  All waits on the
+    // gradient MMAs (dS tile free, P tile free, dQ ready) sit at the end of the pass, a whole pass after their MMAs
+    // were issued.  (First version of this kernel: P phase, dQ drain, dS phase one after the other with every warp in
+    // lockstep: 3570 cycles per pair, of which 1130 MUFU-bound, 780 in the drain's barriers / fences, 450 dS arithmetic.)
+    float l_cur = 0.f, d_cur = 0.f, l_nxt = 0.f, d_nxt = 0.f;
+    auto load_ld = [&](int i, float& l, float& dl) {
+      const int q = i * 128 + row;
+      // +inf makes exp2(. - L) == 0 for padding queries
+      l = q < p.Nq ? p.lse[bh * p.Nq + q] : INFINITY;
+      dl = q < p.Nq ? p.delta[bh * p.Nq + q] : 0.f;
+    };
+    uint32_t pk[16];  // this thread's 32 entries of P(it) as packed fp16, kept for the dS product
+    auto p_compute = [&](int it, float L, auto masked_tag) {  // P(it) -> pk
+      constexpr bool MASKED = decltype(masked_tag)::value;
+      const uint64_t negl2 = pack_f32x2(-L, -L);
+      mbar_wait(smem_u32(bar_s), it & 1);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld32(lane_addr + S_COL + cb, r);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(smem_u32(bar_sfree));  // S(it) is in registers: the next pair's scores may overwrite it
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const uint64_t e = fma_f32x2(pack_f32x2(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1])), sc2, negl2);
+        float p0, p1;
+        exp2_pair_mufu(e, p0, p1);
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pk[k]) : "f"(p1), "f"(p0));
+        if (MASKED) {
+          if (cb + 2 * k >= kvalid) pk[k] &= 0xffff0000u;
+          if (cb + 2 * k + 1 >= kvalid) pk[k] &= 0x0000ffffu;
+        }
+      }
+    };
+    auto p_store = [&](int it) {
+      if (it > 0) mbar_wait(smem_u32(bar_dv), (it - 1) & 1);  // dV(it-1) has finished reading the P tile
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        st_shared_v4(sp_base + sw128_off(row, cg * 4 + g), pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+    };
+    // dQ(it): each warp owns a [32 rows x 16 columns] block of the tile: TMEM -> its own 2 KB of staging -> (after the
+    // proxy fence) two TMA reduce-adds of [32 x 8] floats.  Only __syncwarp is needed: lane 0 issued the previous
+    // reduce-adds of this block and waits until they have read the staging block before the warp overwrites it.
+    const bool dq_warp = p.dQacc != nullptr && cg * 16 < p.dn;
+    const uint32_t sdq_warp = smem_u32(sDQ) + (uint32_t)warp * 2048;  // [2 column groups][32 rows][8 floats]
+    auto dq_to_staging = [&](int it) {
+      mbar_wait(smem_u32(bar_dq), it & 1);  // dK / dQ of that pair retired (also: the dS tile may be overwritten)
+      tc_fence_after();
+      if (dq_warp) {
+        uint32_t r[16];
+        tmem_ld16(lane_addr + DQ_COL + cg * 16, r);
+        tmem_ld_wait();
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const uint32_t dst = sdq_warp + (uint32_t)(g * 32 + lane) * 32;
+          st_shared_v4f(dst, __uint_as_float(r[g * 8 + 0]) * p.scale, __uint_as_float(r[g * 8 + 1]) * p.scale,
+                        __uint_as_float(r[g * 8 + 2]) * p.scale, __uint_as_float(r[g * 8 + 3]) * p.scale);
+          st_shared_v4f(dst + 16, __uint_as_float(r[g * 8 + 4]) * p.scale, __uint_as_float(r[g * 8 + 5]) * p.scale,
+                        __uint_as_float(r[g * 8 + 6]) * p.scale, __uint_as_float(r[g * 8 + 7]) * p.scale);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(bar_dqfree));
+    };
+    auto dq_reduce = [&](int it) {  // after fence.proxy.async
+      if (!dq_warp) return;
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+          if (cg * 16 + g * 8 < p.d)  // (rows >= Nq are clipped by the tensor map)
+            tma_reduce_add_3d(&tmDQ, sdq_warp + g * 1024, h * p.d + cg * 16 + g * 8, (i_begin + it) * 128 + quarter * 32, b);
+        tma_store_commit();
+      }
+    };
+    auto body = [&](auto masked_tag) {
+      load_ld(i_begin, l_cur, d_cur);
+      if (n_it > 1) load_ld(i_begin + 1, l_nxt, d_nxt);
+      p_compute(0, l_cur, masked_tag);
+      p_store(0);
+      fence_async_smem();
+      mbar_arrive(smem_u32(bar_p));
+      for (int it = 0; it < n_it; ++it) {
+        const uint32_t par = it & 1;
+        const bool more = it + 1 < n_it;
+        const uint64_t delta2 = pack_f32x2(d_cur, d_cur);
+        // ---- dS(it) = P(it) o (dP(it) - delta), kept in registers
+        TB_TRACE3(it, 1);
+        mbar_wait(smem_u32(bar_dp), par);
+        tc_fence_after();
+        TB_TRACE3(it, 2);
+        uint32_t ds[16];
+        {
+          uint32_t r[32];
+          tmem_ld32(lane_addr + DP_COL + cb, r);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(smem_u32(bar_dpfree));  // dP(it) is in registers
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            ds[k] = hmul2_sub(pk[k], pack_f32x2(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1])), delta2);
+        }
+        TB_TRACE3(it, 3);
+        // ---- P(it+1) -> pk
+        if (more) {
+          l_cur = l_nxt;
+          d_cur = d_nxt;
+          if (it + 2 < n_it) load_ld(i_begin + it + 2, l_nxt, d_nxt);
+          p_compute(it + 1, l_cur, masked_tag);
+        }
+        TB_TRACE3(it, 4);
+        // ---- everything that waits for the gradient MMAs of the previous pass
+        if (it > 0) dq_to_staging(it - 1);  // (also: dK / dQ(it-1) have finished reading the dS tile)
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          st_shared_v4(sds_base + sw128_off(row, cg * 4 + g), ds[g * 4], ds[g * 4 + 1], ds[g * 4 + 2], ds[g * 4 + 3]);
+        if (more) p_store(it + 1);
+        fence_async_smem();
+        mbar_arrive(smem_u32(bar_ds));
+        if (more) mbar_arrive(smem_u32(bar_p));
+        if (it > 0) dq_reduce(it - 1);
+        TB_TRACE3(it, 5);
+      }
+      // the last pair's dQ; its bar_dq also covers every MMA the gradient warp has issued (dV, dK are final)
+      dq_to_staging(n_it - 1);
+      fence_async_smem();
+      dq_reduce(n_it - 1);
+      if (lane == 0) tma_store_wait_all<0>();  // every reduce-add has been performed before the CTA retires
+    };
+    if (kvalid >= 128) body(std::false_type{});
+    else body(std::true_type{});
+
+    // ------------------------------------------------------------ dV / dK epilogue (16 columns per warp group)
+    const bool kv_ok = kv0 + row < p.Nk;
+    const int c = cg * 16;
+    if (c < p.dn) {
+      uint32_t rv[16], rk[16];
+      tmem_ld16(lane_addr + DV_COL + c, rv);
+      tmem_ld16(lane_addr + DK_COL + c, rk);
+      tmem_ld_wait();
+      if (kv_ok && p.qsplit > 1) {
+        const long long Cc = (long long)p.heads * p.d;
+        float* wv = p.dkv_ws + ((long long)b * p.Nk + kv0 + row) * Cc + h * p.d;
+        float* wk = wv + (long long)gridDim.z * p.Nk * Cc;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (c + g * 4 < p.d) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wv + c + g * 4),
+                         "f"(__uint_as_float(rv[g * 4 + 0])), "f"(__uint_as_float(rv[g * 4 + 1])),
+                         "f"(__uint_as_float(rv[g * 4 + 2])), "f"(__uint_as_float(rv[g * 4 + 3]))
+                         : "memory");
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wk + c + g * 4),
+                         "f"(__uint_as_float(rk[g * 4 + 0]) * p.scale), "f"(__uint_as_float(rk[g * 4 + 1]) * p.scale),
+                         "f"(__uint_as_float(rk[g * 4 + 2]) * p.scale), "f"(__uint_as_float(rk[g * 4 + 3]) * p.scale)
+                         : "memory");
+          }
+        }
+      } else if (kv_ok) {
+        __half* dv = p.dV + ((long long)b * p.Nk + kv0 + row) * p.lddv + h * p.d;
+        __half* dk = p.dK + ((long long)b * p.Nk + kv0 + row) * p.lddk + h * p.d;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (c + g * 8 < p.d) {
+            uint4 o;
+            o.x = pack_half2(__uint_as_float(rv[g * 8 + 0]), __uint_as_float(rv[g * 8 + 1]));
+            o.y = pack_half2(__uint_as_float(rv[g * 8 + 2]), __uint_as_float(rv[g * 8 + 3]));
+            o.z = pack_half2(__uint_as_float(rv[g * 8 + 4]), __uint_as_float(rv[g * 8 + 5]));
+            o.w = pack_half2(__uint_as_float(rv[g * 8 + 6]), __uint_as_float(rv[g * 8 + 7]));
+            *reinterpret_cast<uint4*>(dv + c + g * 8) = o;
+            o.x = pack_half2(__uint_as_float(rk[g * 8 + 0]) * p.scale, __uint_as_float(rk[g * 8 + 1]) * p.scale);
+            o.y = pack_half2(__uint_as_float(rk[g * 8 + 2]) * p.scale, __uint_as_float(rk[g * 8 + 3]) * p.scale);
+            o.z = pack_half2(__uint_as_float(rk[g * 8 + 4]) * p.scale, __uint_as_float(rk[g * 8 + 5]) * p.scale);
+            o.w = pack_half2(__uint_as_float(rk[g * 8 + 6]) * p.scale, __uint_as_float(rk[g * 8 + 7]) * p.scale);
+            *reinterpret_cast<uint4*>(dk + c + g * 8) = o;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc_rt(tmem, 512u);
+}
+
 }  // namespace tb
 
 // ------------------------------------------------------------------------------------ host side
@@ -2007,6 +2445,32 @@ static int launch_attn_bwd2(const CUtensorMap& tq, const CUtensorMap& tk, const 
   dim3 grid(((p.Nk + 127) / 128) * p.qsplit, p.heads, B);
   attn_bwd2_kernel<STAGES><<<grid, 576, smem, st>>>(tq, tk, tv, tdo, tdq, p);
   return check_launch("attn_bwd2_kernel");
+}
+
+static int launch_attn_bwd3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                            const CUtensorMap& tdo, const AttnParams& p, int B, cudaStream_t st) {
+  constexpr int STAGES = 3;
+  constexpr int smem = ABOX * (2 + 2 * STAGES) + 4 * ABOX + 128 * 64 * 4 + 256 + 1024;
+  CUtensorMap tdq = tq;  // (unused without dQ)
+  if (p.dQacc) {
+    uint64_t dims[3] = {(uint64_t)p.lddq, (uint64_t)p.Nq, (uint64_t)B};
+    uint64_t strides[2] = {(uint64_t)p.lddq * 4, (uint64_t)p.Nq * p.lddq * 4};
+    uint32_t box[3] = {8u, 32u, 1u};  // one [32 rows x 8 columns] block per reduce-add (two per softmax warp)
+    int rc = make_tmap_f32_plain(&tdq, p.dQacc, 3, dims, strides, box);
+    if (rc) return rc;
+  }
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd3_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(attn_bwd3, %d): %s", smem, cudaGetErrorString(e));
+      return TB_E_CUDA;
+    }
+    configured = true;
+  }
+  dim3 grid(((p.Nk + 127) / 128) * p.qsplit, p.heads, B);
+  attn_bwd3_kernel<STAGES><<<grid, 608, smem, st>>>(tq, tk, tv, tdo, tdq, p);
+  return check_launch("attn_bwd3_kernel");
 }
 
 template <int NB, int STAGES>
@@ -2145,7 +2609,9 @@ extern "C" int tb_attn_bwd_f16(const void* q, int64_t ldq, const void* k, int64_
     }
   }
   static const bool v1 = getenv("TB_ATTN_BWD_V1") != nullptr;  // diagnostic switch: the two-CTA-per-SM kernel
-  if (nb == 1 && !causal && !v1) rc = launch_attn_bwd2(tq, tk, tv, tdo, p, B, st);
+  static const bool v2 = getenv("TB_ATTN_BWD_V2") != nullptr;  // diagnostic switch: the transposed-score kernel
+  if (nb == 1 && !causal && !v1 && !v2) rc = launch_attn_bwd3(tq, tk, tv, tdo, p, B, st);
+  else if (nb == 1 && !causal && !v1) rc = launch_attn_bwd2(tq, tk, tv, tdo, p, B, st);
   else if (nb == 1) rc = launch_attn_bwd<1, 1>(tq, tk, tv, tdo, p, B, st);
   else if (nb == 2) rc = launch_attn_bwd<2, 1>(tq, tk, tv, tdo, p, B, st);
   else rc = launch_attn_bwd<3, 1>(tq, tk, tv, tdo, p, B, st);
