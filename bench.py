@@ -84,6 +84,44 @@ def read_attention_tensor_pipe():
                     "(16384 exp per 128x128 tile), see DESIGN.md section 4"}
 
 
+def attention_microbench(peak_tf):
+    """The attention half of BASELINE.json's metric, measured IN THIS RUN: CUDA-event time of the forward and
+    backward attention kernels at the three UNet self-attention levels (B=8, heads 8) and the achieved algorithmic
+    TFLOP/s (4 N^2 d per head forward, 8 N^2 d backward; d is the true head_dim, not its 16-padded MMA width).
+    Inputs (q/k/v/o/dO of a level: 0.1-0.2 GB) exceed nothing special: 3 warm-ups, 10 timed launches each."""
+    import torch
+    from textboost_b200 import ops
+    out = {}
+    for (N, d) in ((4096, 40), (1024, 80), (256, 160)):
+        B, H = 8, 8
+        C_ = H * d
+        g = torch.Generator(device="cuda").manual_seed(N + d)
+        qkv = torch.randn(B, N, 3 * C_, device="cuda", dtype=torch.float16, generator=g)
+        q, k, v = qkv[..., :C_], qkv[..., C_:2 * C_], qkv[..., 2 * C_:]
+        do = torch.randn(B, N, C_, device="cuda", dtype=torch.float16, generator=g)
+        o, lse = ops.attn_fwd(q, k, v, H)
+
+        def t(fn, iters=10):
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / iters
+        tf_ = t(lambda: ops.attn_fwd(q, k, v, H))
+        tb_ = t(lambda: ops.attn_bwd(q, k, v, o, do, lse, H))
+        fl = 4.0 * B * H * N * N * d
+        out[f"N{N}_d{d}"] = {"fwd_ms": round(tf_, 4), "fwd_tflops": round(fl / tf_ / 1e9, 1),
+                             "fwd_frac_of_peak": round(fl / tf_ / 1e9 / peak_tf, 3),
+                             "bwd_ms": round(tb_, 4), "bwd_tflops": round(2 * fl / tb_ / 1e9, 1),
+                             "bwd_frac_of_peak": round(2 * fl / tb_ / 1e9 / peak_tf, 3)}
+    return out
+
+
 def read_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -411,6 +449,12 @@ def run_ours(args):
         cpu_base = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                     "sample": f"{done} step of the oracle port (fp32 autograd, torch CPU) at bs={args.ref_images} "
                               f"of the same SD-1.5 workload ({cms / 1e3:.1f} s); {threads} torch threads"}
+    attn = None
+    if rank == 0:
+        attn = read_attention_tensor_pipe() or {}
+        attn["measured"] = attention_microbench(read_peaks()["tf_burst"])
+        attn["measured_how"] = ("CUDA events in this run, kernels timed alone (burst bf16 peak as denominator); "
+                                "tensor_pipe_pct is ncu's counter from the committed capture")
     if rank == 0:
         peaks = read_peaks()
         images = B * world
@@ -447,7 +491,7 @@ def run_ours(args):
                 "step": {"achieved": step_tf, "frac": step_tf / peaks["tf_sustained"],
                          "tflop_per_image": TFLOP_PER_IMG[use_kpl]},
             },
-            "attention": read_attention_tensor_pipe(),
+            "attention": attn,
             "cpu_baseline": cpu_base,
             "loss": loss_val, "loss_scale": state[0], "skipped_steps": state[8],
         }

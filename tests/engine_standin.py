@@ -109,8 +109,16 @@ def attn_bwd(q, k, v, o, do, lse, heads, scale=None, need_dq=True, dk=None, dv=N
     return dq, gk, gv
 
 
+class _NoEvent:
+    def record(self, stream=None):
+        pass
+
+
 class _NoStream:
     def wait_stream(self, other):
+        pass
+
+    def wait_event(self, event):
         pass
 
     def synchronize(self):
@@ -125,5 +133,6 @@ def install(monkeypatch):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _NoStream())
     monkeypatch.setattr(torch.cuda, "Stream", lambda *a, **k: _NoStream())
+    monkeypatch.setattr(torch.cuda, "Event", lambda *a, **k: _NoEvent())
     monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)

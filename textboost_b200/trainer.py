@@ -99,15 +99,23 @@ class TextBoostTrainer:
         te.pack_lora()
         self.loss.zero_()
         noisy, target = ops.add_noise(latents, noise, timesteps, self.acp, self.v_pred)
-        h = te.forward(input_ids, save_for_backward=True)  # fp32 [B, L, D]
-        ctx_i = te.pop_ctx()
-        if use_kpl:
-            # fork AFTER the instance-prompt encoder pass: that pass is on the critical path (the UNet waits for
-            # it) and should not share the SMs with the prior-prompt branch, which has the whole UNet to hide behind
-            side = self._side_stream()
-            self._loss_kpl.zero_()
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
+        # The text-encoder passes run on a side stream: first the instance prompts (the UNet needs them at its first
+        # cross-attention: an event, not a join), then the whole knowledge-preservation branch.  The main stream goes
+        # straight into the UNet, whose prefix (conv_in, time MLP, first resnet, first self-attention) does not read
+        # the text: the 616-row encoder kernels fill a fraction of the SMs, the UNet prefix takes the rest.
+        side = self._side_stream()
+        self._loss_kpl.zero_()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            h = te.forward(input_ids, save_for_backward=True)  # fp32 [B, L, D]
+            ctx_i = te.pop_ctx()
+            _, L, D = h.shape
+            ehs = ops.cast_f32_f16(h.view(B * L, D)).view(B, L, D)
+            if ehs.is_cuda:
+                ehs.record_stream(main)
+            ehs_ready = torch.cuda.Event()
+            ehs_ready.record(side)
+            if use_kpl:
                 hp = te.forward(prior_ids, save_for_backward=True)
                 ctx_p = te.pop_ctx()
                 h0 = self.te0.forward(prior_ids)
@@ -117,8 +125,7 @@ class TextBoostTrainer:
                        C.ptr(scale), C.ptr(self._loss_kpl), C.ptr(d_hp), C.stream_ptr())
                 te.backward(d_hp, ctx=ctx_p)
         _, L, D = h.shape
-        ehs = ops.cast_f32_f16(h.view(B * L, D)).view(B, L, D)
-        pred = unet.forward(noisy, timesteps, ehs)
+        pred = unet.forward(noisy, timesteps, ehs, ehs_ready=ehs_ready)
         if self.image_prior_weight is None:
             dpred = ops.mse_fwd_bwd(pred, target, self.loss, 1.0, scale)
         else:
@@ -131,8 +138,8 @@ class TextBoostTrainer:
                             out=dpred[half:])
         d_h = torch.zeros((B, L, D), device=self.dev, dtype=F32)
         unet.backward(dpred, d_h)
+        main.wait_stream(side)  # gradient accumulation into state.grads is serialised from here on
         if use_kpl:
-            main.wait_stream(side)  # gradient accumulation into state.grads is serialised from here on
             self.loss.add_(self._loss_kpl)
             C.launch_count += 1
         te.backward(d_h, ctx=ctx_i)

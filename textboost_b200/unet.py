@@ -151,6 +151,7 @@ class _Transformer:
         self.ff1 = _Linear(sd[t + "ff.net.0.proj.weight"], sd[t + "ff.net.0.proj.bias"])
         self.ff2 = _Linear(sd[t + "ff.net.2.weight"], sd[t + "ff.net.2.bias"])
         self.first = False  # first cross-attention of the net: backward stops at dK/dV
+        self.ehs_ready = None  # set on the first cross-attention: event after which encoder_hidden_states is valid
 
     def forward(self, x, ehs, save):
         B, H, W, Cc = x.shape
@@ -164,6 +165,8 @@ class _Transformer:
         h1 = self.o1.fwd(o1.view(M, Cc), residual=h0)
         n2, s2 = ops.layernorm(h1, *self.ln2)
         q2 = self.q2.fwd(n2).view(B, N, Cc)
+        if self.ehs_ready is not None:  # the text encoder runs on another stream up to here (trainer.py)
+            torch.cuda.current_stream().wait_event(self.ehs_ready)
         kv2 = self.kv2.fwd(ehs.reshape(B * L, -1)).view(B, L, 2 * Cc)
         o2, lse2 = ops.attn_fwd(q2, kv2[..., :Cc], kv2[..., Cc:], self.heads)
         h2 = self.o2.fwd(o2.view(M, Cc), residual=h1)
@@ -284,9 +287,15 @@ class UNetEngine:
         self._saved = None
 
     # ------------------------------------------------------------------ forward
-    def forward(self, sample, timesteps, ehs, save_for_backward=True):
-        """sample [B,4,H,W] fp16 NCHW, timesteps int64 [B], ehs [B,L,ctx] fp16 -> [B,4,H,W] fp16."""
+    def forward(self, sample, timesteps, ehs, save_for_backward=True, ehs_ready=None):
+        """sample [B,4,H,W] fp16 NCHW, timesteps int64 [B], ehs [B,L,ctx] fp16 -> [B,4,H,W] fp16.
+
+        ehs_ready (torch.cuda.Event): `ehs` is still being produced on another stream; nothing up to the first
+        cross-attention K/V projection reads it, so only that point waits for the event -- conv_in, the time MLP, the
+        first resnet and the first self-attention overlap the text encoder (the reference runs them back to back,
+        train_textboost.py:1054-1067)."""
         cfg = self.cfg
+        self.first_attn.ehs_ready = ehs_ready
         assert sample.dtype == F16 and ehs.dtype == F16 and timesteps.dtype == torch.int64
         sample = sample.contiguous()
         ehs = ehs.contiguous()
@@ -321,6 +330,7 @@ class UNetEngine:
                 x = blk["up"].forward(x)
         hn, st = ops.groupnorm(x, *self.norm_out, cfg.norm_num_groups, cfg.norm_eps, True)
         out = ops.conv_out(hn, self.conv_out_w, self.conv_out_b)
+        self.first_attn.ehs_ready = None
         if save:
             self._saved = (x, st, cat_split, ehs.shape)
         return out
