@@ -277,11 +277,22 @@ int tb_kpl_fwd_bwd(const float* h, const float* h0, int M, int D, int kind, floa
 /* ---- optimiser tail (train_textboost.py:1109-1149; torch.optim.AdamW; accelerate GradScaler) ----
  * Flat fp32 buffers [LoRA (n_lora) | added embedding rows (n_rows*D)].  state: fp32[16] on the device:
  * [0] loss scale [1] growth tracker [2] found_inf [3] sum g^2 [4] step [5] frozen-row decay
- * [6] clip coef [7] grad norm [8] skipped steps.  grads are consumed AND zeroed. */
+ * [6] clip coef [7] grad norm [8] skipped steps [9] learning-rate multiplier of the last step.
+ * grads are consumed AND zeroed.  lr_schedule (TB_LR_*) restates diffusers.optimization.get_scheduler
+ * (train_textboost.py:911-916) on the device: both learning rates are multiplied by the schedule's value at the
+ * number of successful steps so far (state[4]), so the schedule advances inside a replayed CUDA graph and pauses on
+ * GradScaler-skipped steps, as accelerate's scheduler wrapper does. */
+#define TB_LR_CONSTANT 0
+#define TB_LR_CONSTANT_WITH_WARMUP 1
+#define TB_LR_LINEAR 2
+#define TB_LR_COSINE 3
+#define TB_LR_COSINE_WITH_RESTARTS 4
+#define TB_LR_POLYNOMIAL 5
 int tb_optim_mix_mask(float* grad_lora_b, int64_t n, int D, int r, int parity, void* stream);
 int tb_adamw_fused_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n_lora,
                         int n_rows, int D, float lr_lora, float lr_emb, float beta1, float beta2, float eps,
                         float weight_decay, float max_grad_norm, float inv_world, float mean_norm,
+                        int lr_schedule, float lr_warmup_steps, float lr_total_steps,
                         float* state, float* row_norm_mean, void* stream);
 
 #ifdef __cplusplus

@@ -202,6 +202,7 @@ extern "C" void emu_adamw_reduce_update(float* p, float* g, float* m, float* v, 
   c.lr_lora = lr_lora; c.lr_emb = lr_emb; c.beta1 = beta1; c.beta2 = beta2; c.eps = eps; c.wd = wd;
   c.max_norm = max_norm; c.inv_world = inv_world; c.mean_norm = 0.f;
   c.growth_factor = 2.f; c.backoff_factor = 0.5f; c.growth_interval = 2000;
+  c.sched_kind = 0; c.sched_warmup = 0.f; c.sched_total = 0.f;
   tb::optim_reduce_kernel(g, c, state);
   tb::optim_update_kernel(p, g, m, v, c, state);
 }

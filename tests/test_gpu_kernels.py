@@ -414,7 +414,8 @@ def test_fused_adamw_matches_torch():
             grads[7] = float("inf")
         before = p.clone()
         C.call("tb_adamw_fused_step", C.ptr(p), C.ptr(grads), C.ptr(m), C.ptr(v), n_lora, n_rows, D, 1e-4, 1e-3,
-               0.9, 0.999, 1e-8, 1e-2, 1.0, 1.0 / world, mean_norm, C.ptr(state), C.ptr(norm_out), C.stream_ptr())
+               0.9, 0.999, 1e-8, 1e-2, 1.0, 1.0 / world, mean_norm, 0, 0.0, 0.0, C.ptr(state), C.ptr(norm_out),
+               C.stream_ptr())
         torch.cuda.synchronize()
         assert torch.count_nonzero(grads) == 0  # zero_grad fused
         if step == 3:
@@ -431,3 +432,40 @@ def test_fused_adamw_matches_torch():
         torch.testing.assert_close(p[n_lora:].view(n_rows, D), rows_ref.detach(), rtol=1e-5, atol=1e-7)
         torch.testing.assert_close(norm_out[0], nv.mean(), rtol=1e-5, atol=1e-7)
     assert state[4].item() == 5 and abs(state[5].item() - (1 - 1e-3 * 1e-2) ** 5) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["constant_with_warmup", "linear", "cosine", "cosine_with_restarts", "polynomial"])
+def test_fused_adamw_lr_schedules_match_torch_lambda_lr(name):
+    """--lr_scheduler (train_textboost.py:224-233, 911-916): the schedule evaluated on the device inside
+    tb_adamw_fused_step against torch.optim.AdamW driven by a LambdaLR with the same diffusers formula, 12 steps with
+    3 warm-up steps; a GradScaler-skipped step (inf gradient) does not advance the schedule."""
+    from textboost_b200 import _cabi as C
+    from textboost_b200.optim import LR_SCHEDULES, lr_multiplier
+    n_lora, D, n_rows, warm, total = 64, 16, 1, 3, 12
+    n = n_lora + n_rows * D
+    g0 = torch.Generator(device=dev).manual_seed(5)
+    p = torch.randn(n, device=dev, generator=g0)
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([ref], lr=1e-2, weight_decay=1e-2)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: lr_multiplier(name, s, warm, total, 1e-2))
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    state = torch.zeros(16, device=dev)
+    state[0], state[5] = 1.0, 1.0
+    norm_out = torch.zeros(1, device=dev)
+    for step in range(total):
+        g = torch.randn(n, device=dev, generator=g0) * 0.1
+        grads = g.clone()
+        if step == 5:
+            grads[3] = float("inf")
+        C.call("tb_adamw_fused_step", C.ptr(p), C.ptr(grads), C.ptr(m), C.ptr(v), n_lora, n_rows, D, 1e-2, 1e-2,
+               0.9, 0.999, 1e-8, 1e-2, 0.0, 1.0, 1e9, LR_SCHEDULES[name], float(warm), float(total), C.ptr(state),
+               C.ptr(norm_out), C.stream_ptr())
+        if step == 5:
+            state[0] = 1.0  # undo the GradScaler back-off so the comparison stays at scale 1
+            continue
+        ref.grad = g.clone()
+        opt.step()
+        sched.step()
+        assert abs(state[9].item() - lr_multiplier(name, int(state[4].item()) - 1, warm, total, 1e-2)) < 1e-6
+    torch.testing.assert_close(p, ref.detach(), rtol=2e-5, atol=2e-6)
+    assert state[4].item() == total - 1 and state[8].item() == 1

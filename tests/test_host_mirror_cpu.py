@@ -202,15 +202,49 @@ def test_cli_rejects_what_the_reference_cannot_run():
     base = ["--pretrained_model_name_or_path", "x"]
     T._unsupported(T.parse_args(base))
     for extra in (["--text_encoder_use_attention_mask"], ["--lora_rank", "0"], ["--unet_params_to_train", "crossattn_kv"],
-                  ["--gradient_accumulation_steps", "2"], ["--lr_scheduler", "cosine"], ["--mixed_precision", "bf16"],
+                  ["--mixed_precision", "bf16"],
                   ["--validation_prompts", "a dog", "--validation_scheduler", "DDPMScheduler"]):
         with pytest.raises(NotImplementedError):
             T._unsupported(T.parse_args(base + extra))
+    for ok in (["--gradient_accumulation_steps", "2"], ["--lr_scheduler", "cosine"]):
+        T._unsupported(T.parse_args(base + ok))  # built in round 2 (csrc/optim.cu lr_multiplier, trainer.step)
+    with pytest.raises(ValueError):
+        T._unsupported(T.parse_args(base + ["--gradient_accumulation_steps", "0"]))
     with pytest.raises(ValueError):
         T._unsupported(T.parse_args(base + ["--with_image_prior", "--class_data_dir", "d", "--class_token", "dog",
                                             "--synthetic_data"]))
     with pytest.warns(UserWarning):
         T._unsupported(T.parse_args(base + ["--report_to", "wandb"]))
+
+
+def test_lr_schedules_follow_the_lambda_lr_formulas():
+    """--lr_scheduler (train_textboost.py:224-233, 911-916): optim.lr_multiplier (the host statement of the device
+    schedule in csrc/optim.cu) against the LambdaLR closed forms of diffusers.optimization.get_scheduler, driven
+    through torch's own LambdaLR so that the step-count convention (value used BY step s = lambda(s)) is torch's."""
+    import math
+    from textboost_b200.optim import LR_SCHEDULES, lr_multiplier
+    warm, total = 4, 20
+    forms = {
+        "constant": lambda s: 1.0,
+        "constant_with_warmup": lambda s: min(1.0, s / max(1.0, warm)),
+        "linear": lambda s: s / max(1, warm) if s < warm else max(0.0, (total - s) / max(1, total - warm)),
+        "cosine": lambda s: s / max(1, warm) if s < warm else max(
+            0.0, 0.5 * (1.0 + math.cos(math.pi * 0.5 * 2.0 * (s - warm) / max(1, total - warm)))),
+    }
+    for name, f in forms.items():
+        w = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.SGD([w], lr=1.0)
+        sch = torch.optim.lr_scheduler.LambdaLR(opt, f)
+        for s in range(total + 3):
+            assert abs(opt.param_groups[0]["lr"] - lr_multiplier(name, s, warm, total)) < 1e-12, (name, s)
+            opt.step()
+            sch.step()
+    assert set(LR_SCHEDULES) == {"linear", "cosine", "cosine_with_restarts", "polynomial", "constant",
+                                 "constant_with_warmup"}  # the reference's choices (train_textboost.py:226-231)
+    # polynomial (power 1, lr_end 1e-7) ends at lr_end; restarts with one cycle equals cosine until the end
+    assert abs(lr_multiplier("polynomial", total, warm, total, 1e-3) - 1e-7 / 1e-3) < 1e-12
+    assert abs(lr_multiplier("cosine_with_restarts", 9, warm, total) - lr_multiplier("cosine", 9, warm, total)) < 1e-12
+    assert lr_multiplier("cosine_with_restarts", total, warm, total) == 0.0
 
 
 def test_scalar_tracker_writes_tensorboard_events(tmp_path):

@@ -105,6 +105,36 @@ def test_three_steps_track_the_oracle(monkeypatch):
     assert harness.rel_max(st.rows(), emb[V:]) < 5e-2
 
 
+def test_gradient_accumulation_equals_one_step_over_the_joined_batch(monkeypatch):
+    """--gradient_accumulation_steps 2 (accelerator.accumulate, train_textboost.py:1039; loss / 2 per micro-batch in
+    accelerate's backward): two micro-batches of one image then ONE optimiser step  ==  one step over the two-image batch
+    (both losses are batch means), with a linear warm-up schedule so the device-side --lr_scheduler is on the path."""
+    from textboost_b200 import synthetic
+    engine_standin.install(monkeypatch)
+    kw = dict(seed=3, n_added=1, lora_b_std=0.02, learning_rate=1e-3, emb_learning_rate=1e-2, lr_scheduler="linear",
+              lr_warmup_steps=2, max_train_steps=10)
+    acc = synthetic.build_trainer("tiny", "cpu", gradient_accumulation_steps=2, **kw)
+    one = synthetic.build_trainer("tiny", "cpu", **kw)
+    V = acc.synthetic["clip_cfg"].vocab_size
+    bt = synthetic.batch(2, 8, 7, V, "cpu")
+    keys = ("latents", "noise", "timesteps", "input_ids", "prior_ids")
+    for _ in range(2):  # two optimiser steps: the first runs at the warm-up's lr = 0, the second at lr / 2
+        acc.step(*(bt[k][:1] for k in keys), sync_gradients=False)
+        assert acc.opt_state[4].item() == one.opt_state[4].item()  # no optimiser step yet
+        acc.step(*(bt[k][1:] for k in keys))
+        one.step(*(bt[k] for k in keys))
+    assert acc.opt_state[4].item() == 2 and abs(acc.opt_state[9].item() - 0.5) < 1e-6
+    assert acc.opt.get_last_lr() == [pytest.approx(5e-3), pytest.approx(5e-4)]
+    a, b = acc.te.state.params, one.te.state.params
+    # Adam moves an element whose gradient is ~0 by +-lr whatever its size (fp16 noise picks the sign): at most two
+    # steps of the second lr apart there, and equal to a hundredth of a step on average
+    d = (a - b).abs()
+    assert d.max().item() <= 2.1 * 5e-3 and d[:acc.te.state.n_lora].max().item() <= 2.1 * 5e-4
+    assert d.mean().item() < 5e-6 and (d > 5e-5).float().mean().item() < 0.02
+    rel = ((acc.opt.exp_avg - one.opt.exp_avg).norm() / one.opt.exp_avg.norm()).item()
+    assert rel < 5e-3, rel  # fp16 activations: the one-image and two-image passes round differently
+
+
 @pytest.mark.parametrize("name", ["small_quickgelu_qkv_r4", "small_gelu_qkvo_r8"])
 def test_clip_engine_lora_on_cpu_matches_reference_golden(monkeypatch, name):
     """The product ClipEngine (LoRA fused into the QKV and out-projection GEMMs as K extensions; SIMT LoRA kernels

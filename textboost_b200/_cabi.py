@@ -102,8 +102,8 @@ _SIGNATURES = {
     "tb_kpl_fwd_bwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
                        c_void_p],
     "tb_optim_mix_mask": [c_void_p, c_int64, c_int, c_int, c_int, c_void_p],
-    "tb_adamw_fused_step": [c_void_p] * 4 + [c_int64, c_int, c_int] + [c_float] * 9 + [c_void_p, c_void_p,
-                                                                                     c_void_p],
+    "tb_adamw_fused_step": [c_void_p] * 4 + [c_int64, c_int, c_int] + [c_float] * 9 + [c_int, c_float, c_float] +
+                           [c_void_p, c_void_p, c_void_p],
 }
 _RESTYPES = {"tb_last_error": c_char_p}
 

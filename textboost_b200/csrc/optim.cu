@@ -9,6 +9,7 @@
 // Device state vector (fp32[16]):
 //   [0] loss_scale  [1] growth_tracker  [2] found_inf  [3] sum g^2 (LoRA, scaled)  [4] step t
 //   [5] frozen-row decay c  [6] last clip coefficient  [7] last grad norm (unscaled)  [8] skipped steps
+//   [9] learning-rate multiplier of the step just taken (the --lr_scheduler value, train_textboost.py:911-916)
 #include "host_util.h"
 #include "sm100.cuh"
 
@@ -20,7 +21,34 @@ struct AdamCfg {
   float lr_lora, lr_emb, beta1, beta2, eps, wd, max_norm, inv_world, mean_norm;
   float growth_factor, backoff_factor;
   int growth_interval;
+  int sched_kind;               // TB_LR_* (diffusers.optimization.get_scheduler names)
+  float sched_warmup, sched_total;
 };
+
+// Multiplier of both learning rates at optimiser step `s` (0-based count of SUCCESSFUL steps so far: accelerate does
+// not advance the scheduler when the GradScaler skipped the step).  Restates diffusers.optimization's LambdaLR
+// factories with their defaults (num_cycles 0.5 / 1, power 1, lr_end 1e-7) as called at train_textboost.py:911-916;
+// accelerate steps the scheduler num_processes times per step with both lengths pre-multiplied by num_processes,
+// which leaves these ratio formulas unchanged.
+__device__ __forceinline__ float lr_multiplier(const AdamCfg& c, float s, float lr_init) {
+  const float warm = c.sched_warmup, total = c.sched_total;
+  if (c.sched_kind == 0) return 1.f;
+  if (s < warm) return s / fmaxf(1.f, warm);
+  if (c.sched_kind == 1) return 1.f;
+  const float progress = (s - warm) / fmaxf(1.f, total - warm);
+  switch (c.sched_kind) {
+    case 2: return fmaxf(0.f, (total - s) / fmaxf(1.f, total - warm));
+    case 3: return fmaxf(0.f, 0.5f * (1.f + cosf(3.14159265358979f * progress)));  // num_cycles = 0.5
+    case 4: return progress >= 1.f ? 0.f : fmaxf(0.f, 0.5f * (1.f + cosf(3.14159265358979f * fmodf(progress, 1.f))));  // one cycle
+    case 5: {
+      const float lr_end = 1e-7f;
+      if (s > total) return lr_end / lr_init;
+      const float pct = 1.f - (s - warm) / (total - warm);
+      return ((lr_init - lr_end) * pct + lr_end) / lr_init;
+    }
+    default: return 1.f;
+  }
+}
 
 __global__ void optim_mix_mask_kernel(float* __restrict__ g, long long n, int D, int r, int parity) {
   // lora_B blocks are [D][r]; zero rows with (row % 2 == parity)  (train_textboost.py:1119-1126)
@@ -60,13 +88,14 @@ __global__ void optim_update_kernel(float* __restrict__ p, float* __restrict__ g
   const float bc2 = 1.f - powf(c.beta2, t);
   const float rsq_bc2 = rsqrtf(bc2);
   const bool finite_norm = isfinite(norm);
+  const float mult_lora = lr_multiplier(c, state[4], c.lr_lora), mult_emb = lr_multiplier(c, state[4], c.lr_emb);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < c.n_total;
        i += (long long)gridDim.x * blockDim.x) {
     const float gs = g[i];
     g[i] = 0.f;  // optimizer.zero_grad(): the next step accumulates from zero
     if (found_inf != 0.f || !finite_norm) continue;
     const bool lora = i < c.n_lora;
-    const float lr = lora ? c.lr_lora : c.lr_emb;
+    const float lr = lora ? c.lr_lora * mult_lora : c.lr_emb * mult_emb;
     const float gr = gs * inv_scale * ((lora && c.max_norm > 0.f) ? clip : 1.f);
     float w = p[i] * (1.f - lr * c.wd);
     const float mi = c.beta1 * m[i] + (1.f - c.beta1) * gr;
@@ -109,8 +138,9 @@ __global__ void optim_finish_kernel(float* __restrict__ p, AdamCfg c, float* __r
       state[1] = 0.f;
       state[8] += 1.f;
     } else {
+      state[9] = lr_multiplier(c, state[4], c.lr_lora);
+      state[5] *= (1.f - c.lr_emb * lr_multiplier(c, state[4], c.lr_emb) * c.wd);  // frozen rows decay too
       state[4] += 1.f;
-      state[5] *= (1.f - c.lr_emb * c.wd);  // every frozen embedding row decays too
       state[1] += 1.f;
       if (state[1] >= (float)c.growth_interval) {
         state[0] *= c.growth_factor;
@@ -139,11 +169,14 @@ extern "C" int tb_optim_mix_mask(float* grad_lora_b, int64_t n, int D, int r, in
 extern "C" int tb_adamw_fused_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq,
                                    int64_t n_lora, int n_rows, int D, float lr_lora, float lr_emb,
                                    float beta1, float beta2, float eps, float weight_decay,
-                                   float max_grad_norm, float inv_world, float mean_norm, float* state,
+                                   float max_grad_norm, float inv_world, float mean_norm, int lr_schedule,
+                                   float lr_warmup_steps, float lr_total_steps, float* state,
                                    float* row_norm_mean, void* stream) {
   int rc = tb_check_device();
   if (rc) return rc;
   TB_REQUIRE(params && grads && exp_avg && exp_avg_sq && state, TB_E_ARG, "tb_adamw_fused_step: null pointer");
+  TB_REQUIRE(lr_schedule >= 0 && lr_schedule <= 5 && lr_warmup_steps >= 0.f, TB_E_ARG,
+             "tb_adamw_fused_step: unknown lr_schedule %d", lr_schedule);
   AdamCfg c;
   c.n_lora = n_lora;
   c.n_rows = n_rows;
@@ -161,6 +194,9 @@ extern "C" int tb_adamw_fused_step(float* params, float* grads, float* exp_avg, 
   c.growth_factor = 2.f;
   c.backoff_factor = 0.5f;
   c.growth_interval = 2000;
+  c.sched_kind = lr_schedule;
+  c.sched_warmup = lr_warmup_steps;
+  c.sched_total = lr_total_steps;
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned blocks = (unsigned)((c.n_total + 255) / 256 > 592 ? 592 : (c.n_total + 255) / 256);
   optim_reduce_kernel<<<blocks, 256, 0, st>>>(grads, c, state);

@@ -23,7 +23,35 @@ from . import _cabi as C
 F32 = torch.float32
 
 # indices into the device state vector (csrc/optim.cu)
-LOSS_SCALE, GROWTH_TRACKER, FOUND_INF, SUM_SQ, STEP, FROZEN_DECAY, CLIP_COEF, GRAD_NORM, SKIPPED = range(9)
+LOSS_SCALE, GROWTH_TRACKER, FOUND_INF, SUM_SQ, STEP, FROZEN_DECAY, CLIP_COEF, GRAD_NORM, SKIPPED, LR_MULT = range(10)
+
+# --lr_scheduler names of the reference CLI (train_textboost.py:224-231 -> diffusers.optimization.get_scheduler)
+LR_SCHEDULES = {"constant": 0, "constant_with_warmup": 1, "linear": 2, "cosine": 3, "cosine_with_restarts": 4,
+                "polynomial": 5}
+
+
+def lr_multiplier(name: str, step: int, warmup: int, total: int, lr_init: float = 1.0) -> float:
+    """Host statement of the schedule the optimiser kernel evaluates on the device (csrc/optim.cu lr_multiplier):
+    diffusers.optimization's LambdaLR factories with their defaults.  `step` = successful optimiser steps so far."""
+    import math
+    kind = LR_SCHEDULES[name]
+    if kind == 0:
+        return 1.0
+    if step < warmup:
+        return step / max(1.0, warmup)
+    if kind == 1:
+        return 1.0
+    progress = (step - warmup) / max(1.0, total - warmup)
+    if kind == 2:
+        return max(0.0, (total - step) / max(1.0, total - warmup))
+    if kind == 3:
+        return max(0.0, 0.5 * (1.0 + math.cos(math.pi * progress)))
+    if kind == 4:
+        return 0.0 if progress >= 1.0 else max(0.0, 0.5 * (1.0 + math.cos(math.pi * (progress % 1.0))))
+    lr_end = 1e-7
+    if step > total:
+        return lr_end / lr_init
+    return ((lr_init - lr_end) * (1.0 - (step - warmup) / (total - warmup)) + lr_end) / lr_init
 
 
 class FusedAdamW:
@@ -31,7 +59,14 @@ class FusedAdamW:
 
     def __init__(self, engine, lr=5e-5, emb_lr=1e-3, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8,
                  max_grad_norm: Optional[float] = 1.0, mean_norm: Optional[float] = None, mixing=None,
-                 mixed_precision="fp16", world_size: int = 1):
+                 mixed_precision="fp16", world_size: int = 1, lr_scheduler: str = "constant",
+                 lr_warmup_steps: int = 0, max_train_steps: int = 0, gradient_accumulation_steps: int = 1):
+        if lr_scheduler not in LR_SCHEDULES:
+            raise ValueError(f"unknown lr_scheduler {lr_scheduler!r}; one of {sorted(LR_SCHEDULES)}")
+        self.lr_scheduler, self.lr_warmup_steps, self.max_train_steps = lr_scheduler, lr_warmup_steps, max_train_steps
+        # accelerate divides the loss by gradient_accumulation_steps before backward; the micro-batch gradients are
+        # summed in the flat buffer here, so the division joins the 1/world of the all-reduce average
+        self.gradient_accumulation_steps = int(gradient_accumulation_steps)
         self.engine = engine
         st = engine.state
         self.betas, self.weight_decay, self.eps = tuple(betas), weight_decay, eps
@@ -72,8 +107,16 @@ class FusedAdamW:
         C.call("tb_adamw_fused_step", C.ptr(st.params), C.ptr(st.grads), C.ptr(self.exp_avg),
                C.ptr(self.exp_avg_sq), st.n_lora, st.n_rows, st.D, float(self.param_groups[1]["lr"]),
                float(self.param_groups[0]["lr"]), self.betas[0], self.betas[1], self.eps, self.weight_decay,
-               self.max_grad_norm, 1.0 / self.world_size, self.mean_norm, C.ptr(self.state),
-               C.ptr(self.added_norm), C.stream_ptr())
+               self.max_grad_norm, 1.0 / (self.world_size * self.gradient_accumulation_steps), self.mean_norm,
+               LR_SCHEDULES[self.lr_scheduler], float(self.lr_warmup_steps), float(self.max_train_steps),
+               C.ptr(self.state), C.ptr(self.added_norm), C.stream_ptr())
+
+    def get_last_lr(self):
+        """[embedding lr, LoRA lr] of the step just taken (lr_scheduler.get_last_lr of the reference, :1230); reads
+        the device state vector, i.e. synchronises."""
+        m = float(self.state[LR_MULT]) if int(self.state[STEP]) > 0 else lr_multiplier(
+            self.lr_scheduler, 0, self.lr_warmup_steps, self.max_train_steps)
+        return [g["lr"] * m for g in self.param_groups]
 
     def zero_grad(self, set_to_none: bool = True):
         """No-op: tb_adamw_fused_step consumes AND zeroes the gradient buffer."""

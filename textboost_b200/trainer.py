@@ -49,7 +49,9 @@ class TextBoostTrainer:
                  emb_learning_rate=1e-3, adam_beta1=0.9, adam_beta2=0.999, adam_weight_decay=1e-2,
                  adam_epsilon=1e-8, max_grad_norm=1.0, kpl_weight=0.1, kpl_type="cos",
                  prediction_type="epsilon", mixing=None, mean_norm: Optional[float] = None,
-                 mixed_precision="fp16", process_group=None, image_prior_weight: Optional[float] = None):
+                 mixed_precision="fp16", process_group=None, image_prior_weight: Optional[float] = None,
+                 lr_scheduler="constant", lr_warmup_steps=0, max_train_steps=0, gradient_accumulation_steps=1,
+                 num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012):
         self.unet, self.te, self.te0 = unet, text_encoder, original_text_encoder
         # --with_image_prior (train_textboost.py:1077-1094): the batch is [instance | class] halves and the loss is
         # mse(instance half) + image_prior_weight * mse(class half); None = the plain single-part loss
@@ -60,11 +62,19 @@ class TextBoostTrainer:
         assert kpl_weight <= 0 or original_text_encoder is not None
         self.sync = GradSync(process_group)
         self.world = self.sync.world
+        if gradient_accumulation_steps > 1 and self.world > 1:
+            # train_textboost.py:573-577
+            raise ValueError("Gradient accumulation is not supported when training the text encoder in distributed "
+                             "training. Please set gradient_accumulation_steps to 1.")
         self.opt = FusedAdamW(text_encoder, lr=learning_rate, emb_lr=emb_learning_rate,
                               betas=(adam_beta1, adam_beta2), weight_decay=adam_weight_decay, eps=adam_epsilon,
                               max_grad_norm=max_grad_norm, mean_norm=mean_norm, mixing=mixing,
-                              mixed_precision=mixed_precision, world_size=self.world)
-        self.acp = alphas_cumprod(device=self.dev)
+                              mixed_precision=mixed_precision, world_size=self.world, lr_scheduler=lr_scheduler,
+                              lr_warmup_steps=lr_warmup_steps, max_train_steps=max_train_steps,
+                              gradient_accumulation_steps=gradient_accumulation_steps)
+        # the checkpoint's scheduler/scheduler_config.json (DDPMScheduler.from_pretrained, train_textboost.py:644)
+        self.num_train_timesteps = int(num_train_timesteps)
+        self.acp = alphas_cumprod(self.num_train_timesteps, beta_start, beta_end, device=self.dev)
         self.loss = torch.zeros(1, device=self.dev, dtype=F32)
         self._graph = None
 
@@ -159,12 +169,17 @@ class TextBoostTrainer:
         self.opt.step()
 
     # ------------------------------------------------------------------ the step
-    def step(self, latents, noise, timesteps, input_ids, prior_ids=None):
+    def step(self, latents, noise, timesteps, input_ids, prior_ids=None, sync_gradients=True):
         """latents/noise fp32 [B,4,H,W]; timesteps int64 [B]; ids int64 [B,L].  Returns the device-side
-        loss scalar (fp32[1]); nothing is synchronised."""
+        loss scalar (fp32[1]); nothing is synchronised.
+
+        sync_gradients=False: a micro-batch of ``accelerator.accumulate`` (train_textboost.py:1039): its gradients are
+        added to the flat buffer and the all-reduce / optimiser tail are left to the micro-batch that closes the
+        window (the 1 / gradient_accumulation_steps of accelerate's backward is applied there)."""
         self.forward_backward(latents, noise, timesteps, input_ids, prior_ids)
-        self.all_reduce()
-        self.optimizer_step()
+        if sync_gradients:
+            self.all_reduce()
+            self.optimizer_step()
         return self.loss
 
     # ------------------------------------------------------------------ CUDA graph of the whole step
@@ -183,12 +198,18 @@ class TextBoostTrainer:
         with torch.cuda.graph(g):
             self.step(*static)
         self._graph = g
+        g_acc = None
+        if self.opt.gradient_accumulation_steps > 1:  # the micro-batches that only accumulate: a second graph
+            g_acc = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_acc, pool=g.pool()):
+                self.step(*static, sync_gradients=False)
+            # (capturing executes nothing: the gradient buffer is untouched)
 
-        def replay(latents, noise, timesteps, input_ids, prior_ids=None):
+        def replay(latents, noise, timesteps, input_ids, prior_ids=None, sync_gradients=True):
             for dst, src in zip(static, (latents, noise, timesteps, input_ids, prior_ids)):
                 if dst is not None and src is not None and dst.data_ptr() != src.data_ptr():
                     dst.copy_(src, non_blocking=True)
-            g.replay()
+            (g if sync_gradients or g_acc is None else g_acc).replay()
             return self.loss
 
         self.static_inputs = static

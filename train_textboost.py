@@ -143,10 +143,8 @@ def _unsupported(args):
         raise NotImplementedError("--unet_params_to_train: the UNet is frozen on this path (SURVEY.md §8 f4)")
     if args.lora_rank <= 0:
         raise NotImplementedError("--lora_rank 0 (full text-encoder fine-tune) is not built (SURVEY.md §8 f4)")
-    if args.gradient_accumulation_steps != 1:
-        raise NotImplementedError("gradient accumulation is not supported (the reference forbids it with >1 process)")
-    if args.lr_scheduler != "constant":
-        raise NotImplementedError("only the reference's constant LR schedule is built")
+    if args.gradient_accumulation_steps < 1:
+        raise ValueError("--gradient_accumulation_steps must be >= 1")
     if args.mixed_precision not in (None, "fp16"):
         raise NotImplementedError("the B200 path computes in fp16 with fp32 master weights (--mixed_precision fp16)")
     if args.text_encoder_use_attention_mask:
@@ -415,7 +413,11 @@ def main(args):
         prediction_type=sched["prediction_type"],
         mixing=("style" if args.augment_ops == "style" else "object") if args.mixing else None,
         mean_norm=mean_norm, mixed_precision=args.mixed_precision or "fp16",
-        image_prior_weight=args.image_ppl_weight if args.with_image_prior else None)
+        image_prior_weight=args.image_ppl_weight if args.with_image_prior else None,
+        lr_scheduler=args.lr_scheduler, lr_warmup_steps=args.lr_warmup_steps, max_train_steps=args.max_train_steps,
+        gradient_accumulation_steps=args.gradient_accumulation_steps,
+        num_train_timesteps=sched["num_train_timesteps"], beta_start=sched.get("beta_start", 0.00085),
+        beta_end=sched.get("beta_end", 0.012))
 
     # ---- data: the image front end (dataset -> augmentation -> VAE encoder), a latents file, or synthetic latents
     B = args.train_batch_size
@@ -524,17 +526,23 @@ def main(args):
     start = time.perf_counter()
     loss_val = float("nan")
     first = step
+    accum = args.gradient_accumulation_steps  # accelerator.accumulate (train_textboost.py:1039): one optimiser
+    micro = step * accum                      # step per `accum` dataloader batches
     while step < args.max_train_steps:
-        loss = run(*draw(step))
-        if step == first and args.max_train_steps - step > 3:
-            run = trainer.capture(*draw(step), warmup=0)
+        for k in range(accum):
+            batch = draw(micro)
+            if step == first + 1 and k == 0 and args.max_train_steps - step > 2:
+                # capture over static copies of THIS batch, then replay it: no batch is drawn and dropped
+                run = trainer.capture(*batch, warmup=0)
+            loss = run(*batch, sync_gradients=(k == accum - 1))
+            micro += 1
         step += 1
         if step % args.log_every == 0 or step == args.max_train_steps:
             loss_val = loss.item()  # the reference syncs every step (:1230); here every --log_every steps
             added_norm = trainer.added_norm.item()
-            logger.info(f"step {step} loss {loss_val:.6f} lr {args.learning_rate} "
-                        f"added_embedding_norm {added_norm:.4f}")
-            tracker.log({"loss": loss_val, "lr": args.learning_rate, "added_embedding_norm": added_norm}, step)
+            lr_now = trainer.opt.get_last_lr()[0]  # lr_scheduler.get_last_lr()[0] of the reference (:1230): group 0 = embeddings
+            logger.info(f"step {step} loss {loss_val:.6f} lr {lr_now:.3e} added_embedding_norm {added_norm:.4f}")
+            tracker.log({"loss": loss_val, "lr": lr_now, "added_embedding_norm": added_norm}, step)
         if is_main and args.validation_prompts and step % args.validation_steps == 0:  # train_textboost.py:1213-1228
             if vae is None or vae.decoder_engine is None:
                 from textboost_b200.vae import AutoencoderKL
