@@ -286,3 +286,22 @@ def test_tokenizer_is_never_a_silent_fallback(tmp_path):
     (real / "vocab.json").write_text("{}")
     with pytest.raises(OSError):
         synthetic.load_tokenizer(str(real))  # vocab.json without merges.txt
+
+
+def test_reference_import_lines_resolve_through_the_shim():
+    """/root/reference/train_textboost.py:36-41 verbatim: the `textboost` package name resolves to the B200 mirrors."""
+    from textboost.dataset import InstructPix2PixDataset, TextBoostDataset, PriorDataset, Wrapper
+    from textboost.utils import (add_augmentation_tokens, add_token, encode_prompt,
+                                 generate_prior_images,
+                                 import_model_class_from_model_name_or_path)
+    from textboost.text_encoder import TextBoostModel
+    import textboost_b200.dataset, textboost_b200.prompts, textboost_b200.text_encoder, textboost_b200.utils
+    assert TextBoostModel is textboost_b200.text_encoder.TextBoostModel
+    assert TextBoostDataset is textboost_b200.dataset.TextBoostDataset
+    assert (InstructPix2PixDataset, PriorDataset, Wrapper) == (
+        textboost_b200.prompts.HumanPromptSource, textboost_b200.prompts.PriorPrompts, textboost_b200.prompts.ShardedStream)
+    assert (add_token, add_augmentation_tokens, encode_prompt) == (
+        textboost_b200.utils.add_token, textboost_b200.utils.add_augmentation_tokens, textboost_b200.utils.encode_prompt)
+    assert import_model_class_from_model_name_or_path("x", None) is textboost_b200.text_encoder.CLIPTextModel
+    with pytest.raises(NotImplementedError):
+        generate_prior_images()
