@@ -57,6 +57,8 @@ typedef struct tb_epilogue {
   float alpha;
   int32_t act;
   int32_t out_kind;
+  int64_t ld_rowvec;    /* row stride of rowvec in elements; 0 = N.  > N: rowvec is a column slice of a wider matrix
+                           (all 22 time_emb_proj of a UNet forward are ONE GEMM, each ResnetBlock2D reads its slice) */
 } tb_epilogue;
 
 int tb_version(void);
@@ -99,12 +101,15 @@ int tb_attn_fwd_f16(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
                     float scale, int causal, void* stream);
 /* delta: workspace [B, heads, Nq] fp32.  dQacc: fp32 [B*Nq, lddq] accumulator, zeroed here and filled
  * with red.add (NULL = dQ not needed: the first cross-attention of the UNet).
+ * dQ16 (instead of dQacc, Nk <= 128 only: the 77-token cross attention and the CLIP self attention): with a single
+ * KV tile each dQ row is complete inside one CTA and is stored once as fp16 [B*Nq, lddq16] -- no accumulator, no
+ * memset, no cast afterwards.
  * dK/dV fp16 [B, Nk, ldd*] head-major columns like k/v. */
 int tb_attn_bwd_f16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                     const void* o, int64_t ldo, const void* dO, int64_t lddo, const float* lse,
-                    float* delta, float* dQacc, int64_t lddq, void* dK, int64_t lddk, void* dV,
-                    int64_t lddv, int B, int heads, int Nq, int Nk, int d, float scale, int causal,
-                    void* stream);
+                    float* delta, float* dQacc, int64_t lddq, void* dQ16, int64_t lddq16, void* dK,
+                    int64_t lddk, void* dV, int64_t lddv, int B, int heads, int Nq, int Nk, int d, float scale,
+                    int causal, void* stream);
 
 /* debug only: buf = device int64[16*8*10] receiving clock64 timestamps of CTA (0,0,0) of the following
  * tb_attn_fwd_f16 launches ([iteration][event][warp]); NULL switches it off.  Not used by the product path. */
@@ -115,6 +120,9 @@ int tb_attn_debug_trace(void* buf);
  * conv_norm_out + conv_act (inside unet(...), train_textboost.py:1063 / backward :1108).
  * x,y,dy,dx [B, HW, C] fp16; gamma/beta fp16 [C]; stats [B,G,2] fp32 = (sum x, sum x^2) written by the
  * forward and consumed by the backward; dstats [B,G,2] fp32 workspace. */
+/* `silu` is a flag word: bit 0 = fuse SiLU; TB_GN_STATS_ZEROED = the stats / dstats buffer is already zero (the caller
+ * cleared one buffer for all 61 GroupNorms of a UNet pass and hands out slices), so no memset node is enqueued. */
+#define TB_GN_STATS_ZEROED 2
 int tb_groupnorm_fwd_f16(const void* x, const void* gamma, const void* beta, void* y, float* stats, int B,
                          int HW, int C, int G, float eps, int silu, void* stream);
 /* dx = GN_backward(dy) + add  (add fp16 [B,HW,C] or NULL: the residual branch's gradient). */
@@ -130,6 +138,21 @@ int tb_layernorm_fwd(const void* x, int x_f32, int64_t ldx, const void* gamma, c
 int tb_layernorm_bwd(const void* dy, int dy_f32, int64_t lddy, const void* x, int x_f32, int64_t ldx,
                      const void* gamma, const float* stats, const void* add, void* dx, int M, int C,
                      void* stream);
+/* Text-encoder LayerNorm with the LoRA glue folded in (the CLIP layers run at M = batch x 77 rows, where every launch is
+ * latency): replaces transformers CLIPEncoderLayer.layer_norm1 followed by peft's lora_A projection
+ * (train_textboost.py:702-709 adapter, textboost/text_encoder.py:62-69 encoder call).
+ * forward: y_ext[m, :C] = fp16(LN(x[m])), y_ext[m, C + j] = fp16(sum_c y[m,c] * lora_A[j,c]) for j < R and 0 for
+ *          R <= j < RPAD -- the [LN(x) | LN(x) A^T] operand of the fused QKV GEMM.  x / gamma / beta / lora_A fp32. */
+int tb_layernorm_lora_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, void* y_ext,
+                          int64_t ldy, float* stats, const float* lora_A, int R, int RPAD, int M, int C, float eps,
+                          void* stream);
+/* backward (fp32 residual stream): dy fp16 [M, lddy] (fp32 when dy_f32) ; with lora_A (fp32 [R, C]) the extension
+ * columns dy[m, C + j] are the gradient of the LoRA down-projection and dy_eff = dy[:, :C] + dy[:, C:C+R] lora_A;
+ * dx = LN_backward(dy_eff) + add (add NULL or aliasing dx); dx_f16 (NULL or fp16 [M, C]) receives fp16(dx), the A
+ * operand of the next input-gradient GEMM. */
+int tb_layernorm_bwd_clip(const void* dy, int dy_f32, int64_t lddy, const float* x, int64_t ldx, const float* gamma,
+                          const float* stats, const float* add, float* dx, void* dx_f16, const float* lora_A, int R,
+                          int M, int C, void* stream);
 
 /* ---- elementwise / data movement (HBM-bound) -------------------------------------------------- */
 /* diffusers GEGLU: out[M,F] = h[:, :F] * gelu(h[:, F:]);  backward gives dh [M,2F]. */
@@ -141,6 +164,10 @@ int tb_upsample2x_bwd_f16(const void* dy, void* dx, int B, int H, int W, int C, 
 /* dst[r, :cols] (=|+=) src[r, :cols] with row strides: skip-connection concat / split / residual adds. */
 int tb_copy2d_f16(void* dst, int64_t ldd, const void* src, int64_t lds, int64_t rows, int cols,
                   int accumulate, void* stream);
+/* dst[r, :] = [a[r, :Ca] | b[r, :Cb]] for fp16 rows with free row strides: torch.cat([hidden_states, res_hidden_states],
+ * dim=1) of diffusers' up blocks on channels-last rows, one launch. */
+int tb_concat2_f16(void* dst, int64_t ldd, const void* a, int64_t lda, int Ca, const void* b, int64_t ldb, int Cb,
+                   int64_t rows, void* stream);
 int tb_cast_f32_f16(void* dst, int64_t ldd, const void* src, int64_t lds, int64_t rows, int cols,
                     float scale, void* stream);
 /* Downsample2D (conv3x3 stride 2 pad 1): forward = im2col + tb_gemm_f16; backward = zero-stuff +

@@ -87,7 +87,7 @@ def attn_fwd(q, k, v, heads, scale=None, out=None, causal=False):
     return o, lse.contiguous()
 
 
-def attn_bwd(q, k, v, o, do, lse, heads, scale=None, need_dq=True, dk=None, dv=None, causal=False):
+def attn_bwd(q, k, v, o, do, lse, heads, scale=None, need_dq=True, dk=None, dv=None, causal=False, dq_out=None):
     B, Nq, Ch = q.shape
     d = Ch // heads
     scale = d ** -0.5 if scale is None else scale
@@ -99,6 +99,13 @@ def attn_bwd(q, k, v, o, do, lse, heads, scale=None, need_dq=True, dk=None, dv=N
         out = (torch.softmax(s, -1) @ _heads(vf, heads)).transpose(1, 2).reshape(B, Nq, Ch)
         out.backward(do.float())
     dq = qf.grad.contiguous() if need_dq else None
+    if dq_out is not None and dq_out is not False:  # the single-KV-tile contract: fp16 dQ written once, in place
+        assert need_dq and k.shape[1] <= 128
+        if dq_out is True:
+            dq = dq.to(F16)
+        else:
+            dq_out.copy_(dq)
+            dq = dq_out
     gk, gv = kf.grad.to(F16), vf.grad.to(F16)
     if dk is not None:
         dk.copy_(gk)

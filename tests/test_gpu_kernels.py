@@ -7,6 +7,8 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+from textboost_b200 import _cabi as C
+
 pytestmark = pytest.mark.gpu
 
 dev = "cuda"
@@ -241,6 +243,19 @@ def test_attention_fwd_bwd(B, H, Nq, Nk, d):
     dq2, dk2, dv2 = ops.attn_bwd(q, k, v, o, do, lse, H, need_dq=False)  # first cross-attention: dK/dV only
     # (under-filled grids split the Q loop over CTAs that meet in fp32 red.adds: equal up to summation order)
     assert dq2 is None and relerr(dk2, dk) < 1e-3 and relerr(dv2, dv) < 1e-3
+    if Nk <= 128:
+        # a single KV tile: dQ stored once as fp16, here into a strided view (as the fused gradient tensor is)
+        buf = torch.full((B, Nq, Cc + 8), 7.0, device=dev, dtype=F16)
+        dq3, dk3, dv3 = ops.attn_bwd(q, k, v, o, do, lse, H, dq_out=buf[..., :Cc])
+        assert dq3.dtype == F16 and dq3.data_ptr() == buf.data_ptr() and bool((buf[..., Cc:] == 7.0).all())
+        assert relerr(dq3, qr.grad.transpose(1, 2).reshape(B, Nq, Cc)) < TOL_ATTN
+        assert relerr(dq3, dq) < 2e-3 and relerr(dk3, dk) < 1e-3 and relerr(dv3, dv) < 1e-3
+    else:
+        with pytest.raises(RuntimeError, match="dQ16 needs Nk <= 128"):
+            C.call("tb_attn_bwd_f16", C.ptr(q), q.stride(1), C.ptr(k), k.stride(1), C.ptr(v), v.stride(1), C.ptr(o),
+                   o.stride(1), C.ptr(do), do.stride(1), C.ptr(lse), C.ptr(torch.empty(B, H, Nq, device=dev)), None, 0,
+                   C.ptr(torch.empty(B, Nq, Cc, device=dev, dtype=F16)), Cc, C.ptr(dk), dk.stride(1), C.ptr(dv),
+                   dv.stride(1), B, H, Nq, Nk, d, d ** -0.5, 0, C.stream_ptr())
 
 
 @pytest.mark.parametrize("d", [40, 80])
@@ -291,6 +306,53 @@ def test_attention_causal(B, H, N, d):
     assert relerr(dq, qr.grad.transpose(1, 2).reshape(B, N, Cc)) < TOL_ATTN
     assert relerr(dk, kr.grad.transpose(1, 2).reshape(B, N, Cc)) < TOL_ATTN
     assert relerr(dv, vr.grad.transpose(1, 2).reshape(B, N, Cc)) < TOL_ATTN
+    if N <= 128:  # the text encoder's case: dQ written as fp16 straight into the fused [dq | dk | dv] tensor
+        dqkv = torch.zeros_like(qkv)
+        dq16, _, _ = ops.attn_bwd(q, k, v, o, do, lse, H, causal=True, dk=dqkv[..., Cc:2 * Cc], dv=dqkv[..., 2 * Cc:],
+                                  dq_out=dqkv[..., :Cc])
+        assert relerr(dqkv[..., :Cc], qr.grad.transpose(1, 2).reshape(B, N, Cc)) < TOL_ATTN
+        assert relerr(dqkv[..., Cc:2 * Cc], dk) < 1e-3 and relerr(dqkv[..., 2 * Cc:], dv) < 1e-3
+
+
+@pytest.mark.parametrize("M,D,R,RPAD", [(616, 768, 12, 16), (77, 1024, 48, 48), (19, 768, 4, 16), (1232, 768, 64, 64)])
+def test_text_encoder_layernorm_with_lora_glue(M, D, R, RPAD):
+    """tb_layernorm_lora_fwd / tb_layernorm_bwd_clip against torch: LayerNorm on the fp32 residual stream with the LoRA
+    down-projection (forward) and its input-gradient + the fp16 copy of dx (backward) in the same launch."""
+    from textboost_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(M + D + R)
+    x = torch.randn(M, D, device=dev, generator=g) * 2 + 0.3
+    gamma = torch.randn(D, device=dev, generator=g)
+    beta = torch.randn(D, device=dev, generator=g)
+    A = torch.randn(R, D, device=dev, generator=g) / R
+    y_ext = torch.full((M, D + RPAD + 8), 5.0, device=dev, dtype=F16)
+    stats = ops.layernorm_lora_fwd(x, gamma, beta, A, y_ext, RPAD)
+    yref = F.layer_norm(x, (D,), gamma, beta)
+    assert relerr(y_ext[:, :D], yref) < 1e-3
+    xa = y_ext[:, :D].float() @ A.t()
+    assert relerr(y_ext[:, D:D + R], xa) < 2e-3
+    assert bool((y_ext[:, D + R:D + RPAD] == 0).all()) and bool((y_ext[:, D + RPAD:] == 5.0).all())
+    torch.testing.assert_close(stats[:, 0], x.mean(-1), rtol=1e-4, atol=1e-5)
+    # backward: dy_ext = [dy | dxa] fp16, residual-stream gradient g32 added, fp16 copy written
+    dy_ext = torch.randn(M, D + RPAD, device=dev, dtype=F16, generator=g)
+    add = torch.randn(M, D, device=dev, generator=g)
+    xr = x.clone().requires_grad_(True)
+    dy_eff = dy_ext[:, :D].float() + dy_ext[:, D:D + R].float() @ A
+    F.layer_norm(xr, (D,), gamma, beta).backward(dy_eff)
+    out16 = torch.empty(M, D, device=dev, dtype=F16)
+    buf = add.clone()
+    dx = ops.layernorm_bwd_clip(dy_ext, x, gamma, stats, add=buf, out=buf, out16=out16, lora_a=A)
+    assert dx.data_ptr() == buf.data_ptr()
+    torch.testing.assert_close(dx, xr.grad + add, rtol=2e-4, atol=2e-4)
+    torch.testing.assert_close(out16.float(), dx, rtol=1e-3, atol=1e-3)
+    # plain variants: fp32 dy (final LayerNorm), no LoRA, no add, no fp16 copy
+    dy32 = torch.randn(M, D, device=dev, generator=g)
+    xr2 = x.clone().requires_grad_(True)
+    F.layer_norm(xr2, (D,), gamma, beta).backward(dy32)
+    torch.testing.assert_close(ops.layernorm_bwd_clip(dy32, x, gamma, stats), xr2.grad, rtol=2e-4, atol=2e-4)
+    dx3 = ops.layernorm_bwd_clip(dy_ext[:, :D], x, gamma, stats, out16=out16)
+    xr3 = x.clone().requires_grad_(True)
+    F.layer_norm(xr3, (D,), gamma, beta).backward(dy_ext[:, :D].float())
+    torch.testing.assert_close(dx3, xr3.grad, rtol=2e-4, atol=2e-4)
 
 
 @pytest.mark.parametrize("B,HW,Cc,silu", [(2, 64, 64, True), (2, 4096, 320, True), (3, 1024, 640, False),

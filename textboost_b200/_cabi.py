@@ -30,6 +30,7 @@ class Epilogue(Structure):
         ("alpha", c_float),
         ("act", c_int32),
         ("out_kind", c_int32),
+        ("ld_rowvec", c_int64),
     ]
 
 
@@ -48,19 +49,24 @@ _SIGNATURES = {
     "tb_attn_fwd_f16": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                         c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
     "tb_attn_bwd_f16": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
-                        c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                        c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                         c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
     "tb_attn_debug_trace": [c_void_p],
     "tb_groupnorm_fwd_f16": [c_void_p] * 5 + [c_int] * 4 + [c_float, c_int, c_void_p],
     "tb_groupnorm_bwd_f16": [c_void_p] * 8 + [c_int] * 4 + [c_float, c_int, c_void_p],
     "tb_layernorm_fwd": [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int64,
                          c_void_p, c_int, c_int, c_float, c_void_p],
+    "tb_layernorm_lora_fwd": [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int,
+                              c_int, c_int, c_float, c_void_p],
+    "tb_layernorm_bwd_clip": [c_void_p, c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "tb_layernorm_bwd": [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p,
                          c_void_p, c_int, c_int, c_void_p],
     "tb_geglu_fwd_f16": [c_void_p, c_void_p, c_int64, c_int, c_void_p],
     "tb_geglu_bwd_f16": [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p],
     "tb_upsample2x_fwd_f16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "tb_upsample2x_bwd_f16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "tb_concat2_f16": [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int64, c_void_p],
     "tb_copy2d_f16": [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p],
     "tb_cast_f32_f16": [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_float, c_void_p],
     "tb_im2col3x3s2_f16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
@@ -138,6 +144,7 @@ _KERNELS_PER_CALL = {"tb_groupnorm_fwd_f16": 2, "tb_groupnorm_bwd_f16": 2, "tb_a
                      "tb_resize_crop_normalize_u8": 2,
                      "tb_adamw_fused_step": 3, "tb_version": 0, "tb_check_device": 0, "tb_set_workspace": 0,
                      "tb_attn_debug_trace": 0}
+TB_GN_STATS_ZEROED = 2
 launch_count = 0  # GPU launches enqueued through this binding since import (bench.py reports the delta)
 
 

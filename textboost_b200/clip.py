@@ -230,9 +230,11 @@ class ClipEngine:
         saved = []
         for l, L in enumerate(self.layers):
             y_ext = torch.empty((M, self.Kext), device=self.device, dtype=F16)
-            _, st1 = ops.layernorm(x, *L["ln1"], eps=self.cfg.layer_norm_eps, out=y_ext[:, :D])
-            if self.Tq:
-                C.call("tb_lora_down", C.ptr(y_ext), self.Kext, C.ptr(st.A(l)), M, D, self.Tq * self.r, self.Rq, s)
+            if self.Tq:  # LayerNorm and the LoRA down-projection [LN(x) | LN(x) A^T] in one launch
+                st1 = ops.layernorm_lora_fwd(x, *L["ln1"], st.A(l)[:self.Tq * self.r], y_ext, self.Rq,
+                                             eps=self.cfg.layer_norm_eps)
+            else:
+                _, st1 = ops.layernorm(x, *L["ln1"], eps=self.cfg.layer_norm_eps, out=y_ext[:, :D])
             qkv = ops.gemm(y_ext, L["wqkv"], bias=L["bqkv"])
             # causal softmax(QK^T/sqrt(64))V on the tcgen05 flash kernels, reading q/k/v in place from the fused
             # projection output (transformers CLIPAttention under the causal mask, text_encoder.py:62-69)
@@ -245,6 +247,8 @@ class ClipEngine:
                 C.call("tb_lora_down", C.ptr(o), self.Ko, C.ptr(st.A(l)[self.Tq * self.r:]), M, D, self.r, self.Ro, s)
             x2 = ops.gemm(o, L["wo"], bias=L["bo"], residual=x, out_kind=C.TB_OUT_F32)
             y2, st2 = ops.layernorm(x2, *L["ln2"], eps=self.cfg.layer_norm_eps)
+            # (activation NOT fused into the fc1 epilogue: measured, the per-element exp / erf in the GEMM's 8 epilogue
+            # warps costs ~11 us per launch against ~4 us for the separate full-occupancy kernel)
             u = ops.gemm(y2, L["wf1"], bias=L["bf1"])
             a = torch.empty_like(u)
             C.call("tb_act_fwd_f16", C.ptr(u), C.ptr(a), u.numel(), self.act, s)
@@ -281,17 +285,18 @@ class ClipEngine:
         d_out = d_out.contiguous().view(M, D)
         C.call("tb_null_override", C.ptr(ids), None, C.ptr(d_out), B, Lq, D, EOS_ID,
                int(self.use_fixed_special), 1, s)
-        g = ops.layernorm_bwd(d_out, xf, self.lnf[0], stf)
+        # every LayerNorm backward also writes the fp16 copy of its result: the next dgrad GEMM's operand
+        g16 = torch.empty((M, D), device=self.device, dtype=F16)
+        g = ops.layernorm_bwd_clip(d_out, xf, self.lnf[0], stf, out16=g16)
         for l in reversed(range(self.nl)):
             L = self.layers[l]
             x, st1, y_ext, qkv, x2, st2, u, o, lse = saved[l]
-            g16 = ops.cast_f32_f16(g)
             da = ops.gemm(g16, L["wf2_t"])
             du = torch.empty_like(da)
             C.call("tb_act_bwd_f16", C.ptr(u), C.ptr(da), C.ptr(du), u.numel(), self.act, s)
             dy2 = ops.gemm(du, L["wf1_t"])
-            g = ops.layernorm_bwd(dy2, x2, L["ln2"][0], st2, add=g, out=g)
-            g16 = ops.cast_f32_f16(g)
+            g16 = torch.empty((M, D), device=self.device, dtype=F16)
+            g = ops.layernorm_bwd_clip(dy2, x2, L["ln2"][0], st2, add=g, out=g, out16=g16)
             do = ops.gemm(g16, L["wo_t"])  # [M, Ko]: d(o) and, in the extension columns, d(o A_o^T)
             if self.has_o:
                 ro = self.Tq * self.r
@@ -300,17 +305,21 @@ class ClipEngine:
                 C.call("tb_lora_dx", C.ptr(do), self.Ko, C.ptr(st.A(l)[ro:]), M, D, self.r, s)
             dqkv = torch.empty_like(qkv)
             q3, d3 = qkv.view(B, Lq, 3 * D), dqkv.view(B, Lq, 3 * D)
-            dq, _, _ = ops.attn_bwd(q3[..., :D], q3[..., D:2 * D], q3[..., 2 * D:], o.view(B, Lq, self.Ko)[..., :D],
-                                    do.view(B, Lq, self.Ko)[..., :D], lse, self.heads, dk=d3[..., D:2 * D],
-                                    dv=d3[..., 2 * D:], causal=True)
-            ops.cast_f32_f16(dq.view(M, D), out=dqkv[:, :D])
+            # 77 tokens = one KV tile: dQ is written once, as fp16, straight into the fused gradient tensor
+            ops.attn_bwd(q3[..., :D], q3[..., D:2 * D], q3[..., 2 * D:], o.view(B, Lq, self.Ko)[..., :D],
+                         do.view(B, Lq, self.Ko)[..., :D], lse, self.heads, dk=d3[..., D:2 * D],
+                         dv=d3[..., 2 * D:], causal=True, dq_out=d3[..., :D])
             dy_ext = ops.gemm(dqkv, L["wqkv_t"])
+            g16 = torch.empty((M, D), device=self.device, dtype=F16) if l else None
             if self.Tq:
                 C.call("tb_lora_grad", C.ptr(dqkv), C.ptr(y_ext), C.ptr(dy_ext), self.Kext,
                        C.ptr(st.B(l, st.grads)), C.ptr(st.A(l, st.grads)), M, 3, self.qkv_mask, D, self.r,
                        self.scaling, s)
-                C.call("tb_lora_dx", C.ptr(dy_ext), self.Kext, C.ptr(st.A(l)), M, D, self.Tq * self.r, s)
-            g = ops.layernorm_bwd(dy_ext[:, :D], x, L["ln1"][0], st1, add=g, out=g)
+                # the down-projection's input-gradient (dy += dxa A) rides on the LayerNorm backward
+                g = ops.layernorm_bwd_clip(dy_ext, x, L["ln1"][0], st1, add=g, out=g, out16=g16,
+                                           lora_a=st.A(l)[:self.Tq * self.r])
+            else:
+                g = ops.layernorm_bwd_clip(dy_ext[:, :D], x, L["ln1"][0], st1, add=g, out=g, out16=g16)
             saved[l] = None
         if st.n_rows:
             C.call("tb_clip_embed_grad", C.ptr(ids), C.ptr(g), C.ptr(st.rows(st.grads)), M, D, self.n_base, s)

@@ -44,6 +44,8 @@ struct AttnParams {
   const float* delta;        // bwd: [B, heads, Nq] rowsum(dO * O)
   float* dQacc;              // bwd: fp32 [B, Nq, lddq] accumulated with red.add (may be null)
   long long lddq;
+  __half* dQ16;              // bwd, single KV tile (Nk <= 128): dQ written once as fp16 [B, Nq, lddq16] (no accumulator)
+  long long lddq16;
   __half* dK;                // bwd: [B, Nk, lddk] head h at h*d
   long long lddk;
   __half* dV;
@@ -1309,7 +1311,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           umma_f16_ss(tmem + DK_COL, umma_desc_pack(pt_lo + offp, hi), umma_desc_pack(q_mn + ks * 128, hi),
                       idesc_acc, (it > 0) || (ks > 0));
         }
-        if (p.dQacc) {
+        if (p.dQacc || p.dQ16) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {  // dQ_i = dS K   (A: [kv][q] read MN-major)
             umma_f16_ss(tmem + X_COL, umma_desc_pack(ds_mn + ks * 128, hi), umma_desc_pack(k_mn + ks * 128, hi),
@@ -1319,7 +1321,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         umma_commit(smem_u32(bar_dq));
       }
       __syncwarp();
-      if (p.dQacc && dq_n1 > 0) {
+      if ((p.dQacc || p.dQ16) && dq_n1 > 0) {
         // columns 128..dn of dQ reuse X once the first 128 have been drained
         mbar_wait(smem_u32(bar_dqfree), ph_dqfree);
         ph_dqfree ^= 1;
@@ -1428,7 +1430,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_before();
       mbar_arrive(smem_u32(bar_ds));
 
-      const int n_chunks = (p.dQacc && p.dn > 128) ? 2 : 1;
+      const int n_chunks = ((p.dQacc || p.dQ16) && p.dn > 128) ? 2 : 1;
       for (int ch = 0; ch < n_chunks; ++ch) {
         mbar_wait(smem_u32(bar_dq), ph_dq);
         ph_dq ^= 1;
@@ -1470,6 +1472,30 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                                "f"(even ? rc[0] : hi[0]), "f"(even ? rc[1] : hi[1]), "f"(even ? rc[2] : hi[2]),
                                "f"(even ? rc[3] : hi[3])
                                : "memory");
+              }
+            }
+          }
+        } else if (p.dQ16) {
+          // single KV tile: this CTA holds the whole dQ row -> one fp16 store, no accumulator, no memset, no cast
+          const int q = q0 + row;
+          const int cbase = ch * 128;
+          __half* dq = p.dQ16 + ((long long)b * p.Nq + q) * p.lddq16 + h * p.d + cbase;
+          const int ncols = (p.dn - cbase) > 128 ? 128 : (p.dn - cbase);
+          for (int c = half * 16; c < ncols; c += 32) {
+            uint32_t r[16];
+            tmem_ld16(lane_addr + X_COL + c, r);
+            tmem_ld_wait();
+            if (q < p.Nq) {
+#pragma unroll
+              for (int gp = 0; gp < 2; ++gp) {
+                if (cbase + c + gp * 8 < p.d) {
+                  uint4 o;
+                  o.x = pack_half2(__uint_as_float(r[gp * 8 + 0]) * p.scale, __uint_as_float(r[gp * 8 + 1]) * p.scale);
+                  o.y = pack_half2(__uint_as_float(r[gp * 8 + 2]) * p.scale, __uint_as_float(r[gp * 8 + 3]) * p.scale);
+                  o.z = pack_half2(__uint_as_float(r[gp * 8 + 4]) * p.scale, __uint_as_float(r[gp * 8 + 5]) * p.scale);
+                  o.w = pack_half2(__uint_as_float(r[gp * 8 + 6]) * p.scale, __uint_as_float(r[gp * 8 + 7]) * p.scale);
+                  *reinterpret_cast<uint4*>(dq + c + gp * 8) = o;
+                }
               }
             }
           }
@@ -2107,7 +2133,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           for (int ks = 0; ks < 8; ++ks)
             umma_f16_ss(tmem + DK_COL, umma_desc_pack(ds_mn + ks * 128, hi), umma_desc_pack(q_mn + ks * 128, hi),
                         idesc_acc, (it > 0) || (ks > 0));
-          if (p.dQacc) {
+          if (p.dQacc || p.dQ16) {
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
               const uint32_t off = ((ks >> 2) * ABOX + (ks & 3) * 32) >> 4;
@@ -2188,12 +2214,32 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // dQ(it): each warp owns a [32 rows x 16 columns] block of the tile: TMEM -> its own 2 KB of staging -> (after the
     // proxy fence) two TMA reduce-adds of [32 x 8] floats.  Only __syncwarp is needed: lane 0 issued the previous
     // reduce-adds of this block and waits until they have read the staging block before the warp overwrites it.
-    const bool dq_warp = p.dQacc != nullptr && cg * 16 < p.dn;
+    const bool dq_warp = (p.dQacc != nullptr || p.dQ16 != nullptr) && cg * 16 < p.dn;
     const uint32_t sdq_warp = smem_u32(sDQ) + (uint32_t)warp * 2048;  // [2 column groups][32 rows][8 floats]
     auto dq_to_staging = [&](int it) {
       mbar_wait(smem_u32(bar_dq), it & 1);  // dK / dQ of that pair retired (also: the dS tile may be overwritten)
       tc_fence_after();
-      if (dq_warp) {
+      if (dq_warp && p.dQ16) {
+        // single KV tile (cross attention): the tile's dQ is complete -> fp16 rows straight to global memory
+        uint32_t r[16];
+        tmem_ld16(lane_addr + DQ_COL + cg * 16, r);
+        tmem_ld_wait();
+        const int q = (i_begin + it) * 128 + row;
+        if (q < p.Nq) {
+          __half* dq = p.dQ16 + ((long long)b * p.Nq + q) * p.lddq16 + h * p.d + cg * 16;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (cg * 16 + g * 8 < p.d) {
+              uint4 o;
+              o.x = pack_half2(__uint_as_float(r[g * 8 + 0]) * p.scale, __uint_as_float(r[g * 8 + 1]) * p.scale);
+              o.y = pack_half2(__uint_as_float(r[g * 8 + 2]) * p.scale, __uint_as_float(r[g * 8 + 3]) * p.scale);
+              o.z = pack_half2(__uint_as_float(r[g * 8 + 4]) * p.scale, __uint_as_float(r[g * 8 + 5]) * p.scale);
+              o.w = pack_half2(__uint_as_float(r[g * 8 + 6]) * p.scale, __uint_as_float(r[g * 8 + 7]) * p.scale);
+              *reinterpret_cast<uint4*>(dq + g * 8) = o;
+            }
+          }
+        }
+      } else if (dq_warp) {
         uint32_t r[16];
         tmem_ld16(lane_addr + DQ_COL + cg * 16, r);
         tmem_ld_wait();
@@ -2212,7 +2258,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_arrive(smem_u32(bar_dqfree));
     };
     auto dq_reduce = [&](int it) {  // after fence.proxy.async
-      if (!dq_warp) return;
+      if (!dq_warp || p.dQ16) return;
       __syncwarp();
       if (lane == 0) {
 #pragma unroll
@@ -2535,9 +2581,9 @@ extern "C" int tb_attn_fwd_f16(const void* q, int64_t ldq, const void* k, int64_
 
 extern "C" int tb_attn_bwd_f16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                                int64_t ldv, const void* o, int64_t ldo, const void* dO, int64_t lddo,
-                               const float* lse, float* delta, float* dQacc, int64_t lddq, void* dK,
-                               int64_t lddk, void* dV, int64_t lddv, int B, int heads, int Nq, int Nk,
-                               int d, float scale, int causal, void* stream) {
+                               const float* lse, float* delta, float* dQacc, int64_t lddq, void* dQ16,
+                               int64_t lddq16, void* dK, int64_t lddk, void* dV, int64_t lddv, int B, int heads,
+                               int Nq, int Nk, int d, float scale, int causal, void* stream) {
   int rc = tb_check_device();
   if (rc) return rc;
   TB_REQUIRE(q && k && v && o && dO && lse && delta && dK && dV, TB_E_ARG, "tb_attn_bwd_f16: null pointer");
@@ -2546,6 +2592,10 @@ extern "C" int tb_attn_bwd_f16(const void* q, int64_t ldq, const void* k, int64_
   TB_REQUIRE(ldo % 8 == 0 && lddo % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0 && lddq % 4 == 0,
              TB_E_ALIGN, "tb_attn_bwd_f16: stride alignment");
   TB_REQUIRE(heads * d <= 1280, TB_E_SHAPE, "tb_attn_bwd_f16: heads*d = %d > 1280", heads * d);
+  // dQ16: with a single KV tile every dQ row is complete inside one CTA, so it is stored once as fp16 and the fp32
+  // accumulator (its memset, the reduce-adds and the cast that followed) is not needed
+  TB_REQUIRE(!dQ16 || (!dQacc && Nk <= 128 && lddq16 % 8 == 0 && d % 8 == 0), TB_E_ARG,
+             "tb_attn_bwd_f16: dQ16 needs Nk <= 128 (Nk=%d), no dQacc, lddq16 %% 8 == 0", Nk);
   cudaStream_t st = (cudaStream_t)stream;
   {
     const long long rows = (long long)B * Nq;
@@ -2573,6 +2623,7 @@ extern "C" int tb_attn_bwd_f16(const void* q, int64_t ldq, const void* k, int64_
   p.lse = const_cast<float*>(lse);
   p.delta = delta;
   p.dQacc = dQacc; p.lddq = lddq;
+  p.dQ16 = (__half*)dQ16; p.lddq16 = lddq16;
   p.dK = (__half*)dK; p.lddk = lddk;
   p.dV = (__half*)dV; p.lddv = lddv;
   p.n_inner = (Nq + 127) / 128;
@@ -2611,7 +2662,7 @@ extern "C" int tb_attn_bwd_f16(const void* q, int64_t ldq, const void* k, int64_
   static const bool v1 = getenv("TB_ATTN_BWD_V1") != nullptr;  // diagnostic switch: the two-CTA-per-SM kernel
   static const bool v2 = getenv("TB_ATTN_BWD_V2") != nullptr;  // diagnostic switch: the transposed-score kernel
   if (nb == 1 && !causal && !v1 && !v2) rc = launch_attn_bwd3(tq, tk, tv, tdo, p, B, st);
-  else if (nb == 1 && !causal && !v1) rc = launch_attn_bwd2(tq, tk, tv, tdo, p, B, st);
+  else if (nb == 1 && !causal && !v1 && !dQ16) rc = launch_attn_bwd2(tq, tk, tv, tdo, p, B, st);
   else if (nb == 1) rc = launch_attn_bwd<1, 1>(tq, tk, tv, tdo, p, B, st);
   else if (nb == 2) rc = launch_attn_bwd<2, 1>(tq, tk, tv, tdo, p, B, st);
   else rc = launch_attn_bwd<3, 1>(tq, tk, tv, tdo, p, B, st);

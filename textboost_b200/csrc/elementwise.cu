@@ -142,6 +142,21 @@ __global__ void copy2d_kernel(__half* __restrict__ dst, long long ldd, const __h
   }
 }
 
+// dst[r, :] = [a[r, :Ca] | b[r, :Cb]]   (torch.cat([hidden, skip], dim=1) of the up blocks: one launch, not two)
+__global__ void concat2_kernel(__half* __restrict__ dst, long long ldd, const __half* __restrict__ a, long long lda,
+                               int Ca, const __half* __restrict__ b, long long ldb, int Cb, long long rows) {
+  const int va = Ca / 8, cv = (Ca + Cb) / 8;
+  const long long total = rows * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cv;
+    const int v = (int)(i % cv);
+    const uint4 q = v < va ? *reinterpret_cast<const uint4*>(a + r * lda + v * 8)
+                           : *reinterpret_cast<const uint4*>(b + r * ldb + (v - va) * 8);
+    *reinterpret_cast<uint4*>(dst + r * ldd + v * 8) = q;
+  }
+}
+
 __global__ void cast_f32_f16_kernel(__half* __restrict__ dst, long long ldd, const float* __restrict__ src,
                                     long long lds, long long rows, int cols, float scale) {
   const int cv = cols / 8;
@@ -440,6 +455,16 @@ extern "C" int tb_copy2d_f16(void* dst, int64_t ldd, const void* src, int64_t ld
   copy2d_kernel<<<grid_for(rows * (cols / 8), 256), 256, 0, st>>>((__half*)dst, ldd, (const __half*)src,
                                                                  lds, rows, cols, accumulate);
   return check_launch("copy2d_kernel");
+}
+extern "C" int tb_concat2_f16(void* dst, int64_t ldd, const void* a, int64_t lda, int Ca, const void* b, int64_t ldb,
+                              int Cb, int64_t rows, void* stream) {
+  TB_ENTER();
+  TB_REQUIRE(dst && a && b && Ca > 0 && Cb > 0 && Ca % 8 == 0 && Cb % 8 == 0 && ldd % 8 == 0 && lda % 8 == 0 &&
+                 ldb % 8 == 0 && ldd >= Ca + Cb,
+             TB_E_ALIGN, "tb_concat2_f16: widths / strides must be multiples of 8 and ldd >= Ca + Cb");
+  concat2_kernel<<<grid_for(rows * ((Ca + Cb) / 8), 256), 256, 0, st>>>((__half*)dst, ldd, (const __half*)a, lda, Ca,
+                                                                       (const __half*)b, ldb, Cb, rows);
+  return check_launch("concat2_kernel");
 }
 extern "C" int tb_cast_f32_f16(void* dst, int64_t ldd, const void* src, int64_t lds, int64_t rows,
                                int cols, float scale, void* stream) {

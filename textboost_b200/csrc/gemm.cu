@@ -33,6 +33,7 @@ struct GemmParams {
   long long ldc;
   const __half* bias;
   const __half* rowvec;
+  long long ldrv;     // row stride of rowvec (>= N: a column slice of one batched time-embedding projection)
   int rows_per_group;
   const void* residual;
   long long ldr;
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
           float bv = p.bias ? __half2float(p.bias[ncol0 + epi_tid]) : 0.f;
           if (p.rowvec)
             bv += __half2float(
-                p.rowvec[((long long)m_tile * p.tile_rows / p.rows_per_group) * p.N + ncol0 + epi_tid]);
+                p.rowvec[((long long)m_tile * p.tile_rows / p.rows_per_group) * p.ldrv + ncol0 + epi_tid]);
           sBV[epi_tid] = bv;
         }
         uint4 rq[4], rq_next[4];
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
       const uint32_t acc_addr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
       const bool row_ok = m < p.M && row < p.tile_rows;
       const __half* rv = nullptr;
-      if (p.rowvec && row_ok) rv = p.rowvec + (m / p.rows_per_group) * (long long)p.N;
+      if (p.rowvec && row_ok) rv = p.rowvec + (m / p.rows_per_group) * p.ldrv;
       const __half* res = nullptr;
       const float* res32 = nullptr;
       if (p.residual && row_ok) {
@@ -525,7 +526,8 @@ static void plan_split(GemmParams& p, int bn, int tiles, cudaStream_t st) {
   // Measured (scripts/probe_small_gemm.py): the fix-up (partials to L2, __threadfence, counter round trip, the
   // last CTA re-reading splits x 64 KB) costs ~8-15 us, so splitting only pays for very long K loops -- the 3x3
   // convolutions of the 8x8 / 16x16 levels (180-360 k-blocks: 80 -> 32 us).  GEMMs with K <= 5120 lose.
-  if (off || !w || tiles * 2 > num_sms() || p.num_kb < 128) return;
+  static const int min_kb = getenv("TB_GEMM_SPLITK_MIN_KB") ? atoi(getenv("TB_GEMM_SPLITK_MIN_KB")) : 128;  // tuning knob
+  if (off || !w || tiles * 2 > num_sms() || p.num_kb < min_kb) return;
   int s = num_sms() / tiles;
   if (s > p.num_kb / 4) s = p.num_kb / 4;
   if (s > 16) s = 16;
@@ -588,6 +590,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 static int pick_bn(int N, int m_tiles, int num_kb) {
   static const int cands[4] = {256, 160, 128, 64};
   const int sms = num_sms();
+  static const int forced = getenv("TB_GEMM_BN") ? atoi(getenv("TB_GEMM_BN")) : 0;  // tuning knob
+  if (forced && N % forced == 0) return forced;
   int best = 0;
   long long best_cost = 0;
   for (int i = 0; i < 4; ++i) {
@@ -659,6 +663,7 @@ static int fill_epilogue(GemmParams& p, void* C, long long ldc, const tb_epilogu
     p.bias = reinterpret_cast<const __half*>(ep->bias);
     p.rowvec = reinterpret_cast<const __half*>(ep->rowvec);
     p.rows_per_group = ep->rows_per_group > 0 ? ep->rows_per_group : 1;
+    p.ldrv = ep->ld_rowvec > 0 ? ep->ld_rowvec : 0;
     p.residual = ep->residual;
     p.ldr = ep->ldr;
     p.res_f32 = ep->residual_f32;
@@ -672,6 +677,9 @@ static int fill_epilogue(GemmParams& p, void* C, long long ldc, const tb_epilogu
     TB_REQUIRE(((uintptr_t)p.bias | (uintptr_t)p.rowvec | (uintptr_t)p.residual) % 16 == 0,
                TB_E_ALIGN, "epilogue: bias/rowvec/residual must be 16-byte aligned");
   }
+  if (p.ldrv == 0) p.ldrv = p.N;
+  TB_REQUIRE(!p.rowvec || (p.ldrv >= p.N && p.ldrv % 8 == 0), TB_E_ALIGN,
+             "epilogue: ld_rowvec must be >= N and a multiple of 8 (%lld)", p.ldrv);
   const int esz = p.out_kind == TB_OUT_F16 ? 2 : 4;
   TB_REQUIRE(((uintptr_t)C % 16 == 0) && ((ldc * esz) % 16 == 0), TB_E_ALIGN,
              "output pointer / ldc not 16-byte aligned");

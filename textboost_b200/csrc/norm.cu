@@ -429,6 +429,163 @@ __global__ void ln_bwd_kernel(const DYT* __restrict__ dy, long long lddy, const 
   }
 }
 
+// ---------------------------------------------------------------------------------- text-encoder LayerNorm + LoRA
+// The CLIP layers run at M = batch x 77 rows: every launch is latency, not bandwidth, so the LoRA glue that used to be
+// separate launches rides on the LayerNorm kernels (one warp per row, the row in registers).
+//
+// forward:  y_ext[m, :C] = fp16(LN(x[m]))  and  y_ext[m, C + j] = fp16(sum_c y[m,c] * A[j,c]) for j < R (0 for
+//           R <= j < RPAD): the K-extension columns of the fused QKV GEMM's A operand (clip.py), previously
+//           tb_layernorm_fwd + tb_lora_down.  The down-projection reads the fp16-rounded y, as the GEMM will.
+template <int MV>
+__global__ void ln_lora_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, __half* __restrict__ y, long long ldy,
+                                   float* __restrict__ stats, const float* __restrict__ A, int R, int RPAD, int M,
+                                   int C, float eps) {
+  const long long row_raw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const bool row_ok = row_raw < M;
+  const long long row = row_ok ? row_raw : M - 1;  // out-of-range warps shadow the last row (shuffles stay warp-wide)
+  const int lane = threadIdx.x & 31;
+  const int nvec = C / 8;
+  float v[MV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < MV; ++j) {
+    const int vi = lane + j * 32;
+    if (vi < nvec) {
+      load8<float>(x + row * ldx + vi * 8, v[j]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += v[j][i];
+    }
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < MV; ++j) {
+    const int vi = lane + j * 32;
+    if (vi < nvec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = v[j][i] - mean;
+        q += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+  for (int j = 0; j < MV; ++j) {
+    const int vi = lane + j * 32;
+    if (vi < nvec) {
+      float gf[8], bf[8];
+      load8<float>(gamma + vi * 8, gf);
+      load8<float>(beta + vi * 8, bf);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[j][i] = __half2float(__float2half((v[j][i] - mean) * rstd * gf[i] + bf[i]));
+      if (row_ok) store8<__half>(y + row * ldy + vi * 8, v[j]);
+    }
+  }
+  if (lane == 0 && stats && row_ok) {
+    stats[row * 2] = mean;
+    stats[row * 2 + 1] = rstd;
+  }
+  for (int j0 = 0; j0 < RPAD; j0 += 16) {
+    float acc[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) acc[r] = 0.f;
+    if (j0 < R) {
+#pragma unroll
+      for (int j = 0; j < MV; ++j) {
+        const int vi = lane + j * 32;
+        if (vi < nvec) {
+#pragma unroll
+          for (int r = 0; r < 16; ++r) {
+            if (j0 + r < R) {
+              float af[8];
+              load8<float>(A + (long long)(j0 + r) * C + vi * 8, af);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc[r] += v[j][i] * af[i];
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 16; ++r) acc[r] = warp_sum(acc[r]);
+    }
+    if (lane < 16 && j0 + lane < RPAD && row_ok) {
+      float o = 0.f;
+#pragma unroll
+      for (int r = 0; r < 16; ++r)
+        if (r == lane && j0 + r < R) o = acc[r];
+      y[row * ldy + C + j0 + lane] = __float2half(o);
+    }
+  }
+}
+
+// backward: dy_eff[m, c] = dy[m, c] + sum_j dy[m, C + j] * A[j, c]   (the LoRA down-projection's input-gradient, from
+//           the extension columns of the QKV dgrad output; previously tb_lora_dx, in place and rounded to fp16)
+//           dx = LN'(dy_eff) + add  (fp32 residual stream),  dx16 = fp16(dx)  (the next dgrad GEMM's A operand,
+//           previously tb_cast_f32_f16).  A == nullptr: plain LayerNorm backward with the optional fp16 copy.
+template <int MV, typename DYT>
+__global__ void ln_bwd_clip_kernel(const DYT* __restrict__ dy, long long lddy, const float* __restrict__ x,
+                                   long long ldx, const float* __restrict__ gamma, const float* __restrict__ stats,
+                                   const float* __restrict__ add, float* __restrict__ dx, __half* __restrict__ dx16,
+                                   const float* __restrict__ A, int R, int M, int C) {
+  const long long row_raw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const bool row_ok = row_raw < M;
+  const long long row = row_ok ? row_raw : M - 1;
+  const int lane = threadIdx.x & 31;
+  const int nvec = C / 8;
+  const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
+  float g[MV][8], xh[MV][8];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < MV; ++j) {
+    const int vi = lane + j * 32;
+    if (vi < nvec) {
+      float df[8], gf[8], xf[8];
+      load8<DYT>(dy + row * lddy + vi * 8, df);
+      load8<float>(gamma + vi * 8, gf);
+      load8<float>(x + row * ldx + vi * 8, xf);
+      if (A) {
+        for (int r = 0; r < R; ++r) {
+          const float dxa = static_cast<float>(dy[row * lddy + C + r]);
+          float af[8];
+          load8<float>(A + (long long)r * C + vi * 8, af);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) df[i] += dxa * af[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        g[j][i] = df[i] * gf[i];
+        xh[j][i] = (xf[i] - mean) * rstd;
+        s1 += g[j][i];
+        s2 += g[j][i] * xh[j][i];
+      }
+    }
+  }
+  s1 = warp_sum(s1) / C;
+  s2 = warp_sum(s2) / C;
+#pragma unroll
+  for (int j = 0; j < MV; ++j) {
+    const int vi = lane + j * 32;
+    if (vi < nvec) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = rstd * (g[j][i] - s1 - xh[j][i] * s2);
+      if (add) {
+        float af[8];
+        load8<float>(add + row * (long long)C + vi * 8, af);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += af[i];
+      }
+      if (row_ok) {
+        store8<float>(dx + row * (long long)C + vi * 8, o);
+        if (dx16) store8<__half>(dx16 + row * (long long)C + vi * 8, o);
+      }
+    }
+  }
+}
+
 }  // namespace tb
 
 using namespace tb;
@@ -442,8 +599,12 @@ extern "C" int tb_groupnorm_fwd_f16(const void* x, const void* gamma, const void
   GnGeom g;
   if ((rc = gn_geom(g, B, HW, C, G))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(stats, 0, (size_t)B * G * 2 * sizeof(float), st);
-  TB_REQUIRE(e == cudaSuccess, TB_E_CUDA, "groupnorm memset: %s", cudaGetErrorString(e));
+  const bool zeroed = (silu & TB_GN_STATS_ZEROED) != 0;  // the caller hands out slices of one buffer it cleared once
+  silu &= 1;
+  if (!zeroed) {
+    cudaError_t e = cudaMemsetAsync(stats, 0, (size_t)B * G * 2 * sizeof(float), st);
+    TB_REQUIRE(e == cudaSuccess, TB_E_CUDA, "groupnorm memset: %s", cudaGetErrorString(e));
+  }
   dim3 grid((HW + g.ppc - 1) / g.ppc, B);
   const int threads = g.nvec * g.k;
   gn_stats_kernel<0><<<grid, threads, 2 * G * sizeof(float), st>>>(
@@ -465,8 +626,12 @@ extern "C" int tb_groupnorm_bwd_f16(const void* dy, const void* x, const void* g
   GnGeom g;
   if ((rc = gn_geom(g, B, HW, C, G))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(dstats, 0, (size_t)B * G * 2 * sizeof(float), st);
-  TB_REQUIRE(e == cudaSuccess, TB_E_CUDA, "groupnorm memset: %s", cudaGetErrorString(e));
+  const bool zeroed = (silu & TB_GN_STATS_ZEROED) != 0;
+  silu &= 1;
+  if (!zeroed) {
+    cudaError_t e = cudaMemsetAsync(dstats, 0, (size_t)B * G * 2 * sizeof(float), st);
+    TB_REQUIRE(e == cudaSuccess, TB_E_CUDA, "groupnorm memset: %s", cudaGetErrorString(e));
+  }
   dim3 grid((HW + g.ppc - 1) / g.ppc, B);
   const int threads = g.nvec * g.k;
   gn_stats_kernel<1><<<grid, threads, 2 * G * sizeof(float), st>>>(
@@ -555,4 +720,56 @@ extern "C" int tb_layernorm_bwd(const void* dy, int dy_f32, int64_t lddy, const 
   else TB_LN_BWD(32, LN_MAXV);
 #undef TB_LN_BWD
   return check_launch("ln_bwd_kernel");
+}
+
+extern "C" int tb_layernorm_lora_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, void* y_ext,
+                                     int64_t ldy, float* stats, const float* lora_A, int R, int RPAD, int M, int C,
+                                     float eps, void* stream) {
+  int rc = tb_check_device();
+  if (rc) return rc;
+  TB_REQUIRE(x && gamma && beta && y_ext && lora_A, TB_E_ARG, "tb_layernorm_lora_fwd: null pointer");
+  TB_REQUIRE(C % 8 == 0 && C <= LN_MAXV * 256, TB_E_SHAPE, "tb_layernorm_lora_fwd: C=%d unsupported", C);
+  TB_REQUIRE(R >= 1 && R <= RPAD && RPAD <= 64 && RPAD % 8 == 0, TB_E_ARG,
+             "tb_layernorm_lora_fwd: bad LoRA extent (R=%d RPAD=%d; R <= RPAD <= 64)", R, RPAD);
+  TB_REQUIRE(ldx % 4 == 0 && ldy % 8 == 0 && ldy >= C + RPAD, TB_E_ALIGN,
+             "tb_layernorm_lora_fwd: ldx %% 4, ldy %% 8, ldy >= C + RPAD");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int wpb = 8;
+  const unsigned grid = (unsigned)((M + wpb - 1) / wpb);
+  if (C <= 768)
+    ln_lora_fwd_kernel<3><<<grid, wpb * 32, 0, st>>>(x, ldx, gamma, beta, (__half*)y_ext, ldy, stats, lora_A, R, RPAD,
+                                                     M, C, eps);
+  else
+    ln_lora_fwd_kernel<LN_MAXV><<<grid, wpb * 32, 0, st>>>(x, ldx, gamma, beta, (__half*)y_ext, ldy, stats, lora_A, R,
+                                                           RPAD, M, C, eps);
+  return check_launch("ln_lora_fwd_kernel");
+}
+
+extern "C" int tb_layernorm_bwd_clip(const void* dy, int dy_f32, int64_t lddy, const float* x, int64_t ldx,
+                                     const float* gamma, const float* stats, const float* add, float* dx,
+                                     void* dx_f16, const float* lora_A, int R, int M, int C, void* stream) {
+  int rc = tb_check_device();
+  if (rc) return rc;
+  TB_REQUIRE(dy && x && gamma && stats && dx, TB_E_ARG, "tb_layernorm_bwd_clip: null pointer");
+  TB_REQUIRE(C % 8 == 0 && C <= LN_MAXV * 256, TB_E_SHAPE, "tb_layernorm_bwd_clip: C=%d unsupported", C);
+  TB_REQUIRE(!lora_A || (!dy_f32 && R >= 1 && R <= 64 && lddy >= C + R), TB_E_ARG,
+             "tb_layernorm_bwd_clip: LoRA needs fp16 dy with R <= 64 extension columns (R=%d lddy=%lld)", R,
+             (long long)lddy);
+  TB_REQUIRE(lddy % (dy_f32 ? 4 : 8) == 0 && ldx % 4 == 0, TB_E_ALIGN, "tb_layernorm_bwd_clip: lddy / ldx alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int wpb = 8;
+  const unsigned grid = (unsigned)((M + wpb - 1) / wpb);
+#define TB_LN_BWD_CLIP(MV)                                                                                           \
+  do {                                                                                                               \
+    if (dy_f32)                                                                                                      \
+      ln_bwd_clip_kernel<MV, float><<<grid, wpb * 32, 0, st>>>((const float*)dy, lddy, x, ldx, gamma, stats, add, dx, \
+                                                               (__half*)dx_f16, nullptr, 0, M, C);                   \
+    else                                                                                                             \
+      ln_bwd_clip_kernel<MV, __half><<<grid, wpb * 32, 0, st>>>((const __half*)dy, lddy, x, ldx, gamma, stats, add,  \
+                                                                dx, (__half*)dx_f16, lora_A, R, M, C);               \
+  } while (0)
+  if (C <= 768) TB_LN_BWD_CLIP(3);
+  else TB_LN_BWD_CLIP(LN_MAXV);
+#undef TB_LN_BWD_CLIP
+  return check_launch("ln_bwd_clip_kernel");
 }

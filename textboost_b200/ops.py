@@ -21,6 +21,8 @@ def _epilogue(bias=None, rowvec=None, rows_per_group=1, residual=None, alpha=1.0
     ep.bias = bias.data_ptr() if bias is not None else None
     ep.rowvec = rowvec.data_ptr() if rowvec is not None else None
     ep.rows_per_group = int(rows_per_group)
+    ep.ld_rowvec = rowvec.stride(-2) if rowvec is not None and rowvec.dim() >= 2 else 0
+    assert rowvec is None or rowvec.stride(-1) == 1
     ep.residual = residual.data_ptr() if residual is not None else None
     ep.ldr = residual.stride(-2) if residual is not None else 0
     ep.residual_f32 = int(residual is not None and residual.dtype == F32)
@@ -81,14 +83,22 @@ def attn_fwd(q, k, v, heads, scale=None, out=None, causal=False):
     return out, lse
 
 
-def attn_bwd(q, k, v, o, do, lse, heads, scale=None, need_dq=True, dk=None, dv=None, causal=False):
-    """Returns (dq_acc fp32 [B,Nq,C] or None, dk, dv fp16 [B,Nk,C])."""
+def attn_bwd(q, k, v, o, do, lse, heads, scale=None, need_dq=True, dk=None, dv=None, causal=False, dq_out=None):
+    """Returns (dq, dk, dv): dk / dv fp16 [B,Nk,C]; dq is the fp32 accumulator [B,Nq,C] (None without need_dq), or --
+    with dq_out (an fp16 [B,Nq,C] view with unit inner stride, or True to allocate one; Nk <= 128 only) -- that fp16
+    tensor, written once by the kernel: no accumulator, memset or cast."""
     B, Nq, Ch = q.shape
     Nk = k.shape[1]
     d = Ch // heads
     scale = d ** -0.5 if scale is None else scale
     delta = torch.empty((B, heads, Nq), device=q.device, dtype=F32)
-    dq = torch.empty((B, Nq, Ch), device=q.device, dtype=F32) if need_dq else None
+    dq16 = None
+    if dq_out is not None and dq_out is not False:
+        assert need_dq and Nk <= 128, "dq_out: single KV tile only"
+        dq16 = torch.empty((B, Nq, Ch), device=q.device, dtype=F16) if dq_out is True else dq_out
+        assert dq16.dtype == F16 and dq16.shape == (B, Nq, Ch) and dq16.stride(2) == 1
+        assert dq16.stride(0) == Nq * dq16.stride(1)
+    dq = torch.empty((B, Nq, Ch), device=q.device, dtype=F32) if need_dq and dq16 is None else None
     if dk is None:
         dk = torch.empty((B, Nk, Ch), device=q.device, dtype=F16)
     if dv is None:
@@ -96,31 +106,54 @@ def attn_bwd(q, k, v, o, do, lse, heads, scale=None, need_dq=True, dk=None, dv=N
     assert do.stride(2) == 1 and o.stride(2) == 1
     C.call("tb_attn_bwd_f16", C.ptr(q), q.stride(1), C.ptr(k), k.stride(1), C.ptr(v), v.stride(1),
            C.ptr(o), o.stride(1), C.ptr(do), do.stride(1), C.ptr(lse), C.ptr(delta), C.ptr(dq),
-           dq.stride(1) if dq is not None else 0, C.ptr(dk), dk.stride(1),
-           C.ptr(dv), dv.stride(1), B, heads, Nq, Nk, d, scale, int(causal), C.stream_ptr())
-    return dq, dk, dv
+           dq.stride(1) if dq is not None else 0, C.ptr(dq16), dq16.stride(1) if dq16 is not None else 0,
+           C.ptr(dk), dk.stride(1), C.ptr(dv), dv.stride(1), B, heads, Nq, Nk, d, scale, int(causal), C.stream_ptr())
+    return (dq16 if dq16 is not None else dq), dk, dv
 
 
 # ---------------------------------------------------------------------------------- normalisation
-def groupnorm(x, gamma, beta, groups, eps, silu):
+class StatsArena:
+    """One zero-filled fp32 buffer per UNet pass for the (image, group) sums of all its GroupNorms: ONE fill launch
+    instead of a memset node per GroupNorm call (61 forward, 58 backward).  take() hands out [B, G, 2] slices."""
+
+    def __init__(self, n_calls, B, groups, device):
+        self.per = B * groups * 2
+        self.buf = torch.zeros(n_calls * self.per, device=device, dtype=F32)
+        self.used, self.shape = 0, (B, groups, 2)
+
+    def take(self):
+        if self.used * self.per >= self.buf.numel():
+            return None  # more calls than planned: the kernel's own memset takes over
+        t = self.buf[self.used * self.per:(self.used + 1) * self.per].view(self.shape)
+        self.used += 1
+        return t
+
+
+def groupnorm(x, gamma, beta, groups, eps, silu, arena=None):
     """x [B, HW, C] (or [B,H,W,C]) fp16 -> (y same shape, stats [B,G,2] fp32 sums)."""
     B, Cc = x.shape[0], x.shape[-1]
     HW = x.numel() // (B * Cc)
     y = torch.empty_like(x)
-    stats = torch.empty((B, groups, 2), device=x.device, dtype=F32)
+    stats = arena.take() if arena is not None else None
+    flags = int(silu) | (C.TB_GN_STATS_ZEROED if stats is not None else 0)
+    if stats is None:
+        stats = torch.empty((B, groups, 2), device=x.device, dtype=F32)
     C.call("tb_groupnorm_fwd_f16", C.ptr(x), C.ptr(gamma), C.ptr(beta), C.ptr(y), C.ptr(stats), B, HW, Cc,
-           groups, eps, int(silu), C.stream_ptr())
+           groups, eps, flags, C.stream_ptr())
     return y, stats
 
 
-def groupnorm_bwd(dy, x, gamma, beta, stats, groups, eps, silu, add=None):
+def groupnorm_bwd(dy, x, gamma, beta, stats, groups, eps, silu, add=None, arena=None):
     B, Cc = x.shape[0], x.shape[-1]
     HW = x.numel() // (B * Cc)
     assert dy.is_contiguous() and x.is_contiguous() and (add is None or add.is_contiguous())
     dx = torch.empty_like(x)
-    dstats = torch.empty((B, groups, 2), device=x.device, dtype=F32)
+    dstats = arena.take() if arena is not None else None
+    flags = int(silu) | (C.TB_GN_STATS_ZEROED if dstats is not None else 0)
+    if dstats is None:
+        dstats = torch.empty((B, groups, 2), device=x.device, dtype=F32)
     C.call("tb_groupnorm_bwd_f16", C.ptr(dy), C.ptr(x), C.ptr(gamma), C.ptr(beta), C.ptr(stats),
-           C.ptr(dstats), C.ptr(add), C.ptr(dx), B, HW, Cc, groups, eps, int(silu), C.stream_ptr())
+           C.ptr(dstats), C.ptr(add), C.ptr(dx), B, HW, Cc, groups, eps, flags, C.stream_ptr())
     return dx
 
 
@@ -145,6 +178,36 @@ def layernorm_bwd(dy, x, gamma, stats, add=None, out=None):
     C.call("tb_layernorm_bwd", C.ptr(dy), int(dy.dtype == F32), dy.stride(0), C.ptr(x),
            int(x.dtype == F32), x.stride(0), C.ptr(gamma), C.ptr(stats), C.ptr(add), C.ptr(out), M, Cc,
            C.stream_ptr())
+    return out
+
+
+def layernorm_lora_fwd(x, gamma, beta, lora_a, y_ext, rpad, eps=1e-5):
+    """Text encoder: y_ext[:, :C] = LN(x) (fp16) and y_ext[:, C:C+rpad] = [LN(x) lora_a^T | 0] in one launch.
+    x fp32 [M, C], lora_a fp32 [R, C], y_ext fp16 [M, >= C + rpad].  Returns stats [M, 2]."""
+    M, Cc = x.shape
+    assert x.dtype == F32 and gamma.dtype == F32 and lora_a.dtype == F32 and y_ext.dtype == F16
+    assert lora_a.is_contiguous() and lora_a.shape[1] == Cc and y_ext.stride(1) == 1
+    stats = torch.empty((M, 2), device=x.device, dtype=F32)
+    C.call("tb_layernorm_lora_fwd", C.ptr(x), x.stride(0), C.ptr(gamma), C.ptr(beta), C.ptr(y_ext), y_ext.stride(0),
+           C.ptr(stats), C.ptr(lora_a), lora_a.shape[0], int(rpad), M, Cc, eps, C.stream_ptr())
+    return stats
+
+
+def layernorm_bwd_clip(dy, x, gamma, stats, add=None, out=None, out16=None, lora_a=None):
+    """Text-encoder LayerNorm backward on the fp32 residual stream: dx = LN'(dy[:, :C] (+ dy[:, C:C+R] lora_a)) + add,
+    plus an fp16 copy of dx in out16 (the next dgrad GEMM's operand).  Returns dx."""
+    M, Cc = x.shape
+    assert x.dtype == F32 and gamma.dtype == F32 and dy.stride(1) == 1
+    if out is None:
+        out = torch.empty((M, Cc), device=x.device, dtype=F32)
+    assert out.is_contiguous() and (add is None or (add.is_contiguous() and add.dtype == F32))
+    assert out16 is None or (out16.is_contiguous() and out16.dtype == F16 and out16.shape == (M, Cc))
+    R = 0
+    if lora_a is not None:
+        assert lora_a.dtype == F32 and lora_a.is_contiguous() and lora_a.shape[1] == Cc and dy.dtype == F16
+        R = lora_a.shape[0]
+    C.call("tb_layernorm_bwd_clip", C.ptr(dy), int(dy.dtype == F32), dy.stride(0), C.ptr(x), x.stride(0),
+           C.ptr(gamma), C.ptr(stats), C.ptr(add), C.ptr(out), C.ptr(out16), C.ptr(lora_a), R, M, Cc, C.stream_ptr())
     return out
 
 
@@ -186,23 +249,25 @@ def copy2d(dst, src, accumulate=False):
 
 
 def concat_channels(a, b):
-    """[..., Ca] , [..., Cb] -> [..., Ca+Cb] (torch.cat([h, skip], dim=1) of the NCHW reference)."""
+    """[..., Ca] , [..., Cb] -> [..., Ca+Cb] (torch.cat([h, skip], dim=1) of the NCHW reference), one launch."""
     Ca, Cb = a.shape[-1], b.shape[-1]
     out = torch.empty(a.shape[:-1] + (Ca + Cb,), device=a.device, dtype=F16)
-    o2 = out.view(-1, Ca + Cb)
-    copy2d(o2[:, :Ca], a.reshape(-1, Ca))
-    copy2d(o2[:, Ca:], b.reshape(-1, Cb))
+    a2, b2 = a.reshape(-1, Ca), b.reshape(-1, Cb)
+    assert a2.stride(1) == 1 and b2.stride(1) == 1
+    C.call("tb_concat2_f16", C.ptr(out), Ca + Cb, C.ptr(a2), a2.stride(0), Ca, C.ptr(b2), b2.stride(0), Cb,
+           a2.shape[0], C.stream_ptr())
     return out
 
 
 def split_channels(x, Ca):
+    """-> (first Ca channels as a contiguous tensor, the remaining channels as a VIEW of x).  The first half feeds
+    kernels that want contiguous rows; the second (a skip connection's gradient) is only ever the strided source of a
+    later accumulate (copy2d), so it is never copied."""
     Ct = x.shape[-1]
     x2 = x.view(-1, Ct)
     a = torch.empty(x.shape[:-1] + (Ca,), device=x.device, dtype=F16)
-    b = torch.empty(x.shape[:-1] + (Ct - Ca,), device=x.device, dtype=F16)
     copy2d(a.view(-1, Ca), x2[:, :Ca])
-    copy2d(b.view(-1, Ct - Ca), x2[:, Ca:])
-    return a, b
+    return a, x[..., Ca:]
 
 
 def cast_f32_f16(src, out=None, scale=1.0):

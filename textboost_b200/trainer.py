@@ -114,9 +114,11 @@ class TextBoostTrainer:
         # straight into the UNet, whose prefix (conv_in, time MLP, first resnet, first self-attention) does not read
         # the text: the 616-row encoder kernels fill a fraction of the SMs, the UNet prefix takes the rest.
         side = self._side_stream()
+        first = self._first_stream()  # the instance prompts' forward: the UNet waits for it -> high priority
         self._loss_kpl.zero_()
+        first.wait_stream(main)
         side.wait_stream(main)
-        with torch.cuda.stream(side):
+        with torch.cuda.stream(first):
             h = te.forward(input_ids, save_for_backward=True)  # fp32 [B, L, D]
             ctx_i = te.pop_ctx()
             _, L, D = h.shape
@@ -124,7 +126,8 @@ class TextBoostTrainer:
             if ehs.is_cuda:
                 ehs.record_stream(main)
             ehs_ready = torch.cuda.Event()
-            ehs_ready.record(side)
+            ehs_ready.record(first)
+        with torch.cuda.stream(side):
             if use_kpl:
                 hp = te.forward(prior_ids, save_for_backward=True)
                 ctx_p = te.pop_ctx()
@@ -149,6 +152,8 @@ class TextBoostTrainer:
         d_h = torch.zeros((B, L, D), device=self.dev, dtype=F32)
         unet.backward(dpred, d_h)
         main.wait_stream(side)  # gradient accumulation into state.grads is serialised from here on
+        if first is not side:
+            main.wait_stream(first)
         if use_kpl:
             self.loss.add_(self._loss_kpl)
             C.launch_count += 1
@@ -161,6 +166,20 @@ class TextBoostTrainer:
             self._side = torch.cuda.Stream(device=self.dev)
             self._loss_kpl = torch.zeros(1, device=self.dev, dtype=F32)
         return self._side
+
+    def _first_stream(self):
+        """Stream of the instance-prompt encoder forward.  The UNet's first cross-attention waits for its result while
+        the UNet prefix fills the machine with persistent kernels; a high-priority stream lets the 616-row encoder
+        kernels take SMs at every kernel boundary of the prefix instead of queueing behind it.  The knowledge-
+        preservation branch keeps its own normal-priority stream: nothing waits for it until the end of the UNet
+        backward.  (TB_ONE_SIDE_STREAM=1: the single side stream of round 1, for comparison.)"""
+        if getattr(self, "_first", None) is None:
+            import os
+            if os.environ.get("TB_ONE_SIDE_STREAM") or not torch.cuda.is_available():
+                self._first = self._side_stream()
+            else:
+                self._first = torch.cuda.Stream(device=self.dev, priority=-1)
+        return self._first
 
     def all_reduce(self):
         self.sync.all_reduce_(self.te.state.grads)

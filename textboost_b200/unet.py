@@ -91,6 +91,8 @@ class _Conv3:
 
 
 class _Resnet:
+    arena = None  # ops.StatsArena of the running UNet pass (set by UNetEngine), None = per-call memset
+
     def __init__(self, sd, p, cfg: UNetConfig):
         self.G, self.eps = cfg.norm_num_groups, cfg.norm_eps
         self.n1 = (sd[p + "norm1.weight"], sd[p + "norm1.bias"])
@@ -102,12 +104,15 @@ class _Resnet:
         if p + "conv_shortcut.weight" in sd:
             self.sc = _Linear(sd[p + "conv_shortcut.weight"], sd[p + "conv_shortcut.bias"])
 
-    def forward(self, x, temb_act, save):
+    def forward(self, x, temb_act, save, tp=None):
+        """tp: this block's time_emb_proj(silu(temb)) [B, Cout], normally a column slice of the ONE GEMM that projects
+        the time embedding for every ResnetBlock2D of the net (UNetEngine.forward)."""
         B, H, W, Cin = x.shape
-        h, st1 = ops.groupnorm(x, *self.n1, self.G, self.eps, True)
-        tp = self.t.fwd(temb_act)
+        h, st1 = ops.groupnorm(x, *self.n1, self.G, self.eps, True, arena=self.arena)
+        if tp is None:
+            tp = self.t.fwd(temb_act)
         h2 = self.c1.fwd(h, rowvec=tp)
-        h3, st2 = ops.groupnorm(h2, *self.n2, self.G, self.eps, True)
+        h3, st2 = ops.groupnorm(h2, *self.n2, self.G, self.eps, True, arena=self.arena)
         if self.sc is not None:
             res = self.sc.fwd(x.view(-1, Cin)).view(B, H, W, -1)
         else:
@@ -122,16 +127,17 @@ class _Resnet:
         self.ctx = None
         B, H, W, Cin = x.shape
         dh3 = self.c2.dgrad(dout)
-        dh2 = ops.groupnorm_bwd(dh3, h2, *self.n2, st2, self.G, self.eps, True)
+        dh2 = ops.groupnorm_bwd(dh3, h2, *self.n2, st2, self.G, self.eps, True, arena=self.arena)
         dh1 = self.c1.dgrad(dh2)
         if self.sc is None:
-            return ops.groupnorm_bwd(dh1, x, *self.n1, st1, self.G, self.eps, True, add=dout)
-        dx = ops.groupnorm_bwd(dh1, x, *self.n1, st1, self.G, self.eps, True)
+            return ops.groupnorm_bwd(dh1, x, *self.n1, st1, self.G, self.eps, True, add=dout, arena=self.arena)
+        dx = ops.groupnorm_bwd(dh1, x, *self.n1, st1, self.G, self.eps, True, arena=self.arena)
         return self.sc.dgrad(dout.view(B * H * W, -1), residual=dx.view(-1, Cin)).view(B, H, W, Cin)
 
 
 class _Transformer:
     """Transformer2DModel with one BasicTransformerBlock."""
+    arena = None  # see _Resnet.arena
 
     def __init__(self, sd, p, cfg: UNetConfig, heads: int):
         self.G, self.heads = cfg.norm_num_groups, heads
@@ -153,11 +159,13 @@ class _Transformer:
         self.first = False  # first cross-attention of the net: backward stops at dK/dV
         self.ehs_ready = None  # set on the first cross-attention: event after which encoder_hidden_states is valid
 
-    def forward(self, x, ehs, save):
+    def forward(self, x, ehs, save, kv2=None):
+        """kv2: this block's [to_k | to_v](encoder_hidden_states) [B, L, 2C], normally a column slice of the ONE GEMM
+        that projects the text states for all cross-attentions of the net (UNetEngine.forward)."""
         B, H, W, Cc = x.shape
         N, M = H * W, B * H * W
         L = ehs.shape[1]
-        hn, st0 = ops.groupnorm(x, *self.norm, self.G, 1e-6, False)
+        hn, st0 = ops.groupnorm(x, *self.norm, self.G, 1e-6, False, arena=self.arena)
         h0 = self.pi.fwd(hn.view(M, Cc))
         n1, s1 = ops.layernorm(h0, *self.ln1)
         qkv = self.qkv.fwd(n1).view(B, N, 3 * Cc)
@@ -165,9 +173,12 @@ class _Transformer:
         h1 = self.o1.fwd(o1.view(M, Cc), residual=h0)
         n2, s2 = ops.layernorm(h1, *self.ln2)
         q2 = self.q2.fwd(n2).view(B, N, Cc)
-        if self.ehs_ready is not None:  # the text encoder runs on another stream up to here (trainer.py)
-            torch.cuda.current_stream().wait_event(self.ehs_ready)
-        kv2 = self.kv2.fwd(ehs.reshape(B * L, -1)).view(B, L, 2 * Cc)
+        if callable(kv2):
+            kv2 = kv2(self)
+        elif kv2 is None:
+            if self.ehs_ready is not None:  # the text encoder runs on another stream up to here (trainer.py)
+                torch.cuda.current_stream().wait_event(self.ehs_ready)
+            kv2 = self.kv2.fwd(ehs.reshape(B * L, -1)).view(B, L, 2 * Cc)
         o2, lse2 = ops.attn_fwd(q2, kv2[..., :Cc], kv2[..., Cc:], self.heads)
         h2 = self.o2.fwd(o2.view(M, Cc), residual=h1)
         n3, s3 = ops.layernorm(h2, *self.ln3)
@@ -179,7 +190,9 @@ class _Transformer:
             self.ctx = (x, st0, h0, s1, qkv, o1, lse1, h1, s2, q2, kv2, o2, lse2, h2, s3, f1)
         return out
 
-    def backward(self, dout, d_ehs):
+    def backward(self, dout, d_ehs, dkv2=None):
+        """dkv2 (fp16 [B, L, 2C] view): where d[to_k | to_v] goes when the caller projects all blocks' K/V gradients
+        back to the text states with one GEMM at the end; None: projected and accumulated into d_ehs here."""
         (x, st0, h0, s1, qkv, o1, lse1, h1, s2, q2, kv2, o2, lse2, h2, s3, f1) = self.ctx
         self.ctx = None
         B, H, W, Cc = x.shape
@@ -193,13 +206,19 @@ class _Transformer:
         dh2 = ops.layernorm_bwd(dn3, h2, self.ln3[0], s3, add=dh3)
         # cross attention
         do2 = self.o2.dgrad(dh2).view(B, N, Cc)
-        dkv2 = torch.empty_like(kv2)
+        batched = dkv2 is not None
+        if not batched:
+            dkv2 = torch.empty((B, L, 2 * Cc), device=kv2.device, dtype=F16)
+        # 77 text tokens = a single KV tile: dQ leaves the kernel as fp16 (no fp32 accumulator, memset or cast)
+        one_tile = L <= 128
         dq2, _, _ = ops.attn_bwd(q2, kv2[..., :Cc], kv2[..., Cc:], o2, do2, lse2, self.heads,
-                                 need_dq=not self.first, dk=dkv2[..., :Cc], dv=dkv2[..., Cc:])
-        ops.gemm(dkv2.view(B * L, 2 * Cc), self.kv2.wt, out=d_ehs, out_kind=C.TB_OUT_F32_ACC)
+                                 need_dq=not self.first, dk=dkv2[..., :Cc], dv=dkv2[..., Cc:],
+                                 dq_out=(one_tile and not self.first) or None)
+        if not batched:
+            ops.gemm(dkv2.view(B * L, 2 * Cc), self.kv2.wt, out=d_ehs, out_kind=C.TB_OUT_F32_ACC)
         if self.first:
             return None
-        dq2h = ops.cast_f32_f16(dq2.view(M, Cc))
+        dq2h = dq2.view(M, Cc) if one_tile else ops.cast_f32_f16(dq2.view(M, Cc))
         dn2 = self.q2.dgrad(dq2h)
         dh1 = ops.layernorm_bwd(dn2, h1, self.ln2[0], s2, add=dh2)
         # self attention
@@ -211,7 +230,7 @@ class _Transformer:
         dn1 = self.qkv.dgrad(dqkv.view(M, 3 * Cc))
         dh0 = ops.layernorm_bwd(dn1, h0, self.ln1[0], s1, add=dh1)
         dhn = self.pi.dgrad(dh0).view(B, H, W, Cc)
-        return ops.groupnorm_bwd(dhn, x, *self.norm, st0, self.G, 1e-6, False, add=dout)
+        return ops.groupnorm_bwd(dhn, x, *self.norm, st0, self.G, 1e-6, False, add=dout, arena=self.arena)
 
 
 class _Down:
@@ -285,6 +304,33 @@ class UNetEngine:
         self.first_attn = first if first is not None else self.mid_attn
         self.first_attn.first = True
         self._saved = None
+        # Horizontal batching of the launches that depend only on the step's inputs (every GEMM with 8 or 616 rows is
+        # pure latency: ~8-10 us per launch for a few MFLOP):
+        #   * time_emb_proj of all ResnetBlock2D: ONE [B,1280] x [sum Cout,1280]^T GEMM; blocks read column slices
+        #   * attn2.to_k / to_v of all Transformer2D blocks: ONE [B*77, ctx] x [sum 2C, ctx]^T GEMM, and in the
+        #     backward ONE [B*77, sum 2C] x [ctx, sum 2C]^T GEMM for d(encoder_hidden_states)
+        self._resnets = [r for blk in self.down for r in blk["res"]] + self.mid_res + \
+                        [r for blk in self.up for r in blk["res"]]
+        self._temb_w = torch.cat([r.t.w for r in self._resnets], 0).contiguous()
+        self._temb_b = torch.cat([r.t.b for r in self._resnets], 0).contiguous()
+        off = 0
+        for r in self._resnets:
+            r.t_off, off = off, off + r.t.w.shape[0]
+        self._attns = [a for blk in self.down for a in blk["attn"]] + [self.mid_attn] + \
+                      [a for blk in self.up for a in blk["attn"]]
+        self._kv_w = torch.cat([a.kv2.w for a in self._attns], 0).contiguous()       # [sum 2C, ctx]
+        self._kv_wt = self._kv_w.t().contiguous()                                    # [ctx, sum 2C]
+        off = 0
+        for a in self._attns:
+            a.kv_off, off = off, off + a.kv2.w.shape[0]
+        self._kv_total = off
+        for a in self._attns:  # the per-block copies are only kept for the unbatched entry points (tests)
+            a.kv2.wt = self._kv_wt[:, a.kv_off:a.kv_off + a.kv2.w.shape[0]]
+
+    def _set_arena(self, arena):
+        self._arena = arena
+        for m in self._resnets + self._attns:
+            m.arena = arena
 
     # ------------------------------------------------------------------ forward
     def forward(self, sample, timesteps, ehs, save_for_backward=True, ehs_ready=None):
@@ -303,33 +349,51 @@ class UNetEngine:
         te = ops.timestep_embedding(timesteps, cfg.block_out_channels[0])
         e1 = self.t1.fwd(te, act=C.TB_ACT_SILU)
         temb_act = self.t2.fwd(e1, act=C.TB_ACT_SILU)  # every consumer applies SiLU first
+        tp_all = ops.gemm(temb_act, self._temb_w, bias=self._temb_b)  # every block's time_emb_proj at once
+        n_gn = 2 * len(self._resnets) + len(self._attns) + 1
+        self._set_arena(ops.StatsArena(n_gn, sample.shape[0], cfg.norm_num_groups, sample.device))
+
+        def tp_of(r):
+            return tp_all[:, r.t_off:r.t_off + r.t.w.shape[0]]
+
+        B, L = ehs.shape[0], ehs.shape[1]
+        kv_all = [None]
+
+        def kv_of(a):
+            if kv_all[0] is None:  # first cross-attention: wait for the text encoder, project K/V for all 16 blocks
+                if ehs_ready is not None:
+                    torch.cuda.current_stream().wait_event(ehs_ready)
+                kv_all[0] = ops.gemm(ehs.reshape(B * L, -1), self._kv_w).view(B, L, self._kv_total)
+            return kv_all[0][..., a.kv_off:a.kv_off + a.kv2.w.shape[0]]
+
         x = ops.conv_in(sample, self.conv_in_w, self.conv_in_b)
         skips = [x]
         for blk in self.down:
             for j, r in enumerate(blk["res"]):
-                x = r.forward(x, temb_act, save)
+                x = r.forward(x, temb_act, save, tp_of(r))
                 if blk["attn"]:
-                    x = blk["attn"][j].forward(x, ehs, save)
+                    x = blk["attn"][j].forward(x, ehs, save, kv_of)
                 skips.append(x)
             if blk["down"] is not None:
                 x = blk["down"].forward(x)
                 skips.append(x)
-        x = self.mid_res[0].forward(x, temb_act, save)
-        x = self.mid_attn.forward(x, ehs, save)
-        x = self.mid_res[1].forward(x, temb_act, save)
+        x = self.mid_res[0].forward(x, temb_act, save, tp_of(self.mid_res[0]))
+        x = self.mid_attn.forward(x, ehs, save, kv_of)
+        x = self.mid_res[1].forward(x, temb_act, save, tp_of(self.mid_res[1]))
         cat_split = []
         for blk in self.up:
             for j, r in enumerate(blk["res"]):
                 s = skips.pop()
                 cat_split.append(x.shape[-1])
                 x = ops.concat_channels(x, s)
-                x = r.forward(x, temb_act, save)
+                x = r.forward(x, temb_act, save, tp_of(r))
                 if blk["attn"]:
-                    x = blk["attn"][j].forward(x, ehs, save)
+                    x = blk["attn"][j].forward(x, ehs, save, kv_of)
             if blk["up"] is not None:
                 x = blk["up"].forward(x)
-        hn, st = ops.groupnorm(x, *self.norm_out, cfg.norm_num_groups, cfg.norm_eps, True)
+        hn, st = ops.groupnorm(x, *self.norm_out, cfg.norm_num_groups, cfg.norm_eps, True, arena=self._arena)
         out = ops.conv_out(hn, self.conv_out_w, self.conv_out_b)
+        self._set_arena(None)
         self.first_attn.ehs_ready = None
         if save:
             self._saved = (x, st, cat_split, ehs.shape)
@@ -346,16 +410,25 @@ class UNetEngine:
         if d_ehs is None:
             d_ehs = torch.zeros((B * L, ctx), device=dout.device, dtype=F32)
         d2 = d_ehs.view(B * L, ctx)
+        n_gn = 2 * len(self._resnets) + len(self._attns) + 1
+        self._set_arena(ops.StatsArena(n_gn, dout.shape[0], cfg.norm_num_groups, dout.device))
         dh = ops.conv_out_bwd(dout.contiguous(), self.conv_out_w)
-        dx = ops.groupnorm_bwd(dh, x_last, *self.norm_out, st, cfg.norm_num_groups, cfg.norm_eps, True)
+        dx = ops.groupnorm_bwd(dh, x_last, *self.norm_out, st, cfg.norm_num_groups, cfg.norm_eps, True,
+                               arena=self._arena)
         dskips = []  # gradients of the skip tensors in the order they are popped in forward
+        # d[to_k | to_v] of all cross-attentions side by side: one GEMM at the end takes them back to the text states
+        dkv_all = torch.empty((B, L, self._kv_total), device=dout.device, dtype=F16)
+
+        def dkv_of(a):
+            return dkv_all[..., a.kv_off:a.kv_off + a.kv2.w.shape[0]]
+
         ci = len(cat_split)
         for blk in reversed(self.up):
             if blk["up"] is not None:
                 dx = blk["up"].backward(dx)
             for j in reversed(range(len(blk["res"]))):
                 if blk["attn"]:
-                    dx = blk["attn"][j].backward(dx, d2)
+                    dx = blk["attn"][j].backward(dx, d2, dkv_of(blk["attn"][j]))
                 dcat = blk["res"][j].backward(dx)
                 ci -= 1
                 dx, ds = ops.split_channels(dcat, cat_split[ci])
@@ -365,27 +438,29 @@ class UNetEngine:
         n = len(dskips)
         dskip_of = dskips
         dx = self.mid_res[1].backward(dx)
-        dx = self.mid_attn.backward(dx, d2)
+        dx = self.mid_attn.backward(dx, d2, dkv_of(self.mid_attn))
         dx = self.mid_res[0].backward(dx)
         k = n - 1  # index of the skip produced last in forward order
         done = False
         for blk in reversed(self.down):
             if blk["down"] is not None:
-                ops.copy2d(dx.view(-1, dx.shape[-1]), dskip_of[k].view(-1, dx.shape[-1]), accumulate=True)
+                ops.copy2d(dx.view(-1, dx.shape[-1]), dskip_of[k].reshape(-1, dx.shape[-1]), accumulate=True)
                 k -= 1
                 dx = blk["down"].backward(dx)
             for j in reversed(range(len(blk["res"]))):
-                ops.copy2d(dx.view(-1, dx.shape[-1]), dskip_of[k].view(-1, dx.shape[-1]), accumulate=True)
+                ops.copy2d(dx.view(-1, dx.shape[-1]), dskip_of[k].reshape(-1, dx.shape[-1]), accumulate=True)
                 k -= 1
                 if blk["attn"]:
                     a = blk["attn"][j]
-                    dx = a.backward(dx, d2)
+                    dx = a.backward(dx, d2, dkv_of(a))
                     if a.first:
                         done = True
                         break
                 dx = blk["res"][j].backward(dx)
             if done:
                 break
+        ops.gemm(dkv_all.view(B * L, self._kv_total), self._kv_wt, out=d2, out_kind=C.TB_OUT_F32_ACC)
+        self._set_arena(None)
         # drop contexts of the pruned prefix
         for blk in self.down:
             for r in blk["res"]:
