@@ -358,11 +358,12 @@ static inline uint32_t pack_half2(float a, float b) {
 }
 float sg[1 << 16];
 __half sw[1 << 17];
+uint4 gsm[1 << 14];  // dynamic shared memory of gn_group_kernel
 }
 // A process-wide pool of OS threads (never torn down: the workers sleep on a barrier until the process exits) runs every
 // launch: worker t plays CUDA thread t of each block in turn; thread 0 installs the block's barriers between two
 // launch-wide phases.  Blocks of more threads than the pool holds are not used by these kernels.
-constexpr unsigned EMU_MAX_THREADS = 320;
+constexpr unsigned EMU_MAX_THREADS = 512;
 struct EmuPool {
   std::barrier<> go{EMU_MAX_THREADS + 1}, done{EMU_MAX_THREADS + 1};
   const std::function<void(unsigned)>* job = nullptr;
@@ -437,8 +438,8 @@ extern "C" int emu_groupnorm_fwd(const void* x, const void* gamma, const void* b
   if (tb::gn_geom(g, B, HW, C, G)) return -1;  // the launch geometry tb_groupnorm_fwd_f16 uses on a 148-SM part
   memset(stats, 0, sizeof(float) * B * G * 2);
   const unsigned gx = (HW + g.ppc - 1) / g.ppc, threads = g.nvec * g.k;
-  emu_launch(gx, B, threads, [&] { tb::gn_stats_kernel<0>((const __half*)x, nullptr, nullptr, nullptr, nullptr, stats, g, eps, silu); });
-  emu_launch(gx, B, threads, [&] { tb::gn_apply_kernel<0>((const __half*)x, nullptr, (const __half*)gamma, (const __half*)beta,
+  emu_launch(gx, B, threads, [&] { tb::gn_stats_kernel<0, 4, 3>((const __half*)x, nullptr, nullptr, nullptr, nullptr, stats, g, eps, silu); });
+  emu_launch(gx, B, threads, [&] { tb::gn_apply_kernel<0, 4, 3>((const __half*)x, nullptr, (const __half*)gamma, (const __half*)beta,
                                                           stats, nullptr, nullptr, (__half*)y, g, eps, silu); });
   return (int)threads;
 }
@@ -448,9 +449,9 @@ extern "C" int emu_groupnorm_bwd(const void* dy, const void* x, const void* gamm
   if (tb::gn_geom(g, B, HW, C, G)) return -1;
   memset(dstats, 0, sizeof(float) * B * G * 2);
   const unsigned gx = (HW + g.ppc - 1) / g.ppc, threads = g.nvec * g.k;
-  emu_launch(gx, B, threads, [&] { tb::gn_stats_kernel<1>((const __half*)x, (const __half*)dy, (const __half*)gamma,
+  emu_launch(gx, B, threads, [&] { tb::gn_stats_kernel<1, 2, 2>((const __half*)x, (const __half*)dy, (const __half*)gamma,
                                                           (const __half*)beta, stats, dstats, g, eps, silu); });
-  emu_launch(gx, B, threads, [&] { tb::gn_apply_kernel<1>((const __half*)x, (const __half*)dy, (const __half*)gamma,
+  emu_launch(gx, B, threads, [&] { tb::gn_apply_kernel<1, 2, 2>((const __half*)x, (const __half*)dy, (const __half*)gamma,
                                                           (const __half*)beta, stats, dstats, (const __half*)add, (__half*)dx,
                                                           g, eps, silu); });
   return (int)threads;

@@ -31,7 +31,10 @@ def _close(a, b, tol):
     assert d <= tol * max(1.0, b.float().abs().max().item()), d
 
 
-@pytest.mark.parametrize("B,HW,C,G,silu", [(2, 40, 64, 32, True), (1, 72, 320, 32, False), (2, 9, 640, 32, True)])
+@pytest.mark.parametrize("B,HW,C,G,silu", [(2, 40, 64, 32, True), (1, 72, 320, 32, False), (2, 9, 640, 32, True),
+                                          # the single-launch group-owner kernel: one group per CTA (cpg 40), two
+                                          # groups per CTA (cpg 20 / 60: a vector straddles the two groups)
+                                          (2, 12, 1280, 32, True), (3, 10, 640, 32, True), (3, 7, 1920, 32, False)])
 def test_groupnorm_entry_points(abi, B, HW, C, G, silu):
     """tb_groupnorm_{fwd,bwd}_f16 incl. the two-group fast path (cpg >= 8) and the generic one (cpg = 2)."""
     from textboost_b200 import ops
@@ -46,6 +49,39 @@ def test_groupnorm_entry_points(abi, B, HW, C, G, silu):
     dx = ops.groupnorm_bwd(dy, x, gamma, beta, stats, G, 1e-5, silu, add=add)
     ref.backward(dy.float().transpose(1, 2))
     _close(dx, xf.grad.transpose(1, 2) + add.float(), 3e-3)
+    # the saved statistics are (sum x, sum x^2) per (image, group) whichever kernel wrote them
+    xs = x.float().view(B, HW, G, C // G)
+    _close(stats[..., 0], xs.sum((1, 3)), 1e-3)
+    _close(stats[..., 1], (xs * xs).sum((1, 3)), 1e-3)
+
+
+@pytest.mark.parametrize("M,D,R,RPAD", [(11, 768, 12, 16), (5, 1024, 40, 48)])
+def test_text_encoder_layernorm_with_lora_glue(abi, M, D, R, RPAD):
+    """tb_layernorm_lora_fwd / tb_layernorm_bwd_clip (LayerNorm + LoRA down-projection; LayerNorm backward + the
+    down-projection's input-gradient + the fp16 copy) run from the product source on the host."""
+    from textboost_b200 import ops
+    g = torch.Generator().manual_seed(M + D)
+    x = torch.randn(M, D, generator=g) * 2 + 0.3
+    gamma, beta = torch.randn(D, generator=g), torch.randn(D, generator=g)
+    A = torch.randn(R, D, generator=g) / R
+    y_ext = torch.full((M, D + RPAD + 8), 5.0).half()
+    stats = ops.layernorm_lora_fwd(x, gamma, beta, A, y_ext, RPAD)
+    _close(y_ext[:, :D], F.layer_norm(x, (D,), gamma, beta), 1e-3)
+    _close(y_ext[:, D:D + R], y_ext[:, :D].float() @ A.t(), 2e-3)
+    assert bool((y_ext[:, D + R:D + RPAD] == 0).all()) and bool((y_ext[:, D + RPAD:] == 5.0).all())
+    dy_ext = torch.randn(M, D + RPAD, generator=g).half()
+    add = torch.randn(M, D, generator=g)
+    xr = x.clone().requires_grad_(True)
+    F.layer_norm(xr, (D,), gamma, beta).backward(dy_ext[:, :D].float() + dy_ext[:, D:D + R].float() @ A)
+    out16 = torch.empty(M, D).half()
+    buf = add.clone()
+    dx = ops.layernorm_bwd_clip(dy_ext, x, gamma, stats, add=buf, out=buf, out16=out16, lora_a=A)
+    torch.testing.assert_close(dx, xr.grad + add, rtol=2e-4, atol=2e-4)
+    torch.testing.assert_close(out16.float(), dx, rtol=1e-3, atol=1e-3)
+    dy32 = torch.randn(M, D, generator=g)
+    xr2 = x.clone().requires_grad_(True)
+    F.layer_norm(xr2, (D,), gamma, beta).backward(dy32)
+    torch.testing.assert_close(ops.layernorm_bwd_clip(dy32, x, gamma, stats), xr2.grad, rtol=2e-4, atol=2e-4)
 
 
 @pytest.mark.parametrize("M,C,f32", [(13, 320, False), (9, 640, False), (10, 128, False), (11, 768, True), (6, 1024, True)])

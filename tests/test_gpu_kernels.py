@@ -356,7 +356,10 @@ def test_text_encoder_layernorm_with_lora_glue(M, D, R, RPAD):
 
 
 @pytest.mark.parametrize("B,HW,Cc,silu", [(2, 64, 64, True), (2, 4096, 320, True), (3, 1024, 640, False),
-                                          (2, 256, 1920, True), (2, 64, 2560, True)])
+                                          (2, 256, 1920, True), (2, 64, 2560, True),
+                                          # the single-launch group-owner kernel at the UNet's batch-8 shapes
+                                          (8, 1024, 640, True), (8, 256, 1280, True), (8, 64, 1280, False),
+                                          (8, 1024, 1280, True), (8, 256, 1920, True), (8, 64, 2560, True)])
 def test_groupnorm_fwd_bwd(B, HW, Cc, silu):
     from textboost_b200 import ops
     torch.manual_seed(HW + Cc)

@@ -98,8 +98,8 @@ __device__ __forceinline__ void gn_group_consts(GnGroupConst& k, const GnGeom& g
 // Per-channel constants are folded so that each kernel carries four of them (A = rstd*gamma, Bz = beta - mean*A,
 // ...): with z = x*A + Bz the normalised value times gamma is z - beta, so the backward sums are
 // s1 += dz*gamma, s2 += dz*(z - beta) and no mean / rstd registers are needed in the loops.
-template <int MODE>
-__global__ void __launch_bounds__(320, MODE == 0 ? 2 : 1)
+template <int MODE, int U, int MINB>
+__global__ void __launch_bounds__(320, MINB)
 gn_stats_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, const __half* __restrict__ gamma,
                 const __half* __restrict__ beta, const float* __restrict__ fstats, float* __restrict__ out,
                 GnGeom g, float eps, int silu) {
@@ -126,7 +126,7 @@ gn_stats_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, con
     }
   }
   const size_t base = (size_t)b * g.HW * g.C + (size_t)v * 8;
-  constexpr int U = MODE == 0 ? 8 : 4;  // pixels per trip: 8 (MODE 0) or 4+4 (MODE 1) 16-byte loads in flight
+  // U pixels per trip: U (MODE 0) or U+U (MODE 1) 16-byte loads in flight
   for (int p = p0 + pl; p < p1; p += U * g.k) {
     uint4 qx[U], qd[U];
 #pragma unroll
@@ -184,8 +184,8 @@ gn_stats_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, con
 }
 
 // MODE 0: y = act(x*A + Bz);  MODE 1: dx = rstd*(dz*gamma - S1/n - xhat*S2/n) = dz*A - x*P + Q (+ add)
-template <int MODE>
-__global__ void __launch_bounds__(320, MODE == 0 ? 2 : 1)
+template <int MODE, int U, int MINB>
+__global__ void __launch_bounds__(320, MINB)
 gn_apply_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, const __half* __restrict__ gamma,
                 const __half* __restrict__ beta, const float* __restrict__ fstats,
                 const float* __restrict__ bstats, const __half* __restrict__ add, __half* __restrict__ out,
@@ -212,7 +212,6 @@ gn_apply_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, con
     }
   }
   const size_t base = (size_t)b * g.HW * g.C + (size_t)v * 8;
-  constexpr int U = MODE == 0 ? 8 : 4;
   for (int p = p0 + pl; p < p1; p += U * g.k) {
     uint4 qx[U], qd[U], qa[U];
 #pragma unroll
@@ -259,6 +258,215 @@ gn_apply_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, con
   }
 }
 
+// ---- group-owner GroupNorm: ONE launch for the levels whose (image, group-chunk) slab fits in shared memory.
+// GroupNorm statistics are independent per (image, group), so a CTA that owns ALL pixels of `gpc` adjacent groups of
+// one image needs nothing from any other CTA: it streams its [HW x gpc*cpg] slab into shared memory while accumulating
+// the sums, reduces inside the block (no atomics: deterministic), and normalises out of shared memory -- one read and
+// one write of the tensor, one launch, no cleared stats buffer.  The two-kernel path above stays for the 64x64 level
+// (320 KB per slab) and the widest concatenations.  Thread (vx, py): vector column vx of the slab, pixels py, py+ty, ..
+//   MODE 0: y = act(x*A + Bz), fstats[b, g] = (sum x, sum x^2)      (same layout the two-kernel path writes)
+//   MODE 1: dx = dz*A - x*P + Q (+ add), from the saved forward sums
+__device__ __forceinline__ float gn_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+struct GnOwnGeom {
+  int HW, C, G, cpg, gpc, nv, ty;  // nv = gpc*cpg/8 vectors per pixel of the slab; block = nv x ty threads
+};
+template <int MODE>
+__global__ void __launch_bounds__(512, 1)
+gn_group_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, const __half* __restrict__ gamma,
+                const __half* __restrict__ beta, float* __restrict__ fstats, const __half* __restrict__ add,
+                __half* __restrict__ out, GnOwnGeom g, float eps, int silu) {
+  extern __shared__ uint4 gsm[];
+  const int nthr = g.nv * g.ty;
+  float* part = reinterpret_cast<float*>(gsm);                   // [nthr][2 groups][2]
+  float* tot = part + (size_t)nthr * 4;                          // [gpc][2] block totals (+ padding to 16 floats)
+  uint4* sx = reinterpret_cast<uint4*>(tot + 16);                // [HW][nv]
+  uint4* sdy = sx + (size_t)g.HW * g.nv;                         // MODE 1: [HW][nv]
+  const int tid = threadIdx.x;
+  const int vx = tid % g.nv, py = tid / g.nv;
+  const int b = blockIdx.y, gc = blockIdx.x;
+  const int c0 = gc * g.gpc * g.cpg;                             // first channel of the slab
+  const size_t base = (size_t)b * g.HW * g.C + c0 + (size_t)vx * 8;
+  const float inv_n = 1.f / ((float)g.HW * g.cpg);
+  // the (at most two, cpg >= 8) groups this thread's 8 channels fall into, relative to the slab
+  const int lg0 = (vx * 8) / g.cpg;
+  const int split = (lg0 + 1) * g.cpg - vx * 8;                  // channels i >= split belong to group lg0 + 1
+  float gm[8], bt[8], A[8], Bz[8];
+  unpack8(*reinterpret_cast<const uint4*>(gamma + c0 + vx * 8), gm);
+  unpack8(*reinterpret_cast<const uint4*>(beta + c0 + vx * 8), bt);
+  if (MODE == 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int grp = gc * g.gpc + lg0 + (i >= split);
+      const float2 st = *reinterpret_cast<const float2*>(fstats + ((size_t)b * g.G + grp) * 2);
+      const float mean = st.x * inv_n;
+      const float rstd = rsqrtf(fmaxf(st.y * inv_n - mean * mean, 0.f) + eps);
+      A[i] = rstd * gm[i];
+      Bz[i] = bt[i] - mean * A[i];
+    }
+  }
+  float s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+  constexpr int U = MODE == 0 ? 4 : 2;
+  for (int p = py; p < g.HW; p += U * g.ty) {
+    uint4 qx[U], qd[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pp = p + u * g.ty;
+      if (pp < g.HW) {
+        qx[u] = *reinterpret_cast<const uint4*>(x + base + (size_t)pp * g.C);
+        if (MODE == 1) qd[u] = *reinterpret_cast<const uint4*>(dy + base + (size_t)pp * g.C);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pp = p + u * g.ty;
+      if (pp >= g.HW) break;
+      sx[(size_t)pp * g.nv + vx] = qx[u];
+      float xf[8];
+      unpack8(qx[u], xf);
+      if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s1[i] += xf[i];
+          s2[i] += xf[i] * xf[i];
+        }
+      } else {
+        sdy[(size_t)pp * g.nv + vx] = qd[u];
+        float df[8];
+        unpack8(qd[u], df);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float z = xf[i] * A[i] + Bz[i];
+          float dz = df[i];
+          if (silu) dz *= silu_grad(z);
+          s1[i] += dz * gm[i];
+          s2[i] += dz * (z - bt[i]);
+        }
+      }
+    }
+  }
+  // per-thread sums of its two groups -> block totals (fixed order: deterministic)
+  {
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < split) {
+        a0 += s1[i];
+        a1 += s2[i];
+      } else {
+        b0 += s1[i];
+        b1 += s2[i];
+      }
+    }
+    *reinterpret_cast<float4*>(part + (size_t)tid * 4) = make_float4(a0, a1, b0, b1);
+  }
+  __syncthreads();
+  if (tid < 32) {
+    // lane l sums the threads whose vector column is l, l+32, ..: each (column -> groups) mapping is fixed
+    for (int lg = 0; lg < g.gpc; ++lg) {
+      float t1 = 0.f, t2 = 0.f;
+      for (int t = tid; t < nthr; t += 32) {
+        const int tv = t % g.nv;
+        const int tg0 = (tv * 8) / g.cpg;
+        const float4 q = *reinterpret_cast<const float4*>(part + (size_t)t * 4);
+        if (tg0 == lg) {
+          t1 += q.x;
+          t2 += q.y;
+        } else if (tg0 + 1 == lg) {
+          t1 += q.z;
+          t2 += q.w;
+        }
+      }
+      t1 = gn_warp_sum(t1);
+      t2 = gn_warp_sum(t2);
+      if (tid == 0) {
+        tot[lg * 2] = t1;
+        tot[lg * 2 + 1] = t2;
+        if (MODE == 0) {
+          fstats[((size_t)b * g.G + gc * g.gpc + lg) * 2] = t1;
+          fstats[((size_t)b * g.G + gc * g.gpc + lg) * 2 + 1] = t2;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  float P[8], Q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int lg = lg0 + (i >= split);
+    const float t1 = lg < g.gpc ? tot[lg * 2] : 0.f, t2 = lg < g.gpc ? tot[lg * 2 + 1] : 0.f;
+    if (MODE == 0) {
+      const float mean = t1 * inv_n;
+      const float rstd = rsqrtf(fmaxf(t2 * inv_n - mean * mean, 0.f) + eps);
+      A[i] = rstd * gm[i];
+      Bz[i] = bt[i] - mean * A[i];
+    } else {
+      // A = rstd*gamma, Bz = beta - mean*A  =>  rstd = A/gamma is not safe (gamma may be 0): recompute from the sums
+      const int grp = gc * g.gpc + lg0 + (i >= split);
+      const float2 st = *reinterpret_cast<const float2*>(fstats + ((size_t)b * g.G + grp) * 2);
+      const float mean = st.x * inv_n;
+      const float rstd = rsqrtf(fmaxf(st.y * inv_n - mean * mean, 0.f) + eps);
+      P[i] = rstd * rstd * (t2 * inv_n);
+      Q[i] = mean * P[i] - rstd * (t1 * inv_n);
+    }
+  }
+  for (int p = py; p < g.HW; p += g.ty) {
+    float xf[8], o[8];
+    unpack8(sx[(size_t)p * g.nv + vx], xf);
+    if (MODE == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float z = xf[i] * A[i] + Bz[i];
+        o[i] = silu ? silu_f(z) : z;
+      }
+    } else {
+      float df[8];
+      unpack8(sdy[(size_t)p * g.nv + vx], df);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float dz = df[i];
+        if (silu) dz *= silu_grad(xf[i] * A[i] + Bz[i]);
+        o[i] = dz * A[i] - xf[i] * P[i] + Q[i];
+      }
+      if (add) {
+        float af[8];
+        unpack8(*reinterpret_cast<const uint4*>(add + base + (size_t)p * g.C), af);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += af[i];
+      }
+    }
+    *reinterpret_cast<uint4*>(out + base + (size_t)p * g.C) = pack8(o);
+  }
+}
+
+// Geometry of the group-owner kernel, or 0 if the shape does not qualify (slab too large, misaligned, grid too small).
+static int gn_own_geom(GnOwnGeom& o, int B, int HW, int C, int G, int bwd) {
+  static const bool off = getenv("TB_GN_NO_GROUP_OWNER") != nullptr;  // diagnostic switch
+  if (off || C % G != 0) return 0;
+  const int cpg = C / G;
+  if (cpg < 8) return 0;
+  int gpc = 0;
+  for (int c = 1; c <= 2; c *= 2)
+    if (G % c == 0 && (c * cpg) % 8 == 0) {
+      gpc = c;
+      break;
+    }
+  if (!gpc) return 0;
+  const int nv = gpc * cpg / 8;
+  if (nv > 64) return 0;
+  const long long slab = (long long)HW * nv * 16 * (bwd ? 2 : 1);
+  const int ty = 512 / nv;
+  const long long smem = slab + (long long)nv * ty * 16 + 64;
+  if (smem > 200 * 1024 || B * (G / gpc) < 48) return 0;
+  o.HW = HW; o.C = C; o.G = G; o.cpg = cpg; o.gpc = gpc; o.nv = nv; o.ty = ty;
+  return (int)smem;
+}
+
 static int gn_geom(GnGeom& g, int B, int HW, int C, int G) {
   TB_REQUIRE(C % 8 == 0 && G > 0 && C % G == 0, TB_E_SHAPE, "groupnorm: C=%d G=%d unsupported", C, G);
   g.HW = HW;
@@ -270,7 +478,12 @@ static int gn_geom(GnGeom& g, int B, int HW, int C, int G) {
   g.k = g.nvec >= 256 ? 1 : 256 / g.nvec;
   // pixels per CTA: aim at >= 4 CTAs per SM over the whole batch (the small 8x8 / 16x16 levels otherwise run on
   // a few dozen CTAs, each a chain of dependent loads), at most 16 pixels per thread
-  const int want_x = (4 * num_sms() + B - 1) / B;
+  // Measured (scripts/probe_gn.py, graph replay): tensors of >= 16 MB want ~4 CTAs per SM over the batch, the smaller
+  // levels 2 -- there the kernels are a chain of launch + prologue + atomics latencies and fewer, fatter CTAs win
+  // ([8,1024,640] backward 33.0 -> 23.7 us, [8,64,1280] 18.2 -> 12.6 us, [8,256,2560] 40.2 -> 22.7 us).
+  static const int forced = getenv("TB_GN_CTAS_PER_SM") ? atoi(getenv("TB_GN_CTAS_PER_SM")) : 0;  // tuning knob
+  const int ctas_per_sm = forced ? forced : ((long long)B * HW * C * 2 >= (16ll << 20) ? 4 : 2);
+  const int want_x = (ctas_per_sm * num_sms() + B - 1) / B;
   int per_thread = (HW + want_x * g.k - 1) / (want_x * g.k);
   per_thread = per_thread < 1 ? 1 : per_thread > 16 ? 16 : per_thread;
   g.ppc = g.k * per_thread;
@@ -601,18 +814,48 @@ extern "C" int tb_groupnorm_fwd_f16(const void* x, const void* gamma, const void
   cudaStream_t st = (cudaStream_t)stream;
   const bool zeroed = (silu & TB_GN_STATS_ZEROED) != 0;  // the caller hands out slices of one buffer it cleared once
   silu &= 1;
+  {
+    GnOwnGeom o;
+    const int smem = gn_own_geom(o, B, HW, C, G, 0);
+    if (smem) {
+      static bool configured = false;
+      if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gn_group_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        TB_REQUIRE(e == cudaSuccess, TB_E_CUDA, "cudaFuncSetAttribute(gn_group_kernel<0>): %s", cudaGetErrorString(e));
+        configured = true;
+      }
+      gn_group_kernel<0><<<dim3(G / o.gpc, B), o.nv * o.ty, smem, st>>>(
+          (const __half*)x, nullptr, (const __half*)gamma, (const __half*)beta, stats, nullptr, (__half*)y, o, eps, silu);
+      return check_launch("gn_group_kernel<0>");
+    }
+  }
   if (!zeroed) {
     cudaError_t e = cudaMemsetAsync(stats, 0, (size_t)B * G * 2 * sizeof(float), st);
     TB_REQUIRE(e == cudaSuccess, TB_E_CUDA, "groupnorm memset: %s", cudaGetErrorString(e));
   }
   dim3 grid((HW + g.ppc - 1) / g.ppc, B);
   const int threads = g.nvec * g.k;
-  gn_stats_kernel<0><<<grid, threads, 2 * G * sizeof(float), st>>>(
-      (const __half*)x, nullptr, nullptr, nullptr, nullptr, stats, g, eps, silu);
-  if ((rc = check_launch("gn_stats_kernel<0>"))) return rc;
-  gn_apply_kernel<0><<<grid, threads, 0, st>>>((const __half*)x, nullptr, (const __half*)gamma,
-                                              (const __half*)beta, stats, nullptr, nullptr, (__half*)y, g,
-                                              eps, silu);
+#define TB_GN_FWD(U, MINB)                                                                                       \
+  do {                                                                                                            \
+    gn_stats_kernel<0, U, MINB><<<grid, threads, 2 * G * sizeof(float), st>>>(                                    \
+        (const __half*)x, nullptr, nullptr, nullptr, nullptr, stats, g, eps, silu);                               \
+    if ((rc = check_launch("gn_stats_kernel<0>"))) return rc;                                                     \
+    gn_apply_kernel<0, U, MINB><<<grid, threads, 0, st>>>((const __half*)x, nullptr, (const __half*)gamma,        \
+                                                         (const __half*)beta, stats, nullptr, nullptr, (__half*)y, \
+                                                         g, eps, silu);                                           \
+  } while (0)
+  static const int variant = getenv("TB_GN_FWD_VARIANT") ? atoi(getenv("TB_GN_FWD_VARIANT")) : 43;  // tuning knob
+  switch (variant) {
+    case 42: TB_GN_FWD(4, 2); break;
+    case 44: TB_GN_FWD(4, 4); break;
+    case 83: TB_GN_FWD(8, 3); break;
+    case 84: TB_GN_FWD(8, 4); break;
+    case 82: TB_GN_FWD(8, 2); break;
+    // 4 loads in flight per thread at 3 CTAs per SM: 25.0 -> 20.8 us at [8,4096,320] against 8 loads at 2 CTAs (the
+    // kernels wait on dependent ALU results, not on memory: more resident warps fill the issue slots)
+    default: TB_GN_FWD(4, 3); break;
+  }
+#undef TB_GN_FWD
   return check_launch("gn_apply_kernel<0>");
 }
 
@@ -628,19 +871,47 @@ extern "C" int tb_groupnorm_bwd_f16(const void* dy, const void* x, const void* g
   cudaStream_t st = (cudaStream_t)stream;
   const bool zeroed = (silu & TB_GN_STATS_ZEROED) != 0;
   silu &= 1;
+  {
+    GnOwnGeom o;
+    const int smem = gn_own_geom(o, B, HW, C, G, 1);
+    if (smem) {
+      static bool configured = false;
+      if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gn_group_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        TB_REQUIRE(e == cudaSuccess, TB_E_CUDA, "cudaFuncSetAttribute(gn_group_kernel<1>): %s", cudaGetErrorString(e));
+        configured = true;
+      }
+      gn_group_kernel<1><<<dim3(G / o.gpc, B), o.nv * o.ty, smem, st>>>(
+          (const __half*)x, (const __half*)dy, (const __half*)gamma, (const __half*)beta, const_cast<float*>(stats),
+          (const __half*)add, (__half*)dx, o, eps, silu);
+      return check_launch("gn_group_kernel<1>");
+    }
+  }
   if (!zeroed) {
     cudaError_t e = cudaMemsetAsync(dstats, 0, (size_t)B * G * 2 * sizeof(float), st);
     TB_REQUIRE(e == cudaSuccess, TB_E_CUDA, "groupnorm memset: %s", cudaGetErrorString(e));
   }
   dim3 grid((HW + g.ppc - 1) / g.ppc, B);
   const int threads = g.nvec * g.k;
-  gn_stats_kernel<1><<<grid, threads, 2 * G * sizeof(float), st>>>(
-      (const __half*)x, (const __half*)dy, (const __half*)gamma, (const __half*)beta, stats, dstats, g,
-      eps, silu);
-  if ((rc = check_launch("gn_stats_kernel<1>"))) return rc;
-  gn_apply_kernel<1><<<grid, threads, 0, st>>>((const __half*)x, (const __half*)dy,
-                                              (const __half*)gamma, (const __half*)beta, stats, dstats,
-                                              (const __half*)add, (__half*)dx, g, eps, silu);
+#define TB_GN_BWD(U, MINB)                                                                                       \
+  do {                                                                                                            \
+    gn_stats_kernel<1, U, MINB><<<grid, threads, 2 * G * sizeof(float), st>>>(                                    \
+        (const __half*)x, (const __half*)dy, (const __half*)gamma, (const __half*)beta, stats, dstats, g, eps,    \
+        silu);                                                                                                    \
+    if ((rc = check_launch("gn_stats_kernel<1>"))) return rc;                                                     \
+    gn_apply_kernel<1, U, MINB><<<grid, threads, 0, st>>>((const __half*)x, (const __half*)dy,                    \
+                                                         (const __half*)gamma, (const __half*)beta, stats, dstats, \
+                                                         (const __half*)add, (__half*)dx, g, eps, silu);          \
+  } while (0)
+  static const int variant = getenv("TB_GN_BWD_VARIANT") ? atoi(getenv("TB_GN_BWD_VARIANT")) : 22;  // tuning knob
+  switch (variant) {
+    case 42: TB_GN_BWD(4, 2); break;
+    case 43: TB_GN_BWD(4, 3); break;
+    case 23: TB_GN_BWD(2, 3); break;
+    case 41: TB_GN_BWD(4, 1); break;
+    default: TB_GN_BWD(2, 2); break;  // 47.5 -> 41.2 us at [8,4096,320] against 4+4 loads at one CTA per SM
+  }
+#undef TB_GN_BWD
   return check_launch("gn_apply_kernel<1>");
 }
 
