@@ -46,6 +46,7 @@ struct GemmParams {
   // bumps counters[tile], and the last arriver adds the partials in split order and runs the epilogue
   int splits;         // 1 = off
   int kb_per_split;
+  int experiment;     // timing experiments only (TB_GEMM_EXPERIMENT): 1 = skip the B-operand loads, 2 = skip the A loads
   float* ws;          // [num_tiles * splits][128][BN] fp32
   int* counters;      // [num_tiles], zero between launches (the fixing CTA resets its tile's counter)
 };
@@ -147,8 +148,9 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
           const uint32_t fb = smem_u32(&full_bar[stage]);
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_STAGE_BYTES;
-          mbar_expect_tx(fb, p.a_stage_bytes + B_STAGE_BYTES);
-          if (CONV) {
+          mbar_expect_tx(fb, (p.experiment == 2 ? 0 : p.a_stage_bytes) + (p.experiment == 1 ? 0 : B_STAGE_BYTES));
+          if (p.experiment == 2) {
+          } else if (CONV) {
             const int tap = kb / p.kb_per_tap;
             const int c0 = (kb - tap * p.kb_per_tap) * BK;
             const int ky = tap / 3, kx = tap - ky * 3;
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
           } else {
             tma_load_2d(sa, &tmA, fb, kb * BK, m_tile * BM);
           }
-          tma_load_2d(sb, &tmB, fb, kb * BK, n_tile * BN);
+          if (p.experiment != 1) tma_load_2d(sb, &tmB, fb, kb * BK, n_tile * BN);
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -572,6 +574,10 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
                        GemmParams& p, int m_tiles, cudaStream_t st) {
   p.n_tiles = (p.N + BN - 1) / BN;
   p.m_tiles = m_tiles;
+  {
+    static const int ex = getenv("TB_GEMM_EXPERIMENT") ? atoi(getenv("TB_GEMM_EXPERIMENT")) : 0;
+    p.experiment = ex;
+  }
   plan_split(p, BN, p.n_tiles * m_tiles, st);
   static const bool no_fast = getenv("TB_GEMM_NO_FAST_EPILOGUE") != nullptr;  // diagnostic switch
   const bool fast = BN >= 64 && !no_fast && p.splits == 1 && p.tma_store == 1 && p.out_kind == TB_OUT_F16 &&
