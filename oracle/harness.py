@@ -104,6 +104,8 @@ def lora_grads_flat(trainer, ref_grads: Dict[str, torch.Tensor], buf: torch.Tens
     st = trainer.te.state
     r = st.r
     ours, refs, worst = [], [], 0.0
+    if not r:  # --lora_rank 0: only the embedding rows train (train_textboost.py:700, 722)
+        return torch.zeros(0), torch.zeros(0), 0.0
     for l in range(st.n_layers):
         for ti, t in enumerate(targets_of(trainer)):
             n = f"text_model.encoder.layers.{l}.self_attn.{t}."
@@ -171,8 +173,11 @@ def compare_step(trainer, batch: Dict[str, torch.Tensor], device="cpu", dtype=to
     out = {"loss": loss.item(), "loss_ref": ref["loss"].item(),
            "pred_rel": rel_max(trainer._pred, ref["pred"])}
     go, gr, worst = lora_grads_flat(trainer, ref["grad_lora"], g)
-    out["lora_grad_rel_l2"] = ((go - gr).norm() / gr.norm()).item()
-    out["lora_grad_cos"] = torch.nn.functional.cosine_similarity(go, gr, dim=0).item()
+    if go.numel():
+        out["lora_grad_rel_l2"] = ((go - gr).norm() / gr.norm()).item()
+        out["lora_grad_cos"] = torch.nn.functional.cosine_similarity(go, gr, dim=0).item()
+    else:
+        out["lora_grad_rel_l2"], out["lora_grad_cos"] = 0.0, 1.0
     out["lora_grad_worst_tensor_rel"] = worst
     out["lora_grad_ours"], out["lora_grad_ref"] = go, gr
     out["pred_ref"] = ref["pred"].detach().float().cpu()
@@ -200,13 +205,16 @@ def compare_step(trainer, batch: Dict[str, torch.Tensor], device="cpu", dtype=to
         p_ours, p_ref = [], []
         r = st.r
         for l, lyr in enumerate(te.text_model.encoder.layers):
-            for ti, t in enumerate(targets_of(trainer)):
+            for ti, t in enumerate(targets_of(trainer) if r else ()):
                 m = getattr(lyr.self_attn, t)
                 p_ours += [st.A(l)[ti * r:(ti + 1) * r].detach().cpu().flatten(), st.B(l)[ti].detach().cpu().flatten()]
                 p_ref += [m.lora_A["default"].weight.detach().cpu().flatten(),
                           m.lora_B["default"].weight.detach().cpu().flatten()]
-        po, pr = torch.cat(p_ours), torch.cat(p_ref)
-        out["lora_param_max_abs_diff"] = (po - pr).abs().max().item()
+        if p_ours:
+            po, pr = torch.cat(p_ours), torch.cat(p_ref)
+            out["lora_param_max_abs_diff"] = (po - pr).abs().max().item()
+        else:
+            out["lora_param_max_abs_diff"] = 0.0
         out["frozen_decay"] = trainer.opt_state[5].item()
         base0 = trainer.synthetic["clip_sd"]["text_model.embeddings.token_embedding.weight"][5].float().cpu()
         out["frozen_decay_ref"] = (emb[5].cpu() / base0).mean().item()

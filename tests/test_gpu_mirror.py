@@ -164,7 +164,15 @@ def test_cli_end_to_end_synthetic_checkpoint(tmp_path):
     assert T.RUN_INFO["prior_prompts"] == 18
     # modes outside the built path fail loudly rather than silently training something else
     with pytest.raises(NotImplementedError):
-        T.main(T.parse_args(base + ["--lora_rank", "0"]))
+        T.main(T.parse_args(base + ["--unet_params_to_train", "crossattn_kv"]))
+    # --lora_rank 0: textual inversion only (train_textboost.py:700, 722, 1237): the embeddings train, no adapter is
+    # written; with a cosine schedule over the run and two accumulated micro-batches per optimiser step
+    out0 = str(tmp_path / "out0")
+    base0 = [a if a != out else out0 for a in base]
+    loss0 = T.main(T.parse_args(base0 + ["--lora_rank", "0", "--max_train_steps", "6", "--lr_scheduler", "cosine",
+                                         "--lr_warmup_steps", "2", "--gradient_accumulation_steps", "2"]))
+    assert loss0 == loss0 and "text_encoder" not in os.listdir(out0) and "dog.bin" in os.listdir(out0)
+    assert torch.load(os.path.join(out0, "dog.bin"))["<dog>"].shape == (128,)
 
 
 def test_cli_trains_from_images_through_vae_front_end(tmp_path):

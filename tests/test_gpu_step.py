@@ -284,6 +284,29 @@ def test_step_tiny_vs_oracle(kpl_type, mixing, pred):
     assert r["lora_param_max_abs_diff"] <= 2.1 * tr.lr
 
 
+def test_step_lora_rank_zero_vs_oracle():
+    """--lora_rank 0 (train_textboost.py:700-722): no adapter, frozen encoder; the added embedding rows are the only
+    trainable state (textual inversion).  Three captured-graph steps keep tracking the oracle."""
+    from oracle import harness, step_ref
+    from textboost_b200 import synthetic
+    tr = synthetic.build_trainer("tiny", dev, seed=1, n_added=2, lora_r=0, keep_sd=True, emb_learning_rate=1e-2)
+    V = tr.synthetic["clip_cfg"].vocab_size
+    bt = synthetic.batch(3, 16, 3, V, dev)
+    bt["input_ids"][1, 4] = V + 1
+    r = harness.compare_step(tr, bt)
+    assert tr.te.state.n_lora == 0
+    assert abs(r["loss"] - r["loss_ref"]) < 2e-3 * abs(r["loss_ref"]) and r["pred_rel"] < 4e-3
+    assert r["row_grad_rel"] < 5e-3 and r["grad_norm"] == 0.0 and r["grad_norm_ref"] == 0.0
+    assert abs(r["added_norm"] - r["added_norm_ref"]) < 1e-4 * r["added_norm_ref"]
+    assert abs(r["frozen_decay"] - r["frozen_decay_ref"]) < 1e-6 and r["rows_after_rel"] < 5e-3
+    args = (bt["latents"], bt["noise"], bt["timesteps"], bt["input_ids"], bt["prior_ids"])
+    replay = tr.capture(*args, warmup=0)
+    for _ in range(3):
+        loss = replay(*args)
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss).all() and tr.opt_state[4].item() == 4 and tr.opt_state[8].item() == 0
+
+
 def test_step_sd15_vs_oracle():
     """configs[1]+[2] at B=2: SD-1.5 widths, 64x64 latents, CLIP-L, KPL on; oracle in fp32 on the same GPU."""
     from oracle import harness

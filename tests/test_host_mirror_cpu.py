@@ -201,12 +201,12 @@ def test_cli_rejects_what_the_reference_cannot_run():
     import train_textboost as T
     base = ["--pretrained_model_name_or_path", "x"]
     T._unsupported(T.parse_args(base))
-    for extra in (["--text_encoder_use_attention_mask"], ["--lora_rank", "0"], ["--unet_params_to_train", "crossattn_kv"],
+    for extra in (["--text_encoder_use_attention_mask"], ["--unet_params_to_train", "crossattn_kv"],
                   ["--mixed_precision", "bf16"],
                   ["--validation_prompts", "a dog", "--validation_scheduler", "DDPMScheduler"]):
         with pytest.raises(NotImplementedError):
             T._unsupported(T.parse_args(base + extra))
-    for ok in (["--gradient_accumulation_steps", "2"], ["--lr_scheduler", "cosine"]):
+    for ok in (["--gradient_accumulation_steps", "2"], ["--lr_scheduler", "cosine"], ["--lora_rank", "0"]):
         T._unsupported(T.parse_args(base + ok))  # built in round 2 (csrc/optim.cu lr_multiplier, trainer.step)
     with pytest.raises(ValueError):
         T._unsupported(T.parse_args(base + ["--gradient_accumulation_steps", "0"]))

@@ -14,12 +14,12 @@ import engine_standin
 pytestmark = pytest.mark.timeout(900, method="thread")
 
 
-def _compare(monkeypatch, B, **trainer_kw):
+def _compare(monkeypatch, B, lora_r=4, **trainer_kw):
     from oracle import harness
     from textboost_b200 import synthetic
     engine_standin.install(monkeypatch)
-    tr = synthetic.build_trainer("tiny", "cpu", seed=1, n_added=2, lora_b_std=0.02, keep_sd=True, learning_rate=1e-4,
-                                 **trainer_kw)
+    tr = synthetic.build_trainer("tiny", "cpu", seed=1, n_added=2, lora_b_std=0.02 if lora_r else 0.0, keep_sd=True,
+                                 learning_rate=1e-4, lora_r=lora_r, **trainer_kw)
     V = tr.synthetic["clip_cfg"].vocab_size
     bt = synthetic.batch(B, 8, 3, V, "cpu")
     bt["input_ids"][1, 4] = V + 1
@@ -103,6 +103,18 @@ def test_three_steps_track_the_oracle(monkeypatch):
     assert worst <= 3 * 2.1 * tr.lr, worst
     emb = te.get_input_embeddings().weight.detach()
     assert harness.rel_max(st.rows(), emb[V:]) < 5e-2
+
+
+def test_lora_rank_zero_trains_only_the_added_rows(monkeypatch):
+    """--lora_rank 0 (train_textboost.py:700-722): no adapter, frozen encoder, the added embedding rows are the only
+    trainable state; nothing to clip (grad norm 0), frozen rows still decay (D8)."""
+    r, tr, _ = _compare(monkeypatch, 2, kpl_type="cos", lora_r=0)
+    assert tr.te.state.n_lora == 0 and tr.te.state.n_rows == 2
+    assert abs(r["loss"] - r["loss_ref"]) < 2e-3 * abs(r["loss_ref"]) and r["pred_rel"] < 4e-3
+    assert r["row_grad_rel"] < 5e-3
+    assert r["grad_norm"] == 0.0 and r["grad_norm_ref"] == 0.0
+    assert abs(r["added_norm"] - r["added_norm_ref"]) < 2e-3 * r["added_norm_ref"]
+    assert abs(r["frozen_decay"] - r["frozen_decay_ref"]) < 1e-6 and r["rows_after_rel"] < 5e-3
 
 
 def test_gradient_accumulation_equals_one_step_over_the_joined_batch(monkeypatch):

@@ -266,6 +266,29 @@ class ClipEngine:
             self._ctx.append((ids, saved, x, stf))
         return out.view(B, Lq, D)
 
+    @staticmethod
+    def split_ctx(ctx, n_first: int):
+        """Split the saved context of ONE forward over a concatenated batch [first n_first prompts | rest] into two
+        contexts that backward() accepts independently (every saved tensor is row-major over prompts x tokens, so the
+        halves are views).  The trainer encodes the instance and the prior prompts in one pass -- the kernels at 616 or
+        1232 rows cost the same latency -- and runs their backwards at different times."""
+        ids, saved, xf, stf = ctx
+        B, Lq = ids.shape
+        m = n_first * Lq
+
+        def cut(t, lo):
+            if t is None:
+                return None
+            if t.dim() == 3 and t.shape[0] == B:      # lse [B, heads, L]
+                return t[:n_first] if lo else t[n_first:]
+            return t[:m] if lo else t[m:]             # [B*L, ...] activations / statistics
+
+        halves = []
+        for lo in (True, False):
+            halves.append((ids[:n_first] if lo else ids[n_first:], [tuple(cut(t, lo) for t in layer) for layer in saved],
+                           cut(xf, lo), cut(stf, lo)))
+        return halves
+
     def pop_ctx(self):
         """Detach the context of the most recent forward(save_for_backward=True) (autograd wrappers keep it
         on their own ctx so several forwards can be outstanding, as in train_textboost.py:1054-1100)."""

@@ -141,8 +141,8 @@ def _unsupported(args):
                          "end: it cannot be combined with --latents_file / --synthetic_data")
     if args.unet_params_to_train != "none":
         raise NotImplementedError("--unet_params_to_train: the UNet is frozen on this path (SURVEY.md §8 f4)")
-    if args.lora_rank <= 0:
-        raise NotImplementedError("--lora_rank 0 (full text-encoder fine-tune) is not built (SURVEY.md §8 f4)")
+    if args.lora_rank < 0:
+        raise ValueError("--lora_rank must be >= 0")
     if args.gradient_accumulation_steps < 1:
         raise ValueError("--gradient_accumulation_steps must be >= 1")
     if args.mixed_precision not in (None, "fp16"):
@@ -389,9 +389,13 @@ def main(args):
 
     unet.eval().requires_grad_(False)
     text_encoder.requires_grad_(False)
-    text_encoder.text_model.encoder.requires_grad_(True)
-    text_encoder.add_adapter(LoraConfig(r=args.lora_rank, lora_alpha=args.lora_rank, init_lora_weights="gaussian",
-                                        target_modules=["q_proj", "k_proj", "v_proj"]))
+    if args.lora_rank > 0:  # train_textboost.py:700-709
+        text_encoder.text_model.encoder.requires_grad_(True)
+        text_encoder.add_adapter(LoraConfig(r=args.lora_rank, lora_alpha=args.lora_rank, init_lora_weights="gaussian",
+                                            target_modules=["q_proj", "k_proj", "v_proj"]))
+    # --lora_rank 0: no adapter and the encoder stays frozen (the reference only un-freezes it inside the branch
+    # above, :700-701), so the added embedding rows are the only trainable state -- plain textual inversion; the
+    # optimiser's second parameter group is empty and the gradient clipping (:1128-1133) has nothing to clip
     text_encoder.get_input_embeddings().requires_grad_(True)
     n_lora = sum(p.numel() for n, p in text_encoder.named_parameters() if "lora" in n)
     logger.info(f"trainable: {n_lora} LoRA floats + {len(added_tokens) + len(aug_token_dict)} embedding rows")
