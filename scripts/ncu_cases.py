@@ -4,7 +4,7 @@
       python scripts/ncu_cases.py [case ...]
 
 Each case runs twice untimed, then once between cudaProfilerStart/Stop.  Numbers printed under ncu are not
-bench values.  Cases: gemm_k320 gemm_m2048 gemm_clip conv_h8 conv_h64 gn attn ln geglu
+bench values.  Cases: every case_* function below (gemm_*, conv_*, gn*, attn*, clip_glue, ln, geglu)
 """
 import sys
 
@@ -88,6 +88,101 @@ def case_attn():
         o, lse = ops.attn_fwd(q, k, v, H)
         ops.attn_bwd(q, k, v, o, do, lse, H)
     return run
+
+
+def _attn_case(B, H, Nq, Nk, d, causal=False, dq_out=None):
+    Cc = H * d
+    if Nq == Nk:
+        qkv = rnd(B, Nq, 3 * Cc)
+        q, k, v = qkv[..., :Cc], qkv[..., Cc:2 * Cc], qkv[..., 2 * Cc:]
+    else:
+        q, kv = rnd(B, Nq, Cc), rnd(B, Nk, 2 * Cc)
+        k, v = kv[..., :Cc], kv[..., Cc:]
+    do = rnd(B, Nq, Cc)
+
+    def run():
+        o, lse = ops.attn_fwd(q, k, v, H, causal=causal)
+        ops.attn_bwd(q, k, v, o, do, lse, H, causal=causal, dq_out=dq_out)
+    return run
+
+
+def case_attn_d80():    # 32x32 level self-attention
+    return _attn_case(8, 8, 1024, 1024, 80)
+
+
+def case_attn_d160():   # 16x16 level self-attention
+    return _attn_case(8, 8, 256, 256, 160)
+
+
+def case_attn_cross():  # 64x64 level cross-attention over the 77 text tokens: fp16 dQ straight out of the kernel
+    return _attn_case(8, 8, 4096, 77, 40, dq_out=True)
+
+
+def case_attn_cross_d80():
+    return _attn_case(8, 8, 1024, 77, 80, dq_out=True)
+
+
+def case_attn_clip():   # text encoder: causal, 12 heads x 64, 77 tokens
+    return _attn_case(8, 12, 77, 77, 64, causal=True, dq_out=True)
+
+
+def case_gn_mid():      # 32x32 level: the single-launch group-owner kernel
+    x, g, b = rnd(8, 1024, 640), rnd(640), rnd(640)
+    dy = rnd(8, 1024, 640)
+
+    def run():
+        y, st = ops.groupnorm(x, g, b, 32, 1e-5, True)
+        ops.groupnorm_bwd(dy, x, g, b, st, 32, 1e-5, True, add=dy)
+    return run
+
+
+def case_clip_glue():   # text-encoder LayerNorm + LoRA kernels and the LoRA gradient kernel at 8 x 77 rows
+    M, D, R, RP = 616, 768, 12, 16
+    x, gamma, beta = rnd(M, D, dtype=torch.float32), rnd(D, dtype=torch.float32), rnd(D, dtype=torch.float32)
+    A = rnd(R, D, dtype=torch.float32, s=0.3)
+    y_ext, dy_ext, dqkv = rnd(M, D + RP), rnd(M, D + RP), rnd(M, 3 * D)
+    g32, g16 = rnd(M, D, dtype=torch.float32), rnd(M, D)
+    dB, dA = torch.zeros(3, D, 4, device=dev), torch.zeros(R, D, device=dev)
+
+    def run():
+        st = ops.layernorm_lora_fwd(x, gamma, beta, A, y_ext, RP)
+        ops.layernorm_bwd_clip(dy_ext, x, gamma, st, add=g32, out=g32, out16=g16, lora_a=A)
+        C.call("tb_lora_grad", C.ptr(dqkv), C.ptr(y_ext), C.ptr(dy_ext), D + RP, C.ptr(dB), C.ptr(dA), M, 3, 7, D, 4,
+               1.0, C.stream_ptr())
+    return run
+
+
+def _clip_glue_parts():
+    M, D, R, RP = 616, 768, 12, 16
+    x, gamma, beta = rnd(M, D, dtype=torch.float32), rnd(D, dtype=torch.float32), rnd(D, dtype=torch.float32)
+    A = rnd(R, D, dtype=torch.float32, s=0.3)
+    y_ext, dy_ext, dqkv = rnd(M, D + RP), rnd(M, D + RP), rnd(M, 3 * D)
+    g32, g16 = rnd(M, D, dtype=torch.float32), rnd(M, D)
+    dB, dA = torch.zeros(3, D, 4, device=dev), torch.zeros(R, D, device=dev)
+    st = ops.layernorm_lora_fwd(x, gamma, beta, A, y_ext, RP)
+    return {
+        "fwd": lambda: ops.layernorm_lora_fwd(x, gamma, beta, A, y_ext, RP),
+        "bwd": lambda: ops.layernorm_bwd_clip(dy_ext, x, gamma, st, add=g32, out=g32, out16=g16, lora_a=A),
+        "bwd_plain": lambda: ops.layernorm_bwd_clip(dy_ext[:, :D], x, gamma, st, add=g32, out=g32, out16=g16),
+        "grad": lambda: C.call("tb_lora_grad", C.ptr(dqkv), C.ptr(y_ext), C.ptr(dy_ext), D + RP, C.ptr(dB), C.ptr(dA),
+                               M, 3, 7, D, 4, 1.0, C.stream_ptr()),
+    }
+
+
+def case_clip_ln_fwd():
+    return _clip_glue_parts()["fwd"]
+
+
+def case_clip_ln_bwd():
+    return _clip_glue_parts()["bwd"]
+
+
+def case_clip_ln_bwd_plain():
+    return _clip_glue_parts()["bwd_plain"]
+
+
+def case_clip_lora_grad():
+    return _clip_glue_parts()["grad"]
 
 
 def case_ln():

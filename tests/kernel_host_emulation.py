@@ -358,7 +358,8 @@ static inline uint32_t pack_half2(float a, float b) {
 }
 float sg[1 << 16];
 __half sw[1 << 17];
-uint4 gsm[1 << 14];  // dynamic shared memory of gn_group_kernel
+uint4 gsm[1 << 14];      // dynamic shared memory of gn_group_kernel
+uint4 ln_smem[1 << 14];  // ... of ln_lora_fwd_kernel / ln_bwd_clip_kernel (the staged LoRA down-projection matrix)
 }
 // A process-wide pool of OS threads (never torn down: the workers sleep on a barrier until the process exits) runs every
 // launch: worker t plays CUDA thread t of each block in turn; thread 0 installs the block's barriers between two

@@ -55,7 +55,7 @@ def test_groupnorm_entry_points(abi, B, HW, C, G, silu):
     _close(stats[..., 1], (xs * xs).sum((1, 3)), 1e-3)
 
 
-@pytest.mark.parametrize("M,D,R,RPAD", [(11, 768, 12, 16), (5, 1024, 40, 48)])
+@pytest.mark.parametrize("M,D,R,RPAD", [(11, 768, 12, 16), (5, 1024, 40, 48), (9, 128, 12, 16)])
 def test_text_encoder_layernorm_with_lora_glue(abi, M, D, R, RPAD):
     """tb_layernorm_lora_fwd / tb_layernorm_bwd_clip (LayerNorm + LoRA down-projection; LayerNorm backward + the
     down-projection's input-gradient + the fp16 copy) run from the product source on the host."""

@@ -314,7 +314,8 @@ def test_attention_causal(B, H, N, d):
         assert relerr(dqkv[..., Cc:2 * Cc], dk) < 1e-3 and relerr(dqkv[..., 2 * Cc:], dv) < 1e-3
 
 
-@pytest.mark.parametrize("M,D,R,RPAD", [(616, 768, 12, 16), (77, 1024, 48, 48), (19, 768, 4, 16), (1232, 768, 64, 64)])
+@pytest.mark.parametrize("M,D,R,RPAD", [(616, 768, 12, 16), (77, 1024, 48, 48), (19, 768, 4, 16), (1232, 768, 64, 64),
+                                        (40, 128, 12, 16)])
 def test_text_encoder_layernorm_with_lora_glue(M, D, R, RPAD):
     """tb_layernorm_lora_fwd / tb_layernorm_bwd_clip against torch: LayerNorm on the fp32 residual stream with the LoRA
     down-projection (forward) and its input-gradient + the fp16 copy of dx (backward) in the same launch."""

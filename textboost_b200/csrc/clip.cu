@@ -135,86 +135,77 @@ __global__ void lora_pack_kernel(const float* __restrict__ Bm, __half* __restric
 // A thread owns two adjacent columns (of dY for dB, of y for dA), so every warp reads 128 contiguous bytes per
 // row; the rows are split over grid.y and the partial sums meet in fp32 atomics; the R-wide xa / dxa rows of the
 // CTA's row chunk are staged in shared memory (every thread reads the same entry: broadcast).
-constexpr int LG_ROWS = 16;  // rows per CTA: all of a thread's 16-byte row loads are in flight at once
-// Thread = 8 consecutive columns (one 16-byte load per row) x LG_ROWS rows.  Columns [0, nblk*D) are outputs of the
-// fused projection (dB of the LoRA target that owns them), columns [nblk*D, nblk*D + D) the LayerNorm output (dA).
-// The first version walked 48 rows with one half2 load per row and 4 loads in flight: 26 us of pure load latency
-// for 4 MB of operands (ncu launch list of the step); this one issues its LG_ROWS loads back to back.
-__global__ void lora_grad_kernel(const __half* __restrict__ dY, const __half* __restrict__ y_ext,
-                                 const __half* __restrict__ dA_ext, long long ld, float* __restrict__ dB,
-                                 float* __restrict__ dA, int M, int nblk, int tmask, int D, int r, float scaling) {
+constexpr int LG_ROWS = 16;  // rows per CTA: all of a thread's row loads are in flight at once
+// Thread = 2 consecutive columns (one half2 per row, a warp reads 128 contiguous bytes) x LG_ROWS rows.  Columns
+// [0, nblk*D) are outputs of the fused projection (dB of the LoRA target that owns them), columns
+// [nblk*D, nblk*D + D) the LayerNorm output (dA).  The reduction over the M = batch x 77 rows is split over grid.y
+// and finished with fp32 atomics.  Shape of the problem: 4 MB of operands, 11 MFMA -- what matters is that enough
+// warps are resident to hide the load latency (a first version with 48 serial rows per thread took 26 us, one with 8
+// columns x 16 rows per thread and 206 registers 21 us at 6 % occupancy; ncu, profiles/r02_ncu_cases_summary.txt).
+__global__ void __launch_bounds__(128)
+lora_grad_kernel(const __half* __restrict__ dY, const __half* __restrict__ y_ext,
+                 const __half* __restrict__ dA_ext, long long ld, float* __restrict__ dB,
+                 float* __restrict__ dA, int M, int nblk, int tmask, int D, int r, float scaling) {
   __shared__ float sxa[LG_ROWS][LORA_RMAX];
   __shared__ float sdx[LG_ROWS][LORA_RMAX];
   const int m0 = blockIdx.y * LG_ROWS;
   const int rows = min(LG_ROWS, M - m0);
   const int R = lora_bits(tmask) * r;
   const int NY = nblk * D;
-  const int col = 8 * (blockIdx.x * blockDim.x + threadIdx.x);
-  // this thread's operand rows first: their latency overlaps the staging of the coefficient rows below
+  const int col = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
   const bool is_b = col < NY, live = col < NY + D;
   const int t = is_b ? lora_slot(tmask, col / D) : 0;
   const bool work = live && t >= 0;
-  uint4 q[LG_ROWS];
+  // this thread's operand rows first: their latency overlaps the staging of the coefficient rows below
+  __half2 q[LG_ROWS];
   if (work) {
     const __half* src = is_b ? dY + (long long)m0 * NY + col : y_ext + (long long)m0 * ld + (col - NY);
     const long long lds = is_b ? NY : ld;
 #pragma unroll
     for (int mm = 0; mm < LG_ROWS; ++mm)
-      q[mm] = mm < rows ? *reinterpret_cast<const uint4*>(src + (long long)mm * lds) : make_uint4(0u, 0u, 0u, 0u);
+      q[mm] = mm < rows ? *reinterpret_cast<const __half2*>(src + (long long)mm * lds) : __half2{};
   }
-  for (int i = threadIdx.x; i < LG_ROWS * LORA_RMAX; i += blockDim.x) {
-    const int mm = i / LORA_RMAX, j = i % LORA_RMAX;
-    const bool ok = mm < rows && j < R;
-    sxa[mm][j] = ok ? __half2float(y_ext[(long long)(m0 + mm) * ld + D + j]) : 0.f;
-    sdx[mm][j] = ok ? __half2float(dA_ext[(long long)(m0 + mm) * ld + D + j]) : 0.f;
+  // coefficient rows: the R extension columns of y_ext (xa) and dA_ext (dxa), two per load
+  for (int i = threadIdx.x; i < LG_ROWS * (LORA_RMAX / 2); i += blockDim.x) {
+    const int mm = i / (LORA_RMAX / 2), j = 2 * (i % (LORA_RMAX / 2));
+    float2 a = {0.f, 0.f}, b = {0.f, 0.f};
+    if (mm < rows && j < R) {  // (R is even or the K extension is padded with zeros: reading j + 1 is in bounds)
+      a = __half22float2(*reinterpret_cast<const __half2*>(y_ext + (long long)(m0 + mm) * ld + D + j));
+      b = __half22float2(*reinterpret_cast<const __half2*>(dA_ext + (long long)(m0 + mm) * ld + D + j));
+      if (j + 1 >= R) a.y = b.y = 0.f;
+    }
+    sxa[mm][j] = a.x;
+    sxa[mm][j + 1] = a.y;
+    sdx[mm][j] = b.x;
+    sdx[mm][j + 1] = b.y;
   }
   __syncthreads();
   if (!work) return;
   const int jn = is_b ? r : R;            // coefficients this thread contracts with
   const int jbase = is_b ? t * r : 0;
-  for (int j0 = 0; j0 < jn; j0 += 4) {
-    float acc[8][4];
+  float v0[LG_ROWS], v1[LG_ROWS];
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[c][j] = 0.f;
+  for (int mm = 0; mm < LG_ROWS; ++mm) {
+    const float2 f = __half22float2(q[mm]);
+    v0[mm] = f.x;
+    v1[mm] = f.y;
+  }
+  for (int j = 0; j < jn; ++j) {
+    float a0 = 0.f, a1 = 0.f;
 #pragma unroll
     for (int mm = 0; mm < LG_ROWS; ++mm) {
-      const __half2* h = reinterpret_cast<const __half2*>(&q[mm]);
-      float v[8];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float2 f = __half22float2(h[c]);
-        v[2 * c] = f.x;
-        v[2 * c + 1] = f.y;
-      }
-      float w[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int jj = j0 + j < jn ? jbase + j0 + j : 0;
-        w[j] = j0 + j < jn ? (is_b ? sxa[mm][jj] : sdx[mm][jj]) : 0.f;
-      }
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[c][j] += v[c] * w[j];
+      const float w = is_b ? sxa[mm][jbase + j] : sdx[mm][jbase + j];
+      a0 += v0[mm] * w;
+      a1 += v1[mm] * w;
     }
     if (is_b) {
-      const int n = col % D;  // D % 8 == 0: the 8 columns stay inside one target block
-      float* dst = dB + ((long long)t * D + n) * r;
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (j0 + j < jn) atomicAdd(&dst[c * r + j0 + j], scaling * acc[c][j]);
+      float* dst = dB + ((long long)t * D + col % D) * r;  // D even: both columns inside one target block
+      atomicAdd(&dst[j], scaling * a0);
+      atomicAdd(&dst[r + j], scaling * a1);
     } else {
-      const int c0 = col - NY;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (j0 + j < jn) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) atomicAdd(&dA[(long long)(j0 + j) * D + c0 + c], acc[c][j]);
-        }
+      float* dst = dA + (long long)j * D + (col - NY);
+      atomicAdd(&dst[0], a0);
+      atomicAdd(&dst[1], a1);
     }
   }
 }
@@ -503,10 +494,9 @@ extern "C" int tb_lora_grad(const void* dY, const void* y_ext, const void* dA_ex
   TB_ENTER();
   TB_REQUIRE(dY && y_ext && dA_ext && dB && dA && lora_mask_ok(nblk, tmask, r, LORA_RMAX), TB_E_ARG,
              "tb_lora_grad: bad args (nblk=%d tmask=%d r=%d)", nblk, tmask, r);
-  TB_REQUIRE(D % 8 == 0 && ld % 8 == 0, TB_E_ALIGN, "tb_lora_grad: D and ld must be multiples of 8");
-  TB_REQUIRE(((uintptr_t)dY | (uintptr_t)y_ext) % 16 == 0, TB_E_ALIGN, "tb_lora_grad: dY / y_ext must be 16-byte aligned");
-  const int vecs = (nblk * D + D) / 8;
-  dim3 grid((vecs + 127) / 128, (M + LG_ROWS - 1) / LG_ROWS);
+  TB_REQUIRE(D % 2 == 0 && ld % 2 == 0, TB_E_ALIGN, "tb_lora_grad: D and ld must be even");
+  const int pairs = (nblk * D + D) / 2;
+  dim3 grid((pairs + 127) / 128, (M + LG_ROWS - 1) / LG_ROWS);
   lora_grad_kernel<<<grid, 128, 0, st>>>((const __half*)dY, (const __half*)y_ext, (const __half*)dA_ext, ld, dB, dA,
                                          M, nblk, tmask, D, r, scaling);
   return check_launch("lora_grad_kernel");

@@ -366,12 +366,28 @@ gn_group_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, con
     *reinterpret_cast<float4*>(part + (size_t)tid * 4) = make_float4(a0, a1, b0, b1);
   }
   __syncthreads();
+  // rows of threads fold pairwise (py, py + half) until one row of nv column slots is left: log2(ty) short steps
+  // with every warp busy (a single warp walking all 510 partials left the other 15 waiting at the barrier:
+  // ncu, 26-42 % of the stall samples)
+  {
+    int span = 1;
+    while (span < g.ty) span <<= 1;
+    for (int h = span >> 1; h >= 1; h >>= 1) {
+      if (py < h && py + h < g.ty) {
+        float4 a = *reinterpret_cast<const float4*>(part + (size_t)tid * 4);
+        const float4 c = *reinterpret_cast<const float4*>(part + (size_t)(tid + h * g.nv) * 4);
+        a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+        *reinterpret_cast<float4*>(part + (size_t)tid * 4) = a;
+      }
+      __syncthreads();
+    }
+  }
   if (tid < 32) {
-    // lane l sums the threads whose vector column is l, l+32, ..: each (column -> groups) mapping is fixed
+    // lane l sums the column slots l, l+32, ..: each (column -> groups) mapping is fixed
     for (int lg = 0; lg < g.gpc; ++lg) {
       float t1 = 0.f, t2 = 0.f;
-      for (int t = tid; t < nthr; t += 32) {
-        const int tv = t % g.nv;
+      for (int t = tid; t < g.nv; t += 32) {
+        const int tv = t;
         const int tg0 = (tv * 8) / g.cpg;
         const float4 q = *reinterpret_cast<const float4*>(part + (size_t)t * 4);
         if (tg0 == lg) {
@@ -653,7 +669,17 @@ template <int MV>
 __global__ void ln_lora_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, __half* __restrict__ y, long long ldy,
                                    float* __restrict__ stats, const float* __restrict__ A, int R, int RPAD, int M,
-                                   int C, float eps) {
+                                   int C, float eps, int a_in_smem) {
+  // the R x C down-projection matrix is read by every row: staged once per CTA in shared memory when it fits (36 KB
+  // at rank 4 on q, k, v); read from global memory it made the kernel a chain of L2 latencies (ncu: long_scoreboard
+  // 76 % of the stall samples, IPC 0.48)
+  extern __shared__ uint4 ln_smem[];
+  if (a_in_smem) {
+    const int n4 = R * C / 4;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) ln_smem[i] = reinterpret_cast<const uint4*>(A)[i];
+    __syncthreads();
+    A = reinterpret_cast<const float*>(ln_smem);
+  }
   const long long row_raw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const bool row_ok = row_raw < M;
   const long long row = row_ok ? row_raw : M - 1;  // out-of-range warps shadow the last row (shuffles stay warp-wide)
@@ -741,35 +767,59 @@ template <int MV, typename DYT>
 __global__ void ln_bwd_clip_kernel(const DYT* __restrict__ dy, long long lddy, const float* __restrict__ x,
                                    long long ldx, const float* __restrict__ gamma, const float* __restrict__ stats,
                                    const float* __restrict__ add, float* __restrict__ dx, __half* __restrict__ dx16,
-                                   const float* __restrict__ A, int R, int M, int C) {
+                                   const float* __restrict__ A, int R, int M, int C, int a_in_smem) {
+  extern __shared__ uint4 ln_smem[];
+  if (A && a_in_smem) {  // see ln_lora_fwd_kernel
+    const int n4 = R * C / 4;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) ln_smem[i] = reinterpret_cast<const uint4*>(A)[i];
+    __syncthreads();
+    A = reinterpret_cast<const float*>(ln_smem);
+  }
   const long long row_raw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const bool row_ok = row_raw < M;
   const long long row = row_ok ? row_raw : M - 1;
   const int lane = threadIdx.x & 31;
   const int nvec = C / 8;
   const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
+  // the row's R down-projection gradients: lane l holds entries l and l + 32, handed round by shuffles
+  float dxa_lo = 0.f, dxa_hi = 0.f;
+  if (A) {
+    if (lane < R) dxa_lo = static_cast<float>(dy[row * lddy + C + lane]);
+    if (lane + 32 < R) dxa_hi = static_cast<float>(dy[row * lddy + C + lane + 32]);
+  }
   float g[MV][8], xh[MV][8];
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int j = 0; j < MV; ++j) {
     const int vi = lane + j * 32;
-    if (vi < nvec) {
-      float df[8], gf[8], xf[8];
-      load8<DYT>(dy + row * lddy + vi * 8, df);
-      load8<float>(gamma + vi * 8, gf);
-      load8<float>(x + row * ldx + vi * 8, xf);
-      if (A) {
-        for (int r = 0; r < R; ++r) {
-          const float dxa = static_cast<float>(dy[row * lddy + C + r]);
+    if (vi < nvec) load8<DYT>(dy + row * lddy + vi * 8, g[j]);
+  }
+  if (A) {
+    for (int r = 0; r < R; ++r) {
+      // (the shuffle is executed by the whole warp: lanes without a vector -- narrow rows -- still take part)
+      const float dxa = __shfl_sync(0xffffffffu, r < 32 ? dxa_lo : dxa_hi, r & 31);
+#pragma unroll
+      for (int j = 0; j < MV; ++j) {
+        const int vi = lane + j * 32;
+        if (vi < nvec) {
           float af[8];
           load8<float>(A + (long long)r * C + vi * 8, af);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) df[i] += dxa * af[i];
+          for (int i = 0; i < 8; ++i) g[j][i] += dxa * af[i];
         }
       }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < MV; ++j) {
+    const int vi = lane + j * 32;
+    if (vi < nvec) {
+      float gf[8], xf[8];
+      load8<float>(gamma + vi * 8, gf);
+      load8<float>(x + row * ldx + vi * 8, xf);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        g[j][i] = df[i] * gf[i];
+        g[j][i] *= gf[i];
         xh[j][i] = (xf[i] - mean) * rstd;
         s1 += g[j][i];
         s2 += g[j][i] * xh[j][i];
@@ -1007,12 +1057,15 @@ extern "C" int tb_layernorm_lora_fwd(const float* x, int64_t ldx, const float* g
   cudaStream_t st = (cudaStream_t)stream;
   const int wpb = 8;
   const unsigned grid = (unsigned)((M + wpb - 1) / wpb);
+  const int a_bytes = R * C * 4;
+  const int a_in_smem = a_bytes <= 48 * 1024 && ((uintptr_t)lora_A % 16 == 0);  // (static limit: no attribute call)
+  const int smem = a_in_smem ? a_bytes : 0;
   if (C <= 768)
-    ln_lora_fwd_kernel<3><<<grid, wpb * 32, 0, st>>>(x, ldx, gamma, beta, (__half*)y_ext, ldy, stats, lora_A, R, RPAD,
-                                                     M, C, eps);
+    ln_lora_fwd_kernel<3><<<grid, wpb * 32, smem, st>>>(x, ldx, gamma, beta, (__half*)y_ext, ldy, stats, lora_A, R,
+                                                        RPAD, M, C, eps, a_in_smem);
   else
-    ln_lora_fwd_kernel<LN_MAXV><<<grid, wpb * 32, 0, st>>>(x, ldx, gamma, beta, (__half*)y_ext, ldy, stats, lora_A, R,
-                                                           RPAD, M, C, eps);
+    ln_lora_fwd_kernel<LN_MAXV><<<grid, wpb * 32, smem, st>>>(x, ldx, gamma, beta, (__half*)y_ext, ldy, stats, lora_A,
+                                                              R, RPAD, M, C, eps, a_in_smem);
   return check_launch("ln_lora_fwd_kernel");
 }
 
@@ -1030,14 +1083,18 @@ extern "C" int tb_layernorm_bwd_clip(const void* dy, int dy_f32, int64_t lddy, c
   cudaStream_t st = (cudaStream_t)stream;
   const int wpb = 8;
   const unsigned grid = (unsigned)((M + wpb - 1) / wpb);
+  const int a_bytes = lora_A ? R * C * 4 : 0;
+  const int a_in_smem = lora_A && a_bytes <= 48 * 1024 && ((uintptr_t)lora_A % 16 == 0);
+  const int smem = a_in_smem ? a_bytes : 0;
 #define TB_LN_BWD_CLIP(MV)                                                                                           \
   do {                                                                                                               \
     if (dy_f32)                                                                                                      \
       ln_bwd_clip_kernel<MV, float><<<grid, wpb * 32, 0, st>>>((const float*)dy, lddy, x, ldx, gamma, stats, add, dx, \
-                                                               (__half*)dx_f16, nullptr, 0, M, C);                   \
+                                                               (__half*)dx_f16, nullptr, 0, M, C, 0);                \
     else                                                                                                             \
-      ln_bwd_clip_kernel<MV, __half><<<grid, wpb * 32, 0, st>>>((const __half*)dy, lddy, x, ldx, gamma, stats, add,  \
-                                                                dx, (__half*)dx_f16, lora_A, R, M, C);               \
+      ln_bwd_clip_kernel<MV, __half><<<grid, wpb * 32, smem, st>>>((const __half*)dy, lddy, x, ldx, gamma, stats,    \
+                                                                   add, dx, (__half*)dx_f16, lora_A, R, M, C,        \
+                                                                   a_in_smem);                                       \
   } while (0)
   if (C <= 768) TB_LN_BWD_CLIP(3);
   else TB_LN_BWD_CLIP(LN_MAXV);
