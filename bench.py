@@ -62,7 +62,9 @@ def read_attention_tensor_pipe():
     committed `ncu --set full` summary (a profiler metric cannot be measured inside the timed run)."""
     import glob
     import re
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_cases_final_summary.txt")))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_cases_final_summary.txt")) +
+                   glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_cases_summary.txt")),
+                   key=lambda f: os.path.basename(f)[:3])  # newest round last (r01_..., r02_...)
     if not files:
         return None
     out, cur = {}, None

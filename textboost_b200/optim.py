@@ -121,6 +121,12 @@ class FusedAdamW:
     def zero_grad(self, set_to_none: bool = True):
         """No-op: tb_adamw_fused_step consumes AND zeroes the gradient buffer."""
 
+    def hyperparameters(self):
+        """Everything step() passes to the kernel by value (what a captured CUDA graph bakes in)."""
+        return (float(self.param_groups[1]["lr"]), float(self.param_groups[0]["lr"]), tuple(self.betas), self.eps,
+                self.weight_decay, self.max_grad_norm, self.mean_norm, self.lr_scheduler, self.lr_warmup_steps,
+                self.max_train_steps, self.gradient_accumulation_steps, self.world_size)
+
     def state_dict(self):
         return {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
                 "state": self.state.clone(), "mean_norm": self.mean_norm,

@@ -238,7 +238,14 @@ class TextBoostTrainer:
                 self.step(*static, sync_gradients=False)
             # (capturing executes nothing: the gradient buffer is untouched)
 
+        # the optimiser's scalar hyper-parameters are arguments of the captured launch: a later edit of
+        # param_groups[...]["lr"] (or betas / weight decay) would be silently ignored by the replay -- refuse instead
+        baked = self.opt.hyperparameters()
+
         def replay(latents, noise, timesteps, input_ids, prior_ids=None, sync_gradients=True):
+            if self.opt.hyperparameters() != baked:
+                raise RuntimeError("optimiser hyper-parameters changed after capture(): they are baked into the CUDA "
+                                   "graph; call capture() again (the --lr_scheduler runs on the device and needs no edit)")
             for dst, src in zip(static, (latents, noise, timesteps, input_ids, prior_ids)):
                 if dst is not None and src is not None and dst.data_ptr() != src.data_ptr():
                     dst.copy_(src, non_blocking=True)

@@ -140,7 +140,13 @@ def _unsupported(args):
         raise ValueError("--with_image_prior takes its class images from --class_data_dir through the image front "
                          "end: it cannot be combined with --latents_file / --synthetic_data")
     if args.unet_params_to_train != "none":
-        raise NotImplementedError("--unet_params_to_train: the UNet is frozen on this path (SURVEY.md §8 f4)")
+        # train_textboost.py:711-720 adds LoRA to attn2.to_k / to_v, then :937 casts the WHOLE UNet -- adapter included --
+        # to weight_dtype.  Under --mixed_precision fp16 (the only policy built here) the trainable tensors are fp16 and
+        # accelerate's clip_grad_norm_ -> GradScaler.unscale_ raises "Attempting to unscale FP16 gradients": the mode
+        # only runs in the reference's fp32 policy, which is outside this path.
+        raise NotImplementedError("--unet_params_to_train crossattn_kv: the UNet is frozen on this path; in the "
+                                  "reference the mode needs --mixed_precision no (its fp16 path fails in "
+                                  "GradScaler.unscale_ on the fp16 adapter tensors)")
     if args.lora_rank < 0:
         raise ValueError("--lora_rank must be >= 0")
     if args.gradient_accumulation_steps < 1:
@@ -296,7 +302,8 @@ def save_checkpoint(trainer, text_encoder, step, directory, gen_state):
 
 
 def load_checkpoint(trainer, directory, device):
-    st = torch.load(os.path.join(directory, "state.pt"), map_location="cpu", weights_only=False)
+    # state.pt holds tensors, ints and floats only (save_checkpoint): nothing is unpickled from the output directory
+    st = torch.load(os.path.join(directory, "state.pt"), map_location="cpu", weights_only=True)
     trainer.te.state.params.copy_(st["params"].to(device))
     trainer.opt.load_state_dict({k: (v.to(device) if torch.is_tensor(v) else v) for k, v in st["optimizer"].items()})
     return st["step"], st["generator"]
