@@ -306,6 +306,12 @@ class ClipEngine:
         st = self.state
         s = C.stream_ptr()
         d_out = d_out.contiguous().view(M, D)
+        # The LoRA weight-gradient kernel of a layer hangs off the chain (nothing downstream reads dA / dB): it runs on
+        # a helper stream next to the following layer's GEMMs instead of adding its ~10 us to each of the 12 links of
+        # the latency-bound tail.  Its operands are kept alive until the join below.
+        main = torch.cuda.current_stream() if d_out.is_cuda else None
+        helper = self._helper_stream(main) if main is not None and self.r else None
+        keep = []
         C.call("tb_null_override", C.ptr(ids), None, C.ptr(d_out), B, Lq, D, EOS_ID,
                int(self.use_fixed_special), 1, s)
         # every LayerNorm backward also writes the fp16 copy of its result: the next dgrad GEMM's operand
@@ -335,9 +341,19 @@ class ClipEngine:
             dy_ext = ops.gemm(dqkv, L["wqkv_t"])
             g16 = torch.empty((M, D), device=self.device, dtype=F16) if l else None
             if self.Tq:
-                C.call("tb_lora_grad", C.ptr(dqkv), C.ptr(y_ext), C.ptr(dy_ext), self.Kext,
-                       C.ptr(st.B(l, st.grads)), C.ptr(st.A(l, st.grads)), M, 3, self.qkv_mask, D, self.r,
-                       self.scaling, s)
+                if helper is not None:
+                    ready = torch.cuda.Event()
+                    ready.record(main)
+                    keep.append((dqkv, y_ext, dy_ext))
+                    with torch.cuda.stream(helper):
+                        helper.wait_event(ready)
+                        C.call("tb_lora_grad", C.ptr(dqkv), C.ptr(y_ext), C.ptr(dy_ext), self.Kext,
+                               C.ptr(st.B(l, st.grads)), C.ptr(st.A(l, st.grads)), M, 3, self.qkv_mask, D, self.r,
+                               self.scaling, C.stream_ptr())
+                else:
+                    C.call("tb_lora_grad", C.ptr(dqkv), C.ptr(y_ext), C.ptr(dy_ext), self.Kext,
+                           C.ptr(st.B(l, st.grads)), C.ptr(st.A(l, st.grads)), M, 3, self.qkv_mask, D, self.r,
+                           self.scaling, s)
                 # the down-projection's input-gradient (dy += dxa A) rides on the LayerNorm backward
                 g = ops.layernorm_bwd_clip(dy_ext, x, L["ln1"][0], st1, add=g, out=g, out16=g16,
                                            lora_a=st.A(l)[:self.Tq * self.r])
@@ -346,4 +362,17 @@ class ClipEngine:
             saved[l] = None
         if st.n_rows:
             C.call("tb_clip_embed_grad", C.ptr(ids), C.ptr(g), C.ptr(st.rows(st.grads)), M, D, self.n_base, s)
+        if helper is not None:
+            main.wait_stream(helper)
+        keep.clear()
         return g.view(B, Lq, D)
+
+    def _helper_stream(self, main):
+        """One helper stream per stream backward() is called on (the prior-prompt backward runs on the trainer's side
+        stream while the UNet owns the main one)."""
+        if not hasattr(self, "_helpers"):
+            self._helpers = {}
+        key = main.cuda_stream
+        if key not in self._helpers:
+            self._helpers[key] = torch.cuda.Stream(device=self.device)
+        return self._helpers[key]
