@@ -220,8 +220,10 @@ def cpu_reference_step_time(n_images: int, steps: int, warmup: int, use_kpl: boo
                                 kpl_weight=0.1 if use_kpl else 0.0, mean_norm=mean_norm)
 
     t_start = time.perf_counter()
+    warm_done = 0
     for _ in range(warmup):
         one()
+        warm_done += 1
         if time.perf_counter() - t_start > budget_s / 3:
             break
     times = []
@@ -232,6 +234,7 @@ def cpu_reference_step_time(n_images: int, steps: int, warmup: int, use_kpl: boo
         if time.perf_counter() - t_start > budget_s:
             break
     ms = 1e3 * sum(times) / len(times)
+    cpu_reference_step_time.warmups_done = warm_done
     return n_images / (ms / 1e3), ms, len(times), threads
 
 
@@ -243,13 +246,16 @@ def run_reference_arm(args):
         return 0
     use_kpl = not args.no_kpl
     n_img = args.ref_images
-    v, ms, done, threads = cpu_reference_step_time(n_img, args.steps, min(args.warmup, 1), use_kpl,
+    # the same --steps / --warmup as the GPU arm (a CPU step of the bs=1 sample takes ~2.4 s on the box's 16 cores:
+    # 25 of them fit the budget; if they would not, the loops stop early and the line reports what was done)
+    v, ms, done, threads = cpu_reference_step_time(n_img, args.steps, args.warmup, use_kpl,
                                                    budget_s=args.ref_budget_s)
     sample = (f"{done} timed step(s) of the oracle port (oracle/step_ref.py, fp32 autograd) at bs={n_img} of the same "
               f"SD-1.5 workload, {threads} torch threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
-        "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "warmup": cpu_reference_step_time.warmups_done, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus, use_kpl, note=f"CPU sample: bs={n_img} per step"),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
@@ -468,7 +474,8 @@ def run_ours(args):
         step_tf = value * TFLOP_PER_IMG[use_kpl]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "warmup": cpu_reference_step_time.warmups_done, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": workload_config(world, use_kpl),
             "cuda_graph": graph_ok,
