@@ -153,6 +153,19 @@ def library_step_graphed():
         return self.to_out[0](o)
 
     unet_ref.Attention.forward = sdpa_forward
+
+    def capturable_forward(self, input_ids):
+        """TextBoostModel.forward without its data-dependent branch (`if null_pos.any()`, text_encoder.py:71, forces a
+        host sync and cannot be captured): same result through torch.where -- the library step gets the benefit of a
+        CUDA graph that the reference itself could not have."""
+        out = self.text_model(input_ids)
+        null_pos = (input_ids[:, 1] == self.EOS_ID)[:, None, None]
+        out = torch.where(null_pos, self.null_embedding.to(out.dtype).unsqueeze(0), out)
+        if self._use_fixed_special_embedding:
+            out = torch.cat([self.null_embedding[0].to(out.dtype).expand(out.shape[0], 1, -1), out[:, 1:]], 1)
+        return out
+
+    clip_ref.TextBoostModelRef.forward = capturable_forward
     with torch.no_grad():
         unet = unet_ref.init_unet_(unet_ref.UNet2DConditionModelRef(unet_ref.UNetConfig.sd15()), 0).to(dev).half()
         unet = unet.to(memory_format=torch.channels_last).requires_grad_(False)
@@ -223,7 +236,9 @@ def library_step_graphed():
             step()
         out["graphed_channels_last_ms"] = timed(g.replay, 3, 10)
     except Exception as e:  # noqa: BLE001
+        import traceback
         out["graph_capture_error"] = repr(e)[:300]
+        out["graph_capture_where"] = [l.strip() for l in traceback.format_exc().splitlines() if "File" in l][-6:]
     del unet, te, te0, opt
     torch.cuda.empty_cache()
     tr = synthetic.build_trainer("sd15", dev, seed=42, n_added=1)
