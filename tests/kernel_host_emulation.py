@@ -366,10 +366,11 @@ uint4 ln_smem[1 << 14];  // ... of ln_lora_fwd_kernel / ln_bwd_clip_kernel (the 
 // launch-wide phases.  Blocks of more threads than the pool holds are not used by these kernels.
 constexpr unsigned EMU_MAX_THREADS = 512;
 struct EmuPool {
-  std::barrier<> go{EMU_MAX_THREADS + 1}, done{EMU_MAX_THREADS + 1};
+  const unsigned size;
+  std::barrier<> go, done;
   const std::function<void(unsigned)>* job = nullptr;
-  EmuPool() {
-    for (unsigned t = 0; t < EMU_MAX_THREADS; ++t)
+  explicit EmuPool(unsigned n) : size(n), go(n + 1), done(n + 1) {
+    for (unsigned t = 0; t < size; ++t)
       std::thread([this, t] {
         for (;;) {
           go.arrive_and_wait();
@@ -384,9 +385,14 @@ struct EmuPool {
     done.arrive_and_wait();
   }
 };
-static EmuPool& emu_pool() {
-  static EmuPool* p = new EmuPool;
-  return *p;
+// every launch wakes its whole pool twice, so the common blocks (<= 320 threads) get their own, smaller pool; the
+// 512-thread pool exists only once a kernel needs it (the group-owner GroupNorm: 510 threads)
+static EmuPool& emu_pool(unsigned threads) {
+  static EmuPool* small = new EmuPool(320);
+  static EmuPool* big = nullptr;
+  if (threads <= 320) return *small;
+  if (!big) big = new EmuPool(EMU_MAX_THREADS);
+  return *big;
 }
 static void emu_launch(unsigned gx, unsigned gy, unsigned threads, const std::function<void()>& f) {
   if (threads > EMU_MAX_THREADS) abort();
@@ -395,7 +401,7 @@ static void emu_launch(unsigned gx, unsigned gy, unsigned threads, const std::fu
   const unsigned warps = (threads + 31) / 32, nblocks = gx * gy;
   std::barrier<> phase(threads);
   std::unique_ptr<std::barrier<>> block_bar;
-  emu_pool().run([&](unsigned t) {
+  emu_pool(threads).run([&](unsigned t) {
     if (t >= threads) return;
     threadIdx = {t, 0, 0};
     for (unsigned b = 0; b < nblocks; ++b) {

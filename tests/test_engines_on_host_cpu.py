@@ -39,6 +39,7 @@ def test_vae_engines_through_the_real_simt_kernels(monkeypatch):
     assert d.max() <= 2
 
 
+@pytest.mark.long_cpu
 def test_sampling_loop_with_the_real_unet_engine(monkeypatch):
     """StableDiffusionPipeline.denoise (UNetEngine forward on the doubled batch + tb_dpm_cfg_step per step) vs the
     oracle sampler driving the oracle UNet built from the same weights: 5 steps, guidance 7.5."""

@@ -45,6 +45,7 @@ def test_whole_step_on_cpu_matches_oracle(monkeypatch):
     _check(r, tr)
 
 
+@pytest.mark.long_cpu
 def test_image_prior_step_on_cpu_matches_oracle(monkeypatch):
     """--with_image_prior (train_textboost.py:1077-1094): [instance | class] halves, weight 0.3, v-prediction, KPL mse,
     --mixing object."""
@@ -56,6 +57,7 @@ def test_image_prior_step_on_cpu_matches_oracle(monkeypatch):
                             bt["prior_ids"][:3])
 
 
+@pytest.mark.long_cpu
 def test_sd2x_shaped_step_on_cpu_matches_oracle(monkeypatch):
     """The SD-2.x branches at toy widths: linear (not 1x1-conv) Transformer2D projections, head_dim 64, and the OpenCLIP
     text encoder's erf-gelu, with v-prediction — what tests/test_gpu_step.py::test_step_sd21_openclip_h_vs_oracle covers
@@ -72,6 +74,7 @@ def test_sd2x_shaped_step_on_cpu_matches_oracle(monkeypatch):
     _check(r, tr)
 
 
+@pytest.mark.long_cpu
 def test_three_steps_track_the_oracle(monkeypatch):
     """Optimiser state and the re-packed LoRA weights across steps: three product steps against three oracle steps from
     the same start.  Adam moves every parameter by ~lr per step whatever the gradient's size, so parameters may differ
@@ -114,7 +117,9 @@ def test_lora_rank_zero_trains_only_the_added_rows(monkeypatch):
     assert r["row_grad_rel"] < 5e-3
     assert r["grad_norm"] == 0.0 and r["grad_norm_ref"] == 0.0
     assert abs(r["added_norm"] - r["added_norm_ref"]) < 2e-3 * r["added_norm_ref"]
-    assert abs(r["frozen_decay"] - r["frozen_decay_ref"]) < 1e-6 and r["rows_after_rel"] < 5e-3
+    # (the updated rows themselves are not compared elementwise: Adam's first step is lr * sign(g), so an element whose
+    # gradient is ~0 may step the other way; the gradient and the post-step norm are what is pinned)
+    assert abs(r["frozen_decay"] - r["frozen_decay_ref"]) < 1e-6
 
 
 def test_gradient_accumulation_equals_one_step_over_the_joined_batch(monkeypatch):
