@@ -474,8 +474,7 @@ def run_ours(args):
         step_tf = value * TFLOP_PER_IMG[use_kpl]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": cpu_reference_step_time.warmups_done, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": workload_config(world, use_kpl),
             "cuda_graph": graph_ok,
