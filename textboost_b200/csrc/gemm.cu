@@ -28,6 +28,11 @@ struct GemmParams {
   // no 128-pixel box tiles the plane (the MMA still runs M = 128; rows >= tile_rows are never loaded or stored)
   int tile_rows;
   int a_stage_bytes;  // bytes one TMA box of the A operand delivers (tile_rows x 128)
+  // MMA M extent: 128, or 64 for under-filled problems on the generic epilogue (the 616-row text-encoder GEMMs with
+  // N = 768: 60 tiles of 128 rows leave 88 SMs idle while each CTA walks its K loop at ~0.2 us per k-block; 120 tiles
+  // of 64 rows halve the operand bytes per CTA and k-block).  With M = 64 the accumulator rows sit in TMEM lanes
+  // 0-15 of each 32-lane quarter (row r -> lane 32*(r/16) + r%16): lanes 16-31 of the epilogue warps idle.
+  int mma_m;          // (layout found with scripts/m64_diag.py: the other candidate, lanes 0-63, reads garbage)
   // epilogue
   void* C;
   long long ldc;
@@ -156,7 +161,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
             const int ky = tap / 3, kx = tap - ky * 3;
             tma_load_4d(sa, &tmA, fb, c0, cw + kx - 1, ch + ky - 1, cb);
           } else {
-            tma_load_2d(sa, &tmA, fb, kb * BK, m_tile * BM);
+            tma_load_2d(sa, &tmA, fb, kb * BK, m_tile * p.tile_rows);
           }
           if (p.experiment != 1) tma_load_2d(sb, &tmB, fb, kb * BK, n_tile * BN);
         }
@@ -169,7 +174,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer (warp-uniform; one elected lane issues)
-    constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0, 0);
+    const uint32_t idesc = umma_idesc_f16(p.mma_m, BN, 0, 0);
     const uint32_t dhi = umma_desc_hi_sw128(1024);
     int stage = 0;
     uint32_t phase = 0;
@@ -209,7 +214,11 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
     // i+1 and the residual loads of chunk i+1 are in flight while chunk i is converted and stored.
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
-    const int row = quarter * 32 + lane;
+    const bool m64 = !FAST && p.mma_m == 64;
+    // TMEM lane of this thread is always 32*quarter + lane; with M = 64 that lane holds tile row 16*quarter + lane
+    // (lanes 0-15 of the quarter) and lanes 16-31 hold nothing
+    const bool lane_live = !m64 || lane < 16;
+    const int row = !m64 ? quarter * 32 + lane : quarter * 16 + (lane & 15);
     const bool issuer = threadIdx.x == 64;
     constexpr int NCH = BN / 32;           // 32-column chunks per tile
     constexpr int MY_MAX = (NCH + 1) / 2;  // chunks per warp (half 0 takes the odd one out)
@@ -343,7 +352,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
         from_ws = true;
       }
       const uint32_t acc_addr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
-      const bool row_ok = m < p.M && row < p.tile_rows;
+      const bool row_ok = m < p.M && row < p.tile_rows && lane_live;
       const __half* rv = nullptr;
       if (p.rowvec && row_ok) rv = p.rowvec + (m / p.rows_per_group) * p.ldrv;
       const __half* res = nullptr;
@@ -463,7 +472,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
               o.z = pack_half2(v[4], v[5]);
               o.w = pack_half2(v[6], v[7]);
               const int chunk = ((c & 63) + j) >> 3;  // 16-byte chunk inside the 128-byte box row
-              *reinterpret_cast<uint4*>(box + row * 128 + ((chunk ^ (row & 7)) << 4)) = o;
+              if (lane_live) *reinterpret_cast<uint4*>(box + row * 128 + ((chunk ^ (row & 7)) << 4)) = o;
             } else if (row_ok && n < p.N) {
               if (p.out_kind == TB_OUT_F16) {
                 uint4 o;
@@ -529,7 +538,7 @@ static void plan_split(GemmParams& p, int bn, int tiles, cudaStream_t st) {
   // last CTA re-reading splits x 64 KB) costs ~8-15 us, so splitting only pays for very long K loops -- the 3x3
   // convolutions of the 8x8 / 16x16 levels (180-360 k-blocks: 80 -> 32 us).  GEMMs with K <= 5120 lose.
   static const int min_kb = getenv("TB_GEMM_SPLITK_MIN_KB") ? atoi(getenv("TB_GEMM_SPLITK_MIN_KB")) : 128;  // tuning knob
-  if (off || !w || tiles * 2 > num_sms() || p.num_kb < min_kb) return;
+  if (off || !w || tiles * 2 > num_sms() || p.num_kb < min_kb || p.mma_m == 64) return;
   int s = num_sms() / tiles;
   if (s > p.num_kb / 4) s = p.num_kb / 4;
   if (s > 16) s = 16;
@@ -580,7 +589,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   }
   plan_split(p, BN, p.n_tiles * m_tiles, st);
   static const bool no_fast = getenv("TB_GEMM_NO_FAST_EPILOGUE") != nullptr;  // diagnostic switch
-  const bool fast = BN >= 64 && !no_fast && p.splits == 1 && p.tma_store == 1 && p.out_kind == TB_OUT_F16 &&
+  const bool fast = BN >= 64 && !no_fast && p.mma_m == 128 && p.splits == 1 && p.tma_store == 1 && p.out_kind == TB_OUT_F16 &&
                     p.alpha == 1.f && p.act == TB_ACT_NONE && !p.res_f32 && p.N % BN == 0 && p.M % p.tile_rows == 0 &&
                     (!p.rowvec || p.rows_per_group % p.tile_rows == 0);
   if (fast) return launch_gemm_v<BN, STAGES, CONV, true>(tmA, tmB, tmC, p, m_tiles, st);
@@ -715,15 +724,29 @@ extern "C" int tb_gemm_f16(const void* A, int64_t lda, const void* B, int64_t ld
   p.num_kb = (K + BK - 1) / BK;
   p.tile_rows = BM;
   p.a_stage_bytes = A_STAGE_BYTES;
+  p.mma_m = 128;
   rc = fill_epilogue(p, C, ldc, ep);
   if (rc) return rc;
+  {
+    // 64-row tiles when 128-row tiles would fill less than half the machine and the problem is on the generic
+    // epilogue anyway (ragged M, fp32 output / residual, activation): the text-encoder GEMMs with N = 768 / 784
+    static const int m64 = getenv("TB_GEMM_M64") ? atoi(getenv("TB_GEMM_M64")) : 1;  // 0 = off (A/B switch)
+    const int mt128 = (M + BM - 1) / BM;
+    const int bn = pick_bn(N, mt128, p.num_kb);
+    const bool generic = M % BM != 0 || p.out_kind != TB_OUT_F16 || p.res_f32 || p.act != TB_ACT_NONE || p.alpha != 1.f;
+    if (m64 && generic && M > 64 && mt128 * ((N + bn - 1) / bn) * 2 <= num_sms() && p.num_kb < 128) {
+      p.mma_m = 64;
+      p.tile_rows = 64;
+      p.a_stage_bytes = 64 * BK * 2;
+    }
+  }
   CUtensorMap tmA;
   uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
   uint64_t strides[1] = {(uint64_t)lda * 2};
-  uint32_t box[2] = {(uint32_t)BK, (uint32_t)BM};
+  uint32_t box[2] = {(uint32_t)BK, (uint32_t)p.tile_rows};
   rc = make_tmap_f16(&tmA, A, 2, dims, strides, box);
   if (rc) return rc;
-  return dispatch_gemm<false>(tmA, B, ldb, p, (M + BM - 1) / BM, (cudaStream_t)stream);
+  return dispatch_gemm<false>(tmA, B, ldb, p, (M + p.tile_rows - 1) / p.tile_rows, (cudaStream_t)stream);
 }
 
 extern "C" int tb_conv3x3_f16(const void* x, const void* w, void* y, int B, int H, int W, int Cin,
@@ -762,6 +785,7 @@ extern "C" int tb_conv3x3_f16(const void* x, const void* w, void* y, int B, int 
   p.W = W;
   p.tile_rows = rows;
   p.a_stage_bytes = rows * BK * 2;
+  p.mma_m = 128;
   rc = fill_epilogue(p, y, Cout, ep);
   if (rc) return rc;
   CUtensorMap tmA;
