@@ -93,14 +93,15 @@ def attention_microbench(peak_tf):
     Inputs (q/k/v/o/dO of a level: 0.1-0.2 GB) exceed nothing special: 3 warm-ups, 10 timed launches each."""
     import torch
     from textboost_b200 import ops
+    from textboost_b200.precision import POLICY
     out = {}
     for (N, d) in ((4096, 40), (1024, 80), (256, 160)):
         B, H = 8, 8
         C_ = H * d
         g = torch.Generator(device="cuda").manual_seed(N + d)
-        qkv = torch.randn(B, N, 3 * C_, device="cuda", dtype=torch.float16, generator=g)
+        qkv = torch.randn(B, N, 3 * C_, device="cuda", dtype=POLICY.act, generator=g)
         q, k, v = qkv[..., :C_], qkv[..., C_:2 * C_], qkv[..., 2 * C_:]
-        do = torch.randn(B, N, C_, device="cuda", dtype=torch.float16, generator=g)
+        do = torch.randn(B, N, C_, device="cuda", dtype=POLICY.act, generator=g)
         o, lse = ops.attn_fwd(q, k, v, H)
 
         def t(fn, iters=10):
@@ -359,6 +360,8 @@ def kernel_family_timing(trainer, bt):
 def run_ours(args):
     import torch
     import torch.distributed as dist
+    from textboost_b200 import precision
+    precision.set_policy(args.precision)  # before anything loads the library: fp16 (BASELINE.json) or the bf16 build
     from textboost_b200 import _cabi, synthetic
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -475,7 +478,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "vs_baseline": None, "dtype": {"fp16": "f16", "bf16": "bf16"}[args.precision], "data": "synthetic",
             "config": workload_config(world, use_kpl),
             "cuda_graph": graph_ok,
             "e2e": {"value": images / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
@@ -529,6 +532,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-kpl", action="store_true", help="configs[1] without the knowledge-preservation loss")
+    ap.add_argument("--precision", choices=["fp16", "bf16"], default=os.environ.get("TEXTBOOST_B200_PRECISION", "fp16"),
+                    help="precision policy = which build of the library runs (BASELINE.json names fp16, the default; "
+                         "bf16 is the reference's --mixed_precision bf16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-images", type=int, default=1, help="images per CPU-baseline step (bounded sample)")
     ap.add_argument("--ref-budget-s", type=float, default=240.0)

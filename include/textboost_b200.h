@@ -65,6 +65,14 @@ int tb_version(void);
 const char* tb_last_error(void);
 /* 0 if the current device is sm_100 and the library can run, else TB_E_ARCH */
 int tb_check_device(void);
+/* Storage / tensor-core operand type of THIS build of the library: TB_STORAGE_F16 (libtextboost_b200.so, the
+ * reference's --mixed_precision fp16, weight_dtype = torch.float16, train_textboost.py:928-931) or TB_STORAGE_BF16
+ * (libtextboost_b200_bf16.so, --mixed_precision bf16, :932-933).  Both builds export the same symbols: wherever a
+ * signature or comment below says "fp16" the bf16 build reads and writes bfloat16 instead; fp32 arguments are fp32
+ * in both.  A process uses ONE of the two (textboost_b200.precision). */
+#define TB_STORAGE_F16 0
+#define TB_STORAGE_BF16 1
+int tb_storage_dtype(void);
 
 /* Optional split-K scratch for under-filled GEMM / conv problems (few output tiles, long K): `ptr` is a
  * caller-owned device buffer (256-byte aligned, >= 128 KiB; 32 MiB covers every SD shape) that tb_gemm_f16 /

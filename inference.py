@@ -64,8 +64,10 @@ def learned_embedding_files(model_path):
             if f.endswith(".bin") and f not in _NOT_EMBEDDINGS]
 
 
-def load_pipeline(model_path, pretrained_model, dtype=torch.float16):
+def load_pipeline(model_path, pretrained_model, dtype=None):
     from textboost_b200.pipeline import DiffusionPipeline
+    from textboost_b200.precision import POLICY
+    dtype = dtype or POLICY.act  # the reference passes torch.float16 (inference.py:41); bf16 under TEXTBOOST_B200_PRECISION=bf16
     if not os.path.isdir(pretrained_model):
         raise OSError(f"base model {pretrained_model!r} is not a local directory (no hub access): pass --model <dir> "
                       "with the diffusers layout (unet/, vae/, text_encoder/, tokenizer/, scheduler/)")

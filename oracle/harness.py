@@ -118,26 +118,29 @@ def lora_grads_flat(trainer, ref_grads: Dict[str, torch.Tensor], buf: torch.Tens
     return torch.cat(ours), torch.cat(refs), worst
 
 
-def _reference_fp16_policy(trainer, b, V, kind, use_kpl, device):
-    """The same step through torch's own fp16 kernels under the reference's precision policy (step_ref
-    mixed_precision="fp16"): returns (pred, LoRA grad vector, added-row grads) on the CPU."""
-    unet, te, te0, _ = twin_of(trainer, device, torch.float32, frozen_dtype=torch.float16)
+def _reference_fp16_policy(trainer, b, V, kind, use_kpl, device, policy="fp16"):
+    """The same step through torch's own 16-bit kernels under the reference's precision policy (step_ref
+    mixed_precision="fp16" or "bf16"; GradScaler only for fp16): returns (pred, LoRA grad vector, added-row grads)
+    on the CPU."""
+    wdt = {"fp16": torch.float16, "bf16": torch.bfloat16}[policy]
+    unet, te, te0, _ = twin_of(trainer, device, torch.float32, frozen_dtype=wdt)
     ref = step_ref.reference_step(
         unet, te, te0, b["latents"].float(), b["noise"].float(), b["timesteps"], b["input_ids"],
         b["prior_ids"] if use_kpl else None, n_base=V, kpl_weight=trainer.kpl_weight, kpl_type=kind,
         prediction_type="v_prediction" if trainer.v_pred else "epsilon", optimizer=None, mixing=trainer.mixing,
-        image_ppl_weight=getattr(trainer, "image_prior_weight", None), mixed_precision="fp16",
-        loss_scale=65536.0)
+        image_ppl_weight=getattr(trainer, "image_prior_weight", None), mixed_precision=policy,
+        loss_scale=65536.0 if policy == "fp16" else 1.0)
     _, gr, _ = lora_grads_flat(trainer, ref["grad_lora"], trainer.te.state.grads)
     rows = ref["grad_rows"].detach().float().cpu() if ref["grad_rows"] is not None else None
     return ref["pred"].detach().float().cpu(), gr, rows
 
 
 def compare_step(trainer, batch: Dict[str, torch.Tensor], device="cpu", dtype=torch.float32,
-                 with_optimizer=True, fp16_reference=False) -> Dict[str, float]:
+                 with_optimizer=True, fp16_reference=False, policy="fp16") -> Dict[str, float]:
     """Run one step on the product (trainer, CUDA) and on the oracle twin; return error metrics.
 
-    fp16_reference (device must be CUDA): also run the oracle under the reference's fp16 policy and report the
+    fp16_reference (device must be CUDA): also run the oracle under the reference's 16-bit policy (`policy`: "fp16",
+    or "bf16" when the product runs its bf16 build) and report the
     north star's elementwise criterion (rtol 1e-3 / atol 1e-4) three ways -- ours vs fp32 oracle, torch-fp16 vs
     fp32 oracle, ours vs torch-fp16 -- as pass fractions (keys tol_*)."""
     ref16 = None
@@ -145,7 +148,8 @@ def compare_step(trainer, batch: Dict[str, torch.Tensor], device="cpu", dtype=to
         V0 = trainer.synthetic["clip_cfg"].vocab_size
         use_kpl0 = trainer.kpl_weight > 0 and trainer.te0 is not None
         b0 = {k: v.to(device) for k, v in batch.items()}
-        ref16 = _reference_fp16_policy(trainer, b0, V0, {0: "cos", 1: "mse"}[trainer.kpl_kind], use_kpl0, device)
+        ref16 = _reference_fp16_policy(trainer, b0, V0, {0: "cos", 1: "mse"}[trainer.kpl_kind], use_kpl0, device,
+                                       policy)
         del b0
         if torch.cuda.is_available():
             torch.cuda.empty_cache()

@@ -40,15 +40,16 @@ def forward_loss(unet, te, te0, latents, noise, timesteps, input_ids, prior_ids=
                  kpl_type="cos", prediction_type="epsilon", image_ppl_weight=None, mixed_precision=None):
     """Returns (loss, model_pred, encoder_hidden_states).  image_ppl_weight (not None = --with_image_prior,
     :1077-1094): the batch is [instance | class] halves, loss = mse(instance) + image_ppl_weight * mse(class)."""
-    assert mixed_precision in (None, "fp16")
-    amp = (lambda: torch.autocast(latents.device.type, dtype=torch.float16)) if mixed_precision else \
+    assert mixed_precision in (None, "fp16", "bf16")
+    wdt = {None: None, "fp16": torch.float16, "bf16": torch.bfloat16}[mixed_precision]  # weight_dtype, :928-933
+    amp = (lambda: torch.autocast(latents.device.type, dtype=wdt)) if mixed_precision else \
         contextlib.nullcontext
     noisy = ddpm_ref.add_noise(latents, noise, timesteps)
     with amp():
         ehs = te(input_ids)
     ehs = ehs.float()  # accelerate's convert_outputs_to_fp32
     if mixed_precision:
-        pred = unet(noisy.half(), timesteps, ehs.half())  # :1063-1066 (weight_dtype casts)
+        pred = unet(noisy.to(wdt), timesteps, ehs.to(wdt))  # :1063-1066 (weight_dtype casts)
     else:
         pred = unet(noisy, timesteps, ehs)
     if prediction_type == "epsilon":

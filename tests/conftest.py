@@ -29,3 +29,17 @@ def pytest_collection_modifyitems(config, items):
 def built_lib():
     from textboost_b200 import build
     return build.build()
+
+
+def act_dtype():
+    """torch dtype of the product's 16-bit tensors under the process's precision policy (fp16, or bf16 when the suite
+    is re-run with TEXTBOOST_B200_PRECISION=bf16 by tests/test_gpu_bf16_policy.py)."""
+    from textboost_b200.precision import POLICY
+    return POLICY.act
+
+
+def tol_scale() -> float:
+    """Every 16-bit tolerance in the GPU tests is written for fp16 (unit roundoff 2^-11); the bf16 build rounds at 2^-8,
+    so its errors against the same fp32 statement are allowed 8x those bounds."""
+    from textboost_b200.precision import POLICY
+    return 8.0 if POLICY.name == "bf16" else 1.0

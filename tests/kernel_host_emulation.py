@@ -70,6 +70,14 @@ static inline float __half2float(__half h) { return (float)h; }
 static inline __half __float2half_rn(float f) { return (__half)f; }
 static inline __half __float2half(float f) { return (__half)f; }
 static inline float2 __half22float2(__half2 h) { return float2{(float)h.x, (float)h.y}; }
+namespace tb {  // csrc/sm100.cuh: the 16-bit type of the build (this host build is the fp16 one) and its conversions
+using half_t = __half;
+using half2_t = __half2;
+static inline float h2f(half_t h) { return (float)h; }
+static inline half_t f2h(float f) { return (half_t)f; }
+static inline float2 h22f2(half2_t h) { return float2{(float)h.x, (float)h.y}; }
+static inline half2_t ff2h2(float a, float b) { return half2_t{(half_t)a, (half_t)b}; }
+}
 #define __shared__ static
 #define __expf(x) expf(x)
 static inline void __syncthreads() {}
@@ -315,6 +323,14 @@ static inline float __half2float(__half h) { return (float)h; }
 static inline __half __float2half_rn(float f) { return (__half)f; }
 static inline __half __float2half(float f) { return (__half)f; }
 static inline float2 __half22float2(__half2 h) { return float2{(float)h.x, (float)h.y}; }
+namespace tb {  // csrc/sm100.cuh: the 16-bit type of the build (this host build is the fp16 one) and its conversions
+using half_t = __half;
+using half2_t = __half2;
+static inline float h2f(half_t h) { return (float)h; }
+static inline half_t f2h(float f) { return (half_t)f; }
+static inline float2 h22f2(half2_t h) { return float2{(float)h.x, (float)h.y}; }
+static inline half2_t ff2h2(float a, float b) { return half2_t{(half_t)a, (half_t)b}; }
+}
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline double __dadd_rn(double a, double b) { return a + b; }

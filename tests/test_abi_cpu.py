@@ -28,6 +28,29 @@ def test_library_exports_every_declared_symbol(built_lib):
     assert _cabi.lib().tb_version() == 1
 
 
+def test_both_precision_builds_export_the_same_surface(built_lib):
+    """libtextboost_b200.so (fp16) and libtextboost_b200_bf16.so (-DTB_BF16) are the same ABI; tb_storage_dtype() tells
+    them apart, and the loader refuses a library that does not match the process's precision policy."""
+    from textboost_b200 import build, precision
+    fp16, bf16 = ctypes.CDLL(build.VARIANTS["fp16"][0]), ctypes.CDLL(build.VARIANTS["bf16"][0])
+    for name in header_symbols():
+        assert hasattr(bf16, name), f"{name} missing from the bf16 build"
+    assert fp16.tb_storage_dtype() == 0 and bf16.tb_storage_dtype() == 1
+    assert precision.POLICY.name == os.environ.get("TEXTBOOST_B200_PRECISION", "fp16")
+    with pytest.raises(NotImplementedError):
+        precision.set_policy("no")
+    with pytest.raises(ValueError):
+        precision.set_policy("fp8")
+    code = ("import os; os.environ['TB_LIB'] = %r\n"
+            "from textboost_b200 import _cabi\n"
+            "try:\n    _cabi.lib()\nexcept RuntimeError as e:\n    print('REFUSED', e)\n") % build.VARIANTS["bf16"][0]
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True,
+                       env={k: v for k, v in os.environ.items() if k != "TEXTBOOST_B200_PRECISION"})
+    assert "REFUSED" in r.stdout and "precision" in r.stdout, r.stdout + r.stderr
+
+
 def test_header_is_plain_c(tmp_path):
     """The header compiles as C (no C++/torch types cross the boundary)."""
     import subprocess

@@ -11,9 +11,15 @@ import os
 from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t,
                     c_void_p)
 
+from .precision import POLICY
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# TB_LIB points at an alternative build of the same library (A/B timing of kernel variants); never a fallback
-LIB_PATH = os.environ.get("TB_LIB") or os.path.join(_HERE, "lib", "libtextboost_b200.so")
+
+
+def lib_path() -> str:
+    """The build of the library that matches the process's precision policy (precision.py).  TB_LIB points at an
+    alternative build of the same library (A/B timing of kernel variants); never a fallback."""
+    return os.environ.get("TB_LIB") or os.path.join(_HERE, "lib", POLICY.lib_name)
 
 TB_ACT_NONE, TB_ACT_SILU, TB_ACT_QUICK_GELU, TB_ACT_GELU = 0, 1, 2, 3
 TB_OUT_F16, TB_OUT_F32, TB_OUT_F32_ACC = 0, 1, 2
@@ -41,6 +47,7 @@ _SIGNATURES = {
     "tb_version": [],
     "tb_last_error": [],
     "tb_check_device": [],
+    "tb_storage_dtype": [],
     "tb_set_workspace": [c_void_p, c_void_p, c_size_t],
     "tb_gemm_f16": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
                     POINTER(Epilogue), c_void_p],
@@ -122,15 +129,20 @@ def exported_symbols():
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = lib_path()
+        if not os.path.exists(path):
             raise RuntimeError(
-                f"{LIB_PATH} is missing: the CUDA extension is the product and has no fallback. "
+                f"{path} is missing: the CUDA extension is the product and has no fallback. "
                 "Build it with `python -m textboost_b200.build`.")
-        l = ctypes.CDLL(LIB_PATH)
+        l = ctypes.CDLL(path)
         for name, argtypes in _SIGNATURES.items():
             fn = getattr(l, name)
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, c_int)
+        if l.tb_storage_dtype() != POLICY.storage_code:
+            raise RuntimeError(f"{path} was built for storage type {l.tb_storage_dtype()} but the process's precision "
+                               f"policy is {POLICY.name} (expects {POLICY.storage_code})")
+        POLICY.locked = True
         _lib = l
     return _lib
 
@@ -142,7 +154,7 @@ def last_error() -> str:
 # KERNELS one call of each entry point enqueues (memset nodes are not counted); entry points not listed launch one
 _KERNELS_PER_CALL = {"tb_groupnorm_fwd_f16": 2, "tb_groupnorm_bwd_f16": 2, "tb_attn_bwd_f16": 2,
                      "tb_resize_crop_normalize_u8": 2,
-                     "tb_adamw_fused_step": 3, "tb_version": 0, "tb_check_device": 0, "tb_set_workspace": 0,
+                     "tb_adamw_fused_step": 3, "tb_version": 0, "tb_check_device": 0, "tb_storage_dtype": 0, "tb_set_workspace": 0,
                      "tb_attn_debug_trace": 0}
 TB_GN_STATS_ZEROED = 2
 launch_count = 0  # GPU launches enqueued through this binding since import (bench.py reports the delta)

@@ -1,8 +1,9 @@
-"""In-tree build of libtextboost_b200.so (sm_100a only) with plain nvcc.
+"""In-tree build of libtextboost_b200.so and libtextboost_b200_bf16.so (sm_100a only) with plain nvcc.
 
-The built library lives at textboost_b200/lib/libtextboost_b200.so: it is git-ignored but travels
-to the GPU box with the gpurun snapshot.  No JIT cache, no torch cpp_extension: the C ABI has no
-torch types in it.
+The built libraries live in textboost_b200/lib/: git-ignored, but they travel to the GPU box with the
+gpurun snapshot.  No JIT cache, no torch cpp_extension: the C ABI has no torch types in it.  The two
+libraries are the same sources compiled for the two precision policies (precision.py): fp16 storage by
+default, bf16 storage with -DTB_BF16.
 """
 from __future__ import annotations
 
@@ -17,6 +18,11 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libtextboost_b200.so")
+# policy -> (library file, object directory, extra nvcc flags)
+VARIANTS = {
+    "fp16": (LIB, OBJDIR, []),
+    "bf16": (os.path.join(LIBDIR, "libtextboost_b200_bf16.so"), os.path.join(HERE, "build_bf16"), ["-DTB_BF16"]),
+}
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -38,17 +44,25 @@ def _sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def _digest(paths) -> str:
+def _digest(paths, extra=()) -> str:
     h = hashlib.sha256()
     for p in sorted(paths):
         with open(p, "rb") as f:
             h.update(p.encode())
             h.update(f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + list(extra)).encode())
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, policies=("fp16", "bf16")) -> str:
+    """Build the library of every policy in `policies`; returns the path of the fp16 one (or the first built)."""
+    with ThreadPoolExecutor(max_workers=len(policies)) as ex:
+        libs = list(ex.map(lambda p: _build_variant(p, force, verbose), policies))
+    return LIB if "fp16" in policies else libs[0]
+
+
+def _build_variant(policy: str, force: bool, verbose: bool) -> str:
+    LIB, OBJDIR, extra = VARIANTS[policy]  # noqa: N806 (shadow the module-level fp16 paths)
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
@@ -60,7 +74,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for s in srcs:
         src = os.path.join(CSRC, s)
         obj = os.path.join(OBJDIR, s[:-3] + ".o")
-        dig = _digest([src] + headers)
+        dig = _digest([src] + headers, extra)
         digf = obj + ".sha"
         objs.append(obj)
         if (not force and os.path.exists(obj) and os.path.exists(digf)
@@ -70,7 +84,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         src, obj, dig, digf = job
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = r.stdout + r.stderr
         with open(obj + ".log", "w") as f:
@@ -86,7 +100,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             for src, log in ex.map(compile_one, jobs):
                 if verbose:
                     print(f"== {src}\n{log}")
-    link_dig = _digest(objs)
+    link_dig = _digest(objs, extra)
     if force or jobs or not os.path.exists(LIB) or not os.path.exists(stamp_path) \
             or open(stamp_path).read() != link_dig:
         cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs

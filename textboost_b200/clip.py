@@ -31,7 +31,7 @@ import torch
 from . import _cabi as C
 from . import ops
 
-F16 = torch.float16
+from .precision import POLICY
 F32 = torch.float32
 EOS_ID = 49407  # hard-coded in textboost/text_encoder.py:71
 RMAX = 16       # largest LoRA rank (K extension = targets x r columns, rounded up to 16, <= 64)
@@ -137,7 +137,7 @@ class ClipEngine:
             return sd[k].detach().to(device=self.device, dtype=F32).contiguous()
 
         def g16(k):
-            return sd[k].detach().to(device=self.device, dtype=F16).contiguous()
+            return sd[k].detach().to(device=self.device, dtype=POLICY.act).contiguous()
 
         def base_key(prefix, kind):  # peft renames W to base_layer.W after injection
             k = f"{prefix}.base_layer.{kind}"
@@ -163,9 +163,9 @@ class ClipEngine:
                 ws.append(g16(base_key(p + "self_attn." + t, "weight")))
                 bs.append(g16(base_key(p + "self_attn." + t, "bias")))
             wqkv = torch.cat(ws, 0)  # [3D, D]
-            wext = torch.zeros((3 * D, self.Kext), device=self.device, dtype=F16)
+            wext = torch.zeros((3 * D, self.Kext), device=self.device, dtype=POLICY.act)
             wext[:, :D] = wqkv
-            wext_t = torch.zeros((self.Kext, 3 * D), device=self.device, dtype=F16)
+            wext_t = torch.zeros((self.Kext, 3 * D), device=self.device, dtype=POLICY.act)
             wext_t[:D] = wqkv.t()
             L["wqkv"], L["wqkv_t"], L["bqkv"] = wext, wext_t, torch.cat(bs, 0)
             for name, key in (("o", "self_attn.out_proj"), ("f1", "mlp.fc1"), ("f2", "mlp.fc2")):
@@ -173,9 +173,9 @@ class ClipEngine:
                 L["w" + name], L["w" + name + "_t"] = w, w.t().contiguous()
                 L["b" + name] = g16(base_key(p + key, "bias"))
             if self.has_o:  # [W_o | s B_o] and its transpose, extension filled by pack_lora
-                wo = torch.zeros((D, self.Ko), device=self.device, dtype=F16)
+                wo = torch.zeros((D, self.Ko), device=self.device, dtype=POLICY.act)
                 wo[:, :D] = L["wo"]
-                wo_t = torch.zeros((self.Ko, D), device=self.device, dtype=F16)
+                wo_t = torch.zeros((self.Ko, D), device=self.device, dtype=POLICY.act)
                 wo_t[:D] = L["wo_t"]
                 L["wo"], L["wo_t"] = wo, wo_t
             self.layers.append(L)
@@ -229,7 +229,7 @@ class ClipEngine:
                C.ptr(self.decay), C.ptr(self.pos), C.ptr(x), M, Lq, D, self.n_base, st.n_rows, s)
         saved = []
         for l, L in enumerate(self.layers):
-            y_ext = torch.empty((M, self.Kext), device=self.device, dtype=F16)
+            y_ext = torch.empty((M, self.Kext), device=self.device, dtype=POLICY.act)
             if self.Tq:  # LayerNorm and the LoRA down-projection [LN(x) | LN(x) A^T] in one launch
                 st1 = ops.layernorm_lora_fwd(x, *L["ln1"], st.A(l)[:self.Tq * self.r], y_ext, self.Rq,
                                              eps=self.cfg.layer_norm_eps)
@@ -240,7 +240,7 @@ class ClipEngine:
             # projection output (transformers CLIPAttention under the causal mask, text_encoder.py:62-69)
             q3 = qkv.view(B, Lq, 3 * D)
             # the attention writes straight into the first D columns of the out-projection's (extended) A operand
-            o = torch.empty((M, self.Ko), device=self.device, dtype=F16)
+            o = torch.empty((M, self.Ko), device=self.device, dtype=POLICY.act)
             _, lse = ops.attn_fwd(q3[..., :D], q3[..., D:2 * D], q3[..., 2 * D:], self.heads, causal=True,
                                   out=o.view(B, Lq, self.Ko)[..., :D])
             if self.has_o:
@@ -315,7 +315,7 @@ class ClipEngine:
         C.call("tb_null_override", C.ptr(ids), None, C.ptr(d_out), B, Lq, D, EOS_ID,
                int(self.use_fixed_special), 1, s)
         # every LayerNorm backward also writes the fp16 copy of its result: the next dgrad GEMM's operand
-        g16 = torch.empty((M, D), device=self.device, dtype=F16)
+        g16 = torch.empty((M, D), device=self.device, dtype=POLICY.act)
         g = ops.layernorm_bwd_clip(d_out, xf, self.lnf[0], stf, out16=g16)
         for l in reversed(range(self.nl)):
             L = self.layers[l]
@@ -324,7 +324,7 @@ class ClipEngine:
             du = torch.empty_like(da)
             C.call("tb_act_bwd_f16", C.ptr(u), C.ptr(da), C.ptr(du), u.numel(), self.act, s)
             dy2 = ops.gemm(du, L["wf1_t"])
-            g16 = torch.empty((M, D), device=self.device, dtype=F16)
+            g16 = torch.empty((M, D), device=self.device, dtype=POLICY.act)
             g = ops.layernorm_bwd_clip(dy2, x2, L["ln2"][0], st2, add=g, out=g, out16=g16)
             do = ops.gemm(g16, L["wo_t"])  # [M, Ko]: d(o) and, in the extension columns, d(o A_o^T)
             if self.has_o:
@@ -339,7 +339,7 @@ class ClipEngine:
                          do.view(B, Lq, self.Ko)[..., :D], lse, self.heads, dk=d3[..., D:2 * D],
                          dv=d3[..., 2 * D:], causal=True, dq_out=d3[..., :D])
             dy_ext = ops.gemm(dqkv, L["wqkv_t"])
-            g16 = torch.empty((M, D), device=self.device, dtype=F16) if l else None
+            g16 = torch.empty((M, D), device=self.device, dtype=POLICY.act) if l else None
             if self.Tq:
                 if helper is not None:
                     ready = torch.cuda.Event()

@@ -38,17 +38,17 @@ struct AttnParams {
   int tmem_cols;             // power of two >= the columns the kernel uses
   float scale_log2;          // softmax scale * log2(e)
   float scale;               // softmax scale
-  __half* O;                 // fwd: output; bwd: unused
+  tb::half_t* O;                 // fwd: output; bwd: unused
   long long ldo;
   float* lse;                // [B, heads, Nq]   log2-domain logsumexp
   const float* delta;        // bwd: [B, heads, Nq] rowsum(dO * O)
   float* dQacc;              // bwd: fp32 [B, Nq, lddq] accumulated with red.add (may be null)
   long long lddq;
-  __half* dQ16;              // bwd, single KV tile (Nk <= 128): dQ written once as fp16 [B, Nq, lddq16] (no accumulator)
+  tb::half_t* dQ16;              // bwd, single KV tile (Nk <= 128): dQ written once as fp16 [B, Nq, lddq16] (no accumulator)
   long long lddq16;
-  __half* dK;                // bwd: [B, Nk, lddk] head h at h*d
+  tb::half_t* dK;                // bwd: [B, Nk, lddk] head h at h*d
   long long lddk;
-  __half* dV;
+  tb::half_t* dV;
   long long lddv;
   int n_inner;               // fwd: kv tiles; bwd: q tiles
   int qsplit;                // bwd: CTAs per KV tile, each owning a contiguous range of Q tiles (1 = whole loop)
@@ -84,15 +84,19 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 __device__ __forceinline__ uint32_t exp2_pack(float lo, float hi) {
 #ifdef TB_ATTN_EX2_F16X2
   uint32_t p, e;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(hi), "f"(lo));
+  asm("cvt.rn." TB_H16X2 ".f32 %0, %1, %2;" : "=r"(p) : "f"(hi), "f"(lo));
+#ifdef TB_BF16
+  asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(e) : "r"(p));
+#else
   asm("ex2.approx.f16x2 %0, %1;" : "=r"(e) : "r"(p));
+#endif
   return e;
 #else
   float a, b;
   uint32_t e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(lo));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(b) : "f"(hi));
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(e) : "f"(b), "f"(a));
+  asm("cvt.rn." TB_H16X2 ".f32 %0, %1, %2;" : "=r"(e) : "f"(b), "f"(a));
   return e;
 #endif
 }
@@ -126,7 +130,7 @@ __device__ __forceinline__ float exp2_poly(float x) {
 __device__ __forceinline__ uint32_t exp2_pack_poly(float lo, float hi) {
   uint32_t e;
   const float a = exp2_poly(lo), b = exp2_poly(hi);
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(e) : "f"(b), "f"(a));
+  asm("cvt.rn." TB_H16X2 ".f32 %0, %1, %2;" : "=r"(e) : "f"(b), "f"(a));
   return e;
 }
 // pack k (0..3) of a group of four: the last TB_ATTN_POLY_PACKS packs use the polynomial
@@ -137,7 +141,7 @@ __device__ __forceinline__ uint32_t exp2_pack_mix(float lo, float hi) {
 }
 __device__ __forceinline__ uint32_t hmul2_u32(uint32_t a, uint32_t b) {
   uint32_t r;
-  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  asm("mul.rn." TB_H16X2 " %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
   return r;
 }
 __device__ __forceinline__ void tmem_alloc_rt(uint32_t smem_dst, uint32_t ncols) {
@@ -207,7 +211,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_fence_init();
   }
   {  // tile of ones (B operand of the row-sum MMA); every element equal, so the swizzle is irrelevant
-    const uint4 ones = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+    const uint4 ones = make_uint4(TB_ONE_X2, TB_ONE_X2, TB_ONE_X2, TB_ONE_X2);  // packed pair of 1.0
     for (int i = threadIdx.x; i < ABOX / 16; i += 320) reinterpret_cast<uint4*>(sOnes)[i] = ones;
     fence_async_smem();
   }
@@ -367,7 +371,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float inv_l = 1.f / l;
     const int q = q0 + row;
     const bool ok = q < p.Nq;
-    __half* op = p.O + ((long long)b * p.Nq + q) * p.ldo + h * p.d;
+    tb::half_t* op = p.O + ((long long)b * p.Nq + q) * p.ldo + h * p.d;
     for (int c = half * 16; c < p.dn; c += 32) {
       uint32_t t[16];
       tmem_ld16(lane_addr + O_COL + c, t);
@@ -735,7 +739,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             if ((i & 7) >= 8 - TB_ATTN_FWD2_POLY) exp2_pair_poly(e, p0, p1);
             else exp2_pair_mufu(e, p0, p1);
             if (i & 1) { l2 += p0; l3 += p1; } else { l0 += p0; l1 += p1; }
-            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pk[i]) : "f"(p1), "f"(p0));
+            asm("cvt.rn." TB_H16X2 ".f32 %0, %1, %2;" : "=r"(pk[i]) : "f"(p1), "f"(p0));
           }
           if (c < 3) tmem_ld_wait32(nxt);
           if (SPLIT && c == 2) {  // the last chunk of S_t(j) is in registers: the next scores may overwrite it
@@ -767,7 +771,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const float inv_l = 1.f / l_run;
     const int q = q0 + t * 128 + row;
     const bool ok = q < p.Nq;
-    __half* op = p.O + ((long long)b * p.Nq + q) * p.ldo + h * p.d;
+    tb::half_t* op = p.O + ((long long)b * p.Nq + q) * p.ldo + h * p.d;
     for (int c = 0; c < p.dn; c += 16) {
       uint32_t v[16];
       tmem_ld16(o_col + c, v);
@@ -1035,7 +1039,7 @@ attn_fwd2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         else exp2_pair_mufu(e, p0, p1);
         if (i & 1) lb = add_f32x2(lb, pack_f32x2(p0, p1));
         else la = add_f32x2(la, pack_f32x2(p0, p1));
-        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pk[i]) : "f"(p1), "f"(p0));
+        asm("cvt.rn." TB_H16X2 ".f32 %0, %1, %2;" : "=r"(pk[i]) : "f"(p1), "f"(p0));
       }
       {
         float a0, a1, b0, b1;
@@ -1068,7 +1072,7 @@ attn_fwd2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const float inv_l = 1.f / l_run;
     const int q = q0 + t * 128 + row;
     const bool ok = q < p.Nq;
-    __half* op = p.O + ((long long)b * p.Nq + q) * p.ldo + h * p.d;
+    tb::half_t* op = p.O + ((long long)b * p.Nq + q) * p.ldo + h * p.d;
     for (int c = half * 16; c < p.dn; c += 32) {
       uint32_t v[16];
       tmem_ld16(o_col + c, v);
@@ -1097,7 +1101,7 @@ attn_fwd2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
 // ------------------------------------------------------------------------------------ backward
 // delta[b,h,q] = sum_c dO[b,q,h*d+c] * O[b,q,h*d+c]   (one warp per (b,q), lanes over heads*d/8 vectors)
-__global__ void attn_delta_kernel(const __half* __restrict__ O, const __half* __restrict__ dO,
+__global__ void attn_delta_kernel(const tb::half_t* __restrict__ O, const tb::half_t* __restrict__ dO,
                                   long long ldo, long long lddo, float* __restrict__ delta, int B,
                                   int Nq, int heads, int d) {
   // all 32 lanes stream the row (one 16-byte vector of O and dO each per trip); the per-vector partial dot
@@ -1112,12 +1116,12 @@ __global__ void attn_delta_kernel(const __half* __restrict__ O, const __half* __
   for (int v = lane; v < nvec; v += 32) {
     const uint4 a = *reinterpret_cast<const uint4*>(O + row * ldo + v * 8);
     const uint4 g = *reinterpret_cast<const uint4*>(dO + row * lddo + v * 8);
-    const __half2* ah = reinterpret_cast<const __half2*>(&a);
-    const __half2* gh = reinterpret_cast<const __half2*>(&g);
+    const tb::half2_t* ah = reinterpret_cast<const tb::half2_t*>(&a);
+    const tb::half2_t* gh = reinterpret_cast<const tb::half2_t*>(&g);
     float acc = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float2 x = __half22float2(ah[i]), y = __half22float2(gh[i]);
+      const float2 x = tb::h22f2(ah[i]), y = tb::h22f2(gh[i]);
       acc += x.x * y.x + x.y * y.y;
     }
     part[w][v] = acc;
@@ -1131,8 +1135,8 @@ __global__ void attn_delta_kernel(const __half* __restrict__ O, const __half* __
 }
 
 // q-split backward: fp32 accumulators [2][rows][C] (dV, dK) -> fp16 dV / dK with their row strides
-__global__ void attn_dkv_finish_kernel(const float* __restrict__ ws, __half* __restrict__ dK, long long lddk,
-                                       __half* __restrict__ dV, long long lddv, long long rows, int C) {
+__global__ void attn_dkv_finish_kernel(const float* __restrict__ ws, tb::half_t* __restrict__ dK, long long lddk,
+                                       tb::half_t* __restrict__ dV, long long lddv, long long rows, int C) {
   const long long nvec = rows * (C / 4);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * nvec;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1141,7 +1145,7 @@ __global__ void attn_dkv_finish_kernel(const float* __restrict__ ws, __half* __r
     const long long r = j / (C / 4);
     const int c = (int)(j % (C / 4)) * 4;
     const float4 f = *reinterpret_cast<const float4*>(ws + (which * rows + r) * C + c);
-    __half* dst = which ? dK + r * lddk + c : dV + r * lddv + c;
+    tb::half_t* dst = which ? dK + r * lddk + c : dV + r * lddv + c;
     uint2 o;
     o.x = pack_half2(f.x, f.y);
     o.y = pack_half2(f.z, f.w);
@@ -1479,7 +1483,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           // single KV tile: this CTA holds the whole dQ row -> one fp16 store, no accumulator, no memset, no cast
           const int q = q0 + row;
           const int cbase = ch * 128;
-          __half* dq = p.dQ16 + ((long long)b * p.Nq + q) * p.lddq16 + h * p.d + cbase;
+          tb::half_t* dq = p.dQ16 + ((long long)b * p.Nq + q) * p.lddq16 + h * p.d + cbase;
           const int ncols = (p.dn - cbase) > 128 ? 128 : (p.dn - cbase);
           for (int c = half * 16; c < ncols; c += 32) {
             uint32_t r[16];
@@ -1529,8 +1533,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
       } else if (kv_ok) {
-        __half* dv = p.dV + ((long long)b * p.Nk + kv0 + row) * p.lddv + h * p.d;
-        __half* dk = p.dK + ((long long)b * p.Nk + kv0 + row) * p.lddk + h * p.d;
+        tb::half_t* dv = p.dV + ((long long)b * p.Nk + kv0 + row) * p.lddv + h * p.d;
+        tb::half_t* dk = p.dK + ((long long)b * p.Nk + kv0 + row) * p.lddk + h * p.d;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           if (c + g * 8 < p.d) {
@@ -1898,8 +1902,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           }
         }
       } else if (kv_ok) {
-        __half* dv = p.dV + ((long long)b * p.Nk + kv0 + row) * p.lddv + h * p.d;
-        __half* dk = p.dK + ((long long)b * p.Nk + kv0 + row) * p.lddk + h * p.d;
+        tb::half_t* dv = p.dV + ((long long)b * p.Nk + kv0 + row) * p.lddv + h * p.d;
+        tb::half_t* dk = p.dK + ((long long)b * p.Nk + kv0 + row) * p.lddk + h * p.d;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           if (c + g * 8 < p.d) {
@@ -1953,7 +1957,7 @@ __device__ __forceinline__ uint32_t hmul2_sub(uint32_t pp, uint64_t dp2, uint64_
   float a, b;
   unpack_f32x2(sub_f32x2(dp2, delta2), a, b);
   uint32_t h;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));
+  asm("cvt.rn." TB_H16X2 ".f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));
   return hmul2_u32(pp, h);
 }
 
@@ -2198,7 +2202,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const uint64_t e = fma_f32x2(pack_f32x2(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1])), sc2, negl2);
         float p0, p1;
         exp2_pair_mufu(e, p0, p1);
-        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pk[k]) : "f"(p1), "f"(p0));
+        asm("cvt.rn." TB_H16X2 ".f32 %0, %1, %2;" : "=r"(pk[k]) : "f"(p1), "f"(p0));
         if (MASKED) {
           if (cb + 2 * k >= kvalid) pk[k] &= 0xffff0000u;
           if (cb + 2 * k + 1 >= kvalid) pk[k] &= 0x0000ffffu;
@@ -2226,7 +2230,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tmem_ld_wait();
         const int q = (i_begin + it) * 128 + row;
         if (q < p.Nq) {
-          __half* dq = p.dQ16 + ((long long)b * p.Nq + q) * p.lddq16 + h * p.d + cg * 16;
+          tb::half_t* dq = p.dQ16 + ((long long)b * p.Nq + q) * p.lddq16 + h * p.d + cg * 16;
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             if (cg * 16 + g * 8 < p.d) {
@@ -2351,8 +2355,8 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           }
         }
       } else if (kv_ok) {
-        __half* dv = p.dV + ((long long)b * p.Nk + kv0 + row) * p.lddv + h * p.d;
-        __half* dk = p.dK + ((long long)b * p.Nk + kv0 + row) * p.lddk + h * p.d;
+        tb::half_t* dv = p.dV + ((long long)b * p.Nk + kv0 + row) * p.lddv + h * p.d;
+        tb::half_t* dk = p.dK + ((long long)b * p.Nk + kv0 + row) * p.lddk + h * p.d;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           if (c + g * 8 < p.d) {
@@ -2558,7 +2562,7 @@ extern "C" int tb_attn_fwd_f16(const void* q, int64_t ldq, const void* k, int64_
   p.tmem_cols = (128 + p.dn + 16 <= 256) ? 256 : 512;
   p.scale = scale;
   p.scale_log2 = scale * 1.4426950408889634f;
-  p.O = (__half*)o; p.ldo = ldo; p.lse = lse;
+  p.O = (tb::half_t*)o; p.ldo = ldo; p.lse = lse;
   p.trace = g_attn_trace;
   p.n_inner = (Nk + 127) / 128;
   const int nb = (d + 63) / 64;
@@ -2601,7 +2605,7 @@ extern "C" int tb_attn_bwd_f16(const void* q, int64_t ldq, const void* k, int64_
     const long long rows = (long long)B * Nq;
     const int wpb = 8;
     attn_delta_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(
-        (const __half*)o, (const __half*)dO, ldo, lddo, delta, B, Nq, heads, d);
+        (const tb::half_t*)o, (const tb::half_t*)dO, ldo, lddo, delta, B, Nq, heads, d);
     if ((rc = check_launch("attn_delta_kernel"))) return rc;
   }
   if (dQacc) {
@@ -2623,9 +2627,9 @@ extern "C" int tb_attn_bwd_f16(const void* q, int64_t ldq, const void* k, int64_
   p.lse = const_cast<float*>(lse);
   p.delta = delta;
   p.dQacc = dQacc; p.lddq = lddq;
-  p.dQ16 = (__half*)dQ16; p.lddq16 = lddq16;
-  p.dK = (__half*)dK; p.lddk = lddk;
-  p.dV = (__half*)dV; p.lddv = lddv;
+  p.dQ16 = (tb::half_t*)dQ16; p.lddq16 = lddq16;
+  p.dK = (tb::half_t*)dK; p.lddk = lddk;
+  p.dV = (tb::half_t*)dV; p.lddv = lddv;
   p.n_inner = (Nq + 127) / 128;
   p.trace = g_attn_trace;
   {
@@ -2670,6 +2674,6 @@ extern "C" int tb_attn_bwd_f16(const void* q, int64_t ldq, const void* k, int64_
   const long long rows = (long long)B * Nk;
   const long long nvec = 2 * rows * (heads * d / 4);
   attn_dkv_finish_kernel<<<(unsigned)((nvec + 255) / 256 > 1184 ? 1184 : (nvec + 255) / 256), 256, 0, st>>>(
-      p.dkv_ws, (__half*)dK, lddk, (__half*)dV, lddv, rows, heads * d);
+      p.dkv_ws, (tb::half_t*)dK, lddk, (tb::half_t*)dV, lddv, rows, heads * d);
   return check_launch("attn_dkv_finish_kernel");
 }

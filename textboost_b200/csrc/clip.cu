@@ -49,12 +49,12 @@ __global__ void clip_embed_grad_kernel(const long long* __restrict__ ids, const 
 // (columns D .. D+R-1 of a row of stride ld; columns D+R .. D+RPAD-1 are zeroed).  R <= LORA_RMAX, processed 16
 // down-projection rows at a time (the activation row is re-read from L1 per group).
 constexpr int LORA_RMAX = 64;  // widest K extension: four fused targets x rank 16
-__global__ void lora_down_kernel(__half* __restrict__ y_ext, long long ld, const float* __restrict__ A,
+__global__ void lora_down_kernel(tb::half_t* __restrict__ y_ext, long long ld, const float* __restrict__ A,
                                  int M, int D, int R, int RPAD) {
   const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (m >= M) return;
   const int lane = threadIdx.x & 31;
-  __half* row = y_ext + (long long)m * ld;
+  tb::half_t* row = y_ext + (long long)m * ld;
   for (int j0 = 0; j0 < RPAD; j0 += 16) {
     float acc[16];
 #pragma unroll
@@ -63,11 +63,11 @@ __global__ void lora_down_kernel(__half* __restrict__ y_ext, long long ld, const
       // 8 consecutive columns per lane and trip: one 16-byte load of y, two float4 loads of each A row (L1-resident)
       for (int c = lane * 8; c < D; c += 256) {
         const uint4 q = *reinterpret_cast<const uint4*>(row + c);
-        const __half2* h = reinterpret_cast<const __half2*>(&q);
+        const tb::half2_t* h = reinterpret_cast<const tb::half2_t*>(&q);
         float v[8];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float2 f = __half22float2(h[i]);
+          const float2 f = tb::h22f2(h[i]);
           v[2 * i] = f.x;
           v[2 * i + 1] = f.y;
         }
@@ -89,7 +89,7 @@ __global__ void lora_down_kernel(__half* __restrict__ y_ext, long long ld, const
 #pragma unroll
       for (int j = 0; j < 16; ++j)
         if (j == lane && j0 + j < R) v = acc[j];
-      row[D + j0 + lane] = __float2half(v);
+      row[D + j0 + lane] = tb::f2h(v);
     }
   }
 }
@@ -109,8 +109,8 @@ __device__ __forceinline__ int lora_bits(int m) {  // (<= 8 blocks; plain arithm
 __device__ __forceinline__ int lora_slot(int tmask, int b) {  // index among the set bits, or -1
   return ((tmask >> b) & 1) ? lora_bits(tmask & ((1 << b) - 1)) : -1;
 }
-__global__ void lora_pack_kernel(const float* __restrict__ Bm, __half* __restrict__ Wext,
-                                 __half* __restrict__ WextT, int nblk, int tmask, int D, int r, int RPAD,
+__global__ void lora_pack_kernel(const float* __restrict__ Bm, tb::half_t* __restrict__ Wext,
+                                 tb::half_t* __restrict__ WextT, int nblk, int tmask, int D, int r, int RPAD,
                                  float scaling) {
   const int K = D + RPAD;
   const long long total = (long long)nblk * D * RPAD;
@@ -122,7 +122,7 @@ __global__ void lora_pack_kernel(const float* __restrict__ Bm, __half* __restric
     const int t = lora_slot(tmask, b);
     float v = 0.f;
     if (t >= 0 && e >= t * r && e < (t + 1) * r) v = scaling * Bm[((long long)t * D + n) * r + (e - t * r)];
-    const __half hv = __float2half(v);
+    const tb::half_t hv = tb::f2h(v);
     Wext[row * K + D + e] = hv;
     WextT[(long long)(D + e) * (nblk * D) + row] = hv;
   }
@@ -143,8 +143,8 @@ constexpr int LG_ROWS = 16;  // rows per CTA: all of a thread's row loads are in
 // warps are resident to hide the load latency (a first version with 48 serial rows per thread took 26 us, one with 8
 // columns x 16 rows per thread and 206 registers 21 us at 6 % occupancy; ncu, profiles/r02_ncu_cases_summary.txt).
 __global__ void __launch_bounds__(128)
-lora_grad_kernel(const __half* __restrict__ dY, const __half* __restrict__ y_ext,
-                 const __half* __restrict__ dA_ext, long long ld, float* __restrict__ dB,
+lora_grad_kernel(const tb::half_t* __restrict__ dY, const tb::half_t* __restrict__ y_ext,
+                 const tb::half_t* __restrict__ dA_ext, long long ld, float* __restrict__ dB,
                  float* __restrict__ dA, int M, int nblk, int tmask, int D, int r, float scaling) {
   __shared__ float sxa[LG_ROWS][LORA_RMAX];
   __shared__ float sdx[LG_ROWS][LORA_RMAX];
@@ -157,21 +157,21 @@ lora_grad_kernel(const __half* __restrict__ dY, const __half* __restrict__ y_ext
   const int t = is_b ? lora_slot(tmask, col / D) : 0;
   const bool work = live && t >= 0;
   // this thread's operand rows first: their latency overlaps the staging of the coefficient rows below
-  __half2 q[LG_ROWS];
+  tb::half2_t q[LG_ROWS];
   if (work) {
-    const __half* src = is_b ? dY + (long long)m0 * NY + col : y_ext + (long long)m0 * ld + (col - NY);
+    const tb::half_t* src = is_b ? dY + (long long)m0 * NY + col : y_ext + (long long)m0 * ld + (col - NY);
     const long long lds = is_b ? NY : ld;
 #pragma unroll
     for (int mm = 0; mm < LG_ROWS; ++mm)
-      q[mm] = mm < rows ? *reinterpret_cast<const __half2*>(src + (long long)mm * lds) : __half2{};
+      q[mm] = mm < rows ? *reinterpret_cast<const tb::half2_t*>(src + (long long)mm * lds) : tb::half2_t{};
   }
   // coefficient rows: the R extension columns of y_ext (xa) and dA_ext (dxa), two per load
   for (int i = threadIdx.x; i < LG_ROWS * (LORA_RMAX / 2); i += blockDim.x) {
     const int mm = i / (LORA_RMAX / 2), j = 2 * (i % (LORA_RMAX / 2));
     float2 a = {0.f, 0.f}, b = {0.f, 0.f};
     if (mm < rows && j < R) {  // (R is even or the K extension is padded with zeros: reading j + 1 is in bounds)
-      a = __half22float2(*reinterpret_cast<const __half2*>(y_ext + (long long)(m0 + mm) * ld + D + j));
-      b = __half22float2(*reinterpret_cast<const __half2*>(dA_ext + (long long)(m0 + mm) * ld + D + j));
+      a = tb::h22f2(*reinterpret_cast<const tb::half2_t*>(y_ext + (long long)(m0 + mm) * ld + D + j));
+      b = tb::h22f2(*reinterpret_cast<const tb::half2_t*>(dA_ext + (long long)(m0 + mm) * ld + D + j));
       if (j + 1 >= R) a.y = b.y = 0.f;
     }
     sxa[mm][j] = a.x;
@@ -186,7 +186,7 @@ lora_grad_kernel(const __half* __restrict__ dY, const __half* __restrict__ y_ext
   float v0[LG_ROWS], v1[LG_ROWS];
 #pragma unroll
   for (int mm = 0; mm < LG_ROWS; ++mm) {
-    const float2 f = __half22float2(q[mm]);
+    const float2 f = tb::h22f2(q[mm]);
     v0[mm] = f.x;
     v1[mm] = f.y;
   }
@@ -211,36 +211,36 @@ lora_grad_kernel(const __half* __restrict__ dY, const __half* __restrict__ y_ext
 }
 
 // dy[m, c] += sum_j dxa[m, j] * A[j, c]   (in place on the first D columns of dA_ext)
-__global__ void lora_dx_kernel(__half* __restrict__ dA_ext, long long ld, const float* __restrict__ A,
+__global__ void lora_dx_kernel(tb::half_t* __restrict__ dA_ext, long long ld, const float* __restrict__ A,
                                int M, int D, int R) {
   const int m = blockIdx.x;
   __shared__ float sx[LORA_RMAX];
-  if (threadIdx.x < LORA_RMAX) sx[threadIdx.x] = threadIdx.x < R ? __half2float(dA_ext[(long long)m * ld + D + threadIdx.x]) : 0.f;
+  if (threadIdx.x < LORA_RMAX) sx[threadIdx.x] = threadIdx.x < R ? tb::h2f(dA_ext[(long long)m * ld + D + threadIdx.x]) : 0.f;
   __syncthreads();
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    float v = __half2float(dA_ext[(long long)m * ld + c]);
+    float v = tb::h2f(dA_ext[(long long)m * ld + c]);
     for (int j = 0; j < R; ++j) v += sx[j] * A[(long long)j * D + c];
-    dA_ext[(long long)m * ld + c] = __float2half(v);
+    dA_ext[(long long)m * ld + c] = tb::f2h(v);
   }
 }
 
 // ------------------------------------------------------------------ causal attention, L <= 128, d = 64
 // qkv [B*L, 3*D] fp16 (q | k | v, head h at columns h*64); one CTA per (b, h).
 template <bool BWD>
-__global__ void clip_attn_kernel(const __half* __restrict__ qkv, const __half* __restrict__ dO,
-                                 __half* __restrict__ out, int L, int D, int heads, float scale) {
+__global__ void clip_attn_kernel(const tb::half_t* __restrict__ qkv, const tb::half_t* __restrict__ dO,
+                                 tb::half_t* __restrict__ out, int L, int D, int heads, float scale) {
   constexpr int HD = 64;
   extern __shared__ float smf[];
   const int PS = (L * (L + 1) + 3) & ~3;  // keep the fp16 tiles 16-byte aligned
   float* sP = smf;                        // [L][L+1]
   float* sdS = sP + PS;                   // [L][L+1] (BWD only)
-  __half* sQ = reinterpret_cast<__half*>(BWD ? sdS + PS : sP + PS);
-  __half* sK = sQ + L * HD;
-  __half* sV = sK + L * HD;
-  __half* sdO = sV + L * HD;  // BWD only
+  tb::half_t* sQ = reinterpret_cast<tb::half_t*>(BWD ? sdS + PS : sP + PS);
+  tb::half_t* sK = sQ + L * HD;
+  tb::half_t* sV = sK + L * HD;
+  tb::half_t* sdO = sV + L * HD;  // BWD only
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const long long rs = 3LL * D;
-  const __half* base = qkv + (long long)b * L * rs + h * HD;
+  const tb::half_t* base = qkv + (long long)b * L * rs + h * HD;
   for (int i = threadIdx.x; i < L * HD / 8; i += blockDim.x) {
     const int l = i / (HD / 8), v = i % (HD / 8);
     reinterpret_cast<uint4*>(sQ)[i] = *reinterpret_cast<const uint4*>(base + l * rs + v * 8);
@@ -257,11 +257,11 @@ __global__ void clip_attn_kernel(const __half* __restrict__ qkv, const __half* _
     float acc = -INFINITY;
     if (j <= i) {
       acc = 0.f;
-      const __half2* qp = reinterpret_cast<const __half2*>(sQ + i * HD);
-      const __half2* kp = reinterpret_cast<const __half2*>(sK + j * HD);
+      const tb::half2_t* qp = reinterpret_cast<const tb::half2_t*>(sQ + i * HD);
+      const tb::half2_t* kp = reinterpret_cast<const tb::half2_t*>(sK + j * HD);
 #pragma unroll 8
       for (int c = 0; c < HD / 2; ++c) {
-        const float2 a = __half22float2(qp[c]), bb = __half22float2(kp[c]);
+        const float2 a = tb::h22f2(qp[c]), bb = tb::h22f2(kp[c]);
         acc += a.x * bb.x + a.y * bb.y;
       }
       acc *= scale;
@@ -285,15 +285,15 @@ __global__ void clip_attn_kernel(const __half* __restrict__ qkv, const __half* _
     sum = warp_sum_c(sum);
     const float inv = 1.f / sum;
     // the reference casts the probabilities to the matmul dtype (fp16 under autocast) before P V
-    for (int j = lane; j < L; j += 32) sP[i * (L + 1) + j] = __half2float(__float2half(sP[i * (L + 1) + j] * inv));
+    for (int j = lane; j < L; j += 32) sP[i * (L + 1) + j] = tb::h2f(tb::f2h(sP[i * (L + 1) + j] * inv));
   }
   __syncthreads();
   if (!BWD) {
     for (int idx = threadIdx.x; idx < L * HD; idx += blockDim.x) {
       const int i = idx / HD, c = idx % HD;
       float acc = 0.f;
-      for (int j = 0; j <= i; ++j) acc += sP[i * (L + 1) + j] * __half2float(sV[j * HD + c]);
-      out[((long long)b * L + i) * D + h * HD + c] = __float2half(acc);
+      for (int j = 0; j <= i; ++j) acc += sP[i * (L + 1) + j] * tb::h2f(sV[j * HD + c]);
+      out[((long long)b * L + i) * D + h * HD + c] = tb::f2h(acc);
     }
     return;
   }
@@ -302,11 +302,11 @@ __global__ void clip_attn_kernel(const __half* __restrict__ qkv, const __half* _
     const int i = idx / L, j = idx % L;
     float acc = 0.f;
     if (j <= i) {
-      const __half2* gp = reinterpret_cast<const __half2*>(sdO + i * HD);
-      const __half2* vp = reinterpret_cast<const __half2*>(sV + j * HD);
+      const tb::half2_t* gp = reinterpret_cast<const tb::half2_t*>(sdO + i * HD);
+      const tb::half2_t* vp = reinterpret_cast<const tb::half2_t*>(sV + j * HD);
 #pragma unroll 8
       for (int c = 0; c < HD / 2; ++c) {
-        const float2 a = __half22float2(gp[c]), bb = __half22float2(vp[c]);
+        const float2 a = tb::h22f2(gp[c]), bb = tb::h22f2(vp[c]);
         acc += a.x * bb.x + a.y * bb.y;
       }
     }
@@ -321,18 +321,18 @@ __global__ void clip_attn_kernel(const __half* __restrict__ qkv, const __half* _
       sdS[i * (L + 1) + j] = j <= i ? sP[i * (L + 1) + j] * (sdS[i * (L + 1) + j] - dsum) * scale : 0.f;
   }
   __syncthreads();
-  __half* obase = out + (long long)b * L * rs + h * HD;  // d(qkv) laid out like qkv
+  tb::half_t* obase = out + (long long)b * L * rs + h * HD;  // d(qkv) laid out like qkv
   for (int idx = threadIdx.x; idx < L * HD; idx += blockDim.x) {
     const int i = idx / HD, c = idx % HD;
     float dq = 0.f, dk = 0.f, dv = 0.f;
-    for (int j = 0; j <= i; ++j) dq += sdS[i * (L + 1) + j] * __half2float(sK[j * HD + c]);
+    for (int j = 0; j <= i; ++j) dq += sdS[i * (L + 1) + j] * tb::h2f(sK[j * HD + c]);
     for (int j = i; j < L; ++j) {
-      dk += sdS[j * (L + 1) + i] * __half2float(sQ[j * HD + c]);
-      dv += sP[j * (L + 1) + i] * __half2float(sdO[j * HD + c]);
+      dk += sdS[j * (L + 1) + i] * tb::h2f(sQ[j * HD + c]);
+      dv += sP[j * (L + 1) + i] * tb::h2f(sdO[j * HD + c]);
     }
-    obase[i * rs + c] = __float2half(dq);
-    obase[i * rs + D + c] = __float2half(dk);
-    obase[i * rs + 2 * D + c] = __float2half(dv);
+    obase[i * rs + c] = tb::f2h(dq);
+    obase[i * rs + D + c] = tb::f2h(dk);
+    obase[i * rs + 2 * D + c] = tb::f2h(dv);
   }
 }
 
@@ -351,30 +351,30 @@ __device__ __forceinline__ float act_bwd(float u, int kind) {
 }
 // BWD=false: out = act(u);  BWD=true: out = g * act'(u).  Eight elements per thread and trip (16-byte accesses).
 template <bool BWD>
-__global__ void act_kernel(const __half* __restrict__ u, const __half* __restrict__ g,
-                           __half* __restrict__ out, long long n, int kind) {
+__global__ void act_kernel(const tb::half_t* __restrict__ u, const tb::half_t* __restrict__ g,
+                           tb::half_t* __restrict__ out, long long n, int kind) {
   const long long nv = n / 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
        i += (long long)gridDim.x * blockDim.x) {
     const uint4 qu = *reinterpret_cast<const uint4*>(u + i * 8);
     uint4 qg = make_uint4(0u, 0u, 0u, 0u);
     if (BWD) qg = *reinterpret_cast<const uint4*>(g + i * 8);
-    const __half* hu = reinterpret_cast<const __half*>(&qu);
-    const __half* hg = reinterpret_cast<const __half*>(&qg);
+    const tb::half_t* hu = reinterpret_cast<const tb::half_t*>(&qu);
+    const tb::half_t* hg = reinterpret_cast<const tb::half_t*>(&qg);
     uint4 qo;
-    __half* ho = reinterpret_cast<__half*>(&qo);
+    tb::half_t* ho = reinterpret_cast<tb::half_t*>(&qo);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float x = __half2float(hu[k]);
-      ho[k] = __float2half(BWD ? __half2float(hg[k]) * act_bwd(x, kind) : act_fwd(x, kind));
+      const float x = tb::h2f(hu[k]);
+      ho[k] = tb::f2h(BWD ? tb::h2f(hg[k]) * act_bwd(x, kind) : act_fwd(x, kind));
     }
     *reinterpret_cast<uint4*>(out + i * 8) = qo;
   }
   // tail (n % 8 elements), one thread
   if (blockIdx.x == 0 && threadIdx.x == 0)
     for (long long i = nv * 8; i < n; ++i) {
-      const float x = __half2float(u[i]);
-      out[i] = __float2half(BWD ? __half2float(g[i]) * act_bwd(x, kind) : act_fwd(x, kind));
+      const float x = tb::h2f(u[i]);
+      out[i] = tb::f2h(BWD ? tb::h2f(g[i]) * act_bwd(x, kind) : act_fwd(x, kind));
     }
 }
 
@@ -470,7 +470,7 @@ extern "C" int tb_lora_down(void* y_ext, int64_t ld, const float* A, int M, int 
   TB_REQUIRE(y_ext && A && R >= 1 && R <= LORA_RMAX && RPAD <= LORA_RMAX && R <= RPAD && RPAD % 8 == 0, TB_E_ARG,
              "tb_lora_down: bad args (R=%d RPAD=%d; R <= RPAD <= %d)", R, RPAD, LORA_RMAX);
   TB_REQUIRE(D % 8 == 0 && ld % 8 == 0, TB_E_ALIGN, "tb_lora_down: D and ld must be multiples of 8");
-  lora_down_kernel<<<(M + 7) / 8, 256, 0, st>>>((__half*)y_ext, ld, A, M, D, R, RPAD);
+  lora_down_kernel<<<(M + 7) / 8, 256, 0, st>>>((tb::half_t*)y_ext, ld, A, M, D, R, RPAD);
   return check_launch("lora_down_kernel");
 }
 static int lora_mask_ok(int nblk, int tmask, int r, int RPAD) {
@@ -485,7 +485,7 @@ extern "C" int tb_lora_pack(const float* Bm, void* Wext, void* WextT, int nblk, 
   TB_REQUIRE(Bm && Wext && WextT && lora_mask_ok(nblk, tmask, r, RPAD), TB_E_ARG,
              "tb_lora_pack: bad args (nblk=%d tmask=%d r=%d RPAD=%d)", nblk, tmask, r, RPAD);
   const long long total = (long long)nblk * D * RPAD;
-  lora_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Bm, (__half*)Wext, (__half*)WextT, nblk, tmask,
+  lora_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Bm, (tb::half_t*)Wext, (tb::half_t*)WextT, nblk, tmask,
                                                                    D, r, RPAD, scaling);
   return check_launch("lora_pack_kernel");
 }
@@ -497,14 +497,14 @@ extern "C" int tb_lora_grad(const void* dY, const void* y_ext, const void* dA_ex
   TB_REQUIRE(D % 2 == 0 && ld % 2 == 0, TB_E_ALIGN, "tb_lora_grad: D and ld must be even");
   const int pairs = (nblk * D + D) / 2;
   dim3 grid((pairs + 127) / 128, (M + LG_ROWS - 1) / LG_ROWS);
-  lora_grad_kernel<<<grid, 128, 0, st>>>((const __half*)dY, (const __half*)y_ext, (const __half*)dA_ext, ld, dB, dA,
+  lora_grad_kernel<<<grid, 128, 0, st>>>((const tb::half_t*)dY, (const tb::half_t*)y_ext, (const tb::half_t*)dA_ext, ld, dB, dA,
                                          M, nblk, tmask, D, r, scaling);
   return check_launch("lora_grad_kernel");
 }
 extern "C" int tb_lora_dx(void* dA_ext, int64_t ld, const float* A, int M, int D, int R, void* stream) {
   TB_ENTER();
   TB_REQUIRE(dA_ext && A && R >= 1 && R <= LORA_RMAX, TB_E_ARG, "tb_lora_dx: bad args (R=%d)", R);
-  lora_dx_kernel<<<M, 256, 0, st>>>((__half*)dA_ext, ld, A, M, D, R);
+  lora_dx_kernel<<<M, 256, 0, st>>>((tb::half_t*)dA_ext, ld, A, M, D, R);
   return check_launch("lora_dx_kernel");
 }
 extern "C" int tb_clip_attn_fwd(const void* qkv, void* out, int B, int L, int D, int heads, void* stream) {
@@ -517,7 +517,7 @@ extern "C" int tb_clip_attn_fwd(const void* qkv, void* out, int B, int L, int D,
     cudaFuncSetAttribute(clip_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 129 * 4 + 3 * 128 * 64 * 2);
     cfg = true;
   }
-  clip_attn_kernel<false><<<B * heads, 256, smem, st>>>((const __half*)qkv, nullptr, (__half*)out, L, D,
+  clip_attn_kernel<false><<<B * heads, 256, smem, st>>>((const tb::half_t*)qkv, nullptr, (tb::half_t*)out, L, D,
                                                         heads, 0.125f);
   return check_launch("clip_attn_kernel<fwd>");
 }
@@ -531,7 +531,7 @@ extern "C" int tb_clip_attn_bwd(const void* qkv, const void* dO, void* dqkv, int
     cudaFuncSetAttribute(clip_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 129 * 4 + 4 * 128 * 64 * 2);
     cfg = true;
   }
-  clip_attn_kernel<true><<<B * heads, 256, smem, st>>>((const __half*)qkv, (const __half*)dO, (__half*)dqkv,
+  clip_attn_kernel<true><<<B * heads, 256, smem, st>>>((const tb::half_t*)qkv, (const tb::half_t*)dO, (tb::half_t*)dqkv,
                                                        L, D, heads, 0.125f);
   return check_launch("clip_attn_kernel<bwd>");
 }
@@ -540,7 +540,7 @@ extern "C" int tb_act_fwd_f16(const void* u, void* out, int64_t n, int kind, voi
   TB_REQUIRE(u && out && (kind == TB_ACT_QUICK_GELU || kind == TB_ACT_GELU), TB_E_ARG, "tb_act_fwd_f16: bad args");
   TB_REQUIRE(((uintptr_t)u | (uintptr_t)out) % 16 == 0, TB_E_ALIGN, "tb_act_fwd_f16: 16-byte alignment");
   act_kernel<false><<<(unsigned)((n / 8 + 255) / 256 > 1184 ? 1184 : (n / 8 + 255) / 256 + 1), 256, 0, st>>>(
-      (const __half*)u, nullptr, (__half*)out, n, kind);
+      (const tb::half_t*)u, nullptr, (tb::half_t*)out, n, kind);
   return check_launch("act_kernel<fwd>");
 }
 extern "C" int tb_act_bwd_f16(const void* u, const void* g, void* out, int64_t n, int kind, void* stream) {
@@ -548,7 +548,7 @@ extern "C" int tb_act_bwd_f16(const void* u, const void* g, void* out, int64_t n
   TB_REQUIRE(u && g && out && (kind == TB_ACT_QUICK_GELU || kind == TB_ACT_GELU), TB_E_ARG, "tb_act_bwd_f16: bad args");
   TB_REQUIRE(((uintptr_t)u | (uintptr_t)g | (uintptr_t)out) % 16 == 0, TB_E_ALIGN, "tb_act_bwd_f16: 16-byte alignment");
   act_kernel<true><<<(unsigned)((n / 8 + 255) / 256 > 1184 ? 1184 : (n / 8 + 255) / 256 + 1), 256, 0, st>>>(
-      (const __half*)u, (const __half*)g, (__half*)out, n, kind);
+      (const tb::half_t*)u, (const tb::half_t*)g, (tb::half_t*)out, n, kind);
   return check_launch("act_kernel<bwd>");
 }
 extern "C" int tb_null_override(const int64_t* ids, const float* null_emb, float* h, int B, int L, int D,

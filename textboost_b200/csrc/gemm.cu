@@ -36,8 +36,8 @@ struct GemmParams {
   // epilogue
   void* C;
   long long ldc;
-  const __half* bias;
-  const __half* rowvec;
+  const tb::half_t* bias;
+  const tb::half_t* rowvec;
   long long ldrv;     // row stride of rowvec (>= N: a column slice of one batched time-embedding projection)
   int rows_per_group;
   const void* residual;
@@ -239,15 +239,15 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
         const long long m = (long long)m_tile * p.tile_rows + row;
         const int ncol0 = n_tile * BN;
         const uint32_t acc_addr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
-        const __half* res = (p.residual && row < p.tile_rows)
-                                ? reinterpret_cast<const __half*>(p.residual) + m * p.ldr + ncol0
+        const tb::half_t* res = (p.residual && row < p.tile_rows)
+                                ? reinterpret_cast<const tb::half_t*>(p.residual) + m * p.ldr + ncol0
                                 : nullptr;
         const bool row_live = row < p.tile_rows;
         named_bar_sync(3, 256);  // every warp has finished reading the previous tile's sBV
         if (epi_tid < BN) {
-          float bv = p.bias ? __half2float(p.bias[ncol0 + epi_tid]) : 0.f;
+          float bv = p.bias ? tb::h2f(p.bias[ncol0 + epi_tid]) : 0.f;
           if (p.rowvec)
-            bv += __half2float(
+            bv += tb::h2f(
                 p.rowvec[((long long)m_tile * p.tile_rows / p.rows_per_group) * p.ldrv + ncol0 + epi_tid]);
           sBV[epi_tid] = bv;
         }
@@ -284,16 +284,16 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
               o.w = pack_half2(__uint_as_float(r[j + 6]) + b1.z, __uint_as_float(r[j + 7]) + b1.w);
               if (res) {
                 const uint4 q = rq[j >> 3];
-                *reinterpret_cast<__half2*>(&o.x) = __hadd2(*reinterpret_cast<const __half2*>(&o.x), *reinterpret_cast<const __half2*>(&q.x));
-                *reinterpret_cast<__half2*>(&o.y) = __hadd2(*reinterpret_cast<const __half2*>(&o.y), *reinterpret_cast<const __half2*>(&q.y));
-                *reinterpret_cast<__half2*>(&o.z) = __hadd2(*reinterpret_cast<const __half2*>(&o.z), *reinterpret_cast<const __half2*>(&q.z));
-                *reinterpret_cast<__half2*>(&o.w) = __hadd2(*reinterpret_cast<const __half2*>(&o.w), *reinterpret_cast<const __half2*>(&q.w));
+                *reinterpret_cast<tb::half2_t*>(&o.x) = __hadd2(*reinterpret_cast<const tb::half2_t*>(&o.x), *reinterpret_cast<const tb::half2_t*>(&q.x));
+                *reinterpret_cast<tb::half2_t*>(&o.y) = __hadd2(*reinterpret_cast<const tb::half2_t*>(&o.y), *reinterpret_cast<const tb::half2_t*>(&q.y));
+                *reinterpret_cast<tb::half2_t*>(&o.z) = __hadd2(*reinterpret_cast<const tb::half2_t*>(&o.z), *reinterpret_cast<const tb::half2_t*>(&q.z));
+                *reinterpret_cast<tb::half2_t*>(&o.w) = __hadd2(*reinterpret_cast<const tb::half2_t*>(&o.w), *reinterpret_cast<const tb::half2_t*>(&q.w));
               }
               if (staged) {
                 const int chunk = ((c & 63) + j) >> 3;
                 *reinterpret_cast<uint4*>(box + row * 128 + ((chunk ^ (row & 7)) << 4)) = o;
               } else if (row_live) {
-                *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C) + m * p.ldc + ncol0 + c + j) = o;
+                *reinterpret_cast<uint4*>(reinterpret_cast<tb::half_t*>(p.C) + m * p.ldc + ncol0 + c + j) = o;
               }
             }
 #pragma unroll
@@ -353,13 +353,13 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
       }
       const uint32_t acc_addr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
       const bool row_ok = m < p.M && row < p.tile_rows && lane_live;
-      const __half* rv = nullptr;
+      const tb::half_t* rv = nullptr;
       if (p.rowvec && row_ok) rv = p.rowvec + (m / p.rows_per_group) * p.ldrv;
-      const __half* res = nullptr;
+      const tb::half_t* res = nullptr;
       const float* res32 = nullptr;
       if (p.residual && row_ok) {
         if (p.res_f32) res32 = reinterpret_cast<const float*>(p.residual) + m * p.ldr;
-        else res = reinterpret_cast<const __half*>(p.residual) + m * p.ldr;
+        else res = reinterpret_cast<const tb::half_t*>(p.residual) + m * p.ldr;
       }
       const int ncol0 = n_tile * BN;
       // The chunk loop is deliberately ROLLED (one copy of the ~600-instruction chunk body): fully unrolled and
@@ -440,11 +440,11 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
               for (int k = 0; k < 8; ++k) v[k] *= p.alpha;
             }
             {
-              const __half2* hb = reinterpret_cast<const __half2*>(&qb[j >> 3]);
-              const __half2* hv = reinterpret_cast<const __half2*>(&qv[j >> 3]);
+              const tb::half2_t* hb = reinterpret_cast<const tb::half2_t*>(&qb[j >> 3]);
+              const tb::half2_t* hv = reinterpret_cast<const tb::half2_t*>(&qv[j >> 3]);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const float2 fb = __half22float2(hb[k]), fv = __half22float2(hv[k]);
+                const float2 fb = tb::h22f2(hb[k]), fv = tb::h22f2(hv[k]);
                 v[2 * k] += fb.x + fv.x;
                 v[2 * k + 1] += fb.y + fv.y;
               }
@@ -454,11 +454,11 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
               for (int k = 0; k < 8; ++k) v[k] = apply_act(v[k], p.act);
             }
             if (p.residual) {
-              const __half2* h = reinterpret_cast<const __half2*>(&rq[j >> 3]);
+              const tb::half2_t* h = reinterpret_cast<const tb::half2_t*>(&rq[j >> 3]);
               const float4 a0 = q32[2 * (j >> 3)], a1 = q32[2 * (j >> 3) + 1];
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const float2 f = __half22float2(h[k]);
+                const float2 f = tb::h22f2(h[k]);
                 v[2 * k] += f.x;
                 v[2 * k + 1] += f.y;
               }
@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
                 o.y = pack_half2(v[2], v[3]);
                 o.z = pack_half2(v[4], v[5]);
                 o.w = pack_half2(v[6], v[7]);
-                *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C) + m * p.ldc + n) = o;
+                *reinterpret_cast<uint4*>(reinterpret_cast<tb::half_t*>(p.C) + m * p.ldc + n) = o;
               } else {
                 float* cp = reinterpret_cast<float*>(p.C) + m * p.ldc + n;
                 float4 o0 = make_float4(v[0], v[1], v[2], v[3]);
@@ -675,8 +675,8 @@ static int fill_epilogue(GemmParams& p, void* C, long long ldc, const tb_epilogu
   p.act = TB_ACT_NONE;
   p.out_kind = TB_OUT_F16;
   if (ep) {
-    p.bias = reinterpret_cast<const __half*>(ep->bias);
-    p.rowvec = reinterpret_cast<const __half*>(ep->rowvec);
+    p.bias = reinterpret_cast<const tb::half_t*>(ep->bias);
+    p.rowvec = reinterpret_cast<const tb::half_t*>(ep->rowvec);
     p.rows_per_group = ep->rows_per_group > 0 ? ep->rows_per_group : 1;
     p.ldrv = ep->ld_rowvec > 0 ? ep->ld_rowvec : 0;
     p.residual = ep->residual;

@@ -50,7 +50,12 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
     es[i] = 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+#ifdef TB_BF16
+  const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+#else
+  const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+#endif
+  CUresult r = enc(out, dt, (cuuint32_t)rank, const_cast<void*>(base),
                    gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -138,6 +143,14 @@ extern "C" int tb_set_workspace(void* stream, void* ptr, size_t bytes) {
 
 
 extern "C" int tb_version(void) { return TB_ABI_VERSION; }
+
+extern "C" int tb_storage_dtype(void) {
+#ifdef TB_BF16
+  return TB_STORAGE_BF16;
+#else
+  return TB_STORAGE_F16;
+#endif
+}
 
 extern "C" const char* tb_last_error(void) { return tb::g_err; }
 

@@ -10,10 +10,10 @@
 namespace tb {
 
 __device__ __forceinline__ void unpack8(const uint4& q, float* f) {
-  const __half2* h = reinterpret_cast<const __half2*>(&q);
+  const tb::half2_t* h = reinterpret_cast<const tb::half2_t*>(&q);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float2 t = __half22float2(h[i]);
+    const float2 t = tb::h22f2(h[i]);
     f[2 * i] = t.x;
     f[2 * i + 1] = t.y;
   }
@@ -100,8 +100,8 @@ __device__ __forceinline__ void gn_group_consts(GnGroupConst& k, const GnGeom& g
 // s1 += dz*gamma, s2 += dz*(z - beta) and no mean / rstd registers are needed in the loops.
 template <int MODE, int U, int MINB>
 __global__ void __launch_bounds__(320, MINB)
-gn_stats_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, const __half* __restrict__ gamma,
-                const __half* __restrict__ beta, const float* __restrict__ fstats, float* __restrict__ out,
+gn_stats_kernel(const tb::half_t* __restrict__ x, const tb::half_t* __restrict__ dy, const tb::half_t* __restrict__ gamma,
+                const tb::half_t* __restrict__ beta, const float* __restrict__ fstats, float* __restrict__ out,
                 GnGeom g, float eps, int silu) {
   extern __shared__ float sg[];  // [G][2]
   const int b = blockIdx.y;
@@ -186,9 +186,9 @@ gn_stats_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, con
 // MODE 0: y = act(x*A + Bz);  MODE 1: dx = rstd*(dz*gamma - S1/n - xhat*S2/n) = dz*A - x*P + Q (+ add)
 template <int MODE, int U, int MINB>
 __global__ void __launch_bounds__(320, MINB)
-gn_apply_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, const __half* __restrict__ gamma,
-                const __half* __restrict__ beta, const float* __restrict__ fstats,
-                const float* __restrict__ bstats, const __half* __restrict__ add, __half* __restrict__ out,
+gn_apply_kernel(const tb::half_t* __restrict__ x, const tb::half_t* __restrict__ dy, const tb::half_t* __restrict__ gamma,
+                const tb::half_t* __restrict__ beta, const float* __restrict__ fstats,
+                const float* __restrict__ bstats, const tb::half_t* __restrict__ add, tb::half_t* __restrict__ out,
                 GnGeom g, float eps, int silu) {
   const int b = blockIdx.y;
   const int v = threadIdx.x % g.nvec, pl = threadIdx.x / g.nvec;
@@ -276,9 +276,9 @@ struct GnOwnGeom {
 };
 template <int MODE>
 __global__ void __launch_bounds__(512, 1)
-gn_group_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, const __half* __restrict__ gamma,
-                const __half* __restrict__ beta, float* __restrict__ fstats, const __half* __restrict__ add,
-                __half* __restrict__ out, GnOwnGeom g, float eps, int silu) {
+gn_group_kernel(const tb::half_t* __restrict__ x, const tb::half_t* __restrict__ dy, const tb::half_t* __restrict__ gamma,
+                const tb::half_t* __restrict__ beta, float* __restrict__ fstats, const tb::half_t* __restrict__ add,
+                tb::half_t* __restrict__ out, GnOwnGeom g, float eps, int silu) {
   extern __shared__ uint4 gsm[];
   const int nthr = g.nv * g.ty;
   float* part = reinterpret_cast<float*>(gsm);                   // [nthr][2 groups][2]
@@ -510,7 +510,7 @@ static int gn_geom(GnGeom& g, int B, int HW, int C, int G) {
 template <typename T>
 __device__ __forceinline__ void load8(const T* p, float* f);
 template <>
-__device__ __forceinline__ void load8<__half>(const __half* p, float* f) {
+__device__ __forceinline__ void load8<tb::half_t>(const tb::half_t* p, float* f) {
   unpack8(*reinterpret_cast<const uint4*>(p), f);
 }
 template <>
@@ -523,7 +523,7 @@ __device__ __forceinline__ void load8<float>(const float* p, float* f) {
 template <typename T>
 __device__ __forceinline__ void store8(T* p, const float* f);
 template <>
-__device__ __forceinline__ void store8<__half>(__half* p, const float* f) {
+__device__ __forceinline__ void store8<tb::half_t>(tb::half_t* p, const float* f) {
   *reinterpret_cast<uint4*>(p) = pack8(f);
 }
 template <>
@@ -667,7 +667,7 @@ __global__ void ln_bwd_kernel(const DYT* __restrict__ dy, long long lddy, const 
 //           tb_layernorm_fwd + tb_lora_down.  The down-projection reads the fp16-rounded y, as the GEMM will.
 template <int MV>
 __global__ void ln_lora_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, __half* __restrict__ y, long long ldy,
+                                   const float* __restrict__ beta, tb::half_t* __restrict__ y, long long ldy,
                                    float* __restrict__ stats, const float* __restrict__ A, int R, int RPAD, int M,
                                    int C, float eps, int a_in_smem) {
   // the R x C down-projection matrix is read by every row: staged once per CTA in shared memory when it fits (36 KB
@@ -718,8 +718,8 @@ __global__ void ln_lora_fwd_kernel(const float* __restrict__ x, long long ldx, c
       load8<float>(gamma + vi * 8, gf);
       load8<float>(beta + vi * 8, bf);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[j][i] = __half2float(__float2half((v[j][i] - mean) * rstd * gf[i] + bf[i]));
-      if (row_ok) store8<__half>(y + row * ldy + vi * 8, v[j]);
+      for (int i = 0; i < 8; ++i) v[j][i] = tb::h2f(tb::f2h((v[j][i] - mean) * rstd * gf[i] + bf[i]));
+      if (row_ok) store8<tb::half_t>(y + row * ldy + vi * 8, v[j]);
     }
   }
   if (lane == 0 && stats && row_ok) {
@@ -754,7 +754,7 @@ __global__ void ln_lora_fwd_kernel(const float* __restrict__ x, long long ldx, c
 #pragma unroll
       for (int r = 0; r < 16; ++r)
         if (r == lane && j0 + r < R) o = acc[r];
-      y[row * ldy + C + j0 + lane] = __float2half(o);
+      y[row * ldy + C + j0 + lane] = tb::f2h(o);
     }
   }
 }
@@ -766,7 +766,7 @@ __global__ void ln_lora_fwd_kernel(const float* __restrict__ x, long long ldx, c
 template <int MV, typename DYT>
 __global__ void ln_bwd_clip_kernel(const DYT* __restrict__ dy, long long lddy, const float* __restrict__ x,
                                    long long ldx, const float* __restrict__ gamma, const float* __restrict__ stats,
-                                   const float* __restrict__ add, float* __restrict__ dx, __half* __restrict__ dx16,
+                                   const float* __restrict__ add, float* __restrict__ dx, tb::half_t* __restrict__ dx16,
                                    const float* __restrict__ A, int R, int M, int C, int a_in_smem) {
   extern __shared__ uint4 ln_smem[];
   if (A && a_in_smem) {  // see ln_lora_fwd_kernel
@@ -843,7 +843,7 @@ __global__ void ln_bwd_clip_kernel(const DYT* __restrict__ dy, long long lddy, c
       }
       if (row_ok) {
         store8<float>(dx + row * (long long)C + vi * 8, o);
-        if (dx16) store8<__half>(dx16 + row * (long long)C + vi * 8, o);
+        if (dx16) store8<tb::half_t>(dx16 + row * (long long)C + vi * 8, o);
       }
     }
   }
@@ -875,7 +875,7 @@ extern "C" int tb_groupnorm_fwd_f16(const void* x, const void* gamma, const void
         configured = true;
       }
       gn_group_kernel<0><<<dim3(G / o.gpc, B), o.nv * o.ty, smem, st>>>(
-          (const __half*)x, nullptr, (const __half*)gamma, (const __half*)beta, stats, nullptr, (__half*)y, o, eps, silu);
+          (const tb::half_t*)x, nullptr, (const tb::half_t*)gamma, (const tb::half_t*)beta, stats, nullptr, (tb::half_t*)y, o, eps, silu);
       return check_launch("gn_group_kernel<0>");
     }
   }
@@ -888,10 +888,10 @@ extern "C" int tb_groupnorm_fwd_f16(const void* x, const void* gamma, const void
 #define TB_GN_FWD(U, MINB)                                                                                       \
   do {                                                                                                            \
     gn_stats_kernel<0, U, MINB><<<grid, threads, 2 * G * sizeof(float), st>>>(                                    \
-        (const __half*)x, nullptr, nullptr, nullptr, nullptr, stats, g, eps, silu);                               \
+        (const tb::half_t*)x, nullptr, nullptr, nullptr, nullptr, stats, g, eps, silu);                               \
     if ((rc = check_launch("gn_stats_kernel<0>"))) return rc;                                                     \
-    gn_apply_kernel<0, U, MINB><<<grid, threads, 0, st>>>((const __half*)x, nullptr, (const __half*)gamma,        \
-                                                         (const __half*)beta, stats, nullptr, nullptr, (__half*)y, \
+    gn_apply_kernel<0, U, MINB><<<grid, threads, 0, st>>>((const tb::half_t*)x, nullptr, (const tb::half_t*)gamma,        \
+                                                         (const tb::half_t*)beta, stats, nullptr, nullptr, (tb::half_t*)y, \
                                                          g, eps, silu);                                           \
   } while (0)
   static const int variant = getenv("TB_GN_FWD_VARIANT") ? atoi(getenv("TB_GN_FWD_VARIANT")) : 43;  // tuning knob
@@ -932,8 +932,8 @@ extern "C" int tb_groupnorm_bwd_f16(const void* dy, const void* x, const void* g
         configured = true;
       }
       gn_group_kernel<1><<<dim3(G / o.gpc, B), o.nv * o.ty, smem, st>>>(
-          (const __half*)x, (const __half*)dy, (const __half*)gamma, (const __half*)beta, const_cast<float*>(stats),
-          (const __half*)add, (__half*)dx, o, eps, silu);
+          (const tb::half_t*)x, (const tb::half_t*)dy, (const tb::half_t*)gamma, (const tb::half_t*)beta, const_cast<float*>(stats),
+          (const tb::half_t*)add, (tb::half_t*)dx, o, eps, silu);
       return check_launch("gn_group_kernel<1>");
     }
   }
@@ -946,12 +946,12 @@ extern "C" int tb_groupnorm_bwd_f16(const void* dy, const void* x, const void* g
 #define TB_GN_BWD(U, MINB)                                                                                       \
   do {                                                                                                            \
     gn_stats_kernel<1, U, MINB><<<grid, threads, 2 * G * sizeof(float), st>>>(                                    \
-        (const __half*)x, (const __half*)dy, (const __half*)gamma, (const __half*)beta, stats, dstats, g, eps,    \
+        (const tb::half_t*)x, (const tb::half_t*)dy, (const tb::half_t*)gamma, (const tb::half_t*)beta, stats, dstats, g, eps,    \
         silu);                                                                                                    \
     if ((rc = check_launch("gn_stats_kernel<1>"))) return rc;                                                     \
-    gn_apply_kernel<1, U, MINB><<<grid, threads, 0, st>>>((const __half*)x, (const __half*)dy,                    \
-                                                         (const __half*)gamma, (const __half*)beta, stats, dstats, \
-                                                         (const __half*)add, (__half*)dx, g, eps, silu);          \
+    gn_apply_kernel<1, U, MINB><<<grid, threads, 0, st>>>((const tb::half_t*)x, (const tb::half_t*)dy,                    \
+                                                         (const tb::half_t*)gamma, (const tb::half_t*)beta, stats, dstats, \
+                                                         (const tb::half_t*)add, (tb::half_t*)dx, g, eps, silu);          \
   } while (0)
   static const int variant = getenv("TB_GN_BWD_VARIANT") ? atoi(getenv("TB_GN_BWD_VARIANT")) : 22;  // tuning knob
   switch (variant) {
@@ -982,11 +982,11 @@ extern "C" int tb_layernorm_fwd(const void* x, int x_f32, int64_t ldx, const voi
 #define TB_LN_FWD(LPR, MV)                                                                                          \
   do {                                                                                                         \
     if (!x_f32 && !w_f32 && !y_f32)                                                                            \
-      ln_fwd_kernel<LPR, MV, __half, __half, __half><<<grid, wpb * 32, 0, st>>>(                                    \
-          (const __half*)x, ldx, (const __half*)gamma, (const __half*)beta, (__half*)y, ldy, stats, M, C, eps); \
+      ln_fwd_kernel<LPR, MV, tb::half_t, tb::half_t, tb::half_t><<<grid, wpb * 32, 0, st>>>(                                    \
+          (const tb::half_t*)x, ldx, (const tb::half_t*)gamma, (const tb::half_t*)beta, (tb::half_t*)y, ldy, stats, M, C, eps); \
     else if (x_f32 && w_f32 && !y_f32)                                                                         \
-      ln_fwd_kernel<LPR, MV, float, float, __half><<<grid, wpb * 32, 0, st>>>(                                      \
-          (const float*)x, ldx, (const float*)gamma, (const float*)beta, (__half*)y, ldy, stats, M, C, eps);   \
+      ln_fwd_kernel<LPR, MV, float, float, tb::half_t><<<grid, wpb * 32, 0, st>>>(                                      \
+          (const float*)x, ldx, (const float*)gamma, (const float*)beta, (tb::half_t*)y, ldy, stats, M, C, eps);   \
     else if (x_f32 && w_f32 && y_f32)                                                                          \
       ln_fwd_kernel<LPR, MV, float, float, float><<<grid, wpb * 32, 0, st>>>(                                       \
           (const float*)x, ldx, (const float*)gamma, (const float*)beta, (float*)y, ldy, stats, M, C, eps);    \
@@ -1022,12 +1022,12 @@ extern "C" int tb_layernorm_bwd(const void* dy, int dy_f32, int64_t lddy, const 
 #define TB_LN_BWD(LPR, MV)                                                                                          \
   do {                                                                                                         \
     if (!x_f32)                                                                                                \
-      ln_bwd_kernel<LPR, MV, __half, __half, __half, __half><<<grid, wpb * 32, 0, st>>>(                            \
-          (const __half*)dy, lddy, (const __half*)x, ldx, (const __half*)gamma, stats, (const __half*)add,     \
-          (__half*)dx, M, C);                                                                                  \
+      ln_bwd_kernel<LPR, MV, tb::half_t, tb::half_t, tb::half_t, tb::half_t><<<grid, wpb * 32, 0, st>>>(                            \
+          (const tb::half_t*)dy, lddy, (const tb::half_t*)x, ldx, (const tb::half_t*)gamma, stats, (const tb::half_t*)add,     \
+          (tb::half_t*)dx, M, C);                                                                                  \
     else if (!dy_f32)                                                                                          \
-      ln_bwd_kernel<LPR, MV, __half, float, float, float><<<grid, wpb * 32, 0, st>>>(                               \
-          (const __half*)dy, lddy, (const float*)x, ldx, (const float*)gamma, stats, (const float*)add,        \
+      ln_bwd_kernel<LPR, MV, tb::half_t, float, float, float><<<grid, wpb * 32, 0, st>>>(                               \
+          (const tb::half_t*)dy, lddy, (const float*)x, ldx, (const float*)gamma, stats, (const float*)add,        \
           (float*)dx, M, C);                                                                                   \
     else                                                                                                       \
       ln_bwd_kernel<LPR, MV, float, float, float, float><<<grid, wpb * 32, 0, st>>>(                                \
@@ -1061,10 +1061,10 @@ extern "C" int tb_layernorm_lora_fwd(const float* x, int64_t ldx, const float* g
   const int a_in_smem = a_bytes <= 48 * 1024 && ((uintptr_t)lora_A % 16 == 0);  // (static limit: no attribute call)
   const int smem = a_in_smem ? a_bytes : 0;
   if (C <= 768)
-    ln_lora_fwd_kernel<3><<<grid, wpb * 32, smem, st>>>(x, ldx, gamma, beta, (__half*)y_ext, ldy, stats, lora_A, R,
+    ln_lora_fwd_kernel<3><<<grid, wpb * 32, smem, st>>>(x, ldx, gamma, beta, (tb::half_t*)y_ext, ldy, stats, lora_A, R,
                                                         RPAD, M, C, eps, a_in_smem);
   else
-    ln_lora_fwd_kernel<LN_MAXV><<<grid, wpb * 32, smem, st>>>(x, ldx, gamma, beta, (__half*)y_ext, ldy, stats, lora_A,
+    ln_lora_fwd_kernel<LN_MAXV><<<grid, wpb * 32, smem, st>>>(x, ldx, gamma, beta, (tb::half_t*)y_ext, ldy, stats, lora_A,
                                                               R, RPAD, M, C, eps, a_in_smem);
   return check_launch("ln_lora_fwd_kernel");
 }
@@ -1090,10 +1090,10 @@ extern "C" int tb_layernorm_bwd_clip(const void* dy, int dy_f32, int64_t lddy, c
   do {                                                                                                               \
     if (dy_f32)                                                                                                      \
       ln_bwd_clip_kernel<MV, float><<<grid, wpb * 32, 0, st>>>((const float*)dy, lddy, x, ldx, gamma, stats, add, dx, \
-                                                               (__half*)dx_f16, nullptr, 0, M, C, 0);                \
+                                                               (tb::half_t*)dx_f16, nullptr, 0, M, C, 0);                \
     else                                                                                                             \
-      ln_bwd_clip_kernel<MV, __half><<<grid, wpb * 32, smem, st>>>((const __half*)dy, lddy, x, ldx, gamma, stats,    \
-                                                                   add, dx, (__half*)dx_f16, lora_A, R, M, C,        \
+      ln_bwd_clip_kernel<MV, tb::half_t><<<grid, wpb * 32, smem, st>>>((const tb::half_t*)dy, lddy, x, ldx, gamma, stats,    \
+                                                                   add, dx, (tb::half_t*)dx_f16, lora_A, R, M, C,        \
                                                                    a_in_smem);                                       \
   } while (0)
   if (C <= 768) TB_LN_BWD_CLIP(3);

@@ -9,6 +9,7 @@
 // Device state vector (fp32[16]):
 //   [0] loss_scale  [1] growth_tracker  [2] found_inf  [3] sum g^2 (LoRA, scaled)  [4] step t
 //   [5] frozen-row decay c  [6] last clip coefficient  [7] last grad norm (unscaled)  [8] skipped steps
+//   [10] fixed-scale flag (0 = GradScaler dynamics, the fp16 policy; 1 = accelerate creates no scaler, bf16)
 //   [9] learning-rate multiplier of the step just taken (the --lr_scheduler value, train_textboost.py:911-916)
 #include "host_util.h"
 #include "sm100.cuh"
@@ -133,8 +134,9 @@ __global__ void optim_finish_kernel(float* __restrict__ p, AdamCfg c, float* __r
     const float inv_scale = c.inv_world / state[0];
     state[7] = sqrtf(state[3]) * inv_scale;
     state[6] = fminf(1.f, c.max_norm / (state[7] + 1e-6f));
+    const bool dynamic_scale = state[10] == 0.f;  // [10] != 0: no GradScaler (bf16 policy), the scale stays put
     if (skipped) {
-      state[0] *= c.backoff_factor;  // GradScaler: halve and skip
+      if (dynamic_scale) state[0] *= c.backoff_factor;  // GradScaler: halve and skip
       state[1] = 0.f;
       state[8] += 1.f;
     } else {
@@ -143,7 +145,7 @@ __global__ void optim_finish_kernel(float* __restrict__ p, AdamCfg c, float* __r
       state[4] += 1.f;
       state[1] += 1.f;
       if (state[1] >= (float)c.growth_interval) {
-        state[0] *= c.growth_factor;
+        if (dynamic_scale) state[0] *= c.growth_factor;
         state[1] = 0.f;
       }
     }

@@ -21,13 +21,13 @@ static inline unsigned sampler_grid_for(long long n, int threads) {
 //   m0  = (x - s_i e) / a_i        (epsilon)   |   a_i x - s_i e   (v-prediction)       data prediction at sigma_i
 //   x'  = c_x x + c_d0 m0 + c_d1 (m0 - m1)                       DPM-Solver++ first (c_d1 = 0) / second order (midpoint)
 // and writes x' (fp32), m0 (fp32, next step's m1) and x' as fp16 into both halves of the next UNet input.
-__global__ void dpm_cfg_step_kernel(float* __restrict__ x, const __half* __restrict__ eps,
+__global__ void dpm_cfg_step_kernel(float* __restrict__ x, const tb::half_t* __restrict__ eps,
                                     const float* __restrict__ m_prev, float* __restrict__ m_out,
-                                    __half* __restrict__ unet_in, long long n, float g, float a_i, float s_i,
+                                    tb::half_t* __restrict__ unet_in, long long n, float g, float a_i, float s_i,
                                     int v_pred, float c_x, float c_d0, float c_d1) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
-    const float eu = __half2float(eps[i]), ec = __half2float(eps[n + i]);
+    const float eu = tb::h2f(eps[i]), ec = tb::h2f(eps[n + i]);
     const float e = eu + g * (ec - eu);
     const float xi = x[i];
     const float m0 = v_pred ? a_i * xi - s_i * e : (xi - s_i * e) / a_i;
@@ -36,7 +36,7 @@ __global__ void dpm_cfg_step_kernel(float* __restrict__ x, const __half* __restr
     x[i] = xn;
     m_out[i] = m0;
     if (unet_in) {
-      const __half h = __float2half_rn(xn);
+      const tb::half_t h = tb::f2h(xn);
       unet_in[i] = h;
       unet_in[n + i] = h;
     }
@@ -45,7 +45,7 @@ __global__ void dpm_cfg_step_kernel(float* __restrict__ x, const __half* __restr
 
 // z[b, o, p] = bias[o] + sum_i w[o, i] * latents[b, i, p] * inv_scale   (post_quant_conv, 1x1, L <= 8), fp16 NCHW out
 __global__ void vae_decode_in_kernel(const float* __restrict__ latents, const float* __restrict__ w,
-                                     const float* __restrict__ bias, __half* __restrict__ z, int L, int HW,
+                                     const float* __restrict__ bias, tb::half_t* __restrict__ z, int L, int HW,
                                      long long total, float inv_scale) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -55,19 +55,19 @@ __global__ void vae_decode_in_kernel(const float* __restrict__ latents, const fl
     const long long b = t / L;
     float acc = bias[o];
     for (int c = 0; c < L; ++c) acc += w[o * L + c] * (latents[(b * L + c) * HW + p] * inv_scale);
-    z[i] = __float2half_rn(acc);
+    z[i] = tb::f2h(acc);
   }
 }
 
 // VaeImageProcessor.postprocess: (x / 2 + 0.5).clamp(0, 1) * 255, round half to even -> uint8 [npix, channels]
-__global__ void image_u8_kernel(const __half* __restrict__ x, long long ld, unsigned char* __restrict__ out,
+__global__ void image_u8_kernel(const tb::half_t* __restrict__ x, long long ld, unsigned char* __restrict__ out,
                                 long long npix, int channels) {
   const long long total = npix * channels;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long p = i / channels;
     const int c = (int)(i - p * channels);
-    const float v = fminf(fmaxf(__half2float(x[p * ld + c]) * 0.5f + 0.5f, 0.f), 1.f);
+    const float v = fminf(fmaxf(tb::h2f(x[p * ld + c]) * 0.5f + 0.5f, 0.f), 1.f);
     out[i] = (unsigned char)rintf(v * 255.f);
   }
 }
@@ -88,8 +88,8 @@ extern "C" int tb_dpm_cfg_step(float* x, const void* eps_f16, const float* m_pre
   TB_REQUIRE(x && eps_f16 && m_out && n > 0, TB_E_ARG, "tb_dpm_cfg_step: bad args");
   TB_REQUIRE(c_d1 == 0.f || m_prev, TB_E_ARG, "tb_dpm_cfg_step: second-order update needs m_prev");
   TB_REQUIRE(alpha_i > 0.f, TB_E_ARG, "tb_dpm_cfg_step: alpha_i must be positive");
-  dpm_cfg_step_kernel<<<sampler_grid_for(n, 256), 256, 0, st>>>(x, (const __half*)eps_f16, m_prev, m_out,
-                                                                (__half*)unet_in_f16, (long long)n,
+  dpm_cfg_step_kernel<<<sampler_grid_for(n, 256), 256, 0, st>>>(x, (const tb::half_t*)eps_f16, m_prev, m_out,
+                                                                (tb::half_t*)unet_in_f16, (long long)n,
                                                                 guidance_scale, alpha_i, sigma_i, v_prediction, c_x,
                                                                 c_d0, c_d1);
   return check_launch("dpm_cfg_step_kernel");
@@ -101,7 +101,7 @@ extern "C" int tb_vae_decode_in(const float* latents, const float* w, const floa
   TB_REQUIRE(latents && w && bias && z_f16 && B > 0 && HW > 0 && latent_channels > 0 && latent_channels <= 8,
              TB_E_ARG, "tb_vae_decode_in: bad args");
   const long long total = (long long)B * latent_channels * HW;
-  vae_decode_in_kernel<<<sampler_grid_for(total, 256), 256, 0, st>>>(latents, w, bias, (__half*)z_f16,
+  vae_decode_in_kernel<<<sampler_grid_for(total, 256), 256, 0, st>>>(latents, w, bias, (tb::half_t*)z_f16,
                                                                      latent_channels, HW, total,
                                                                      inv_scaling_factor);
   return check_launch("vae_decode_in_kernel");
@@ -110,7 +110,7 @@ extern "C" int tb_vae_decode_in(const float* latents, const float* w, const floa
 extern "C" int tb_image_u8(const void* x_f16, int64_t ld, void* out_u8, int64_t npix, int channels, void* stream) {
   TB_ENTER();
   TB_REQUIRE(x_f16 && out_u8 && npix > 0 && channels > 0 && ld >= channels, TB_E_ARG, "tb_image_u8: bad args");
-  image_u8_kernel<<<sampler_grid_for(npix * channels, 256), 256, 0, st>>>((const __half*)x_f16, (long long)ld,
+  image_u8_kernel<<<sampler_grid_for(npix * channels, 256), 256, 0, st>>>((const tb::half_t*)x_f16, (long long)ld,
                                                                          (unsigned char*)out_u8, (long long)npix,
                                                                          channels);
   return check_launch("image_u8_kernel");

@@ -7,7 +7,38 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// The 16-bit storage / tensor-core operand type of the build.  The library is compiled twice from the same sources:
+// libtextboost_b200.so (fp16, --mixed_precision fp16) and, with -DTB_BF16, libtextboost_b200_bf16.so (bf16,
+// --mixed_precision bf16, train_textboost.py:928-933 weight_dtype).  Everything wider (accumulators, statistics,
+// softmax, residual stream where it is fp32, master weights, optimiser) is fp32 in both.
+#ifdef TB_BF16
+#include <cuda_bf16.h>
+#define TB_H16X2 "bf16x2"
+#define TB_UMMA_AB_FMT 1u  // cute::UMMA::F16F32Format::BF16
+#define TB_ONE_X2 0x3F803F80u  // {1.0, 1.0} as a packed pair
+#else
+#define TB_H16X2 "f16x2"
+#define TB_UMMA_AB_FMT 0u  // F16
+#define TB_ONE_X2 0x3C003C00u
+#endif
+
 namespace tb {
+
+#ifdef TB_BF16
+using half_t = __nv_bfloat16;
+using half2_t = __nv_bfloat162;
+__device__ __forceinline__ float h2f(half_t x) { return __bfloat162float(x); }
+__device__ __forceinline__ half_t f2h(float x) { return __float2bfloat16_rn(x); }
+__device__ __forceinline__ float2 h22f2(half2_t x) { return __bfloat1622float2(x); }
+__device__ __forceinline__ half2_t ff2h2(float a, float b) { return __floats2bfloat162_rn(a, b); }
+#else
+using half_t = __half;
+using half2_t = __half2;
+__device__ __forceinline__ float h2f(half_t x) { return __half2float(x); }
+__device__ __forceinline__ half_t f2h(float x) { return __float2half_rn(x); }
+__device__ __forceinline__ float2 h22f2(half2_t x) { return __half22float2(x); }
+__device__ __forceinline__ half2_t ff2h2(float a, float b) { return __floats2half2_rn(a, b); }
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -270,16 +301,16 @@ __device__ __forceinline__ uint64_t umma_desc_pack(uint32_t lo, uint32_t hi) {
   return d;
 }
 
-// Instruction descriptor for kind::f16, fp16 A/B, fp32 D (cute::UMMA::InstrDescriptor):
-// [4,6) D fmt (1=f32), [7,10) A fmt (0=f16), [10,13) B fmt, bit15 A major (1=MN), bit16 B major,
+// Instruction descriptor for kind::f16, fp16 (or bf16) A/B, fp32 D (cute::UMMA::InstrDescriptor):
+// [4,6) D fmt (1=f32), [7,10) A fmt (0=f16, 1=bf16), [10,13) B fmt, bit15 A major (1=MN), bit16 B major,
 // [17,23) N>>3, [24,29) M>>4.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)a_mn_major << 15) |
+  return (1u << 4) | (TB_UMMA_AB_FMT << 7) | (TB_UMMA_AB_FMT << 10) | ((uint32_t)a_mn_major << 15) |
          ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
+  tb::half2_t h = tb::ff2h2(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
 

@@ -18,7 +18,7 @@ static inline unsigned vae_grid_for(long long n, int threads) {
 
 // col[(b,oy,ox), (ky*3+kx)*C + c] = x[b, 2*oy+ky-pad_lo, 2*ox+kx-pad_lo, c]  (zero outside the image).
 // pad_lo = 1: UNet Downsample2D (symmetric pad 1); pad_lo = 0: VAE Downsample2D = F.pad(x, (0,1,0,1)) + conv pad 0.
-__global__ void im2col3x3s2_pad_kernel(const __half* __restrict__ x, __half* __restrict__ col, int B, int H, int W,
+__global__ void im2col3x3s2_pad_kernel(const tb::half_t* __restrict__ x, tb::half_t* __restrict__ col, int B, int H, int W,
                                        int C, int pad_lo) {
   const int Ho = H / 2, Wo = W / 2, cv = C / 8;
   const long long total = (long long)B * Ho * Wo * 9 * cv;
@@ -43,10 +43,10 @@ __global__ void im2col3x3s2_pad_kernel(const __half* __restrict__ x, __half* __r
 // In-place softmax over each row of an fp16 matrix (fp32 arithmetic).  One CTA of 256 threads per row, the row held
 // in registers (cols <= 8192): one read and one write of the score matrix.
 constexpr int SM_MAXV = 4;
-__global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ x, long long ld, int cols) {
+__global__ void __launch_bounds__(256) softmax_rows_kernel(tb::half_t* __restrict__ x, long long ld, int cols) {
   __shared__ float red[8];
   __shared__ float bcast;
-  __half* row = x + (long long)blockIdx.x * ld;
+  tb::half_t* row = x + (long long)blockIdx.x * ld;
   const int nv = cols / 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float f[SM_MAXV][8];
@@ -56,10 +56,10 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ 
     const int v = threadIdx.x + j * 256;
     if (v < nv) {
       const uint4 q = *reinterpret_cast<const uint4*>(row + v * 8);
-      const __half2* h = reinterpret_cast<const __half2*>(&q);
+      const tb::half2_t* h = reinterpret_cast<const tb::half2_t*>(&q);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float2 t = __half22float2(h[i]);
+        const float2 t = tb::h22f2(h[i]);
         f[j][2 * i] = t.x;
         f[j][2 * i + 1] = t.y;
         m = fmaxf(m, fmaxf(t.x, t.y));
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ 
 
 // DiagonalGaussianDistribution.sample() * scaling_factor.  moments: fp16 channels-last rows [B*HW, ld], columns
 // [0,L) = mean, [L,2L) = logvar (clamped to [-30, 20]); eps / latents: fp32 NCHW [B, L, HW].
-__global__ void vae_sample_kernel(const __half* __restrict__ moments, long long ld, const float* __restrict__ eps,
+__global__ void vae_sample_kernel(const tb::half_t* __restrict__ moments, long long ld, const float* __restrict__ eps,
                                   float* __restrict__ latents, float* __restrict__ mean_out,
                                   float* __restrict__ std_out, int HW, int L, long long total, float scale) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -125,9 +125,9 @@ __global__ void vae_sample_kernel(const __half* __restrict__ moments, long long 
     const long long t = i / HW;
     const int c = (int)(t % L);
     const long long b = t / L;
-    const __half* row = moments + (b * HW + pix) * ld;
-    const float mean = __half2float(row[c]);
-    const float logvar = fminf(fmaxf(__half2float(row[L + c]), -30.f), 20.f);
+    const tb::half_t* row = moments + (b * HW + pix) * ld;
+    const float mean = tb::h2f(row[c]);
+    const float logvar = fminf(fmaxf(tb::h2f(row[L + c]), -30.f), 20.f);
     const float sd = expf(0.5f * logvar);
     if (latents) latents[i] = (mean + sd * eps[i]) * scale;
     if (mean_out) mean_out[i] = mean;
@@ -150,7 +150,7 @@ extern "C" int tb_im2col3x3s2_pad_f16(const void* x, void* col, int B, int H, in
   TB_REQUIRE(x && col && C % 8 == 0 && H % 2 == 0 && W % 2 == 0 && (pad_lo == 0 || pad_lo == 1), TB_E_ARG,
              "tb_im2col3x3s2_pad_f16: bad args");
   im2col3x3s2_pad_kernel<<<vae_grid_for((long long)B * (H / 2) * (W / 2) * 9 * (C / 8), 256), 256, 0, st>>>(
-      (const __half*)x, (__half*)col, B, H, W, C, pad_lo);
+      (const tb::half_t*)x, (tb::half_t*)col, B, H, W, C, pad_lo);
   return check_launch("im2col3x3s2_pad_kernel");
 }
 
@@ -159,7 +159,7 @@ extern "C" int tb_softmax_rows_f16(void* x, int64_t ld, int64_t rows, int cols, 
   TB_REQUIRE(x && rows > 0 && rows <= 0x7fffffff, TB_E_ARG, "tb_softmax_rows_f16: bad args");
   TB_REQUIRE(cols % 8 == 0 && cols > 0 && cols <= SM_MAXV * 256 * 8 && ld % 8 == 0, TB_E_SHAPE,
              "tb_softmax_rows_f16: cols=%d unsupported (multiple of 8, <= %d)", cols, SM_MAXV * 256 * 8);
-  softmax_rows_kernel<<<(unsigned)rows, 256, 0, st>>>((__half*)x, (long long)ld, cols);
+  softmax_rows_kernel<<<(unsigned)rows, 256, 0, st>>>((tb::half_t*)x, (long long)ld, cols);
   return check_launch("softmax_rows_kernel");
 }
 
@@ -170,7 +170,7 @@ extern "C" int tb_vae_sample(const void* moments_f16, int64_t ld, const float* e
              "tb_vae_sample: bad args");
   TB_REQUIRE((latents == nullptr) || eps, TB_E_ARG, "tb_vae_sample: latents requested without eps");
   const long long total = (long long)B * latent_channels * HW;
-  vae_sample_kernel<<<vae_grid_for(total, 256), 256, 0, st>>>((const __half*)moments_f16, (long long)ld, eps,
+  vae_sample_kernel<<<vae_grid_for(total, 256), 256, 0, st>>>((const tb::half_t*)moments_f16, (long long)ld, eps,
                                                               latents, mean, std, HW, latent_channels, total,
                                                               scaling_factor);
   return check_launch("vae_sample_kernel");

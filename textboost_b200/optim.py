@@ -23,7 +23,7 @@ from . import _cabi as C
 F32 = torch.float32
 
 # indices into the device state vector (csrc/optim.cu)
-LOSS_SCALE, GROWTH_TRACKER, FOUND_INF, SUM_SQ, STEP, FROZEN_DECAY, CLIP_COEF, GRAD_NORM, SKIPPED, LR_MULT = range(10)
+LOSS_SCALE, GROWTH_TRACKER, FOUND_INF, SUM_SQ, STEP, FROZEN_DECAY, CLIP_COEF, GRAD_NORM, SKIPPED, LR_MULT, FIXED_SCALE = range(11)
 
 # --lr_scheduler names of the reference CLI (train_textboost.py:224-231 -> diffusers.optimization.get_scheduler)
 LR_SCHEDULES = {"constant": 0, "constant_with_warmup": 1, "linear": 2, "cosine": 3, "cosine_with_restarts": 4,
@@ -79,7 +79,10 @@ class FusedAdamW:
         self.exp_avg = torch.zeros_like(st.params)
         self.exp_avg_sq = torch.zeros_like(st.params)
         self.state = torch.zeros(16, device=st.params.device, dtype=F32)
-        self.state[LOSS_SCALE] = 65536.0 if mixed_precision == "fp16" else 1.0  # GradScaler init_scale
+        # accelerate creates a GradScaler for fp16 only (init_scale 65536, growth 2x / 2000 steps, backoff 0.5); under
+        # bf16 the loss is not scaled and the scale never moves
+        self.state[LOSS_SCALE] = 65536.0 if mixed_precision == "fp16" else 1.0
+        self.state[FIXED_SCALE] = 0.0 if mixed_precision == "fp16" else 1.0
         self.state[FROZEN_DECAY] = 1.0
         engine.decay = self.state[FROZEN_DECAY:FROZEN_DECAY + 1]
         if mean_norm is None:

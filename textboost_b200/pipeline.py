@@ -32,7 +32,7 @@ import torch
 
 from . import ops
 
-F16 = torch.float16
+from .precision import POLICY
 F32 = torch.float32
 
 
@@ -160,7 +160,7 @@ class StableDiffusionPipeline:
         if device is not None:
             self.vae.to(device)
             self.text_encoder.to(device)
-            self.unet.to(device, dtype=F16)
+            self.unet.to(device, dtype=POLICY.act)
         return self
 
     def set_progress_bar_config(self, **_kw):
@@ -210,7 +210,7 @@ class StableDiffusionPipeline:
         with torch.no_grad():
             cond = self.text_encoder(self._tokenize(prompts).to(device))[0]
             uncond = self.text_encoder(self._tokenize(negatives).to(device))[0]
-        rep = lambda e: e.to(F16).repeat_interleave(num_images_per_prompt, dim=0).contiguous()  # noqa: E731
+        rep = lambda e: e.to(POLICY.act).repeat_interleave(num_images_per_prompt, dim=0).contiguous()  # noqa: E731
         return rep(cond), rep(uncond)
 
     def prepare_latents(self, n, height, width, device, generator=None, latents=None):
@@ -236,7 +236,7 @@ class StableDiffusionPipeline:
         cfg = guidance_scale > 1.0
         ehs = torch.cat([uncond, cond]) if cfg else cond
         nb = 2 * N if cfg else N
-        unet_in = torch.empty((2 * N,) + tuple(x.shape[1:]), device=x.device, dtype=F16)
+        unet_in = torch.empty((2 * N,) + tuple(x.shape[1:]), device=x.device, dtype=POLICY.act)
         unet_in[:N] = x
         unet_in[N:] = x
         tt = torch.empty(nb, device=x.device, dtype=torch.int64)

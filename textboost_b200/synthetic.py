@@ -9,6 +9,7 @@ from typing import Dict, Tuple
 
 import torch
 
+from .precision import POLICY
 from .clip import ClipConfig, ClipEngine
 from .trainer import TextBoostTrainer
 from .unet import UNetConfig, UNetEngine
@@ -122,7 +123,7 @@ def clip_shapes(cfg: ClipConfig, vocab: int) -> Dict[str, Tuple[int, ...]]:
 
 
 # ---------------------------------------------------------------------------------- random init
-def random_unet_sd(cfg: UNetConfig, device, seed=0, dtype=torch.float16):
+def random_unet_sd(cfg: UNetConfig, device, seed=0, dtype=None):
     """N(0, 1/fan_in) conv/linear weights (residual-branch outputs damped), norm affine 1 + N(0,.1):
     activations stay O(1) through the ~60 layers (a plain N(0, .02) init collapses the GroupNorm inputs)."""
     g = torch.Generator(device=device).manual_seed(seed)
@@ -137,7 +138,7 @@ def random_unet_sd(cfg: UNetConfig, device, seed=0, dtype=torch.float16):
             fan_in = math.prod(shp[1:])
             gain = 0.5 if any(x in k for x in ("conv2.", "to_out.0", "ff.net.2", "proj_out")) else 1.0
             t = torch.randn(shp, generator=g, device=device) * (gain / math.sqrt(fan_in))
-        sd[k] = t.to(dtype)
+        sd[k] = t.to(dtype or POLICY.act)
     return sd
 
 

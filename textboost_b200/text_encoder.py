@@ -33,6 +33,7 @@ from typing import Dict, Iterator, Optional, Tuple
 
 import torch
 
+from .precision import POLICY
 from .clip import EOS_ID, LORA_TARGETS, ClipConfig, ClipEngine, canonical_targets
 from .lora import LoraConfig
 
@@ -433,8 +434,8 @@ class TextBoostModel:
         # pooled output (unused by the reference, utils.py:24 takes [0]): hidden state at the first EOS
         eos = (ids == EOS_ID).int().argmax(dim=-1)
         pooled = h.detach()[torch.arange(ids.shape[0], device=h.device), eos]
-        if self._dtype == torch.float16 and not trainable:
-            h = h.half()
+        if self._dtype in (torch.float16, torch.bfloat16) and not trainable:
+            h = h.to(POLICY.act)
         out = ModelOutput(h, pooled)
         return out if (return_dict if return_dict is not None else True) else tuple(out)
 

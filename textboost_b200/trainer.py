@@ -26,7 +26,7 @@ from .dp import GradSync
 from .optim import FusedAdamW
 from .unet import UNetEngine
 
-F16 = torch.float16
+from .precision import POLICY
 F32 = torch.float32
 
 

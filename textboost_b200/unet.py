@@ -24,7 +24,7 @@ import torch
 from . import _cabi as C
 from . import ops
 
-F16 = torch.float16
+from .precision import POLICY
 F32 = torch.float32
 
 
@@ -208,7 +208,7 @@ class _Transformer:
         do2 = self.o2.dgrad(dh2).view(B, N, Cc)
         batched = dkv2 is not None
         if not batched:
-            dkv2 = torch.empty((B, L, 2 * Cc), device=kv2.device, dtype=F16)
+            dkv2 = torch.empty((B, L, 2 * Cc), device=kv2.device, dtype=POLICY.act)
         # 77 text tokens = a single KV tile: dQ leaves the kernel as fp16 (no fp32 accumulator, memset or cast)
         one_tile = L <= 128
         dq2, _, _ = ops.attn_bwd(q2, kv2[..., :Cc], kv2[..., Cc:], o2, do2, lse2, self.heads,
@@ -263,7 +263,7 @@ class UNetEngine:
     def __init__(self, cfg: UNetConfig, sd: Dict[str, torch.Tensor]):
         self.cfg = cfg
         ch = cfg.block_out_channels
-        sd = {k: v.detach().to(dtype=F16).contiguous() for k, v in sd.items()}
+        sd = {k: v.detach().to(dtype=POLICY.act).contiguous() for k, v in sd.items()}
         self.conv_in_w, self.conv_in_b = sd["conv_in.weight"], sd["conv_in.bias"]
         self.t1 = _Linear(sd["time_embedding.linear_1.weight"], sd["time_embedding.linear_1.bias"])
         self.t2 = _Linear(sd["time_embedding.linear_2.weight"], sd["time_embedding.linear_2.bias"])
@@ -342,7 +342,7 @@ class UNetEngine:
         train_textboost.py:1054-1067)."""
         cfg = self.cfg
         self.first_attn.ehs_ready = ehs_ready
-        assert sample.dtype == F16 and ehs.dtype == F16 and timesteps.dtype == torch.int64
+        assert sample.dtype == POLICY.act and ehs.dtype == POLICY.act and timesteps.dtype == torch.int64
         sample = sample.contiguous()
         ehs = ehs.contiguous()
         save = save_for_backward
@@ -417,7 +417,7 @@ class UNetEngine:
                                arena=self._arena)
         dskips = []  # gradients of the skip tensors in the order they are popped in forward
         # d[to_k | to_v] of all cross-attentions side by side: one GEMM at the end takes them back to the text states
-        dkv_all = torch.empty((B, L, self._kv_total), device=dout.device, dtype=F16)
+        dkv_all = torch.empty((B, L, self._kv_total), device=dout.device, dtype=POLICY.act)
 
         def dkv_of(a):
             return dkv_all[..., a.kv_off:a.kv_off + a.kv2.w.shape[0]]

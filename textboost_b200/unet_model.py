@@ -25,7 +25,7 @@ import torch
 
 from .unet import UNetConfig, UNetEngine
 
-F16 = torch.float16
+from .precision import POLICY
 F32 = torch.float32
 
 
@@ -84,11 +84,11 @@ class _UNetFunction(torch.autograd.Function):
     def forward(ctx, ehs, engine, sample, timesteps):
         ctx.engine = engine
         ctx.ehs_dtype = ehs.dtype
-        return engine.forward(sample, timesteps, ehs.to(F16), save_for_backward=True)
+        return engine.forward(sample, timesteps, ehs.to(POLICY.act), save_for_backward=True)
 
     @staticmethod
     def backward(ctx, d_out):
-        d_ehs = ctx.engine.backward(d_out.to(F16).contiguous())
+        d_ehs = ctx.engine.backward(d_out.to(POLICY.act).contiguous())
         return d_ehs.to(ctx.ehs_dtype), None, None, None
 
 
@@ -170,14 +170,15 @@ class UNet2DConditionModel:
         if isinstance(device, torch.dtype):
             device, dtype = None, device
         if dtype is not None:
-            if dtype not in (F16, F32):
-                raise NotImplementedError("the B200 UNet computes in fp16 (mixed_precision fp16)")
+            if dtype not in (POLICY.act, F32):
+                raise NotImplementedError(f"the B200 UNet computes in {POLICY.act} (precision policy {POLICY.name}); "
+                                          f"asked for {dtype}")
             self._dtype = dtype
         if device is not None:
             device = torch.device(device)
             if device.type == "cuda":
                 if self._engine is None:
-                    dsd = {k: v.to(device=device, dtype=F16) for k, v in self._sd.items()}
+                    dsd = {k: v.to(device=device, dtype=POLICY.act) for k, v in self._sd.items()}
                     self._engine = UNetEngine(self._cfg, dsd)
                     del dsd
             elif self._engine is not None:
@@ -208,11 +209,11 @@ class UNet2DConditionModel:
         t = timestep.to(device=dev, dtype=torch.int64).reshape(-1)
         if t.numel() == 1 and B > 1:
             t = t.expand(B)
-        x = sample.to(F16).contiguous()
+        x = sample.to(POLICY.act).contiguous()
         if encoder_hidden_states.requires_grad and torch.is_grad_enabled():
             out = _UNetFunction.apply(encoder_hidden_states, e, x, t.contiguous())
         else:
-            out = e.forward(x, t.contiguous(), encoder_hidden_states.to(F16), save_for_backward=False)
+            out = e.forward(x, t.contiguous(), encoder_hidden_states.to(POLICY.act), save_for_backward=False)
         if self._dtype == F32:
             out = out.float()
         return UNet2DConditionOutput(out) if return_dict else (out,)

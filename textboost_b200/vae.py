@@ -29,7 +29,7 @@ import torch
 from . import ops
 from .unet import _Conv3, _Linear, _conv_fwd_weight
 
-F16 = torch.float16
+from .precision import POLICY
 F32 = torch.float32
 
 
@@ -191,7 +191,7 @@ class _MidAttention:
         h, _ = ops.groupnorm(x, *self.n, self.G, _EPS, False)
         h = h.view(B, N, Cc)
         qk = ops.gemm(h.view(B * N, Cc), self.wqk, bias=self.bqk).view(B, N, 2 * Cc)
-        o = torch.empty((B, N, Cc), device=x.device, dtype=F16)
+        o = torch.empty((B, N, Cc), device=x.device, dtype=POLICY.act)
         for b in range(B):
             s = ops.gemm(qk[b, :, :Cc], qk[b, :, Cc:], alpha=Cc ** -0.5)      # [N, N] scores
             ops.softmax_rows_(s)
@@ -222,9 +222,9 @@ class VAEEncoderEngine:
         w_pad[:L2] = w_fold
         b_pad = torch.zeros(self.PAD_OUT, device=dev, dtype=F32)
         b_pad[:L2] = b_fold
-        self.out_w = _conv_fwd_weight(w_pad.to(F16))
-        self.out_b = b_pad.to(F16)
-        sd = {k[len("encoder."):]: v.detach().to(dtype=F16).contiguous() for k, v in sd.items()
+        self.out_w = _conv_fwd_weight(w_pad.to(POLICY.act))
+        self.out_b = b_pad.to(POLICY.act)
+        sd = {k[len("encoder."):]: v.detach().to(dtype=POLICY.act).contiguous() for k, v in sd.items()
               if k.startswith("encoder.")}
         self.conv_in_w, self.conv_in_b = sd["conv_in.weight"], sd["conv_in.bias"]
         self.down = []
@@ -271,7 +271,7 @@ class VAEEncoderEngine:
         hw = (H // f) * (W // f)
         means, stds = [], []
         for i in range(0, B, self.max_chunk):
-            px = pixel_values[i:i + self.max_chunk].to(F16).contiguous()
+            px = pixel_values[i:i + self.max_chunk].to(POLICY.act).contiguous()
             rows = self._moments_rows(px)
             _, m, s = ops.vae_sample(rows, px.shape[0], hw, L, want_moments=True)
             means.append(m)
@@ -290,7 +290,7 @@ class VAEEncoderEngine:
         eps = eps.to(F32).contiguous()
         out = []
         for i in range(0, B, self.max_chunk):
-            px = pixel_values[i:i + self.max_chunk].to(F16).contiguous()
+            px = pixel_values[i:i + self.max_chunk].to(POLICY.act).contiguous()
             rows = self._moments_rows(px)
             lat, _, _ = ops.vae_sample(rows, px.shape[0], h * w, L, eps=eps[i:i + self.max_chunk],
                                        scaling_factor=self.cfg.scaling_factor)
@@ -327,7 +327,7 @@ class VAEDecoderEngine:
         L = cfg.latent_channels
         self.pq_w = sd["post_quant_conv.weight"].detach().to(F32).reshape(L, L).contiguous()
         self.pq_b = sd["post_quant_conv.bias"].detach().to(F32).contiguous()
-        sd = {k[len("decoder."):]: v.detach().to(dtype=F16).contiguous() for k, v in sd.items()
+        sd = {k[len("decoder."):]: v.detach().to(dtype=POLICY.act).contiguous() for k, v in sd.items()
               if k.startswith("decoder.")}
         self.conv_in_w, self.conv_in_b = sd["conv_in.weight"], sd["conv_in.bias"]
         self.mid = (_Resnet(sd, "mid_block.resnets.0.", G), _MidAttention(sd, "mid_block.attentions.0.", G),
@@ -340,9 +340,9 @@ class VAEDecoderEngine:
             self.up.append((res, up))
         self.norm_out = (sd["conv_norm_out.weight"], sd["conv_norm_out.bias"])
         w = sd["conv_out.weight"]
-        w_pad = torch.zeros((self.PAD_OUT,) + tuple(w.shape[1:]), device=w.device, dtype=F16)
+        w_pad = torch.zeros((self.PAD_OUT,) + tuple(w.shape[1:]), device=w.device, dtype=POLICY.act)
         w_pad[:cfg.in_channels] = w
-        b_pad = torch.zeros(self.PAD_OUT, device=w.device, dtype=F16)
+        b_pad = torch.zeros(self.PAD_OUT, device=w.device, dtype=POLICY.act)
         b_pad[:cfg.in_channels] = sd["conv_out.bias"]
         self.out_w, self.out_b = _conv_fwd_weight(w_pad), b_pad
 
@@ -485,7 +485,7 @@ class AutoencoderKL:
         """dtype is accepted for call-site compatibility (train_textboost.py:938 asks for fp32) but the engines compute
         in fp16 with fp32 accumulation whatever it says; asking for anything else is reported once, with the measured
         deviation, rather than dropped silently."""
-        if dtype is not None and dtype != F16 and not getattr(AutoencoderKL, "_dtype_warned", False):
+        if dtype is not None and dtype != POLICY.act and not getattr(AutoencoderKL, "_dtype_warned", False):
             import warnings
             AutoencoderKL._dtype_warned = True
             warnings.warn(f"AutoencoderKL.to(dtype={dtype}): the B200 VAE engines compute in fp16 with fp32 accumulation "

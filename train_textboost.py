@@ -141,7 +141,7 @@ def _unsupported(args):
                          "end: it cannot be combined with --latents_file / --synthetic_data")
     if args.unet_params_to_train != "none":
         # train_textboost.py:711-720 adds LoRA to attn2.to_k / to_v, then :937 casts the WHOLE UNet -- adapter included --
-        # to weight_dtype.  Under --mixed_precision fp16 (the only policy built here) the trainable tensors are fp16 and
+        # to weight_dtype.  Under --mixed_precision fp16 the trainable tensors are fp16 and
         # accelerate's clip_grad_norm_ -> GradScaler.unscale_ raises "Attempting to unscale FP16 gradients": the mode
         # only runs in the reference's fp32 policy, which is outside this path.
         raise NotImplementedError("--unet_params_to_train crossattn_kv: the UNet is frozen on this path; in the "
@@ -151,8 +151,11 @@ def _unsupported(args):
         raise ValueError("--lora_rank must be >= 0")
     if args.gradient_accumulation_steps < 1:
         raise ValueError("--gradient_accumulation_steps must be >= 1")
-    if args.mixed_precision not in (None, "fp16"):
-        raise NotImplementedError("the B200 path computes in fp16 with fp32 master weights (--mixed_precision fp16)")
+    if args.mixed_precision == "no":
+        # weight_dtype = torch.float32 (train_textboost.py:928): every tensor-core operand would be fp32 / tf32
+        raise NotImplementedError("--mixed_precision no (fp32 weights and activations) is not built: the B200 path "
+                                  "keeps 16-bit tensor-core operands with fp32 accumulation and fp32 master weights "
+                                  "(--mixed_precision fp16 or bf16)")
     if args.text_encoder_use_attention_mask:
         # train_textboost.py:1058 hands encode_prompt the collated attention_mask, which is a Python LIST
         # (dataset.py:428, 455): the reference itself fails on `.to(device)` there
@@ -329,6 +332,10 @@ def main(args):
     import copy
 
     _unsupported(args)
+    # weight_dtype (train_textboost.py:928-933): selects the fp16 or the bf16 build of the library for this process
+    from textboost_b200 import precision
+    precision.set_policy(args.mixed_precision or "fp16")
+    weight_dtype = precision.POLICY.act
     if not torch.cuda.is_available():
         raise SystemExit("train_textboost.py needs a B200: the CUDA library is the product, there is no CPU path")
     rank, world, local_rank = dp.init_from_env()
@@ -414,8 +421,8 @@ def main(args):
     mean_norm = text_encoder.get_input_embeddings().weight.norm(dim=-1).mean().item()
 
     text_encoder.to(device)
-    unet.to(device, dtype=torch.float16)
-    original_text_encoder.to(device, dtype=torch.float16)
+    unet.to(device, dtype=weight_dtype)
+    original_text_encoder.to(device, dtype=weight_dtype)
     trainer = TextBoostTrainer(
         unet.engine, text_encoder.engine, original_text_encoder.engine if args.kpl_weight > 0 else None,
         learning_rate=args.learning_rate, emb_learning_rate=args.emb_learning_rate, adam_beta1=args.adam_beta1,
@@ -578,6 +585,8 @@ def main(args):
                                                            safe_serialization=not args.no_safe_serialization)
         save_learned_embeddings(text_encoder, added_tokens, aug_token_dict, args.output_dir)
     tracker.close()
+    _st = trainer.opt_state.tolist()
+    RUN_INFO.update(precision=precision.POLICY.name, loss_scale=_st[0], skipped_steps=int(_st[8]))
     logger.info(f"Training took {time.perf_counter() - start:.2f} seconds")
     if world > 1:
         # the captured graph holds the NCCL communicator: release it before the ranks part (destroying the process
