@@ -49,10 +49,15 @@ class TextBoostTrainer:
                  emb_learning_rate=1e-3, adam_beta1=0.9, adam_beta2=0.999, adam_weight_decay=1e-2,
                  adam_epsilon=1e-8, max_grad_norm=1.0, kpl_weight=0.1, kpl_type="cos",
                  prediction_type="epsilon", mixing=None, mean_norm: Optional[float] = None,
-                 mixed_precision="fp16", process_group=None, image_prior_weight: Optional[float] = None,
+                 mixed_precision: Optional[str] = None, process_group=None, image_prior_weight: Optional[float] = None,
                  lr_scheduler="constant", lr_warmup_steps=0, max_train_steps=0, gradient_accumulation_steps=1,
                  num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012):
         self.unet, self.te, self.te0 = unet, text_encoder, original_text_encoder
+        # the engines were built for the process's precision policy (precision.py); the GradScaler follows it
+        mixed_precision = mixed_precision or POLICY.name
+        if mixed_precision != POLICY.name:
+            raise ValueError(f"mixed_precision={mixed_precision!r} but the process's precision policy is {POLICY.name!r} "
+                             "(textboost_b200.precision.set_policy before building the engines)")
         # --with_image_prior (train_textboost.py:1077-1094): the batch is [instance | class] halves and the loss is
         # mse(instance half) + image_prior_weight * mse(class half); None = the plain single-part loss
         self.image_prior_weight = image_prior_weight
