@@ -293,6 +293,19 @@ int tb_lora_grad(const void* dY, const void* y_ext, const void* dA_ext, int64_t 
                  int M, int nblk, int tmask, int D, int r, float scaling, void* stream);
 /* dA_ext[:, :D] += dA_ext[:, D:D+R] @ A. */
 int tb_lora_dx(void* dA_ext, int64_t ld, const float* A, int M, int D, int R, void* stream);
+/* ---- UNet cross-attention K/V LoRA (--unet_params_to_train crossattn_kv, train_textboost.py:712-721, 838-841: peft
+ * adapters on attn2.to_k / attn2.to_v of every transformer block, third optimiser group).  The blocks' K | V
+ * projections are one fused GEMM over the text states (KV output columns); the n_adapters adapters are stacked:
+ * A fp32 [n_adapters*r, ctx], B fp32 [KV, r] (row j = lora_B row of fused output column j), blk int32 [KV] = adapter of
+ * column j (blk[j] == blk[j+1] for even j), off int32 [n_adapters+1] = column range of each adapter.
+ * fwd: Z (fp32 [M, n_adapters*r], kept for the backward) = ehs A^T;  kv[m, j] += scaling * Z[m, blk[j] r ..] . B[j, :]
+ * bwd: dZ (fp32 scratch [M, n_adapters*r]) = scaling * dkv B per adapter;  dB += scaling * dkv^T Z;  dA += dZ^T ehs;
+ *      d_ehs (fp32 [M, ctx]) += dZ A.  ehs, kv, dkv are 16-bit [M, ctx] / [M, KV] contiguous. */
+int tb_unet_lora_fwd(const void* ehs, const float* A, const float* B, const int32_t* blk, float* Z, void* kv, int M,
+                     int ctx, int KV, int n_adapters, int r, float scaling, void* stream);
+int tb_unet_lora_bwd(const void* dkv, const void* ehs, const float* A, const float* B, const float* Z,
+                     const int32_t* blk, const int32_t* off, float* dZ, float* dA, float* dB, float* d_ehs, int M,
+                     int ctx, int KV, int n_adapters, int r, float scaling, void* stream);
 /* causal attention over L <= 128 tokens, head_dim 64; qkv [B*L, 3D] fused; dqkv laid out like qkv. */
 int tb_clip_attn_fwd(const void* qkv, void* out, int B, int L, int D, int heads, void* stream);
 int tb_clip_attn_bwd(const void* qkv, const void* dO, void* dqkv, int B, int L, int D, int heads,

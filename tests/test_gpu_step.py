@@ -282,7 +282,7 @@ def test_step_tiny_vs_oracle(kpl_type, mixing, pred):
     assert r["lora_grad_rel_l2"] < 5e-3 * TOLX and r["lora_grad_cos"] > 1 - 1e-5 * TOLX ** 2
     assert r["row_grad_rel"] < 5e-3 * TOLX
     assert abs(r["grad_norm"] - r["grad_norm_ref"]) < 3e-3 * TOLX * r["grad_norm_ref"]
-    assert abs(r["added_norm"] - r["added_norm_ref"]) < 1e-4 * r["added_norm_ref"]
+    assert abs(r["added_norm"] - r["added_norm_ref"]) < 1e-4 * TOLX * r["added_norm_ref"]
     assert abs(r["frozen_decay"] - r["frozen_decay_ref"]) < 1e-6
     # Adam's first step is lr*sign(g): parameters agree to a fraction of one lr step except where |g| ~ 0
     assert r["lora_param_max_abs_diff"] <= 2.1 * tr.lr

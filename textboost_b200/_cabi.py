@@ -107,6 +107,8 @@ _SIGNATURES = {
     "tb_lora_grad": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                      c_float, c_void_p],
     "tb_lora_dx": [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p],
+    "tb_unet_lora_fwd": [c_void_p] * 6 + [c_int] * 5 + [c_float, c_void_p],
+    "tb_unet_lora_bwd": [c_void_p] * 11 + [c_int] * 5 + [c_float, c_void_p],
     "tb_clip_attn_fwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "tb_clip_attn_bwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "tb_act_fwd_f16": [c_void_p, c_void_p, c_int64, c_int, c_void_p],
@@ -152,7 +154,7 @@ def last_error() -> str:
 
 
 # KERNELS one call of each entry point enqueues (memset nodes are not counted); entry points not listed launch one
-_KERNELS_PER_CALL = {"tb_groupnorm_fwd_f16": 2, "tb_groupnorm_bwd_f16": 2, "tb_attn_bwd_f16": 2,
+_KERNELS_PER_CALL = {"tb_groupnorm_fwd_f16": 2, "tb_groupnorm_bwd_f16": 2, "tb_attn_bwd_f16": 2, "tb_unet_lora_fwd": 2, "tb_unet_lora_bwd": 4,
                      "tb_resize_crop_normalize_u8": 2,
                      "tb_adamw_fused_step": 3, "tb_version": 0, "tb_check_device": 0, "tb_storage_dtype": 0, "tb_set_workspace": 0,
                      "tb_attn_debug_trace": 0}

@@ -409,3 +409,30 @@ def image_u8(rows, npix, channels=3):
     out = torch.empty((npix, channels), device=rows.device, dtype=torch.uint8)
     C.call("tb_image_u8", C.ptr(rows), rows.stride(0), C.ptr(out), npix, channels, C.stream_ptr())
     return out
+
+
+def unet_lora_fwd(ehs2d, A, Bm, blk, kv2d, r, scaling):
+    """UNet cross-attention K/V LoRA, forward (tb_unet_lora_fwd): kv2d [M, KV] += scaling * (ehs2d A^T) B^T per
+    adapter, in place; returns Z = ehs2d A^T (fp32 [M, n_adapters*r]) for the backward."""
+    M, ctx = ehs2d.shape
+    KV, R = kv2d.shape[1], A.shape[0]
+    assert ehs2d.dtype == POLICY.act and kv2d.dtype == POLICY.act and ehs2d.is_contiguous() and kv2d.is_contiguous()
+    assert A.dtype == F32 and Bm.dtype == F32 and A.shape == (R, ctx) and Bm.shape == (KV, r) and R % r == 0
+    assert blk.dtype == torch.int32 and blk.numel() == KV
+    Z = torch.empty((M, R), device=ehs2d.device, dtype=F32)
+    C.call("tb_unet_lora_fwd", C.ptr(ehs2d), C.ptr(A), C.ptr(Bm), C.ptr(blk), C.ptr(Z), C.ptr(kv2d), M, ctx, KV, R // r,
+           r, float(scaling), C.stream_ptr())
+    return Z
+
+
+def unet_lora_bwd(dkv2d, ehs2d, A, Bm, Z, blk, off, dA, dB, d_ehs, r, scaling):
+    """UNet cross-attention K/V LoRA, backward (tb_unet_lora_bwd): dA / dB (fp32, accumulated) and d_ehs (fp32 [M, ctx],
+    accumulated) from dkv2d [M, KV]."""
+    M, ctx = ehs2d.shape
+    KV, R = dkv2d.shape[1], A.shape[0]
+    assert dkv2d.dtype == POLICY.act and dkv2d.is_contiguous() and ehs2d.is_contiguous() and Z.shape == (M, R)
+    assert dA.dtype == F32 and dB.dtype == F32 and dA.numel() == R * ctx and dB.numel() == KV * r
+    assert d_ehs.dtype == F32 and d_ehs.is_contiguous() and d_ehs.numel() == M * ctx
+    dZ = torch.empty((M, R), device=dkv2d.device, dtype=F32)
+    C.call("tb_unet_lora_bwd", C.ptr(dkv2d), C.ptr(ehs2d), C.ptr(A), C.ptr(Bm), C.ptr(Z), C.ptr(blk), C.ptr(off),
+           C.ptr(dZ), C.ptr(dA), C.ptr(dB), C.ptr(d_ehs), M, ctx, KV, R // r, r, float(scaling), C.stream_ptr())

@@ -141,3 +141,49 @@ class FusedAdamW:
         self.state.copy_(sd["state"])
         self.mean_norm = sd["mean_norm"]
         self.param_groups[1]["lr"], self.param_groups[0]["lr"] = sd["lr"], sd["emb_lr"]
+
+
+class FlatAdamW:
+    """AdamW over one flat fp32 buffer with one learning rate, no gradient clipping and no embedding rows: the third
+    parameter group of train_textboost.py:838-841 (the UNet LoRA of --unet_params_to_train crossattn_kv; clipping
+    covers the text encoder only, :1128-1133).  The same tb_adamw_fused_step, with an empty row segment and
+    max_grad_norm 0.  No GradScaler of its own (the loss scale of the step is 1: the mode runs under the bf16 policy,
+    see TextBoostTrainer)."""
+
+    def __init__(self, params: torch.Tensor, grads: torch.Tensor, lr=5e-5, betas=(0.9, 0.999), weight_decay=1e-2,
+                 eps=1e-8, world_size: int = 1, lr_scheduler: str = "constant", lr_warmup_steps: int = 0,
+                 max_train_steps: int = 0, gradient_accumulation_steps: int = 1):
+        assert params.dtype == F32 and grads.shape == params.shape and params.is_contiguous()
+        self.params, self.grads = params, grads
+        self.lr, self.betas, self.weight_decay, self.eps = lr, tuple(betas), weight_decay, eps
+        self.world_size, self.gradient_accumulation_steps = world_size, int(gradient_accumulation_steps)
+        self.lr_scheduler, self.lr_warmup_steps, self.max_train_steps = lr_scheduler, lr_warmup_steps, max_train_steps
+        self.exp_avg = torch.zeros_like(params)
+        self.exp_avg_sq = torch.zeros_like(params)
+        self.state = torch.zeros(16, device=params.device, dtype=F32)
+        self.state[LOSS_SCALE] = 1.0
+        self.state[FIXED_SCALE] = 1.0
+        self.state[FROZEN_DECAY] = 1.0
+        self._norm_out = torch.zeros(1, device=params.device, dtype=F32)
+
+    def step(self):
+        C.call("tb_adamw_fused_step", C.ptr(self.params), C.ptr(self.grads), C.ptr(self.exp_avg),
+               C.ptr(self.exp_avg_sq), self.params.numel(), 0, 0, float(self.lr), float(self.lr), self.betas[0],
+               self.betas[1], self.eps, self.weight_decay, 0.0,
+               1.0 / (self.world_size * self.gradient_accumulation_steps), 0.0, LR_SCHEDULES[self.lr_scheduler],
+               float(self.lr_warmup_steps), float(self.max_train_steps), C.ptr(self.state), C.ptr(self._norm_out),
+               C.stream_ptr())
+
+    def hyperparameters(self):
+        return (float(self.lr), self.betas, self.eps, self.weight_decay, self.lr_scheduler, self.lr_warmup_steps,
+                self.max_train_steps, self.gradient_accumulation_steps, self.world_size)
+
+    def state_dict(self):
+        return {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "state": self.state.clone(),
+                "lr": self.lr}
+
+    def load_state_dict(self, sd):
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.state.copy_(sd["state"])
+        self.lr = sd["lr"]

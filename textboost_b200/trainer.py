@@ -23,7 +23,7 @@ from . import _cabi as C
 from . import ops
 from .clip import ClipEngine
 from .dp import GradSync
-from .optim import FusedAdamW
+from .optim import FlatAdamW, FusedAdamW
 from .unet import UNetEngine
 
 from .precision import POLICY
@@ -77,6 +77,22 @@ class TextBoostTrainer:
                               mixed_precision=mixed_precision, world_size=self.world, lr_scheduler=lr_scheduler,
                               lr_warmup_steps=lr_warmup_steps, max_train_steps=max_train_steps,
                               gradient_accumulation_steps=gradient_accumulation_steps)
+        # --unet_params_to_train crossattn_kv (train_textboost.py:712-721, 838-841): the UNet engine carries a K/V
+        # adapter (UNetEngine.add_cross_kv_lora); its flat buffer is the third parameter group: the LoRA learning
+        # rate, weight decay, no clipping (:1128-1133 clip the text encoder only).  In the reference the mode only runs
+        # without a GradScaler (its fp16 policy raises in GradScaler.unscale_ on the fp16 adapter tensors): here it is
+        # tied to the bf16 policy, whose loss scale is the constant 1 both optimiser calls assume.
+        self.opt_unet = None
+        if getattr(unet, "kv_lora", None) is not None:
+            if mixed_precision != "bf16":
+                raise NotImplementedError("the UNet K/V adapter (--unet_params_to_train crossattn_kv) needs "
+                                          "--mixed_precision bf16: the reference's fp16 path fails in "
+                                          "GradScaler.unscale_ on the fp16 adapter tensors, and fp32 is not built")
+            self.opt_unet = FlatAdamW(unet.kv_lora.params, unet.kv_lora.grads, lr=learning_rate,
+                                      betas=(adam_beta1, adam_beta2), weight_decay=adam_weight_decay, eps=adam_epsilon,
+                                      world_size=self.world, lr_scheduler=lr_scheduler,
+                                      lr_warmup_steps=lr_warmup_steps, max_train_steps=max_train_steps,
+                                      gradient_accumulation_steps=gradient_accumulation_steps)
         # the checkpoint's scheduler/scheduler_config.json (DDPMScheduler.from_pretrained, train_textboost.py:644)
         self.num_train_timesteps = int(num_train_timesteps)
         self.acp = alphas_cumprod(self.num_train_timesteps, beta_start, beta_end, device=self.dev)
@@ -202,9 +218,13 @@ class TextBoostTrainer:
 
     def all_reduce(self):
         self.sync.all_reduce_(self.te.state.grads)
+        if self.opt_unet is not None:
+            self.sync.all_reduce_(self.opt_unet.grads)
 
     def optimizer_step(self):
         self.opt.step()
+        if self.opt_unet is not None:
+            self.opt_unet.step()
 
     # ------------------------------------------------------------------ the step
     def step(self, latents, noise, timesteps, input_ids, prior_ids=None, sync_gradients=True):

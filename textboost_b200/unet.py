@@ -141,6 +141,7 @@ class _Transformer:
 
     def __init__(self, sd, p, cfg: UNetConfig, heads: int):
         self.G, self.heads = cfg.norm_num_groups, heads
+        self.prefix = p  # diffusers module path of the Transformer2DModel ("down_blocks.0.attentions.0.")
         self.norm = (sd[p + "norm.weight"], sd[p + "norm.bias"])
         self.pi = _Linear(sd[p + "proj_in.weight"], sd[p + "proj_in.bias"])
         self.po = _Linear(sd[p + "proj_out.weight"], sd[p + "proj_out.bias"])
@@ -257,6 +258,74 @@ class _Up:
         return ops.upsample2x_bwd(self.w.dgrad(dout))
 
 
+class CrossKVLora:
+    """The UNet adapter of ``--unet_params_to_train crossattn_kv`` (train_textboost.py:712-721): peft LoRA
+    (``LoraConfig(r, lora_alpha=r, init_lora_weights="gaussian", target_modules=["attn2.to_k", "attn2.to_v"])``) on the
+    K and V projections of every cross-attention.  Adapter 2i / 2i+1 is to_k / to_v of the i-th transformer block in
+    forward order; they are stacked the way the engine stacks the projections themselves (one GEMM for all blocks):
+
+      params = [ A (n_adapters*r, ctx) | B (KV, r) ]  fp32 master, flat (the third optimiser group, :838-841);
+      grads  = same layout, accumulated by backward (loss-scaled like every other gradient of the step).
+
+    peft's gaussian init: lora_A ~ N(0, 1/r), lora_B = 0; scaling = lora_alpha / r = 1."""
+
+    def __init__(self, engine: "UNetEngine", r: int, alpha: Optional[float] = None, seed: int = 0):
+        if not 1 <= r <= 16:
+            raise ValueError(f"UNet LoRA rank {r}: 1..16")
+        dev = engine._kv_w.device
+        self.r, self.scaling = r, (alpha if alpha is not None else r) / r
+        self.ctx, self.KV = engine._kv_w.shape[1], engine._kv_total
+        self.n_adapters = 2 * len(engine._attns)
+        self.R = self.n_adapters * r
+        self.n_a, self.n_b = self.R * self.ctx, self.KV * r
+        self.params = torch.zeros(self.n_a + self.n_b, device=dev, dtype=F32)
+        self.grads = torch.zeros_like(self.params)
+        g = torch.Generator().manual_seed(seed)
+        self.A().copy_((torch.randn(self.R, self.ctx, generator=g) / r).to(dev))
+        blk = torch.empty(self.KV, dtype=torch.int32)
+        off = [0]
+        self.names = []  # diffusers / peft module path of every adapter
+        for i, a in enumerate(engine._attns):
+            Cc = a.kv2.w.shape[0] // 2
+            blk[a.kv_off:a.kv_off + Cc] = 2 * i
+            blk[a.kv_off + Cc:a.kv_off + 2 * Cc] = 2 * i + 1
+            off += [a.kv_off + Cc, a.kv_off + 2 * Cc]
+            self.names += [a.prefix + "transformer_blocks.0.attn2.to_k", a.prefix + "transformer_blocks.0.attn2.to_v"]
+        self.blk, self.off = blk.to(dev), torch.tensor(off, dtype=torch.int32, device=dev)
+        self._ctx = None
+
+    def A(self, buf=None):
+        return (self.params if buf is None else buf)[:self.n_a].view(self.R, self.ctx)
+
+    def B(self, buf=None):
+        return (self.params if buf is None else buf)[self.n_a:].view(self.KV, self.r)
+
+    def forward(self, ehs2d, kv2d, save):
+        Z = ops.unet_lora_fwd(ehs2d, self.A(), self.B(), self.blk, kv2d, self.r, self.scaling)
+        self._ctx = (ehs2d, Z) if save else None
+
+    def backward(self, dkv2d, d_ehs2d):
+        ehs2d, Z = self._ctx
+        self._ctx = None
+        ops.unet_lora_bwd(dkv2d, ehs2d, self.A(), self.B(), Z, self.blk, self.off, self.A(self.grads),
+                          self.B(self.grads), d_ehs2d, self.r, self.scaling)
+
+    # peft state-dict surface (get_peft_model_state_dict names: "<module>.lora_A.weight" [r, ctx], ".lora_B.weight" [C, r])
+    def state_dict(self):
+        sd = {}
+        for i, n in enumerate(self.names):
+            lo, hi = int(self.off[i]), int(self.off[i + 1])
+            sd[n + ".lora_A.weight"] = self.A()[i * self.r:(i + 1) * self.r].detach().clone()
+            sd[n + ".lora_B.weight"] = self.B()[lo:hi].detach().clone()
+        return sd
+
+    def load_state_dict(self, sd):
+        off = self.off.tolist()
+        for i, n in enumerate(self.names):
+            self.A()[i * self.r:(i + 1) * self.r].copy_(sd[n + ".lora_A.weight"])
+            self.B()[off[i]:off[i + 1]].copy_(sd[n + ".lora_B.weight"])
+
+
 class UNetEngine:
     """Weights + forward/backward orchestration.  `sd` maps diffusers keys to fp16 CUDA tensors."""
 
@@ -326,6 +395,12 @@ class UNetEngine:
         self._kv_total = off
         for a in self._attns:  # the per-block copies are only kept for the unbatched entry points (tests)
             a.kv2.wt = self._kv_wt[:, a.kv_off:a.kv_off + a.kv2.w.shape[0]]
+        self.kv_lora: Optional[CrossKVLora] = None
+
+    def add_cross_kv_lora(self, r: int, alpha: Optional[float] = None, seed: int = 0) -> CrossKVLora:
+        """unet.add_adapter(LoraConfig(target_modules=["attn2.to_k", "attn2.to_v"])) of train_textboost.py:712-720."""
+        self.kv_lora = CrossKVLora(self, r, alpha, seed)
+        return self.kv_lora
 
     def _set_arena(self, arena):
         self._arena = arena
@@ -363,7 +438,11 @@ class UNetEngine:
             if kv_all[0] is None:  # first cross-attention: wait for the text encoder, project K/V for all 16 blocks
                 if ehs_ready is not None:
                     torch.cuda.current_stream().wait_event(ehs_ready)
-                kv_all[0] = ops.gemm(ehs.reshape(B * L, -1), self._kv_w).view(B, L, self._kv_total)
+                ehs2d = ehs.reshape(B * L, -1)
+                kv2d = ops.gemm(ehs2d, self._kv_w)
+                if self.kv_lora is not None:
+                    self.kv_lora.forward(ehs2d, kv2d, save_for_backward)
+                kv_all[0] = kv2d.view(B, L, self._kv_total)
             return kv_all[0][..., a.kv_off:a.kv_off + a.kv2.w.shape[0]]
 
         x = ops.conv_in(sample, self.conv_in_w, self.conv_in_b)
@@ -460,6 +539,8 @@ class UNetEngine:
             if done:
                 break
         ops.gemm(dkv_all.view(B * L, self._kv_total), self._kv_wt, out=d2, out_kind=C.TB_OUT_F32_ACC)
+        if self.kv_lora is not None:
+            self.kv_lora.backward(dkv_all.view(B * L, self._kv_total), d2)
         self._set_arena(None)
         # drop contexts of the pruned prefix
         for blk in self.down:
