@@ -66,6 +66,16 @@ def twin_of(trainer, device="cpu", dtype=torch.float32, frozen_dtype=None):
     unet = unet_ref.UNet2DConditionModelRef(_unet_cfg(ucfg))
     unet.load_state_dict({k: v.detach().to("cpu", torch.float32) for k, v in syn["unet_sd"].items()})
     unet = unet.to(device, frozen_dtype).requires_grad_(False)
+    kvl = getattr(trainer.unet, "kv_lora", None)
+    if kvl is not None:  # --unet_params_to_train crossattn_kv: same adapter weights on the oracle UNet
+        mods = unet.add_cross_kv_lora(kvl.r, kvl.scaling * kvl.r)
+        assert [n for n, _ in mods] == [n for n in kvl.names], "adapter order differs from the engine's"
+        sd = kvl.state_dict()
+        with torch.no_grad():
+            for n, m in mods:
+                m.lora_A["default"].weight.copy_(sd[n + ".lora_A.weight"])
+                m.lora_B["default"].weight.copy_(sd[n + ".lora_B.weight"])
+        unet = unet.to(device, frozen_dtype)  # the reference casts the adapter with the UNet (:937)
     csd = {k: v.detach().to("cpu", torch.float32) for k, v in syn["clip_sd"].items()}
     te_eng = trainer.te
     null = te_eng.null_embedding.detach().to("cpu", torch.float32)
@@ -94,7 +104,7 @@ def twin_of(trainer, device="cpu", dtype=torch.float32, frozen_dtype=None):
     te = te.to(device, dtype)
     te.get_input_embeddings().weight.requires_grad_(True)
     opt = step_ref.make_optimizer(te, learning_rate=trainer.lr, emb_learning_rate=trainer.emb_lr,
-                                  betas=(trainer.b1, trainer.b2), weight_decay=trainer.wd, eps=trainer.eps)
+                                  betas=(trainer.b1, trainer.b2), weight_decay=trainer.wd, eps=trainer.eps, unet=unet)
     return unet, te, te0, opt
 
 
@@ -188,6 +198,19 @@ def compare_step(trainer, batch: Dict[str, torch.Tensor], device="cpu", dtype=to
     if ref["grad_rows"] is not None and st.n_rows:
         out["row_grad_rel"] = rel_max(st.rows(g), ref["grad_rows"])
         out["row_grad_ours"], out["row_grad_ref"] = st.rows(g).detach().cpu(), ref["grad_rows"].detach().cpu()
+    kvl = getattr(trainer.unet, "kv_lora", None)
+    if kvl is not None:
+        gu = kvl.grads.detach().clone() / scale
+        ours_u, ref_u = [], []
+        off = kvl.off.tolist()
+        for i, n in enumerate(kvl.names):
+            ours_u += [kvl.A(gu)[i * kvl.r:(i + 1) * kvl.r].flatten().cpu(), kvl.B(gu)[off[i]:off[i + 1]].flatten().cpu()]
+            ref_u += [ref["grad_unet_lora"][n + ".lora_A.default.weight"].float().flatten().cpu(),
+                      ref["grad_unet_lora"][n + ".lora_B.default.weight"].float().flatten().cpu()]
+        uo, ur = torch.cat(ours_u), torch.cat(ref_u)
+        out["unet_lora_grad_rel_l2"] = ((uo - ur).norm() / ur.norm()).item()
+        out["unet_lora_grad_cos"] = torch.nn.functional.cosine_similarity(uo, ur, dim=0).item()
+        out["unet_lora_grad_norm_ref"] = ur.norm().item()
     if ref16 is not None:
         p16, g16, r16 = ref16
         pairs = {"pred": (trainer._pred, ref["pred"], p16), "lora_grad": (go, gr, g16)}
@@ -219,6 +242,15 @@ def compare_step(trainer, batch: Dict[str, torch.Tensor], device="cpu", dtype=to
             out["lora_param_max_abs_diff"] = (po - pr).abs().max().item()
         else:
             out["lora_param_max_abs_diff"] = 0.0
+        if kvl is not None:
+            pu, pr = [], []
+            mods = dict(unet.cross_kv_lora_modules())
+            off = kvl.off.tolist()
+            for i, n in enumerate(kvl.names):
+                pu += [kvl.A()[i * kvl.r:(i + 1) * kvl.r].detach().flatten().cpu(), kvl.B()[off[i]:off[i + 1]].detach().flatten().cpu()]
+                pr += [mods[n].lora_A["default"].weight.detach().float().flatten().cpu(),
+                       mods[n].lora_B["default"].weight.detach().float().flatten().cpu()]
+            out["unet_lora_param_max_abs_diff"] = (torch.cat(pu) - torch.cat(pr)).abs().max().item()
         out["frozen_decay"] = trainer.opt_state[5].item()
         base0 = trainer.synthetic["clip_sd"]["text_model.embeddings.token_embedding.weight"][5].float().cpu()
         out["frozen_decay_ref"] = (emb[5].cpu() / base0).mean().item()

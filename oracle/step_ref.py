@@ -93,6 +93,9 @@ def reference_step(unet, te, te0, latents, noise, timesteps, input_ids, prior_id
     for _, p in lora_named_parameters(te):
         p.grad = None
     emb.grad = None
+    unet_lora = [(n, p) for n, p in unet.named_parameters() if p.requires_grad]  # crossattn_kv adapter (:712-721)
+    for _, p in unet_lora:
+        p.grad = None
     loss, pred, ehs = forward_loss(unet, te, te0, latents, noise, timesteps, input_ids, prior_ids,
                                    kpl_weight, kpl_type, prediction_type, image_ppl_weight, mixed_precision)
     ehs.retain_grad()
@@ -103,6 +106,9 @@ def reference_step(unet, te, te0, latents, noise, timesteps, input_ids, prior_id
         if emb.grad is not None:
             emb.grad.mul_(inv)
         for _, p in lora_named_parameters(te):
+            if p.grad is not None:
+                p.grad.mul_(inv)
+        for _, p in unet_lora:
             if p.grad is not None:
                 p.grad.mul_(inv)
     if emb.grad is not None:
@@ -116,7 +122,8 @@ def reference_step(unet, te, te0, latents, noise, timesteps, input_ids, prior_id
                     p.grad[0::2, :] = 0.0
     out = {"loss": loss.detach(), "pred": pred.detach(), "d_ehs": ehs.grad.detach().clone(),
            "grad_rows": emb.grad[n_base:].detach().clone() if emb.grad is not None else None,
-           "grad_lora": {n: p.grad.detach().clone() for n, p in lora_named_parameters(te)}}
+           "grad_lora": {n: p.grad.detach().clone() for n, p in lora_named_parameters(te)},
+           "grad_unet_lora": {n: p.grad.detach().clone() for n, p in unet_lora if p.grad is not None}}
     if optimizer is not None:
         if max_grad_norm:
             out["grad_norm"] = torch.nn.utils.clip_grad_norm_(
@@ -133,9 +140,12 @@ def reference_step(unet, te, te0, latents, noise, timesteps, input_ids, prior_id
 
 
 def make_optimizer(te, learning_rate=5e-5, emb_learning_rate=1e-3, betas=(0.9, 0.999), weight_decay=1e-2,
-                   eps=1e-8):
-    """train_textboost.py:829-854."""
+                   eps=1e-8, unet=None):
+    """train_textboost.py:829-854; `unet` with trainable (LoRA) parameters adds the third group of :838-841."""
+    groups = [{"params": [te.get_input_embeddings().weight], "lr": emb_learning_rate},
+              {"params": [p for _, p in lora_named_parameters(te)]}]
+    if unet is not None and any(p.requires_grad for p in unet.parameters()):
+        groups.append({"params": [p for p in unet.parameters() if p.requires_grad]})
     return torch.optim.AdamW(
-        [{"params": [te.get_input_embeddings().weight], "lr": emb_learning_rate},
-         {"params": [p for _, p in lora_named_parameters(te)]}],
+        groups,
         lr=learning_rate, betas=betas, weight_decay=weight_decay, eps=eps)

@@ -304,6 +304,29 @@ class UNet2DConditionModelRef(nn.Module):
         self.conv_norm_out = nn.GroupNorm(cfg.norm_num_groups, ch[0], eps=cfg.norm_eps)
         self.conv_out = nn.Conv2d(ch[0], cfg.out_channels, 3, padding=1)
 
+
+    def add_cross_kv_lora(self, r: int, lora_alpha=None):
+        """``unet.add_adapter(LoraConfig(r, lora_alpha=r, init_lora_weights="gaussian",
+        target_modules=["attn2.to_k", "attn2.to_v"]))`` of /root/reference/train_textboost.py:712-720: every
+        cross-attention's K and V projections become peft LoRA linears (clip_ref.LoraLinear restates peft's layer);
+        only the lora_A / lora_B weights are trainable afterwards.  Returns the wrapped modules in forward order,
+        to_k before to_v within a block."""
+        from .clip_ref import LoraLinear
+        self.requires_grad_(False)
+        wrapped = []
+        for name, mod in list(self.named_modules()):
+            if name.endswith("attn2"):
+                for t in ("to_k", "to_v"):
+                    lin = LoraLinear(getattr(mod, t), r, lora_alpha if lora_alpha is not None else r)
+                    setattr(mod, t, lin)
+                    wrapped.append((f"{name}.{t}", lin))
+        return wrapped
+
+    def cross_kv_lora_modules(self):
+        """(module path, LoraLinear) of every adapter, in the engine's order: down blocks, mid block, up blocks."""
+        from .clip_ref import LoraLinear
+        return [(n, m) for n, m in self.named_modules() if isinstance(m, LoraLinear)]
+
     def forward(self, sample, timesteps, encoder_hidden_states):
         """sample [B,4,H,W], timesteps int64 [B], encoder_hidden_states [B,L,ctx] -> [B,4,H,W]."""
         cfg = self.config

@@ -66,7 +66,24 @@ assert precision.POLICY.name == "bf16" and _cabi.lib().tb_storage_dtype() == 1
 assert _cabi.lib_path().endswith("libtextboost_b200_bf16.so")
 assert {{"text_encoder", "dog.bin"}} <= set(os.listdir(out))
 assert T.RUN_INFO["loss_scale"] == 1.0 and T.RUN_INFO["skipped_steps"] == 0, T.RUN_INFO  # no GradScaler under bf16
-print("BF16_CLI_OK", loss)
+# --unet_params_to_train crossattn_kv: runs under bf16 (the reference's fp16 path cannot), writes the UNet adapter
+out2 = out + "_kv"
+loss2 = T.main(T.parse_args(["--pretrained_model_name_or_path", ck, "--output_dir", out2, "--synthetic_data",
+    "--resolution", "128", "--train_batch_size", "2", "--learning_rate", "1e-3", "--mixed_precision", "bf16",
+    "--max_train_steps", "8", "--checkpointing_steps", "4", "--unet_params_to_train", "crossattn_kv"]))
+assert loss2 == loss2 and loss2 < 10, loss2
+from safetensors.torch import load_file
+ad = load_file(os.path.join(out2, "unet", "pytorch_lora_weights.safetensors"))
+kb = [k for k in ad if k.endswith("attn2.to_v.lora_B.weight")]
+assert len(kb) == len(ad) // 4 and all(k.startswith("unet.") for k in ad)
+assert sum(float(ad[k].abs().sum()) for k in kb) > 0  # lora_B left its zero init: the UNet adapter trained
+assert os.path.exists(os.path.join(out2, "checkpoint-4", "pytorch_lora_weights.safetensors"))
+loss3 = T.main(T.parse_args(["--pretrained_model_name_or_path", ck, "--output_dir", out2, "--synthetic_data",
+    "--resolution", "128", "--train_batch_size", "2", "--learning_rate", "1e-3", "--mixed_precision", "bf16",
+    "--max_train_steps", "10", "--checkpointing_steps", "4", "--unet_params_to_train", "crossattn_kv",
+    "--resume_from_checkpoint", "latest"]))
+assert loss3 == loss3
+print("BF16_CLI_OK", loss, loss2, loss3)
 """
     env = {k: v for k, v in os.environ.items() if k != "TEXTBOOST_B200_PRECISION"}
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)

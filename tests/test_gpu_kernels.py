@@ -537,3 +537,46 @@ def test_fused_adamw_lr_schedules_match_torch_lambda_lr(name):
         assert abs(state[9].item() - lr_multiplier(name, int(state[4].item()) - 1, warm, total, 1e-2)) < 1e-6
     torch.testing.assert_close(p, ref.detach(), rtol=2e-5, atol=2e-6)
     assert state[4].item() == total - 1 and state[8].item() == 1
+
+
+@pytest.mark.parametrize("r", [4, 8])
+def test_unet_cross_kv_lora_fwd_bwd(r):
+    """tb_unet_lora_fwd / tb_unet_lora_bwd (peft LoRA on attn2.to_k / to_v of all blocks at once,
+    train_textboost.py:712-721) against autograd on the same fp32 adapters: three blocks of different widths."""
+    from textboost_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(5 + r)
+    M, ctx, widths = 154, 128, (64, 128, 64)
+    KV = 2 * sum(widths)
+    n_ad = 2 * len(widths)
+    R = n_ad * r
+    blk, off = [], [0]
+    for i, w in enumerate(widths):
+        blk += [2 * i] * w + [2 * i + 1] * w
+        off += [off[-1] + w, off[-1] + 2 * w]
+    blk_t = torch.tensor(blk, dtype=torch.int32, device=dev)
+    off_t = torch.tensor(off, dtype=torch.int32, device=dev)
+    ehs = torch.randn(M, ctx, device=dev, generator=g).to(F16)
+    kv0 = torch.randn(M, KV, device=dev, generator=g).to(F16)
+    A = (torch.randn(R, ctx, device=dev, generator=g) / r).requires_grad_(True)
+    Bm = (0.05 * torch.randn(KV, r, device=dev, generator=g)).requires_grad_(True)
+    dkv = torch.randn(M, KV, device=dev, generator=g).to(F16)
+    scaling = 1.5
+    # reference: per adapter, kv[:, cols] += scaling * (ehs A_a^T) B_a^T
+    e32 = ehs.float().requires_grad_(True)
+    parts = []
+    for a in range(n_ad):
+        lo, hi = off[a], off[a + 1]
+        parts.append(scaling * (e32 @ A[a * r:(a + 1) * r].t()) @ Bm[lo:hi].t())
+    ref = kv0.float() + torch.cat(parts, 1)
+    ref.backward(dkv.float())
+    kv = kv0.clone()
+    Z = ops.unet_lora_fwd(ehs, A.detach(), Bm.detach(), blk_t, kv, r, scaling)
+    assert relerr(kv, ref) < 2e-3
+    torch.testing.assert_close(Z, ehs.float() @ A.detach().t(), rtol=1e-4, atol=1e-4)
+    dA = torch.full_like(A, 0.25)  # accumulating outputs
+    dB = torch.full_like(Bm, -0.5)
+    d_ehs = torch.ones(M, ctx, device=dev)
+    ops.unet_lora_bwd(dkv, ehs, A.detach(), Bm.detach(), Z, blk_t, off_t, dA, dB, d_ehs, r, scaling)
+    torch.testing.assert_close(dA - 0.25, A.grad, rtol=2e-4, atol=2e-4 * A.grad.abs().max().item())
+    torch.testing.assert_close(dB + 0.5, Bm.grad, rtol=2e-4, atol=2e-4 * Bm.grad.abs().max().item())
+    torch.testing.assert_close(d_ehs - 1.0, e32.grad, rtol=2e-4, atol=2e-4 * e32.grad.abs().max().item())

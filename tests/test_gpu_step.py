@@ -465,3 +465,46 @@ def test_empty_prompt_batch_gives_zero_instance_gradient():
     ids[:, 0] = synthetic.BOS
     tr.forward_backward(bt["latents"], bt["noise"], bt["timesteps"], ids, None)
     assert torch.count_nonzero(tr.te.state.grads) == 0
+
+
+
+def test_step_unet_cross_kv_lora_vs_oracle():
+    """--unet_params_to_train crossattn_kv (train_textboost.py:712-721, 838-841): LoRA on attn2.to_k / to_v of every
+    cross-attention, third optimiser group (LoRA learning rate, not clipped).  The reference's fp16 policy cannot run
+    the mode (GradScaler.unscale_ on fp16 adapter tensors), so it is tied to the bf16 policy: under fp16 the trainer
+    refuses it; under the bf16 re-run of this file (tests/test_gpu_bf16_policy.py) the step is compared with the
+    oracle, whose UNet carries the same adapters (oracle/unet_ref.add_cross_kv_lora)."""
+    from oracle import harness
+    from textboost_b200 import synthetic
+    from textboost_b200.precision import POLICY
+    kw = dict(seed=1, n_added=2, lora_b_std=0.02, keep_sd=True, learning_rate=1e-4, unet_lora_r=4)
+    if POLICY.name != "bf16":
+        with pytest.raises(NotImplementedError, match="bf16"):
+            synthetic.build_trainer("tiny", dev, **kw)
+        return
+    tr = synthetic.build_trainer("tiny", dev, **kw)
+    kvl = tr.unet.kv_lora
+    assert kvl.n_adapters == 2 * len(tr.unet._attns) and tr.opt_unet is not None
+    V = tr.synthetic["clip_cfg"].vocab_size
+    bt = synthetic.batch(3, 16, 3, V, dev)
+    bt["input_ids"][1, 4] = V + 1
+    before = kvl.params.clone()
+    r = harness.compare_step(tr, bt)
+    print({k: v for k, v in r.items() if isinstance(v, float)})
+    assert abs(r["loss"] - r["loss_ref"]) < 2e-3 * TOLX * abs(r["loss_ref"])
+    assert r["pred_rel"] < 4e-3 * TOLX
+    assert r["lora_grad_rel_l2"] < 5e-3 * TOLX and r["row_grad_rel"] < 5e-3 * TOLX
+    assert r["unet_lora_grad_norm_ref"] > 0
+    assert r["unet_lora_grad_rel_l2"] < 5e-3 * TOLX and r["unet_lora_grad_cos"] > 1 - 1e-5 * TOLX ** 2
+    # Adam's first step is lr * sign(g) (not clipped, :1128-1133 clip the text encoder only) plus the weight decay
+    assert r["unet_lora_param_max_abs_diff"] <= 2.1 * tr.lr
+    assert (kvl.params - before).abs().max().item() > 0.5 * tr.lr
+    assert torch.count_nonzero(kvl.grads) == 0  # consumed and zeroed by the optimiser call
+    # the captured graph carries the adapter's forward, backward and optimiser call
+    args = (bt["latents"], bt["noise"], bt["timesteps"], bt["input_ids"], bt["prior_ids"])
+    replay = tr.capture(*args, warmup=0)
+    l0 = None
+    for _ in range(6):
+        loss = replay(*args).item()
+        l0 = loss if l0 is None else l0
+    assert loss == loss and loss < l0 and tr.opt_unet.state[4].item() == 7 and tr.opt_state[8].item() == 0

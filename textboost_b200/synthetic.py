@@ -225,13 +225,19 @@ def model_configs(model: str):
 
 def build_trainer(model: str = "sd15", device="cuda", seed: int = 42, n_added: int = 1, lora_r: int = 4,
                   kpl_weight: float = 0.1, lora_b_std: float = 0.0, keep_sd: bool = False,
-                  lora_targets=("q_proj", "k_proj", "v_proj"), lora_alpha=None, **trainer_kw) -> TextBoostTrainer:
+                  lora_targets=("q_proj", "k_proj", "v_proj"), lora_alpha=None, unet_lora_r: int = 0,
+                  **trainer_kw) -> TextBoostTrainer:
     """Random-init TextBoost trainer.  n_added rows are appended to the vocabulary and initialised from an
     existing row (utils.add_token, textboost/utils.py:117-166).  keep_sd=True stashes the generated
     state dicts on ``trainer.synthetic`` so a checker can rebuild the same model elsewhere."""
     ucfg, ccfg = model_configs(model)
     usd = random_unet_sd(ucfg, device, seed)
     unet = UNetEngine(ucfg, usd)
+    if unet_lora_r:  # --unet_params_to_train crossattn_kv (bf16 policy only, see TextBoostTrainer)
+        kvl = unet.add_cross_kv_lora(unet_lora_r, seed=seed + 5)
+        if lora_b_std > 0:
+            g = torch.Generator(device=device).manual_seed(seed + 6)
+            kvl.B().copy_(lora_b_std * torch.randn(kvl.B().shape, generator=g, device=device))
     csd = random_clip_sd(ccfg, ccfg.vocab_size, device, seed + 1)
     null = torch.randn((ccfg.max_position_embeddings, ccfg.hidden_size),
                        generator=torch.Generator().manual_seed(seed + 2))

@@ -139,14 +139,14 @@ def _unsupported(args):
     if args.with_image_prior and (args.latents_file or args.synthetic_data):
         raise ValueError("--with_image_prior takes its class images from --class_data_dir through the image front "
                          "end: it cannot be combined with --latents_file / --synthetic_data")
-    if args.unet_params_to_train != "none":
+    if args.unet_params_to_train == "crossattn_kv" and args.lora_rank > 0 and args.mixed_precision != "bf16":
         # train_textboost.py:711-720 adds LoRA to attn2.to_k / to_v, then :937 casts the WHOLE UNet -- adapter included --
-        # to weight_dtype.  Under --mixed_precision fp16 the trainable tensors are fp16 and
-        # accelerate's clip_grad_norm_ -> GradScaler.unscale_ raises "Attempting to unscale FP16 gradients": the mode
-        # only runs in the reference's fp32 policy, which is outside this path.
-        raise NotImplementedError("--unet_params_to_train crossattn_kv: the UNet is frozen on this path; in the "
-                                  "reference the mode needs --mixed_precision no (its fp16 path fails in "
-                                  "GradScaler.unscale_ on the fp16 adapter tensors)")
+        # to weight_dtype.  Under --mixed_precision fp16 the trainable tensors are fp16 and accelerate's
+        # clip_grad_norm_ -> GradScaler.unscale_ raises "Attempting to unscale FP16 gradients": the mode only runs in
+        # the reference's bf16 policy (no GradScaler: built here) and its fp32 policy (not built).
+        raise NotImplementedError("--unet_params_to_train crossattn_kv needs --mixed_precision bf16: the reference's "
+                                  "fp16 path fails in GradScaler.unscale_ on the fp16 adapter tensors, and fp32 "
+                                  "(--mixed_precision no) is not built")
     if args.lora_rank < 0:
         raise ValueError("--lora_rank must be >= 0")
     if args.gradient_accumulation_steps < 1:
@@ -298,10 +298,25 @@ def save_learned_embeddings(text_encoder, added_tokens, aug_token_dict, director
 
 def save_checkpoint(trainer, text_encoder, step, directory, gen_state):
     os.makedirs(directory, exist_ok=True)
-    torch.save({"step": step, "params": trainer.te.state.params.detach().cpu(),
-                "optimizer": {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in trainer.opt.state_dict().items()},
-                "generator": gen_state}, os.path.join(directory, "state.pt"))
+    st = {"step": step, "params": trainer.te.state.params.detach().cpu(),
+          "optimizer": {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in trainer.opt.state_dict().items()},
+          "generator": gen_state}
+    if trainer.opt_unet is not None:  # --unet_params_to_train crossattn_kv: the third parameter group
+        st["unet_lora_params"] = trainer.opt_unet.params.detach().cpu()
+        st["unet_optimizer"] = {k: (v.cpu() if torch.is_tensor(v) else v)
+                                for k, v in trainer.opt_unet.state_dict().items()}
+        save_unet_lora(trainer.unet.kv_lora, directory)  # the hook's LoraLoaderMixin.save_lora_weights (:753-778)
+    torch.save(st, os.path.join(directory, "state.pt"))
     text_encoder.save_pretrained(os.path.join(directory, "text_encoder"))
+
+
+def save_unet_lora(kv_lora, directory):
+    """The UNet adapter as ``pytorch_lora_weights.safetensors`` with the ``unet.`` key prefix of
+    LoraLoaderMixin.save_lora_weights (train_textboost.py:753-778): "unet.<module>.lora_A.weight" / "lora_B.weight"."""
+    from safetensors.torch import save_file
+    os.makedirs(directory, exist_ok=True)
+    save_file({"unet." + k: v.cpu().contiguous() for k, v in kv_lora.state_dict().items()},
+              os.path.join(directory, "pytorch_lora_weights.safetensors"))
 
 
 def load_checkpoint(trainer, directory, device):
@@ -309,6 +324,10 @@ def load_checkpoint(trainer, directory, device):
     st = torch.load(os.path.join(directory, "state.pt"), map_location="cpu", weights_only=True)
     trainer.te.state.params.copy_(st["params"].to(device))
     trainer.opt.load_state_dict({k: (v.to(device) if torch.is_tensor(v) else v) for k, v in st["optimizer"].items()})
+    if trainer.opt_unet is not None:
+        trainer.opt_unet.params.copy_(st["unet_lora_params"].to(device))
+        trainer.opt_unet.load_state_dict({k: (v.to(device) if torch.is_tensor(v) else v)
+                                          for k, v in st["unet_optimizer"].items()})
     return st["step"], st["generator"]
 
 
@@ -423,6 +442,11 @@ def main(args):
     text_encoder.to(device)
     unet.to(device, dtype=weight_dtype)
     original_text_encoder.to(device, dtype=weight_dtype)
+    unet_lora = None
+    if args.unet_params_to_train == "crossattn_kv" and args.lora_rank > 0:  # train_textboost.py:712-721
+        unet_lora = unet.engine.add_cross_kv_lora(args.lora_rank, alpha=args.lora_rank,
+                                                  seed=(args.seed if args.seed is not None else 0) + 17)
+        logger.info(f"Added LoRA to U-Net: {unet_lora.n_adapters} adapters, {unet_lora.params.numel()} floats")
     trainer = TextBoostTrainer(
         unet.engine, text_encoder.engine, original_text_encoder.engine if args.kpl_weight > 0 else None,
         learning_rate=args.learning_rate, emb_learning_rate=args.emb_learning_rate, adam_beta1=args.adam_beta1,
@@ -584,6 +608,10 @@ def main(args):
             text_encoder.to(torch.float32).save_pretrained(os.path.join(args.output_dir, "text_encoder"),
                                                            safe_serialization=not args.no_safe_serialization)
         save_learned_embeddings(text_encoder, added_tokens, aug_token_dict, args.output_dir)
+        if unet_lora is not None:
+            # the reference writes the whole peft-wrapped UNet (unet.save_pretrained, :1237-1239); the frozen base is
+            # the checkpoint the run started from, so only the adapter is written here
+            save_unet_lora(unet_lora, os.path.join(args.output_dir, "unet"))
     tracker.close()
     _st = trainer.opt_state.tolist()
     RUN_INFO.update(precision=precision.POLICY.name, loss_scale=_st[0], skipped_steps=int(_st[8]))
