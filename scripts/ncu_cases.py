@@ -204,6 +204,26 @@ def case_geglu():
     return run
 
 
+def case_unet_lora():   # --unet_params_to_train crossattn_kv: 32 rank-4 adapters on the fused K/V projection, SD-1.5
+    M, ctx, r = 616, 768, 4
+    widths = [320, 320, 640, 640, 1280, 1280, 1280] + [1280] * 3 + [640] * 3 + [320] * 3
+    KV, n_ad = 2 * sum(widths), 2 * len(widths)
+    blk, off = [], [0]
+    for i, w in enumerate(widths):
+        blk += [2 * i] * w + [2 * i + 1] * w
+        off += [off[-1] + w, off[-1] + 2 * w]
+    blk_t = torch.tensor(blk, dtype=torch.int32, device=dev)
+    off_t = torch.tensor(off, dtype=torch.int32, device=dev)
+    ehs, kv, dkv = rnd(M, ctx), rnd(M, KV), rnd(M, KV, s=0.01)
+    A, Bm = rnd(n_ad * r, ctx, dtype=torch.float32, s=0.25), rnd(KV, r, dtype=torch.float32, s=0.02)
+    dA, dB, d_ehs = torch.zeros_like(A), torch.zeros_like(Bm), torch.zeros(M, ctx, device=dev)
+
+    def run():
+        Z = ops.unet_lora_fwd(ehs, A, Bm, blk_t, kv, r, 1.0)
+        ops.unet_lora_bwd(dkv, ehs, A, Bm, Z, blk_t, off_t, dA, dB, d_ehs, r, 1.0)
+    return run
+
+
 CASES = {k[5:]: v for k, v in globals().items() if k.startswith("case_")}
 TIME = "--time" in sys.argv
 if TIME:

@@ -450,7 +450,7 @@ def test_data_parallel_identity_on_the_cuda_path():
     # Adam's first step is ~lr*sign(g): compare the parameter UPDATES, away from g ~ 0
     d_dp = ra.te.state.params - rb.te.state.params
     d_full = full.te.state.params - rb.te.state.params
-    big = g_full.abs() > 1e-3 * g_full.abs().max()
+    big = g_full.abs() > 1e-3 * TOLX ** 2 * g_full.abs().max()  # sign(g) is only stable above the 16-bit noise floor
     assert ((d_dp - d_full)[big].abs().max() / d_full[big].abs().max()).item() < 2e-2 * TOLX
     assert abs(ra.opt_state[7].item() - full.opt_state[7].item()) < 2e-3 * TOLX * full.opt_state[7].item()  # grad norm
 
