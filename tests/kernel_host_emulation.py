@@ -604,7 +604,8 @@ static void emu_launch_serial(dim3 grid, dim3 block, const std::function<void()>
 }
 """
 
-ABI_FILES = ["norm.cu", "elementwise.cu", "clip.cu", "optim.cu", "vae.cu", "sampler.cu", "image.cu", "augment.cu"]
+ABI_FILES = ["norm.cu", "elementwise.cu", "clip.cu", "optim.cu", "vae.cu", "sampler.cu", "image.cu", "augment.cu",
+             "unet_lora.cu"]
 _lib_abi = None
 
 

@@ -371,3 +371,57 @@ def test_lora_entry_points(abi, nblk, tmask, r):
     with pytest.raises(RuntimeError, match="tb_lora_grad"):
         C.call("tb_lora_grad", C.ptr(dY), C.ptr(y_ext), C.ptr(dA_ext), ld, C.ptr(dB), C.ptr(dA), M, nblk, tmask, D, 17,
                0.5, C.stream_ptr())
+
+
+@pytest.mark.parametrize("r", [4, 5])
+def test_unet_cross_kv_lora_entry_points(abi, r):
+    """tb_unet_lora_fwd / tb_unet_lora_bwd (peft LoRA on attn2.to_k / to_v of all blocks side by side,
+    train_textboost.py:712-721) against autograd on the same fp32 adapters; then the third parameter group
+    (optim.FlatAdamW: the LoRA learning rate, weight decay, no clipping, :838-841) against torch.optim.AdamW."""
+    from textboost_b200 import ops
+    from textboost_b200.optim import FlatAdamW
+    g = torch.Generator().manual_seed(3 + r)
+    M, ctx, widths = 9, 40, (8, 24, 16)
+    KV, n_ad = 2 * sum(widths), 2 * len(widths)
+    blk, off = [], [0]
+    for i, w in enumerate(widths):
+        blk += [2 * i] * w + [2 * i + 1] * w
+        off += [off[-1] + w, off[-1] + 2 * w]
+    blk_t, off_t = torch.tensor(blk, dtype=torch.int32), torch.tensor(off, dtype=torch.int32)
+    ehs, kv0, dkv = _h(M, ctx, seed=1), _h(M, KV, seed=2), _h(M, KV, seed=3)
+    params = torch.cat([(torch.randn(n_ad * r * ctx, generator=g) / r), 0.05 * torch.randn(KV * r, generator=g)])
+    A = params[:n_ad * r * ctx].view(n_ad * r, ctx).clone().requires_grad_(True)
+    Bm = params[n_ad * r * ctx:].view(KV, r).clone().requires_grad_(True)
+    e32 = ehs.float().requires_grad_(True)
+    ref = kv0.float() + torch.cat([1.5 * (e32 @ A[a * r:(a + 1) * r].t()) @ Bm[off[a]:off[a + 1]].t()
+                                   for a in range(n_ad)], 1)
+    ref.backward(dkv.float())
+    kv = kv0.clone()
+    Z = ops.unet_lora_fwd(ehs, A.detach(), Bm.detach(), blk_t, kv, r, 1.5)
+    _close(kv, ref.detach(), 2e-3)
+    _close(Z, ehs.float() @ A.detach().t(), 1e-5)
+    grads = torch.zeros_like(params)
+    dA, dB = grads[:A.numel()].view_as(A), grads[A.numel():].view_as(Bm)
+    d_ehs = torch.ones(M, ctx)
+    ops.unet_lora_bwd(dkv, ehs, A.detach(), Bm.detach(), Z, blk_t, off_t, dA, dB, d_ehs, r, 1.5)
+    _close(dA, A.grad, 1e-5)
+    _close(dB, Bm.grad, 1e-5)
+    _close(d_ehs - 1.0, e32.grad, 1e-5)
+    from textboost_b200 import _cabi as C
+    with pytest.raises(RuntimeError, match="bad args"):  # rank above the kernels' register budget (16)
+        C.call("tb_unet_lora_fwd", C.ptr(ehs), C.ptr(A.detach()), C.ptr(Bm.detach()), C.ptr(blk_t), C.ptr(Z), C.ptr(kv),
+               M, ctx, KV, n_ad, 17, 1.0, C.stream_ptr())
+    # the optimiser call of the third group: two steps against torch.optim.AdamW on the same gradients
+    p_ref = params.clone().requires_grad_(True)
+    ref_opt = torch.optim.AdamW([p_ref], lr=1e-3, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)
+    ours_p = params.clone()
+    opt = FlatAdamW(ours_p, grads, lr=1e-3)
+    for it in range(2):
+        if it:
+            grads.copy_(torch.randn(grads.shape, generator=g))
+        p_ref.grad = grads.clone()
+        ref_opt.step()
+        opt.step()
+        assert torch.count_nonzero(grads) == 0
+        torch.testing.assert_close(ours_p, p_ref.detach(), rtol=1e-5, atol=1e-7)
+    assert opt.state[0].item() == 1.0 and opt.state[4].item() == 2 and opt.state[8].item() == 0

@@ -21,15 +21,15 @@ constexpr int UL_RMAX = 16;  // rank per adapter
 // Z[m, q] = sum_c ehs[m, c] A[q, c]: one CTA per text row (cached in shared memory as fp32), one warp per q
 __global__ void __launch_bounds__(256)
 unet_lora_down_kernel(const half_t* __restrict__ ehs, const float* __restrict__ A, float* __restrict__ Z, int ctx, int R) {
-  extern __shared__ float srow[];
+  extern __shared__ float smf[];  // the text row as fp32
   const int m = blockIdx.x;
-  for (int c = threadIdx.x; c < ctx; c += blockDim.x) srow[c] = h2f(ehs[(size_t)m * ctx + c]);
+  for (int c = threadIdx.x; c < ctx; c += blockDim.x) smf[c] = h2f(ehs[(size_t)m * ctx + c]);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   for (int q = warp; q < R; q += nwarp) {
     const float* a = A + (size_t)q * ctx;
     float acc = 0.f;
-    for (int c = lane; c < ctx; c += 32) acc += srow[c] * a[c];
+    for (int c = lane; c < ctx; c += 32) acc += smf[c] * a[c];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) Z[(size_t)m * R + q] = acc;
@@ -94,7 +94,7 @@ unet_lora_grad_b_kernel(const half_t* __restrict__ dkv, const float* __restrict_
                         float* __restrict__ dB, int M, int KV, int R, int r, float s, int rows_per_cta) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= KV) return;
-  const int m0 = blockIdx.y * rows_per_cta, m1 = min(M, m0 + rows_per_cta);
+  const int m0 = blockIdx.y * rows_per_cta, m1 = m0 + rows_per_cta < M ? m0 + rows_per_cta : M;
   const int zo = blk[j] * r;
   float acc[UL_RMAX];
 #pragma unroll
