@@ -81,3 +81,8 @@ def test_sass_uses_blackwell_tensor_and_tma_paths(built_lib):
     sass = subprocess.run([cuobjdump, "-sass", built_lib], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass and "LDTM" in sass and "UTMALDG" in sass
     assert "HMMA.16816" not in sass  # no legacy mma.sync path
+    # the bf16 build: same tensor / TMA paths, bf16 conversions instead of fp16 ones in the epilogues and SIMT kernels
+    from textboost_b200 import build
+    sass16 = subprocess.run([cuobjdump, "-sass", build.VARIANTS["bf16"][0]], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass16 and "LDTM" in sass16 and "UTMALDG" in sass16 and "HMMA.16816" not in sass16
+    assert "F2FP.BF16" in sass16 and "F2FP.BF16" not in sass and "F2FP.F16" in sass
