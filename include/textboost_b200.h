@@ -297,7 +297,8 @@ int tb_lora_dx(void* dA_ext, int64_t ld, const float* A, int M, int D, int R, vo
  * adapters on attn2.to_k / attn2.to_v of every transformer block, third optimiser group).  The blocks' K | V
  * projections are one fused GEMM over the text states (KV output columns); the n_adapters adapters are stacked:
  * A fp32 [n_adapters*r, ctx], B fp32 [KV, r] (row j = lora_B row of fused output column j), blk int32 [KV] = adapter of
- * column j (blk[j] == blk[j+1] for even j), off int32 [n_adapters+1] = column range of each adapter.
+ * column j, off int32 [n_adapters+1] = column range of each adapter (multiples of 8: a 16-byte vector of K/V columns
+ * never straddles two adapters; KV % 8 == 0).
  * fwd: Z (fp32 [M, n_adapters*r], kept for the backward) = ehs A^T;  kv[m, j] += scaling * Z[m, blk[j] r ..] . B[j, :]
  * bwd: dZ (fp32 scratch [M, n_adapters*r]) = scaling * dkv B per adapter;  dB += scaling * dkv^T Z;  dA += dZ^T ehs;
  *      d_ehs (fp32 [M, ctx]) += dZ A.  ehs, kv, dkv are 16-bit [M, ctx] / [M, KV] contiguous. */

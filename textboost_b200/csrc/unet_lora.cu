@@ -18,43 +18,75 @@ namespace tb {
 
 constexpr int UL_RMAX = 16;  // rank per adapter
 
-// Z[m, q] = sum_c ehs[m, c] A[q, c]: one CTA per text row (cached in shared memory as fp32), one warp per q
+// Z[m, q] = sum_c ehs[m, c] A[q, c]: one CTA per UL_DOWN_ROWS text rows (cached in shared memory as fp32), one warp per
+// q -- each A row is read once per CTA and used for all its text rows
+constexpr int UL_DOWN_ROWS = 4;
 __global__ void __launch_bounds__(256)
-unet_lora_down_kernel(const half_t* __restrict__ ehs, const float* __restrict__ A, float* __restrict__ Z, int ctx, int R) {
-  extern __shared__ float smf[];  // the text row as fp32
-  const int m = blockIdx.x;
-  for (int c = threadIdx.x; c < ctx; c += blockDim.x) smf[c] = h2f(ehs[(size_t)m * ctx + c]);
+unet_lora_down_kernel(const half_t* __restrict__ ehs, const float* __restrict__ A, float* __restrict__ Z, int M, int ctx,
+                      int R) {
+  extern __shared__ float smf[];  // [UL_DOWN_ROWS][ctx]
+  const int m0 = blockIdx.x * UL_DOWN_ROWS;
+  for (int i = threadIdx.x; i < UL_DOWN_ROWS * ctx; i += blockDim.x) {
+    const int m = m0 + i / ctx;
+    smf[i] = m < M ? h2f(ehs[(size_t)m * ctx + i % ctx]) : 0.f;
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   for (int q = warp; q < R; q += nwarp) {
     const float* a = A + (size_t)q * ctx;
-    float acc = 0.f;
-    for (int c = lane; c < ctx; c += 32) acc += smf[c] * a[c];
+    float acc[UL_DOWN_ROWS];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) Z[(size_t)m * R + q] = acc;
+    for (int i = 0; i < UL_DOWN_ROWS; ++i) acc[i] = 0.f;
+    for (int c = lane; c < ctx; c += 32) {
+      const float av = a[c];
+#pragma unroll
+      for (int i = 0; i < UL_DOWN_ROWS; ++i) acc[i] += smf[i * ctx + c] * av;
+    }
+#pragma unroll
+    for (int i = 0; i < UL_DOWN_ROWS; ++i) {
+      float v = acc[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && m0 + i < M) Z[(size_t)(m0 + i) * R + q] = v;
+    }
   }
 }
 
-// kv[m, j] += s * Z[m, blk[j] r ..] . B[j, :]: two adjacent columns per thread (one packed load / store)
+// The three kernels below stream the [M, KV] 16-bit tensor once, eight adjacent columns (one 16-byte vector) per
+// thread; adapter column ranges are multiples of 8 (channel counts are), so a vector never straddles two adapters.
+__device__ __forceinline__ void ul_unpack8(const uint4& q, float* f) {
+  const half2_t* h = reinterpret_cast<const half2_t*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 v = h22f2(h[i]);
+    f[2 * i] = v.x;
+    f[2 * i + 1] = v.y;
+  }
+}
+
+// kv[m, j] += s * Z[m, blk[j] r ..] . B[j, :]
 __global__ void __launch_bounds__(256)
 unet_lora_up_kernel(half_t* __restrict__ kv, const float* __restrict__ Z, const float* __restrict__ B,
                     const int* __restrict__ blk, int KV, int R, int r, float s) {
   const int m = blockIdx.y;
-  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (j >= KV) return;
-  half2_t* p = reinterpret_cast<half2_t*>(kv + (size_t)m * KV + j);
-  float2 v = h22f2(*p);
-  const float* z0 = Z + (size_t)m * R + blk[j] * r;
-  const float* z1 = Z + (size_t)m * R + blk[j + 1] * r;
-  float a0 = 0.f, a1 = 0.f;
-  for (int k = 0; k < r; ++k) {
-    a0 += z0[k] * B[(size_t)j * r + k];
-    a1 += z1[k] * B[(size_t)(j + 1) * r + k];
+  uint4* p = reinterpret_cast<uint4*>(kv + (size_t)m * KV + j);
+  float v[8];
+  ul_unpack8(*p, v);
+  const float* z = Z + (size_t)m * R + blk[j] * r;
+  const float* b = B + (size_t)j * r;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float a = 0.f;
+    for (int k = 0; k < r; ++k) a += z[k] * b[i * r + k];
+    v[i] += s * a;
   }
-  v.x += s * a0;
-  v.y += s * a1;
-  *p = ff2h2(v.x, v.y);
+  uint4 o;
+  half2_t* oh = reinterpret_cast<half2_t*>(&o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) oh[i] = ff2h2(v[2 * i], v[2 * i + 1]);
+  *p = o;
 }
 
 // dZ[m, a r + k] = s * sum_{j in [off[a], off[a+1])} dkv[m, j] B[j, k]: one CTA per (adapter, text row)
@@ -66,11 +98,15 @@ unet_lora_dz_kernel(const half_t* __restrict__ dkv, const float* __restrict__ B,
   float acc[UL_RMAX];
 #pragma unroll
   for (int k = 0; k < UL_RMAX; ++k) acc[k] = 0.f;
-  for (int j = off[a] + threadIdx.x; j < off[a + 1]; j += blockDim.x) {
-    const float g = h2f(dkv[(size_t)m * KV + j]);
+  for (int j = off[a] + threadIdx.x * 8; j < off[a + 1]; j += blockDim.x * 8) {
+    float g[8];
+    ul_unpack8(*reinterpret_cast<const uint4*>(dkv + (size_t)m * KV + j), g);
+    const float* b = B + (size_t)j * r;
 #pragma unroll
-    for (int k = 0; k < UL_RMAX; ++k)
-      if (k < r) acc[k] += g * B[(size_t)j * r + k];
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int k = 0; k < UL_RMAX; ++k)
+        if (k < r) acc[k] += g[i] * b[i * r + k];
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
@@ -88,38 +124,63 @@ unet_lora_dz_kernel(const half_t* __restrict__ dkv, const float* __restrict__ B,
         s * (red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]);
 }
 
-// dB[j, k] += s * sum_m dkv[m, j] Z[m, blk[j] r + k]: one thread per column j, the text rows split over blockIdx.y
+// dB[j, k] += s * sum_m dkv[m, j] Z[m, blk[j] r + k]: one thread per 8 columns, the text rows split over blockIdx.y.
+// RR = compile-time rank bound (accumulators stay in registers: 8 x RR floats)
+template <int RR>
 __global__ void __launch_bounds__(128)
 unet_lora_grad_b_kernel(const half_t* __restrict__ dkv, const float* __restrict__ Z, const int* __restrict__ blk,
                         float* __restrict__ dB, int M, int KV, int R, int r, float s, int rows_per_cta) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (j >= KV) return;
   const int m0 = blockIdx.y * rows_per_cta, m1 = m0 + rows_per_cta < M ? m0 + rows_per_cta : M;
   const int zo = blk[j] * r;
-  float acc[UL_RMAX];
+  float acc[8][RR];
 #pragma unroll
-  for (int k = 0; k < UL_RMAX; ++k) acc[k] = 0.f;
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int k = 0; k < RR; ++k) acc[i][k] = 0.f;
   for (int m = m0; m < m1; ++m) {
-    const float g = h2f(dkv[(size_t)m * KV + j]);
+    float g[8];
+    ul_unpack8(*reinterpret_cast<const uint4*>(dkv + (size_t)m * KV + j), g);
     const float* z = Z + (size_t)m * R + zo;
 #pragma unroll
-    for (int k = 0; k < UL_RMAX; ++k)
-      if (k < r) acc[k] += g * z[k];
+    for (int k = 0; k < RR; ++k) {
+      if (k < r) {
+        const float zk = z[k];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i][k] += g[i] * zk;
+      }
+    }
   }
 #pragma unroll
-  for (int k = 0; k < UL_RMAX; ++k)
-    if (k < r) atomicAdd(dB + (size_t)j * r + k, s * acc[k]);
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int k = 0; k < RR; ++k)
+      if (k < r) atomicAdd(dB + (size_t)(j + i) * r + k, s * acc[i][k]);
 }
 
-// dA[q, c] += sum_m dZ[m, q] ehs[m, c]  and  d_ehs[m, c] += sum_q dZ[m, q] A[q, c]: one thread per context column c
+// dA[q, c] += sum_m dZ[m, q] ehs[m, c]  and  d_ehs[m, c] += sum_q dZ[m, q] A[q, c]: one thread per context column c.
+// grad_a: eight adapter rows q per thread (the ehs element is loaded once for the eight), text rows split into
+// n_chunks (folded into blockIdx.y) and combined with atomics (98 k outputs x 616 rows would otherwise be 384 CTAs of serial loops)
 __global__ void __launch_bounds__(256)
 unet_lora_grad_a_kernel(const float* __restrict__ dZ, const half_t* __restrict__ ehs, float* __restrict__ dA, int M,
-                        int ctx, int R) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x, q = blockIdx.y;
+                        int ctx, int R, int rows_per_cta, int n_chunks) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, q0 = (blockIdx.y / n_chunks) * 8;
   if (c >= ctx) return;
-  float acc = 0.f;
-  for (int m = 0; m < M; ++m) acc += dZ[(size_t)m * R + q] * h2f(ehs[(size_t)m * ctx + c]);
-  dA[(size_t)q * ctx + c] += acc;
+  const int m0 = (blockIdx.y % n_chunks) * rows_per_cta, m1 = m0 + rows_per_cta < M ? m0 + rows_per_cta : M;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int m = m0; m < m1; ++m) {
+    const float e = h2f(ehs[(size_t)m * ctx + c]);
+    const float* dz = dZ + (size_t)m * R + q0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (q0 + i < R) acc[i] += dz[i] * e;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (q0 + i < R) atomicAdd(dA + (size_t)(q0 + i) * ctx + c, acc[i]);
 }
 __global__ void __launch_bounds__(256)
 unet_lora_dehs_kernel(const float* __restrict__ dZ, const float* __restrict__ A, float* __restrict__ d_ehs, int ctx,
@@ -136,7 +197,7 @@ unet_lora_dehs_kernel(const float* __restrict__ dZ, const float* __restrict__ A,
 using namespace tb;
 
 static int unet_lora_args_ok(int M, int ctx, int KV, int n_adapters, int r) {
-  return M > 0 && ctx > 0 && ctx <= 4096 && KV > 0 && KV % 2 == 0 && n_adapters > 0 && r >= 1 && r <= UL_RMAX;
+  return M > 0 && ctx > 0 && ctx <= 2048 && KV > 0 && KV % 8 == 0 && n_adapters > 0 && r >= 1 && r <= UL_RMAX;
 }
 
 extern "C" int tb_unet_lora_fwd(const void* ehs, const float* A, const float* B, const int32_t* blk, float* Z,
@@ -148,9 +209,10 @@ extern "C" int tb_unet_lora_fwd(const void* ehs, const float* A, const float* B,
   TB_REQUIRE(ehs && A && B && blk && Z && kv && unet_lora_args_ok(M, ctx, KV, n_adapters, r), TB_E_ARG,
              "tb_unet_lora_fwd: bad args (M=%d ctx=%d KV=%d adapters=%d r=%d)", M, ctx, KV, n_adapters, r);
   const int R = n_adapters * r;
-  unet_lora_down_kernel<<<M, 256, ctx * sizeof(float), st>>>((const half_t*)ehs, A, Z, ctx, R);
+  unet_lora_down_kernel<<<(M + UL_DOWN_ROWS - 1) / UL_DOWN_ROWS, 256, UL_DOWN_ROWS * ctx * sizeof(float), st>>>(
+      (const half_t*)ehs, A, Z, M, ctx, R);
   if ((rc = check_launch("unet_lora_down_kernel"))) return rc;
-  unet_lora_up_kernel<<<dim3((KV / 2 + 255) / 256, M), 256, 0, st>>>((half_t*)kv, Z, B, blk, KV, R, r, scaling);
+  unet_lora_up_kernel<<<dim3((KV / 8 + 255) / 256, M), 256, 0, st>>>((half_t*)kv, Z, B, blk, KV, R, r, scaling);
   return check_launch("unet_lora_up_kernel");
 }
 
@@ -168,10 +230,18 @@ extern "C" int tb_unet_lora_bwd(const void* dkv, const void* ehs, const float* A
   unet_lora_dz_kernel<<<dim3(n_adapters, M), 128, 0, st>>>((const half_t*)dkv, B, off, dZ, KV, R, r, scaling);
   if ((rc = check_launch("unet_lora_dz_kernel"))) return rc;
   const int rows_per_cta = 80;
-  unet_lora_grad_b_kernel<<<dim3((KV + 127) / 128, (M + rows_per_cta - 1) / rows_per_cta), 128, 0, st>>>(
-      (const half_t*)dkv, Z, blk, dB, M, KV, R, r, scaling, rows_per_cta);
+  const dim3 gb((KV / 8 + 127) / 128, (M + rows_per_cta - 1) / rows_per_cta);
+  if (r <= 4)
+    unet_lora_grad_b_kernel<4><<<gb, 128, 0, st>>>((const half_t*)dkv, Z, blk, dB, M, KV, R, r, scaling, rows_per_cta);
+  else if (r <= 8)
+    unet_lora_grad_b_kernel<8><<<gb, 128, 0, st>>>((const half_t*)dkv, Z, blk, dB, M, KV, R, r, scaling, rows_per_cta);
+  else
+    unet_lora_grad_b_kernel<UL_RMAX><<<gb, 128, 0, st>>>((const half_t*)dkv, Z, blk, dB, M, KV, R, r, scaling,
+                                                         rows_per_cta);
   if ((rc = check_launch("unet_lora_grad_b_kernel"))) return rc;
-  unet_lora_grad_a_kernel<<<dim3((ctx + 255) / 256, R), 256, 0, st>>>(dZ, (const half_t*)ehs, dA, M, ctx, R);
+  const int rows_a = 64, chunks_a = (M + rows_a - 1) / rows_a;
+  unet_lora_grad_a_kernel<<<dim3((ctx + 255) / 256, ((R + 7) / 8) * chunks_a), 256, 0, st>>>(
+      dZ, (const half_t*)ehs, dA, M, ctx, R, rows_a, chunks_a);
   if ((rc = check_launch("unet_lora_grad_a_kernel"))) return rc;
   unet_lora_dehs_kernel<<<dim3((ctx + 255) / 256, M), 256, 0, st>>>(dZ, A, d_ehs, ctx, R);
   return check_launch("unet_lora_dehs_kernel");

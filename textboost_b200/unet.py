@@ -287,6 +287,7 @@ class CrossKVLora:
         self.names = []  # diffusers / peft module path of every adapter
         for i, a in enumerate(engine._attns):
             Cc = a.kv2.w.shape[0] // 2
+            assert Cc % 8 == 0 and a.kv_off % 8 == 0  # the kernels walk K/V in 8-column vectors, one adapter each
             blk[a.kv_off:a.kv_off + Cc] = 2 * i
             blk[a.kv_off + Cc:a.kv_off + 2 * Cc] = 2 * i + 1
             off += [a.kv_off + Cc, a.kv_off + 2 * Cc]
