@@ -64,64 +64,111 @@ __device__ __forceinline__ void ul_unpack8(const uint4& q, float* f) {
   }
 }
 
-// kv[m, j] += s * Z[m, blk[j] r ..] . B[j, :]
-__global__ void __launch_bounds__(256)
-unet_lora_up_kernel(half_t* __restrict__ kv, const float* __restrict__ Z, const float* __restrict__ B,
-                    const int* __restrict__ blk, int KV, int R, int r, float s) {
-  const int m = blockIdx.y;
-  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  if (j >= KV) return;
-  uint4* p = reinterpret_cast<uint4*>(kv + (size_t)m * KV + j);
-  float v[8];
-  ul_unpack8(*p, v);
-  const float* z = Z + (size_t)m * R + blk[j] * r;
-  const float* b = B + (size_t)j * r;
+// Both kernels keep the 8 x r lora_B floats of a thread's column vector in registers (float4 loads: 8r contiguous
+// floats, 32r-byte aligned) and reuse them over ROWS text rows: lora_B is read M / ROWS times instead of M times.
+// RR = compile-time bound of the rank (register arrays), ROWS x RR <= 32.
+template <int RR>
+__device__ __forceinline__ void ul_load_b(const float* __restrict__ B, int j, int r, float (&bb)[8][RR]) {
+  const float4* src = reinterpret_cast<const float4*>(B + (size_t)j * r);
+  float flat[8 * RR];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float a = 0.f;
-    for (int k = 0; k < r; ++k) a += z[k] * b[i * r + k];
-    v[i] += s * a;
+  for (int q = 0; q < 2 * RR; ++q) {
+    if (q < 2 * r) {
+      const float4 t = src[q];
+      flat[4 * q] = t.x; flat[4 * q + 1] = t.y; flat[4 * q + 2] = t.z; flat[4 * q + 3] = t.w;
+    }
   }
-  uint4 o;
-  half2_t* oh = reinterpret_cast<half2_t*>(&o);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) oh[i] = ff2h2(v[2 * i], v[2 * i + 1]);
-  *p = o;
-}
-
-// dZ[m, a r + k] = s * sum_{j in [off[a], off[a+1])} dkv[m, j] B[j, k]: one CTA per (adapter, text row)
-__global__ void __launch_bounds__(128)
-unet_lora_dz_kernel(const half_t* __restrict__ dkv, const float* __restrict__ B, const int* __restrict__ off,
-                    float* __restrict__ dZ, int KV, int R, int r, float s) {
-  __shared__ float red[4][UL_RMAX];
-  const int a = blockIdx.x, m = blockIdx.y;
-  float acc[UL_RMAX];
-#pragma unroll
-  for (int k = 0; k < UL_RMAX; ++k) acc[k] = 0.f;
-  for (int j = off[a] + threadIdx.x * 8; j < off[a + 1]; j += blockDim.x * 8) {
-    float g[8];
-    ul_unpack8(*reinterpret_cast<const uint4*>(dkv + (size_t)m * KV + j), g);
-    const float* b = B + (size_t)j * r;
+  if (r == RR) {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int k = 0; k < UL_RMAX; ++k)
-        if (k < r) acc[k] += g[i] * b[i * r + k];
+      for (int k = 0; k < RR; ++k) bb[i][k] = flat[i * RR + k];
+  } else {  // ranks between the template bounds: re-read the few floats with their true stride
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int k = 0; k < RR; ++k) bb[i][k] = k < r ? B[(size_t)(j + i) * r + k] : 0.f;
+  }
+}
+
+// kv[m, j] += s * Z[m, blk[j] r ..] . B[j, :]
+template <int RR, int ROWS>
+__global__ void __launch_bounds__(128)
+unet_lora_up_kernel(half_t* __restrict__ kv, const float* __restrict__ Z, const float* __restrict__ B,
+                    const int* __restrict__ blk, int M, int KV, int R, int r, float s) {
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (j >= KV) return;
+  float bb[8][RR];
+  ul_load_b<RR>(B, j, r, bb);
+  const int zo = blk[j] * r;
+  const int m0 = blockIdx.y * ROWS;
+#pragma unroll
+  for (int mi = 0; mi < ROWS; ++mi) {
+    const int m = m0 + mi;
+    if (m >= M) break;
+    uint4* p = reinterpret_cast<uint4*>(kv + (size_t)m * KV + j);
+    float v[8], z[RR];
+    ul_unpack8(*p, v);
+#pragma unroll
+    for (int k = 0; k < RR; ++k) z[k] = k < r ? Z[(size_t)m * R + zo + k] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < RR; ++k) a += z[k] * bb[i][k];
+      v[i] += s * a;
+    }
+    uint4 o;
+    half2_t* oh = reinterpret_cast<half2_t*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) oh[i] = ff2h2(v[2 * i], v[2 * i + 1]);
+    *p = o;
+  }
+}
+
+// dZ[m, a r + k] = s * sum_{j in [off[a], off[a+1])} dkv[m, j] B[j, k]: one CTA per (adapter, ROWS text rows)
+template <int RR, int ROWS>
+__global__ void __launch_bounds__(128)
+unet_lora_dz_kernel(const half_t* __restrict__ dkv, const float* __restrict__ B, const int* __restrict__ off,
+                    float* __restrict__ dZ, int M, int KV, int R, int r, float s) {
+  __shared__ float red[4][ROWS][RR];
+  const int a = blockIdx.x, m0 = blockIdx.y * ROWS;
+  float acc[ROWS][RR];
+#pragma unroll
+  for (int mi = 0; mi < ROWS; ++mi)
+#pragma unroll
+    for (int k = 0; k < RR; ++k) acc[mi][k] = 0.f;
+  for (int j = off[a] + threadIdx.x * 8; j < off[a + 1]; j += blockDim.x * 8) {
+    float bb[8][RR];
+    ul_load_b<RR>(B, j, r, bb);
+#pragma unroll
+    for (int mi = 0; mi < ROWS; ++mi) {
+      if (m0 + mi < M) {
+        float g[8];
+        ul_unpack8(*reinterpret_cast<const uint4*>(dkv + (size_t)(m0 + mi) * KV + j), g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int k = 0; k < RR; ++k) acc[mi][k] += g[i] * bb[i][k];
+      }
+    }
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-  for (int k = 0; k < UL_RMAX; ++k) {
-    if (k < r) {
-      float v = acc[k];
+  for (int mi = 0; mi < ROWS; ++mi)
+#pragma unroll
+    for (int k = 0; k < RR; ++k) {
+      float v = acc[mi][k];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) red[warp][k] = v;
+      if (lane == 0) red[warp][mi][k] = v;
     }
-  }
   __syncthreads();
-  if (threadIdx.x < r)
-    dZ[(size_t)m * R + a * r + threadIdx.x] =
-        s * (red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]);
+  for (int t = threadIdx.x; t < ROWS * r; t += blockDim.x) {
+    const int mi = t / r, k = t % r;
+    if (m0 + mi < M)
+      dZ[(size_t)(m0 + mi) * R + a * r + k] = s * (red[0][mi][k] + red[1][mi][k] + red[2][mi][k] + red[3][mi][k]);
+  }
 }
 
 // dB[j, k] += s * sum_m dkv[m, j] Z[m, blk[j] r + k]: one thread per 8 columns, the text rows split over blockIdx.y.
@@ -212,7 +259,14 @@ extern "C" int tb_unet_lora_fwd(const void* ehs, const float* A, const float* B,
   unet_lora_down_kernel<<<(M + UL_DOWN_ROWS - 1) / UL_DOWN_ROWS, 256, UL_DOWN_ROWS * ctx * sizeof(float), st>>>(
       (const half_t*)ehs, A, Z, M, ctx, R);
   if ((rc = check_launch("unet_lora_down_kernel"))) return rc;
-  unet_lora_up_kernel<<<dim3((KV / 8 + 255) / 256, M), 256, 0, st>>>((half_t*)kv, Z, B, blk, KV, R, r, scaling);
+  const unsigned gx = (unsigned)((KV / 8 + 127) / 128);
+#define TB_UL_UP(RR, ROWS)                                                                                   \
+  unet_lora_up_kernel<RR, ROWS><<<dim3(gx, (M + ROWS - 1) / ROWS), 128, 0, st>>>((half_t*)kv, Z, B, blk, M, KV, R, r, \
+                                                                                 scaling)
+  if (r <= 4) TB_UL_UP(4, 8);
+  else if (r <= 8) TB_UL_UP(8, 4);
+  else TB_UL_UP(16, 2);
+#undef TB_UL_UP
   return check_launch("unet_lora_up_kernel");
 }
 
@@ -227,9 +281,15 @@ extern "C" int tb_unet_lora_bwd(const void* dkv, const void* ehs, const float* A
                  unet_lora_args_ok(M, ctx, KV, n_adapters, r),
              TB_E_ARG, "tb_unet_lora_bwd: bad args (M=%d ctx=%d KV=%d adapters=%d r=%d)", M, ctx, KV, n_adapters, r);
   const int R = n_adapters * r;
-  unet_lora_dz_kernel<<<dim3(n_adapters, M), 128, 0, st>>>((const half_t*)dkv, B, off, dZ, KV, R, r, scaling);
+#define TB_UL_DZ(RR, ROWS)                                                                                   \
+  unet_lora_dz_kernel<RR, ROWS><<<dim3(n_adapters, (M + ROWS - 1) / ROWS), 128, 0, st>>>((const half_t*)dkv, B, off, dZ, \
+                                                                                         M, KV, R, r, scaling)
+  if (r <= 4) TB_UL_DZ(4, 8);
+  else if (r <= 8) TB_UL_DZ(8, 4);
+  else TB_UL_DZ(16, 2);
+#undef TB_UL_DZ
   if ((rc = check_launch("unet_lora_dz_kernel"))) return rc;
-  const int rows_per_cta = 80;
+  const int rows_per_cta = 16;
   const dim3 gb((KV / 8 + 127) / 128, (M + rows_per_cta - 1) / rows_per_cta);
   if (r <= 4)
     unet_lora_grad_b_kernel<4><<<gb, 128, 0, st>>>((const half_t*)dkv, Z, blk, dB, M, KV, R, r, scaling, rows_per_cta);
