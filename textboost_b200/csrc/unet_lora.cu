@@ -32,7 +32,8 @@ unet_lora_down_kernel(const half_t* __restrict__ ehs, const float* __restrict__ 
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  for (int q = warp; q < R; q += nwarp) {
+  // the adapter rows q are split over gridDim.y CTAs (154 CTAs of 8 warps would leave the machine a third full)
+  for (int q = blockIdx.y * nwarp + warp; q < R; q += nwarp * gridDim.y) {
     const float* a = A + (size_t)q * ctx;
     float acc[UL_DOWN_ROWS];
 #pragma unroll
@@ -256,7 +257,7 @@ extern "C" int tb_unet_lora_fwd(const void* ehs, const float* A, const float* B,
   TB_REQUIRE(ehs && A && B && blk && Z && kv && unet_lora_args_ok(M, ctx, KV, n_adapters, r), TB_E_ARG,
              "tb_unet_lora_fwd: bad args (M=%d ctx=%d KV=%d adapters=%d r=%d)", M, ctx, KV, n_adapters, r);
   const int R = n_adapters * r;
-  unet_lora_down_kernel<<<(M + UL_DOWN_ROWS - 1) / UL_DOWN_ROWS, 256, UL_DOWN_ROWS * ctx * sizeof(float), st>>>(
+  unet_lora_down_kernel<<<dim3((M + UL_DOWN_ROWS - 1) / UL_DOWN_ROWS, R >= 64 ? 4 : 1), 256, UL_DOWN_ROWS * ctx * sizeof(float), st>>>(
       (const half_t*)ehs, A, Z, M, ctx, R);
   if ((rc = check_launch("unet_lora_down_kernel"))) return rc;
   const unsigned gx = (unsigned)((KV / 8 + 127) / 128);
