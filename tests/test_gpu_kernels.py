@@ -362,7 +362,12 @@ def test_text_encoder_layernorm_with_lora_glue(M, D, R, RPAD):
                                           (2, 256, 1920, True), (2, 64, 2560, True),
                                           # the single-launch group-owner kernel at the UNet's batch-8 shapes
                                           (8, 1024, 640, True), (8, 256, 1280, True), (8, 64, 1280, False),
-                                          (8, 1024, 1280, True), (8, 256, 1920, True), (8, 64, 2560, True)])
+                                          (8, 1024, 1280, True), (8, 256, 1920, True), (8, 64, 2560, True),
+                                          # the cluster variant of it (slab split over 2 / 4 / 8 CTAs, totals through
+                                          # distributed shared memory): the 64x64 level, the wide 32x32 concatenations,
+                                          # the 96x96 level of a 768^2 image
+                                          (8, 4096, 320, True), (8, 4096, 640, False), (8, 4096, 960, True),
+                                          (8, 1024, 1920, True), (8, 9216, 320, False)])
 def test_groupnorm_fwd_bwd(B, HW, Cc, silu):
     from textboost_b200 import ops
     torch.manual_seed(HW + Cc)
@@ -380,6 +385,10 @@ def test_groupnorm_fwd_bwd(B, HW, Cc, silu):
     assert relerr(y, yr.transpose(1, 2)) < 2e-3
     dx = ops.groupnorm_bwd(dy, x, gamma, beta, st, 32, 1e-5, silu, add=add)
     assert relerr(dx, xr.grad.transpose(1, 2) + add.float()) < 3e-3
+    # the saved statistics are (sum x, sum x^2) per (image, group) whichever kernel wrote them
+    xs = x.float().view(B, HW, 32, Cc // 32)
+    torch.testing.assert_close(st[..., 0], xs.sum((1, 3)), rtol=1e-4, atol=1e-2 * HW ** 0.5)
+    torch.testing.assert_close(st[..., 1], (xs * xs).sum((1, 3)), rtol=1e-4, atol=1e-2 * HW ** 0.5)
 
 
 @pytest.mark.parametrize("M,Cc,f32", [(512, 320, False), (77, 1280, False), (616, 768, True), (154, 1024, True),

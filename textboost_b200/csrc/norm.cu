@@ -274,22 +274,50 @@ __device__ __forceinline__ float gn_warp_sum(float v) {
 struct GnOwnGeom {
   int HW, C, G, cpg, gpc, nv, ty;  // nv = gpc*cpg/8 vectors per pixel of the slab; block = nv x ty threads
 };
-template <int MODE>
-__global__ void __launch_bounds__(512, 1)
-gn_group_kernel(const tb::half_t* __restrict__ x, const tb::half_t* __restrict__ dy, const tb::half_t* __restrict__ gamma,
-                const tb::half_t* __restrict__ beta, float* __restrict__ fstats, const tb::half_t* __restrict__ add,
-                tb::half_t* __restrict__ out, GnOwnGeom g, float eps, int silu) {
-  extern __shared__ uint4 gsm[];
+// CS > 1: the slab is shared by a thread-block cluster of CS CTAs, rank r owning pixels [r*HW/CS, (r+1)*HW/CS): every
+// CTA sums its part, the CS partial totals are exchanged through distributed shared memory (each CTA reads its peers'
+// totals in rank order, so all of them normalise with bit-identical statistics), and the levels whose slab exceeds one
+// SM's shared memory (64x64 pixels: 320 KB forward, 640 KB backward per 40-channel chunk) become one launch and one
+// read + one write of the tensor as well.
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t gn_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void gn_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void gn_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ float gn_peer_load(const float* local, uint32_t rank) {
+  uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(local)), ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+#else  // host build of the SIMT sources (tests/kernel_host_emulation.py): single-CTA path only
+static inline void gn_cluster_arrive() {}
+static inline void gn_cluster_wait() {}
+static inline float gn_peer_load(const float* local, unsigned) { return *local; }
+#endif
+
+template <int MODE, int CS>
+__device__ __forceinline__ void
+gn_group_body(uint4* gsm, const tb::half_t* __restrict__ x, const tb::half_t* __restrict__ dy,
+              const tb::half_t* __restrict__ gamma, const tb::half_t* __restrict__ beta, float* __restrict__ fstats,
+              const tb::half_t* __restrict__ add, tb::half_t* __restrict__ out, const GnOwnGeom& g, float eps, int silu,
+              int rank) {
   const int nthr = g.nv * g.ty;
+  const int HWc = g.HW / CS;                                     // pixels of this CTA
+  const int p_lo = rank * HWc;
   float* part = reinterpret_cast<float*>(gsm);                   // [nthr][2 groups][2]
   float* tot = part + (size_t)nthr * 4;                          // [gpc][2] block totals (+ padding to 16 floats)
-  uint4* sx = reinterpret_cast<uint4*>(tot + 16);                // [HW][nv]
-  uint4* sdy = sx + (size_t)g.HW * g.nv;                         // MODE 1: [HW][nv]
+  uint4* sx = reinterpret_cast<uint4*>(tot + 16);                // [HWc][nv]
+  uint4* sdy = sx + (size_t)HWc * g.nv;                          // MODE 1: [HWc][nv]
   const int tid = threadIdx.x;
   const int vx = tid % g.nv, py = tid / g.nv;
-  const int b = blockIdx.y, gc = blockIdx.x;
+  const int b = blockIdx.y, gc = blockIdx.x / CS;
   const int c0 = gc * g.gpc * g.cpg;                             // first channel of the slab
-  const size_t base = (size_t)b * g.HW * g.C + c0 + (size_t)vx * 8;
+  const size_t base = ((size_t)b * g.HW + p_lo) * g.C + c0 + (size_t)vx * 8;  // first pixel of this CTA
   const float inv_n = 1.f / ((float)g.HW * g.cpg);
   // the (at most two, cpg >= 8) groups this thread's 8 channels fall into, relative to the slab
   const int lg0 = (vx * 8) / g.cpg;
@@ -312,12 +340,12 @@ gn_group_kernel(const tb::half_t* __restrict__ x, const tb::half_t* __restrict__
 #pragma unroll
   for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
   constexpr int U = MODE == 0 ? 4 : 2;
-  for (int p = py; p < g.HW; p += U * g.ty) {
+  for (int p = py; p < HWc; p += U * g.ty) {
     uint4 qx[U], qd[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int pp = p + u * g.ty;
-      if (pp < g.HW) {
+      if (pp < HWc) {
         qx[u] = *reinterpret_cast<const uint4*>(x + base + (size_t)pp * g.C);
         if (MODE == 1) qd[u] = *reinterpret_cast<const uint4*>(dy + base + (size_t)pp * g.C);
       }
@@ -325,7 +353,7 @@ gn_group_kernel(const tb::half_t* __restrict__ x, const tb::half_t* __restrict__
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int pp = p + u * g.ty;
-      if (pp >= g.HW) break;
+      if (pp >= HWc) break;
       sx[(size_t)pp * g.nv + vx] = qx[u];
       float xf[8];
       unpack8(qx[u], xf);
@@ -403,7 +431,7 @@ gn_group_kernel(const tb::half_t* __restrict__ x, const tb::half_t* __restrict__
       if (tid == 0) {
         tot[lg * 2] = t1;
         tot[lg * 2 + 1] = t2;
-        if (MODE == 0) {
+        if (MODE == 0 && CS == 1) {
           fstats[((size_t)b * g.G + gc * g.gpc + lg) * 2] = t1;
           fstats[((size_t)b * g.G + gc * g.gpc + lg) * 2 + 1] = t2;
         }
@@ -411,6 +439,21 @@ gn_group_kernel(const tb::half_t* __restrict__ x, const tb::half_t* __restrict__
     }
   }
   __syncthreads();
+  if (CS > 1) {
+    // cluster totals: slot t of every rank, summed in rank order by every CTA (identical on all of them)
+    float* ctot = tot + 8;
+    gn_cluster_arrive();
+    gn_cluster_wait();
+    if (tid < 2 * g.gpc) {
+      float v = 0.f;
+      for (int r = 0; r < CS; ++r) v += gn_peer_load(tot + tid, (unsigned)r);
+      ctot[tid] = v;
+      if (MODE == 0 && rank == 0) fstats[((size_t)b * g.G + gc * g.gpc) * 2 + tid] = v;
+    }
+    gn_cluster_arrive();  // peers may leave (and release their shared memory) only after everyone has read: see the end
+    __syncthreads();
+    tot = ctot;
+  }
   float P[8], Q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -431,7 +474,7 @@ gn_group_kernel(const tb::half_t* __restrict__ x, const tb::half_t* __restrict__
       Q[i] = mean * P[i] - rstd * (t1 * inv_n);
     }
   }
-  for (int p = py; p < g.HW; p += g.ty) {
+  for (int p = py; p < HWc; p += g.ty) {
     float xf[8], o[8];
     unpack8(sx[(size_t)p * g.nv + vx], xf);
     if (MODE == 0) {
@@ -458,7 +501,29 @@ gn_group_kernel(const tb::half_t* __restrict__ x, const tb::half_t* __restrict__
     }
     *reinterpret_cast<uint4*>(out + base + (size_t)p * g.C) = pack8(o);
   }
+  if (CS > 1) gn_cluster_wait();
 }
+
+template <int MODE>
+__global__ void __launch_bounds__(512, 1)
+gn_group_kernel(const tb::half_t* __restrict__ x, const tb::half_t* __restrict__ dy, const tb::half_t* __restrict__ gamma,
+                const tb::half_t* __restrict__ beta, float* __restrict__ fstats, const tb::half_t* __restrict__ add,
+                tb::half_t* __restrict__ out, GnOwnGeom g, float eps, int silu) {
+  extern __shared__ uint4 gsm[];
+  __syncthreads();  // (keeps the host emulator on its cooperative launcher: the body below uses barriers and shuffles)
+  gn_group_body<MODE, 1>(gsm, x, dy, gamma, beta, fstats, add, out, g, eps, silu, 0);
+}
+#ifdef __CUDACC__
+template <int MODE, int CS>
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(512, 1)
+gn_group_cluster_kernel(const tb::half_t* __restrict__ x, const tb::half_t* __restrict__ dy,
+                        const tb::half_t* __restrict__ gamma, const tb::half_t* __restrict__ beta,
+                        float* __restrict__ fstats, const tb::half_t* __restrict__ add, tb::half_t* __restrict__ out,
+                        GnOwnGeom g, float eps, int silu) {
+  extern __shared__ uint4 gsm[];
+  gn_group_body<MODE, CS>(gsm, x, dy, gamma, beta, fstats, add, out, g, eps, silu, (int)gn_cluster_rank());
+}
+#endif
 
 // Geometry of the group-owner kernel, or 0 if the shape does not qualify (slab too large, misaligned, grid too small).
 static int gn_own_geom(GnOwnGeom& o, int B, int HW, int C, int G, int bwd) {
@@ -482,6 +547,65 @@ static int gn_own_geom(GnOwnGeom& o, int B, int HW, int C, int G, int bwd) {
   o.HW = HW; o.C = C; o.G = G; o.cpg = cpg; o.gpc = gpc; o.nv = nv; o.ty = ty;
   return (int)smem;
 }
+
+#ifdef __CUDACC__
+// Cluster variant of the group-owner geometry: the slab of `gpc` groups split over a cluster of cs CTAs (2, 4 or 8),
+// for the shapes gn_own_geom turns down because the slab exceeds one SM's shared memory.  0 = does not qualify.
+static int gn_cluster_geom(GnOwnGeom& o, int& cs_out, int B, int HW, int C, int G, int bwd) {
+  static const bool off = getenv("TB_GN_NO_GROUP_OWNER") != nullptr || getenv("TB_GN_NO_CLUSTER") != nullptr;
+  if (off || C % G != 0) return 0;
+  const int cpg = C / G;
+  if (cpg < 8) return 0;
+  int gpc = 0;
+  for (int c = 1; c <= 4; c *= 2)
+    if (G % c == 0 && (c * cpg) % 8 == 0) {
+      gpc = c;
+      break;
+    }
+  if (!gpc) return 0;
+  const int nv = gpc * cpg / 8;
+  if (nv > 64) return 0;
+  const int ty = 512 / nv;
+  for (int cs = 2; cs <= 8; cs *= 2) {
+    if (HW % cs != 0) continue;
+    const long long slab = (long long)(HW / cs) * nv * 16 * (bwd ? 2 : 1);
+    const long long smem = slab + (long long)nv * ty * 16 + 64;
+    if (smem > 200 * 1024) continue;
+    if (B * (G / gpc) * cs < 48) return 0;
+    o.HW = HW; o.C = C; o.G = G; o.cpg = cpg; o.gpc = gpc; o.nv = nv; o.ty = ty;
+    cs_out = cs;
+    return (int)smem;
+  }
+  return 0;
+}
+
+template <int MODE, int CS>
+static int gn_cluster_launch(const GnOwnGeom& o, int smem, int B, const void* x, const void* dy, const void* gamma,
+                             const void* beta, float* fstats, const void* add, void* out, float eps, int silu,
+                             cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gn_group_cluster_kernel<MODE, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         200 * 1024);
+    TB_REQUIRE(e == cudaSuccess, TB_E_CUDA, "cudaFuncSetAttribute(gn_group_cluster_kernel): %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  gn_group_cluster_kernel<MODE, CS><<<dim3(CS * (o.G / o.gpc), B), o.nv * o.ty, smem, st>>>(
+      (const tb::half_t*)x, (const tb::half_t*)dy, (const tb::half_t*)gamma, (const tb::half_t*)beta, fstats,
+      (const tb::half_t*)add, (tb::half_t*)out, o, eps, silu);
+  return check_launch("gn_group_cluster_kernel");
+}
+template <int MODE>
+static int gn_cluster_dispatch(const GnOwnGeom& o, int cs, int smem, int B, const void* x, const void* dy,
+                               const void* gamma, const void* beta, float* fstats, const void* add, void* out,
+                               float eps, int silu, cudaStream_t st) {
+  switch (cs) {
+    case 2: return gn_cluster_launch<MODE, 2>(o, smem, B, x, dy, gamma, beta, fstats, add, out, eps, silu, st);
+    case 4: return gn_cluster_launch<MODE, 4>(o, smem, B, x, dy, gamma, beta, fstats, add, out, eps, silu, st);
+    default: return gn_cluster_launch<MODE, 8>(o, smem, B, x, dy, gamma, beta, fstats, add, out, eps, silu, st);
+  }
+}
+#endif
 
 static int gn_geom(GnGeom& g, int B, int HW, int C, int G) {
   TB_REQUIRE(C % 8 == 0 && G > 0 && C % G == 0, TB_E_SHAPE, "groupnorm: C=%d G=%d unsupported", C, G);
@@ -878,6 +1002,11 @@ extern "C" int tb_groupnorm_fwd_f16(const void* x, const void* gamma, const void
           (const tb::half_t*)x, nullptr, (const tb::half_t*)gamma, (const tb::half_t*)beta, stats, nullptr, (tb::half_t*)y, o, eps, silu);
       return check_launch("gn_group_kernel<0>");
     }
+#ifdef __CUDACC__
+    int cs = 0;
+    const int csmem = gn_cluster_geom(o, cs, B, HW, C, G, 0);
+    if (csmem) return gn_cluster_dispatch<0>(o, cs, csmem, B, x, nullptr, gamma, beta, stats, nullptr, y, eps, silu, st);
+#endif
   }
   if (!zeroed) {
     cudaError_t e = cudaMemsetAsync(stats, 0, (size_t)B * G * 2 * sizeof(float), st);
@@ -936,6 +1065,12 @@ extern "C" int tb_groupnorm_bwd_f16(const void* dy, const void* x, const void* g
           (const tb::half_t*)add, (tb::half_t*)dx, o, eps, silu);
       return check_launch("gn_group_kernel<1>");
     }
+#ifdef __CUDACC__
+    int cs = 0;
+    const int csmem = gn_cluster_geom(o, cs, B, HW, C, G, 1);
+    if (csmem)
+      return gn_cluster_dispatch<1>(o, cs, csmem, B, x, dy, gamma, beta, const_cast<float*>(stats), add, dx, eps, silu, st);
+#endif
   }
   if (!zeroed) {
     cudaError_t e = cudaMemsetAsync(dstats, 0, (size_t)B * G * 2 * sizeof(float), st);
