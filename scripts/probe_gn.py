@@ -10,6 +10,8 @@ from textboost_b200 import ops  # noqa: E402
 dev = "cuda"
 SHAPES = [(8, 4096, 320), (8, 1024, 640), (8, 256, 1280), (8, 64, 1280), (8, 4096, 640), (8, 4096, 960), (8, 1024, 1920),
           (8, 256, 2560)]
+if "--big" in sys.argv:  # the shapes the cluster variant of the group-owner kernel covers
+    SHAPES = [(8, 4096, 320), (8, 4096, 640), (8, 4096, 960), (8, 1024, 1920)]
 
 
 def graph_us(fn, n=20):

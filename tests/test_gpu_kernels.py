@@ -391,6 +391,21 @@ def test_groupnorm_fwd_bwd(B, HW, Cc, silu):
     torch.testing.assert_close(st[..., 1], (xs * xs).sum((1, 3)), rtol=1e-4, atol=1e-2 * HW ** 0.5)
 
 
+def test_groupnorm_cluster_backward_and_8_cta_variants_in_a_child_process():
+    """The cluster kernel also has a backward mode and 8-CTA clusters, off by default because the two-pass kernels
+    measure faster there (csrc/norm.cu gn_cluster_geom); TB_GN_CLUSTER_ALL=1 (read once per process) turns them on:
+    the same GroupNorm cases must pass through them."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, TB_GN_CLUSTER_ALL="1", TB_GN_CLUSTER_THREADS="512", TB_GN_CLUSTER_SMEM_KB="200")
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_kernels.py", "-m", "gpu", "-q", "-k",
+                        "test_groupnorm_fwd_bwd", "-p", "no:cacheprovider"], cwd=root, env=env, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("M,Cc,f32", [(512, 320, False), (77, 1280, False), (616, 768, True), (154, 1024, True),
                                       (130, 320, False), (1001, 640, False), (3, 640, False), (37, 128, True)])
 def test_layernorm_fwd_bwd(M, Cc, f32):

@@ -565,12 +565,23 @@ static int gn_cluster_geom(GnOwnGeom& o, int& cs_out, int B, int HW, int C, int 
   if (!gpc) return 0;
   const int nv = gpc * cpg / 8;
   if (nv > 64) return 0;
-  const int ty = 512 / nv;
-  for (int cs = 2; cs <= 8; cs *= 2) {
+  // tuning knobs: threads per CTA and the shared-memory budget per CTA (two CTAs per SM overlap one's loads with the
+  // other's stores when both fit: <= ~100 KB and <= 32 K registers each)
+  // Measured (scripts/probe_gn.py --big, graph replay, two-pass -> cluster): with 256 threads and <= 100 KB per CTA (two
+  // CTAs per SM) the FORWARD wins at [8,4096,320] 20.9 -> 16.0 us, [8,4096,640] 33.3 -> 31.2, [8,1024,1920] 24.8 -> 23.6
+  // and loses at [8,4096,960] (47.6 -> 90: 8 CTAs of 17 pixel rows); the BACKWARD never wins (41.2 -> 42.6, 87.2 ->
+  // 88.8, 59.6 -> 70.4): its two-pass kernels already re-read x / dy from L2, not HBM (21-63 MB tensors in a 126 MB
+  // L2), so one pass saves no DRAM traffic there.  Defaults: forward only, clusters of 2 or 4.
+  static const int thr = getenv("TB_GN_CLUSTER_THREADS") ? atoi(getenv("TB_GN_CLUSTER_THREADS")) : 256;
+  static const int budget_kb = getenv("TB_GN_CLUSTER_SMEM_KB") ? atoi(getenv("TB_GN_CLUSTER_SMEM_KB")) : 100;
+  static const bool all = getenv("TB_GN_CLUSTER_ALL") != nullptr;  // also the backward and clusters of 8 (tests, A/B)
+  if (bwd && !all) return 0;
+  const int ty = thr / nv;
+  for (int cs = 2; cs <= (all ? 8 : 4); cs *= 2) {
     if (HW % cs != 0) continue;
     const long long slab = (long long)(HW / cs) * nv * 16 * (bwd ? 2 : 1);
     const long long smem = slab + (long long)nv * ty * 16 + 64;
-    if (smem > 200 * 1024) continue;
+    if (smem > (long long)budget_kb * 1024 && !(cs == 8 && smem <= 200 * 1024)) continue;
     if (B * (G / gpc) * cs < 48) return 0;
     o.HW = HW; o.C = C; o.G = G; o.cpg = cpg; o.gpc = gpc; o.nv = nv; o.ty = ty;
     cs_out = cs;
