@@ -95,9 +95,68 @@ class DPMSolverMultistepRef:
         return prev
 
 
+class DDPMRef:
+    """diffusers 0.29 ``DDPMScheduler`` as ``--validation_scheduler DDPMScheduler`` uses it
+    (/root/reference/train_textboost.py:341-346, 483-495): set_timesteps over strided timesteps, step = posterior mean
+    of q(x_{t-1} | x_t, x0) (formula (7) of the DDPM paper) plus sqrt(variance) * noise for t > 0; variance_type
+    "fixed_small" (learned variances are mapped onto it, :488-489) or "fixed_large"; clip_sample False, no thresholding
+    (the SD scheduler configs)."""
+
+    init_noise_sigma = 1.0
+
+    def __init__(self, alphas_cumprod=None, prediction_type="epsilon", timestep_spacing="leading", steps_offset=1,
+                 variance_type="fixed_small"):
+        if alphas_cumprod is None:
+            from . import ddpm_ref
+            alphas_cumprod = ddpm_ref.alphas_cumprod().numpy()
+        self.acp = np.asarray(alphas_cumprod, dtype=np.float64)
+        self.T = len(self.acp)
+        self.prediction_type, self.variance_type = prediction_type, variance_type
+        self.timestep_spacing, self.steps_offset = timestep_spacing, steps_offset
+
+    def set_timesteps(self, n: int):
+        T = self.T
+        if self.timestep_spacing == "linspace":
+            ts = np.linspace(0, T - 1, n).round()[::-1].copy().astype(np.int64)
+        elif self.timestep_spacing == "leading":
+            ts = (np.arange(0, n) * (T // n)).round()[::-1].copy().astype(np.int64) + self.steps_offset
+        elif self.timestep_spacing == "trailing":
+            ts = np.round(np.arange(T, 0, -T / n)).astype(np.int64) - 1
+        else:
+            raise ValueError(self.timestep_spacing)
+        self.timesteps, self.n, self.step_index = ts, n, 0
+        return ts
+
+    def step(self, model_output: torch.Tensor, sample: torch.Tensor, generator=None) -> torch.Tensor:
+        t = int(self.timesteps[self.step_index])
+        prev_t = t - self.T // self.n
+        a_t = self.acp[t]
+        a_prev = self.acp[prev_t] if prev_t >= 0 else 1.0
+        b_t, b_prev = 1.0 - a_t, 1.0 - a_prev
+        cur_alpha = a_t / a_prev
+        cur_beta = 1.0 - cur_alpha
+        if self.prediction_type == "epsilon":
+            x0 = (sample - b_t ** 0.5 * model_output) / a_t ** 0.5
+        elif self.prediction_type == "v_prediction":
+            x0 = a_t ** 0.5 * sample - b_t ** 0.5 * model_output
+        else:
+            raise ValueError(self.prediction_type)
+        prev = (a_prev ** 0.5 * cur_beta / b_t) * x0 + (cur_alpha ** 0.5 * b_prev / b_t) * sample
+        if t > 0:
+            var = max(b_prev / b_t * cur_beta, 1e-20) if self.variance_type == "fixed_small" else cur_beta
+            if isinstance(generator, (list, tuple)):
+                z = torch.cat([torch.randn((1,) + tuple(sample.shape[1:]), generator=g, device=sample.device,
+                                           dtype=torch.float32) for g in generator])
+            else:
+                z = torch.randn(sample.shape, generator=generator, device=sample.device, dtype=torch.float32)
+            prev = prev + var ** 0.5 * z.to(sample.dtype)
+        self.step_index += 1
+        return prev
+
+
 @torch.no_grad()
-def sample_latents(unet, cond, uncond, latents, scheduler: DPMSolverMultistepRef, num_inference_steps=50,
-                   guidance_scale=7.5):
+def sample_latents(unet, cond, uncond, latents, scheduler, num_inference_steps=50, guidance_scale=7.5,
+                   generator=None):
     """The denoising loop of StableDiffusionPipeline.__call__: `unet(x, t, ehs)` on the [uncond | cond] doubled batch,
     classifier-free guidance, scheduler.step.  cond / uncond [B,L,D]; latents [B,4,h,w] unit Gaussian."""
     ts = scheduler.set_timesteps(num_inference_steps)
@@ -107,5 +166,6 @@ def sample_latents(unet, cond, uncond, latents, scheduler: DPMSolverMultistepRef
         tt = torch.full((2 * x.shape[0],), int(t), dtype=torch.int64, device=x.device)
         eps = unet(torch.cat([x, x]), tt, ehs)
         e_u, e_c = eps.chunk(2)
-        x = scheduler.step(e_u + guidance_scale * (e_c - e_u), x)
+        out = e_u + guidance_scale * (e_c - e_u)
+        x = scheduler.step(out, x, generator) if isinstance(scheduler, DDPMRef) else scheduler.step(out, x)
     return x

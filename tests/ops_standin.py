@@ -103,7 +103,14 @@ def dpm_cfg_step(x, eps, m_prev, m_out, unet_in, guidance_scale, alpha_i, sigma_
 
 
 NAMES = ["gemm", "conv3x3", "groupnorm", "conv_in", "im2col3x3s2_pad", "upsample2x", "softmax_rows_", "vae_sample",
-         "vae_decode_in", "image_u8", "dpm_cfg_step"]
+         "vae_decode_in", "image_u8", "dpm_cfg_step", "cast_f32_f16"]
+
+
+def cast_f32_f16(src, out=None, scale=1.0):
+    if out is None:
+        out = torch.empty(src.shape, dtype=H16)
+    out.copy_((src.float() * scale).to(H16))
+    return out
 
 
 def install(monkeypatch):

@@ -159,6 +159,47 @@ def test_sampling_loop_eager_graph_and_oracle(tmp_path):
         pipe("a dog", height=100, width=128)
 
 
+def test_sampling_loop_with_ddpm_scheduler_vs_oracle(tmp_path):
+    """--validation_scheduler DDPMScheduler (train_textboost.py:341-346, 493-495): the ancestral loop of the pipeline
+    against the fp32 oracle loop (oracle UNet, oracle/sampler_ref.DDPMRef) with identically seeded CUDA generators --
+    both draw one [N,4,h,w] fp32 tensor per step -- within the same 16-bit-through-CFG envelope as the DPM-Solver loop;
+    and the CUDA-graph replay of the UNet forward agrees with the eager loop."""
+    from oracle import harness, sampler_ref, unet_ref
+    from textboost_b200 import synthetic
+    from textboost_b200.pipeline import DDPMScheduler, StableDiffusionPipeline
+    ck, usd, _ = _tiny_checkpoint(tmp_path)
+    pipe = StableDiffusionPipeline.from_pretrained(ck, safety_checker=None)
+    pipe.scheduler = DDPMScheduler.from_config(pipe.scheduler.config, variance_type="fixed_small")
+    pipe = pipe.to(dev)
+    steps, N = 8, 2
+    lat0 = torch.randn(N, 4, 16, 16, generator=torch.Generator().manual_seed(9))
+
+    def run(graph):
+        pipe.use_cuda_graph = graph
+        return pipe("a photo of a dog", num_images_per_prompt=N, num_inference_steps=steps, latents=lat0,
+                    generator=torch.Generator(device=dev).manual_seed(21), output_type="latent").images.clone()
+    eager, graphed, eager2 = run(False), run(True), run(False)
+    floor, gerr = rel_l2(eager2, eager), rel_l2(graphed, eager)
+    assert torch.isfinite(eager).all()
+    ucfg, _ = synthetic.model_configs("tiny")
+    unet = unet_ref.UNet2DConditionModelRef(harness._unet_cfg(ucfg))
+    unet.load_state_dict({k: v.float() for k, v in usd.items()})
+    unet = unet.to(dev).eval().requires_grad_(False)
+    cond, uncond = pipe.encode_prompt("a photo of a dog", dev, N)
+    c = pipe.scheduler.config
+    ref = sampler_ref.sample_latents(lambda x, t, e: unet(x, t, e), cond.float(), uncond.float(), lat0.to(dev),
+                                     sampler_ref.DDPMRef(timestep_spacing=c.timestep_spacing,
+                                                         steps_offset=c.steps_offset), steps, 7.5,
+                                     generator=torch.Generator(device=dev).manual_seed(21))
+    err = rel_l2(eager, ref)
+    print(f"DDPM_SAMPLER_PARITY steps={steps} rel_l2 {err:.2e} graph-vs-eager {gerr:.2e} floor {floor:.2e}")
+    assert gerr < max(2e-2, 4 * floor), (gerr, floor)
+    assert err < 5e-2, err
+    imgs = pipe("a photo of a dog", num_images_per_prompt=2, num_inference_steps=4,
+                generator=[torch.Generator(device=dev).manual_seed(s) for s in (1, 2)]).images
+    assert len(imgs) == 2 and imgs[0].size == (128, 128)
+
+
 def test_training_cli_validation_and_inference_cli(tmp_path, monkeypatch):
     """train_textboost.py --validation_prompts writes validation_<step>.jpg (train_textboost.py:1213-1228); then
     inference.py loads the adapter + learned embeddings it saved and samples a grid (inference.py:46-113)."""
@@ -176,6 +217,14 @@ def test_training_cli_validation_and_inference_cli(tmp_path, monkeypatch):
     grid = Image.open(os.path.join(out, "validation_4.jpg"))
     assert grid.size == (2 * 128, 2 * 128)
     assert {"text_encoder", "dog.bin", "hflip.bin"} <= set(os.listdir(out))
+    # --validation_scheduler DDPMScheduler (train_textboost.py:341-346): the ancestral sampler behind the same flag
+    out_d = str(tmp_path / "out_ddpm")
+    T.main(T.parse_args([
+        "--pretrained_model_name_or_path", ck, "--output_dir", out_d, "--synthetic_data", "--resolution", "128",
+        "--train_batch_size", "2", "--max_train_steps", "2", "--learning_rate", "1e-3", "--mixed_precision", "fp16",
+        "--validation_prompts", "a <0> in the snow", "--validation_steps", "2", "--num_validation_images", "2",
+        "--validation_scheduler", "DDPMScheduler", "--seed", "3"]))
+    assert Image.open(os.path.join(out_d, "validation_2.jpg")).size == (2 * 128, 128)
     monkeypatch.chdir(tmp_path)
     sheet = str(tmp_path / "sheet.jpg")
     I.main(I.parse_args([out + "/", "--model", ck, "--prompt", "photo of a <dog> dog", "--seeds", "0", "1", "2",

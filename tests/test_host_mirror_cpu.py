@@ -202,12 +202,12 @@ def test_cli_rejects_what_the_reference_cannot_run():
     base = ["--pretrained_model_name_or_path", "x"]
     T._unsupported(T.parse_args(base))
     for extra in (["--text_encoder_use_attention_mask"], ["--unet_params_to_train", "crossattn_kv"],
-                  ["--mixed_precision", "no"],
-                  ["--validation_prompts", "a dog", "--validation_scheduler", "DDPMScheduler"]):
+                  ["--mixed_precision", "no"]):
         with pytest.raises(NotImplementedError):
             T._unsupported(T.parse_args(base + extra))
     for ok in (["--gradient_accumulation_steps", "2"], ["--lr_scheduler", "cosine"], ["--lora_rank", "0"],
-               ["--mixed_precision", "bf16"]):  # bf16: the second build of the library (precision.py)
+               ["--mixed_precision", "bf16"],  # bf16: the second build of the library (precision.py)
+               ["--validation_prompts", "a dog", "--validation_scheduler", "DDPMScheduler"]):  # pipeline.DDPMScheduler
         T._unsupported(T.parse_args(base + ok))  # built in round 2 (csrc/optim.cu lr_multiplier, trainer.step)
     with pytest.raises(ValueError):
         T._unsupported(T.parse_args(base + ["--gradient_accumulation_steps", "0"]))

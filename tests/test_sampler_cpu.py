@@ -191,3 +191,63 @@ def test_inference_cli_flags_match_reference_table(tmp_path):
     assert I.parse_args(["x", "--model", str(d)]).model == str(d)  # ... unless they are local directories
     g = I.make_image_grid([__import__("PIL.Image").Image.new("RGB", (8, 6))] * 6, 2, 3)
     assert g.size == (24, 12)
+
+
+@pytest.mark.parametrize("pred", ["epsilon", "v_prediction"])
+@pytest.mark.parametrize("spacing,off,n,var", [("leading", 1, 25, "fixed_small"), ("linspace", 0, 10, "fixed_small"),
+                                               ("trailing", 0, 7, "fixed_large"), ("leading", 0, 1000, "fixed_small")])
+def test_ddpm_step_coefficients_reproduce_reference_update(pred, spacing, off, n, var):
+    """--validation_scheduler DDPMScheduler: x <- c_x x + c_d0 x0 + noise_std z with the host coefficients of the mirror
+    equals DDPMScheduler.step as restated in oracle/sampler_ref.DDPMRef (posterior mean + fixed variance), float64;
+    the timestep grids match, and the last step (t = 0 on the leading / linspace grids without offset) adds no noise."""
+    from oracle import sampler_ref
+    from textboost_b200.pipeline import DDPMScheduler
+    ours = DDPMScheduler(prediction_type=pred, timestep_spacing=spacing, steps_offset=off, variance_type=var)
+    ref = sampler_ref.DDPMRef(prediction_type=pred, timestep_spacing=spacing, steps_offset=off, variance_type=var)
+    assert ours.set_timesteps(n).tolist() == ref.set_timesteps(n).tolist()
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(2, 4, 8, 8, generator=g, dtype=torch.float64)
+    xr = x.clone()
+    steps = range(n) if n <= 25 else list(range(3)) + [n - 2, n - 1]
+    for i in steps:
+        ref.step_index = i
+        e = torch.randn(x.shape, generator=g, dtype=torch.float64)
+        k = ours.step_coefficients(i)
+        assert k["c_d1"] == 0.0
+        x0 = k["alpha_i"] * x - k["sigma_i"] * e if pred == "v_prediction" else (x - k["sigma_i"] * e) / k["alpha_i"]
+        gz = torch.Generator().manual_seed(100 + i)
+        z = torch.randn(x.shape, generator=gz, dtype=torch.float32).double()
+        x = k["c_x"] * x + k["c_d0"] * x0 + k["noise_std"] * z
+        xr = ref.step(e, xr, torch.Generator().manual_seed(100 + i))
+        assert torch.allclose(x, xr, rtol=1e-9, atol=1e-9), i
+        assert (k["noise_std"] == 0.0) == (int(ours.timesteps[i]) == 0)
+    # the reference maps learned variances onto fixed_small (train_textboost.py:488-489); from_config keeps the SD keys
+    s = DDPMScheduler.from_config({"num_train_timesteps": 1000, "beta_schedule": "scaled_linear", "beta_start": 0.00085,
+                                   "beta_end": 0.012, "variance_type": "learned_range", "clip_sample": False,
+                                   "skip_prk_steps": True, "set_alpha_to_one": False, "steps_offset": 1,
+                                   "timestep_spacing": "leading", "_class_name": "PNDMScheduler"})
+    assert s.config.variance_type == "fixed_small" and s.config.steps_offset == 1
+
+
+def test_denoise_loop_with_ddpm_scheduler_matches_oracle(monkeypatch):
+    """The pipeline's loop with the DDPM mirror against the oracle loop: same generator, one noise draw per step, the
+    next UNet input written after the noise."""
+    from oracle import sampler_ref
+    from textboost_b200 import pipeline
+    ops_standin.install(monkeypatch)
+    eng = _FakeUNetEngine()
+    unet = SimpleNamespace(engine=eng, config=SimpleNamespace(sample_size=8, in_channels=4))
+    vae = SimpleNamespace(config={"block_out_channels": (1, 2, 3, 4)})
+    pipe = pipeline.StableDiffusionPipeline(vae, None, None, unet,
+                                            pipeline.DDPMScheduler(timestep_spacing="leading", steps_offset=1))
+    pipe.use_cuda_graph = False
+    g = torch.Generator().manual_seed(3)
+    cond = (torch.randn(3, 7, 16, generator=g) * 0.5).half()
+    uncond = (torch.randn(3, 7, 16, generator=g) * 0.5).half()
+    lat = pipe.prepare_latents(3, 64, 64, "cpu", generator=torch.Generator().manual_seed(5))
+    x = pipe.denoise(lat.clone(), cond, uncond, 9, 7.5, generator=torch.Generator().manual_seed(11))
+    ref = sampler_ref.sample_latents(lambda a, t, e: eng.fn(a, t, e), cond.float(), uncond.float(), lat.clone(),
+                                     sampler_ref.DDPMRef(), 9, 7.5, generator=torch.Generator().manual_seed(11))
+    assert [c[1] for c in eng.calls] == pipe.scheduler.timesteps.tolist() == [889, 778, 667, 556, 445, 334, 223, 112, 1]
+    err = ((x - ref).norm() / ref.norm()).item()
+    assert err < 5e-3, err

@@ -118,6 +118,65 @@ class DPMSolverMultistepScheduler:
         return dict(alpha_i=a_i, sigma_i=s_i, c_x=s_t / s_i, c_d0=c_d0, c_d1=c_d1)
 
 
+class DDPMScheduler(DPMSolverMultistepScheduler):
+    """``--validation_scheduler DDPMScheduler`` (train_textboost.py:341-346, 493-495): ancestral DDPM sampling over
+    ``num_inference_steps`` strided timesteps, diffusers 0.29 ``DDPMScheduler`` at the settings an SD scheduler config
+    gives it (variance_type "fixed_small" — the reference maps learned variances onto it, :485-491 —, no sample clipping,
+    no thresholding).  Shares the config handling of the DPM-Solver mirror; the update is
+    ``x <- c_xt x + c_x0 x0 + sqrt(var) z`` with x0 the data prediction: the first two terms are one call of the fused
+    CFG + update kernel (``tb_dpm_cfg_step`` with no second-order term), the noise is drawn from the pipeline's generator."""
+
+    def __init__(self, *a, variance_type="fixed_small", clip_sample=False, **kw):
+        kw.pop("solver_order", None), kw.pop("algorithm_type", None), kw.pop("solver_type", None)
+        super().__init__(*a, **kw)
+        if variance_type in ("learned", "learned_range"):
+            variance_type = "fixed_small"  # train_textboost.py:488-489
+        if variance_type not in ("fixed_small", "fixed_large"):
+            raise NotImplementedError(f"DDPMScheduler variance_type {variance_type!r}")
+        if clip_sample:
+            raise NotImplementedError("DDPMScheduler clip_sample=True (SD scheduler configs set it to false)")
+        self.config.variance_type = variance_type
+
+    @classmethod
+    def from_config(cls, config, **overrides):
+        cfg = dict(config) if isinstance(config, dict) else dict(vars(config))
+        cfg.update(overrides)
+        keep = ("num_train_timesteps", "beta_start", "beta_end", "beta_schedule", "prediction_type",
+                "timestep_spacing", "steps_offset", "variance_type", "clip_sample")
+        return cls(**{k: cfg[k] for k in keep if k in cfg})
+
+    def set_timesteps(self, num_inference_steps: int, device=None):
+        c, n = self.config, int(num_inference_steps)
+        T = c.num_train_timesteps
+        if c.timestep_spacing == "linspace":
+            ts = np.linspace(0, T - 1, n).round()[::-1]
+        elif c.timestep_spacing == "leading":
+            ts = (np.arange(0, n) * (T // n)).round()[::-1] + c.steps_offset
+        elif c.timestep_spacing == "trailing":
+            ts = np.round(np.arange(T, 0, -T / n)) - 1
+        else:
+            raise ValueError(f"timestep_spacing {c.timestep_spacing!r}")
+        self.timesteps = ts.copy().astype(np.int64)
+        self.num_inference_steps = n
+        self.sigmas = None
+        return self.timesteps
+
+    def step_coefficients(self, i: int) -> dict:
+        """Host scalars of step i: (alpha_i, sigma_i) give the data prediction x0 = (x - sigma eps) / alpha (or
+        alpha x - sigma v); x <- c_x x + c_d0 x0 + noise_std z  (z omitted at t = 0).  DDPMScheduler.step / _get_variance."""
+        t = int(self.timesteps[i])
+        prev_t = t - self.config.num_train_timesteps // self.num_inference_steps
+        acp = self.alphas_cumprod.double()
+        a_t = float(acp[t])
+        a_prev = float(acp[prev_t]) if prev_t >= 0 else 1.0
+        b_t, b_prev = 1.0 - a_t, 1.0 - a_prev
+        cur_alpha = a_t / a_prev
+        cur_beta = 1.0 - cur_alpha
+        var = max(b_prev / b_t * cur_beta, 1e-20) if self.config.variance_type == "fixed_small" else cur_beta
+        return dict(alpha_i=math.sqrt(a_t), sigma_i=math.sqrt(b_t), c_x=math.sqrt(cur_alpha) * b_prev / b_t,
+                    c_d0=math.sqrt(a_prev) * cur_beta / b_t, c_d1=0.0, noise_std=math.sqrt(var) if t > 0 else 0.0)
+
+
 class StableDiffusionPipelineOutput:
     def __init__(self, images):
         self.images = images
@@ -228,8 +287,9 @@ class StableDiffusionPipeline:
             x = torch.randn(shape, generator=generator, device=device, dtype=F32)
         return (x * self.scheduler.init_noise_sigma).contiguous()
 
-    def denoise(self, x, cond, uncond, num_inference_steps, guidance_scale):
-        """The sampling loop on fp32 latents x [N,4,h,w] (in place); returns x."""
+    def denoise(self, x, cond, uncond, num_inference_steps, guidance_scale, generator=None):
+        """The sampling loop on fp32 latents x [N,4,h,w] (in place); returns x.  `generator`: the ancestral noise of a
+        DDPMScheduler (one draw per step, like scheduler.step(..., generator=generator) of the diffusers pipeline)."""
         sch, eng = self.scheduler, self.unet.engine
         ts = sch.set_timesteps(num_inference_steps)
         N = x.shape[0]
@@ -257,9 +317,22 @@ class StableDiffusionPipeline:
             if not cfg:
                 eps = torch.cat([eps, eps])
             k = sch.step_coefficients(i)
+            noise_std = k.get("noise_std", 0.0)
+            last = i + 1 == len(ts)
             ops.dpm_cfg_step(x, eps.contiguous(), m[(i + 1) % 2] if k["c_d1"] != 0.0 else None, m[i % 2],
-                             unet_in if i + 1 < len(ts) else None, guidance_scale if cfg else 1.0, k["alpha_i"],
-                             k["sigma_i"], v_pred, k["c_x"], k["c_d0"], k["c_d1"])
+                             unet_in if not last and noise_std == 0.0 else None, guidance_scale if cfg else 1.0,
+                             k["alpha_i"], k["sigma_i"], v_pred, k["c_x"], k["c_d0"], k["c_d1"])
+            if noise_std != 0.0:  # ancestral step: the next UNet input is written after the noise has been added
+                if isinstance(generator, (list, tuple)):
+                    z = torch.cat([torch.randn((1,) + tuple(x.shape[1:]), generator=g, device=x.device, dtype=F32)
+                                   for g in generator])
+                else:
+                    z = torch.randn(x.shape, generator=generator, device=x.device, dtype=F32)
+                x.add_(z, alpha=noise_std)
+                if not last:
+                    x2 = x.view(N, -1)
+                    ops.cast_f32_f16(x2, out=unet_in[:N].view(N, -1))
+                    ops.cast_f32_f16(x2, out=unet_in[N:].view(N, -1))
         return x
 
     @staticmethod
@@ -285,7 +358,7 @@ class StableDiffusionPipeline:
             raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
         cond, uncond = self.encode_prompt(prompt, dev, num_images_per_prompt, negative_prompt)
         x = self.prepare_latents(cond.shape[0], height, width, dev, generator, latents)
-        x = self.denoise(x, cond, uncond, num_inference_steps, guidance_scale)
+        x = self.denoise(x, cond, uncond, num_inference_steps, guidance_scale, generator)
         self.last_latents = x
         if output_type == "latent":
             images = x

@@ -164,8 +164,6 @@ def _unsupported(args):
     if args.report_to not in (None, "tensorboard"):
         warnings.warn(f"--report_to {args.report_to}: no tracker is attached here; metrics go to "
                       "<output_dir>/training.log and RUN_INFO")
-    if args.validation_prompts and args.validation_scheduler != "DPMSolverMultistepScheduler":
-        raise NotImplementedError("--validation_scheduler: only the default DPMSolverMultistepScheduler is built")
 
 
 def load_scheduler_config(path):
@@ -233,13 +231,21 @@ def build_image_batches(args, tokenizer, rank, world):
 def log_validation(text_encoder, tokenizer, unet, vae, args, device, global_step):
     """train_textboost.py:453-531: sample ``num_validation_images`` images per validation prompt with the modules being
     trained (25 DPM-Solver++ steps, guidance 7.5); ``<i>`` in a prompt stands for concept i's placeholder tokens."""
-    from textboost_b200.pipeline import DiffusionPipeline, DPMSolverMultistepScheduler
+    from textboost_b200 import pipeline as _pl
+    from textboost_b200.pipeline import DiffusionPipeline
     logger.info(f"Running validation... \n Generating {args.num_validation_images} images with prompt:"
                 f" {args.validation_prompts}.")
     pipeline = DiffusionPipeline.from_pretrained(args.pretrained_model_name_or_path, vae=vae, tokenizer=tokenizer,
                                                  text_encoder=text_encoder, unet=unet, safety_checker=None,
                                                  revision=args.revision, variant=args.variant)
-    pipeline.scheduler = DPMSolverMultistepScheduler.from_config(pipeline.scheduler.config)
+    # train_textboost.py:483-495: a learned variance is mapped onto "fixed_small", then --validation_scheduler picks
+    # the class (DPMSolverMultistepScheduler by default, DDPMScheduler)
+    scheduler_args = {}
+    cfg = pipeline.scheduler.config
+    variance_type = cfg.get("variance_type") if isinstance(cfg, dict) else getattr(cfg, "variance_type", None)
+    if variance_type is not None:
+        scheduler_args["variance_type"] = "fixed_small" if variance_type in ("learned", "learned_range") else variance_type
+    pipeline.scheduler = getattr(_pl, args.validation_scheduler).from_config(cfg, **scheduler_args)
     pipeline.set_progress_bar_config(disable=True)
     generator = None if args.seed is None else torch.Generator(device=device).manual_seed(args.seed)
     images = []
