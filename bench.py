@@ -445,6 +445,19 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = t.tolist()
     state = tr.opt_state.tolist()
+    # exact launch count: the kernel nodes of the step's CUDA graph, by name (graph_stats.py); the binding's own count
+    # (one or two kernels per GroupNorm / attention-backward call, decided on the C side) is only an estimate
+    launch_src = "ctypes binding estimate (kernels per entry point)"
+    graph_nodes = None
+    try:
+        from textboost_b200 import graph_stats
+        graph_nodes = graph_stats.kernel_nodes(lambda: tr.step(*dev_args))
+        torch.cuda.synchronize()
+        launches_per_step = graph_nodes["tb_kernels"]
+        launch_src = ("kernel nodes of the captured step graph whose function is in namespace tb (cuda-python "
+                      "cuGraphGetNodes / cuFuncGetName); other_kernels are torch's fills / add and NCCL's all-reduce")
+    except Exception as e:  # never let the accounting break the measurement
+        sys.stderr.write(f"[bench] graph node count unavailable ({type(e).__name__}: {e}); using the binding's estimate\n")
 
     fam = None
     cpu_base = None
@@ -486,6 +499,10 @@ def run_ours(args):
                     "api": "TextBoostTrainer.step_from_host (pinned host batch -> loss float)"},
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
+            "gpu_launches_how": launch_src,
+            "graph_nodes": None if graph_nodes is None else {
+                "kernel_nodes": graph_nodes["kernel_nodes"], "tb_kernels": graph_nodes["tb_kernels"],
+                "memset_nodes": graph_nodes["memset_nodes"], "other_kernels": graph_nodes["other_kernels"]},
             "clocks": clocks,
             "roofline": {
                 "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["tf_sustained"],

@@ -508,3 +508,23 @@ def test_step_unet_cross_kv_lora_vs_oracle():
         loss = replay(*args).item()
         l0 = loss if l0 is None else l0
     assert loss == loss and loss < l0 and tr.opt_unet.state[4].item() == 7 and tr.opt_state[8].item() == 0
+
+
+
+def test_graph_kernel_nodes_account_for_the_step():
+    """graph_stats.kernel_nodes: the captured step's kernel nodes by name -- what bench.py reports as gpu_launches.  Every
+    node is attributed; this library's kernels (namespace tb) are all but a handful of torch fills / adds."""
+    from textboost_b200 import graph_stats, synthetic
+    tr = synthetic.build_trainer("tiny", dev, seed=1, n_added=1, lora_b_std=0.02)
+    bt = synthetic.batch(2, 16, 3, tr.synthetic["clip_cfg"].vocab_size, dev)
+    args = (bt["latents"], bt["noise"], bt["timesteps"], bt["input_ids"], bt["prior_ids"])
+    tr.step(*args)
+    torch.cuda.synchronize()
+    before = tr.te.state.params.clone()
+    gs = graph_stats.kernel_nodes(lambda: tr.step(*args))
+    torch.cuda.synchronize()
+    assert torch.equal(before, tr.te.state.params)  # capturing executes nothing
+    assert gs["kernel_nodes"] == gs["tb_kernels"] + sum(gs["other_kernels"].values())
+    assert gs["tb_kernels"] > 200 and sum(gs["other_kernels"].values()) <= 16, gs["other_kernels"]
+    assert any("gemm_tc_kernel" in k for k in gs["by_name"]) and any("attn" in k for k in gs["by_name"])
+    assert "?" not in gs["by_name"]
