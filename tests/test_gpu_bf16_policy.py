@@ -47,6 +47,14 @@ def test_step_suite_under_the_bf16_build():
     assert " passed" in out and " failed" not in out
 
 
+def test_vae_and_sampler_suites_under_the_bf16_build():
+    """The front end (AutoencoderKL encoder) and the sampler (DPM-Solver++ / DDPM loops, VAE decoder) on the bf16 build;
+    the CLI cases of those files pass --mixed_precision fp16 and stay with the fp16 run."""
+    out = _child(["-m", "pytest", "tests/test_gpu_vae.py", "tests/test_gpu_sampler.py", "-m", "gpu", "-q", "-k",
+                  "not cli", "-p", "no:cacheprovider"], "pytest_bf16_vae_sampler.log")
+    assert " passed" in out and " failed" not in out
+
+
 def test_cli_mixed_precision_bf16(tmp_path):
     """train_textboost.py --mixed_precision bf16 in a fresh interpreter: the CLI itself selects the bf16 library (no
     environment variable), trains without a GradScaler (loss scale 1, nothing skipped) and writes the output files."""

@@ -7,7 +7,11 @@ import os
 import pytest
 import torch
 
+from conftest import act_dtype, tol_scale
+
 pytestmark = pytest.mark.gpu
+F16 = act_dtype()  # fp16; bf16 when the file is re-run under the bf16 policy (tests/test_gpu_bf16_policy.py)
+TOLX = tol_scale()  # 1 for fp16, 8 for bf16: rel_l2() reports errors in units of the fp16 bounds written below
 dev = "cuda"
 
 
@@ -22,7 +26,7 @@ def _need_gpu(built_lib):
 
 
 def rel_l2(a, b):
-    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-20)).item()
+    return (((a.float() - b.float()).norm() / (b.float().norm() + 1e-20)).item()) / TOLX
 
 
 @pytest.mark.parametrize("v_pred", [False, True])
@@ -39,11 +43,11 @@ def test_dpm_cfg_step_kernel(v_pred):
     m = [torch.zeros_like(x), torch.zeros_like(x)]
     mr = [torch.zeros_like(xr), torch.zeros_like(xr)]
     for i in range(6):
-        eps = torch.randn(6, 4, 16, 16, generator=g).half()
+        eps = torch.randn(6, 4, 16, 16, generator=g).to(F16)
         k = s.step_coefficients(i)
         last = i == 5
-        uin = None if last else torch.zeros(6, 4, 16, 16, dtype=torch.float16, device=dev)
-        uin_r = None if last else torch.zeros(6, 4, 16, 16, dtype=torch.float16)
+        uin = None if last else torch.zeros(6, 4, 16, 16, dtype=F16, device=dev)
+        uin_r = None if last else torch.zeros(6, 4, 16, 16, dtype=F16)
         args = (7.5, k["alpha_i"], k["sigma_i"], v_pred, k["c_x"], k["c_d0"], k["c_d1"])
         ops.dpm_cfg_step(x, eps.to(dev), m[(i + 1) % 2] if k["c_d1"] else None, m[i % 2], uin, *args)
         ops_standin.dpm_cfg_step(xr, eps, mr[(i + 1) % 2] if k["c_d1"] else None, mr[i % 2], uin_r, *args)
@@ -61,8 +65,8 @@ def test_vae_decode_in_and_image_u8_kernels():
     w, b = torch.randn(4, 4, generator=g) * 0.5, torch.randn(4, generator=g) * 0.1
     z = ops.vae_decode_in(lat.to(dev), w.to(dev), b.to(dev), 0.18215)
     zr = ops_standin.vae_decode_in(lat, w, b, 0.18215)
-    assert z.shape == (3, 4, 6, 10) and z.dtype == torch.float16 and rel_l2(z.cpu(), zr) < 1e-3
-    rows = (torch.randn(500, 64, generator=g) * 0.8).half()
+    assert z.shape == (3, 4, 6, 10) and z.dtype == F16 and rel_l2(z.cpu(), zr) < 1e-3
+    rows = (torch.randn(500, 64, generator=g) * 0.8).to(F16)
     rows[:4, :3] = torch.tensor([[-1.0, 1.0, 0.0], [-3.0, 3.0, 0.5], [1 / 255 - 1, 3 / 255 - 1, 0.25], [0.1, 0.2, 0.3]])
     u8 = ops.image_u8(rows.to(dev), 500, 3)
     ref = ops_standin.image_u8(rows, 500, 3)
