@@ -185,6 +185,11 @@ int tb_zero_stuff2x_f16(const void* dy, void* out, int B, int Ho, int Wo, int C,
 /* diffusers get_timestep_embedding(flip_sin_to_cos=True, freq_shift=0) -> fp16 [B, dim] = [cos | sin]. */
 int tb_timestep_embedding_f16(const int64_t* t, void* out, int B, int dim, void* stream);
 int tb_silu_f16(const void* x, void* y, int64_t n, void* stream);
+/* dst[i] += alpha * src[i], fp32 (loss += knowledge-preservation term, train_textboost.py:1106), and a stream-ordered
+ * clear of a buffer (cudaMemsetAsync: a memset node in the captured step, not a kernel) for the accumulators the step
+ * starts from zero (loss, d(text states), GroupNorm sums). */
+int tb_axpy_f32(float* dst, const float* src, int64_t n, float alpha, void* stream);
+int tb_fill_zero(void* ptr, size_t bytes, void* stream);
 /* DDPMScheduler.add_noise (+ target: epsilon or get_velocity), train_textboost.py:1052, :1070-1075.
  * x0/eps fp32 [B, per_image]; acp = alphas_cumprod fp32 [T]; noisy fp16; target fp32 (may be NULL). */
 int tb_add_noise(const float* x0, const float* eps, const int64_t* t, const float* acp, void* noisy_f16,

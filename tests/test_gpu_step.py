@@ -525,6 +525,8 @@ def test_graph_kernel_nodes_account_for_the_step():
     torch.cuda.synchronize()
     assert torch.equal(before, tr.te.state.params)  # capturing executes nothing
     assert gs["kernel_nodes"] == gs["tb_kernels"] + sum(gs["other_kernels"].values())
-    assert gs["tb_kernels"] > 200 and sum(gs["other_kernels"].values()) <= 16, gs["other_kernels"]
+    # every kernel of the step is this library's: clears are memset nodes (tb_fill_zero), the prompt batches are joined by
+    # device-to-device copies, the loss terms by tb_axpy_f32
+    assert gs["tb_kernels"] > 200 and not gs["other_kernels"], gs["other_kernels"]
     assert any("gemm_tc_kernel" in k for k in gs["by_name"]) and any("attn" in k for k in gs["by_name"])
     assert "?" not in gs["by_name"]

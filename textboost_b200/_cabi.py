@@ -95,6 +95,8 @@ _SIGNATURES = {
                                     c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p],
     "tb_timestep_embedding_f16": [c_void_p, c_void_p, c_int, c_int, c_void_p],
     "tb_silu_f16": [c_void_p, c_void_p, c_int64, c_void_p],
+    "tb_axpy_f32": [c_void_p, c_void_p, c_int64, c_float, c_void_p],
+    "tb_fill_zero": [c_void_p, c_size_t, c_void_p],
     "tb_add_noise": [c_void_p] * 6 + [c_int, c_int, c_int, c_void_p],
     "tb_mse_fwd_bwd": [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p],
     "tb_conv_in_f16": [c_void_p] * 4 + [c_int] * 5 + [c_void_p],
@@ -156,7 +158,7 @@ def last_error() -> str:
 # KERNELS one call of each entry point enqueues (memset nodes are not counted); entry points not listed launch one
 _KERNELS_PER_CALL = {"tb_groupnorm_fwd_f16": 2, "tb_groupnorm_bwd_f16": 2, "tb_attn_bwd_f16": 2, "tb_unet_lora_fwd": 2, "tb_unet_lora_bwd": 4,
                      "tb_resize_crop_normalize_u8": 2,
-                     "tb_adamw_fused_step": 3, "tb_version": 0, "tb_check_device": 0, "tb_storage_dtype": 0, "tb_set_workspace": 0,
+                     "tb_adamw_fused_step": 3, "tb_fill_zero": 0, "tb_version": 0, "tb_check_device": 0, "tb_storage_dtype": 0, "tb_set_workspace": 0,
                      "tb_attn_debug_trace": 0}
 TB_GN_STATS_ZEROED = 2
 launch_count = 0  # GPU launches enqueued through this binding since import (bench.py reports the delta)

@@ -411,6 +411,12 @@ __global__ void conv_out_bwd_kernel(const tb::half_t* __restrict__ dy, const tb:
   }
 }
 
+// dst += alpha * src (fp32): the step's scalar / small-vector accumulations (loss += knowledge-preservation term)
+__global__ void axpy_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n, float alpha) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] += alpha * src[i];
+}
+
 }  // namespace tb
 
 using namespace tb;
@@ -502,6 +508,20 @@ extern "C" int tb_silu_f16(const void* x, void* y, int64_t n, void* stream) {
   TB_REQUIRE(x && y && n % 8 == 0, TB_E_ARG, "tb_silu_f16: n %% 8");
   silu_kernel<<<grid_for(n / 8, 256), 256, 0, st>>>((const tb::half_t*)x, (tb::half_t*)y, n / 8);
   return check_launch("silu_kernel");
+}
+extern "C" int tb_axpy_f32(float* dst, const float* src, int64_t n, float alpha, void* stream) {
+  TB_ENTER();
+  TB_REQUIRE(dst && src && n > 0, TB_E_ARG, "tb_axpy_f32: bad args");
+  axpy_f32_kernel<<<grid_for(n, 256), 256, 0, st>>>(dst, src, n, alpha);
+  return check_launch("axpy_f32_kernel");
+}
+extern "C" int tb_fill_zero(void* ptr, size_t bytes, void* stream) {
+  TB_ENTER();
+  TB_REQUIRE(ptr || bytes == 0, TB_E_ARG, "tb_fill_zero: null pointer");
+  if (bytes == 0) return TB_OK;
+  cudaError_t e = cudaMemsetAsync(ptr, 0, bytes, st);
+  TB_REQUIRE(e == cudaSuccess, TB_E_CUDA, "tb_fill_zero: %s", cudaGetErrorString(e));
+  return TB_OK;
 }
 extern "C" int tb_add_noise(const float* x0, const float* eps, const int64_t* t, const float* acp,
                             void* noisy_f16, float* target, int B, int per_image, int v_prediction,

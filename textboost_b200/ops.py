@@ -113,12 +113,12 @@ def attn_bwd(q, k, v, o, do, lse, heads, scale=None, need_dq=True, dk=None, dv=N
 
 # ---------------------------------------------------------------------------------- normalisation
 class StatsArena:
-    """One zero-filled fp32 buffer per UNet pass for the (image, group) sums of all its GroupNorms: ONE fill launch
+    """One zero-filled fp32 buffer per UNet pass for the (image, group) sums of all its GroupNorms: ONE memset
     instead of a memset node per GroupNorm call (61 forward, 58 backward).  take() hands out [B, G, 2] slices."""
 
     def __init__(self, n_calls, B, groups, device):
         self.per = B * groups * 2
-        self.buf = torch.zeros(n_calls * self.per, device=device, dtype=F32)
+        self.buf = zeros(n_calls * self.per, device)
         self.used, self.shape = 0, (B, groups, 2)
 
     def take(self):
@@ -436,3 +436,24 @@ def unet_lora_bwd(dkv2d, ehs2d, A, Bm, Z, blk, off, dA, dB, d_ehs, r, scaling):
     dZ = torch.empty((M, R), device=dkv2d.device, dtype=F32)
     C.call("tb_unet_lora_bwd", C.ptr(dkv2d), C.ptr(ehs2d), C.ptr(A), C.ptr(Bm), C.ptr(Z), C.ptr(blk), C.ptr(off),
            C.ptr(dZ), C.ptr(dA), C.ptr(dB), C.ptr(d_ehs), M, ctx, KV, R // r, r, float(scaling), C.stream_ptr())
+
+
+def zeros(shape, device, dtype=F32):
+    """A zero-filled buffer cleared on the current stream by a memset (tb_fill_zero), not by a fill kernel."""
+    t = torch.empty(shape, device=device, dtype=dtype)
+    zero_(t)
+    return t
+
+
+def zero_(t):
+    assert t.is_contiguous()
+    C.call("tb_fill_zero", C.ptr(t), t.numel() * t.element_size(), C.stream_ptr())
+    return t
+
+
+def axpy_(dst, src, alpha=1.0):
+    """dst += alpha * src (fp32, contiguous, same size)."""
+    assert dst.dtype == F32 and src.dtype == F32 and dst.is_contiguous() and src.is_contiguous()
+    assert dst.numel() == src.numel()
+    C.call("tb_axpy_f32", C.ptr(dst), C.ptr(src), dst.numel(), float(alpha), C.stream_ptr())
+    return dst

@@ -130,7 +130,7 @@ class TextBoostTrainer:
         scale = self.opt_state[0:1]
         main = torch.cuda.current_stream()
         te.pack_lora()
-        self.loss.zero_()
+        ops.zero_(self.loss)
         noisy, target = ops.add_noise(latents, noise, timesteps, self.acp, self.v_pred)
         # The text-encoder passes run on a side stream: first the instance prompts (the UNet needs them at its first
         # cross-attention: an event, not a join), then the whole knowledge-preservation branch.  The main stream goes
@@ -138,7 +138,7 @@ class TextBoostTrainer:
         # the text: the 616-row encoder kernels fill a fraction of the SMs, the UNet prefix takes the rest.
         side = self._side_stream()
         first = self._first_stream()  # the instance prompts' forward: the UNet waits for it -> high priority
-        self._loss_kpl.zero_()
+        ops.zero_(self._loss_kpl)
         first.wait_stream(main)
         side.wait_stream(main)
         # instance and prior prompts go through the trainable encoder in ONE pass when they have the same length: the
@@ -147,7 +147,11 @@ class TextBoostTrainer:
         one_pass = use_kpl and prior_ids.shape[1:] == input_ids.shape[1:] and not self.separate_encoder_passes
         with torch.cuda.stream(first):
             if one_pass:
-                h_all = te.forward(torch.cat([input_ids, prior_ids], 0), save_for_backward=True)
+                ids_all = torch.empty((B + prior_ids.shape[0],) + tuple(input_ids.shape[1:]), device=input_ids.device,
+                                      dtype=input_ids.dtype)
+                ids_all[:B].copy_(input_ids)  # two device-to-device copies (memcpy nodes), not a cat kernel
+                ids_all[B:].copy_(prior_ids)
+                h_all = te.forward(ids_all, save_for_backward=True)
                 ctx_i, ctx_p = te.split_ctx(te.pop_ctx(), B)
                 h, hp = h_all[:B], h_all[B:]
             else:
@@ -168,7 +172,7 @@ class TextBoostTrainer:
                     ctx_p = te.pop_ctx()
                 h0 = self.te0.forward(prior_ids)
                 Bp, L, D = hp.shape
-                d_hp = torch.zeros((Bp, L, D), device=self.dev, dtype=F32)
+                d_hp = ops.zeros((Bp, L, D), self.dev)
                 C.call("tb_kpl_fwd_bwd", C.ptr(hp), C.ptr(h0), Bp * L, D, self.kpl_kind, float(self.kpl_weight),
                        C.ptr(scale), C.ptr(self._loss_kpl), C.ptr(d_hp), C.stream_ptr())
                 te.backward(d_hp, ctx=ctx_p)
@@ -184,14 +188,13 @@ class TextBoostTrainer:
             ops.mse_fwd_bwd(pred[:half], target[:half], self.loss, 1.0, scale, out=dpred[:half])
             ops.mse_fwd_bwd(pred[half:], target[half:], self.loss, float(self.image_prior_weight), scale,
                             out=dpred[half:])
-        d_h = torch.zeros((B, L, D), device=self.dev, dtype=F32)
+        d_h = ops.zeros((B, L, D), self.dev)
         unet.backward(dpred, d_h)
         main.wait_stream(side)  # gradient accumulation into state.grads is serialised from here on
         if first is not side:
             main.wait_stream(first)
         if use_kpl:
-            self.loss.add_(self._loss_kpl)
-            C.launch_count += 1
+            ops.axpy_(self.loss, self._loss_kpl)
         te.backward(d_h, ctx=ctx_i)
         self._pred = pred
         return self.loss

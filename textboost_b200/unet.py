@@ -488,7 +488,7 @@ class UNetEngine:
         self._saved = None
         B, L, ctx = ehs_shape
         if d_ehs is None:
-            d_ehs = torch.zeros((B * L, ctx), device=dout.device, dtype=F32)
+            d_ehs = ops.zeros((B * L, ctx), dout.device)
         d2 = d_ehs.view(B * L, ctx)
         n_gn = 2 * len(self._resnets) + len(self._attns) + 1
         self._set_arena(ops.StatsArena(n_gn, dout.shape[0], cfg.norm_num_groups, dout.device))
