@@ -606,13 +606,14 @@ static void emu_launch_serial(dim3 grid, dim3 block, const std::function<void()>
 
 ABI_FILES = ["norm.cu", "elementwise.cu", "clip.cu", "optim.cu", "vae.cu", "sampler.cu", "image.cu", "augment.cu",
              "unet_lora.cu"]
-_lib_abi = None
+_lib_abi = {}
 
 
-def lib_abi():
-    """The SIMT entry points of include/textboost_b200.h, built for the host from the product source (see above)."""
-    global _lib_abi
-    if _lib_abi is None:
+def lib_abi(bf16: bool = False):
+    """The SIMT entry points of include/textboost_b200.h, built for the host from the product source (see above).
+    bf16=True: the host twin of libtextboost_b200_bf16.so -- the 16-bit type of the build is the compiler's bfloat16
+    (`__bf16`, round-to-nearest-even conversions) instead of binary16, everything else identical."""
+    if bf16 not in _lib_abi:
         d = tempfile.mkdtemp(prefix="tb_abi_emu_")
         src = os.path.join(d, "abi.cpp")
         header = '#include "%s"\n' % os.path.join(ROOT, "include", "textboost_b200.h")
@@ -622,15 +623,19 @@ def lib_abi():
             text = "\n".join(l for l in text.splitlines() if not l.startswith("#include"))
             text = text.replace("extern __shared__", "extern").replace("#define TB_ENTER", "#undef TB_ENTER\n#define TB_ENTER")
             body.append(f"// ===== {name}\n" + _rewrite_launches(text))
+        shim = SHIM_BLOCK
+        if bf16:
+            assert "typedef _Float16 __half;" in shim
+            shim = shim.replace("typedef _Float16 __half;", "typedef __bf16 __half;  // the -DTB_BF16 build")
         with open(src, "w") as f:
-            f.write(SHIM_BLOCK + header + SHIM_ABI + "\n".join(body))
+            f.write(shim + header + SHIM_ABI + "\n".join(body))
         so = os.path.join(d, "abi.so")
         r = subprocess.run(["g++", "-O1", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC", "-std=c++20",
                             "-pthread", "-Wno-unknown-pragmas", "-o", so, src], capture_output=True, text=True)
         if r.returncode:
             raise RuntimeError(r.stderr[:6000])
-        _lib_abi = ctypes.CDLL(so)
-    return _lib_abi
+        _lib_abi[bf16] = ctypes.CDLL(so)
+    return _lib_abi[bf16]
 
 
 _lib_f16 = None
@@ -716,12 +721,20 @@ def install(monkeypatch):
     monkeypatch.setattr(S, "FAKES", fakes())
 
 
-def install_abi(monkeypatch):
+def install_abi_bf16(monkeypatch):
+    """install_abi with the bf16 host build and the process's precision policy switched to bf16 for the test (the
+    ops layer then expects torch.bfloat16 tensors, as it does beside libtextboost_b200_bf16.so)."""
+    from textboost_b200.precision import POLICY
+    monkeypatch.setattr(POLICY, "name", "bf16")
+    return install_abi(monkeypatch, bf16=True)
+
+
+def install_abi(monkeypatch, bf16: bool = False):
     """Bind textboost_b200._cabi to the host build of the SIMT entry points for one test: `ops.*` / `C.call` then run the
     product's own ctypes signatures, argument checks, launch geometry and kernel source on CPU tensors.  The tcgen05
     entry points (GEMM, conv, attention) are absent and raise AttributeError."""
     from textboost_b200 import _cabi
-    L = lib_abi()
+    L = lib_abi(bf16)
     for name, argtypes in _cabi._SIGNATURES.items():
         if hasattr(L, name):
             fn = getattr(L, name)

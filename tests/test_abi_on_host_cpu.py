@@ -425,3 +425,86 @@ def test_unet_cross_kv_lora_entry_points(abi, r):
         assert torch.count_nonzero(grads) == 0
         torch.testing.assert_close(ours_p, p_ref.detach(), rtol=1e-5, atol=1e-7)
     assert opt.state[0].item() == 1.0 and opt.state[4].item() == 2 and opt.state[8].item() == 0
+
+
+def test_simt_entry_points_under_the_bf16_host_build(monkeypatch):
+    """The bf16 precision policy on the CPU: the same SIMT sources built for the host with the 16-bit type set to
+    bfloat16 (the host twin of libtextboost_b200_bf16.so, -DTB_BF16) behind the product's ops layer with the policy
+    switched to bf16 -- GroupNorm (+SiLU) forward / backward on both paths, LayerNorm, GEGLU, the fp32 -> 16-bit cast,
+    noise / MSE, and the UNet-adapter kernels, against fp32 formulas with the bf16 bounds (8x the fp16 ones)."""
+    abi = K.install_abi_bf16(monkeypatch)  # noqa: F841
+    from textboost_b200 import ops
+    from textboost_b200.precision import POLICY
+    assert POLICY.act == torch.bfloat16
+    BF, TX = torch.bfloat16, 8.0
+
+    def b(*shape, seed=0, scale=1.0, shift=0.0):
+        return (torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale + shift).to(BF)
+
+    # GroupNorm: two-kernel path (cpg 2) and group-owner path (cpg 40)
+    for B, HW, Cc, silu in ((2, 40, 64, True), (2, 12, 1280, False)):
+        x, gamma, beta = b(B, HW, Cc, seed=Cc, scale=1.5, shift=0.3), b(Cc, seed=1, scale=0.1, shift=1.0), b(Cc, seed=2, scale=0.1)
+        y, stats = ops.groupnorm(x, gamma, beta, 32, 1e-5, silu)
+        assert y.dtype == BF
+        xf = x.float().transpose(1, 2).requires_grad_(True)
+        ref = F.group_norm(xf, 32, gamma.float(), beta.float(), 1e-5)
+        ref = F.silu(ref) if silu else ref
+        _close(y, ref.detach().transpose(1, 2), 2e-3 * TX)
+        dy, add = b(B, HW, Cc, seed=3), b(B, HW, Cc, seed=4)
+        dx = ops.groupnorm_bwd(dy, x, gamma, beta, stats, 32, 1e-5, silu, add=add)
+        ref.backward(dy.float().transpose(1, 2))
+        _close(dx, xf.grad.transpose(1, 2) + add.float(), 3e-3 * TX)
+    # LayerNorm on 16-bit rows
+    x, gamma, beta = b(37, 320, seed=5), b(320, seed=6, scale=0.1, shift=1.0), b(320, seed=7, scale=0.1)
+    y, st = ops.layernorm(x, gamma, beta)
+    xr = x.float().requires_grad_(True)
+    yr = F.layer_norm(xr, (320,), gamma.float(), beta.float(), 1e-5)
+    _close(y, yr.detach(), 2e-3 * TX)
+    dy = b(37, 320, seed=8)
+    yr.backward(dy.float())
+    _close(ops.layernorm_bwd(dy, x, gamma, st), xr.grad, 3e-3 * TX)
+    # GEGLU and the fp32 -> 16-bit cast
+    h = b(9, 64, seed=9)
+    hr = h.float().requires_grad_(True)
+    gr = hr[:, :32] * F.gelu(hr[:, 32:])
+    _close(ops.geglu(h), gr.detach(), 2e-3 * TX)
+    dg = b(9, 32, seed=10)
+    gr.backward(dg.float())
+    _close(ops.geglu_bwd(dg, h), hr.grad, 3e-3 * TX)
+    f = torch.randn(5, 16, generator=torch.Generator().manual_seed(11))
+    assert torch.equal(ops.cast_f32_f16(f, scale=0.5), (f * 0.5).to(BF))
+    # add_noise + MSE (fp32 in, 16-bit noisy sample / prediction)
+    acp = torch.linspace(0.999, 0.01, 1000)
+    x0, eps = torch.randn(2, 4, 8, 8, generator=torch.Generator().manual_seed(12)), torch.randn(2, 4, 8, 8)
+    t = torch.tensor([10, 900])
+    noisy, target = ops.add_noise(x0, eps, t, acp, False)
+    sa, sb = acp[t].sqrt().view(2, 1, 1, 1), (1 - acp[t]).sqrt().view(2, 1, 1, 1)
+    assert noisy.dtype == BF and torch.equal(target, eps)
+    _close(noisy, sa * x0 + sb * eps, 1e-3 * TX)
+    loss = torch.zeros(1)
+    dpred = ops.mse_fwd_bwd(noisy, target, loss, 1.0, torch.ones(1))
+    _close(loss, F.mse_loss(noisy.float(), target).view(1), 1e-5)
+    _close(dpred, 2 * (noisy.float() - target) / noisy.numel(), 1e-3 * TX)
+    # the UNet-adapter kernels on bf16 text states / K-V
+    r, M, ctx, widths = 4, 6, 40, (8, 16)
+    KV, n_ad = 2 * sum(widths), 2 * len(widths)
+    blk, off = [], [0]
+    for i, w in enumerate(widths):
+        blk += [2 * i] * w + [2 * i + 1] * w
+        off += [off[-1] + w, off[-1] + 2 * w]
+    blk_t, off_t = torch.tensor(blk, dtype=torch.int32), torch.tensor(off, dtype=torch.int32)
+    g = torch.Generator().manual_seed(13)
+    ehs, kv0, dkv = b(M, ctx, seed=14), b(M, KV, seed=15), b(M, KV, seed=16)
+    A = (torch.randn(n_ad * r, ctx, generator=g) / r).requires_grad_(True)
+    Bm = (0.05 * torch.randn(KV, r, generator=g)).requires_grad_(True)
+    e32 = ehs.float().requires_grad_(True)
+    ref = kv0.float() + torch.cat([(e32 @ A[a * r:(a + 1) * r].t()) @ Bm[off[a]:off[a + 1]].t() for a in range(n_ad)], 1)
+    ref.backward(dkv.float())
+    kv = kv0.clone()
+    Z = ops.unet_lora_fwd(ehs, A.detach(), Bm.detach(), blk_t, kv, r, 1.0)
+    _close(kv, ref.detach(), 2e-3 * TX)
+    dA, dB, d_ehs = torch.zeros_like(A), torch.zeros_like(Bm), torch.zeros(M, ctx)
+    ops.unet_lora_bwd(dkv, ehs, A.detach(), Bm.detach(), Z, blk_t, off_t, dA, dB, d_ehs, r, 1.0)
+    _close(dA, A.grad, 1e-5)
+    _close(dB, Bm.grad, 1e-5)
+    _close(d_ehs, e32.grad, 1e-5)
