@@ -15,7 +15,13 @@ import torch.nn.functional as F
 
 from textboost_b200 import _cabi as C
 
-F16, F32 = torch.float16, torch.float32
+F32 = torch.float32
+
+
+def _h16():
+    """The policy's 16-bit dtype, looked up at call time (fp16; bf16 when a test switched the policy)."""
+    from textboost_b200.precision import POLICY
+    return POLICY.act
 
 
 def _act(y, act):
@@ -40,7 +46,7 @@ def _finish(y, bias, rowvec, rows_per_group, residual, alpha, act, out, out_kind
     if out_kind == C.TB_OUT_F32_ACC:
         out.add_(y.reshape(out.shape))
         return out
-    y = y.to(F16 if out_kind == C.TB_OUT_F16 else F32)
+    y = y.to(_h16() if out_kind == C.TB_OUT_F16 else F32)
     if out is not None:
         out.copy_(y.reshape(out.shape))
         return out
@@ -49,14 +55,14 @@ def _finish(y, bias, rowvec, rows_per_group, residual, alpha, act, out, out_kind
 
 def gemm(a, w, *, bias=None, rowvec=None, rows_per_group=1, residual=None, alpha=1.0, act=C.TB_ACT_NONE, out=None,
          out_kind=C.TB_OUT_F16):
-    assert a.dtype == F16 and w.dtype == F16 and a.stride(1) == 1 and w.stride(1) == 1 and w.shape[1] == a.shape[1]
+    assert a.dtype == _h16() and w.dtype == _h16() and a.stride(1) == 1 and w.stride(1) == 1 and w.shape[1] == a.shape[1]
     return _finish(a.float() @ w.float().t(), bias, rowvec, rows_per_group, residual, alpha, act, out, out_kind)
 
 
 def conv3x3(x, w, *, bias=None, rowvec=None, residual=None, act=C.TB_ACT_NONE, out=None):
     B, H, W, Cin = x.shape
     Cout = w.shape[0]
-    assert x.dtype == F16 and x.is_contiguous() and w.shape[1] == 9 * Cin and Cin % 64 == 0
+    assert x.dtype == _h16() and x.is_contiguous() and w.shape[1] == 9 * Cin and Cin % 64 == 0
     wt = w.float().view(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
     y = F.conv2d(x.float().permute(0, 3, 1, 2), wt, padding=1).permute(0, 2, 3, 1).reshape(B * H * W, Cout)
     res = residual.reshape(B * H * W, Cout) if residual is not None else None
@@ -80,7 +86,7 @@ def attn_fwd(q, k, v, heads, scale=None, out=None, causal=False):
     if causal:
         s = s.masked_fill(torch.ones(Nq, k.shape[1], dtype=torch.bool).triu(1), float("-inf"))
     lse = torch.logsumexp(s, -1) / 0.6931471805599453  # the kernels keep it in the log2 domain
-    o = (torch.softmax(s, -1) @ _heads(v, heads)).transpose(1, 2).reshape(B, Nq, Ch).to(F16)
+    o = (torch.softmax(s, -1) @ _heads(v, heads)).transpose(1, 2).reshape(B, Nq, Ch).to(_h16())
     if out is not None:
         out.copy_(o)
         o = out
@@ -102,11 +108,11 @@ def attn_bwd(q, k, v, o, do, lse, heads, scale=None, need_dq=True, dk=None, dv=N
     if dq_out is not None and dq_out is not False:  # the single-KV-tile contract: fp16 dQ written once, in place
         assert need_dq and k.shape[1] <= 128
         if dq_out is True:
-            dq = dq.to(F16)
+            dq = dq.to(_h16())
         else:
             dq_out.copy_(dq)
             dq = dq_out
-    gk, gv = kf.grad.to(F16), vf.grad.to(F16)
+    gk, gv = kf.grad.to(_h16()), vf.grad.to(_h16())
     if dk is not None:
         dk.copy_(gk)
         gk = dk
@@ -132,10 +138,11 @@ class _NoStream:
         pass
 
 
-def install(monkeypatch):
+def install(monkeypatch, bf16: bool = False):
+    """bf16=True: the bf16 host build of the SIMT sources and the policy switched to bf16 (K.install_abi_bf16)."""
     import kernel_host_emulation as K
     from textboost_b200 import ops
-    K.install_abi(monkeypatch)
+    (K.install_abi_bf16 if bf16 else K.install_abi)(monkeypatch)
     for name in ("gemm", "conv3x3", "attn_fwd", "attn_bwd"):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _NoStream())

@@ -188,3 +188,31 @@ def test_clip_engine_lora_on_cpu_matches_reference_golden(monkeypatch, name):
     assert rel(st.rows(st.grads), gold["grad_added_rows_fixed"]) < 3e-3
     assert ((flat - ref).norm() / ref.norm()).item() < 3e-3
     assert torch.nn.functional.cosine_similarity(flat, ref, dim=0).item() > 0.99999
+
+
+@pytest.mark.long_cpu
+def test_unet_cross_kv_lora_step_on_cpu_matches_oracle(monkeypatch):
+    """--unet_params_to_train crossattn_kv (train_textboost.py:712-721, 838-841) through the product engines on the CPU,
+    under the bf16 policy the mode is tied to: the bf16 host build of the SIMT sources (incl. csrc/unet_lora.cu), the
+    trainer's third parameter group (optim.FlatAdamW: LoRA learning rate, not clipped), against the oracle step whose
+    UNet carries the same adapters.  bf16 bounds = 8x the fp16 ones of _check."""
+    from oracle import harness
+    from textboost_b200 import synthetic
+    engine_standin.install(monkeypatch, bf16=True)
+    tr = synthetic.build_trainer("tiny", "cpu", seed=1, n_added=2, lora_b_std=0.02, keep_sd=True, learning_rate=1e-4,
+                                 unet_lora_r=4)
+    assert tr.opt_unet is not None and tr.opt_state[0].item() == 1.0  # no GradScaler under bf16
+    V = tr.synthetic["clip_cfg"].vocab_size
+    bt = synthetic.batch(2, 8, 3, V, "cpu")
+    bt["input_ids"][1, 4] = V + 1
+    before = tr.unet.kv_lora.params.clone()
+    r = harness.compare_step(tr, bt)
+    TX = 8.0
+    assert abs(r["loss"] - r["loss_ref"]) < 2e-3 * TX * abs(r["loss_ref"])
+    assert r["pred_rel"] < 4e-3 * TX
+    assert r["lora_grad_rel_l2"] < 5e-3 * TX and r["row_grad_rel"] < 5e-3 * TX
+    assert r["unet_lora_grad_norm_ref"] > 0
+    assert r["unet_lora_grad_rel_l2"] < 5e-3 * TX and r["unet_lora_grad_cos"] > 1 - 1e-5 * TX ** 2
+    assert r["unet_lora_param_max_abs_diff"] <= 2.1 * tr.lr
+    assert (tr.unet.kv_lora.params - before).abs().max().item() > 0.5 * tr.lr
+    assert torch.count_nonzero(tr.unet.kv_lora.grads) == 0 and tr.opt_unet.state[4].item() == 1
