@@ -26,7 +26,7 @@ def _flat_grads(te, out, V):
     return torch.cat(parts)
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, unet_adapter=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
     torch.set_num_threads(2)
@@ -38,6 +38,11 @@ def _worker(rank, world, port, q):
     assert (r, w) == (rank, world)
     sync = dp.GradSync()
     unet, te, te0, ccfg = T._tiny_step_models()
+    if unet_adapter:  # --unet_params_to_train crossattn_kv: a second flat buffer, all-reduced like the first
+        g = torch.Generator().manual_seed(7)
+        for _, m in unet.add_cross_kv_lora(2):
+            with torch.no_grad():
+                m.lora_B["default"].weight.copy_(0.05 * torch.randn(m.lora_B["default"].weight.shape, generator=g))
     V = ccfg.vocab_size
     lat, noise, t, ids, pr = T._tiny_batch(4, V)
     sl = sync.shard_rows(4)
@@ -47,20 +52,38 @@ def _worker(rank, world, port, q):
     n_bytes = sync.payload_bytes(flat)
     sync.all_reduce_(flat)
     flat *= sync.inv_world
+
+    def unet_flat(o):
+        return torch.cat([o["grad_unet_lora"][n].flatten() for n in sorted(o["grad_unet_lora"])])
+    if unet_adapter:
+        flat_u = unet_flat(out)
+        sync.all_reduce_(flat_u)
+        flat_u *= sync.inv_world
     loss = out["loss"].clone()
     dist.all_reduce(loss)
     if rank == 0:
         full = step_ref.reference_step(unet, te, te0, lat, noise, t, ids, pr, n_base=V)
-        q.put((flat.tolist(), _flat_grads(te, full, V).tolist(), (loss / world).item(), full["loss"].item(), n_bytes))
+        if unet_adapter:
+            flat, ref_flat = torch.cat([flat, flat_u]), torch.cat([_flat_grads(te, full, V), unet_flat(full)])
+            assert flat_u.numel() > 0 and float(flat_u.abs().sum()) > 0
+        else:
+            ref_flat = _flat_grads(te, full, V)
+        q.put((flat.tolist(), ref_flat.tolist(), (loss / world).item(), full["loss"].item(), n_bytes))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_rank_shard_allreduce_equals_global_batch():
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("unet_adapter", [False, True])
+def test_two_rank_shard_allreduce_equals_global_batch(unet_adapter):
+    """unet_adapter: with the UNet K/V LoRA (--unet_params_to_train crossattn_kv) a second flat gradient buffer goes
+    through the same all-reduce (TextBoostTrainer.all_reduce), and the identity holds for it too."""
     ctx = mp.get_context("spawn")
     q = ctx.SimpleQueue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, unet_adapter)) for r in range(2)]
     for p in procs:
         p.start()
     flat, ref, loss, loss_ref, n_bytes = q.get()
@@ -70,7 +93,7 @@ def test_two_rank_shard_allreduce_equals_global_batch():
     flat, ref = torch.tensor(flat), torch.tensor(ref)
     torch.testing.assert_close(flat, ref, rtol=1e-4, atol=1e-7)
     assert abs(loss - loss_ref) < 1e-5 * abs(loss_ref)
-    assert n_bytes == flat.numel() * 4
+    assert unet_adapter or n_bytes == flat.numel() * 4
 
 
 def test_single_process_sync_is_identity():
