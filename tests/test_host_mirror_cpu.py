@@ -306,3 +306,35 @@ def test_reference_import_lines_resolve_through_the_shim():
     assert import_model_class_from_model_name_or_path("x", None) is textboost_b200.text_encoder.CLIPTextModel
     with pytest.raises(NotImplementedError):
         generate_prior_images()
+
+
+def test_unet_cross_kv_lora_state_layout_and_peft_names():
+    """unet.CrossKVLora (--unet_params_to_train crossattn_kv, train_textboost.py:712-721): adapter 2i / 2i+1 = to_k / to_v
+    of the i-th transformer block in forward order, peft state-dict names, gaussian init of lora_A (std 1/r) with
+    lora_B = 0, column tables consistent with the engine's fused K/V projection, state-dict round trip."""
+    from textboost_b200 import synthetic
+    from textboost_b200.unet import UNetEngine
+    ucfg, _ = synthetic.model_configs("tiny")
+    eng = UNetEngine(ucfg, synthetic.random_unet_sd(ucfg, "cpu", 0))
+    kvl = eng.add_cross_kv_lora(4, seed=3)
+    assert eng.kv_lora is kvl and kvl.n_adapters == 2 * len(eng._attns) == 32 and kvl.R == 128
+    assert kvl.params.numel() == kvl.R * kvl.ctx + kvl.KV * 4 and kvl.scaling == 1.0
+    assert kvl.names[0] == "down_blocks.0.attentions.0.transformer_blocks.0.attn2.to_k"
+    assert kvl.names[1].endswith("attn2.to_v") and kvl.names[-1] == "up_blocks.3.attentions.2.transformer_blocks.0.attn2.to_v"
+    off = kvl.off.tolist()
+    assert off[0] == 0 and off[-1] == kvl.KV == eng._kv_total and all(o % 8 == 0 for o in off)
+    for i, a in enumerate(eng._attns):
+        Cc = a.kv2.w.shape[0] // 2
+        assert off[2 * i] == a.kv_off and off[2 * i + 1] == a.kv_off + Cc and off[2 * i + 2] == a.kv_off + 2 * Cc
+        assert kvl.blk[a.kv_off:a.kv_off + Cc].eq(2 * i).all() and kvl.blk[a.kv_off + Cc:a.kv_off + 2 * Cc].eq(2 * i + 1).all()
+    assert kvl.B().abs().max() == 0 and abs(kvl.A().std().item() - 0.25) < 0.02  # peft "gaussian": N(0, 1/r), B = 0
+    sd = kvl.state_dict()
+    assert len(sd) == 64 and sd[kvl.names[5] + ".lora_A.weight"].shape == (4, kvl.ctx)
+    assert sd[kvl.names[5] + ".lora_B.weight"].shape == (off[6] - off[5], 4)
+    other = UNetEngine(ucfg, synthetic.random_unet_sd(ucfg, "cpu", 0)).add_cross_kv_lora(4, seed=9)
+    assert not torch.equal(other.A(), kvl.A())
+    sd[kvl.names[2] + ".lora_B.weight"] = torch.full_like(sd[kvl.names[2] + ".lora_B.weight"], 0.5)
+    other.load_state_dict(sd)
+    assert torch.equal(other.A(), kvl.A()) and other.B()[off[2]:off[3]].eq(0.5).all() and other.B()[off[3]:].abs().max() == 0
+    with pytest.raises(ValueError):
+        eng.add_cross_kv_lora(17)
