@@ -18,6 +18,9 @@ pytestmark = pytest.mark.gpu
 dev = "cuda"
 F16 = act_dtype()  # fp16; bf16 when the file is re-run under the bf16 policy (tests/test_gpu_bf16_policy.py)
 TOLX = tol_scale()  # 1 for fp16, 8 for bf16 (unit roundoff 2^-8 against 2^-11): the bounds below are the fp16 ones
+# gradient vectors and norms at the full-width configurations: bf16 measures 0.79-0.82 of the 8x bound (B = 8: LoRA gradients
+# 1.90e-2 rel-L2, torch's own bf16 execution 3.0e-2), so those asserts get 1.5x head-room under bf16 (TOLG)
+TOLG = TOLX * (1.5 if TOLX > 1 else 1.0)
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 
@@ -324,9 +327,9 @@ def test_step_sd15_vs_oracle():
     print({k: v for k, v in r.items() if isinstance(v, float)})
     assert abs(r["loss"] - r["loss_ref"]) < 1e-3 * TOLX * abs(r["loss_ref"])
     assert r["pred_rel"] < 3e-3 * TOLX
-    assert r["lora_grad_rel_l2"] < 3e-3 * TOLX and r["lora_grad_cos"] > 1 - 1e-5 * TOLX ** 2
-    assert r["row_grad_rel"] < 3e-3 * TOLX
-    assert abs(r["grad_norm"] - r["grad_norm_ref"]) < 2e-3 * TOLX * r["grad_norm_ref"]
+    assert r["lora_grad_rel_l2"] < 3e-3 * TOLG and r["lora_grad_cos"] > 1 - 1e-5 * TOLX ** 2
+    assert r["row_grad_rel"] < 3e-3 * TOLG
+    assert abs(r["grad_norm"] - r["grad_norm_ref"]) < 2e-3 * TOLG * r["grad_norm_ref"]
 
 
 def test_step_sd15_b8_vs_oracle_with_stated_tolerance_report():
@@ -355,9 +358,9 @@ def test_step_sd15_b8_vs_oracle_with_stated_tolerance_report():
         json.dump(rep, f, indent=1)
     assert abs(r["loss"] - r["loss_ref"]) < 1e-3 * TOLX * abs(r["loss_ref"])
     assert r["pred_rel"] < 3e-3 * TOLX
-    assert r["lora_grad_rel_l2"] < 3e-3 * TOLX and r["lora_grad_cos"] > 1 - 1e-5 * TOLX ** 2
-    assert r["row_grad_rel"] < 3e-3 * TOLX
-    assert abs(r["grad_norm"] - r["grad_norm_ref"]) < 2e-3 * TOLX * r["grad_norm_ref"]
+    assert r["lora_grad_rel_l2"] < 3e-3 * TOLG and r["lora_grad_cos"] > 1 - 1e-5 * TOLX ** 2
+    assert r["row_grad_rel"] < 3e-3 * TOLG
+    assert abs(r["grad_norm"] - r["grad_norm_ref"]) < 2e-3 * TOLG * r["grad_norm_ref"]
     for q in ("pred", "lora_grad", "row_grad"):
         assert r[f"tol_{q}_ours_vs_fp32"] >= r[f"tol_{q}_torch16_vs_fp32"] - 0.02, (q, rep)
 
@@ -375,8 +378,8 @@ def test_step_sd21_openclip_h_vs_oracle():
     print({k: v for k, v in r.items() if isinstance(v, float)})
     assert abs(r["loss"] - r["loss_ref"]) < 1e-3 * TOLX * abs(r["loss_ref"])
     assert r["pred_rel"] < 3e-3 * TOLX
-    assert r["lora_grad_rel_l2"] < 5e-3 * TOLX and r["lora_grad_cos"] > 1 - 1e-5 * TOLX ** 2
-    assert r["row_grad_rel"] < 5e-3 * TOLX
+    assert r["lora_grad_rel_l2"] < 5e-3 * TOLG and r["lora_grad_cos"] > 1 - 1e-5 * TOLX ** 2
+    assert r["row_grad_rel"] < 5e-3 * TOLG
 
 
 def test_config5_full_size_768px_step_properties():
